@@ -1,0 +1,244 @@
+#!/usr/bin/env python
+"""bench.py -- motion-windows/sec of the stage-2 sampling path (BASELINE.json metric).
+
+A "step" is one pass of the hot path over one batch: a full N_diffusion(=1000)-step conditional sampling of
+B (=256 per GPU) windows of T=120 frames (BASELINE config 2: "batch=256 T=120 1000-step sampling, random-init
+denoiser, synthetic head-pose cond, 1xB200").  `value` is device-resident throughput (inputs already in HBM),
+`e2e` goes through the host entry point (pinned host buffers, H2D + loop + D2H inside the timed region).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--diffusion-steps N]
+    torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_WINDOW_CALL = 2850.718e6      # algorithmic FLOPs per window per denoiser call (L=121)
+QKV_FLOP_PER_WINDOW_CALL = 380.633e6   # dominant kernel: fused QKV projection, per layer
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="windows per GPU")
+    ap.add_argument("--diffusion-steps", type=int, default=1000)
+    ap.add_argument("--engine", default=None, choices=[None, "tcgen05", "simt"])
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU-baseline sample budget")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synth_inputs(B, T, seed=1234):
+    import torch
+    from oracle.gen_golden import synth_x_start
+    from oracle import egoego_oracle as O
+    xs = synth_x_start(seed, B, T)
+    return xs, O.prep_head_condition_mask(xs.shape)
+
+
+def cpu_baseline(B_cpu, T, N, budget_s):
+    """The oracle port (torch CPU fp32 restatement of the reference sampler) on all host cores, bounded sample."""
+    import torch
+    from oracle import egoego_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    params = O.init_params(0)
+    sched = O.make_schedule(N)
+    xs, cm = synth_inputs(B_cpu, T)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(xs.shape, generator=g)
+    xc = O.make_x_cond(xs, cm, torch.randn(xs.shape, generator=g))
+    with torch.no_grad():
+        O.p_sample(params, sched, x, N - 1, xc, torch.randn(xs.shape, generator=g))   # warm-up
+        t0 = time.perf_counter(); n = 0
+        while True:
+            x = O.p_sample(params, sched, x, N - 1 - (n % N), xc, torch.randn(xs.shape, generator=g))
+            n += 1
+            el = time.perf_counter() - t0
+            if (el > budget_s and n >= 3) or n >= N:
+                break
+    per_step = el / n
+    return {"value": B_cpu / (per_step * N), "unit": "windows/s", "cores": cores, "kind": "port",
+            "sample": f"oracle p_sample, B={B_cpu}, T={T}, {n} of {N} steps timed ({el:.1f} s), scaled linearly to {N} steps",
+            "ms_per_denoiser_step": per_step * 1e3}
+
+
+def main():
+    a = parse()
+    os.environ.setdefault("TQDM_DISABLE", "1")
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    T, D, N, B = 120, 198, a.diffusion_steps, a.batch
+    cfg = {"workload": f"configs[1]: batch={B}/GPU T={T} {N}-step sampling, random-init denoiser (oracle.init_params seed 0), "
+                       "synthetic head-pose cond", "windows_per_gpu": B, "T": T, "diffusion_steps": N, "d_feats": D,
+           "parallelism": f"windows sharded over {world} GPU(s), one all-gather of finished windows" if world > 1 else "single GPU",
+           "l2": "per-step working set (bf16/fp32 activation planes for 256 windows, >1 GB) exceeds the 126 MB L2; no flush"}
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        cb = cpu_baseline(32, T, N, max(a.cpu_seconds, 10.0) * max(1, a.steps) / 3.0)
+        line = {"impl": "reference", "metric": "motion-windows/sec (T=120, 1000-step)", "value": cb["value"], "unit": "windows/s",
+                "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": B / cb["value"] * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": cfg, "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "note": "reference arm = CPU oracle port of the reference sampler on the host cores (the Python reference "
+                        "itself cannot travel to the GPU box); bounded sample scaled to the full workload"}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py needs a B200 (no CPU fallback in the product path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import egoego_release_b200 as E
+    from oracle import egoego_oracle as O
+    m = E.CondGaussianDiffusion(d_feats=D, d_model=512, n_dec_layers=4, n_head=4, d_k=256, d_v=256, max_timesteps=121,
+                                out_dim=D, timesteps=N, objective="pred_x0", loss_type="l1", max_batch=B, engine=a.engine)
+    m.load_state_dict(O.init_params(0), strict=False)
+    m = m.to(dev)
+    m.window_offset = rank * B                      # Philox streams keyed by GLOBAL window id
+    xs_h, cm_h = synth_inputs(B * world, T)
+    xs_h = xs_h[rank * B:(rank + 1) * B].contiguous().pin_memory()
+    cm_h = cm_h[rank * B:(rank + 1) * B].contiguous().pin_memory()
+    out_h = torch.empty(B, T, D).pin_memory()
+    xs, cm = xs_h.to(dev), cm_h.to(dev)
+    gathered = torch.empty(world * B, T, D, device=dev) if world > 1 else None
+    torch.manual_seed(1234)
+
+    def step_device():
+        y = m.sample(xs, cm)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, y)
+        return y
+
+    def step_host():
+        y = m.sample_host(xs_h, cm_h, out=out_h)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, y.to(dev, non_blocking=True))
+        return y
+
+    def timed(fn, k):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = m.launch_count()
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            dist.barrier()
+        return ms, m.launch_count() - l0
+
+    for _ in range(max(a.warmup, 3)):
+        step_device()
+    with ClockSampler(local) as cs:
+        ms, launches = timed(step_device, a.steps)
+    clocks = cs.summary()
+    step_host()                                          # warm the host path (staging buffers)
+    ms_h, _ = timed(step_host, a.steps)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk, pk_src = peaks()
+    ms_per_step = ms / a.steps
+    value = world * B / (ms_per_step / 1e3)
+    e2e = world * B / (ms_h / a.steps / 1e3)
+    path_tflops = value / world * N * FLOP_PER_WINDOW_CALL / 1e12          # per GPU
+    peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+    line = {
+        "metric": "motion-windows/sec (T=120, 1000-step)", "value": value, "unit": "windows/s", "n_gpus": world,
+        "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16x3-split (fp32 accumulate)" if (a.engine or E.diffusion.DEFAULT_ENGINE) == "tcgen05" else "f32",
+        "data": "synthetic", "config": dict(cfg, engine=a.engine or E.diffusion.DEFAULT_ENGINE),
+        "e2e": {"value": e2e, "unit": "windows/s", "h2d_bytes_per_step": 2 * B * T * D * 4, "d2h_bytes_per_step": B * T * D * 4},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": {"bound": "tensor", "achieved": path_tflops, "peak": peak, "unit": "TFLOP/s", "frac": path_tflops / peak,
+                     "traffic": None, "peak_source": pk_src + ", sustained bf16 (kernel timed inside a long step)",
+                     "scope": "whole sampling path (algorithmic FLOPs 2.8507 TFLOP per 1000-step window / wall time per GPU)"},
+    }
+    line["cpu_baseline"] = cpu_baseline(32, T, N, a.cpu_seconds)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

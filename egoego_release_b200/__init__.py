@@ -1,0 +1,15 @@
+"""egoego_release_b200 -- B200-native (sm_100a) implementation of EgoEgo's stage-2 conditional
+motion-diffusion sampling path behind the reference's own Python boundary.
+
+Public surface (mirrors egoego/model/transformer_cond_diffusion_model.py):
+    CondGaussianDiffusion, TransformerDiffusionModel, MotionDataStub, prep_head_condition_mask
+The numeric path lives in lib/libegoego_b200.so (C ABI: include/egoego_b200.h); importing this package
+never falls back to PyTorch math -- using it without the built library or without a B200 raises.
+"""
+from ._capi import EgoEgoError  # noqa: F401
+from .diffusion import CondGaussianDiffusion, TransformerDiffusionModel  # noqa: F401
+from .motion_data import MotionDataStub  # noqa: F401
+from .trainer_glue import prep_head_condition_mask, prep_padding_mask, full_body_gen_cond_head_pose_sliding_window  # noqa: F401
+
+__all__ = ["CondGaussianDiffusion", "TransformerDiffusionModel", "MotionDataStub", "EgoEgoError",
+           "prep_head_condition_mask", "prep_padding_mask", "full_body_gen_cond_head_pose_sliding_window"]

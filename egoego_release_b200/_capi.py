@@ -1,0 +1,73 @@
+"""ctypes binding of libegoego_b200.so (declarations mirror include/egoego_b200.h)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from .build import LIB_PATH
+
+EXPORTS = [
+    "egoego_last_error", "egoego_version", "egoego_create", "egoego_destroy", "egoego_set_tensor",
+    "egoego_make_cosine_schedule", "egoego_commit_weights", "egoego_denoiser_forward", "egoego_p_sample_step",
+    "egoego_sample", "egoego_sample_host", "egoego_set_skeleton", "egoego_postprocess", "egoego_fk_smpl",
+    "egoego_canonicalize_head", "egoego_launch_count",
+]
+
+ENGINE_TCGEN05, ENGINE_SIMT = 0, 1
+
+
+class Cfg(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "d_feats", "d_model", "n_head", "n_dec_layers", "d_k", "d_v", "max_timesteps", "timesteps",
+        "objective", "max_batch", "device", "engine")]
+
+
+class Rng(C.Structure):
+    _fields_ = [("tape", C.c_void_p), ("seed", C.c_uint64), ("window_offset", C.c_uint64)]
+
+
+class EgoEgoError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library.  There is no fallback: a missing library is a hard error."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EgoEgoError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  egoego_release_b200 has no CPU / PyTorch fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, u64 = C.c_void_p, C.c_int, C.c_int64, C.c_uint64
+    L.egoego_last_error.restype = C.c_char_p
+    L.egoego_version.restype = i32
+    L.egoego_create.argtypes = [C.POINTER(Cfg), C.POINTER(vp)]
+    L.egoego_destroy.argtypes = [vp]
+    L.egoego_set_tensor.argtypes = [vp, C.c_char_p, vp, i64, i32]
+    L.egoego_make_cosine_schedule.argtypes = [vp]
+    L.egoego_commit_weights.argtypes = [vp, vp]
+    L.egoego_denoiser_forward.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp]
+    L.egoego_p_sample_step.argtypes = [vp, vp, vp, vp, vp, C.POINTER(Rng), u64, vp, i32, vp, i32, i32, i32, vp, vp]
+    L.egoego_sample.argtypes = [vp, vp, vp, i32, i32, C.POINTER(Rng), vp, vp, i32, vp, vp]
+    L.egoego_sample_host.argtypes = [vp, vp, vp, i32, i32, C.POINTER(Rng), vp, vp]
+    L.egoego_set_skeleton.argtypes = [vp, vp, vp, vp, vp]
+    L.egoego_postprocess.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp]
+    L.egoego_fk_smpl.argtypes = [vp, vp, vp, i64, vp, vp, vp]
+    L.egoego_canonicalize_head.argtypes = [vp, vp, vp, i64, i32, i32, vp, vp, vp]
+    L.egoego_launch_count.argtypes = [vp]
+    L.egoego_launch_count.restype = i64
+    for name in EXPORTS:
+        if name not in ("egoego_last_error", "egoego_launch_count"):
+            getattr(L, name).restype = i32
+    _lib = L
+    return L
+
+
+def check(rc: int):
+    if rc != 0:
+        raise EgoEgoError(lib().egoego_last_error().decode())

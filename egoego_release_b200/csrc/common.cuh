@@ -1,0 +1,108 @@
+// Shared declarations for libegoego_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include <map>
+
+#include "../../include/egoego_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libegoego_b200 is written for sm_100a (Blackwell B200) only"
+#endif
+
+namespace egoego {
+
+constexpr int LP = 128;         // padded tokens per window: 1 time token + up to 120 frames + pad
+constexpr int NJ = 22;          // SMPL body joints
+constexpr int HEAD_IDX = 15;
+
+void set_error(const std::string& msg);
+
+#define EG_CHECK(cond, msg)                                                      \
+    do { if (!(cond)) { ::egoego::set_error(std::string(msg)); return 1; } } while (0)
+
+#define EG_CUDA(call)                                                            \
+    do { cudaError_t _e = (call);                                                \
+         if (_e != cudaSuccess) {                                                \
+             ::egoego::set_error(std::string(#call) + ": " + cudaGetErrorString(_e) + \
+                                 " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"); \
+             return 1; } } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// Which diffusion step a window is at.  Loop mode: t = t_start - *d_step (device counter advanced
+// once per step so one captured CUDA graph serves every step).  Step-API mode: explicit int64 array.
+// ---------------------------------------------------------------------------------------------
+struct TSrc {
+    const long long* t_arr;   // [B] or nullptr
+    const int*       d_step;  // device counter or nullptr
+    int              t_start;
+    __device__ __forceinline__ int get(int w) const {
+        if (t_arr) return (int)t_arr[w];
+        return t_start - (d_step ? *d_step : 0);
+    }
+};
+
+// Gaussian source: tape (explicit) or Philox4x32-10 + Box-Muller.
+struct NoiseSrc {
+    const float* tape;          // base of the tape (or of one explicit draw), nullptr => philox
+    long long    draw_stride;   // elements between consecutive draws in the tape
+    const int*   d_step;        // device step counter added to draw_static (nullable)
+    int          draw_static;
+    unsigned long long seed;
+    unsigned long long window_offset;
+    __device__ __forceinline__ int draw() const { return draw_static + (d_step ? *d_step : 0); }
+};
+
+__device__ __forceinline__ uint32_t mulhilo32(uint32_t a, uint32_t b, uint32_t* hi) {
+    unsigned long long p = (unsigned long long)a * b;
+    *hi = (uint32_t)(p >> 32);
+    return (uint32_t)p;
+}
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0, hi1;
+        uint32_t lo0 = mulhilo32(M0, ctr.x, &hi0);
+        uint32_t lo1 = mulhilo32(M1, ctr.z, &hi1);
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += W0; key.y += W1;
+    }
+    return ctr;
+}
+
+// 4 standard normals for (window, draw, quad index) -- quad = element_index / 4 within the window.
+__device__ __forceinline__ float4 philox_normal4(unsigned long long seed, unsigned long long window,
+                                                 uint32_t draw, uint32_t quad) {
+    uint4 r = philox4x32_10(make_uint4(quad, draw, (uint32_t)window, (uint32_t)(window >> 32)),
+                            make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const float k = 2.3283064365386963e-10f;  // 2^-32
+    float u0 = ((float)r.x + 0.5f) * k, u1 = ((float)r.y + 0.5f) * k;
+    float u2 = ((float)r.z + 0.5f) * k, u3 = ((float)r.w + 0.5f) * k;
+    u0 = fminf(u0, 0.99999994f); u2 = fminf(u2, 0.99999994f);
+    float r0 = sqrtf(-2.0f * logf(u0)), r1 = sqrtf(-2.0f * logf(u2));
+    float s0, c0, s1, c1;
+    sincospif(2.0f * u1, &s0, &c0);
+    sincospif(2.0f * u3, &s1, &c1);
+    return make_float4(r0 * c0, r0 * s0, r1 * c1, r1 * s1);
+}
+
+// One normal for flat element e of window w (elements are grouped in quads).
+__device__ __forceinline__ float noise_at(const NoiseSrc& ns, int draw, int w, long long elems_per_window, int e) {
+    if (ns.tape) return ns.tape[(long long)draw * ns.draw_stride + (long long)w * elems_per_window + e];
+    float4 n = philox_normal4(ns.seed, ns.window_offset + (unsigned long long)w, (uint32_t)draw, (uint32_t)(e >> 2));
+    int r = e & 3;
+    return r == 0 ? n.x : (r == 1 ? n.y : (r == 2 ? n.z : n.w));
+}
+
+// bf16 hi/lo split of an fp32 value: v ~= hi + lo with |v - hi - lo| <= 2^-17 |v|.
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+    hi = __float2bfloat16_rn(v);
+    lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+}  // namespace egoego

@@ -1,0 +1,643 @@
+// libegoego_b200: C-ABI + orchestration of the stage-2 sampling path (see include/egoego_b200.h).
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+
+#include "common.cuh"
+#include "kernels_simt.cuh"
+#include "postprocess.cuh"
+#include "engine_tc.cuh"
+
+namespace egoego {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+
+struct DevBuf {
+    void* p = nullptr; size_t bytes = 0;
+    int alloc(size_t n) {
+        release();
+        if (n == 0) return 0;
+        EG_CUDA(cudaMalloc(&p, n));
+        bytes = n;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct LayerW {
+    DevBuf wqkv, bqkv;       // fused [3*H*dk, d], [3*H*dk]
+    DevBuf fc_w, fc_b, ln1_g, ln1_b;
+    DevBuf w1, b1, w2, b2, ln2_g, ln2_b;
+};
+
+}  // namespace egoego
+
+using namespace egoego;
+
+struct egoego_ctx {
+    egoego_cfg cfg{};
+    int D = 0, d = 0, H = 0, dk = 0, NL = 0, N = 0, Tmax = 0;
+    int kin_pad = 0;                       // 2*D rounded up to 16 (SIMT start GEMM K)
+    std::map<std::string, std::vector<float>> staged;   // host copies until commit
+    bool committed = false;
+
+    // packed fp32 weights (both engines)
+    DevBuf start_w, start_b, pos, out_w, out_b, t_w1, t_b1, t_w2, t_b2, temb;
+    std::vector<LayerW> layers;
+    DevBuf coef1, coef2, logvar, sqrt_recip, sqrt_recipm1;
+    bool have_sched = false;
+
+    // workspace (sized for cfg.max_batch windows)
+    DevBuf Ain, Hbuf, Ybuf, QKV, Obuf, Fbuf, model_out, x_cur, x_cond, d_step, t_tmp;
+    DevBuf h_xstart, h_mask, h_out, h_tape;   // device staging of the *_host entry point
+
+    Skeleton sk{}; bool have_sk = false;
+    cudaStream_t own_stream = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+    cudaGraphExec_t step_graph = nullptr; int graph_B = -1, graph_T = -1; const void* graph_key[4] = {nullptr};
+    bool use_graph = true;
+    int64_t launches = 0;
+    std::unique_ptr<TcEngine> tc;
+};
+
+namespace egoego {
+
+static inline dim3 grid1d(long long n, int bs) { return dim3((unsigned)((n + bs - 1) / bs)); }
+
+// ---- SIMT engine: one denoiser call.  Expects Ain staged; writes model_out[B,T,D]. ---------------
+static int denoiser_simt(egoego_ctx* c, int B, int T, TSrc ts, const float* pmask, cudaStream_t s) {
+    const int M = B * LP, d = c->d, H = c->H, dk = c->dk;
+    const int L = T + 1;
+    {
+        EpiStart e{c->Hbuf.as<float>(), d, c->start_b.as<float>(), nullptr, c->pos.as<float>(), c->temb.as<float>(), ts, T};
+        sgemm_tn_kernel<<<dim3(d / 128, M / 128), 256, 0, s>>>(c->Ain.as<float>(), c->kin_pad, c->start_w.as<float>(),
+                                                              c->kin_pad, d, c->kin_pad, e);
+        c->launches++;
+    }
+    for (int l = 0; l < c->NL; ++l) {
+        LayerW& w = c->layers[l];
+        const int nqkv = 3 * H * dk;
+        EpiBiasScale eq{c->QKV.as<float>(), nqkv, w.bqkv.as<float>(), H * dk, 1.0f / sqrtf((float)dk)};
+        sgemm_tn_kernel<<<dim3(nqkv / 128, M / 128), 256, 0, s>>>(c->Hbuf.as<float>(), d, w.wqkv.as<float>(), d, nqkv, d, eq);
+        attention_simt_kernel<<<B * H, 256, ATT_SIMT_SMEM, s>>>(c->QKV.as<float>(), nqkv, c->Obuf.as<float>(), H * dk, H, L);
+        EpiBiasResid ef{c->Ybuf.as<float>(), d, w.fc_b.as<float>(), c->Hbuf.as<float>()};
+        sgemm_tn_kernel<<<dim3(d / 128, M / 128), 256, 0, s>>>(c->Obuf.as<float>(), H * dk, w.fc_w.as<float>(), H * dk, d, H * dk, ef);
+        layernorm512_kernel<<<M / 8, 256, 0, s>>>(c->Ybuf.as<float>(), c->Hbuf.as<float>(), nullptr, nullptr,
+                                                  w.ln1_g.as<float>(), w.ln1_b.as<float>(), pmask, T, M);
+        EpiBiasRelu e1{c->Fbuf.as<float>(), d, w.b1.as<float>()};
+        sgemm_tn_kernel<<<dim3(d / 128, M / 128), 256, 0, s>>>(c->Hbuf.as<float>(), d, w.w1.as<float>(), d, d, d, e1);
+        EpiBiasResid e2{c->Ybuf.as<float>(), d, w.b2.as<float>(), c->Hbuf.as<float>()};
+        sgemm_tn_kernel<<<dim3(d / 128, M / 128), 256, 0, s>>>(c->Fbuf.as<float>(), d, w.w2.as<float>(), d, d, d, e2);
+        layernorm512_kernel<<<M / 8, 256, 0, s>>>(c->Ybuf.as<float>(), c->Hbuf.as<float>(), nullptr, nullptr,
+                                                  w.ln2_g.as<float>(), w.ln2_b.as<float>(), pmask, T, M);
+        c->launches += 7;
+    }
+    {
+        EpiOut eo{c->model_out.as<float>(), c->D, c->out_b.as<float>(), T};
+        sgemm_tn_kernel<<<dim3((c->D + 127) / 128, M / 128), 256, 0, s>>>(c->Hbuf.as<float>(), d, c->out_w.as<float>(), d, c->D, d, eo);
+        c->launches++;
+    }
+    EG_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int run_denoiser(egoego_ctx* c, int B, int T, TSrc ts, const float* pmask, cudaStream_t s) {
+    if (c->cfg.engine == EGOEGO_ENGINE_SIMT) return denoiser_simt(c, B, T, ts, pmask, s);
+    int64_t n = 0;
+    int rc = c->tc->denoiser(B, T, ts, pmask, c->model_out.as<float>(), s, &n);
+    c->launches += n;
+    return rc;
+}
+
+// Stage the GEMM input (x half and/or x_cond half) of the engine from compact [B,T,*] rows.
+static int stage_input(egoego_ctx* c, const float* src, int src_ld, int src_col0, bool cond_half, int B, int T, cudaStream_t s) {
+    const long long tot = (long long)B * T * c->D;
+    if (c->cfg.engine == EGOEGO_ENGINE_SIMT) {
+        stage_rows_f32_kernel<<<grid1d(tot, 256), 256, 0, s>>>(c->Ain.as<float>(), c->kin_pad, cond_half ? c->D : 0,
+                                                              src, src_ld, src_col0, c->D, B, T);
+        c->launches++;
+        EG_CUDA(cudaGetLastError());
+        return 0;
+    }
+    int64_t n = 0;
+    int rc = c->tc->stage(src, src_ld, src_col0, cond_half, B, T, s, &n);
+    c->launches += n;
+    return rc;
+}
+
+// After the x_cond half has been staged: engine-specific per-window constant work (tensor engine
+// folds the x_cond contribution of start_conv + bias + positional rows into a base tensor).
+static int prepare_cond(egoego_ctx* c, int B, int T, cudaStream_t s) {
+    if (c->cfg.engine == EGOEGO_ENGINE_SIMT) return 0;
+    int64_t n = 0;
+    int rc = c->tc->prepare_cond(B, T, s, &n);
+    c->launches += n;
+    return rc;
+}
+
+static int clear_staging(egoego_ctx* c, int B, cudaStream_t s) {
+    if (c->cfg.engine == EGOEGO_ENGINE_SIMT) {
+        EG_CUDA(cudaMemsetAsync(c->Ain.p, 0, (size_t)B * LP * c->kin_pad * sizeof(float), s));
+        return 0;
+    }
+    return c->tc->clear_staging(B, s);
+}
+
+static void fill_ddpm(egoego_ctx* c, DdpmArgs& a, const float* x, float* x_out, TSrc ts, NoiseSrc ns, int clip,
+                      const float* inpaint, int inpaint_len, int B, int T, bool stage_next) {
+    a.model_out = c->model_out.as<float>(); a.x = x; a.x_out = x_out;
+    a.coef1 = c->coef1.as<float>(); a.coef2 = c->coef2.as<float>(); a.logvar = c->logvar.as<float>();
+    a.sqrt_recip = c->sqrt_recip.as<float>(); a.sqrt_recipm1 = c->sqrt_recipm1.as<float>();
+    a.objective = c->cfg.objective; a.clip = clip; a.inpaint = inpaint; a.inpaint_len = inpaint_len;
+    a.stage_f32 = nullptr; a.stage_ld = 0; a.stage_hi = nullptr; a.stage_lo = nullptr; a.stage_ld16 = 0;
+    if (stage_next) {
+        if (c->cfg.engine == EGOEGO_ENGINE_SIMT) { a.stage_f32 = c->Ain.as<float>(); a.stage_ld = c->kin_pad; }
+        else c->tc->stage_targets(&a.stage_hi, &a.stage_lo, &a.stage_ld16);
+    }
+    a.ts = ts; a.ns = ns; a.B = B; a.T = T; a.D = c->D;
+}
+
+static int check_ready(egoego_ctx* c, int B, int T) {
+    EG_CHECK(c != nullptr, "null handle");
+    EG_CHECK(c->committed, "egoego_commit_weights has not been called");
+    EG_CHECK(B >= 1, "B must be >= 1");
+    EG_CHECK(T >= 1 && T <= c->Tmax, "T out of range (1..max_timesteps-1)");
+    return 0;
+}
+
+}  // namespace egoego
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+const char* egoego_last_error(void) { return g_err.c_str(); }
+int egoego_version(void) { return 100; }
+
+int egoego_create(const egoego_cfg* cfg, egoego_handle* out) {
+    EG_CHECK(cfg && out, "null argument");
+    EG_CHECK(cfg->d_model == 512, "only d_model = 512 is supported (LayerNorm / tile shapes are specialised)");
+    EG_CHECK(cfg->d_k == 256 && cfg->d_v == 256, "only d_k = d_v = 256 is supported");
+    EG_CHECK(cfg->n_head >= 1 && cfg->n_head * cfg->d_k % 128 == 0, "n_head * d_k must be a multiple of 128");
+    EG_CHECK(cfg->max_timesteps >= 2 && cfg->max_timesteps <= LP, "max_timesteps must be in [2,128]");
+    EG_CHECK(cfg->d_feats >= 1 && cfg->d_feats <= 256 && cfg->d_feats % 2 == 0, "d_feats must be even and <= 256");
+    EG_CHECK(cfg->timesteps >= 1, "timesteps must be >= 1");
+    EG_CHECK(cfg->objective == 0 || cfg->objective == 1, "objective must be 0 (pred_noise) or 1 (pred_x0)");
+    EG_CHECK(cfg->max_batch >= 1, "max_batch must be >= 1");
+    EG_CHECK(cfg->engine == EGOEGO_ENGINE_TCGEN05 || cfg->engine == EGOEGO_ENGINE_SIMT, "unknown engine");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    EG_CHECK(e == cudaSuccess && ndev > 0, "no CUDA device: libegoego_b200 has no CPU fallback");
+    EG_CHECK(cfg->device >= 0 && cfg->device < ndev, "bad device ordinal");
+    cudaDeviceProp prop;
+    EG_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+    EG_CHECK(prop.major == 10, "libegoego_b200 is built for sm_100a (B200) only; device is sm_" +
+                                   std::to_string(prop.major) + std::to_string(prop.minor));
+    EG_CUDA(cudaSetDevice(cfg->device));
+    auto* c = new egoego_ctx();
+    c->cfg = *cfg;
+    c->D = cfg->d_feats; c->d = cfg->d_model; c->H = cfg->n_head; c->dk = cfg->d_k; c->NL = cfg->n_dec_layers;
+    c->N = cfg->timesteps; c->Tmax = cfg->max_timesteps - 1;
+    c->kin_pad = ((2 * c->D + 15) / 16) * 16;
+    c->layers.resize(c->NL);
+    const char* g = getenv("EGOEGO_GRAPH");
+    c->use_graph = !(g && g[0] == '0');
+    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming) != cudaSuccess) {
+        set_error("stream/event creation failed");
+        delete c;
+        return 1;
+    }
+    EG_CUDA(cudaFuncSetAttribute(attention_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SIMT_SMEM));
+    *out = c;
+    return 0;
+}
+
+int egoego_destroy(egoego_handle c) {
+    if (!c) return 0;
+    cudaSetDevice(c->cfg.device);
+    cudaDeviceSynchronize();
+    if (c->step_graph) cudaGraphExecDestroy(c->step_graph);
+    DevBuf* bufs[] = {&c->start_w, &c->start_b, &c->pos, &c->out_w, &c->out_b, &c->t_w1, &c->t_b1, &c->t_w2, &c->t_b2,
+                      &c->temb, &c->coef1, &c->coef2, &c->logvar, &c->sqrt_recip, &c->sqrt_recipm1, &c->Ain, &c->Hbuf,
+                      &c->Ybuf, &c->QKV, &c->Obuf, &c->Fbuf, &c->model_out, &c->x_cur, &c->x_cond, &c->d_step, &c->t_tmp,
+                      &c->h_xstart, &c->h_mask, &c->h_out, &c->h_tape};
+    for (DevBuf* b : bufs) b->release();
+    for (auto& l : c->layers) {
+        DevBuf* lb[] = {&l.wqkv, &l.bqkv, &l.fc_w, &l.fc_b, &l.ln1_g, &l.ln1_b, &l.w1, &l.b1, &l.w2, &l.b2, &l.ln2_g, &l.ln2_b};
+        for (DevBuf* b : lb) b->release();
+    }
+    c->tc.reset();
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    if (c->ev_in) cudaEventDestroy(c->ev_in);
+    if (c->ev_out) cudaEventDestroy(c->ev_out);
+    delete c;
+    return 0;
+}
+
+int egoego_set_tensor(egoego_handle c, const char* name_in, const float* data, int64_t numel, int on_device) {
+    EG_CHECK(c && name_in && data, "null argument");
+    EG_CHECK(numel > 0, "numel must be > 0");
+    std::string name(name_in);
+    for (const char* pre : {"ema_model.", "model.", "module."})
+        if (name.rfind(pre, 0) == 0) name = name.substr(strlen(pre));
+    // expected sizes
+    const int D = c->D, d = c->d, H = c->H, dk = c->dk;
+    std::map<std::string, int64_t> expect = {
+        {"denoise_fn.motion_transformer.start_conv.weight", (int64_t)d * 2 * D},
+        {"denoise_fn.motion_transformer.start_conv.bias", d},
+        {"denoise_fn.motion_transformer.position_vec.weight", (int64_t)(c->cfg.max_timesteps + 1) * d},
+        {"denoise_fn.linear_out.weight", (int64_t)D * d}, {"denoise_fn.linear_out.bias", D},
+        {"denoise_fn.time_mlp.1.weight", 256 * 64}, {"denoise_fn.time_mlp.1.bias", 256},
+        {"denoise_fn.time_mlp.3.weight", (int64_t)d * 256}, {"denoise_fn.time_mlp.3.bias", d},
+        {"posterior_mean_coef1", c->N}, {"posterior_mean_coef2", c->N}, {"posterior_log_variance_clipped", c->N},
+        {"sqrt_recip_alphas_cumprod", c->N}, {"sqrt_recipm1_alphas_cumprod", c->N}};
+    for (int l = 0; l < c->NL; ++l) {
+        std::string a = "denoise_fn.motion_transformer.layer_stack." + std::to_string(l) + ".self_attn.";
+        std::string f = "denoise_fn.motion_transformer.layer_stack." + std::to_string(l) + ".pos_ffn.";
+        for (const char* nm : {"w_q", "w_k", "w_v"}) { expect[a + nm + ".weight"] = (int64_t)H * dk * d; expect[a + nm + ".bias"] = H * dk; }
+        expect[a + "fc.weight"] = (int64_t)d * H * dk; expect[a + "fc.bias"] = d;
+        expect[a + "layer_norm.weight"] = d; expect[a + "layer_norm.bias"] = d;
+        expect[f + "w_1.weight"] = (int64_t)d * d; expect[f + "w_1.bias"] = d;
+        expect[f + "w_2.weight"] = (int64_t)d * d; expect[f + "w_2.bias"] = d;
+        expect[f + "layer_norm.weight"] = d; expect[f + "layer_norm.bias"] = d;
+    }
+    auto it = expect.find(name);
+    if (it == expect.end()) return 0;   // strict=False: ignore unknown keys
+    EG_CHECK(it->second == numel, "tensor '" + name + "': expected " + std::to_string(it->second) +
+                                      " elements, got " + std::to_string(numel));
+    std::vector<float>& v = c->staged[name];
+    v.resize(numel);
+    if (on_device) {
+        EG_CUDA(cudaSetDevice(c->cfg.device));
+        EG_CUDA(cudaMemcpy(v.data(), data, numel * sizeof(float), cudaMemcpyDeviceToHost));
+    } else {
+        memcpy(v.data(), data, numel * sizeof(float));
+    }
+    c->committed = false;
+    return 0;
+}
+
+int egoego_make_cosine_schedule(egoego_handle c) {
+    EG_CHECK(c, "null handle");
+    // transformer_cond_diffusion_model.py:47-57,173-214 in double precision, cast to fp32 at the end
+    const int N = c->N;
+    std::vector<double> ac(N + 1), betas(N), acp(N), cum(N);
+    const double s = 0.008;
+    for (int i = 0; i <= N; ++i) {
+        double x = (double)i * ((double)N / (double)N);   // linspace(0, N, N+1)
+        double v = cos(((x / N) + s) / (1 + s) * M_PI * 0.5);
+        ac[i] = v * v;
+    }
+    for (int i = N; i >= 0; --i) ac[i] /= ac[0];
+    for (int i = 0; i < N; ++i) { double b = 1 - ac[i + 1] / ac[i]; betas[i] = b < 0 ? 0 : (b > 0.999 ? 0.999 : b); }
+    double run = 1.0;
+    for (int i = 0; i < N; ++i) { run *= (1.0 - betas[i]); cum[i] = run; acp[i] = i == 0 ? 1.0 : cum[i - 1]; }
+    std::vector<float> c1(N), c2(N), lv(N), sr(N), srm(N);
+    for (int i = 0; i < N; ++i) {
+        double pv = betas[i] * (1.0 - acp[i]) / (1.0 - cum[i]);
+        lv[i] = (float)log(pv < 1e-20 ? 1e-20 : pv);
+        c1[i] = (float)(betas[i] * sqrt(acp[i]) / (1.0 - cum[i]));
+        c2[i] = (float)((1.0 - acp[i]) * sqrt(1.0 - betas[i]) / (1.0 - cum[i]));
+        sr[i] = (float)sqrt(1.0 / cum[i]);
+        srm[i] = (float)sqrt(1.0 / cum[i] - 1);
+    }
+    if (egoego_set_tensor(c, "posterior_mean_coef1", c1.data(), N, 0)) return 1;
+    if (egoego_set_tensor(c, "posterior_mean_coef2", c2.data(), N, 0)) return 1;
+    if (egoego_set_tensor(c, "posterior_log_variance_clipped", lv.data(), N, 0)) return 1;
+    if (egoego_set_tensor(c, "sqrt_recip_alphas_cumprod", sr.data(), N, 0)) return 1;
+    if (egoego_set_tensor(c, "sqrt_recipm1_alphas_cumprod", srm.data(), N, 0)) return 1;
+    return 0;
+}
+
+static int upload(DevBuf& b, const std::vector<float>& v) {
+    if (b.alloc(v.size() * sizeof(float))) return 1;
+    EG_CUDA(cudaMemcpy(b.p, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int egoego_commit_weights(egoego_handle c, void* stream_v) {
+    EG_CHECK(c, "null handle");
+    EG_CUDA(cudaSetDevice(c->cfg.device));
+    cudaStream_t s = (cudaStream_t)stream_v;
+    auto need = [&](const std::string& k) -> const std::vector<float>* {
+        auto it = c->staged.find(k);
+        return it == c->staged.end() ? nullptr : &it->second;
+    };
+#define NEED(var, key) const std::vector<float>* var = need(key); EG_CHECK(var, std::string("missing tensor: ") + (key))
+    const int D = c->D, d = c->d, H = c->H, dk = c->dk;
+    const std::string pre = "denoise_fn.motion_transformer.";
+    NEED(sw, pre + "start_conv.weight"); NEED(sb, pre + "start_conv.bias"); NEED(pv, pre + "position_vec.weight");
+    NEED(ow, "denoise_fn.linear_out.weight"); NEED(ob, "denoise_fn.linear_out.bias");
+    NEED(tw1, "denoise_fn.time_mlp.1.weight"); NEED(tb1, "denoise_fn.time_mlp.1.bias");
+    NEED(tw2, "denoise_fn.time_mlp.3.weight"); NEED(tb2, "denoise_fn.time_mlp.3.bias");
+    NEED(c1, "posterior_mean_coef1"); NEED(c2, "posterior_mean_coef2"); NEED(lv, "posterior_log_variance_clipped");
+    if (c->cfg.objective == 0) { EG_CHECK(need("sqrt_recip_alphas_cumprod") && need("sqrt_recipm1_alphas_cumprod"),
+                                          "pred_noise objective needs sqrt_recip(m1)_alphas_cumprod"); }
+    // start_conv weight padded to kin_pad columns
+    std::vector<float> swp((size_t)d * c->kin_pad, 0.f);
+    for (int o = 0; o < d; ++o) memcpy(&swp[(size_t)o * c->kin_pad], &(*sw)[(size_t)o * 2 * D], 2 * D * sizeof(float));
+    if (upload(c->start_w, swp) || upload(c->start_b, *sb) || upload(c->pos, *pv) || upload(c->out_w, *ow) ||
+        upload(c->out_b, *ob) || upload(c->t_w1, *tw1) || upload(c->t_b1, *tb1) || upload(c->t_w2, *tw2) ||
+        upload(c->t_b2, *tb2) || upload(c->coef1, *c1) || upload(c->coef2, *c2) || upload(c->logvar, *lv)) return 1;
+    {
+        std::vector<float> ones(c->N, 1.f), zeros(c->N, 0.f);
+        const std::vector<float>* sr = need("sqrt_recip_alphas_cumprod");
+        const std::vector<float>* srm = need("sqrt_recipm1_alphas_cumprod");
+        if (upload(c->sqrt_recip, sr ? *sr : ones) || upload(c->sqrt_recipm1, srm ? *srm : zeros)) return 1;
+    }
+    std::vector<std::vector<float>> host_layers;   // for the tensor engine packer
+    for (int l = 0; l < c->NL; ++l) {
+        std::string a = pre + "layer_stack." + std::to_string(l) + ".self_attn.";
+        std::string f = pre + "layer_stack." + std::to_string(l) + ".pos_ffn.";
+        NEED(wq, a + "w_q.weight"); NEED(wk, a + "w_k.weight"); NEED(wv, a + "w_v.weight");
+        NEED(bq, a + "w_q.bias"); NEED(bk, a + "w_k.bias"); NEED(bv, a + "w_v.bias");
+        NEED(fw, a + "fc.weight"); NEED(fb, a + "fc.bias"); NEED(g1, a + "layer_norm.weight"); NEED(be1, a + "layer_norm.bias");
+        NEED(w1, f + "w_1.weight"); NEED(b1, f + "w_1.bias"); NEED(w2, f + "w_2.weight"); NEED(b2, f + "w_2.bias");
+        NEED(g2, f + "layer_norm.weight"); NEED(be2, f + "layer_norm.bias");
+        std::vector<float> wqkv; wqkv.reserve((size_t)3 * H * dk * d);
+        wqkv.insert(wqkv.end(), wq->begin(), wq->end()); wqkv.insert(wqkv.end(), wk->begin(), wk->end());
+        wqkv.insert(wqkv.end(), wv->begin(), wv->end());
+        std::vector<float> bqkv; bqkv.insert(bqkv.end(), bq->begin(), bq->end());
+        bqkv.insert(bqkv.end(), bk->begin(), bk->end()); bqkv.insert(bqkv.end(), bv->begin(), bv->end());
+        LayerW& L = c->layers[l];
+        if (upload(L.wqkv, wqkv) || upload(L.bqkv, bqkv) || upload(L.fc_w, *fw) || upload(L.fc_b, *fb) ||
+            upload(L.ln1_g, *g1) || upload(L.ln1_b, *be1) || upload(L.w1, *w1) || upload(L.b1, *b1) ||
+            upload(L.w2, *w2) || upload(L.b2, *b2) || upload(L.ln2_g, *g2) || upload(L.ln2_b, *be2)) return 1;
+    }
+#undef NEED
+    // timestep-embedding table for every t in [0, N)
+    if (c->temb.alloc((size_t)c->N * d * sizeof(float))) return 1;
+    time_table_kernel<<<c->N, 256, 0, s>>>(c->t_w1.as<float>(), c->t_b1.as<float>(), c->t_w2.as<float>(),
+                                           c->t_b2.as<float>(), c->temb.as<float>(), d);
+    c->launches++;
+    EG_CUDA(cudaGetLastError());
+    // workspace
+    const size_t MB = (size_t)c->cfg.max_batch, M = MB * LP, xe = MB * c->Tmax * D;
+    if (c->model_out.alloc(xe * 4) || c->x_cur.alloc(xe * 4) || c->x_cond.alloc(xe * 4) || c->d_step.alloc(64) ||
+        c->t_tmp.alloc(MB * sizeof(long long))) return 1;
+    if (c->cfg.engine == EGOEGO_ENGINE_SIMT) {
+        if (c->Ain.alloc(M * c->kin_pad * 4) || c->Hbuf.alloc(M * d * 4) || c->Ybuf.alloc(M * d * 4) ||
+            c->QKV.alloc(M * 3 * H * dk * 4) || c->Obuf.alloc(M * H * dk * 4) || c->Fbuf.alloc(M * d * 4)) return 1;
+    } else {
+        c->tc.reset(new TcEngine());
+        TcWeights tw;
+        tw.D = D; tw.d = d; tw.H = H; tw.dk = dk; tw.NL = c->NL; tw.N = c->N; tw.Tmax = c->Tmax; tw.max_batch = c->cfg.max_batch;
+        tw.start_w = sw->data(); tw.start_b = c->start_b.as<float>(); tw.pos = c->pos.as<float>(); tw.temb = c->temb.as<float>();
+        tw.out_w = ow->data(); tw.out_b = c->out_b.as<float>();
+        for (int l = 0; l < c->NL; ++l) {
+            std::string a = pre + "layer_stack." + std::to_string(l) + ".self_attn.";
+            std::string f = pre + "layer_stack." + std::to_string(l) + ".pos_ffn.";
+            TcLayerW lw;
+            lw.wq = c->staged[a + "w_q.weight"].data(); lw.wk = c->staged[a + "w_k.weight"].data();
+            lw.wv = c->staged[a + "w_v.weight"].data(); lw.fc = c->staged[a + "fc.weight"].data();
+            lw.w1 = c->staged[f + "w_1.weight"].data(); lw.w2 = c->staged[f + "w_2.weight"].data();
+            LayerW& L = c->layers[l];
+            lw.bqkv = L.bqkv.as<float>(); lw.fc_b = L.fc_b.as<float>(); lw.b1 = L.b1.as<float>(); lw.b2 = L.b2.as<float>();
+            lw.ln1_g = L.ln1_g.as<float>(); lw.ln1_b = L.ln1_b.as<float>(); lw.ln2_g = L.ln2_g.as<float>(); lw.ln2_b = L.ln2_b.as<float>();
+            tw.layers.push_back(lw);
+        }
+        if (c->tc->init(tw, s)) return 1;
+    }
+    EG_CUDA(cudaStreamSynchronize(s));
+    if (c->step_graph) { cudaGraphExecDestroy(c->step_graph); c->step_graph = nullptr; c->graph_B = -1; }
+    c->committed = true;
+    return 0;
+}
+
+int egoego_denoiser_forward(egoego_handle c, const float* x_all, const int64_t* t_dev, const float* pmask,
+                            int B, int T, float* out, void* stream_v) {
+    if (check_ready(c, B, T)) return 1;
+    EG_CHECK(x_all && t_dev && out, "null argument");
+    EG_CUDA(cudaSetDevice(c->cfg.device));
+    cudaStream_t s = (cudaStream_t)stream_v;
+    for (int b0 = 0; b0 < B; b0 += c->cfg.max_batch) {
+        int Bc = std::min(c->cfg.max_batch, B - b0);
+        const float* xa = x_all + (size_t)b0 * T * 2 * c->D;
+        if (clear_staging(c, Bc, s)) return 1;
+        if (stage_input(c, xa, 2 * c->D, c->D, true, Bc, T, s)) return 1;
+        if (prepare_cond(c, Bc, T, s)) return 1;
+        if (stage_input(c, xa, 2 * c->D, 0, false, Bc, T, s)) return 1;
+        TSrc ts{reinterpret_cast<const long long*>(t_dev) + b0, nullptr, 0};
+        if (run_denoiser(c, Bc, T, ts, pmask ? pmask + (size_t)b0 * (T + 1) : nullptr, s)) return 1;
+        EG_CUDA(cudaMemcpyAsync(out + (size_t)b0 * T * c->D, c->model_out.p, (size_t)Bc * T * c->D * 4, cudaMemcpyDeviceToDevice, s));
+    }
+    return 0;
+}
+
+int egoego_p_sample_step(egoego_handle c, const float* x, const int64_t* t_dev, const float* x_cond,
+                         const float* noise, const egoego_rng* rng, uint64_t draw_index, const float* pmask,
+                         int clip, const float* inpaint, int inpaint_len, int B, int T, float* x_out, void* stream_v) {
+    if (check_ready(c, B, T)) return 1;
+    EG_CHECK(x && t_dev && x_cond && x_out, "null argument");
+    EG_CHECK(noise || rng, "either an explicit noise tensor or an rng must be given");
+    EG_CHECK(inpaint_len >= 0 && inpaint_len <= T, "inpaint_len out of range");
+    EG_CUDA(cudaSetDevice(c->cfg.device));
+    cudaStream_t s = (cudaStream_t)stream_v;
+    const int D = c->D;
+    for (int b0 = 0; b0 < B; b0 += c->cfg.max_batch) {
+        int Bc = std::min(c->cfg.max_batch, B - b0);
+        size_t off = (size_t)b0 * T * D;
+        if (clear_staging(c, Bc, s)) return 1;
+        if (stage_input(c, x_cond + off, D, 0, true, Bc, T, s)) return 1;
+        if (prepare_cond(c, Bc, T, s)) return 1;
+        if (stage_input(c, x + off, D, 0, false, Bc, T, s)) return 1;
+        TSrc ts{reinterpret_cast<const long long*>(t_dev) + b0, nullptr, 0};
+        if (run_denoiser(c, Bc, T, ts, pmask ? pmask + (size_t)b0 * (T + 1) : nullptr, s)) return 1;
+        NoiseSrc ns{};
+        if (noise) { ns.tape = noise + off; ns.draw_stride = 0; ns.draw_static = 0; }
+        else { ns.tape = nullptr; ns.seed = rng->seed; ns.window_offset = rng->window_offset + b0; ns.draw_static = (int)draw_index; }
+        DdpmArgs a;
+        fill_ddpm(c, a, x + off, x_out + off, ts, ns, clip, inpaint ? inpaint + (size_t)b0 * inpaint_len * D : nullptr,
+                  inpaint_len, Bc, T, false);
+        long long quads = ((long long)T * D + 3) / 4 * Bc;
+        ddpm_update_kernel<<<grid1d(quads, 256), 256, 0, s>>>(a);
+        c->launches++;
+        EG_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+// One chunk (Bc <= max_batch) of the sampling loop on stream `s` (must be capturable, i.e. not legacy).
+static int sample_chunk(egoego_ctx* c, const float* x_start, const float* cond_mask, int Bc, int T, NoiseSrc ns_base,
+                        const float* x_init, const float* inpaint, int inpaint_len, float* out, cudaStream_t s) {
+    const int D = c->D, N = c->N;
+    const long long quads = ((long long)T * D + 3) / 4 * Bc;
+    float* xc = c->x_cur.as<float>();
+    float* xcond = c->x_cond.as<float>();
+    int* d_step = c->d_step.as<int>();
+    init_sample_kernel<<<grid1d(quads, 256), 256, 0, s>>>(xc, xcond, x_init, x_start, cond_mask, ns_base, Bc, T, D);
+    c->launches++;
+    EG_CUDA(cudaGetLastError());
+    if (clear_staging(c, Bc, s)) return 1;
+    if (stage_input(c, xcond, D, 0, true, Bc, T, s)) return 1;
+    if (prepare_cond(c, Bc, T, s)) return 1;
+    if (stage_input(c, xc, D, 0, false, Bc, T, s)) return 1;
+    EG_CUDA(cudaMemsetAsync(d_step, 0, sizeof(int), s));
+    TSrc ts{nullptr, d_step, N - 1};
+    NoiseSrc ns = ns_base;
+    ns.d_step = d_step; ns.draw_static = 2;
+    DdpmArgs a;
+    fill_ddpm(c, a, xc, xc, ts, ns, 1, inpaint, inpaint_len, Bc, T, true);
+
+    auto one_step = [&](cudaStream_t st) -> int {
+        if (run_denoiser(c, Bc, T, ts, nullptr, st)) return 1;
+        ddpm_update_kernel<<<grid1d(quads, 256), 256, 0, st>>>(a);
+        advance_step_kernel<<<1, 32, 0, st>>>(d_step);
+        c->launches += 2;
+        EG_CUDA(cudaGetLastError());
+        return 0;
+    };
+    const void* key[4] = {ns.tape, inpaint, (const void*)(uintptr_t)(ns.seed ^ (ns.window_offset * 0x9E3779B97F4A7C15ull)),
+                          (const void*)(uintptr_t)(((uint64_t)inpaint_len << 32) ^ (uint64_t)ns.draw_stride)};
+    if (c->use_graph) {
+        bool reuse = c->step_graph && c->graph_B == Bc && c->graph_T == T && !memcmp(key, c->graph_key, sizeof(key));
+        if (!reuse) {
+            if (c->step_graph) { cudaGraphExecDestroy(c->step_graph); c->step_graph = nullptr; }
+            cudaGraph_t g = nullptr;
+            int64_t before = c->launches;
+            EG_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+            int rc = one_step(s);
+            cudaError_t ce = cudaStreamEndCapture(s, &g);
+            c->launches = before;                       // captured, not launched
+            EG_CHECK(rc == 0, std::string("capture failed: ") + g_err);
+            EG_CUDA(ce);
+            EG_CUDA(cudaGraphInstantiate(&c->step_graph, g, 0));
+            cudaGraphDestroy(g);
+            c->graph_B = Bc; c->graph_T = T; memcpy(c->graph_key, key, sizeof(key));
+        }
+        int64_t per_step = 0;
+        { int64_t before = c->launches; c->launches = 0;   // count kernels of one step without launching: re-derive
+          per_step = (c->cfg.engine == EGOEGO_ENGINE_SIMT ? (2 + 7 * c->NL) : c->tc->launches_per_denoiser()) + 2;
+          c->launches = before; }
+        for (int i = 0; i < N; ++i) EG_CUDA(cudaGraphLaunch(c->step_graph, s));
+        c->launches += per_step * N;
+    } else {
+        for (int i = 0; i < N; ++i) if (one_step(s)) return 1;
+    }
+    EG_CUDA(cudaMemcpyAsync(out, xc, (size_t)Bc * T * D * 4, cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
+int egoego_sample(egoego_handle c, const float* x_start, const float* cond_mask, int B, int T, const egoego_rng* rng,
+                  const float* x_init, const float* inpaint, int inpaint_len, float* out, void* stream_v) {
+    if (check_ready(c, B, T)) return 1;
+    EG_CHECK(x_start && cond_mask && rng && out, "null argument");
+    EG_CHECK(inpaint_len >= 0 && inpaint_len <= T && (inpaint || inpaint_len == 0), "bad inpaint arguments");
+    EG_CUDA(cudaSetDevice(c->cfg.device));
+    cudaStream_t user = (cudaStream_t)stream_v;
+    cudaStream_t s = c->own_stream;            // capturable stream; ordered after/before the caller's stream
+    EG_CUDA(cudaEventRecord(c->ev_in, user));
+    EG_CUDA(cudaStreamWaitEvent(s, c->ev_in, 0));
+    const int D = c->D;
+    for (int b0 = 0; b0 < B; b0 += c->cfg.max_batch) {
+        int Bc = std::min(c->cfg.max_batch, B - b0);
+        size_t off = (size_t)b0 * T * D;
+        NoiseSrc ns{};
+        ns.tape = rng->tape ? rng->tape + off : nullptr;
+        ns.draw_stride = (long long)B * T * D;
+        ns.seed = rng->seed; ns.window_offset = rng->window_offset + b0;
+        if (sample_chunk(c, x_start + off, cond_mask + off, Bc, T, ns, x_init ? x_init + off : nullptr,
+                         inpaint ? inpaint + (size_t)b0 * inpaint_len * D : nullptr, inpaint_len, out + off, s)) return 1;
+    }
+    EG_CUDA(cudaEventRecord(c->ev_out, s));
+    EG_CUDA(cudaStreamWaitEvent(user, c->ev_out, 0));
+    return 0;
+}
+
+int egoego_sample_host(egoego_handle c, const float* x_start_h, const float* cond_mask_h, int B, int T,
+                       const egoego_rng* rng, float* out_h, void* stream_v) {
+    if (check_ready(c, B, T)) return 1;
+    EG_CHECK(x_start_h && cond_mask_h && rng && out_h, "null argument");
+    EG_CUDA(cudaSetDevice(c->cfg.device));
+    cudaStream_t user = (cudaStream_t)stream_v;
+    const int D = c->D;
+    const size_t MB = (size_t)c->cfg.max_batch, xe = MB * T * D;
+    if (c->h_xstart.bytes < xe * 4) { if (c->h_xstart.alloc(xe * 4) || c->h_mask.alloc(xe * 4) || c->h_out.alloc(xe * 4)) return 1; }
+    for (int b0 = 0; b0 < B; b0 += c->cfg.max_batch) {
+        int Bc = std::min(c->cfg.max_batch, B - b0);
+        size_t off = (size_t)b0 * T * D, n = (size_t)Bc * T * D;
+        EG_CUDA(cudaMemcpyAsync(c->h_xstart.p, x_start_h + off, n * 4, cudaMemcpyHostToDevice, user));
+        EG_CUDA(cudaMemcpyAsync(c->h_mask.p, cond_mask_h + off, n * 4, cudaMemcpyHostToDevice, user));
+        egoego_rng r = *rng;
+        r.window_offset = rng->window_offset + b0;
+        if (rng->tape) {   // host tape [N+2, B, T, D] -> device tape [N+2, Bc, T, D] of this chunk
+            size_t need = (size_t)(c->N + 2) * n * 4;
+            if (c->h_tape.bytes < need && c->h_tape.alloc(need)) return 1;
+            EG_CUDA(cudaMemcpy2DAsync(c->h_tape.p, n * 4, rng->tape + off, (size_t)B * T * D * 4, n * 4, c->N + 2,
+                                      cudaMemcpyHostToDevice, user));
+            r.tape = c->h_tape.as<float>();
+        }
+        // the device entry point expects tape stride = its own B: call it per chunk
+        if (egoego_sample(c, c->h_xstart.as<float>(), c->h_mask.as<float>(), Bc, T, &r, nullptr, nullptr, 0,
+                          c->h_out.as<float>(), user)) return 1;
+        EG_CUDA(cudaMemcpyAsync(out_h + off, c->h_out.p, n * 4, cudaMemcpyDeviceToHost, user));
+    }
+    EG_CUDA(cudaStreamSynchronize(user));
+    return 0;
+}
+
+int egoego_set_skeleton(egoego_handle c, const int32_t* parents, const float* rest_offsets, const float* jmin, const float* jmax) {
+    EG_CHECK(c && parents && rest_offsets && jmin && jmax, "null argument");
+    EG_CHECK(parents[0] == -1, "parents[0] must be -1");
+    Skeleton& sk = c->sk;
+    sk.max_depth = 0;
+    for (int j = 0; j < NJ; ++j) {
+        EG_CHECK(j == 0 || (parents[j] >= 0 && parents[j] < j), "parents must be topologically ordered");
+        sk.parents[j] = parents[j];
+        sk.depth[j] = j == 0 ? 0 : sk.depth[parents[j]] + 1;
+        sk.max_depth = std::max(sk.max_depth, sk.depth[j]);
+        for (int k = 0; k < 3; ++k) sk.off[j][k] = rest_offsets[j * 3 + k];
+    }
+    memcpy(sk.jmin, jmin, sizeof(sk.jmin));
+    memcpy(sk.jmax, jmax, sizeof(sk.jmax));
+    c->have_sk = true;
+    return 0;
+}
+
+int egoego_postprocess(egoego_handle c, const float* x, const float* recover_quat, int B, int T, float* aa, float* root,
+                       float* head, float* jpos, float* gquat, void* stream_v) {
+    EG_CHECK(c && x, "null argument");
+    EG_CHECK(c->have_sk, "egoego_set_skeleton has not been called");
+    EG_CHECK(c->D == 198, "post-processing is defined for d_feats = 198 (22*3 + 22*6)");
+    EG_CHECK(B >= 1 && T >= 1, "bad shape");
+    EG_CUDA(cudaSetDevice(c->cfg.device));
+    postprocess_kernel<<<(B * T + 7) / 8, 256, 0, (cudaStream_t)stream_v>>>(c->sk, x, recover_quat, B, T, aa, root, head, jpos, gquat);
+    c->launches++;
+    EG_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int egoego_fk_smpl(egoego_handle c, const float* root, const float* aa, int64_t N, float* gquat, float* jpos, void* stream_v) {
+    EG_CHECK(c && root && aa, "null argument");
+    EG_CHECK(c->have_sk, "egoego_set_skeleton has not been called");
+    EG_CHECK(N >= 1, "bad shape");
+    EG_CUDA(cudaSetDevice(c->cfg.device));
+    fk_smpl_kernel<<<(unsigned)((N + 7) / 8), 256, 0, (cudaStream_t)stream_v>>>(c->sk, root, aa, N, gquat, jpos);
+    c->launches++;
+    EG_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int egoego_canonicalize_head(egoego_handle c, const float* head_pos, const float* head_quat, int64_t stride_frames,
+                             int B, int T, float* x_start, float* recover_quat, void* stream_v) {
+    EG_CHECK(c && head_pos && head_quat && x_start, "null argument");
+    EG_CHECK(c->have_sk, "egoego_set_skeleton has not been called");
+    EG_CHECK(c->D == 198 && B >= 1 && T >= 1 && stride_frames >= T, "bad shape");
+    EG_CUDA(cudaSetDevice(c->cfg.device));
+    canonicalize_head_kernel<<<(B * T + 127) / 128, 128, 0, (cudaStream_t)stream_v>>>(c->sk, head_pos, head_quat, stride_frames,
+                                                                                      B, T, x_start, recover_quat);
+    c->launches++;
+    EG_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int64_t egoego_launch_count(egoego_handle c) { return c ? c->launches : -1; }
+
+}  // extern "C"

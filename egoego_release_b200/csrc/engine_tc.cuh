@@ -1,0 +1,46 @@
+// Tensor-core engine (EGOEGO_ENGINE_TCGEN05): interface used by egoego_b200.cu.
+// Implementation: engine_tc.cu (tcgen05 + TMA GEMMs with a 3-term bf16 hi/lo split).
+#pragma once
+#include <vector>
+#include "common.cuh"
+
+namespace egoego {
+
+struct TcLayerW {
+    const float *wq, *wk, *wv, *fc, *w1, *w2;                                  // host fp32 (reference layouts)
+    const float *bqkv, *fc_b, *b1, *b2, *ln1_g, *ln1_b, *ln2_g, *ln2_b;        // device fp32
+};
+
+struct TcWeights {
+    int D, d, H, dk, NL, N, Tmax, max_batch;
+    const float* start_w;   // host [d, 2D]
+    const float* start_b;   // device [d]
+    const float* pos;       // device [max_timesteps+1, d]
+    const float* temb;      // device [N, d]
+    const float* out_w;     // host [D, d]
+    const float* out_b;     // device [D]
+    std::vector<TcLayerW> layers;
+};
+
+struct TcImpl;
+
+class TcEngine {
+public:
+    TcEngine();
+    ~TcEngine();
+    int init(const TcWeights& w, cudaStream_t s);
+    // zero the padded A-operand planes for B windows
+    int clear_staging(int B, cudaStream_t s);
+    // scatter compact rows into the bf16 hi/lo A-operand planes (x half or x_cond half)
+    int stage(const float* src, int src_ld, int src_col0, bool cond_half, int B, int T, cudaStream_t s, int64_t* n);
+    // base[M, d] = x_cond-half of start_conv + bias + positional rows (constant over the loop)
+    int prepare_cond(int B, int T, cudaStream_t s, int64_t* n);
+    // one denoiser call; expects the x half staged; writes model_out[B, T, D]
+    int denoiser(int B, int T, TSrc ts, const float* pmask, float* model_out, cudaStream_t s, int64_t* n);
+    void stage_targets(__nv_bfloat16** hi, __nv_bfloat16** lo, int* ld);
+    int launches_per_denoiser() const;
+private:
+    TcImpl* impl_;
+};
+
+}  // namespace egoego

@@ -1,0 +1,156 @@
+/*
+ * egoego_b200.h -- C ABI of libegoego_b200.so: the B200-native (sm_100a) implementation of EgoEgo's
+ * stage-2 conditional motion-diffusion sampling path.
+ *
+ * The reference (lijiaman/egoego_release) is pure Python/PyTorch and has no FFI layer; its call
+ * boundary for this path is a set of methods on an nn.Module.  Each entry point below replaces one
+ * of them (paths relative to the reference repo):
+ *
+ *   egoego_create / egoego_set_tensor / egoego_commit_weights
+ *        CondGaussianDiffusion.__init__ + load_state_dict
+ *        (egoego/model/transformer_cond_diffusion_model.py:144-214,
+ *         trainer_amass_cond_motion_diffusion.py:108-122)
+ *   egoego_denoiser_forward   TransformerDiffusionModel.forward          (..._diffusion_model.py:118-141)
+ *   egoego_p_sample_step      CondGaussianDiffusion.p_sample (+ in-paint) (..._diffusion_model.py:248-256,392-397)
+ *   egoego_sample             CondGaussianDiffusion.sample / p_sample_loop (..._diffusion_model.py:258-270,527-535)
+ *   egoego_sample_host        same, host buffers in/out (H2D + loop + D2H inside the call)
+ *   egoego_postprocess        convert_model_res_to_data + AMASSDataset.fk_smpl
+ *                             (..._diffusion_model.py:469-525; egoego/data/amass_diffusion_dataset.py:265-293)
+ *   egoego_canonicalize_head  rotate_at_frame_smplh + x_start build       (egoego/lafan1/utils.py:111-137;
+ *                                                                           ..._diffusion_model.py:358-386)
+ *
+ * Conventions: every pointer is BORROWED for the duration of the call; the caller owns all buffers,
+ * the library owns only its workspace and packed weights.  "dev" pointers are CUDA device pointers on
+ * the handle's device; all tensors are dense row-major fp32 unless stated.  `stream` is a
+ * cudaStream_t passed as void* (NULL = legacy default stream); calls are asynchronous on that stream
+ * except the *_host entry points, which synchronise the stream before returning.  Every function
+ * returns 0 on success, non-zero on error (message via egoego_last_error()).  There is no CPU
+ * fallback: without a CUDA device of compute capability 10.x every call fails.
+ * A handle is re-entrant across handles, not thread-safe per handle.
+ */
+#ifndef EGOEGO_B200_H
+#define EGOEGO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct egoego_ctx* egoego_handle;
+
+/* Mirrors the constructor arguments of CondGaussianDiffusion (..._diffusion_model.py:144-161). */
+typedef struct egoego_cfg {
+    int32_t d_feats;       /* 198 = 22*3 + 22*6                                        */
+    int32_t d_model;       /* 512                                                      */
+    int32_t n_head;        /* 4                                                        */
+    int32_t n_dec_layers;  /* 4                                                        */
+    int32_t d_k;           /* 256                                                      */
+    int32_t d_v;           /* 256                                                      */
+    int32_t max_timesteps; /* 121 = window + 1 (time token)                            */
+    int32_t timesteps;     /* diffusion steps N (1000)                                 */
+    int32_t objective;     /* 0 = pred_noise, 1 = pred_x0                              */
+    int32_t max_batch;     /* workspace is sized for this many windows per call        */
+    int32_t device;        /* CUDA ordinal                                             */
+    int32_t engine;        /* EGOEGO_ENGINE_*                                          */
+} egoego_cfg;
+
+enum {
+    EGOEGO_ENGINE_TCGEN05 = 0, /* tcgen05/TMA GEMMs, 3-term bf16 hi/lo split, fp32 accumulate (default) */
+    EGOEGO_ENGINE_SIMT    = 1  /* fp32 CUDA-core GEMMs: validation / bisecting engine               */
+};
+
+/* Gaussian noise source of the sampler.
+ * tape != NULL : draws are read from `tape`, draw k at tape + k*B*T*d_feats (device memory for the
+ *                *device* entry points, host memory for egoego_sample_host).  Draw order is the
+ *                reference's: 0 = x init, 1 = x_cond noise, 2+k = k-th executed step.
+ * tape == NULL : counter-based Philox4x32-10 + Box-Muller keyed by (seed, window_offset + window,
+ *                draw, element) -- independent of batch split and GPU count. */
+typedef struct egoego_rng {
+    const float* tape;
+    uint64_t     seed;
+    uint64_t     window_offset;
+} egoego_rng;
+
+const char* egoego_last_error(void);
+int  egoego_version(void);
+
+int  egoego_create(const egoego_cfg* cfg, egoego_handle* out);
+int  egoego_destroy(egoego_handle h);
+
+/* Weight upload by the reference's state_dict key, e.g.
+ * "denoise_fn.motion_transformer.layer_stack.0.self_attn.w_q.weight" (an optional leading
+ * "ema_model." / "model." prefix is ignored).  Also accepts the schedule buffers
+ * "posterior_mean_coef1", "posterior_mean_coef2", "posterior_log_variance_clipped",
+ * "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod" ([timesteps]).  Unknown keys return 0 and
+ * are ignored (load_state_dict(strict=False) semantics); a wrong element count is an error. */
+int  egoego_set_tensor(egoego_handle h, const char* name, const float* data, int64_t numel, int on_device);
+/* Computes the schedule buffers from cfg.timesteps (cosine schedule, fp64 then cast), for callers
+ * without the reference's registered buffers. */
+int  egoego_make_cosine_schedule(egoego_handle h);
+/* Packs weights for the engine (fused QKV, bf16 hi/lo planes, timestep-embedding table, TMA maps).
+ * Must be called after the last set_tensor and before any compute call. */
+int  egoego_commit_weights(egoego_handle h, void* stream);
+
+/* out[B,T,d_feats] = denoise_fn(x_all[B,T,2*d_feats], t[B])   (t: int64 device array, 0 <= t < timesteps)
+ * padding_mask: NULL or float [B,T+1] (1 = keep, 0 = zero the row after every sub-layer). */
+int  egoego_denoiser_forward(egoego_handle h, const float* x_all_dev, const int64_t* t_dev,
+                             const float* padding_mask_dev, int B, int T, float* out_dev, void* stream);
+
+/* x_out = p_sample(x, t, x_cond): denoiser -> (pred_x0|pred_noise) -> clamp(-1,1) if clip_denoised ->
+ * posterior mean -> + 1[t>0] * exp(0.5*logvar[t]) * noise.  noise_dev NULL => Philox draw `draw_index`.
+ * If inpaint_dev != NULL, frames [0, inpaint_len) of x_out are then overwritten with
+ * inpaint_dev[B, inpaint_len, d_feats] (the sliding-window overlap conditioning).
+ * x_out may alias x. */
+int  egoego_p_sample_step(egoego_handle h, const float* x_dev, const int64_t* t_dev, const float* x_cond_dev,
+                          const float* noise_dev, const egoego_rng* rng, uint64_t draw_index,
+                          const float* padding_mask_dev, int clip_denoised,
+                          const float* inpaint_dev, int inpaint_len,
+                          int B, int T, float* x_out_dev, void* stream);
+
+/* Whole sampling loop on the device: x ~ N(0,I); x_cond = x_start*(1-mask) + mask*N(0,I);
+ * for t = N-1..0: x = p_sample(x, t, x_cond) [+ in-paint].  out_dev[B,T,d_feats].
+ * inpaint_dev/inpaint_len as above (NULL/0 for plain sample()).  x_init_dev: NULL (draw 0 of the rng)
+ * or an explicit initial x (the sliding-window path slices one long noise tensor). */
+int  egoego_sample(egoego_handle h, const float* x_start_dev, const float* cond_mask_dev, int B, int T,
+                   const egoego_rng* rng, const float* x_init_dev,
+                   const float* inpaint_dev, int inpaint_len, float* out_dev, void* stream);
+
+/* Same with HOST buffers (pinned or pageable): copies x_start/cond_mask (and the tape, if any) to the
+ * device, runs the loop, copies the result back and synchronises.  Batches larger than
+ * cfg.max_batch are processed in chunks. */
+int  egoego_sample_host(egoego_handle h, const float* x_start_host, const float* cond_mask_host, int B, int T,
+                        const egoego_rng* rng, float* out_host, void* stream);
+
+/* Skeleton + normalisation statistics used by the post-processing kernels:
+ * parents[22] (parents[0] = -1), rest_offsets[22*3], jpos_min[66], jpos_max[66] (host pointers). */
+int  egoego_set_skeleton(egoego_handle h, const int32_t* parents, const float* rest_offsets,
+                         const float* jpos_min, const float* jpos_max);
+
+/* convert_model_res_to_data (+ optional FK): x[B,T,198] normalised sample, recover_quat[B,4] (wxyz,
+ * NULL = identity).  Outputs (each nullable): local axis-angle aa[B,T,22,3], root[B,T,3], head[B,T,3],
+ * FK global joint positions jpos[B,T,22,3] and global rotations gquat[B,T,22,4] (wxyz, w>=0). */
+int  egoego_postprocess(egoego_handle h, const float* x_dev, const float* recover_quat_dev, int B, int T,
+                        float* aa_dev, float* root_dev, float* head_dev, float* jpos_dev, float* gquat_dev,
+                        void* stream);
+
+/* AMASSDataset.fk_smpl: (root[N,3], aa[N,22,3]) -> gquat[N,22,4], jpos[N,22,3] (either nullable). */
+int  egoego_fk_smpl(egoego_handle h, const float* root_dev, const float* aa_dev, int64_t N,
+                    float* gquat_dev, float* jpos_dev, void* stream);
+
+/* Head-frame canonicalisation of one window (rotate_at_frame_smplh with cano_t_idx=0, then move the
+ * first frame's x,y to 0) and construction of the window's conditioning:
+ *   head_pos[B,T,3], head_quat[B,T,4] (wxyz)  ->  x_start[B,T,198] (zeros except normalised head
+ *   position at 45:48 and head rot6d at 156:162), recover_quat[B,4]. */
+int  egoego_canonicalize_head(egoego_handle h, const float* head_pos_dev, const float* head_quat_dev,
+                              int64_t pos_stride_frames, int B, int T,
+                              float* x_start_dev, float* recover_quat_dev, void* stream);
+
+/* Introspection for tests/bench: number of kernels launched by this handle since creation, and the
+ * cumulative count of denoiser steps executed. */
+int64_t egoego_launch_count(egoego_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EGOEGO_B200_H */

@@ -1,0 +1,79 @@
+"""CPU-side checks of the boundary: the library loads, exports every symbol include/egoego_b200.h declares,
+refuses to run without a B200, and the host mirror keeps the reference's state_dict / signatures."""
+import ctypes as C
+import inspect
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as g
+    g.build()
+    from egoego_release_b200 import _capi
+    return _capi.lib()
+
+
+def test_header_symbols_exported(lib):
+    hdr = open(os.path.join(ROOT, "include", "egoego_b200.h")).read()
+    names = set(re.findall(r"\b(egoego_[a-z_0-9]+)\s*\(", hdr))
+    names -= {"egoego_ctx"}
+    assert len(names) >= 16
+    for n in sorted(names):
+        assert hasattr(lib, n), f"{n} declared in include/egoego_b200.h but not exported"
+    from egoego_release_b200 import _capi
+    assert set(_capi.EXPORTS) == names
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only behaviour")
+def test_no_cpu_fallback(lib):
+    from egoego_release_b200 import _capi
+    h = C.c_void_p()
+    cfg = _capi.Cfg(d_feats=198, d_model=512, n_head=4, n_dec_layers=4, d_k=256, d_v=256, max_timesteps=121,
+                    timesteps=50, objective=1, max_batch=2, device=0, engine=0)
+    assert lib.egoego_create(C.byref(cfg), C.byref(h)) != 0
+    assert b"no CPU fallback" in lib.egoego_last_error()
+    import egoego_release_b200 as E
+    m = E.CondGaussianDiffusion(d_feats=198, d_model=512, n_dec_layers=4, n_head=4, d_k=256, d_v=256,
+                                max_timesteps=121, out_dim=198, timesteps=10, objective="pred_x0")
+    x = torch.zeros(1, 120, 198)
+    with pytest.raises(E.EgoEgoError):
+        m.sample(x, torch.ones_like(x))
+
+
+def test_state_dict_and_signatures_match_reference():
+    import egoego_release_b200 as E
+    from oracle import egoego_oracle as O
+    m = E.CondGaussianDiffusion(d_feats=198, d_model=512, n_dec_layers=4, n_head=4, d_k=256, d_v=256,
+                                max_timesteps=121, out_dim=198, timesteps=1000, objective="pred_x0")
+    sd = m.state_dict()
+    p = O.init_params(0)
+    assert set(p) <= set(sd)
+    for k, v in p.items():
+        assert tuple(sd[k].shape) == tuple(v.shape), k
+    sched = O.make_schedule(1000)
+    for k, v in sched.items():
+        assert torch.equal(sd[k], v), k                      # schedule buffers bit-exact vs the pinned oracle
+    assert len(sd) == len(p) + 13
+    # reference signatures (transformer_cond_diffusion_model.py:248,258,527,547)
+    assert list(inspect.signature(m.sample).parameters)[:3] == ["x_start", "cond_mask", "padding_mask"]
+    assert list(inspect.signature(m.p_sample).parameters)[:5] == ["x", "t", "x_cond", "clip_denoised", "padding_mask"]
+    assert list(inspect.signature(m.sample_sliding_window_w_canonical).parameters)[:5] == \
+        ["ds", "global_head_jpos", "global_head_jquat", "x_start", "cond_mask"]
+    with pytest.raises(ValueError):
+        E.CondGaussianDiffusion(d_feats=198, d_model=512, n_dec_layers=4, n_head=4, d_k=256, d_v=256,
+                                max_timesteps=121, out_dim=198, beta_schedule="quadratic")
+
+
+def test_condition_mask_glue():
+    import egoego_release_b200 as E
+    from oracle import egoego_oracle as O
+    d = torch.zeros(2, 7, 198)
+    assert torch.equal(E.prep_head_condition_mask(d), O.prep_head_condition_mask(d.shape))
+    pm = E.prep_padding_mask(d, torch.tensor([120, 60]))
+    assert pm.shape == (2, 1, 121) and pm[1, 0].sum() == 61

@@ -1,0 +1,192 @@
+"""GPU parity: the CUDA path (through the C ABI / host mirror) against the CPU oracle and the golden
+vectors produced by the unmodified reference.  Tolerances (north_star): joint positions within 1e-3 m
+abs of the reference's CPU fp32 path on identical conditioning and noise; raw normalised output
+tolerances are stated per test."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import egoego_oracle as O
+from oracle import rotations as R
+from oracle.gen_golden import Tape, synth_x_start
+from helpers import ENGINES, joints, make_model, maxabs
+
+pytestmark = pytest.mark.gpu
+
+JPOS_TOL_M = 1e-3
+
+
+def _g(golden_dir, name):
+    return dict(np.load(os.path.join(golden_dir, name)))
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_denoiser_forward_vs_golden(engine, golden_dir, params0):
+    g = _g(golden_dir, "denoiser_forward.npz")
+    m = make_model(1000, engine, params0)
+    tol = 1e-4 if engine == "simt" else 2e-4
+    for tag, B, T, ts in (("b2_t120", 2, 120, (0, 999)), ("b1_t30", 1, 30, (500,))):
+        x = torch.from_numpy(O.noise_tape(11, 1, (B, T, 396))[0]).cuda()
+        for t in ts:
+            y = m.denoise_fn(x, torch.full((B,), t, dtype=torch.long, device="cuda"))
+            assert maxabs(y, g[f"{tag}_t{t}"]) < tol, (tag, t)
+    x = torch.from_numpy(O.noise_tape(12, 1, (2, 120, 396))[0]).cuda()
+    pm = (torch.arange(121)[None, None, :] < torch.tensor([121, 61])[:, None, None]).cuda()
+    y = m.denoise_fn(x, torch.full((2,), 7, dtype=torch.long, device="cuda"), padding_mask=pm)
+    assert maxabs(y, g["b2_t120_t7_padmask"]) < tol
+    # per-window timesteps (training-style call): rows must match single-t calls
+    tt = torch.tensor([3, 977], device="cuda")
+    y2 = m.denoise_fn(x, tt)
+    for b in range(2):
+        yb = m.denoise_fn(x[b:b + 1], tt[b:b + 1])
+        assert maxabs(y2[b:b + 1], yb) < 1e-6
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_p_sample_inpaint_vs_golden(engine, golden_dir, params0):
+    g = _g(golden_dir, "p_sample_inpaint.npz")
+    m = make_model(1000, engine, params0)
+    for T in (120, 30):
+        rng = Tape(31 + T)
+        x = rng.draw((2, T, 198)).cuda()
+        xc = rng.draw((2, T, 198)).cuda()
+        inp = rng.draw((2, 10, 198)).clamp(-1, 1).cuda()
+        for k, t in enumerate((999, 998, 997, 1, 0)):
+            nz = rng.draw(x.shape).cuda()
+            x = m.p_sample(x, torch.full((2,), t, dtype=torch.long, device="cuda"), xc, noise=nz, inpaint=inp)
+            assert maxabs(x, g[f"t{T}"][k]) < 3e-4, (T, t)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_sample_50_steps_vs_golden(engine, golden_dir, params0):
+    g = _g(golden_dir, "sample.npz")
+    N, B, seed = 50, 2, 21
+    m = make_model(N, engine, params0)
+    xs = synth_x_start(100 + N, B, 120)
+    cm = O.prep_head_condition_mask(xs.shape)
+    tp = Tape(seed)
+    tape = torch.stack([tp.draw(xs.shape) for _ in range(N + 2)])
+    m.set_noise_tape(tape.cuda())
+    y = m.sample(xs.cuda(), cm.cuda())
+    ref = torch.from_numpy(g[f"n{N}_b{B}_seed{seed}"])
+    raw = maxabs(y, ref)
+    jerr = maxabs(joints(y), joints(ref))
+    mp = O.mpjpe_mm(joints(y), joints(ref))
+    print(f"[{engine}] sample N=50: raw max-abs {raw:.3e}, joint max-abs {jerr * 1e3:.4f} mm, MPJPE {mp:.5f} mm")
+    assert jerr < JPOS_TOL_M
+    assert raw < 5e-4
+    # host entry point (H2D + loop + D2H inside the call) gives the same result
+    m.set_noise_tape(tape)
+    yh = m.sample_host(xs, cm)
+    assert maxabs(yh, y) < 1e-6
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_sample_1000_steps_vs_golden(engine, golden_dir, params0):
+    g = _g(golden_dir, "sample.npz")
+    N, B, seed = 1000, 1, 22
+    m = make_model(N, engine, params0)
+    xs = synth_x_start(100 + N, B, 120)
+    cm = O.prep_head_condition_mask(xs.shape)
+    tp = Tape(seed)
+    tape = torch.stack([tp.draw(xs.shape) for _ in range(N + 2)])
+    m.set_noise_tape(tape.cuda())
+    y = m.sample(xs.cuda(), cm.cuda())
+    ref = torch.from_numpy(g[f"n{N}_b{B}_seed{seed}"])
+    jerr = maxabs(joints(y), joints(ref))
+    print(f"[{engine}] sample N=1000: raw max-abs {maxabs(y, ref):.3e}, joint max-abs {jerr * 1e3:.4f} mm")
+    assert jerr < JPOS_TOL_M
+
+
+def test_postprocess_vs_golden(golden_dir, params0):
+    import egoego_release_b200 as E
+    g = _g(golden_dir, "postprocess.npz")
+    m = make_model(50, "simt", params0)
+    ds = E.MotionDataStub().bind(m)
+    rng = Tape(41)
+    xr = rng.draw((2, 16, 198)).clamp(-1, 1)
+    xr[0, 0, 66:72] = 0.0
+    xr[0, 1, 66:72] = torch.tensor([1., 0, 0, 2., 0, 0])
+    xr[0, 2, 66:72] = torch.tensor([1e-9, 0, 0, 0, 1e-9, 0])
+    rec = O._np_normalize(rng.draw((2, 1, 1, 4)).numpy()).astype(np.float32)
+    aa, root, head, jpos, gq = m.postprocess(ds, xr.cuda(), rec, with_fk=True)
+    ok = np.isfinite(g["fk_jpos"]).all(axis=(1, 2))
+    assert maxabs(root, g["root"]) < 1e-5 and maxabs(head, g["head"]) < 1e-5
+    jp = jpos.reshape(-1, 22, 3).cpu().numpy()
+    assert np.abs(jp[ok] - g["fk_jpos"][ok]).max() < 2e-5
+    Ra = R.axis_angle_to_matrix(aa.cpu()).numpy().reshape(-1, 22, 3, 3)
+    Rg = R.axis_angle_to_matrix(torch.from_numpy(g["aa"])).numpy().reshape(-1, 22, 3, 3)
+    assert np.abs(Ra[ok] - Rg[ok]).max() < 2e-5
+    # standalone fk_smpl (AMASSDataset.fk_smpl signature) on the golden's own inputs
+    gq2, gj2 = ds.fk_smpl(torch.from_numpy(g["root"]).reshape(-1, 3).cuda(), torch.from_numpy(g["aa"]).reshape(-1, 22, 3).cuda())
+    assert np.abs(gj2.cpu().numpy()[ok] - g["fk_jpos"][ok]).max() < 2e-5
+    q_ref = torch.from_numpy(g["fk_quat"])[torch.from_numpy(ok)]
+    q_got = gq2.cpu()[torch.from_numpy(ok)]
+    assert (R.quaternion_to_matrix(q_ref) - R.quaternion_to_matrix(q_got)).abs().max() < 2e-5
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_sliding_window_vs_golden(engine, golden_dir, params0):
+    import egoego_release_b200 as E
+    g = _g(golden_dir, "sliding_window.npz")
+    m = make_model(50, engine, params0)
+    ds = E.MotionDataStub().bind(m)
+    hp = torch.from_numpy(np.load(os.path.join(golden_dir, "demo_head_qpos.npy")))[None].cuda()
+    tp = Tape(51)
+    aa, root = E.full_body_gen_cond_head_pose_sliding_window(m, ds, hp, noise_fn=tp.draw)
+    assert tuple(aa.shape) == (1, 140, 22, 3) and tuple(root.shape) == (1, 140, 3)
+    assert maxabs(root, g["root"]) < 1e-3
+    Ra = R.axis_angle_to_matrix(aa.cpu()).numpy()
+    Rg = R.axis_angle_to_matrix(torch.from_numpy(g["aa"])).numpy()
+    assert np.abs(Ra - Rg).max() < 5e-3
+    # judged quantity: global joint positions of the stitched sequence
+    ods = O.MotionDataStub()
+    _, j_got = ods.fk_smpl(root.cpu().reshape(-1, 3), aa.cpu().reshape(-1, 22, 3))
+    _, j_ref = ods.fk_smpl(torch.from_numpy(g["root"]).reshape(-1, 3), torch.from_numpy(g["aa"]).reshape(-1, 22, 3))
+    assert (j_got - j_ref).abs().max() < JPOS_TOL_M
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_philox_mode_properties_full_size(engine, params0):
+    """BASELINE config-2 shape (B=256, T=120) at a short schedule: size-independent properties --
+    (a) results do not depend on how the batch is split / offset (multi-GPU sharding invariant),
+    (b) the final sample is the clamped x0 prediction, i.e. inside [-1, 1] and finite,
+    (c) conditioned channels differ from unconditioned ones only through the model (smoke statistic)."""
+    N, B = 8, 256
+    m = make_model(N, engine, params0, max_batch=256)
+    xs = synth_x_start(7, B, 120).cuda()
+    cm = O.prep_head_condition_mask(xs.shape).cuda()
+    torch.manual_seed(123)
+    y_full = m.sample(xs, cm)
+    assert torch.isfinite(y_full).all() and y_full.abs().max() <= 1.0
+    parts = []
+    for r in range(4):                      # 4 "ranks" of 64 windows each, keyed by global window id
+        torch.manual_seed(123)
+        m.window_offset = r * 64
+        parts.append(m.sample(xs[r * 64:(r + 1) * 64], cm[r * 64:(r + 1) * 64]))
+    m.window_offset = 0
+    assert torch.equal(torch.cat(parts), y_full)
+    torch.manual_seed(124)
+    assert not torch.equal(m.sample(xs, cm), y_full)      # a different seed gives a different sample
+    assert m.launch_count() > 0
+
+
+def test_error_behaviour(params0):
+    import egoego_release_b200 as E
+    m = make_model(10, "simt", params0, max_batch=2)
+    x = torch.zeros(1, 121, 198, device="cuda")
+    with pytest.raises(E.EgoEgoError):
+        m.sample(x, torch.ones_like(x))                    # T > max_timesteps - 1
+    m2 = E.CondGaussianDiffusion(d_feats=198, d_model=512, n_dec_layers=4, n_head=4, d_k=256, d_v=256,
+                                 max_timesteps=121, out_dim=198, timesteps=10, objective="pred_v").cuda()
+    with pytest.raises(ValueError):
+        m2.p_sample(x[:, :120], torch.zeros(1, dtype=torch.long, device="cuda"), x[:, :120])
+    # chunking: B > max_batch is processed in chunks and equals the one-shot result of a larger engine
+    xs = synth_x_start(9, 5, 30).cuda()
+    cm = O.prep_head_condition_mask(xs.shape).cuda()
+    torch.manual_seed(5); a = m.sample(xs, cm)
+    m3 = make_model(10, "simt", params0, max_batch=8)
+    torch.manual_seed(5); b = m3.sample(xs, cm)
+    assert torch.equal(a, b)
