@@ -10,7 +10,7 @@ EXPORTS = [
     "egoego_last_error", "egoego_version", "egoego_create", "egoego_destroy", "egoego_set_tensor",
     "egoego_make_cosine_schedule", "egoego_commit_weights", "egoego_denoiser_forward", "egoego_p_sample_step",
     "egoego_sample", "egoego_sample_host", "egoego_set_skeleton", "egoego_postprocess", "egoego_fk_smpl",
-    "egoego_canonicalize_head", "egoego_launch_count",
+    "egoego_canonicalize_head", "egoego_launch_count", "egoego_selftest_gemm",
 ]
 
 ENGINE_TCGEN05, ENGINE_SIMT = 0, 1
@@ -59,6 +59,7 @@ def lib():
     L.egoego_postprocess.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp]
     L.egoego_fk_smpl.argtypes = [vp, vp, vp, i64, vp, vp, vp]
     L.egoego_canonicalize_head.argtypes = [vp, vp, vp, i64, i32, i32, vp, vp, vp]
+    L.egoego_selftest_gemm.argtypes = [i32, i32, i32, i32, u64, vp, vp, vp]
     L.egoego_launch_count.argtypes = [vp]
     L.egoego_launch_count.restype = i64
     for name in EXPORTS:

@@ -83,7 +83,7 @@ static int denoiser_simt(egoego_ctx* c, int B, int T, TSrc ts, const float* pmas
         const int nqkv = 3 * H * dk;
         EpiBiasScale eq{c->QKV.as<float>(), nqkv, w.bqkv.as<float>(), H * dk, 1.0f / sqrtf((float)dk)};
         sgemm_tn_kernel<<<dim3(nqkv / 128, M / 128), 256, 0, s>>>(c->Hbuf.as<float>(), d, w.wqkv.as<float>(), d, nqkv, d, eq);
-        attention_simt_kernel<<<B * H, 256, ATT_SIMT_SMEM, s>>>(c->QKV.as<float>(), nqkv, c->Obuf.as<float>(), H * dk, H, L);
+        attention_simt_kernel<false><<<B * H, 256, ATT_SIMT_SMEM, s>>>(c->QKV.as<float>(), nqkv, c->Obuf.as<float>(), nullptr, nullptr, H * dk, H, L);
         EpiBiasResid ef{c->Ybuf.as<float>(), d, w.fc_b.as<float>(), c->Hbuf.as<float>()};
         sgemm_tn_kernel<<<dim3(d / 128, M / 128), 256, 0, s>>>(c->Obuf.as<float>(), H * dk, w.fc_w.as<float>(), H * dk, d, H * dk, ef);
         layernorm512_kernel<<<M / 8, 256, 0, s>>>(c->Ybuf.as<float>(), c->Hbuf.as<float>(), nullptr, nullptr,
@@ -214,7 +214,7 @@ int egoego_create(const egoego_cfg* cfg, egoego_handle* out) {
         delete c;
         return 1;
     }
-    EG_CUDA(cudaFuncSetAttribute(attention_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SIMT_SMEM));
+    EG_CUDA(cudaFuncSetAttribute(attention_simt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SIMT_SMEM));
     *out = c;
     return 0;
 }
@@ -639,5 +639,13 @@ int egoego_canonicalize_head(egoego_handle c, const float* head_pos, const float
 }
 
 int64_t egoego_launch_count(egoego_handle c) { return c ? c->launches : -1; }
+
+int egoego_selftest_gemm(int device, int M, int N, int K, uint64_t seed, float* max_abs_err, float* max_abs_ref, float* ms) {
+    EG_CHECK(max_abs_err && max_abs_ref && ms, "null argument");
+    int ndev = 0;
+    EG_CHECK(cudaGetDeviceCount(&ndev) == cudaSuccess && device >= 0 && device < ndev, "no such CUDA device");
+    EG_CUDA(cudaSetDevice(device));
+    return selftest_gemm(M, N, K, seed, max_abs_err, max_abs_ref, ms);
+}
 
 }  // extern "C"

@@ -1,14 +1,282 @@
-// Placeholder until the tcgen05 engine lands (replaced in the next milestone).
+// Tensor-core engine: tcgen05/TMA split-bf16 GEMMs for every projection of the denoiser, warp-level
+// LayerNorm, attention; see gemm_tcgen05.cuh for the GEMM kernel.
+#include <cuda.h>
+#include <cstring>
+#include <memory>
+
 #include "engine_tc.cuh"
+#include "gemm_tcgen05.cuh"
+#include "kernels_simt.cuh"
+
 namespace egoego {
-struct TcImpl {};
-TcEngine::TcEngine() : impl_(nullptr) {}
-TcEngine::~TcEngine() {}
-int TcEngine::init(const TcWeights&, cudaStream_t) { set_error("tcgen05 engine not built yet"); return 1; }
-int TcEngine::clear_staging(int, cudaStream_t) { return 1; }
-int TcEngine::stage(const float*, int, int, bool, int, int, cudaStream_t, int64_t*) { return 1; }
-int TcEngine::prepare_cond(int, int, cudaStream_t, int64_t*) { return 1; }
-int TcEngine::denoiser(int, int, TSrc, const float*, float*, cudaStream_t, int64_t*) { return 1; }
-void TcEngine::stage_targets(__nv_bfloat16**, __nv_bfloat16**, int*) {}
-int TcEngine::launches_per_denoiser() const { return 0; }
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+    return fn;
 }
+
+// 2D bf16 row-major [rows, cols] tensor, box = [box_rows, 64 cols], 128-byte swizzle.
+static int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    PFN_encodeTiled enc = get_encode();
+    EG_CHECK(enc, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * 2};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    EG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
+    return 0;
+}
+
+struct Plane {                 // a bf16 hi/lo pair with its TMA maps
+    __nv_bfloat16 *hi = nullptr, *lo = nullptr;
+    CUtensorMap mhi, mlo;
+    size_t rows = 0, cols = 0;
+    int alloc(size_t r, size_t c, uint32_t box_rows) {
+        rows = r; cols = c;
+        EG_CUDA(cudaMalloc(&hi, r * c * 2));
+        EG_CUDA(cudaMalloc(&lo, r * c * 2));
+        EG_CUDA(cudaMemset(hi, 0, r * c * 2));
+        EG_CUDA(cudaMemset(lo, 0, r * c * 2));
+        if (make_map(&mhi, hi, r, c, box_rows) || make_map(&mlo, lo, r, c, box_rows)) return 1;
+        return 0;
+    }
+    void release() { if (hi) cudaFree(hi); if (lo) cudaFree(lo); hi = lo = nullptr; }
+};
+
+// Host fp32 [rows, src_ld] (columns [col0, col0+ncols)) -> zero-padded [rows_pad, cols_pad] hi/lo planes.
+static int upload_weight(Plane& p, const float* w, int rows, int src_ld, int col0, int ncols, int rows_pad, int cols_pad, uint32_t box_rows) {
+    if (p.alloc(rows_pad, cols_pad, box_rows)) return 1;
+    std::vector<__nv_bfloat16> hi((size_t)rows_pad * cols_pad, __float2bfloat16(0.f)), lo(hi);
+    for (int r = 0; r < rows; ++r)
+        for (int c = 0; c < ncols; ++c) {
+            float v = w[(size_t)r * src_ld + col0 + c];
+            __nv_bfloat16 h = __float2bfloat16_rn(v);
+            hi[(size_t)r * cols_pad + c] = h;
+            lo[(size_t)r * cols_pad + c] = __float2bfloat16_rn(v - __bfloat162float(h));
+        }
+    EG_CUDA(cudaMemcpy(p.hi, hi.data(), hi.size() * 2, cudaMemcpyHostToDevice));
+    EG_CUDA(cudaMemcpy(p.lo, lo.data(), lo.size() * 2, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+struct TcLayer {
+    Plane wqkv, fc, w1, w2;
+    const float *bqkv, *fc_b, *b1, *b2, *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+};
+
+struct TcImpl {
+    TcWeights w;
+    int M = 0, kx = 0, nout = 0, sms = 148;
+    Plane Wx, Wc, Wout;
+    std::vector<TcLayer> layers;
+    Plane X, C, Hs, O, F;                       // activation planes (A operands)
+    float *base = nullptr, *H = nullptr, *Y = nullptr, *QKV = nullptr;
+    ~TcImpl() {
+        for (Plane* p : {&Wx, &Wc, &Wout, &X, &C, &Hs, &O, &F}) p->release();
+        for (auto& l : layers) for (Plane* p : {&l.wqkv, &l.fc, &l.w1, &l.w2}) p->release();
+        for (float* p : {base, H, Y, QKV}) if (p) cudaFree(p);
+    }
+};
+
+template <int BN, class Epi>
+static int launch_gemm(TcImpl* I, const Plane& A, const Plane& W, int M, int N, int K, const Epi& epi, cudaStream_t s) {
+    using Cfg = GemmCfg<BN>;
+    static bool attr_set = false;
+    auto kern = gemm_split3_kernel<BN, Epi>;
+    if (!attr_set) {
+        EG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    EG_CHECK(M % GEMM_BM == 0 && N % BN == 0 && K % GEMM_BK == 0, "gemm shape not tile-aligned");
+    const int tiles = (M / GEMM_BM) * (N / BN);
+    const int grid = tiles < I->sms ? tiles : I->sms;
+    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(A.mhi, A.mlo, W.mhi, W.mlo, M, N, K, epi);
+    EG_CUDA(cudaGetLastError());
+    return 0;
+}
+
+TcEngine::TcEngine() : impl_(nullptr) {}
+TcEngine::~TcEngine() { delete impl_; }
+
+int TcEngine::init(const TcWeights& w, cudaStream_t) {
+    delete impl_;
+    impl_ = new TcImpl();
+    TcImpl* I = impl_;
+    I->w = w;
+    const int D = w.D, d = w.d, H = w.H, dk = w.dk;
+    EG_CHECK(d == 512 && dk == 256, "tensor engine is specialised for d_model = 512, d_k = d_v = 256");
+    int dev = 0;
+    EG_CUDA(cudaGetDevice(&dev));
+    EG_CUDA(cudaDeviceGetAttribute(&I->sms, cudaDevAttrMultiProcessorCount, dev));
+    I->M = w.max_batch * LP;
+    I->kx = ((D + 63) / 64) * 64;                 // 198 -> 256
+    I->nout = ((D + 255) / 256) * 256;            // 198 -> 256 (zero rows)
+    const size_t M = I->M;
+    // weights: [N, K] K-major planes, B-operand boxes of 256 rows
+    if (upload_weight(I->Wx, w.start_w, d, 2 * D, 0, D, d, I->kx, 256)) return 1;
+    if (upload_weight(I->Wc, w.start_w, d, 2 * D, D, D, d, I->kx, 256)) return 1;
+    if (upload_weight(I->Wout, w.out_w, D, d, 0, d, I->nout, d, 256)) return 1;
+    I->layers.resize(w.NL);
+    for (int l = 0; l < w.NL; ++l) {
+        const TcLayerW& s = w.layers[l];
+        TcLayer& L = I->layers[l];
+        std::vector<float> qkv((size_t)3 * H * dk * d);
+        memcpy(&qkv[0], s.wq, (size_t)H * dk * d * 4);
+        memcpy(&qkv[(size_t)H * dk * d], s.wk, (size_t)H * dk * d * 4);
+        memcpy(&qkv[(size_t)2 * H * dk * d], s.wv, (size_t)H * dk * d * 4);
+        if (upload_weight(L.wqkv, qkv.data(), 3 * H * dk, d, 0, d, 3 * H * dk, d, 256)) return 1;
+        if (upload_weight(L.fc, s.fc, d, H * dk, 0, H * dk, d, H * dk, 256)) return 1;
+        if (upload_weight(L.w1, s.w1, d, d, 0, d, d, d, 256)) return 1;
+        if (upload_weight(L.w2, s.w2, d, d, 0, d, d, d, 256)) return 1;
+        L.bqkv = s.bqkv; L.fc_b = s.fc_b; L.b1 = s.b1; L.b2 = s.b2;
+        L.ln1_g = s.ln1_g; L.ln1_b = s.ln1_b; L.ln2_g = s.ln2_g; L.ln2_b = s.ln2_b;
+    }
+    // activation planes: A-operand boxes of 128 rows
+    if (I->X.alloc(M, I->kx, 128) || I->C.alloc(M, I->kx, 128) || I->Hs.alloc(M, d, 128) ||
+        I->O.alloc(M, (size_t)H * dk, 128) || I->F.alloc(M, d, 128)) return 1;
+    EG_CUDA(cudaMalloc(&I->base, M * d * 4));
+    EG_CUDA(cudaMalloc(&I->H, M * d * 4));
+    EG_CUDA(cudaMalloc(&I->Y, M * d * 4));
+    EG_CUDA(cudaMalloc(&I->QKV, M * 3 * H * dk * 4));
+    EG_CUDA(cudaFuncSetAttribute(attention_simt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SIMT_SMEM));
+    return 0;
+}
+
+int TcEngine::clear_staging(int B, cudaStream_t s) {
+    TcImpl* I = impl_;
+    const size_t n = (size_t)B * LP * I->kx * 2;
+    EG_CUDA(cudaMemsetAsync(I->X.hi, 0, n, s)); EG_CUDA(cudaMemsetAsync(I->X.lo, 0, n, s));
+    EG_CUDA(cudaMemsetAsync(I->C.hi, 0, n, s)); EG_CUDA(cudaMemsetAsync(I->C.lo, 0, n, s));
+    return 0;
+}
+
+int TcEngine::stage(const float* src, int src_ld, int src_col0, bool cond_half, int B, int T, cudaStream_t s, int64_t* n) {
+    TcImpl* I = impl_;
+    Plane& P = cond_half ? I->C : I->X;
+    const long long tot = (long long)B * T * I->w.D;
+    stage_rows_split_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(P.hi, P.lo, I->kx, src, src_ld, src_col0, I->w.D, B, T);
+    EG_CUDA(cudaGetLastError());
+    *n += 1;
+    return 0;
+}
+
+int TcEngine::prepare_cond(int B, int T, cudaStream_t s, int64_t* n) {
+    TcImpl* I = impl_;
+    TcEpiBase e{I->base, I->w.d, I->w.start_b, I->w.pos, T};
+    if (launch_gemm<256>(I, I->C, I->Wc, B * LP, I->w.d, I->kx, e, s)) return 1;
+    *n += 1;
+    return 0;
+}
+
+void TcEngine::stage_targets(__nv_bfloat16** hi, __nv_bfloat16** lo, int* ld) {
+    *hi = impl_->X.hi; *lo = impl_->X.lo; *ld = impl_->kx;
+}
+
+int TcEngine::launches_per_denoiser() const { return 2 + 7 * impl_->w.NL; }
+
+int TcEngine::denoiser(int B, int T, TSrc ts, const float* pmask, float* model_out, cudaStream_t s, int64_t* n) {
+    TcImpl* I = impl_;
+    const int M = B * LP, d = I->w.d, H = I->w.H, dk = I->w.dk, L = T + 1;
+    const int nqkv = 3 * H * dk;
+    {
+        TcEpiStart e{I->H, I->Hs.hi, I->Hs.lo, d, I->base, I->w.pos, I->w.temb, ts, T};
+        if (launch_gemm<256>(I, I->X, I->Wx, M, d, I->kx, e, s)) return 1;
+    }
+    for (int l = 0; l < I->w.NL; ++l) {
+        TcLayer& W = I->layers[l];
+        TcEpiBiasScaleF32 eq{I->QKV, nqkv, W.bqkv, H * dk, 1.0f / sqrtf((float)dk)};
+        if (launch_gemm<256>(I, I->Hs, W.wqkv, M, nqkv, d, eq, s)) return 1;
+        attention_simt_kernel<true><<<B * H, 256, ATT_SIMT_SMEM, s>>>(I->QKV, nqkv, nullptr, I->O.hi, I->O.lo, H * dk, H, L);
+        TcEpiBiasResidF32 ef{I->Y, d, W.fc_b, I->H};
+        if (launch_gemm<256>(I, I->O, W.fc, M, d, H * dk, ef, s)) return 1;
+        layernorm512_kernel<<<M / 8, 256, 0, s>>>(I->Y, I->H, I->Hs.hi, I->Hs.lo, W.ln1_g, W.ln1_b, pmask, T, M);
+        TcEpiBiasReluSplit e1{I->F.hi, I->F.lo, d, W.b1};
+        if (launch_gemm<256>(I, I->Hs, W.w1, M, d, d, e1, s)) return 1;
+        TcEpiBiasResidF32 e2{I->Y, d, W.b2, I->H};
+        if (launch_gemm<256>(I, I->F, W.w2, M, d, d, e2, s)) return 1;
+        layernorm512_kernel<<<M / 8, 256, 0, s>>>(I->Y, I->H, I->Hs.hi, I->Hs.lo, W.ln2_g, W.ln2_b, pmask, T, M);
+    }
+    {
+        TcEpiOut eo{model_out, I->w.D, I->w.out_b, T};
+        if (launch_gemm<256>(I, I->Hs, I->Wout, M, I->nout, d, eo, s)) return 1;
+    }
+    EG_CUDA(cudaGetLastError());
+    *n += launches_per_denoiser();
+    return 0;
+}
+
+// ---- self test: split GEMM against the fp32 SIMT GEMM on random data ------------------------------
+__global__ void fill_uniform_kernel(float* p, long long n, unsigned long long seed, float scale) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint4 r = philox4x32_10(make_uint4((uint32_t)i, (uint32_t)(i >> 32), 7u, 9u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    p[i] = ((float)r.x * 2.3283064365386963e-10f * 2.0f - 1.0f) * scale;
+}
+__global__ void split_rows_kernel(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    split_bf16(src[i], hi[i], lo[i]);
+}
+__global__ void maxdiff_kernel(const float* a, const float* b, long long n, float* out /*[2]: max|a-b|, max|b|*/) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    float d = 0.f, m = 0.f;
+    if (i < n) { d = fabsf(a[i] - b[i]); m = fabsf(b[i]); if (!(d == d)) d = INFINITY; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { d = fmaxf(d, __shfl_xor_sync(0xffffffffu, d, o)); m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o)); }
+    if ((threadIdx.x & 31) == 0) { atomicMax(reinterpret_cast<int*>(out), __float_as_int(d)); atomicMax(reinterpret_cast<int*>(out) + 1, __float_as_int(m)); }
+}
+
+struct EpiStore { float* C; int ldc; __device__ void operator()(int r, int c, float a) const { C[(long long)r * ldc + c] = a; } };
+
+int selftest_gemm(int M, int N, int K, unsigned long long seed, float* max_abs_err, float* max_abs_ref, float* ms) {
+    EG_CHECK(M % 128 == 0 && N % 256 == 0 && K % 64 == 0, "selftest_gemm: need M%128==0, N%256==0, K%64==0");
+    TcImpl I;
+    int dev = 0;
+    EG_CUDA(cudaGetDevice(&dev));
+    EG_CUDA(cudaDeviceGetAttribute(&I.sms, cudaDevAttrMultiProcessorCount, dev));
+    float *A = nullptr, *W = nullptr, *C1 = nullptr, *C2 = nullptr, *res = nullptr;
+    EG_CUDA(cudaMalloc(&A, (size_t)M * K * 4)); EG_CUDA(cudaMalloc(&W, (size_t)N * K * 4));
+    EG_CUDA(cudaMalloc(&C1, (size_t)M * N * 4)); EG_CUDA(cudaMalloc(&C2, (size_t)M * N * 4)); EG_CUDA(cudaMalloc(&res, 8));
+    EG_CUDA(cudaMemset(res, 0, 8)); EG_CUDA(cudaMemset(C1, 0xff, (size_t)M * N * 4));
+    fill_uniform_kernel<<<(unsigned)(((long long)M * K + 255) / 256), 256>>>(A, (long long)M * K, seed, 1.0f);
+    fill_uniform_kernel<<<(unsigned)(((long long)N * K + 255) / 256), 256>>>(W, (long long)N * K, seed + 1, 0.05f);
+    Plane PA, PW;
+    if (PA.alloc(M, K, 128) || PW.alloc(N, K, 256)) return 1;
+    split_rows_kernel<<<(unsigned)(((long long)M * K + 255) / 256), 256>>>(A, PA.hi, PA.lo, (long long)M * K);
+    split_rows_kernel<<<(unsigned)(((long long)N * K + 255) / 256), 256>>>(W, PW.hi, PW.lo, (long long)N * K);
+    TcEpiPlain e{C1, N, nullptr, N};
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    if (launch_gemm<256>(&I, PA, PW, M, N, K, e, 0)) return 1;
+    EG_CUDA(cudaDeviceSynchronize());
+    cudaEventRecord(e0);
+    const int reps = 5;
+    for (int r = 0; r < reps; ++r) if (launch_gemm<256>(&I, PA, PW, M, N, K, e, 0)) return 1;
+    cudaEventRecord(e1);
+    EG_CUDA(cudaDeviceSynchronize());
+    float t = 0.f; cudaEventElapsedTime(&t, e0, e1); *ms = t / reps;
+    EpiStore st{C2, N};
+    sgemm_tn_kernel<<<dim3((N + 127) / 128, M / 128), 256>>>(A, K, W, K, N, K, st);
+    maxdiff_kernel<<<(unsigned)(((long long)M * N + 255) / 256), 256>>>(C1, C2, (long long)M * N, res);
+    float h[2];
+    EG_CUDA(cudaMemcpy(h, res, 8, cudaMemcpyDeviceToHost));
+    *max_abs_err = h[0]; *max_abs_ref = h[1];
+    PA.release(); PW.release();
+    cudaFree(A); cudaFree(W); cudaFree(C1); cudaFree(C2); cudaFree(res);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return 0;
+}
+
+}  // namespace egoego

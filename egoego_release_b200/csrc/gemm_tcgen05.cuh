@@ -1,0 +1,276 @@
+// Split-precision GEMM on the 5th-generation tensor cores.
+//
+//   D[M,N] = A[M,K] * W[N,K]^T   with   A = A_hi + A_lo,  W = W_hi + W_lo  (bf16 planes, K-major)
+//   D ~= A_hi W_hi^T + A_hi W_lo^T + A_lo W_hi^T     (three tcgen05.mma per k-step, one fp32 accumulator)
+//
+// which reproduces fp32 GEMM results to ~2^-16 relative (single-pass bf16/fp16/tf32
+// miss the 1e-3 m parity bar; the 3-term split meets it with 8x margin).  The four operand planes of a
+// k-block share one pipeline stage, so the split moves 4 tiles per 3 MMAs (better bytes/FLOP than a plain
+// bf16 GEMM).
+//
+// Structure (persistent, one CTA per SM, 192 threads):
+//   warp 0    TMA producer: cp.async.bulk.tensor 2D, 128B swizzle, mbarrier complete_tx
+//   warp 1    TMEM allocator + MMA issuer (one elected lane issues tcgen05.mma / tcgen05.commit)
+//   warps 2-5 epilogue: tcgen05.ld 32x32b -> registers -> fused epilogue -> global
+// Accumulators are double-buffered in TMEM (2 x BN columns of the 512) so the epilogue of tile i overlaps
+// the main loop of tile i+1.
+#pragma once
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace egoego {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;            // 64 bf16 = 128 B = one swizzle row
+constexpr int GEMM_THREADS = 192;
+
+template <int BN> struct GemmCfg {
+    static constexpr int STAGE_BYTES = 2 * GEMM_BM * GEMM_BK * 2 + 2 * BN * GEMM_BK * 2;   // A_hi A_lo W_hi W_lo
+    static constexpr int STAGES = (BN == 256) ? 2 : 3;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// ---- epilogues: called with 32 consecutive fp32 columns of one output row ------------------------
+struct TcEpiPlain {                       // C = acc (+ bias): self-test / generic
+    float* C; int ldc; const float* bias; int n_valid;
+    __device__ __forceinline__ void operator()(int row, int col0, const float (&v)[32]) const {
+        float* o = C + (long long)row * ldc + col0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            if (col0 + j < n_valid) {
+                float4 r = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                if (bias) { r.x += bias[col0 + j]; r.y += bias[col0 + j + 1]; r.z += bias[col0 + j + 2]; r.w += bias[col0 + j + 3]; }
+                *reinterpret_cast<float4*>(o + j) = r;
+            }
+        }
+    }
+};
+
+__device__ __forceinline__ void store_split8(__nv_bfloat16* hi, __nv_bfloat16* lo, const float* v) {
+    uint32_t ph[4], pl[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        __nv_bfloat16 h0, l0, h1, l1;
+        split_bf16(v[2 * q], h0, l0); split_bf16(v[2 * q + 1], h1, l1);
+        __nv_bfloat162 hh(h0, h1), ll(l0, l1);
+        ph[q] = *reinterpret_cast<uint32_t*>(&hh); pl[q] = *reinterpret_cast<uint32_t*>(&ll);
+    }
+    *reinterpret_cast<uint4*>(hi) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+    *reinterpret_cast<uint4*>(lo) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+}
+
+struct TcEpiBase {                        // base = x_cond-half of start_conv + bias + positional row (constant per window)
+    float* base; int ld; const float* bias; const float* pos; int T;
+    __device__ __forceinline__ void operator()(int row, int col0, const float (&v)[32]) const {
+        const int l = row % LP;
+        float* o = base + (long long)row * ld + col0;
+        const bool live = (l >= 1 && l <= T);
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live) {
+                const float* p = pos + (long long)(l + 1) * ld + col0 + j;
+                r.x = v[j] + bias[col0 + j] + p[0]; r.y = v[j + 1] + bias[col0 + j + 1] + p[1];
+                r.z = v[j + 2] + bias[col0 + j + 2] + p[2]; r.w = v[j + 3] + bias[col0 + j + 3] + p[3];
+            }
+            *reinterpret_cast<float4*>(o + j) = r;
+        }
+    }
+};
+
+struct TcEpiStart {                       // H = x-half GEMM + base ; row 0 = time token ; writes fp32 + hi/lo planes
+    float* H; __nv_bfloat16* Hhi; __nv_bfloat16* Hlo; int ld;
+    const float* base; const float* pos; const float* temb; TSrc ts; int T;
+    __device__ __forceinline__ void operator()(int row, int col0, const float (&v)[32]) const {
+        const int w = row / LP, l = row % LP;
+        float r[32];
+        if (l == 0) {
+            const float* te = temb + (long long)ts.get(w) * ld + col0;
+            const float* p1 = pos + ld + col0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = te[j] + p1[j];
+        } else if (l <= T) {
+            const float* b = base + (long long)row * ld + col0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = v[j] + b[j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = 0.f;
+        }
+        const long long o = (long long)row * ld + col0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(H + o + j) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) store_split8(Hhi + o + j, Hlo + o + j, r + j);
+    }
+};
+
+struct TcEpiBiasScaleF32 {                // QKV projection -> fp32 [M, ldc] (q block pre-scaled by 1/sqrt(d_k))
+    float* C; int ldc; const float* bias; int scale_cols; float scale;
+    __device__ __forceinline__ void operator()(int row, int col0, const float (&v)[32]) const {
+        float* o = C + (long long)row * ldc + col0;
+        const float s = col0 < scale_cols ? scale : 1.0f;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(o + j) = make_float4((v[j] + bias[col0 + j]) * s, (v[j + 1] + bias[col0 + j + 1]) * s,
+                                                            (v[j + 2] + bias[col0 + j + 2]) * s, (v[j + 3] + bias[col0 + j + 3]) * s);
+    }
+};
+
+struct TcEpiBiasResidF32 {                // fc / w_2: acc + bias + residual -> fp32 (pre-LayerNorm)
+    float* C; int ldc; const float* bias; const float* res;
+    __device__ __forceinline__ void operator()(int row, int col0, const float (&v)[32]) const {
+        const long long o = (long long)row * ldc + col0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            float4 r = *reinterpret_cast<const float4*>(res + o + j);
+            r.x += v[j] + bias[col0 + j]; r.y += v[j + 1] + bias[col0 + j + 1];
+            r.z += v[j + 2] + bias[col0 + j + 2]; r.w += v[j + 3] + bias[col0 + j + 3];
+            *reinterpret_cast<float4*>(C + o + j) = r;
+        }
+    }
+};
+
+struct TcEpiBiasReluSplit {               // w_1: relu(acc + bias) -> bf16 hi/lo planes (A operand of w_2)
+    __nv_bfloat16* hi; __nv_bfloat16* lo; int ld; const float* bias;
+    __device__ __forceinline__ void operator()(int row, int col0, const float (&v)[32]) const {
+        float r[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = fmaxf(v[j] + bias[col0 + j], 0.f);
+        const long long o = (long long)row * ld + col0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) store_split8(hi + o + j, lo + o + j, r + j);
+    }
+};
+
+struct TcEpiOut {                         // linear_out: tokens 1..T, first d_feats columns -> compact [B,T,d_feats]
+    float* out; int d_feats; const float* bias; int T;
+    __device__ __forceinline__ void operator()(int row, int col0, const float (&v)[32]) const {
+        const int w = row / LP, l = row % LP;
+        if (l < 1 || l > T) return;
+        float* o = out + ((long long)w * T + (l - 1)) * d_feats;
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+            const int c = col0 + j;
+            if (c + 1 < d_feats + 1 && c < d_feats)       // d_feats is even: pairs never straddle the edge
+                *reinterpret_cast<float2*>(o + c) = make_float2(v[j] + bias[c], v[j + 1] + bias[c + 1]);
+        }
+    }
+};
+
+// ---- the kernel ---------------------------------------------------------------------------------
+template <int BN, class Epi>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_split3_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl,
+                   const __grid_constant__ CUtensorMap mWh, const __grid_constant__ CUtensorMap mWl,
+                   int M, int N, int K, Epi epi) {
+    using Cfg = GemmCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+    constexpr int W_BYTES = BN * GEMM_BK * 2;
+    constexpr uint32_t IDESC = ptx::make_idesc_bf16(GEMM_BM, BN);
+    constexpr int ACC_STAGES = 512 / BN >= 2 ? 2 : 1;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* full_bar = bars;                         // [STAGES]
+    uint64_t* empty_bar = bars + STAGES;               // [STAGES]
+    uint64_t* tfull_bar = bars + 2 * STAGES;           // [2]
+    uint64_t* tempty_bar = bars + 2 * STAGES + 2;      // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int m_tiles = M / GEMM_BM, n_tiles = N / BN, k_blocks = K / GEMM_BK;
+    const int total_tiles = m_tiles * n_tiles;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&mAh); ptx::prefetch_tmap(&mAl); ptx::prefetch_tmap(&mWh); ptx::prefetch_tmap(&mWl);
+        for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], 128); }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) { ptx::tmem_alloc(tmem_slot, 512); ptx::tmem_relinquish(); }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {                                 // ===== TMA producer =====
+            int s = 0; uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int m0 = (tile / n_tiles) * GEMM_BM, n0 = (tile % n_tiles) * BN;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+                    uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+                    ptx::mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+                    ptx::tma_load_2d(st, &mAh, &full_bar[s], kb * GEMM_BK, m0);
+                    ptx::tma_load_2d(st + A_BYTES, &mAl, &full_bar[s], kb * GEMM_BK, m0);
+                    ptx::tma_load_2d(st + 2 * A_BYTES, &mWh, &full_bar[s], kb * GEMM_BK, n0);
+                    ptx::tma_load_2d(st + 2 * A_BYTES + W_BYTES, &mWl, &full_bar[s], kb * GEMM_BK, n0);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                                 // ===== MMA issuer =====
+            int s = 0; uint32_t ph = 0; int it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const int a = (ACC_STAGES == 2) ? (it & 1) : 0;
+                const uint32_t aph = (ACC_STAGES == 2) ? ((it >> 1) & 1) : (it & 1);
+                ptx::mbar_wait(&tempty_bar[a], aph ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + a * BN;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    ptx::mbar_wait(&full_bar[s], ph);
+                    ptx::tc_fence_after();
+                    const uint32_t st = ptx::smem_u32(smem + s * Cfg::STAGE_BYTES);
+                    const uint64_t dAh = ptx::make_smem_desc_sw128(st);
+                    const uint64_t dAl = ptx::make_smem_desc_sw128(st + A_BYTES);
+                    const uint64_t dWh = ptx::make_smem_desc_sw128(st + 2 * A_BYTES);
+                    const uint64_t dWl = ptx::make_smem_desc_sw128(st + 2 * A_BYTES + W_BYTES);
+#pragma unroll
+                    for (int kk = 0; kk < GEMM_BK / 16; ++kk) {
+                        const uint64_t adv = (uint64_t)(kk * 32 >> 4);       // +32 B per UMMA_K inside the swizzle row
+                        ptx::umma_f16(d_tmem, dAh + adv, dWh + adv, IDESC, (kb | kk) != 0);
+                        ptx::umma_f16(d_tmem, dAh + adv, dWl + adv, IDESC, 1);
+                        ptx::umma_f16(d_tmem, dAl + adv, dWh + adv, IDESC, 1);
+                    }
+                    ptx::umma_commit(&empty_bar[s]);                        // frees the smem stage when the MMAs retire
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+                ptx::umma_commit(&tfull_bar[a]);                            // accumulator ready for the epilogue
+            }
+        }
+    } else {                                             // ===== epilogue warps 2..5 =====
+        const int quarter = warp & 3;                    // TMEM lane quarter this warp may access
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int a = (ACC_STAGES == 2) ? (it & 1) : 0;
+            const uint32_t aph = (ACC_STAGES == 2) ? ((it >> 1) & 1) : (it & 1);
+            const int m0 = (tile / n_tiles) * GEMM_BM, n0 = (tile % n_tiles) * BN;
+            ptx::mbar_wait(&tfull_bar[a], aph);
+            ptx::tc_fence_after();
+            const int row = m0 + quarter * 32 + lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * BN;
+#pragma unroll 1
+            for (int c = 0; c < BN; c += 32) {
+                uint32_t r[32];
+                ptx::tmem_ld_32x32(taddr + c, r);
+                ptx::tmem_ld_wait();
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                epi(row, n0 + c, v);
+            }
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(&tempty_bar[a]);
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, 512); }
+}
+
+}  // namespace egoego

@@ -123,8 +123,10 @@ __global__ void __launch_bounds__(256) sgemm_tn_kernel(const float* __restrict__
 constexpr int ATT_SIMT_SMEM = (128 * 129 + 16 * 132 * 2) * 4 > (128 * 129 + 16 * 256) * 4
                                   ? (128 * 129 + 16 * 132 * 2) * 4 : (128 * 129 + 16 * 256) * 4;
 
+template <bool SPLIT>
 __global__ void __launch_bounds__(256) attention_simt_kernel(const float* __restrict__ QKV, int ldq,
-                                                             float* __restrict__ O, int ldo,
+                                                             float* __restrict__ O, __nv_bfloat16* __restrict__ Ohi,
+                                                             __nv_bfloat16* __restrict__ Olo, int ldo,
                                                              int n_head, int L) {
     constexpr int DH = 256;
     extern __shared__ __align__(16) float sm[];
@@ -234,13 +236,24 @@ __global__ void __launch_bounds__(256) attention_simt_kernel(const float* __rest
             }
             __syncthreads();
         }
-        float* Ow = O + (long long)w * LP * ldo + h * DH;
+        const long long obase = (long long)w * LP * ldo + h * DH;
 #pragma unroll
         for (int i = 0; i < 8; ++i)
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                *reinterpret_cast<float4*>(Ow + (long long)(ty * 8 + i) * ldo + q * 64 + tx * 4) =
-                    make_float4(acc[i][q * 4 + 0], acc[i][q * 4 + 1], acc[i][q * 4 + 2], acc[i][q * 4 + 3]);
+            for (int q = 0; q < 4; ++q) {
+                const long long o = obase + (long long)(ty * 8 + i) * ldo + q * 64 + tx * 4;
+                if (SPLIT) {
+                    __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
+                    split_bf16(acc[i][q * 4 + 0], h0, l0); split_bf16(acc[i][q * 4 + 1], h1, l1);
+                    split_bf16(acc[i][q * 4 + 2], h2, l2); split_bf16(acc[i][q * 4 + 3], h3, l3);
+                    __nv_bfloat162 a0(h0, h1), a1(h2, h3), b0(l0, l1), b1(l2, l3);
+                    *reinterpret_cast<uint2*>(Ohi + o) = make_uint2(*reinterpret_cast<uint32_t*>(&a0), *reinterpret_cast<uint32_t*>(&a1));
+                    *reinterpret_cast<uint2*>(Olo + o) = make_uint2(*reinterpret_cast<uint32_t*>(&b0), *reinterpret_cast<uint32_t*>(&b1));
+                } else {
+                    *reinterpret_cast<float4*>(O + o) =
+                        make_float4(acc[i][q * 4 + 0], acc[i][q * 4 + 1], acc[i][q * 4 + 2], acc[i][q * 4 + 3]);
+                }
+            }
     }
 }
 
@@ -249,7 +262,7 @@ __global__ void __launch_bounds__(256) attention_simt_kernel(const float* __rest
 // Optional row mask (padding_mask, [B, T+1]) multiplies the normalised row (DecoderLayer :135,139).
 // Optionally also emits the bf16 hi/lo planes consumed by the tensor-core engine.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) layernorm512_kernel(const float* __restrict__ Y, float* __restrict__ H,
+static __global__ void __launch_bounds__(256) layernorm512_kernel(const float* __restrict__ Y, float* __restrict__ H,
                                                            __nv_bfloat16* __restrict__ Hhi,
                                                            __nv_bfloat16* __restrict__ Hlo,
                                                            const float* __restrict__ gamma,
@@ -303,7 +316,7 @@ __global__ void __launch_bounds__(256) layernorm512_kernel(const float* __restri
 // Timestep-embedding table: temb[t] = Linear(256->512)(GELU(Linear(64->256)([sin(t f), cos(t f)])))
 // for every t in [0, timesteps)  (transformer_cond_diffusion_model.py:61-73,111-116).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) time_table_kernel(const float* __restrict__ w1, const float* __restrict__ b1,
+static __global__ void __launch_bounds__(256) time_table_kernel(const float* __restrict__ w1, const float* __restrict__ b1,
                                                          const float* __restrict__ w2, const float* __restrict__ b2,
                                                          float* __restrict__ temb, int d_model) {
     __shared__ float emb[64];
@@ -334,7 +347,7 @@ __global__ void __launch_bounds__(256) time_table_kernel(const float* __restrict
 // Philox call feeds four outputs; windows have T*D elements (D = 198).
 // ---------------------------------------------------------------------------------------------
 // x = noise(draw 0)   and/or   x_cond = x_start*(1-m) + m*noise(draw 1)
-__global__ void init_sample_kernel(float* __restrict__ x, float* __restrict__ x_cond,
+static __global__ void init_sample_kernel(float* __restrict__ x, float* __restrict__ x_cond,
                                    const float* __restrict__ x_init, const float* __restrict__ x_start,
                                    const float* __restrict__ cond_mask, NoiseSrc ns, int B, int T, int D) {
     const long long epw = (long long)T * D;
@@ -368,7 +381,7 @@ __global__ void init_sample_kernel(float* __restrict__ x, float* __restrict__ x_
 
 // Scatter compact [B,T,*] rows into the padded fp32 A operand of the SIMT start GEMM:
 // Ain[w*LP + 1 + f][col0 + c] = src[w][f][c]; other rows / pad columns are zeroed once at setup.
-__global__ void stage_rows_f32_kernel(float* __restrict__ Ain, int lda, int col0,
+static __global__ void stage_rows_f32_kernel(float* __restrict__ Ain, int lda, int col0,
                                       const float* __restrict__ src, int src_ld, int src_col0, int ncols,
                                       int B, int T) {
     long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -381,7 +394,7 @@ __global__ void stage_rows_f32_kernel(float* __restrict__ Ain, int lda, int col0
 }
 
 // Same, into bf16 hi/lo planes (tensor-core engine A operand).
-__global__ void stage_rows_split_kernel(__nv_bfloat16* __restrict__ Ahi, __nv_bfloat16* __restrict__ Alo, int lda,
+static __global__ void stage_rows_split_kernel(__nv_bfloat16* __restrict__ Ahi, __nv_bfloat16* __restrict__ Alo, int lda,
                                         const float* __restrict__ src, int src_ld, int src_col0, int ncols,
                                         int B, int T) {
     long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -413,7 +426,7 @@ struct DdpmArgs {
     int B, T, D;
 };
 
-__global__ void ddpm_update_kernel(DdpmArgs a) {
+static __global__ void ddpm_update_kernel(DdpmArgs a) {
     const long long epw = (long long)a.T * a.D;
     const long long quads_pw = (epw + 3) / 4;
     long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -457,6 +470,6 @@ __global__ void ddpm_update_kernel(DdpmArgs a) {
     }
 }
 
-__global__ void advance_step_kernel(int* d_step) { if (threadIdx.x == 0 && blockIdx.x == 0) (*d_step)++; }
+static __global__ void advance_step_kernel(int* d_step) { if (threadIdx.x == 0 && blockIdx.x == 0) (*d_step)++; }
 
 }  // namespace egoego

@@ -126,7 +126,7 @@ __device__ __forceinline__ void warp_fk(const Skeleton& sk, int j, Q4 lrot, cons
     gp[0] += root[0]; gp[1] += root[1]; gp[2] += root[2];
 }
 
-__global__ void __launch_bounds__(256) postprocess_kernel(Skeleton sk, const float* __restrict__ x,
+static __global__ void __launch_bounds__(256) postprocess_kernel(Skeleton sk, const float* __restrict__ x,
                                                           const float* __restrict__ recover_quat, int B, int T,
                                                           float* __restrict__ aa_out, float* __restrict__ root_out,
                                                           float* __restrict__ head_out, float* __restrict__ jpos_out,
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(256) postprocess_kernel(Skeleton sk, const flo
     }
 }
 
-__global__ void __launch_bounds__(256) fk_smpl_kernel(Skeleton sk, const float* __restrict__ root_in,
+static __global__ void __launch_bounds__(256) fk_smpl_kernel(Skeleton sk, const float* __restrict__ root_in,
                                                       const float* __restrict__ aa_in, long long N,
                                                       float* __restrict__ gquat_out, float* __restrict__ jpos_out) {
     const long long frame = (long long)blockIdx.x * 8 + threadIdx.x / 32;
@@ -210,7 +210,7 @@ __device__ __forceinline__ void qv_rot(Q4 q, const float x[3], float out[3]) {  
     out[2] = x[2] + q.w * t[2] + (q.x * t[1] - q.y * t[0]);
 }
 
-__global__ void canonicalize_head_kernel(Skeleton sk, const float* __restrict__ head_pos,
+static __global__ void canonicalize_head_kernel(Skeleton sk, const float* __restrict__ head_pos,
                                          const float* __restrict__ head_quat, long long stride_frames, int B, int T,
                                          float* __restrict__ x_start, float* __restrict__ recover_quat) {
     int gid = blockIdx.x * blockDim.x + threadIdx.x;
