@@ -1,0 +1,244 @@
+// Fused self-attention of one (window, head) on the tensor cores: S = Q K^T, row softmax over the first L
+// keys, O = P V -- S and P never leave the SM.
+//
+// Every product uses the same 3-term bf16 hi/lo split as the GEMMs (fp32-grade results):
+//   S = Qh Kh^T + Qh Kl^T + Ql Kh^T           (UMMA 128x128x16, K = d_k = 256)
+//   O = Ph Vh   + Ph Vl   + Pl Vh             (UMMA 128x256x16, K = 128 keys)
+// Operand planes (written by the QKV projection epilogue, bf16, K-major):
+//   Q, K : [(window*H + head)*128 + token, 256]      (Q pre-scaled by 1/sqrt(d_k))
+//   V^T  : [(window*H + head)*256 + dim,  128 tokens]
+// Persistent CTAs (one per SM, 192 threads) loop over (window, head) items:
+//   warp 0    TMA producer, ring of 2 x 64 KB stages: 4 Q/K k-blocks then 2 V^T k-blocks per item
+//   warp 1    MMA issuer (S of item i+1 is issued right after P V of item i, overlapping its epilogue)
+//   warps 2-5 softmax (TMEM -> registers -> P hi/lo into swizzled smem) and O epilogue (TMEM -> bf16 hi/lo planes)
+// TMEM: S at columns [0,128), O at [128,384).
+#pragma once
+#include "common.cuh"
+#include "tc_ptx.cuh"
+#include "gemm_tcgen05.cuh"
+
+namespace egoego {
+
+constexpr int ATT_STAGE_BYTES = 65536;
+constexpr int ATT_STAGES = 2;
+constexpr int ATT_P_BYTES = 2 * 2 * 128 * 128;          // hi/lo x 2 key blocks x [128 rows x 128 B]
+constexpr int ATT_SMEM_BYTES = ATT_STAGES * ATT_STAGE_BYTES + ATT_P_BYTES + 1024 + 256;
+constexpr int ATT_THREADS = 192;
+
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_constant__ CUtensorMap mQl,
+                    const __grid_constant__ CUtensorMap mKh, const __grid_constant__ CUtensorMap mKl,
+                    const __grid_constant__ CUtensorMap mVh, const __grid_constant__ CUtensorMap mVl,
+                    __nv_bfloat16* __restrict__ Ohi, __nv_bfloat16* __restrict__ Olo, int ldo,
+                    int n_items, int n_head, int L) {
+    constexpr uint32_t IDESC_S = ptx::make_idesc_bf16(128, 128);
+    constexpr uint32_t IDESC_O = ptx::make_idesc_bf16(128, 256);
+    constexpr uint32_t TM_S = 0, TM_O = 128;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* p_smem = smem + ATT_STAGES * ATT_STAGE_BYTES;           // P_hi [2][128][128B], P_lo [2][128][128B]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(p_smem + ATT_P_BYTES);
+    uint64_t* full_bar = bars;          // [2]
+    uint64_t* empty_bar = bars + 2;     // [2]
+    uint64_t* s_full = bars + 4;        // S accumulator ready (MMA -> softmax)
+    uint64_t* p_ready = bars + 5;       // P written to smem and S drained (softmax -> MMA), 128 arrivals
+    uint64_t* o_full = bars + 6;        // O accumulator ready (MMA -> epilogue)
+    uint64_t* o_free = bars + 7;        // O drained (epilogue -> MMA), 128 arrivals
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&mQh); ptx::prefetch_tmap(&mQl); ptx::prefetch_tmap(&mKh);
+        ptx::prefetch_tmap(&mKl); ptx::prefetch_tmap(&mVh); ptx::prefetch_tmap(&mVl);
+        for (int s = 0; s < ATT_STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+        ptx::mbar_init(s_full, 1); ptx::mbar_init(p_ready, 128); ptx::mbar_init(o_full, 1); ptx::mbar_init(o_free, 128);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) { ptx::tmem_alloc(tmem_slot, 512); ptx::tmem_relinquish(); }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {                                   // ===== TMA producer =====
+            int s = 0; uint32_t ph = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                for (int kb = 0; kb < 4; ++kb) {           // Q/K k-blocks of 64 dims: Qh Ql Kh Kl (16 KB each)
+                    ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+                    uint8_t* st = smem + s * ATT_STAGE_BYTES;
+                    ptx::mbar_arrive_expect_tx(&full_bar[s], ATT_STAGE_BYTES);
+                    ptx::tma_load_2d(st, &mQh, &full_bar[s], kb * 64, item * 128);
+                    ptx::tma_load_2d(st + 16384, &mQl, &full_bar[s], kb * 64, item * 128);
+                    ptx::tma_load_2d(st + 32768, &mKh, &full_bar[s], kb * 64, item * 128);
+                    ptx::tma_load_2d(st + 49152, &mKl, &full_bar[s], kb * 64, item * 128);
+                    if (++s == ATT_STAGES) { s = 0; ph ^= 1; }
+                }
+                for (int kb = 0; kb < 2; ++kb) {           // V^T k-blocks of 64 keys: Vh Vl (32 KB each)
+                    ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+                    uint8_t* st = smem + s * ATT_STAGE_BYTES;
+                    ptx::mbar_arrive_expect_tx(&full_bar[s], ATT_STAGE_BYTES);
+                    ptx::tma_load_2d(st, &mVh, &full_bar[s], kb * 64, item * 256);
+                    ptx::tma_load_2d(st + 32768, &mVl, &full_bar[s], kb * 64, item * 256);
+                    if (++s == ATT_STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                                   // ===== MMA issuer =====
+            int s = 0; uint32_t ph = 0; int it = 0;
+            const uint32_t p_hi = ptx::smem_u32(p_smem), p_lo = p_hi + 2 * 16384;
+            auto issue_S = [&]() {
+                for (int kb = 0; kb < 4; ++kb) {
+                    ptx::mbar_wait(&full_bar[s], ph);
+                    ptx::tc_fence_after();
+                    const uint32_t st = ptx::smem_u32(smem + s * ATT_STAGE_BYTES);
+                    const uint64_t dQh = ptx::make_smem_desc_sw128(st), dQl = ptx::make_smem_desc_sw128(st + 16384);
+                    const uint64_t dKh = ptx::make_smem_desc_sw128(st + 32768), dKl = ptx::make_smem_desc_sw128(st + 49152);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const uint64_t adv = (uint64_t)(kk * 2);
+                        ptx::umma_f16(tmem_base + TM_S, dQh + adv, dKh + adv, IDESC_S, (kb | kk) != 0);
+                        ptx::umma_f16(tmem_base + TM_S, dQh + adv, dKl + adv, IDESC_S, 1);
+                        ptx::umma_f16(tmem_base + TM_S, dQl + adv, dKh + adv, IDESC_S, 1);
+                    }
+                    ptx::umma_commit(&empty_bar[s]);
+                    if (++s == ATT_STAGES) { s = 0; ph ^= 1; }
+                }
+                ptx::umma_commit(s_full);
+            };
+            // Stream order of the ring is QK(i) V(i) QK(i+1) V(i+1) ..., so S(i+1) can only be issued after P V(i).
+            if (blockIdx.x < n_items) issue_S();
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+                const uint32_t iph = it & 1;
+                ptx::mbar_wait(p_ready, iph);              // P(i) in smem, S drained
+                ptx::mbar_wait(o_free, iph ^ 1);           // O of the previous item drained
+                ptx::tc_fence_after();
+                for (int kb = 0; kb < 2; ++kb) {
+                    ptx::mbar_wait(&full_bar[s], ph);
+                    ptx::tc_fence_after();
+                    const uint32_t st = ptx::smem_u32(smem + s * ATT_STAGE_BYTES);
+                    const uint64_t dVh = ptx::make_smem_desc_sw128(st), dVl = ptx::make_smem_desc_sw128(st + 32768);
+                    const uint64_t dPh = ptx::make_smem_desc_sw128(p_hi + kb * 16384), dPl = ptx::make_smem_desc_sw128(p_lo + kb * 16384);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const uint64_t adv = (uint64_t)(kk * 2);
+                        ptx::umma_f16(tmem_base + TM_O, dPh + adv, dVh + adv, IDESC_O, (kb | kk) != 0);
+                        ptx::umma_f16(tmem_base + TM_O, dPh + adv, dVl + adv, IDESC_O, 1);
+                        ptx::umma_f16(tmem_base + TM_O, dPl + adv, dVh + adv, IDESC_O, 1);
+                    }
+                    ptx::umma_commit(&empty_bar[s]);
+                    if (++s == ATT_STAGES) { s = 0; ph ^= 1; }
+                }
+                ptx::umma_commit(o_full);
+                if (item + (int)gridDim.x < n_items) issue_S();
+            }
+        }
+    } else {                                               // ===== softmax + epilogue warps 2..5 =====
+        const int quarter = warp & 3;
+        const int r = quarter * 32 + lane;                 // query row = TMEM lane
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        int it = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            const uint32_t iph = it & 1;
+            // ---- softmax over keys [0, L) ----
+            ptx::mbar_wait(s_full, iph);
+            ptx::tc_fence_after();
+            float v[128];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t raw[32];
+                ptx::tmem_ld_32x32(lane_addr + TM_S + c * 32, raw);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[c * 32 + j] = __uint_as_float(raw[j]);
+            }
+            float mx = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < 128; ++k) { if (k >= L) v[k] = -INFINITY; mx = fmaxf(mx, v[k]); }
+            float sum = 0.f;
+#pragma unroll
+            for (int k = 0; k < 128; ++k) { v[k] = (k < L) ? expf(v[k] - mx) : 0.f; sum += v[k]; }
+            const float inv = 1.0f / sum;
+            // P hi/lo -> K-major SW128 smem: 16-byte chunk j (keys 8j..8j+7) of row r lands at chunk (j%8)^(r%8)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                uint32_t ph4[4], pl4[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    __nv_bfloat16 h0, l0, h1, l1;
+                    split_bf16(v[8 * j + 2 * q] * inv, h0, l0);
+                    split_bf16(v[8 * j + 2 * q + 1] * inv, h1, l1);
+                    __nv_bfloat162 hh(h0, h1), ll(l0, l1);
+                    ph4[q] = *reinterpret_cast<uint32_t*>(&hh); pl4[q] = *reinterpret_cast<uint32_t*>(&ll);
+                }
+                const int kb = j >> 3, chunk = (j & 7) ^ (r & 7);
+                uint8_t* dst = p_smem + kb * 16384 + r * 128 + chunk * 16;
+                *reinterpret_cast<uint4*>(dst) = make_uint4(ph4[0], ph4[1], ph4[2], ph4[3]);
+                *reinterpret_cast<uint4*>(dst + 2 * 16384) = make_uint4(pl4[0], pl4[1], pl4[2], pl4[3]);
+            }
+            ptx::fence_proxy_async();                      // generic-proxy smem writes -> visible to the tensor core
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(p_ready);
+            // ---- O epilogue ----
+            ptx::mbar_wait(o_full, iph);
+            ptx::tc_fence_after();
+            const int w = item / n_head, h = item % n_head;
+            const long long obase = ((long long)w * LP + r) * ldo + h * 256;
+#pragma unroll 1
+            for (int c = 0; c < 8; ++c) {
+                uint32_t raw[32];
+                ptx::tmem_ld_32x32(lane_addr + TM_O + c * 32, raw);
+                ptx::tmem_ld_wait();
+                float o[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(raw[j]);
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) store_split8(Ohi + obase + c * 32 + j, Olo + obase + c * 32 + j, o + j);
+            }
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(o_free);
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, 512); }
+}
+
+// QKV projection epilogue writing the attention operand planes directly (one 256-wide tile = one (section, head)).
+struct TcEpiQKVPlanes {
+    __nv_bfloat16 *Qh, *Ql, *Kh, *Kl, *Vh, *Vl;       // Q,K: [(w*H+h)*128 + l][256];  V^T: [(w*H+h)*256 + c][128]
+    const float* bias; int n_head; float q_scale;
+    __device__ __forceinline__ void operator()(int row, int col0, const float (&v)[32]) const {
+        const int w = row / LP, l = row % LP;
+        const int sec = col0 / (n_head * 256), hc = col0 % (n_head * 256);
+        const int h = hc / 256, c0 = hc % 256;
+        float r[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = v[j] + bias[col0 + j];
+        if (sec == 2) {
+            const long long base = ((long long)(w * n_head + h) * 256 + c0) * 128 + l;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                __nv_bfloat16 hi, lo;
+                split_bf16(r[j], hi, lo);
+                Vh[base + (long long)j * 128] = hi;
+                Vl[base + (long long)j * 128] = lo;
+            }
+        } else {
+            __nv_bfloat16* ph = sec == 0 ? Qh : Kh;
+            __nv_bfloat16* pl = sec == 0 ? Ql : Kl;
+            if (sec == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) r[j] *= q_scale;
+            }
+            const long long o = ((long long)(w * n_head + h) * 128 + l) * 256 + c0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) store_split8(ph + o + j, pl + o + j, r + j);
+        }
+    }
+};
+
+}  // namespace egoego
