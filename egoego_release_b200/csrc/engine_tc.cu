@@ -2,10 +2,12 @@
 // LayerNorm, attention; see gemm_tcgen05.cuh for the GEMM kernel.
 #include <cuda.h>
 #include <cstring>
+#include <cstdlib>
 #include <memory>
 
 #include "engine_tc.cuh"
 #include "gemm_tcgen05.cuh"
+#include "attn_tcgen05.cuh"
 #include "kernels_simt.cuh"
 
 namespace egoego {
@@ -82,9 +84,11 @@ struct TcImpl {
     Plane Wx, Wc, Wout;
     std::vector<TcLayer> layers;
     Plane X, C, Hs, O, F;                       // activation planes (A operands)
+    Plane Qp, Kp, VT;                           // attention operand planes (see attn_tcgen05.cuh)
+    bool attn_tc = true;                        // EGOEGO_ATTN=simt selects the fp32 CUDA-core attention (bisecting)
     float *base = nullptr, *H = nullptr, *Y = nullptr, *QKV = nullptr;
     ~TcImpl() {
-        for (Plane* p : {&Wx, &Wc, &Wout, &X, &C, &Hs, &O, &F}) p->release();
+        for (Plane* p : {&Wx, &Wc, &Wout, &X, &C, &Hs, &O, &F, &Qp, &Kp, &VT}) p->release();
         for (auto& l : layers) for (Plane* p : {&l.wqkv, &l.fc, &l.w1, &l.w2}) p->release();
         for (float* p : {base, H, Y, QKV}) if (p) cudaFree(p);
     }
@@ -149,8 +153,16 @@ int TcEngine::init(const TcWeights& w, cudaStream_t) {
     EG_CUDA(cudaMalloc(&I->base, M * d * 4));
     EG_CUDA(cudaMalloc(&I->H, M * d * 4));
     EG_CUDA(cudaMalloc(&I->Y, M * d * 4));
-    EG_CUDA(cudaMalloc(&I->QKV, M * 3 * H * dk * 4));
-    EG_CUDA(cudaFuncSetAttribute(attention_simt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SIMT_SMEM));
+    const char* am = getenv("EGOEGO_ATTN");
+    I->attn_tc = !(am && strcmp(am, "simt") == 0);
+    if (I->attn_tc) {
+        if (I->Qp.alloc((size_t)w.max_batch * H * 128, 256, 128) || I->Kp.alloc((size_t)w.max_batch * H * 128, 256, 128) ||
+            I->VT.alloc((size_t)w.max_batch * H * 256, 128, 256)) return 1;
+        EG_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+    } else {
+        EG_CUDA(cudaMalloc(&I->QKV, M * 3 * H * dk * 4));
+        EG_CUDA(cudaFuncSetAttribute(attention_simt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SIMT_SMEM));
+    }
     return 0;
 }
 
@@ -196,9 +208,17 @@ int TcEngine::denoiser(int B, int T, TSrc ts, const float* pmask, float* model_o
     }
     for (int l = 0; l < I->w.NL; ++l) {
         TcLayer& W = I->layers[l];
-        TcEpiBiasScaleF32 eq{I->QKV, nqkv, W.bqkv, H * dk, 1.0f / sqrtf((float)dk)};
-        if (launch_gemm<256>(I, I->Hs, W.wqkv, M, nqkv, d, eq, s)) return 1;
-        attention_simt_kernel<true><<<B * H, 256, ATT_SIMT_SMEM, s>>>(I->QKV, nqkv, nullptr, I->O.hi, I->O.lo, H * dk, H, L);
+        if (I->attn_tc) {
+            TcEpiQKVPlanes eq{I->Qp.hi, I->Qp.lo, I->Kp.hi, I->Kp.lo, I->VT.hi, I->VT.lo, W.bqkv, H, 1.0f / sqrtf((float)dk)};
+            if (launch_gemm<256>(I, I->Hs, W.wqkv, M, nqkv, d, eq, s)) return 1;
+            const int items = B * H;
+            attention_tc_kernel<<<items < I->sms ? items : I->sms, ATT_THREADS, ATT_SMEM_BYTES, s>>>(
+                I->Qp.mhi, I->Qp.mlo, I->Kp.mhi, I->Kp.mlo, I->VT.mhi, I->VT.mlo, I->O.hi, I->O.lo, H * dk, items, H, L);
+        } else {
+            TcEpiBiasScaleF32 eq{I->QKV, nqkv, W.bqkv, H * dk, 1.0f / sqrtf((float)dk)};
+            if (launch_gemm<256>(I, I->Hs, W.wqkv, M, nqkv, d, eq, s)) return 1;
+            attention_simt_kernel<true><<<B * H, 256, ATT_SIMT_SMEM, s>>>(I->QKV, nqkv, nullptr, I->O.hi, I->O.lo, H * dk, H, L);
+        }
         TcEpiBiasResidF32 ef{I->Y, d, W.fc_b, I->H};
         if (launch_gemm<256>(I, I->O, W.fc, M, d, H * dk, ef, s)) return 1;
         layernorm512_kernel<<<M / 8, 256, 0, s>>>(I->Y, I->H, I->Hs.hi, I->Hs.lo, W.ln1_g, W.ln1_b, pmask, T, M);

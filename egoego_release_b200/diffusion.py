@@ -25,7 +25,7 @@ from . import _capi
 from ._capi import Cfg, EgoEgoError, Rng, check
 
 HEAD_IDX = 15
-DEFAULT_ENGINE = "simt"   # flipped to "tcgen05" once that engine is parity-green on the GPU
+DEFAULT_ENGINE = "tcgen05"   # "simt" = fp32 CUDA-core validation engine
 
 
 def _ptr(t: Optional[torch.Tensor]):
