@@ -137,6 +137,38 @@ def cpu_baseline(B_cpu, T, N, budget_s):
             "ms_per_denoiser_step": per_step * 1e3}
 
 
+def torch_gpu_baseline(dev, B, T, N, n_steps=12):
+    """The reference's own arithmetic (oracle port: same op sequence) as stock PyTorch eager fp32 on this B200 --
+    the denominator of north_star's ">= 10x the reference single-GPU PyTorch sampling throughput"."""
+    import torch
+    from oracle import egoego_oracle as O
+    params = {k: v.to(dev) for k, v in O.init_params(0).items()}
+    sched = {k: v.to(dev) for k, v in O.make_schedule(N).items()}
+    xs, cm = synth_inputs(B, T)
+    xs, cm = xs.to(dev), cm.to(dev)
+    out = {}
+    for tag, conv in (("linear_fp32", False), ("conv1d_cudnn_tf32_default", True)):
+        O.USE_CONV1D = conv
+        x = torch.randn(xs.shape, device=dev)
+        xc = O.make_x_cond(xs, cm, torch.randn(xs.shape, device=dev))
+        with torch.no_grad():
+            for i in range(3):
+                x = O.p_sample(params, sched, x, N - 1 - i, xc, torch.randn(xs.shape, device=dev))
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(n_steps):
+                x = O.p_sample(params, sched, x, N - 4 - i, xc, torch.randn(xs.shape, device=dev))
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n_steps
+        out[tag] = {"windows_per_s": B / (ms * 1e-3 * N), "ms_per_denoiser_step": ms}
+    O.USE_CONV1D = False
+    out["kind"] = (f"oracle port (reference op sequence) in PyTorch eager on the same GPU, B={B}, {n_steps} steps timed with CUDA events, "
+                   "scaled to 1000 steps; conv1d variant = reference's Conv1d k=1 layers via cuDNN with stock TF32 flags")
+    return out
+
+
 def main():
     a = parse()
     os.environ.setdefault("TQDM_DISABLE", "1")
@@ -245,6 +277,13 @@ def main():
                      "scope": "whole sampling path (algorithmic FLOPs 2.8507 TFLOP per 1000-step window / wall time per GPU)"},
     }
     line["cpu_baseline"] = cpu_baseline(32, T, N, a.cpu_seconds)
+    if world == 1 and not os.environ.get("EGOEGO_BENCH_SKIP_TORCH"):
+        del m
+        torch.cuda.empty_cache()
+        try:
+            line["torch_gpu_baseline"] = torch_gpu_baseline(dev, B, T, N)
+        except Exception as ex:   # reported baseline only; never masks the product numbers
+            line["torch_gpu_baseline"] = {"error": repr(ex)[:200]}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -123,6 +123,11 @@ class TransformerDiffusionModel(nn.Module):
         self.time_mlp = nn.Sequential(nn.Identity(), nn.Linear(dim, dim * 4), nn.GELU(), nn.Linear(dim * 4, d_model))
         self._owner = None  # set by CondGaussianDiffusion (plain attribute, not a submodule)
 
+    def __getstate__(self):                       # the back-reference is re-bound by the owner's __setstate__
+        st = dict(self.__dict__)
+        st["_owner"] = None
+        return st
+
     def forward(self, src, noise_t, padding_mask=None):
         owner = object.__getattribute__(self, "_owner")
         if owner is None:
@@ -187,6 +192,7 @@ class CondGaussianDiffusion(nn.Module):
         self._weights_sig = None
         self._skeleton_sig = None
         self._noise_tape = None   # parity mode: explicit [n_draws, B, T, D] tape consumed by the next sample()
+        self._tape_keepalive = None
 
     # ------------------------------------------------------------------------------------------
     # engine plumbing
@@ -197,6 +203,19 @@ class CondGaussianDiffusion(nn.Module):
                 _capi.lib().egoego_destroy(self._h)
         except Exception:
             pass
+
+    # engine handles are process-local: drop them when the module is pickled / deep-copied (ema_pytorch.EMA
+    # deep-copies the model, trainer_amass_cond_motion_diffusion.py:58) and re-create lazily in the copy
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        for k in ("_h", "_h_device", "_weights_sig", "_skeleton_sig", "_noise_tape", "_tape_keepalive"):
+            st[k] = None
+        return st
+
+    def __setstate__(self, st):
+        super().__setstate__(st)
+        import weakref
+        object.__setattr__(self.denoise_fn, "_owner", weakref.ref(self))
 
     def _device(self) -> torch.device:
         dev = self.betas.device

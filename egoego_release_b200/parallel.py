@@ -1,0 +1,55 @@
+"""Batch-sharded sampling across the GPUs of one box.
+
+Windows are independent, so the only communication of the path is ONE all-gather of the finished windows; the
+sampling loop itself contains no collective.  Each rank draws its noise from Philox streams keyed by the GLOBAL
+window id (``window_offset``), so the gathered result equals the single-GPU run of the global batch window for window.
+One process per GPU, ``torch.distributed`` (NCCL on GPUs, gloo in the CPU tests) for the plumbing."""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(global_batch: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous shard [start, start+count) of ``global_batch`` windows for ``rank`` (remainder spread over the first ranks)."""
+    base, rem = divmod(global_batch, world)
+    count = base + (1 if rank < rem else 0)
+    start = rank * base + min(rank, rem)
+    return start, count
+
+
+def sample_sharded(sample_fn: Callable[[torch.Tensor, torch.Tensor, int], torch.Tensor], x_start: torch.Tensor,
+                   cond_mask: torch.Tensor, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """``x_start`` / ``cond_mask`` hold the GLOBAL batch on every rank; each rank samples its shard with
+    ``sample_fn(x_shard, mask_shard, window_offset)`` and all ranks return the full [B, T, D] result."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    B = x_start.shape[0]
+    start, count = shard_range(B, world, rank)
+    local = sample_fn(x_start[start:start + count], cond_mask[start:start + count], start)
+    if world == 1:
+        return local
+    if B % world == 0:
+        out = torch.empty((B,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+        return out
+    # ragged shards: pad to the largest shard, gather, then strip
+    mx = shard_range(B, world, 0)[1]
+    pad = torch.zeros((mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[:count] = local
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad, group=group)
+    return torch.cat([bufs[r][:shard_range(B, world, r)[1]] for r in range(world)], dim=0)
+
+
+def model_sample_fn(model) -> Callable[[torch.Tensor, torch.Tensor, int], torch.Tensor]:
+    """Adapter: CondGaussianDiffusion.sample with Philox streams keyed by the global window id."""
+    def fn(xs, cm, offset):
+        model.window_offset = int(offset)
+        try:
+            return model.sample(xs, cm)
+        finally:
+            model.window_offset = 0
+    return fn

@@ -77,3 +77,15 @@ def test_condition_mask_glue():
     assert torch.equal(E.prep_head_condition_mask(d), O.prep_head_condition_mask(d.shape))
     pm = E.prep_padding_mask(d, torch.tensor([120, 60]))
     assert pm.shape == (2, 1, 121) and pm[1, 0].sum() == 61
+
+
+def test_mirror_survives_deepcopy_and_pickle():
+    """ema_pytorch.EMA deep-copies the model (trainer_amass_cond_motion_diffusion.py:58): engine handles must not travel."""
+    import copy
+    import pickle
+    import egoego_release_b200 as E
+    m = E.CondGaussianDiffusion(d_feats=198, d_model=512, n_dec_layers=4, n_head=4, d_k=256, d_v=256,
+                                max_timesteps=121, out_dim=198, timesteps=10, objective="pred_x0")
+    for c in (copy.deepcopy(m), pickle.loads(pickle.dumps(m))):
+        assert c.denoise_fn._owner() is c and c._h is None
+        assert set(c.state_dict()) == set(m.state_dict())

@@ -1,0 +1,63 @@
+"""Host-side logic of the N>1 path on CPU: world_size-2 gloo processes shard a batch by global window id and
+all-gather the finished windows; the result must equal the single-process run (sampler replaced by a deterministic
+function of the global window id -- the CUDA engine itself is covered by the -m gpu tests)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from egoego_release_b200.parallel import sample_sharded, shard_range
+
+
+def _fake_sample(xs, cm, offset):
+    ids = torch.arange(offset, offset + xs.shape[0], dtype=torch.float32).view(-1, 1, 1)
+    return xs * (1 - cm) + cm * torch.sin(ids + torch.arange(xs.shape[2]).float().view(1, 1, -1))
+
+
+def _worker(rank, world, port, B, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(0)
+    xs = torch.randn(B, 6, 198, generator=g)
+    cm = (torch.rand(B, 6, 198, generator=g) > 0.5).float()
+    out = sample_sharded(_fake_sample, xs, cm)
+    if rank == 0:
+        q.put(out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("B", [8, 7])
+def test_sharded_sampling_equals_single_process(B):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, B, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    g = torch.Generator().manual_seed(0)
+    xs = torch.randn(B, 6, 198, generator=g)
+    cm = (torch.rand(B, 6, 198, generator=g) > 0.5).float()
+    assert torch.equal(out, _fake_sample(xs, cm, 0))
+
+
+def test_shard_range_partitions():
+    for B in (1, 7, 8, 256, 2048):
+        for world in (1, 2, 3, 4, 8):
+            spans = [shard_range(B, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and sum(c for _, c in spans) == B
+            for (s0, c0), (s1, _) in zip(spans, spans[1:]):
+                assert s0 + c0 == s1
