@@ -59,7 +59,7 @@ def lib():
     L.egoego_postprocess.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp]
     L.egoego_fk_smpl.argtypes = [vp, vp, vp, i64, vp, vp, vp]
     L.egoego_canonicalize_head.argtypes = [vp, vp, vp, i64, i32, i32, vp, vp, vp]
-    L.egoego_selftest_gemm.argtypes = [i32, i32, i32, i32, u64, vp, vp, vp]
+    L.egoego_selftest_gemm.argtypes = [i32, i32, i32, i32, u64, i32, vp, vp, vp]
     L.egoego_launch_count.argtypes = [vp]
     L.egoego_launch_count.restype = i64
     for name in EXPORTS:

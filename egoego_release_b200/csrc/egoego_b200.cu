@@ -640,12 +640,12 @@ int egoego_canonicalize_head(egoego_handle c, const float* head_pos, const float
 
 int64_t egoego_launch_count(egoego_handle c) { return c ? c->launches : -1; }
 
-int egoego_selftest_gemm(int device, int M, int N, int K, uint64_t seed, float* max_abs_err, float* max_abs_ref, float* ms) {
+int egoego_selftest_gemm(int device, int M, int N, int K, uint64_t seed, int two_cta, float* max_abs_err, float* max_abs_ref, float* ms) {
     EG_CHECK(max_abs_err && max_abs_ref && ms, "null argument");
     int ndev = 0;
     EG_CHECK(cudaGetDeviceCount(&ndev) == cudaSuccess && device >= 0 && device < ndev, "no such CUDA device");
     EG_CUDA(cudaSetDevice(device));
-    return selftest_gemm(M, N, K, seed, max_abs_err, max_abs_ref, ms);
+    return selftest_gemm(M, N, K, seed, two_cta, max_abs_err, max_abs_ref, ms);
 }
 
 }  // extern "C"

@@ -44,6 +44,7 @@ static int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t co
 struct Plane {                 // a bf16 hi/lo pair with its TMA maps
     __nv_bfloat16 *hi = nullptr, *lo = nullptr;
     CUtensorMap mhi, mlo;
+    CUtensorMap mhi128, mlo128;     // 128-row boxes (per-CTA half of a W tile in the 2-CTA GEMM)
     size_t rows = 0, cols = 0;
     int alloc(size_t r, size_t c, uint32_t box_rows) {
         rows = r; cols = c;
@@ -52,6 +53,7 @@ struct Plane {                 // a bf16 hi/lo pair with its TMA maps
         EG_CUDA(cudaMemset(hi, 0, r * c * 2));
         EG_CUDA(cudaMemset(lo, 0, r * c * 2));
         if (make_map(&mhi, hi, r, c, box_rows) || make_map(&mlo, lo, r, c, box_rows)) return 1;
+        if (make_map(&mhi128, hi, r, c, 128) || make_map(&mlo128, lo, r, c, 128)) return 1;
         return 0;
     }
     void release() { if (hi) cudaFree(hi); if (lo) cudaFree(lo); hi = lo = nullptr; }
@@ -94,6 +96,8 @@ struct TcImpl {
     }
 };
 
+static inline int Mr(int B) { return ((B + 1) / 2) * 2 * LP; }
+
 template <int BN, class Epi>
 static int launch_gemm(TcImpl* I, const Plane& A, const Plane& W, int M, int N, int K, const Epi& epi, cudaStream_t s) {
     using Cfg = GemmCfg<BN>;
@@ -111,6 +115,41 @@ static int launch_gemm(TcImpl* I, const Plane& A, const Plane& W, int M, int N, 
     return 0;
 }
 
+static bool use_2cta() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("EGOEGO_GEMM"); v = (e && strcmp(e, "1cta") == 0) ? 0 : 1; }
+    return v == 1;
+}
+
+// 2-CTA (cluster of 2, cta_group::2) launch: 256 x 256 tiles per CTA pair.
+template <class Epi>
+static int launch_gemm_2cta(TcImpl* I, const Plane& A, const Plane& W, int M, int N, int K, const Epi& epi, cudaStream_t s) {
+    static bool attr_set = false;
+    auto kern = gemm_split3_2cta_kernel<Epi>;
+    if (!attr_set) {
+        EG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_BYTES));
+        attr_set = true;
+    }
+    EG_CHECK(M % 256 == 0 && N % 256 == 0 && K % GEMM_BK == 0, "2-CTA gemm shape not tile-aligned");
+    const int tiles = (M / 256) * (N / 256);
+    int pairs = I->sms / 2;
+    if (tiles < pairs) pairs = tiles;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = GEMM2_SMEM_BYTES; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    EG_CUDA(cudaLaunchKernelEx(&cfg, kern, A.mhi, A.mlo, W.mhi128, W.mlo128, M, N, K, epi));
+    return 0;
+}
+
+template <class Epi>
+static int gemm(TcImpl* I, const Plane& A, const Plane& W, int M, int N, int K, const Epi& epi, cudaStream_t s) {
+    if (use_2cta() && M % 256 == 0) return launch_gemm_2cta(I, A, W, M, N, K, epi, s);
+    return launch_gemm<256>(I, A, W, M, N, K, epi, s);
+}
+
 TcEngine::TcEngine() : impl_(nullptr) {}
 TcEngine::~TcEngine() { delete impl_; }
 
@@ -124,7 +163,7 @@ int TcEngine::init(const TcWeights& w, cudaStream_t) {
     int dev = 0;
     EG_CUDA(cudaGetDevice(&dev));
     EG_CUDA(cudaDeviceGetAttribute(&I->sms, cudaDevAttrMultiProcessorCount, dev));
-    I->M = w.max_batch * LP;
+    I->M = ((w.max_batch + 1) / 2) * 2 * LP;          // even number of windows: 2-CTA tiles cover 256 rows
     I->kx = ((D + 63) / 64) * 64;                 // 198 -> 256
     I->nout = ((D + 255) / 256) * 256;            // 198 -> 256 (zero rows)
     const size_t M = I->M;
@@ -156,8 +195,9 @@ int TcEngine::init(const TcWeights& w, cudaStream_t) {
     const char* am = getenv("EGOEGO_ATTN");
     I->attn_tc = !(am && strcmp(am, "simt") == 0);
     if (I->attn_tc) {
-        if (I->Qp.alloc((size_t)w.max_batch * H * 128, 256, 128) || I->Kp.alloc((size_t)w.max_batch * H * 128, 256, 128) ||
-            I->VT.alloc((size_t)w.max_batch * H * 256, 128, 256)) return 1;
+        const size_t MBe = (size_t)((w.max_batch + 1) / 2) * 2;
+        if (I->Qp.alloc(MBe * H * 128, 256, 128) || I->Kp.alloc(MBe * H * 128, 256, 128) ||
+            I->VT.alloc(MBe * H * 256, 128, 256)) return 1;
         EG_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
     } else {
         EG_CUDA(cudaMalloc(&I->QKV, M * 3 * H * dk * 4));
@@ -187,7 +227,7 @@ int TcEngine::stage(const float* src, int src_ld, int src_col0, bool cond_half, 
 int TcEngine::prepare_cond(int B, int T, cudaStream_t s, int64_t* n) {
     TcImpl* I = impl_;
     TcEpiBase e{I->base, I->w.d, I->w.start_b, I->w.pos, T};
-    if (launch_gemm<256>(I, I->C, I->Wc, B * LP, I->w.d, I->kx, e, s)) return 1;
+    if (gemm(I, I->C, I->Wc, Mr(B), I->w.d, I->kx, e, s)) return 1;
     *n += 1;
     return 0;
 }
@@ -201,36 +241,37 @@ int TcEngine::launches_per_denoiser() const { return 2 + 7 * impl_->w.NL; }
 int TcEngine::denoiser(int B, int T, TSrc ts, const float* pmask, float* model_out, cudaStream_t s, int64_t* n) {
     TcImpl* I = impl_;
     const int M = B * LP, d = I->w.d, H = I->w.H, dk = I->w.dk, L = T + 1;
+    const int Mg = Mr(B);                          // GEMM rows: whole 256-row tiles (an odd window count is rounded up)
     const int nqkv = 3 * H * dk;
     {
-        TcEpiStart e{I->H, I->Hs.hi, I->Hs.lo, d, I->base, I->w.pos, I->w.temb, ts, T};
-        if (launch_gemm<256>(I, I->X, I->Wx, M, d, I->kx, e, s)) return 1;
+        TcEpiStart e{I->H, I->Hs.hi, I->Hs.lo, d, I->base, I->w.pos, I->w.temb, ts, T, B};
+        if (gemm(I, I->X, I->Wx, Mg, d, I->kx, e, s)) return 1;
     }
     for (int l = 0; l < I->w.NL; ++l) {
         TcLayer& W = I->layers[l];
         if (I->attn_tc) {
             TcEpiQKVPlanes eq{I->Qp.hi, I->Qp.lo, I->Kp.hi, I->Kp.lo, I->VT.hi, I->VT.lo, W.bqkv, H, 1.0f / sqrtf((float)dk)};
-            if (launch_gemm<256>(I, I->Hs, W.wqkv, M, nqkv, d, eq, s)) return 1;
+            if (gemm(I, I->Hs, W.wqkv, Mg, nqkv, d, eq, s)) return 1;
             const int items = B * H;
             attention_tc_kernel<<<items < I->sms ? items : I->sms, ATT_THREADS, ATT_SMEM_BYTES, s>>>(
                 I->Qp.mhi, I->Qp.mlo, I->Kp.mhi, I->Kp.mlo, I->VT.mhi, I->VT.mlo, I->O.hi, I->O.lo, H * dk, items, H, L);
         } else {
             TcEpiBiasScaleF32 eq{I->QKV, nqkv, W.bqkv, H * dk, 1.0f / sqrtf((float)dk)};
-            if (launch_gemm<256>(I, I->Hs, W.wqkv, M, nqkv, d, eq, s)) return 1;
+            if (gemm(I, I->Hs, W.wqkv, Mg, nqkv, d, eq, s)) return 1;
             attention_simt_kernel<true><<<B * H, 256, ATT_SIMT_SMEM, s>>>(I->QKV, nqkv, nullptr, I->O.hi, I->O.lo, H * dk, H, L);
         }
         TcEpiBiasResidF32 ef{I->Y, d, W.fc_b, I->H};
-        if (launch_gemm<256>(I, I->O, W.fc, M, d, H * dk, ef, s)) return 1;
+        if (gemm(I, I->O, W.fc, Mg, d, H * dk, ef, s)) return 1;
         layernorm512_kernel<<<M / 8, 256, 0, s>>>(I->Y, I->H, I->Hs.hi, I->Hs.lo, W.ln1_g, W.ln1_b, pmask, T, M);
         TcEpiBiasReluSplit e1{I->F.hi, I->F.lo, d, W.b1};
-        if (launch_gemm<256>(I, I->Hs, W.w1, M, d, d, e1, s)) return 1;
+        if (gemm(I, I->Hs, W.w1, Mg, d, d, e1, s)) return 1;
         TcEpiBiasResidF32 e2{I->Y, d, W.b2, I->H};
-        if (launch_gemm<256>(I, I->F, W.w2, M, d, d, e2, s)) return 1;
+        if (gemm(I, I->F, W.w2, Mg, d, d, e2, s)) return 1;
         layernorm512_kernel<<<M / 8, 256, 0, s>>>(I->Y, I->H, I->Hs.hi, I->Hs.lo, W.ln2_g, W.ln2_b, pmask, T, M);
     }
     {
-        TcEpiOut eo{model_out, I->w.D, I->w.out_b, T};
-        if (launch_gemm<256>(I, I->Hs, I->Wout, M, I->nout, d, eo, s)) return 1;
+        TcEpiOut eo{model_out, I->w.D, I->w.out_b, T, B};
+        if (gemm(I, I->Hs, I->Wout, Mg, I->nout, d, eo, s)) return 1;
     }
     EG_CUDA(cudaGetLastError());
     *n += launches_per_denoiser();
@@ -260,7 +301,7 @@ __global__ void maxdiff_kernel(const float* a, const float* b, long long n, floa
 
 struct EpiStore { float* C; int ldc; __device__ void operator()(int r, int c, float a) const { C[(long long)r * ldc + c] = a; } };
 
-int selftest_gemm(int M, int N, int K, unsigned long long seed, float* max_abs_err, float* max_abs_ref, float* ms) {
+int selftest_gemm(int M, int N, int K, unsigned long long seed, int two_cta, float* max_abs_err, float* max_abs_ref, float* ms) {
     EG_CHECK(M % 128 == 0 && N % 256 == 0 && K % 64 == 0, "selftest_gemm: need M%128==0, N%256==0, K%64==0");
     TcImpl I;
     int dev = 0;
@@ -279,11 +320,13 @@ int selftest_gemm(int M, int N, int K, unsigned long long seed, float* max_abs_e
     TcEpiPlain e{C1, N, nullptr, N};
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
-    if (launch_gemm<256>(&I, PA, PW, M, N, K, e, 0)) return 1;
+    EG_CHECK(!two_cta || M % 256 == 0, "2-CTA self test needs M % 256 == 0");
+    auto run = [&]() -> int { return two_cta ? launch_gemm_2cta(&I, PA, PW, M, N, K, e, 0) : launch_gemm<256>(&I, PA, PW, M, N, K, e, 0); };
+    if (run()) return 1;
     EG_CUDA(cudaDeviceSynchronize());
     cudaEventRecord(e0);
     const int reps = 5;
-    for (int r = 0; r < reps; ++r) if (launch_gemm<256>(&I, PA, PW, M, N, K, e, 0)) return 1;
+    for (int r = 0; r < reps; ++r) if (run()) return 1;
     cudaEventRecord(e1);
     EG_CUDA(cudaDeviceSynchronize());
     float t = 0.f; cudaEventElapsedTime(&t, e0, e1); *ms = t / reps;

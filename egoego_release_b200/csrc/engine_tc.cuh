@@ -44,6 +44,6 @@ private:
 };
 
 // tcgen05 split GEMM vs fp32 SIMT GEMM on random data (C = A W^T, no epilogue); returns max |err|, max |ref|, ms/launch.
-int selftest_gemm(int M, int N, int K, unsigned long long seed, float* max_abs_err, float* max_abs_ref, float* ms);
+int selftest_gemm(int M, int N, int K, unsigned long long seed, int two_cta, float* max_abs_err, float* max_abs_ref, float* ms);
 
 }  // namespace egoego

@@ -80,9 +80,10 @@ struct TcEpiBase {                        // base = x_cond-half of start_conv + 
 
 struct TcEpiStart {                       // H = x-half GEMM + base ; row 0 = time token ; writes fp32 + hi/lo planes
     float* H; __nv_bfloat16* Hhi; __nv_bfloat16* Hlo; int ld;
-    const float* base; const float* pos; const float* temb; TSrc ts; int T;
+    const float* base; const float* pos; const float* temb; TSrc ts; int T; int n_windows;
     __device__ __forceinline__ void operator()(int row, int col0, const float (&v)[32]) const {
-        const int w = row / LP, l = row % LP;
+        const int w = row / LP;
+        const int l = (w < n_windows) ? row % LP : LP;      // rows of the rounding-up window are padding
         float r[32];
         if (l == 0) {
             const float* te = temb + (long long)ts.get(w) * ld + col0;
@@ -144,10 +145,10 @@ struct TcEpiBiasReluSplit {               // w_1: relu(acc + bias) -> bf16 hi/lo
 };
 
 struct TcEpiOut {                         // linear_out: tokens 1..T, first d_feats columns -> compact [B,T,d_feats]
-    float* out; int d_feats; const float* bias; int T;
+    float* out; int d_feats; const float* bias; int T; int n_windows;
     __device__ __forceinline__ void operator()(int row, int col0, const float (&v)[32]) const {
         const int w = row / LP, l = row % LP;
-        if (l < 1 || l > T) return;
+        if (l < 1 || l > T || w >= n_windows) return;
         float* o = out + ((long long)w * T + (l - 1)) * d_feats;
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
@@ -271,6 +272,133 @@ gemm_split3_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constan
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, 512); }
+}
+
+// ---- 2-CTA variant: CTA pairs (cluster of 2) share the W tile ---------------------------------------
+// One pair computes a 256 x 256 output tile with tcgen05.mma.cta_group::2 (M = 256): each CTA stages its own
+// 128 A rows (hi+lo) and HALF of the W tile (128 of the 256 N rows, hi+lo), so operand traffic per CTA drops
+// from 96 KB to 64 KB per k-block and three stages fit in shared memory.  The leader (even) CTA issues the
+// MMAs for the pair; TMA completions of both CTAs are credited to the leader's `full` barrier; `empty` and
+// `tmem_full` are signalled to both CTAs by a multicast tcgen05.commit; the epilogues of both CTAs release the
+// accumulator through remote arrives on the leader's `tmem_empty` barrier.
+constexpr int GEMM2_STAGES = 3;
+constexpr int GEMM2_STAGE_BYTES = 4 * GEMM_BM * GEMM_BK * 2;      // A_hi A_lo Whalf_hi Whalf_lo, 16 KB each
+constexpr int GEMM2_SMEM_BYTES = GEMM2_STAGES * GEMM2_STAGE_BYTES + 1024 + 256;
+
+template <class Epi>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_split3_2cta_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl,
+                        const __grid_constant__ CUtensorMap mWh, const __grid_constant__ CUtensorMap mWl,   // W maps: 128-row boxes
+                        int M, int N, int K, Epi epi) {
+    constexpr int BN = 256;
+    constexpr int T_BYTES = GEMM_BM * GEMM_BK * 2;                   // 16 KB tile
+    constexpr uint32_t IDESC = ptx::make_idesc_bf16(256, BN);
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GEMM2_STAGES * GEMM2_STAGE_BYTES);
+    uint64_t* full_bar = bars;                          // [S]  (used on the leader)
+    uint64_t* empty_bar = bars + GEMM2_STAGES;          // [S]  (both CTAs)
+    uint64_t* tfull_bar = bars + 2 * GEMM2_STAGES;      // [2]  (both CTAs)
+    uint64_t* tempty_bar = bars + 2 * GEMM2_STAGES + 2; // [2]  (used on the leader)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * GEMM2_STAGES + 4);
+
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const uint32_t rank = ptx::cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair = blockIdx.x / 2, n_pairs = gridDim.x / 2;
+    const int m_tiles = M / 256, n_tiles = N / BN, k_blocks = K / GEMM_BK;
+    const int total_tiles = m_tiles * n_tiles;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&mAh); ptx::prefetch_tmap(&mAl); ptx::prefetch_tmap(&mWh); ptx::prefetch_tmap(&mWl);
+        for (int s = 0; s < GEMM2_STAGES; ++s) { ptx::mbar_init(&full_bar[s], 2); ptx::mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], 8); }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) { ptx::tmem_alloc_2cta(tmem_slot, 512); ptx::tmem_relinquish_2cta(); }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync();                                 // peer's barriers are initialised before any remote arrive
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {                                 // ===== TMA producer (both CTAs) =====
+            int s = 0; uint32_t ph = 0;
+            for (int tile = pair; tile < total_tiles; tile += n_pairs) {
+                const int m0 = (tile / n_tiles) * 256 + (int)rank * 128;
+                const int n0 = (tile % n_tiles) * BN + (int)rank * 128;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+                    uint8_t* st = smem + s * GEMM2_STAGE_BYTES;
+                    if (leader) ptx::mbar_arrive_expect_tx(&full_bar[s], 2 * GEMM2_STAGE_BYTES);
+                    else        ptx::mbar_arrive_cluster(&full_bar[s], 0);
+                    ptx::tma_load_2d_2cta(st, &mAh, &full_bar[s], kb * GEMM_BK, m0);
+                    ptx::tma_load_2d_2cta(st + T_BYTES, &mAl, &full_bar[s], kb * GEMM_BK, m0);
+                    ptx::tma_load_2d_2cta(st + 2 * T_BYTES, &mWh, &full_bar[s], kb * GEMM_BK, n0);
+                    ptx::tma_load_2d_2cta(st + 3 * T_BYTES, &mWl, &full_bar[s], kb * GEMM_BK, n0);
+                    if (++s == GEMM2_STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && leader) {                       // ===== MMA issuer (leader CTA only) =====
+            int s = 0; uint32_t ph = 0; int it = 0;
+            for (int tile = pair; tile < total_tiles; tile += n_pairs, ++it) {
+                const int a = it & 1;
+                const uint32_t aph = (it >> 1) & 1;
+                ptx::mbar_wait(&tempty_bar[a], aph ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + a * BN;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    ptx::mbar_wait(&full_bar[s], ph);
+                    ptx::tc_fence_after();
+                    const uint32_t st = ptx::smem_u32(smem + s * GEMM2_STAGE_BYTES);
+                    const uint64_t dAh = ptx::make_smem_desc_sw128(st), dAl = ptx::make_smem_desc_sw128(st + T_BYTES);
+                    const uint64_t dWh = ptx::make_smem_desc_sw128(st + 2 * T_BYTES), dWl = ptx::make_smem_desc_sw128(st + 3 * T_BYTES);
+#pragma unroll
+                    for (int kk = 0; kk < GEMM_BK / 16; ++kk) {
+                        const uint64_t adv = (uint64_t)(kk * 2);
+                        ptx::umma_f16_2cta(d_tmem, dAh + adv, dWh + adv, IDESC, (kb | kk) != 0);
+                        ptx::umma_f16_2cta(d_tmem, dAh + adv, dWl + adv, IDESC, 1);
+                        ptx::umma_f16_2cta(d_tmem, dAl + adv, dWh + adv, IDESC, 1);
+                    }
+                    ptx::umma_commit_2cta(&empty_bar[s]);
+                    if (++s == GEMM2_STAGES) { s = 0; ph ^= 1; }
+                }
+                ptx::umma_commit_2cta(&tfull_bar[a]);
+            }
+        }
+    } else {                                             // ===== epilogue warps 2..5 (both CTAs) =====
+        const int quarter = warp & 3;
+        int it = 0;
+        for (int tile = pair; tile < total_tiles; tile += n_pairs, ++it) {
+            const int a = it & 1;
+            const uint32_t aph = (it >> 1) & 1;
+            const int m0 = (tile / n_tiles) * 256 + (int)rank * 128, n0 = (tile % n_tiles) * BN;
+            ptx::mbar_wait(&tfull_bar[a], aph);
+            ptx::tc_fence_after();
+            const int row = m0 + quarter * 32 + lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * BN;
+#pragma unroll 1
+            for (int c = 0; c < BN; c += 32) {
+                uint32_t r[32];
+                ptx::tmem_ld_32x32(taddr + c, r);
+                ptx::tmem_ld_wait();
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                epi(row, n0 + c, v);
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(&tempty_bar[a], 0);
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync();                                 // nobody leaves while the peer may still touch its smem / TMEM
+    if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc_2cta(tmem_base, 512); }
 }
 
 }  // namespace egoego

@@ -152,9 +152,10 @@ int64_t egoego_launch_count(egoego_handle h);
 
 /* Self test of the tensor-core GEMM primitive: C = A W^T (A[M,K], W[N,K] random fp32) computed by the
  * tcgen05 3-term bf16-split kernel and by the fp32 CUDA-core kernel; reports max |difference|, max |reference|
- * and the average device time of one tcgen05 launch in milliseconds.  M%128 == N%256 == K%64 == 0. */
-int  egoego_selftest_gemm(int device, int M, int N, int K, uint64_t seed, float* max_abs_err, float* max_abs_ref,
-                          float* ms_per_launch);
+ * and the average device time of one tcgen05 launch in milliseconds.  M%128 == N%256 == K%64 == 0.
+ * two_cta != 0 selects the CTA-pair kernel (cta_group::2, 256x256 tiles; needs M%256 == 0). */
+int  egoego_selftest_gemm(int device, int M, int N, int K, uint64_t seed, int two_cta, float* max_abs_err,
+                          float* max_abs_ref, float* ms_per_launch);
 
 #ifdef __cplusplus
 }
