@@ -19,7 +19,7 @@ ENGINE_TCGEN05, ENGINE_SIMT = 0, 1
 class Cfg(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "d_feats", "d_model", "n_head", "n_dec_layers", "d_k", "d_v", "max_timesteps", "timesteps",
-        "objective", "max_batch", "device", "engine")]
+        "objective", "max_batch", "device", "engine", "precise_last_steps")]
 
 
 class Rng(C.Structure):
@@ -59,7 +59,7 @@ def lib():
     L.egoego_postprocess.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp]
     L.egoego_fk_smpl.argtypes = [vp, vp, vp, i64, vp, vp, vp]
     L.egoego_canonicalize_head.argtypes = [vp, vp, vp, i64, i32, i32, vp, vp, vp]
-    L.egoego_selftest_gemm.argtypes = [i32, i32, i32, i32, u64, i32, vp, vp, vp]
+    L.egoego_selftest_gemm.argtypes = [i32, i32, i32, i32, u64, i32, i32, vp, vp, vp]
     L.egoego_launch_count.argtypes = [vp]
     L.egoego_launch_count.restype = i64
     for name in EXPORTS:

@@ -13,6 +13,7 @@
 //   warps 2-5 softmax (TMEM -> registers -> P hi/lo into swizzled smem) and O epilogue (TMEM -> bf16 hi/lo planes)
 // TMEM: S at columns [0,128), O at [128,384).
 #pragma once
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include "gemm_tcgen05.cuh"
@@ -25,14 +26,17 @@ constexpr int ATT_P_BYTES = 2 * 2 * 128 * 128;          // hi/lo x 2 key blocks 
 constexpr int ATT_SMEM_BYTES = ATT_STAGES * ATT_STAGE_BYTES + ATT_P_BYTES + 1024 + 256;
 constexpr int ATT_THREADS = 192;
 
+template <int FMT>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_constant__ CUtensorMap mQl,
                     const __grid_constant__ CUtensorMap mKh, const __grid_constant__ CUtensorMap mKl,
                     const __grid_constant__ CUtensorMap mVh, const __grid_constant__ CUtensorMap mVl,
                     __nv_bfloat16* __restrict__ Ohi, __nv_bfloat16* __restrict__ Olo, int ldo,
                     int n_items, int n_head, int L) {
-    constexpr uint32_t IDESC_S = ptx::make_idesc_bf16(128, 128);
-    constexpr uint32_t IDESC_O = ptx::make_idesc_bf16(128, 256);
+    constexpr int NP = FmtTraits<FMT>::NP;            // FMT_HALF: single fp16 plane per operand, one MMA per k-step
+    constexpr uint32_t IDESC_S = (FMT == FMT_SPLIT) ? ptx::make_idesc_bf16(128, 128) : ptx::make_idesc_f16(128, 128);
+    constexpr uint32_t IDESC_O = (FMT == FMT_SPLIT) ? ptx::make_idesc_bf16(128, 256) : ptx::make_idesc_f16(128, 256);
+    constexpr uint32_t QK_BYTES = NP * 2 * 16384, V_BYTES = NP * 32768;
     constexpr uint32_t TM_S = 0, TM_O = 128;
 
     extern __shared__ uint8_t smem_raw[];
@@ -69,19 +73,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_consta
                 for (int kb = 0; kb < 4; ++kb) {           // Q/K k-blocks of 64 dims: Qh Ql Kh Kl (16 KB each)
                     ptx::mbar_wait(&empty_bar[s], ph ^ 1);
                     uint8_t* st = smem + s * ATT_STAGE_BYTES;
-                    ptx::mbar_arrive_expect_tx(&full_bar[s], ATT_STAGE_BYTES);
+                    ptx::mbar_arrive_expect_tx(&full_bar[s], QK_BYTES);
                     ptx::tma_load_2d(st, &mQh, &full_bar[s], kb * 64, item * 128);
-                    ptx::tma_load_2d(st + 16384, &mQl, &full_bar[s], kb * 64, item * 128);
+                    if (NP == 2) ptx::tma_load_2d(st + 16384, &mQl, &full_bar[s], kb * 64, item * 128);
                     ptx::tma_load_2d(st + 32768, &mKh, &full_bar[s], kb * 64, item * 128);
-                    ptx::tma_load_2d(st + 49152, &mKl, &full_bar[s], kb * 64, item * 128);
+                    if (NP == 2) ptx::tma_load_2d(st + 49152, &mKl, &full_bar[s], kb * 64, item * 128);
                     if (++s == ATT_STAGES) { s = 0; ph ^= 1; }
                 }
                 for (int kb = 0; kb < 2; ++kb) {           // V^T k-blocks of 64 keys: Vh Vl (32 KB each)
                     ptx::mbar_wait(&empty_bar[s], ph ^ 1);
                     uint8_t* st = smem + s * ATT_STAGE_BYTES;
-                    ptx::mbar_arrive_expect_tx(&full_bar[s], ATT_STAGE_BYTES);
+                    ptx::mbar_arrive_expect_tx(&full_bar[s], V_BYTES);
                     ptx::tma_load_2d(st, &mVh, &full_bar[s], kb * 64, item * 256);
-                    ptx::tma_load_2d(st + 32768, &mVl, &full_bar[s], kb * 64, item * 256);
+                    if (NP == 2) ptx::tma_load_2d(st + 32768, &mVl, &full_bar[s], kb * 64, item * 256);
                     if (++s == ATT_STAGES) { s = 0; ph ^= 1; }
                 }
             }
@@ -101,8 +105,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_consta
                     for (int kk = 0; kk < 4; ++kk) {
                         const uint64_t adv = (uint64_t)(kk * 2);
                         ptx::umma_f16(tmem_base + TM_S, dQh + adv, dKh + adv, IDESC_S, (kb | kk) != 0);
-                        ptx::umma_f16(tmem_base + TM_S, dQh + adv, dKl + adv, IDESC_S, 1);
-                        ptx::umma_f16(tmem_base + TM_S, dQl + adv, dKh + adv, IDESC_S, 1);
+                        if (NP == 2) {
+                            ptx::umma_f16(tmem_base + TM_S, dQh + adv, dKl + adv, IDESC_S, 1);
+                            ptx::umma_f16(tmem_base + TM_S, dQl + adv, dKh + adv, IDESC_S, 1);
+                        }
                     }
                     ptx::umma_commit(&empty_bar[s]);
                     if (++s == ATT_STAGES) { s = 0; ph ^= 1; }
@@ -126,8 +132,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_consta
                     for (int kk = 0; kk < 4; ++kk) {
                         const uint64_t adv = (uint64_t)(kk * 2);
                         ptx::umma_f16(tmem_base + TM_O, dPh + adv, dVh + adv, IDESC_O, (kb | kk) != 0);
-                        ptx::umma_f16(tmem_base + TM_O, dPh + adv, dVl + adv, IDESC_O, 1);
-                        ptx::umma_f16(tmem_base + TM_O, dPl + adv, dVh + adv, IDESC_O, 1);
+                        if (NP == 2) {
+                            ptx::umma_f16(tmem_base + TM_O, dPh + adv, dVl + adv, IDESC_O, 1);
+                            ptx::umma_f16(tmem_base + TM_O, dPl + adv, dVh + adv, IDESC_O, 1);
+                        }
                     }
                     ptx::umma_commit(&empty_bar[s]);
                     if (++s == ATT_STAGES) { s = 0; ph ^= 1; }
@@ -168,16 +176,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_consta
                 uint32_t ph4[4], pl4[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    __nv_bfloat16 h0, l0, h1, l1;
-                    split_bf16(v[8 * j + 2 * q] * inv, h0, l0);
-                    split_bf16(v[8 * j + 2 * q + 1] * inv, h1, l1);
-                    __nv_bfloat162 hh(h0, h1), ll(l0, l1);
-                    ph4[q] = *reinterpret_cast<uint32_t*>(&hh); pl4[q] = *reinterpret_cast<uint32_t*>(&ll);
+                    if (FMT == FMT_SPLIT) {
+                        __nv_bfloat16 h0, l0, h1, l1;
+                        split_bf16(v[8 * j + 2 * q] * inv, h0, l0);
+                        split_bf16(v[8 * j + 2 * q + 1] * inv, h1, l1);
+                        __nv_bfloat162 hh(h0, h1), ll(l0, l1);
+                        ph4[q] = *reinterpret_cast<uint32_t*>(&hh); pl4[q] = *reinterpret_cast<uint32_t*>(&ll);
+                    } else {
+                        __half2 hh = __floats2half2_rn(v[8 * j + 2 * q] * inv, v[8 * j + 2 * q + 1] * inv);
+                        ph4[q] = *reinterpret_cast<uint32_t*>(&hh); pl4[q] = 0u;
+                    }
                 }
                 const int kb = j >> 3, chunk = (j & 7) ^ (r & 7);
                 uint8_t* dst = p_smem + kb * 16384 + r * 128 + chunk * 16;
                 *reinterpret_cast<uint4*>(dst) = make_uint4(ph4[0], ph4[1], ph4[2], ph4[3]);
-                *reinterpret_cast<uint4*>(dst + 2 * 16384) = make_uint4(pl4[0], pl4[1], pl4[2], pl4[3]);
+                if (FMT == FMT_SPLIT) *reinterpret_cast<uint4*>(dst + 2 * 16384) = make_uint4(pl4[0], pl4[1], pl4[2], pl4[3]);
             }
             ptx::fence_proxy_async();                      // generic-proxy smem writes -> visible to the tensor core
             ptx::tc_fence_before();
@@ -196,7 +209,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_consta
 #pragma unroll
                 for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(raw[j]);
 #pragma unroll
-                for (int j = 0; j < 32; j += 8) store_split8(Ohi + obase + c * 32 + j, Olo + obase + c * 32 + j, o + j);
+                for (int j = 0; j < 32; j += 8) store_planes8<FMT>(Ohi + obase + c * 32 + j, Olo + obase + c * 32 + j, o + j);
             }
             ptx::tc_fence_before();
             ptx::mbar_arrive(o_free);
@@ -208,6 +221,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_consta
 }
 
 // QKV projection epilogue writing the attention operand planes directly (one 256-wide tile = one (section, head)).
+template <int FMT>
 struct TcEpiQKVPlanes {
     __nv_bfloat16 *Qh, *Ql, *Kh, *Kl, *Vh, *Vl;       // Q,K: [(w*H+h)*128 + l][256];  V^T: [(w*H+h)*256 + c][128]
     const float* bias; int n_head; float q_scale;
@@ -222,10 +236,14 @@ struct TcEpiQKVPlanes {
             const long long base = ((long long)(w * n_head + h) * 256 + c0) * 128 + l;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                __nv_bfloat16 hi, lo;
-                split_bf16(r[j], hi, lo);
-                Vh[base + (long long)j * 128] = hi;
-                Vl[base + (long long)j * 128] = lo;
+                if (FMT == FMT_SPLIT) {
+                    __nv_bfloat16 hi, lo;
+                    split_bf16(r[j], hi, lo);
+                    Vh[base + (long long)j * 128] = hi;
+                    Vl[base + (long long)j * 128] = lo;
+                } else {
+                    reinterpret_cast<__half*>(Vh)[base + (long long)j * 128] = __float2half_rn(r[j]);
+                }
             }
         } else {
             __nv_bfloat16* ph = sec == 0 ? Qh : Kh;
@@ -236,7 +254,7 @@ struct TcEpiQKVPlanes {
             }
             const long long o = ((long long)(w * n_head + h) * 128 + l) * 256 + c0;
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) store_split8(ph + o + j, pl + o + j, r + j);
+            for (int j = 0; j < 32; j += 8) store_planes8<FMT>(ph + o + j, pl + o + j, r + j);
         }
     }
 };

@@ -58,7 +58,9 @@ struct egoego_ctx {
     Skeleton sk{}; bool have_sk = false;
     cudaStream_t own_stream = nullptr;
     cudaEvent_t ev_in = nullptr, ev_out = nullptr;
-    cudaGraphExec_t step_graph = nullptr; int graph_B = -1, graph_T = -1; const void* graph_key[4] = {nullptr};
+    cudaGraphExec_t step_graph[2] = {nullptr, nullptr};   // [FMT_SPLIT, FMT_HALF]
+    int graph_B = -1, graph_T = -1; const void* graph_key[4] = {nullptr};
+    int precise_last = 0;                  // steps t < precise_last use the 3-term split; earlier steps single-pass fp16
     bool use_graph = true;
     int64_t launches = 0;
     std::unique_ptr<TcEngine> tc;
@@ -87,13 +89,13 @@ static int denoiser_simt(egoego_ctx* c, int B, int T, TSrc ts, const float* pmas
         EpiBiasResid ef{c->Ybuf.as<float>(), d, w.fc_b.as<float>(), c->Hbuf.as<float>()};
         sgemm_tn_kernel<<<dim3(d / 128, M / 128), 256, 0, s>>>(c->Obuf.as<float>(), H * dk, w.fc_w.as<float>(), H * dk, d, H * dk, ef);
         layernorm512_kernel<<<M / 8, 256, 0, s>>>(c->Ybuf.as<float>(), c->Hbuf.as<float>(), nullptr, nullptr,
-                                                  w.ln1_g.as<float>(), w.ln1_b.as<float>(), pmask, T, M);
+                                                  w.ln1_g.as<float>(), w.ln1_b.as<float>(), pmask, T, M, 0);
         EpiBiasRelu e1{c->Fbuf.as<float>(), d, w.b1.as<float>()};
         sgemm_tn_kernel<<<dim3(d / 128, M / 128), 256, 0, s>>>(c->Hbuf.as<float>(), d, w.w1.as<float>(), d, d, d, e1);
         EpiBiasResid e2{c->Ybuf.as<float>(), d, w.b2.as<float>(), c->Hbuf.as<float>()};
         sgemm_tn_kernel<<<dim3(d / 128, M / 128), 256, 0, s>>>(c->Fbuf.as<float>(), d, w.w2.as<float>(), d, d, d, e2);
         layernorm512_kernel<<<M / 8, 256, 0, s>>>(c->Ybuf.as<float>(), c->Hbuf.as<float>(), nullptr, nullptr,
-                                                  w.ln2_g.as<float>(), w.ln2_b.as<float>(), pmask, T, M);
+                                                  w.ln2_g.as<float>(), w.ln2_b.as<float>(), pmask, T, M, 0);
         c->launches += 7;
     }
     {
@@ -105,10 +107,10 @@ static int denoiser_simt(egoego_ctx* c, int B, int T, TSrc ts, const float* pmas
     return 0;
 }
 
-static int run_denoiser(egoego_ctx* c, int B, int T, TSrc ts, const float* pmask, cudaStream_t s) {
+static int run_denoiser(egoego_ctx* c, int B, int T, TSrc ts, const float* pmask, cudaStream_t s, int fmt = 0) {
     if (c->cfg.engine == EGOEGO_ENGINE_SIMT) return denoiser_simt(c, B, T, ts, pmask, s);
     int64_t n = 0;
-    int rc = c->tc->denoiser(B, T, ts, pmask, c->model_out.as<float>(), s, &n);
+    int rc = c->tc->denoiser(B, T, ts, pmask, c->model_out.as<float>(), s, &n, fmt);
     c->launches += n;
     return rc;
 }
@@ -153,10 +155,10 @@ static void fill_ddpm(egoego_ctx* c, DdpmArgs& a, const float* x, float* x_out, 
     a.coef1 = c->coef1.as<float>(); a.coef2 = c->coef2.as<float>(); a.logvar = c->logvar.as<float>();
     a.sqrt_recip = c->sqrt_recip.as<float>(); a.sqrt_recipm1 = c->sqrt_recipm1.as<float>();
     a.objective = c->cfg.objective; a.clip = clip; a.inpaint = inpaint; a.inpaint_len = inpaint_len;
-    a.stage_f32 = nullptr; a.stage_ld = 0; a.stage_hi = nullptr; a.stage_lo = nullptr; a.stage_ld16 = 0;
+    a.stage_f32 = nullptr; a.stage_ld = 0; a.stage_hi = nullptr; a.stage_lo = nullptr; a.stage_ld16 = 0; a.stage_h16 = nullptr;
     if (stage_next) {
         if (c->cfg.engine == EGOEGO_ENGINE_SIMT) { a.stage_f32 = c->Ain.as<float>(); a.stage_ld = c->kin_pad; }
-        else c->tc->stage_targets(&a.stage_hi, &a.stage_lo, &a.stage_ld16);
+        else c->tc->stage_targets(&a.stage_hi, &a.stage_lo, &a.stage_h16, &a.stage_ld16);
     }
     a.ts = ts; a.ns = ns; a.B = B; a.T = T; a.D = c->D;
 }
@@ -207,6 +209,16 @@ int egoego_create(const egoego_cfg* cfg, egoego_handle* out) {
     c->layers.resize(c->NL);
     const char* g = getenv("EGOEGO_GRAPH");
     c->use_graph = !(g && g[0] == '0');
+    // precision policy: the last `precise_last` steps (t < precise_last) run the 3-term bf16 split,
+    // earlier steps a single fp16 pass.  cfg.precise_last_steps < 0 selects the default ceil(N/4); N = all precise.
+    {
+        int pl = cfg->precise_last_steps;
+        const char* e = getenv("EGOEGO_PRECISE_STEPS");
+        if (e && e[0]) pl = atoi(e);
+        if (pl < 0) pl = (cfg->timesteps + 3) / 4;
+        if (pl > cfg->timesteps) pl = cfg->timesteps;
+        c->precise_last = (cfg->engine == EGOEGO_ENGINE_TCGEN05) ? pl : cfg->timesteps;
+    }
     if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming) != cudaSuccess) {
@@ -223,7 +235,7 @@ int egoego_destroy(egoego_handle c) {
     if (!c) return 0;
     cudaSetDevice(c->cfg.device);
     cudaDeviceSynchronize();
-    if (c->step_graph) cudaGraphExecDestroy(c->step_graph);
+    for (auto& g : c->step_graph) if (g) cudaGraphExecDestroy(g);
     DevBuf* bufs[] = {&c->start_w, &c->start_b, &c->pos, &c->out_w, &c->out_b, &c->t_w1, &c->t_b1, &c->t_w2, &c->t_b2,
                       &c->temb, &c->coef1, &c->coef2, &c->logvar, &c->sqrt_recip, &c->sqrt_recipm1, &c->Ain, &c->Hbuf,
                       &c->Ybuf, &c->QKV, &c->Obuf, &c->Fbuf, &c->model_out, &c->x_cur, &c->x_cond, &c->d_step, &c->t_tmp,
@@ -406,7 +418,8 @@ int egoego_commit_weights(egoego_handle c, void* stream_v) {
         if (c->tc->init(tw, s)) return 1;
     }
     EG_CUDA(cudaStreamSynchronize(s));
-    if (c->step_graph) { cudaGraphExecDestroy(c->step_graph); c->step_graph = nullptr; c->graph_B = -1; }
+    for (auto& g : c->step_graph) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+    c->graph_B = -1;
     c->committed = true;
     return 0;
 }
@@ -486,40 +499,41 @@ static int sample_chunk(egoego_ctx* c, const float* x_start, const float* cond_m
     DdpmArgs a;
     fill_ddpm(c, a, xc, xc, ts, ns, 1, inpaint, inpaint_len, Bc, T, true);
 
-    auto one_step = [&](cudaStream_t st) -> int {
-        if (run_denoiser(c, Bc, T, ts, nullptr, st)) return 1;
+    auto one_step = [&](cudaStream_t st, int fmt) -> int {
+        if (run_denoiser(c, Bc, T, ts, nullptr, st, fmt)) return 1;
         ddpm_update_kernel<<<grid1d(quads, 256), 256, 0, st>>>(a);
         advance_step_kernel<<<1, 32, 0, st>>>(d_step);
         c->launches += 2;
         EG_CUDA(cudaGetLastError());
         return 0;
     };
+    auto fmt_of_step = [&](int i) -> int { return (N - 1 - i) >= c->precise_last ? 1 : 0; };   // i-th executed step has t = N-1-i
     const void* key[4] = {ns.tape, inpaint, (const void*)(uintptr_t)(ns.seed ^ (ns.window_offset * 0x9E3779B97F4A7C15ull)),
                           (const void*)(uintptr_t)(((uint64_t)inpaint_len << 32) ^ (uint64_t)ns.draw_stride)};
     if (c->use_graph) {
-        bool reuse = c->step_graph && c->graph_B == Bc && c->graph_T == T && !memcmp(key, c->graph_key, sizeof(key));
-        if (!reuse) {
-            if (c->step_graph) { cudaGraphExecDestroy(c->step_graph); c->step_graph = nullptr; }
+        bool reuse = c->graph_B == Bc && c->graph_T == T && !memcmp(key, c->graph_key, sizeof(key));
+        if (!reuse) for (auto& g : c->step_graph) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+        for (int fmt = 0; fmt < 2; ++fmt) {
+            bool needed = false;
+            for (int i = 0; i < N && !needed; ++i) needed = fmt_of_step(i) == fmt;
+            if (!needed || c->step_graph[fmt]) continue;
             cudaGraph_t g = nullptr;
             int64_t before = c->launches;
             EG_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-            int rc = one_step(s);
+            int rc = one_step(s, fmt);
             cudaError_t ce = cudaStreamEndCapture(s, &g);
             c->launches = before;                       // captured, not launched
             EG_CHECK(rc == 0, std::string("capture failed: ") + g_err);
             EG_CUDA(ce);
-            EG_CUDA(cudaGraphInstantiate(&c->step_graph, g, 0));
+            EG_CUDA(cudaGraphInstantiate(&c->step_graph[fmt], g, 0));
             cudaGraphDestroy(g);
-            c->graph_B = Bc; c->graph_T = T; memcpy(c->graph_key, key, sizeof(key));
         }
-        int64_t per_step = 0;
-        { int64_t before = c->launches; c->launches = 0;   // count kernels of one step without launching: re-derive
-          per_step = (c->cfg.engine == EGOEGO_ENGINE_SIMT ? (2 + 7 * c->NL) : c->tc->launches_per_denoiser()) + 2;
-          c->launches = before; }
-        for (int i = 0; i < N; ++i) EG_CUDA(cudaGraphLaunch(c->step_graph, s));
+        c->graph_B = Bc; c->graph_T = T; memcpy(c->graph_key, key, sizeof(key));
+        const int64_t per_step = (c->cfg.engine == EGOEGO_ENGINE_SIMT ? (2 + 7 * c->NL) : c->tc->launches_per_denoiser()) + 2;
+        for (int i = 0; i < N; ++i) EG_CUDA(cudaGraphLaunch(c->step_graph[fmt_of_step(i)], s));
         c->launches += per_step * N;
     } else {
-        for (int i = 0; i < N; ++i) if (one_step(s)) return 1;
+        for (int i = 0; i < N; ++i) if (one_step(s, fmt_of_step(i))) return 1;
     }
     EG_CUDA(cudaMemcpyAsync(out, xc, (size_t)Bc * T * D * 4, cudaMemcpyDeviceToDevice, s));
     return 0;
@@ -640,12 +654,12 @@ int egoego_canonicalize_head(egoego_handle c, const float* head_pos, const float
 
 int64_t egoego_launch_count(egoego_handle c) { return c ? c->launches : -1; }
 
-int egoego_selftest_gemm(int device, int M, int N, int K, uint64_t seed, int two_cta, float* max_abs_err, float* max_abs_ref, float* ms) {
+int egoego_selftest_gemm(int device, int M, int N, int K, uint64_t seed, int two_cta, int half_fmt, float* max_abs_err, float* max_abs_ref, float* ms) {
     EG_CHECK(max_abs_err && max_abs_ref && ms, "null argument");
     int ndev = 0;
     EG_CHECK(cudaGetDeviceCount(&ndev) == cudaSuccess && device >= 0 && device < ndev, "no such CUDA device");
     EG_CUDA(cudaSetDevice(device));
-    return selftest_gemm(M, N, K, seed, two_cta, max_abs_err, max_abs_ref, ms);
+    return selftest_gemm(M, N, K, seed, two_cta, half_fmt, max_abs_err, max_abs_ref, ms);
 }
 
 }  // extern "C"

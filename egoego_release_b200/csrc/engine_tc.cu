@@ -1,6 +1,7 @@
 // Tensor-core engine: tcgen05/TMA split-bf16 GEMMs for every projection of the denoiser, warp-level
 // LayerNorm, attention; see gemm_tcgen05.cuh for the GEMM kernel.
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cstring>
 #include <cstdlib>
 #include <memory>
@@ -45,6 +46,9 @@ struct Plane {                 // a bf16 hi/lo pair with its TMA maps
     __nv_bfloat16 *hi = nullptr, *lo = nullptr;
     CUtensorMap mhi, mlo;
     CUtensorMap mhi128, mlo128;     // 128-row boxes (per-CTA half of a W tile in the 2-CTA GEMM)
+    __nv_bfloat16* h16 = nullptr;   // fp16 plane for FMT_HALF launches: a separate buffer (weights, X) or an alias of `hi`
+    CUtensorMap m16, m16_128;
+    bool own16 = false;
     size_t rows = 0, cols = 0;
     int alloc(size_t r, size_t c, uint32_t box_rows) {
         rows = r; cols = c;
@@ -54,9 +58,19 @@ struct Plane {                 // a bf16 hi/lo pair with its TMA maps
         EG_CUDA(cudaMemset(lo, 0, r * c * 2));
         if (make_map(&mhi, hi, r, c, box_rows) || make_map(&mlo, lo, r, c, box_rows)) return 1;
         if (make_map(&mhi128, hi, r, c, 128) || make_map(&mlo128, lo, r, c, 128)) return 1;
+        h16 = hi; m16 = mhi; m16_128 = mhi128; own16 = false;       // activations: the fp16 plane reuses the hi buffer
+        box = box_rows;
         return 0;
     }
-    void release() { if (hi) cudaFree(hi); if (lo) cudaFree(lo); hi = lo = nullptr; }
+    int alloc16() {                                                  // separate fp16 buffer (weights, sampler input)
+        EG_CUDA(cudaMalloc(&h16, rows * cols * 2));
+        EG_CUDA(cudaMemset(h16, 0, rows * cols * 2));
+        own16 = true;
+        if (make_map(&m16, h16, rows, cols, box) || make_map(&m16_128, h16, rows, cols, 128)) return 1;
+        return 0;
+    }
+    uint32_t box = 128;
+    void release() { if (hi) cudaFree(hi); if (lo) cudaFree(lo); if (own16 && h16) cudaFree(h16); hi = lo = h16 = nullptr; }
 };
 
 // Host fp32 [rows, src_ld] (columns [col0, col0+ncols)) -> zero-padded [rows_pad, cols_pad] hi/lo planes.
@@ -72,6 +86,11 @@ static int upload_weight(Plane& p, const float* w, int rows, int src_ld, int col
         }
     EG_CUDA(cudaMemcpy(p.hi, hi.data(), hi.size() * 2, cudaMemcpyHostToDevice));
     EG_CUDA(cudaMemcpy(p.lo, lo.data(), lo.size() * 2, cudaMemcpyHostToDevice));
+    if (p.alloc16()) return 1;
+    std::vector<__half> h16((size_t)rows_pad * cols_pad, __float2half(0.f));
+    for (int r = 0; r < rows; ++r)
+        for (int c = 0; c < ncols; ++c) h16[(size_t)r * cols_pad + c] = __float2half_rn(w[(size_t)r * src_ld + col0 + c]);
+    EG_CUDA(cudaMemcpy(p.h16, h16.data(), h16.size() * 2, cudaMemcpyHostToDevice));
     return 0;
 }
 
@@ -98,11 +117,11 @@ struct TcImpl {
 
 static inline int Mr(int B) { return ((B + 1) / 2) * 2 * LP; }
 
-template <int BN, class Epi>
+template <int BN, int FMT, class Epi>
 static int launch_gemm(TcImpl* I, const Plane& A, const Plane& W, int M, int N, int K, const Epi& epi, cudaStream_t s) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, FMT>;
     static bool attr_set = false;
-    auto kern = gemm_split3_kernel<BN, Epi>;
+    auto kern = gemm_split3_kernel<BN, FMT, Epi>;
     if (!attr_set) {
         EG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr_set = true;
@@ -110,7 +129,8 @@ static int launch_gemm(TcImpl* I, const Plane& A, const Plane& W, int M, int N, 
     EG_CHECK(M % GEMM_BM == 0 && N % BN == 0 && K % GEMM_BK == 0, "gemm shape not tile-aligned");
     const int tiles = (M / GEMM_BM) * (N / BN);
     const int grid = tiles < I->sms ? tiles : I->sms;
-    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(A.mhi, A.mlo, W.mhi, W.mlo, M, N, K, epi);
+    if (FMT == FMT_SPLIT) kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(A.mhi, A.mlo, W.mhi, W.mlo, M, N, K, epi);
+    else                  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(A.m16, A.m16, W.m16, W.m16, M, N, K, epi);
     EG_CUDA(cudaGetLastError());
     return 0;
 }
@@ -122,10 +142,11 @@ static bool use_2cta() {
 }
 
 // 2-CTA (cluster of 2, cta_group::2) launch: 256 x 256 tiles per CTA pair.
-template <class Epi>
+template <int FMT, class Epi>
 static int launch_gemm_2cta(TcImpl* I, const Plane& A, const Plane& W, int M, int N, int K, const Epi& epi, cudaStream_t s) {
     static bool attr_set = false;
-    auto kern = gemm_split3_2cta_kernel<Epi>;
+    auto kern = gemm_split3_2cta_kernel<FMT, Epi>;
+    constexpr int GEMM2_SMEM_BYTES = Gemm2Cfg<FMT>::SMEM_BYTES;
     if (!attr_set) {
         EG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_BYTES));
         attr_set = true;
@@ -140,14 +161,15 @@ static int launch_gemm_2cta(TcImpl* I, const Plane& A, const Plane& W, int M, in
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    EG_CUDA(cudaLaunchKernelEx(&cfg, kern, A.mhi, A.mlo, W.mhi128, W.mlo128, M, N, K, epi));
+    if (FMT == FMT_SPLIT) { EG_CUDA(cudaLaunchKernelEx(&cfg, kern, A.mhi, A.mlo, W.mhi128, W.mlo128, M, N, K, epi)); }
+    else                  { EG_CUDA(cudaLaunchKernelEx(&cfg, kern, A.m16, A.m16, W.m16_128, W.m16_128, M, N, K, epi)); }
     return 0;
 }
 
-template <class Epi>
+template <int FMT, class Epi>
 static int gemm(TcImpl* I, const Plane& A, const Plane& W, int M, int N, int K, const Epi& epi, cudaStream_t s) {
-    if (use_2cta() && M % 256 == 0) return launch_gemm_2cta(I, A, W, M, N, K, epi, s);
-    return launch_gemm<256>(I, A, W, M, N, K, epi, s);
+    if (use_2cta() && M % 256 == 0) return launch_gemm_2cta<FMT>(I, A, W, M, N, K, epi, s);
+    return launch_gemm<256, FMT>(I, A, W, M, N, K, epi, s);
 }
 
 TcEngine::TcEngine() : impl_(nullptr) {}
@@ -187,7 +209,7 @@ int TcEngine::init(const TcWeights& w, cudaStream_t) {
         L.ln1_g = s.ln1_g; L.ln1_b = s.ln1_b; L.ln2_g = s.ln2_g; L.ln2_b = s.ln2_b;
     }
     // activation planes: A-operand boxes of 128 rows
-    if (I->X.alloc(M, I->kx, 128) || I->C.alloc(M, I->kx, 128) || I->Hs.alloc(M, d, 128) ||
+    if (I->X.alloc(M, I->kx, 128) || I->X.alloc16() || I->C.alloc(M, I->kx, 128) || I->Hs.alloc(M, d, 128) ||
         I->O.alloc(M, (size_t)H * dk, 128) || I->F.alloc(M, d, 128)) return 1;
     EG_CUDA(cudaMalloc(&I->base, M * d * 4));
     EG_CUDA(cudaMalloc(&I->H, M * d * 4));
@@ -198,7 +220,8 @@ int TcEngine::init(const TcWeights& w, cudaStream_t) {
         const size_t MBe = (size_t)((w.max_batch + 1) / 2) * 2;
         if (I->Qp.alloc(MBe * H * 128, 256, 128) || I->Kp.alloc(MBe * H * 128, 256, 128) ||
             I->VT.alloc(MBe * H * 256, 128, 256)) return 1;
-        EG_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+        EG_CUDA(cudaFuncSetAttribute(attention_tc_kernel<FMT_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+        EG_CUDA(cudaFuncSetAttribute(attention_tc_kernel<FMT_HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
     } else {
         EG_CUDA(cudaMalloc(&I->QKV, M * 3 * H * dk * 4));
         EG_CUDA(cudaFuncSetAttribute(attention_simt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SIMT_SMEM));
@@ -211,6 +234,7 @@ int TcEngine::clear_staging(int B, cudaStream_t s) {
     const size_t n = (size_t)B * LP * I->kx * 2;
     EG_CUDA(cudaMemsetAsync(I->X.hi, 0, n, s)); EG_CUDA(cudaMemsetAsync(I->X.lo, 0, n, s));
     EG_CUDA(cudaMemsetAsync(I->C.hi, 0, n, s)); EG_CUDA(cudaMemsetAsync(I->C.lo, 0, n, s));
+    EG_CUDA(cudaMemsetAsync(I->X.h16, 0, n, s));
     return 0;
 }
 
@@ -218,7 +242,7 @@ int TcEngine::stage(const float* src, int src_ld, int src_col0, bool cond_half, 
     TcImpl* I = impl_;
     Plane& P = cond_half ? I->C : I->X;
     const long long tot = (long long)B * T * I->w.D;
-    stage_rows_split_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(P.hi, P.lo, I->kx, src, src_ld, src_col0, I->w.D, B, T);
+    stage_rows_split_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(P.hi, P.lo, cond_half ? nullptr : reinterpret_cast<__half*>(P.h16), I->kx, src, src_ld, src_col0, I->w.D, B, T);
     EG_CUDA(cudaGetLastError());
     *n += 1;
     return 0;
@@ -227,55 +251,64 @@ int TcEngine::stage(const float* src, int src_ld, int src_col0, bool cond_half, 
 int TcEngine::prepare_cond(int B, int T, cudaStream_t s, int64_t* n) {
     TcImpl* I = impl_;
     TcEpiBase e{I->base, I->w.d, I->w.start_b, I->w.pos, T};
-    if (gemm(I, I->C, I->Wc, Mr(B), I->w.d, I->kx, e, s)) return 1;
+    if (gemm<FMT_SPLIT>(I, I->C, I->Wc, Mr(B), I->w.d, I->kx, e, s)) return 1;
     *n += 1;
     return 0;
 }
 
-void TcEngine::stage_targets(__nv_bfloat16** hi, __nv_bfloat16** lo, int* ld) {
-    *hi = impl_->X.hi; *lo = impl_->X.lo; *ld = impl_->kx;
+void TcEngine::stage_targets(__nv_bfloat16** hi, __nv_bfloat16** lo, __half** h16, int* ld) {
+    *hi = impl_->X.hi; *lo = impl_->X.lo; *h16 = reinterpret_cast<__half*>(impl_->X.h16); *ld = impl_->kx;
 }
 
 int TcEngine::launches_per_denoiser() const { return 2 + 7 * impl_->w.NL; }
 
-int TcEngine::denoiser(int B, int T, TSrc ts, const float* pmask, float* model_out, cudaStream_t s, int64_t* n) {
-    TcImpl* I = impl_;
+template <int FMT>
+static int denoiser_impl(TcImpl* I, int B, int T, TSrc ts, const float* pmask, float* model_out, cudaStream_t s) {
     const int M = B * LP, d = I->w.d, H = I->w.H, dk = I->w.dk, L = T + 1;
     const int Mg = Mr(B);                          // GEMM rows: whole 256-row tiles (an odd window count is rounded up)
     const int nqkv = 3 * H * dk;
+    const int half = (FMT == FMT_HALF) ? 1 : 0;
     {
-        TcEpiStart e{I->H, I->Hs.hi, I->Hs.lo, d, I->base, I->w.pos, I->w.temb, ts, T, B};
-        if (gemm(I, I->X, I->Wx, Mg, d, I->kx, e, s)) return 1;
+        TcEpiStart<FMT> e{I->H, I->Hs.hi, I->Hs.lo, d, I->base, I->w.pos, I->w.temb, ts, T, B};
+        if (gemm<FMT>(I, I->X, I->Wx, Mg, d, I->kx, e, s)) return 1;
     }
     for (int l = 0; l < I->w.NL; ++l) {
         TcLayer& W = I->layers[l];
         if (I->attn_tc) {
-            TcEpiQKVPlanes eq{I->Qp.hi, I->Qp.lo, I->Kp.hi, I->Kp.lo, I->VT.hi, I->VT.lo, W.bqkv, H, 1.0f / sqrtf((float)dk)};
-            if (gemm(I, I->Hs, W.wqkv, Mg, nqkv, d, eq, s)) return 1;
+            TcEpiQKVPlanes<FMT> eq{I->Qp.hi, I->Qp.lo, I->Kp.hi, I->Kp.lo, I->VT.hi, I->VT.lo, W.bqkv, H, 1.0f / sqrtf((float)dk)};
+            if (gemm<FMT>(I, I->Hs, W.wqkv, Mg, nqkv, d, eq, s)) return 1;
             const int items = B * H;
-            attention_tc_kernel<<<items < I->sms ? items : I->sms, ATT_THREADS, ATT_SMEM_BYTES, s>>>(
+            attention_tc_kernel<FMT><<<items < I->sms ? items : I->sms, ATT_THREADS, ATT_SMEM_BYTES, s>>>(
                 I->Qp.mhi, I->Qp.mlo, I->Kp.mhi, I->Kp.mlo, I->VT.mhi, I->VT.mlo, I->O.hi, I->O.lo, H * dk, items, H, L);
         } else {
             TcEpiBiasScaleF32 eq{I->QKV, nqkv, W.bqkv, H * dk, 1.0f / sqrtf((float)dk)};
-            if (gemm(I, I->Hs, W.wqkv, Mg, nqkv, d, eq, s)) return 1;
+            if (gemm<FMT_SPLIT>(I, I->Hs, W.wqkv, Mg, nqkv, d, eq, s)) return 1;
             attention_simt_kernel<true><<<B * H, 256, ATT_SIMT_SMEM, s>>>(I->QKV, nqkv, nullptr, I->O.hi, I->O.lo, H * dk, H, L);
         }
         TcEpiBiasResidF32 ef{I->Y, d, W.fc_b, I->H};
-        if (gemm(I, I->O, W.fc, Mg, d, H * dk, ef, s)) return 1;
-        layernorm512_kernel<<<M / 8, 256, 0, s>>>(I->Y, I->H, I->Hs.hi, I->Hs.lo, W.ln1_g, W.ln1_b, pmask, T, M);
-        TcEpiBiasReluSplit e1{I->F.hi, I->F.lo, d, W.b1};
-        if (gemm(I, I->Hs, W.w1, Mg, d, d, e1, s)) return 1;
+        if (gemm<FMT>(I, I->O, W.fc, Mg, d, H * dk, ef, s)) return 1;
+        layernorm512_kernel<<<M / 8, 256, 0, s>>>(I->Y, I->H, I->Hs.hi, I->Hs.lo, W.ln1_g, W.ln1_b, pmask, T, M, half);
+        TcEpiBiasReluSplit<FMT> e1{I->F.hi, I->F.lo, d, W.b1};
+        if (gemm<FMT>(I, I->Hs, W.w1, Mg, d, d, e1, s)) return 1;
         TcEpiBiasResidF32 e2{I->Y, d, W.b2, I->H};
-        if (gemm(I, I->F, W.w2, Mg, d, d, e2, s)) return 1;
-        layernorm512_kernel<<<M / 8, 256, 0, s>>>(I->Y, I->H, I->Hs.hi, I->Hs.lo, W.ln2_g, W.ln2_b, pmask, T, M);
+        if (gemm<FMT>(I, I->F, W.w2, Mg, d, d, e2, s)) return 1;
+        layernorm512_kernel<<<M / 8, 256, 0, s>>>(I->Y, I->H, I->Hs.hi, I->Hs.lo, W.ln2_g, W.ln2_b, pmask, T, M, half);
     }
     {
         TcEpiOut eo{model_out, I->w.D, I->w.out_b, T, B};
-        if (gemm(I, I->Hs, I->Wout, Mg, I->nout, d, eo, s)) return 1;
+        if (gemm<FMT>(I, I->Hs, I->Wout, Mg, I->nout, d, eo, s)) return 1;
     }
     EG_CUDA(cudaGetLastError());
-    *n += launches_per_denoiser();
     return 0;
+}
+
+int TcEngine::denoiser(int B, int T, TSrc ts, const float* pmask, float* model_out, cudaStream_t s, int64_t* n, int fmt) {
+    TcImpl* I = impl_;
+    EG_CHECK(fmt == FMT_SPLIT || (I->attn_tc), "fp16 single-pass steps need the tensor-core attention");
+    int rc = (fmt == FMT_HALF) ? denoiser_impl<FMT_HALF>(I, B, T, ts, pmask, model_out, s)
+                               : denoiser_impl<FMT_SPLIT>(I, B, T, ts, pmask, model_out, s);
+    *n += launches_per_denoiser();
+    return rc;
 }
 
 // ---- self test: split GEMM against the fp32 SIMT GEMM on random data ------------------------------
@@ -290,6 +323,10 @@ __global__ void split_rows_kernel(const float* src, __nv_bfloat16* hi, __nv_bflo
     if (i >= n) return;
     split_bf16(src[i], hi[i], lo[i]);
 }
+__global__ void to_half_kernel(const float* src, __half* dst, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = __float2half_rn(src[i]);
+}
 __global__ void maxdiff_kernel(const float* a, const float* b, long long n, float* out /*[2]: max|a-b|, max|b|*/) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     float d = 0.f, m = 0.f;
@@ -301,7 +338,7 @@ __global__ void maxdiff_kernel(const float* a, const float* b, long long n, floa
 
 struct EpiStore { float* C; int ldc; __device__ void operator()(int r, int c, float a) const { C[(long long)r * ldc + c] = a; } };
 
-int selftest_gemm(int M, int N, int K, unsigned long long seed, int two_cta, float* max_abs_err, float* max_abs_ref, float* ms) {
+int selftest_gemm(int M, int N, int K, unsigned long long seed, int two_cta, int half_fmt, float* max_abs_err, float* max_abs_ref, float* ms) {
     EG_CHECK(M % 128 == 0 && N % 256 == 0 && K % 64 == 0, "selftest_gemm: need M%128==0, N%256==0, K%64==0");
     TcImpl I;
     int dev = 0;
@@ -321,7 +358,15 @@ int selftest_gemm(int M, int N, int K, unsigned long long seed, int two_cta, flo
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     EG_CHECK(!two_cta || M % 256 == 0, "2-CTA self test needs M % 256 == 0");
-    auto run = [&]() -> int { return two_cta ? launch_gemm_2cta(&I, PA, PW, M, N, K, e, 0) : launch_gemm<256>(&I, PA, PW, M, N, K, e, 0); };
+    if (half_fmt) {
+        if (PA.alloc16() || PW.alloc16()) return 1;
+        to_half_kernel<<<(unsigned)(((long long)M * K + 255) / 256), 256>>>(A, reinterpret_cast<__half*>(PA.h16), (long long)M * K);
+        to_half_kernel<<<(unsigned)(((long long)N * K + 255) / 256), 256>>>(W, reinterpret_cast<__half*>(PW.h16), (long long)N * K);
+    }
+    auto run = [&]() -> int {
+        if (half_fmt) return two_cta ? launch_gemm_2cta<FMT_HALF>(&I, PA, PW, M, N, K, e, 0) : launch_gemm<256, FMT_HALF>(&I, PA, PW, M, N, K, e, 0);
+        return two_cta ? launch_gemm_2cta<FMT_SPLIT>(&I, PA, PW, M, N, K, e, 0) : launch_gemm<256, FMT_SPLIT>(&I, PA, PW, M, N, K, e, 0);
+    };
     if (run()) return 1;
     EG_CUDA(cudaDeviceSynchronize());
     cudaEventRecord(e0);

@@ -2,6 +2,7 @@
 // Implementation: engine_tc.cu (tcgen05 + TMA GEMMs with a 3-term bf16 hi/lo split).
 #pragma once
 #include <vector>
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace egoego {
@@ -36,14 +37,14 @@ public:
     // base[M, d] = x_cond-half of start_conv + bias + positional rows (constant over the loop)
     int prepare_cond(int B, int T, cudaStream_t s, int64_t* n);
     // one denoiser call; expects the x half staged; writes model_out[B, T, D]
-    int denoiser(int B, int T, TSrc ts, const float* pmask, float* model_out, cudaStream_t s, int64_t* n);
-    void stage_targets(__nv_bfloat16** hi, __nv_bfloat16** lo, int* ld);
+    int denoiser(int B, int T, TSrc ts, const float* pmask, float* model_out, cudaStream_t s, int64_t* n, int fmt /* FMT_SPLIT=0 | FMT_HALF=1 */);
+    void stage_targets(__nv_bfloat16** hi, __nv_bfloat16** lo, __half** h16, int* ld);
     int launches_per_denoiser() const;
 private:
     TcImpl* impl_;
 };
 
 // tcgen05 split GEMM vs fp32 SIMT GEMM on random data (C = A W^T, no epilogue); returns max |err|, max |ref|, ms/launch.
-int selftest_gemm(int M, int N, int K, unsigned long long seed, int two_cta, float* max_abs_err, float* max_abs_ref, float* ms);
+int selftest_gemm(int M, int N, int K, unsigned long long seed, int two_cta, int half_fmt, float* max_abs_err, float* max_abs_ref, float* ms);
 
 }  // namespace egoego

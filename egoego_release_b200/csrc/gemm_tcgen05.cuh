@@ -15,18 +15,30 @@
 // Accumulators are double-buffered in TMEM (2 x BN columns of the 512) so the epilogue of tile i overlaps
 // the main loop of tile i+1.
 #pragma once
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
 namespace egoego {
 
 constexpr int GEMM_BM = 128;
-constexpr int GEMM_BK = 64;            // 64 bf16 = 128 B = one swizzle row
+constexpr int GEMM_BK = 64;            // 64 16-bit elements = 128 B = one swizzle row
 constexpr int GEMM_THREADS = 192;
 
-template <int BN> struct GemmCfg {
-    static constexpr int STAGE_BYTES = 2 * GEMM_BM * GEMM_BK * 2 + 2 * BN * GEMM_BK * 2;   // A_hi A_lo W_hi W_lo
-    static constexpr int STAGES = (BN == 256) ? 2 : 3;
+// Operand format of a GEMM / attention launch:
+//   FMT_SPLIT  bf16 hi/lo planes, three MMAs per k-step (fp32-grade; the default everywhere)
+//   FMT_HALF   one fp16 plane, one MMA per k-step (used only for the early, high-noise diffusion steps whose
+//              error is damped by posterior_mean_coef1 -- see DESIGN.md "Precision policy")
+enum { FMT_SPLIT = 0, FMT_HALF = 1 };
+template <int FMT> struct FmtTraits {
+    static constexpr int NP = (FMT == FMT_SPLIT) ? 2 : 1;                       // operand planes per matrix
+    static constexpr int MMAS = (FMT == FMT_SPLIT) ? 3 : 1;                     // MMAs per k-step
+};
+
+template <int BN, int FMT> struct GemmCfg {
+    static constexpr int NP = FmtTraits<FMT>::NP;
+    static constexpr int STAGE_BYTES = NP * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2);   // A planes then W planes
+    static constexpr int STAGES = (FMT == FMT_SPLIT) ? 2 : 4;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -46,6 +58,16 @@ struct TcEpiPlain {                       // C = acc (+ bias): self-test / gener
     }
 };
 
+__device__ __forceinline__ void store_half8(__nv_bfloat16* dst /* fp16 bits */, const float* v) {
+    uint32_t p[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        __half2 h = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
+        p[q] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(dst) = make_uint4(p[0], p[1], p[2], p[3]);
+}
+
 __device__ __forceinline__ void store_split8(__nv_bfloat16* hi, __nv_bfloat16* lo, const float* v) {
     uint32_t ph[4], pl[4];
 #pragma unroll
@@ -57,6 +79,11 @@ __device__ __forceinline__ void store_split8(__nv_bfloat16* hi, __nv_bfloat16* l
     }
     *reinterpret_cast<uint4*>(hi) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
     *reinterpret_cast<uint4*>(lo) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+}
+
+template <int FMT>
+__device__ __forceinline__ void store_planes8(__nv_bfloat16* hi, __nv_bfloat16* lo, const float* v) {
+    if (FMT == FMT_SPLIT) store_split8(hi, lo, v); else store_half8(hi, v);
 }
 
 struct TcEpiBase {                        // base = x_cond-half of start_conv + bias + positional row (constant per window)
@@ -78,7 +105,8 @@ struct TcEpiBase {                        // base = x_cond-half of start_conv + 
     }
 };
 
-struct TcEpiStart {                       // H = x-half GEMM + base ; row 0 = time token ; writes fp32 + hi/lo planes
+template <int FMT>
+struct TcEpiStart {                       // H = x-half GEMM + base ; row 0 = time token ; writes fp32 + operand planes
     float* H; __nv_bfloat16* Hhi; __nv_bfloat16* Hlo; int ld;
     const float* base; const float* pos; const float* temb; TSrc ts; int T; int n_windows;
     __device__ __forceinline__ void operator()(int row, int col0, const float (&v)[32]) const {
@@ -102,7 +130,7 @@ struct TcEpiStart {                       // H = x-half GEMM + base ; row 0 = ti
 #pragma unroll
         for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(H + o + j) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) store_split8(Hhi + o + j, Hlo + o + j, r + j);
+        for (int j = 0; j < 32; j += 8) store_planes8<FMT>(Hhi + o + j, Hlo + o + j, r + j);
     }
 };
 
@@ -132,7 +160,8 @@ struct TcEpiBiasResidF32 {                // fc / w_2: acc + bias + residual -> 
     }
 };
 
-struct TcEpiBiasReluSplit {               // w_1: relu(acc + bias) -> bf16 hi/lo planes (A operand of w_2)
+template <int FMT>
+struct TcEpiBiasReluSplit {               // w_1: relu(acc + bias) -> operand planes (A operand of w_2)
     __nv_bfloat16* hi; __nv_bfloat16* lo; int ld; const float* bias;
     __device__ __forceinline__ void operator()(int row, int col0, const float (&v)[32]) const {
         float r[32];
@@ -140,7 +169,7 @@ struct TcEpiBiasReluSplit {               // w_1: relu(acc + bias) -> bf16 hi/lo
         for (int j = 0; j < 32; ++j) r[j] = fmaxf(v[j] + bias[col0 + j], 0.f);
         const long long o = (long long)row * ld + col0;
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) store_split8(hi + o + j, lo + o + j, r + j);
+        for (int j = 0; j < 32; j += 8) store_planes8<FMT>(hi + o + j, lo + o + j, r + j);
     }
 };
 
@@ -160,16 +189,17 @@ struct TcEpiOut {                         // linear_out: tokens 1..T, first d_fe
 };
 
 // ---- the kernel ---------------------------------------------------------------------------------
-template <int BN, class Epi>
+template <int BN, int FMT, class Epi>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_split3_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl,
                    const __grid_constant__ CUtensorMap mWh, const __grid_constant__ CUtensorMap mWl,
                    int M, int N, int K, Epi epi) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, FMT>;
+    constexpr int NP = Cfg::NP;
     constexpr int STAGES = Cfg::STAGES;
     constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
     constexpr int W_BYTES = BN * GEMM_BK * 2;
-    constexpr uint32_t IDESC = ptx::make_idesc_bf16(GEMM_BM, BN);
+    constexpr uint32_t IDESC = (FMT == FMT_SPLIT) ? ptx::make_idesc_bf16(GEMM_BM, BN) : ptx::make_idesc_f16(GEMM_BM, BN);
     constexpr int ACC_STAGES = 512 / BN >= 2 ? 2 : 1;
 
     extern __shared__ uint8_t smem_raw[];
@@ -207,9 +237,9 @@ gemm_split3_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constan
                     uint8_t* st = smem + s * Cfg::STAGE_BYTES;
                     ptx::mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
                     ptx::tma_load_2d(st, &mAh, &full_bar[s], kb * GEMM_BK, m0);
-                    ptx::tma_load_2d(st + A_BYTES, &mAl, &full_bar[s], kb * GEMM_BK, m0);
-                    ptx::tma_load_2d(st + 2 * A_BYTES, &mWh, &full_bar[s], kb * GEMM_BK, n0);
-                    ptx::tma_load_2d(st + 2 * A_BYTES + W_BYTES, &mWl, &full_bar[s], kb * GEMM_BK, n0);
+                    if (NP == 2) ptx::tma_load_2d(st + A_BYTES, &mAl, &full_bar[s], kb * GEMM_BK, m0);
+                    ptx::tma_load_2d(st + NP * A_BYTES, &mWh, &full_bar[s], kb * GEMM_BK, n0);
+                    if (NP == 2) ptx::tma_load_2d(st + NP * A_BYTES + W_BYTES, &mWl, &full_bar[s], kb * GEMM_BK, n0);
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
             }
@@ -229,14 +259,16 @@ gemm_split3_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constan
                     const uint32_t st = ptx::smem_u32(smem + s * Cfg::STAGE_BYTES);
                     const uint64_t dAh = ptx::make_smem_desc_sw128(st);
                     const uint64_t dAl = ptx::make_smem_desc_sw128(st + A_BYTES);
-                    const uint64_t dWh = ptx::make_smem_desc_sw128(st + 2 * A_BYTES);
-                    const uint64_t dWl = ptx::make_smem_desc_sw128(st + 2 * A_BYTES + W_BYTES);
+                    const uint64_t dWh = ptx::make_smem_desc_sw128(st + NP * A_BYTES);
+                    const uint64_t dWl = ptx::make_smem_desc_sw128(st + NP * A_BYTES + W_BYTES);
 #pragma unroll
                     for (int kk = 0; kk < GEMM_BK / 16; ++kk) {
                         const uint64_t adv = (uint64_t)(kk * 32 >> 4);       // +32 B per UMMA_K inside the swizzle row
                         ptx::umma_f16(d_tmem, dAh + adv, dWh + adv, IDESC, (kb | kk) != 0);
-                        ptx::umma_f16(d_tmem, dAh + adv, dWl + adv, IDESC, 1);
-                        ptx::umma_f16(d_tmem, dAl + adv, dWh + adv, IDESC, 1);
+                        if (NP == 2) {
+                            ptx::umma_f16(d_tmem, dAh + adv, dWl + adv, IDESC, 1);
+                            ptx::umma_f16(d_tmem, dAl + adv, dWh + adv, IDESC, 1);
+                        }
                     }
                     ptx::umma_commit(&empty_bar[s]);                        // frees the smem stage when the MMAs retire
                     if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -281,18 +313,24 @@ gemm_split3_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constan
 // MMAs for the pair; TMA completions of both CTAs are credited to the leader's `full` barrier; `empty` and
 // `tmem_full` are signalled to both CTAs by a multicast tcgen05.commit; the epilogues of both CTAs release the
 // accumulator through remote arrives on the leader's `tmem_empty` barrier.
-constexpr int GEMM2_STAGES = 3;
-constexpr int GEMM2_STAGE_BYTES = 4 * GEMM_BM * GEMM_BK * 2;      // A_hi A_lo Whalf_hi Whalf_lo, 16 KB each
-constexpr int GEMM2_SMEM_BYTES = GEMM2_STAGES * GEMM2_STAGE_BYTES + 1024 + 256;
+template <int FMT> struct Gemm2Cfg {
+    static constexpr int NP = FmtTraits<FMT>::NP;
+    static constexpr int STAGES = (FMT == FMT_SPLIT) ? 3 : 6;
+    static constexpr int STAGE_BYTES = 2 * NP * GEMM_BM * GEMM_BK * 2;     // A planes + W-half planes, 16 KB each
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
 
-template <class Epi>
+template <int FMT, class Epi>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_split3_2cta_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl,
                         const __grid_constant__ CUtensorMap mWh, const __grid_constant__ CUtensorMap mWl,   // W maps: 128-row boxes
                         int M, int N, int K, Epi epi) {
     constexpr int BN = 256;
+    constexpr int NP = Gemm2Cfg<FMT>::NP;
+    constexpr int GEMM2_STAGES = Gemm2Cfg<FMT>::STAGES;
+    constexpr int GEMM2_STAGE_BYTES = Gemm2Cfg<FMT>::STAGE_BYTES;
     constexpr int T_BYTES = GEMM_BM * GEMM_BK * 2;                   // 16 KB tile
-    constexpr uint32_t IDESC = ptx::make_idesc_bf16(256, BN);
+    constexpr uint32_t IDESC = (FMT == FMT_SPLIT) ? ptx::make_idesc_bf16(256, BN) : ptx::make_idesc_f16(256, BN);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GEMM2_STAGES * GEMM2_STAGE_BYTES);
@@ -334,9 +372,9 @@ gemm_split3_2cta_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_co
                     if (leader) ptx::mbar_arrive_expect_tx(&full_bar[s], 2 * GEMM2_STAGE_BYTES);
                     else        ptx::mbar_arrive_cluster(&full_bar[s], 0);
                     ptx::tma_load_2d_2cta(st, &mAh, &full_bar[s], kb * GEMM_BK, m0);
-                    ptx::tma_load_2d_2cta(st + T_BYTES, &mAl, &full_bar[s], kb * GEMM_BK, m0);
-                    ptx::tma_load_2d_2cta(st + 2 * T_BYTES, &mWh, &full_bar[s], kb * GEMM_BK, n0);
-                    ptx::tma_load_2d_2cta(st + 3 * T_BYTES, &mWl, &full_bar[s], kb * GEMM_BK, n0);
+                    if (NP == 2) ptx::tma_load_2d_2cta(st + T_BYTES, &mAl, &full_bar[s], kb * GEMM_BK, m0);
+                    ptx::tma_load_2d_2cta(st + NP * T_BYTES, &mWh, &full_bar[s], kb * GEMM_BK, n0);
+                    if (NP == 2) ptx::tma_load_2d_2cta(st + 3 * T_BYTES, &mWl, &full_bar[s], kb * GEMM_BK, n0);
                     if (++s == GEMM2_STAGES) { s = 0; ph ^= 1; }
                 }
             }
@@ -355,13 +393,15 @@ gemm_split3_2cta_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_co
                     ptx::tc_fence_after();
                     const uint32_t st = ptx::smem_u32(smem + s * GEMM2_STAGE_BYTES);
                     const uint64_t dAh = ptx::make_smem_desc_sw128(st), dAl = ptx::make_smem_desc_sw128(st + T_BYTES);
-                    const uint64_t dWh = ptx::make_smem_desc_sw128(st + 2 * T_BYTES), dWl = ptx::make_smem_desc_sw128(st + 3 * T_BYTES);
+                    const uint64_t dWh = ptx::make_smem_desc_sw128(st + NP * T_BYTES), dWl = ptx::make_smem_desc_sw128(st + 3 * T_BYTES);
 #pragma unroll
                     for (int kk = 0; kk < GEMM_BK / 16; ++kk) {
                         const uint64_t adv = (uint64_t)(kk * 2);
                         ptx::umma_f16_2cta(d_tmem, dAh + adv, dWh + adv, IDESC, (kb | kk) != 0);
-                        ptx::umma_f16_2cta(d_tmem, dAh + adv, dWl + adv, IDESC, 1);
-                        ptx::umma_f16_2cta(d_tmem, dAl + adv, dWh + adv, IDESC, 1);
+                        if (NP == 2) {
+                            ptx::umma_f16_2cta(d_tmem, dAh + adv, dWl + adv, IDESC, 1);
+                            ptx::umma_f16_2cta(d_tmem, dAl + adv, dWh + adv, IDESC, 1);
+                        }
                     }
                     ptx::umma_commit_2cta(&empty_bar[s]);
                     if (++s == GEMM2_STAGES) { s = 0; ph ^= 1; }

@@ -2,6 +2,7 @@
 // reduction kernels shared by both engines.  Everything here is fp32 SIMT, vectorised where the
 // layout allows; the tensor-core engine lives in gemm_tcgen05.cuh / attn_tcgen05.cuh.
 #pragma once
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace egoego {
@@ -267,7 +268,8 @@ static __global__ void __launch_bounds__(256) layernorm512_kernel(const float* _
                                                            __nv_bfloat16* __restrict__ Hlo,
                                                            const float* __restrict__ gamma,
                                                            const float* __restrict__ beta,
-                                                           const float* __restrict__ row_mask, int T, int M) {
+                                                           const float* __restrict__ row_mask, int T, int M,
+                                                           int half_fmt /* 1: write one fp16 plane into Hhi */) {
     const int row = blockIdx.x * 8 + threadIdx.x / 32, lane = threadIdx.x % 32;
     if (row >= M) return;
     const float4* y4 = reinterpret_cast<const float4*>(Y + (long long)row * 512);
@@ -299,7 +301,12 @@ static __global__ void __launch_bounds__(256) layernorm512_kernel(const float* _
         o.z = ((v[j].z - mean) * rstd * g.z + b.z) * mk;
         o.w = ((v[j].w - mean) * rstd * g.w + b.w) * mk;
         reinterpret_cast<float4*>(H + (long long)row * 512)[lane + 32 * j] = o;
-        if (Hhi) {
+        if (Hhi && half_fmt) {
+            __half2 a = __floats2half2_rn(o.x, o.y), b2 = __floats2half2_rn(o.z, o.w);
+            uint2 ph;
+            ph.x = *reinterpret_cast<uint32_t*>(&a); ph.y = *reinterpret_cast<uint32_t*>(&b2);
+            reinterpret_cast<uint2*>(Hhi + (long long)row * 512)[lane + 32 * j] = ph;
+        } else if (Hhi) {
             __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
             split_bf16(o.x, h0, l0); split_bf16(o.y, h1, l1); split_bf16(o.z, h2, l2); split_bf16(o.w, h3, l3);
             __nv_bfloat162 hh0(h0, h1), hh1(h2, h3), ll0(l0, l1), ll1(l2, l3);
@@ -394,7 +401,8 @@ static __global__ void stage_rows_f32_kernel(float* __restrict__ Ain, int lda, i
 }
 
 // Same, into bf16 hi/lo planes (tensor-core engine A operand).
-static __global__ void stage_rows_split_kernel(__nv_bfloat16* __restrict__ Ahi, __nv_bfloat16* __restrict__ Alo, int lda,
+static __global__ void stage_rows_split_kernel(__nv_bfloat16* __restrict__ Ahi, __nv_bfloat16* __restrict__ Alo,
+                                        __half* __restrict__ A16 /* nullable: extra fp16 plane */, int lda,
                                         const float* __restrict__ src, int src_ld, int src_col0, int ncols,
                                         int B, int T) {
     long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -407,6 +415,7 @@ static __global__ void stage_rows_split_kernel(__nv_bfloat16* __restrict__ Ahi, 
     split_bf16(src[((long long)w * T + f) * src_ld + src_col0 + c], hi, lo);
     long long o = ((long long)w * LP + 1 + f) * lda + c;
     Ahi[o] = hi; Alo[o] = lo;
+    if (A16) A16[o] = __float2half_rn(src[((long long)w * T + f) * src_ld + src_col0 + c]);
 }
 
 // DDPM update (p_mean_variance tail + p_sample, transformer_cond_diffusion_model.py:235-256) fused with
@@ -422,6 +431,7 @@ struct DdpmArgs {
     const float* inpaint; int inpaint_len;
     float* stage_f32; int stage_ld;                                  // SIMT engine A operand (nullable)
     __nv_bfloat16* stage_hi; __nv_bfloat16* stage_lo; int stage_ld16; // tensor engine A operand (nullable)
+    __half* stage_h16;                                                // fp16 plane for FMT_HALF steps (nullable)
     TSrc ts; NoiseSrc ns;
     int B, T, D;
 };
@@ -466,6 +476,7 @@ static __global__ void ddpm_update_kernel(DdpmArgs a) {
             split_bf16(v, hi, lo);
             long long o = ((long long)w * LP + 1 + f) * a.stage_ld16 + c;
             a.stage_hi[o] = hi; a.stage_lo[o] = lo;
+            if (a.stage_h16) a.stage_h16[o] = __float2half_rn(v);
         }
     }
 }

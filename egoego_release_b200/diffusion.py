@@ -139,7 +139,7 @@ class CondGaussianDiffusion(nn.Module):
     def __init__(self, d_feats, d_model, n_head, n_dec_layers, d_k, d_v, max_timesteps, out_dim,
                  timesteps=1000, loss_type='l1', objective='pred_noise', beta_schedule='cosine',
                  p2_loss_weight_gamma=0., p2_loss_weight_k=1, batch_size=None,
-                 max_batch: int = 256, engine: Optional[str] = None):
+                 max_batch: int = 256, engine: Optional[str] = None, precise_last_steps: int = -1):
         super().__init__()
         import weakref
         self.denoise_fn = TransformerDiffusionModel(d_feats=d_feats, d_model=d_model, n_head=n_head, d_k=d_k, d_v=d_v,
@@ -183,6 +183,7 @@ class CondGaussianDiffusion(nn.Module):
         self._cfg = dict(d_feats=d_feats, d_model=d_model, n_head=n_head, n_dec_layers=n_dec_layers, d_k=d_k, d_v=d_v,
                          max_timesteps=max_timesteps)
         self._max_batch = int(max_batch)
+        self._precise_last_steps = int(precise_last_steps)   # -1: default policy ceil(N/4); N: every step 3-term split
         eng = engine or os.environ.get("EGOEGO_ENGINE", DEFAULT_ENGINE)
         if eng not in ("tcgen05", "simt"):
             raise ValueError(f"unknown engine {eng}")
@@ -238,7 +239,7 @@ class CondGaussianDiffusion(nn.Module):
                 raise ValueError(f'unknown objective {self.objective}')
             cfg = Cfg(timesteps=self.num_timesteps, objective=1 if self.objective == 'pred_x0' else 0,
                       max_batch=self._max_batch, device=dev.index if dev.index is not None else torch.cuda.current_device(),
-                      engine=self._engine, **self._cfg)
+                      engine=self._engine, precise_last_steps=self._precise_last_steps, **self._cfg)
             h = C.c_void_p()
             check(L.egoego_create(C.byref(cfg), C.byref(h)))
             self._h, self._h_device, self._weights_sig, self._skeleton_sig = h, dev, None, None

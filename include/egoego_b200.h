@@ -53,6 +53,10 @@ typedef struct egoego_cfg {
     int32_t max_batch;     /* workspace is sized for this many windows per call        */
     int32_t device;        /* CUDA ordinal                                             */
     int32_t engine;        /* EGOEGO_ENGINE_*                                          */
+    int32_t precise_last_steps; /* tensor engine precision policy: the last K diffusion steps (t < K) use the
+                              3-term bf16 split (fp32-grade); earlier steps one fp16 pass, whose error is damped
+                              by posterior_mean_coef1[t].  -1 = default ceil(timesteps/4); timesteps = all steps
+                              split.  The per-call entry points (denoiser_forward, p_sample_step) always split. */
 } egoego_cfg;
 
 enum {
@@ -153,9 +157,10 @@ int64_t egoego_launch_count(egoego_handle h);
 /* Self test of the tensor-core GEMM primitive: C = A W^T (A[M,K], W[N,K] random fp32) computed by the
  * tcgen05 3-term bf16-split kernel and by the fp32 CUDA-core kernel; reports max |difference|, max |reference|
  * and the average device time of one tcgen05 launch in milliseconds.  M%128 == N%256 == K%64 == 0.
- * two_cta != 0 selects the CTA-pair kernel (cta_group::2, 256x256 tiles; needs M%256 == 0). */
-int  egoego_selftest_gemm(int device, int M, int N, int K, uint64_t seed, int two_cta, float* max_abs_err,
-                          float* max_abs_ref, float* ms_per_launch);
+ * two_cta != 0 selects the CTA-pair kernel (cta_group::2, 256x256 tiles; needs M%256 == 0); half_fmt != 0 the
+ * single-pass fp16 operand format (errors are then fp16-grade, ~1e-3 relative). */
+int  egoego_selftest_gemm(int device, int M, int N, int K, uint64_t seed, int two_cta, int half_fmt,
+                          float* max_abs_err, float* max_abs_ref, float* ms_per_launch);
 
 #ifdef __cplusplus
 }
