@@ -652,7 +652,27 @@ int egoego_canonicalize_head(egoego_handle c, const float* head_pos, const float
     return 0;
 }
 
+int egoego_tail_condition(egoego_handle c, const float* gquat, const float* gjpos, int B, int n, float* inpaint_out, void* stream_v) {
+    EG_CHECK(c && gquat && gjpos && inpaint_out, "null argument");
+    EG_CHECK(c->have_sk, "egoego_set_skeleton has not been called");
+    EG_CHECK(c->D == 198 && B >= 1 && n >= 1, "bad shape");
+    EG_CUDA(cudaSetDevice(c->cfg.device));
+    tail_condition_kernel<<<(B * n + 7) / 8, 256, 0, (cudaStream_t)stream_v>>>(c->sk, gquat, gjpos, B, n, inpaint_out);
+    c->launches++;
+    EG_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int64_t egoego_launch_count(egoego_handle c) { return c ? c->launches : -1; }
+
+int egoego_time_dominant_kernel(egoego_handle c, int B, int half_fmt, int iters, float* ms_per_launch, void* stream_v) {
+    EG_CHECK(c && ms_per_launch, "null argument");
+    EG_CHECK(c->committed && c->cfg.engine == EGOEGO_ENGINE_TCGEN05, "needs a committed tensor-core engine");
+    EG_CUDA(cudaSetDevice(c->cfg.device));
+    return c->tc->time_qkv(B, half_fmt ? 1 : 0, iters, (cudaStream_t)stream_v, ms_per_launch);
+}
+
+int egoego_precise_last_steps(egoego_handle c) { return c ? c->precise_last : -1; }
 
 int egoego_selftest_gemm(int device, int M, int N, int K, uint64_t seed, int two_cta, int half_fmt, float* max_abs_err, float* max_abs_ref, float* ms) {
     EG_CHECK(max_abs_err && max_abs_ref && ms, "null argument");

@@ -311,6 +311,36 @@ int TcEngine::denoiser(int B, int T, TSrc ts, const float* pmask, float* model_o
     return rc;
 }
 
+// Time the dominant kernel (fused QKV projection of layer 0, attention-plane epilogue) in isolation on the engine's
+// own buffers: `iters` back-to-back launches between two CUDA events on stream `s`.
+int TcEngine::time_qkv(int B, int fmt, int iters, cudaStream_t s, float* ms) {
+    TcImpl* I = impl_;
+    EG_CHECK(I && I->attn_tc, "time_qkv needs the tensor-core attention layout");
+    EG_CHECK(B >= 1 && B <= I->w.max_batch && iters >= 1, "bad arguments");
+    const int d = I->w.d, H = I->w.H, dk = I->w.dk, nqkv = 3 * H * dk, Mg = Mr(B);
+    TcLayer& W = I->layers[0];
+    cudaEvent_t e0, e1;
+    EG_CUDA(cudaEventCreate(&e0)); EG_CUDA(cudaEventCreate(&e1));
+    auto run = [&]() -> int {
+        if (fmt == FMT_HALF) {
+            TcEpiQKVPlanes<FMT_HALF> eq{I->Qp.hi, I->Qp.lo, I->Kp.hi, I->Kp.lo, I->VT.hi, I->VT.lo, W.bqkv, H, 1.0f / sqrtf((float)dk)};
+            return gemm<FMT_HALF>(I, I->Hs, W.wqkv, Mg, nqkv, d, eq, s);
+        }
+        TcEpiQKVPlanes<FMT_SPLIT> eq{I->Qp.hi, I->Qp.lo, I->Kp.hi, I->Kp.lo, I->VT.hi, I->VT.lo, W.bqkv, H, 1.0f / sqrtf((float)dk)};
+        return gemm<FMT_SPLIT>(I, I->Hs, W.wqkv, Mg, nqkv, d, eq, s);
+    };
+    for (int i = 0; i < 3; ++i) if (run()) return 1;
+    EG_CUDA(cudaEventRecord(e0, s));
+    for (int i = 0; i < iters; ++i) if (run()) return 1;
+    EG_CUDA(cudaEventRecord(e1, s));
+    EG_CUDA(cudaEventSynchronize(e1));
+    float t = 0.f;
+    EG_CUDA(cudaEventElapsedTime(&t, e0, e1));
+    *ms = t / iters;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return 0;
+}
+
 // ---- self test: split GEMM against the fp32 SIMT GEMM on random data ------------------------------
 __global__ void fill_uniform_kernel(float* p, long long n, unsigned long long seed, float scale) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

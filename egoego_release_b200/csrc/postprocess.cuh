@@ -254,4 +254,48 @@ static __global__ void canonicalize_head_kernel(Skeleton sk, const float* __rest
     for (int c = 0; c < 6; ++c) xs[66 + HEAD_IDX * 6 + c] = Rm.m[c];
 }
 
+// Conditioning of the NEXT sliding window from the tail of the current one (reference :423-464): the last `n`
+// frames' FK result (global quaternions / joint positions) is re-canonicalised at its first frame (yaw of the head
+// joint, x/y of the head moved to 0), positions are min-max normalised and rotations converted to rot6d, giving the
+// [B, n, 198] tensor that overwrites the first n frames after every step of the next window.
+// One warp per frame, lane = joint.
+static __global__ void __launch_bounds__(256) tail_condition_kernel(Skeleton sk, const float* __restrict__ gquat,
+                                                                    const float* __restrict__ gjpos, int B, int n,
+                                                                    float* __restrict__ out) {
+    const int frame = blockIdx.x * 8 + threadIdx.x / 32;
+    const int j = threadIdx.x % 32;
+    if (frame >= B * n) return;
+    const int w = frame / n;
+    const float* q0 = gquat + ((long long)w * n * NJ + HEAD_IDX) * 4;      // head joint, first frame of the tail
+    const float* p0 = gjpos + ((long long)w * n * NJ + HEAD_IDX) * 3;
+    Q4 key = {q0[0], q0[1], q0[2], q0[3]};
+    const float ex[3] = {1.f, 0.f, 0.f};
+    float fw[3];
+    qv_rot(key, ex, fw);
+    fw[2] = 0.f;
+    float fn = sqrtf(fw[0] * fw[0] + fw[1] * fw[1]) + 1e-8f;
+    fw[0] /= fn; fw[1] /= fn;
+    float yw = sqrtf(fw[0] * fw[0] + fw[1] * fw[1]) + fw[0];
+    float yy = -fw[2], yz = fw[1];
+    float yn = sqrtf(yw * yw + yy * yy + yz * yz) + 1e-8f;
+    Q4 yrot = {yw / yn, 0.f, yy / yn, yz / yn};
+    Q4 inv = q_inv(yrot);
+    float hp[3] = {p0[0], p0[1], p0[2]}, a0[3];
+    qv_rot(inv, hp, a0);                                   // rotate_at_frame_smplh on the head positions, frame 0
+    if (j >= NJ) return;
+    const float* pj = gjpos + ((long long)frame * NJ + j) * 3;
+    const float* qj = gquat + ((long long)frame * NJ + j) * 4;
+    float pin[3] = {pj[0], pj[1], pj[2]}, pr[3];
+    q_apply(inv, pin, pr);
+    pr[0] -= a0[0]; pr[1] -= a0[1];
+    float* o = out + (long long)frame * 198;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+        o[j * 3 + c] = (pr[c] - sk.jmin[j * 3 + c]) / (sk.jmax[j * 3 + c] - sk.jmin[j * 3 + c]) * 2.0f - 1.0f;
+    Q4 qq = {qj[0], qj[1], qj[2], qj[3]};
+    M3 Rm = q_to_mat(q_mul(inv, qq));
+#pragma unroll
+    for (int c = 0; c < 6; ++c) o[66 + j * 6 + c] = Rm.m[c];
+}
+
 }  // namespace egoego

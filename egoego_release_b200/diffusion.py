@@ -260,6 +260,19 @@ class CondGaussianDiffusion(nn.Module):
         self._weights_sig = None
         self._handle()
 
+    def precise_last_steps(self) -> int:
+        """Resolved precision policy of the engine: diffusion steps t < K use the 3-term split."""
+        return int(_capi.lib().egoego_precise_last_steps(self._handle()))
+
+    def time_dominant_kernel(self, B: int, half_fmt: bool, iters: int = 20) -> float:
+        """ms per launch of the fused QKV projection kernel (CUDA events on the current stream)."""
+        h = self._handle()
+        dev = self._device()
+        ms = C.c_float()
+        with torch.cuda.device(dev):
+            check(_capi.lib().egoego_time_dominant_kernel(h, B, 1 if half_fmt else 0, iters, C.byref(ms), _stream(dev)))
+        return float(ms.value)
+
     def launch_count(self) -> int:
         return int(_capi.lib().egoego_launch_count(self._h)) if self._h is not None else 0
 
@@ -487,22 +500,14 @@ class CondGaussianDiffusion(nn.Module):
         return whole_aa, whole_root
 
     def _tail_condition(self, ds, gq, gj):
-        """Reference :423-464 on device tensors (tiny: b x 10 frames).  Uses the library's canonicalisation for the
-        yaw and torch tensor ops only for indexing/affine glue on [b,10,22,*] tensors."""
-        b = gq.shape[0]
-        _, rq = self.canonicalize_head(ds, gj[:, :, HEAD_IDX, :].contiguous(), gq[:, :, HEAD_IDX, :].contiguous())
-        inv = rq * rq.new_tensor([1, -1, -1, -1])
-        inv = inv[:, None, None, :].expand(b, gj.shape[1], 22, 4)
-        gj_c = _quat_apply(inv, gj)
-        tmz = gj_c[:, 0:1, HEAD_IDX, :].clone()
-        tmz[:, :, 2] = 0
-        gj_c = gj_c - tmz[:, :, None, :]
-        jmin = ds.global_jpos_min.to(gj.device).reshape(1, 1, 22, 3)
-        jmax = ds.global_jpos_max.to(gj.device).reshape(1, 1, 22, 3)
-        prev_jpos = (gj_c - jmin) / (jmax - jmin) * 2 - 1
-        pq = _quat_std(_quat_raw_mul(inv, gq))
-        r6 = _quat_to_rot6d(pq)
-        return torch.cat((prev_jpos.reshape(b, -1, 66), r6.reshape(b, -1, 132)), dim=-1).contiguous()
+        """Reference :423-464 in the CUDA library: [b,n,22,4] / [b,n,22,3] tail FK -> in-paint tensor [b,n,198]."""
+        h = self._set_skeleton(ds)
+        dev = self._device()
+        b, n = gq.shape[0], gq.shape[1]
+        out = torch.empty(b, n, 198, device=dev)
+        with torch.cuda.device(dev):
+            check(_capi.lib().egoego_tail_condition(h, _ptr(gq), _ptr(gj), b, n, _ptr(out), _stream(dev)))
+        return out
 
     @torch.no_grad()
     def sample_sliding_window_w_canonical(self, ds, global_head_jpos, global_head_jquat, x_start, cond_mask, noise_fn=None):
@@ -524,27 +529,3 @@ class CondGaussianDiffusion(nn.Module):
 
     def forward(self, x_start, cond_mask, padding_mask=None):
         raise NotImplementedError("training (q_sample / p_losses / forward) is outside the B200 sampling path")
-
-
-# -- tiny tensor glue for the [b,10,22,*] tail conditioning (index/affine only; no model math) --------
-def _quat_raw_mul(a, b):
-    aw, ax, ay, az = a.unbind(-1)
-    bw, bx, by, bz = b.unbind(-1)
-    return torch.stack((aw * bw - ax * bx - ay * by - az * bz, aw * bx + ax * bw + ay * bz - az * by,
-                        aw * by - ax * bz + ay * bw + az * bx, aw * bz + ax * by - ay * bx + az * bw), -1)
-
-
-def _quat_std(q):
-    return torch.where(q[..., 0:1] < 0, -q, q)
-
-
-def _quat_apply(q, p):
-    p4 = torch.cat((torch.zeros_like(p[..., :1]), p), -1)
-    return _quat_raw_mul(_quat_raw_mul(q, p4), q * q.new_tensor([1, -1, -1, -1]))[..., 1:]
-
-
-def _quat_to_rot6d(q):
-    r, i, j, k = q.unbind(-1)
-    two_s = 2.0 / (q * q).sum(-1)
-    return torch.stack((1 - two_s * (j * j + k * k), two_s * (i * j - k * r), two_s * (i * k + j * r),
-                        two_s * (i * j + k * r), 1 - two_s * (i * i + k * k), two_s * (j * k - i * r)), -1)

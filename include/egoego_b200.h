@@ -18,6 +18,7 @@
  *                             (..._diffusion_model.py:469-525; egoego/data/amass_diffusion_dataset.py:265-293)
  *   egoego_canonicalize_head  rotate_at_frame_smplh + x_start build       (egoego/lafan1/utils.py:111-137;
  *                                                                           ..._diffusion_model.py:358-386)
+ *   egoego_tail_condition     next-window conditioning from the tail      (..._diffusion_model.py:423-464)
  *
  * Conventions: every pointer is BORROWED for the duration of the call; the caller owns all buffers,
  * the library owns only its workspace and packed weights.  "dev" pointers are CUDA device pointers on
@@ -150,9 +151,22 @@ int  egoego_canonicalize_head(egoego_handle h, const float* head_pos_dev, const 
                               int64_t pos_stride_frames, int B, int T,
                               float* x_start_dev, float* recover_quat_dev, void* stream);
 
+/* Conditioning of the next sliding window (reference :423-464): FK result of the last n frames of a window,
+ * gquat[B,n,22,4] (wxyz) / gjpos[B,n,22,3], re-canonicalised at the tail's first frame, normalised and converted to
+ * rot6d -> inpaint_out[B,n,198] (the tensor egoego_sample's `inpaint_dev` expects). */
+int  egoego_tail_condition(egoego_handle h, const float* gquat_dev, const float* gjpos_dev, int B, int n,
+                           float* inpaint_out_dev, void* stream);
+
 /* Introspection for tests/bench: number of kernels launched by this handle since creation, and the
  * cumulative count of denoiser steps executed. */
 int64_t egoego_launch_count(egoego_handle h);
+
+/* Measurement hook (bench.py roofline): average device time of one launch of the dominant kernel -- the fused QKV
+ * projection GEMM of layer 0 with its attention-plane epilogue -- over `iters` back-to-back launches on `stream`,
+ * timed with CUDA events on that stream.  Operates on the handle's own workspace for B windows. */
+int  egoego_time_dominant_kernel(egoego_handle h, int B, int half_fmt, int iters, float* ms_per_launch, void* stream);
+/* Resolved precision policy: steps t < K run the 3-term split (see egoego_cfg.precise_last_steps). */
+int  egoego_precise_last_steps(egoego_handle h);
 
 /* Self test of the tensor-core GEMM primitive: C = A W^T (A[M,K], W[N,K] random fp32) computed by the
  * tcgen05 3-term bf16-split kernel and by the fp32 CUDA-core kernel; reports max |difference|, max |reference|
