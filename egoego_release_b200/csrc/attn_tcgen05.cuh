@@ -27,6 +27,15 @@ constexpr int ATT_SMEM_BYTES = ATT_STAGES * ATT_STAGE_BYTES + ATT_P_BYTES + 1024
 constexpr int ATT_THREADS = 192;
 
 template <int FMT>
+struct OStore : EpiNoDirect {              // attention output rows -> operand planes of the fc GEMM
+    __nv_bfloat16* hi; __nv_bfloat16* lo; long long base; int ld;
+    __device__ __forceinline__ void apply4(int row, int col, float4 a) const {
+        const long long o = base + (long long)row * ld + col;
+        store_planes4<FMT>(hi + o, lo + o, a);
+    }
+};
+
+template <int FMT>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_constant__ CUtensorMap mQl,
                     const __grid_constant__ CUtensorMap mKh, const __grid_constant__ CUtensorMap mKl,
@@ -198,18 +207,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_consta
             // ---- O epilogue ----
             ptx::mbar_wait(o_full, iph);
             ptx::tc_fence_after();
+            // P(i) has been consumed once o_full fired: its smem is reused as the per-warp transpose tiles of the
+            // coalesced O store (softmax of item i+1 rewrites it only after this epilogue).
             const int w = item / n_head, h = item % n_head;
-            const long long obase = ((long long)w * LP + r) * ldo + h * 256;
+            float4* tile = reinterpret_cast<float4*>(p_smem) + (warp - 2) * 256;
+            OStore<FMT> ost{{}, Ohi, Olo, ((long long)w * LP) * ldo + h * 256, ldo};
 #pragma unroll 1
             for (int c = 0; c < 8; ++c) {
                 uint32_t raw[32];
                 ptx::tmem_ld_32x32(lane_addr + TM_O + c * 32, raw);
                 ptx::tmem_ld_wait();
-                float o[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(raw[j]);
-#pragma unroll
-                for (int j = 0; j < 32; j += 8) store_planes8<FMT>(Ohi + obase + c * 32 + j, Olo + obase + c * 32 + j, o + j);
+                epilogue_chunk(ost, tile, raw, lane, quarter * 32, c * 32);
             }
             ptx::tc_fence_before();
             ptx::mbar_arrive(o_free);
@@ -221,41 +229,38 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_consta
 }
 
 // QKV projection epilogue writing the attention operand planes directly (one 256-wide tile = one (section, head)).
+// Q / K sections use the coalesced apply4 path; the V section's destination is transposed ([dim][token]), for which
+// the accumulator's native thread-per-row layout is the coalesced one (32 lanes = 32 consecutive tokens).
 template <int FMT>
 struct TcEpiQKVPlanes {
     __nv_bfloat16 *Qh, *Ql, *Kh, *Kl, *Vh, *Vl;       // Q,K: [(w*H+h)*128 + l][256];  V^T: [(w*H+h)*256 + c][128]
     const float* bias; int n_head; float q_scale;
-    __device__ __forceinline__ void operator()(int row, int col0, const float (&v)[32]) const {
+    __device__ __forceinline__ bool direct(int col0) const { return col0 >= 2 * n_head * 256; }
+    __device__ __forceinline__ void apply_row(int row, int col0, const float (&v)[32]) const {
         const int w = row / LP, l = row % LP;
-        const int sec = col0 / (n_head * 256), hc = col0 % (n_head * 256);
-        const int h = hc / 256, c0 = hc % 256;
-        float r[32];
+        const int hc = col0 - 2 * n_head * 256, h = hc / 256, c0 = hc % 256;
+        const long long base = ((long long)(w * n_head + h) * 256 + c0) * 128 + l;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = v[j] + bias[col0 + j];
-        if (sec == 2) {
-            const long long base = ((long long)(w * n_head + h) * 256 + c0) * 128 + l;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                if (FMT == FMT_SPLIT) {
-                    __nv_bfloat16 hi, lo;
-                    split_bf16(r[j], hi, lo);
-                    Vh[base + (long long)j * 128] = hi;
-                    Vl[base + (long long)j * 128] = lo;
-                } else {
-                    reinterpret_cast<__half*>(Vh)[base + (long long)j * 128] = __float2half_rn(r[j]);
-                }
+        for (int j = 0; j < 32; ++j) {
+            const float r = v[j] + bias[col0 + j];
+            if (FMT == FMT_SPLIT) {
+                __nv_bfloat16 hi, lo;
+                split_bf16(r, hi, lo);
+                Vh[base + (long long)j * 128] = hi;
+                Vl[base + (long long)j * 128] = lo;
+            } else {
+                reinterpret_cast<__half*>(Vh)[base + (long long)j * 128] = __float2half_rn(r);
             }
-        } else {
-            __nv_bfloat16* ph = sec == 0 ? Qh : Kh;
-            __nv_bfloat16* pl = sec == 0 ? Ql : Kl;
-            if (sec == 0) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) r[j] *= q_scale;
-            }
-            const long long o = ((long long)(w * n_head + h) * 128 + l) * 256 + c0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) store_planes8<FMT>(ph + o + j, pl + o + j, r + j);
         }
+    }
+    __device__ __forceinline__ void apply4(int row, int col, float4 a) const {
+        const int w = row / LP, l = row % LP;
+        const int sec = col / (n_head * 256), hc = col % (n_head * 256);
+        const int h = hc / 256, c = hc % 256;
+        a = add4(a, ld4(bias + col));
+        if (sec == 0) a = make_float4(a.x * q_scale, a.y * q_scale, a.z * q_scale, a.w * q_scale);
+        const long long o = ((long long)(w * n_head + h) * 128 + l) * 256 + c;
+        store_planes4<FMT>((sec == 0 ? Qh : Kh) + o, (sec == 0 ? Ql : Kl) + o, a);
     }
 };
 

@@ -39,23 +39,48 @@ template <int BN, int FMT> struct GemmCfg {
     static constexpr int NP = FmtTraits<FMT>::NP;
     static constexpr int STAGE_BYTES = NP * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2);   // A planes then W planes
     static constexpr int STAGES = (FMT == FMT_SPLIT) ? 2 : 4;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 4 * 4096 /*epilogue tiles*/ + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-// ---- epilogues: called with 32 consecutive fp32 columns of one output row ------------------------
-struct TcEpiPlain {                       // C = acc (+ bias): self-test / generic
-    float* C; int ldc; const float* bias; int n_valid;
-    __device__ __forceinline__ void operator()(int row, int col0, const float (&v)[32]) const {
-        float* o = C + (long long)row * ldc + col0;
+// ---- epilogues -----------------------------------------------------------------------------------------
+// tcgen05.ld hands each thread one accumulator ROW (32 consecutive columns).  Writing global memory in that layout
+// touches 32 cache lines per warp instruction (measured: 32 sectors/request, LSU-bound epilogue), so each epilogue
+// warp first transposes its 32x32 chunk through a private 4 KB shared-memory tile (XOR-swizzled, conflict-free) and
+// then runs the fused epilogue in a COALESCED layout: a lane owns 4 consecutive columns of one row, 8 lanes cover a
+// 128-byte row segment, one warp instruction touches 4 full lines.  Functors implement
+//     apply4(row, col, float4 acc)          coalesced element-wise epilogue (bias/residual/activation/split/store)
+//     direct(col0) / apply_row(...)         optional thread-per-row path for TRANSPOSED destinations (V^T), where
+//                                           the thread=row layout is already the coalesced one.
+constexpr int EPI_TILE_BYTES = 32 * 32 * 4;              // per epilogue warp
+
+template <class Epi>
+__device__ __forceinline__ void epilogue_chunk(const Epi& epi, float4* tile, const uint32_t (&raw)[32], int lane,
+                                               int row_base /* first row of this warp's 32 */, int col0) {
+    if (epi.direct(col0)) {                                // warp-uniform
+        float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-            if (col0 + j < n_valid) {
-                float4 r = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                if (bias) { r.x += bias[col0 + j]; r.y += bias[col0 + j + 1]; r.z += bias[col0 + j + 2]; r.w += bias[col0 + j + 3]; }
-                *reinterpret_cast<float4*>(o + j) = r;
-            }
-        }
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+        epi.apply_row(row_base + lane, col0, v);
+        return;
     }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        tile[lane * 8 + (j ^ (lane & 7))] = make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]),
+                                                        __uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3]));
+    __syncwarp();
+    const int j = lane & 7;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int r = it * 4 + (lane >> 3);
+        const float4 acc = tile[r * 8 + (j ^ (r & 7))];
+        epi.apply4(row_base + r, col0 + 4 * j, acc);
+    }
+    __syncwarp();
+}
+
+struct EpiNoDirect {
+    __device__ __forceinline__ bool direct(int) const { return false; }
+    __device__ __forceinline__ void apply_row(int, int, const float (&)[32]) const {}
 };
 
 __device__ __forceinline__ void store_half8(__nv_bfloat16* dst /* fp16 bits */, const float* v) {
@@ -86,105 +111,96 @@ __device__ __forceinline__ void store_planes8(__nv_bfloat16* hi, __nv_bfloat16* 
     if (FMT == FMT_SPLIT) store_split8(hi, lo, v); else store_half8(hi, v);
 }
 
-struct TcEpiBase {                        // base = x_cond-half of start_conv + bias + positional row (constant per window)
+// 4 consecutive values -> operand plane(s): 8 bytes per plane
+template <int FMT>
+__device__ __forceinline__ void store_planes4(__nv_bfloat16* hi, __nv_bfloat16* lo, float4 v) {
+    if (FMT == FMT_SPLIT) {
+        __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
+        split_bf16(v.x, h0, l0); split_bf16(v.y, h1, l1); split_bf16(v.z, h2, l2); split_bf16(v.w, h3, l3);
+        __nv_bfloat162 a0(h0, h1), a1(h2, h3), b0(l0, l1), b1(l2, l3);
+        *reinterpret_cast<uint2*>(hi) = make_uint2(*reinterpret_cast<uint32_t*>(&a0), *reinterpret_cast<uint32_t*>(&a1));
+        *reinterpret_cast<uint2*>(lo) = make_uint2(*reinterpret_cast<uint32_t*>(&b0), *reinterpret_cast<uint32_t*>(&b1));
+    } else {
+        __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+        *reinterpret_cast<uint2*>(hi) = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+    }
+}
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+
+struct TcEpiPlain : EpiNoDirect {         // C = acc (+ bias): self-test / generic
+    float* C; int ldc; const float* bias; int n_valid;
+    __device__ __forceinline__ void apply4(int row, int col, float4 a) const {
+        if (col >= n_valid) return;
+        if (bias) a = add4(a, ld4(bias + col));
+        *reinterpret_cast<float4*>(C + (long long)row * ldc + col) = a;
+    }
+};
+
+struct TcEpiBase : EpiNoDirect {          // base = x_cond-half of start_conv + bias + positional row (constant per window)
     float* base; int ld; const float* bias; const float* pos; int T;
-    __device__ __forceinline__ void operator()(int row, int col0, const float (&v)[32]) const {
+    __device__ __forceinline__ void apply4(int row, int col, float4 a) const {
         const int l = row % LP;
-        float* o = base + (long long)row * ld + col0;
-        const bool live = (l >= 1 && l <= T);
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-            float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (live) {
-                const float* p = pos + (long long)(l + 1) * ld + col0 + j;
-                r.x = v[j] + bias[col0 + j] + p[0]; r.y = v[j + 1] + bias[col0 + j + 1] + p[1];
-                r.z = v[j + 2] + bias[col0 + j + 2] + p[2]; r.w = v[j + 3] + bias[col0 + j + 3] + p[3];
-            }
-            *reinterpret_cast<float4*>(o + j) = r;
-        }
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (l >= 1 && l <= T) r = add4(add4(a, ld4(bias + col)), ld4(pos + (long long)(l + 1) * ld + col));
+        *reinterpret_cast<float4*>(base + (long long)row * ld + col) = r;
     }
 };
 
 template <int FMT>
-struct TcEpiStart {                       // H = x-half GEMM + base ; row 0 = time token ; writes fp32 + operand planes
+struct TcEpiStart : EpiNoDirect {         // H = x-half GEMM + base ; row 0 = time token ; writes fp32 + operand planes
     float* H; __nv_bfloat16* Hhi; __nv_bfloat16* Hlo; int ld;
     const float* base; const float* pos; const float* temb; TSrc ts; int T; int n_windows;
-    __device__ __forceinline__ void operator()(int row, int col0, const float (&v)[32]) const {
+    __device__ __forceinline__ void apply4(int row, int col, float4 a) const {
         const int w = row / LP;
         const int l = (w < n_windows) ? row % LP : LP;      // rows of the rounding-up window are padding
-        float r[32];
-        if (l == 0) {
-            const float* te = temb + (long long)ts.get(w) * ld + col0;
-            const float* p1 = pos + ld + col0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) r[j] = te[j] + p1[j];
-        } else if (l <= T) {
-            const float* b = base + (long long)row * ld + col0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) r[j] = v[j] + b[j];
-        } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) r[j] = 0.f;
-        }
-        const long long o = (long long)row * ld + col0;
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(H + o + j) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) store_planes8<FMT>(Hhi + o + j, Hlo + o + j, r + j);
+        float4 r;
+        if (l == 0)      r = add4(ld4(temb + (long long)ts.get(w) * ld + col), ld4(pos + ld + col));
+        else if (l <= T) r = add4(a, ld4(base + (long long)row * ld + col));
+        else             r = make_float4(0.f, 0.f, 0.f, 0.f);
+        const long long o = (long long)row * ld + col;
+        *reinterpret_cast<float4*>(H + o) = r;
+        store_planes4<FMT>(Hhi + o, Hlo + o, r);
     }
 };
 
-struct TcEpiBiasScaleF32 {                // QKV projection -> fp32 [M, ldc] (q block pre-scaled by 1/sqrt(d_k))
+struct TcEpiBiasScaleF32 : EpiNoDirect {  // QKV projection -> fp32 [M, ldc] (q block pre-scaled by 1/sqrt(d_k))
     float* C; int ldc; const float* bias; int scale_cols; float scale;
-    __device__ __forceinline__ void operator()(int row, int col0, const float (&v)[32]) const {
-        float* o = C + (long long)row * ldc + col0;
-        const float s = col0 < scale_cols ? scale : 1.0f;
-#pragma unroll
-        for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(o + j) = make_float4((v[j] + bias[col0 + j]) * s, (v[j + 1] + bias[col0 + j + 1]) * s,
-                                                            (v[j + 2] + bias[col0 + j + 2]) * s, (v[j + 3] + bias[col0 + j + 3]) * s);
+    __device__ __forceinline__ void apply4(int row, int col, float4 a) const {
+        const float s = col < scale_cols ? scale : 1.0f;
+        a = add4(a, ld4(bias + col));
+        *reinterpret_cast<float4*>(C + (long long)row * ldc + col) = make_float4(a.x * s, a.y * s, a.z * s, a.w * s);
     }
 };
 
-struct TcEpiBiasResidF32 {                // fc / w_2: acc + bias + residual -> fp32 (pre-LayerNorm)
+struct TcEpiBiasResidF32 : EpiNoDirect {  // fc / w_2: acc + bias + residual -> fp32 (pre-LayerNorm)
     float* C; int ldc; const float* bias; const float* res;
-    __device__ __forceinline__ void operator()(int row, int col0, const float (&v)[32]) const {
-        const long long o = (long long)row * ldc + col0;
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-            float4 r = *reinterpret_cast<const float4*>(res + o + j);
-            r.x += v[j] + bias[col0 + j]; r.y += v[j + 1] + bias[col0 + j + 1];
-            r.z += v[j + 2] + bias[col0 + j + 2]; r.w += v[j + 3] + bias[col0 + j + 3];
-            *reinterpret_cast<float4*>(C + o + j) = r;
-        }
+    __device__ __forceinline__ void apply4(int row, int col, float4 a) const {
+        const long long o = (long long)row * ldc + col;
+        *reinterpret_cast<float4*>(C + o) = add4(add4(a, ld4(bias + col)), ld4(res + o));
     }
 };
 
 template <int FMT>
-struct TcEpiBiasReluSplit {               // w_1: relu(acc + bias) -> operand planes (A operand of w_2)
+struct TcEpiBiasReluSplit : EpiNoDirect { // w_1: relu(acc + bias) -> operand planes (A operand of w_2)
     __nv_bfloat16* hi; __nv_bfloat16* lo; int ld; const float* bias;
-    __device__ __forceinline__ void operator()(int row, int col0, const float (&v)[32]) const {
-        float r[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = fmaxf(v[j] + bias[col0 + j], 0.f);
-        const long long o = (long long)row * ld + col0;
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) store_planes8<FMT>(hi + o + j, lo + o + j, r + j);
+    __device__ __forceinline__ void apply4(int row, int col, float4 a) const {
+        a = add4(a, ld4(bias + col));
+        a = make_float4(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f), fmaxf(a.z, 0.f), fmaxf(a.w, 0.f));
+        const long long o = (long long)row * ld + col;
+        store_planes4<FMT>(hi + o, lo + o, a);
     }
 };
 
-struct TcEpiOut {                         // linear_out: tokens 1..T, first d_feats columns -> compact [B,T,d_feats]
+struct TcEpiOut : EpiNoDirect {           // linear_out: tokens 1..T, first d_feats columns -> compact [B,T,d_feats]
     float* out; int d_feats; const float* bias; int T; int n_windows;
-    __device__ __forceinline__ void operator()(int row, int col0, const float (&v)[32]) const {
+    __device__ __forceinline__ void apply4(int row, int col, float4 a) const {
         const int w = row / LP, l = row % LP;
-        if (l < 1 || l > T || w >= n_windows) return;
-        float* o = out + ((long long)w * T + (l - 1)) * d_feats;
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-            const int c = col0 + j;
-            if (c + 1 < d_feats + 1 && c < d_feats)       // d_feats is even: pairs never straddle the edge
-                *reinterpret_cast<float2*>(o + c) = make_float2(v[j] + bias[c], v[j + 1] + bias[c + 1]);
-        }
+        if (l < 1 || l > T || w >= n_windows || col >= d_feats) return;
+        float* o = out + ((long long)w * T + (l - 1)) * d_feats + col;       // 8-byte aligned (d_feats even, col % 4 == 0)
+        *reinterpret_cast<float2*>(o) = make_float2(a.x + bias[col], a.y + bias[col + 1]);
+        if (col + 2 < d_feats) *reinterpret_cast<float2*>(o + 2) = make_float2(a.z + bias[col + 2], a.w + bias[col + 3]);
     }
 };
 
@@ -204,7 +220,8 @@ gemm_split3_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constan
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    float4* epi_tiles = reinterpret_cast<float4*>(smem + STAGES * Cfg::STAGE_BYTES);          // 4 x 4 KB
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + 4 * 4096);
     uint64_t* full_bar = bars;                         // [STAGES]
     uint64_t* empty_bar = bars + STAGES;               // [STAGES]
     uint64_t* tfull_bar = bars + 2 * STAGES;           // [2]
@@ -285,17 +302,14 @@ gemm_split3_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constan
             const int m0 = (tile / n_tiles) * GEMM_BM, n0 = (tile % n_tiles) * BN;
             ptx::mbar_wait(&tfull_bar[a], aph);
             ptx::tc_fence_after();
-            const int row = m0 + quarter * 32 + lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * BN;
+            float4* etile = epi_tiles + (warp - 2) * 256;
 #pragma unroll 1
             for (int c = 0; c < BN; c += 32) {
                 uint32_t r[32];
                 ptx::tmem_ld_32x32(taddr + c, r);
                 ptx::tmem_ld_wait();
-                float v[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                epi(row, n0 + c, v);
+                epilogue_chunk(epi, etile, r, lane, m0 + quarter * 32, n0 + c);
             }
             ptx::tc_fence_before();
             ptx::mbar_arrive(&tempty_bar[a]);
@@ -317,7 +331,7 @@ template <int FMT> struct Gemm2Cfg {
     static constexpr int NP = FmtTraits<FMT>::NP;
     static constexpr int STAGES = (FMT == FMT_SPLIT) ? 3 : 6;
     static constexpr int STAGE_BYTES = 2 * NP * GEMM_BM * GEMM_BK * 2;     // A planes + W-half planes, 16 KB each
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 4 * 4096 /*epilogue tiles*/ + 1024 + 256;
 };
 
 template <int FMT, class Epi>
@@ -333,7 +347,8 @@ gemm_split3_2cta_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_co
     constexpr uint32_t IDESC = (FMT == FMT_SPLIT) ? ptx::make_idesc_bf16(256, BN) : ptx::make_idesc_f16(256, BN);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GEMM2_STAGES * GEMM2_STAGE_BYTES);
+    float4* epi_tiles = reinterpret_cast<float4*>(smem + GEMM2_STAGES * GEMM2_STAGE_BYTES);   // 4 x 4 KB
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GEMM2_STAGES * GEMM2_STAGE_BYTES + 4 * 4096);
     uint64_t* full_bar = bars;                          // [S]  (used on the leader)
     uint64_t* empty_bar = bars + GEMM2_STAGES;          // [S]  (both CTAs)
     uint64_t* tfull_bar = bars + 2 * GEMM2_STAGES;      // [2]  (both CTAs)
@@ -418,17 +433,14 @@ gemm_split3_2cta_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_co
             const int m0 = (tile / n_tiles) * 256 + (int)rank * 128, n0 = (tile % n_tiles) * BN;
             ptx::mbar_wait(&tfull_bar[a], aph);
             ptx::tc_fence_after();
-            const int row = m0 + quarter * 32 + lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * BN;
+            float4* etile = epi_tiles + (warp - 2) * 256;
 #pragma unroll 1
             for (int c = 0; c < BN; c += 32) {
                 uint32_t r[32];
                 ptx::tmem_ld_32x32(taddr + c, r);
                 ptx::tmem_ld_wait();
-                float v[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                epi(row, n0 + c, v);
+                epilogue_chunk(epi, etile, r, lane, m0 + quarter * 32, n0 + c);
             }
             ptx::tc_fence_before();
             __syncwarp();
