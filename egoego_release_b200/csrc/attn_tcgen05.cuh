@@ -255,8 +255,9 @@ struct TcEpiQKVPlanes {
     }
     __device__ __forceinline__ void apply4(int row, int col, float4 a) const {
         const int w = row / LP, l = row % LP;
-        const int sec = col / (n_head * 256), hc = col % (n_head * 256);
-        const int h = hc / 256, c = hc % 256;
+        const int hw = n_head * 256;
+        const int sec = col >= hw ? 1 : 0, hc = col - sec * hw;
+        const int h = hc >> 8, c = hc & 255;
         a = add4(a, ld4(bias + col));
         if (sec == 0) a = make_float4(a.x * q_scale, a.y * q_scale, a.z * q_scale, a.w * q_scale);
         const long long o = ((long long)(w * n_head + h) * 128 + l) * 256 + c;

@@ -11,7 +11,7 @@
 // Structure (persistent, one CTA per SM, 192 threads):
 //   warp 0    TMA producer: cp.async.bulk.tensor 2D, 128B swizzle, mbarrier complete_tx
 //   warp 1    TMEM allocator + MMA issuer (one elected lane issues tcgen05.mma / tcgen05.commit)
-//   warps 2-5 epilogue: tcgen05.ld 32x32b -> registers -> fused epilogue -> global
+//   warps 2-9 epilogue: tcgen05.ld 32x32b -> registers -> smem transpose -> fused, coalesced epilogue -> global
 // Accumulators are double-buffered in TMEM (2 x BN columns of the 512) so the epilogue of tile i overlaps
 // the main loop of tile i+1.
 #pragma once
@@ -23,7 +23,8 @@ namespace egoego {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;            // 64 16-bit elements = 128 B = one swizzle row
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_EPI_WARPS = 8;                  // two warps per TMEM lane quarter, each takes half of the tile columns
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
 
 // Operand format of a GEMM / attention launch:
 //   FMT_SPLIT  bf16 hi/lo planes, three MMAs per k-step (fp32-grade; the default everywhere)
@@ -39,7 +40,7 @@ template <int BN, int FMT> struct GemmCfg {
     static constexpr int NP = FmtTraits<FMT>::NP;
     static constexpr int STAGE_BYTES = NP * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2);   // A planes then W planes
     static constexpr int STAGES = (FMT == FMT_SPLIT) ? 2 : 4;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 4 * 4096 /*epilogue tiles*/ + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + GEMM_EPI_WARPS * 4096 /*epilogue tiles*/ + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 // ---- epilogues -----------------------------------------------------------------------------------------
@@ -126,7 +127,9 @@ __device__ __forceinline__ void store_planes4(__nv_bfloat16* hi, __nv_bfloat16* 
     }
 }
 
-__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+// read-only inputs of an epilogue (bias, residual, tables) go through the non-coherent path so the compiler may
+// hoist all loads of a chunk above its stores
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
 struct TcEpiPlain : EpiNoDirect {         // C = acc (+ bias): self-test / generic
@@ -221,7 +224,7 @@ gemm_split3_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constan
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     float4* epi_tiles = reinterpret_cast<float4*>(smem + STAGES * Cfg::STAGE_BYTES);          // 4 x 4 KB
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + 4 * 4096);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + GEMM_EPI_WARPS * 4096);
     uint64_t* full_bar = bars;                         // [STAGES]
     uint64_t* empty_bar = bars + STAGES;               // [STAGES]
     uint64_t* tfull_bar = bars + 2 * STAGES;           // [2]
@@ -235,7 +238,7 @@ gemm_split3_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constan
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&mAh); ptx::prefetch_tmap(&mAl); ptx::prefetch_tmap(&mWh); ptx::prefetch_tmap(&mWl);
         for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], 128); }
+        for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], 32 * GEMM_EPI_WARPS); }
         ptx::fence_barrier_init();
     }
     if (warp == 1) { ptx::tmem_alloc(tmem_slot, 512); ptx::tmem_relinquish(); }
@@ -293,7 +296,7 @@ gemm_split3_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constan
                 ptx::umma_commit(&tfull_bar[a]);                            // accumulator ready for the epilogue
             }
         }
-    } else {                                             // ===== epilogue warps 2..5 =====
+    } else {                                             // ===== epilogue warps 2..9 =====
         const int quarter = warp & 3;                    // TMEM lane quarter this warp may access
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -304,8 +307,9 @@ gemm_split3_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constan
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * BN;
             float4* etile = epi_tiles + (warp - 2) * 256;
+            const int chalf = (warp - 2) >> 2;                 // which half of the tile columns this warp drains
 #pragma unroll 1
-            for (int c = 0; c < BN; c += 32) {
+            for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 32) {
                 uint32_t r[32];
                 ptx::tmem_ld_32x32(taddr + c, r);
                 ptx::tmem_ld_wait();
@@ -331,7 +335,7 @@ template <int FMT> struct Gemm2Cfg {
     static constexpr int NP = FmtTraits<FMT>::NP;
     static constexpr int STAGES = (FMT == FMT_SPLIT) ? 3 : 6;
     static constexpr int STAGE_BYTES = 2 * NP * GEMM_BM * GEMM_BK * 2;     // A planes + W-half planes, 16 KB each
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 4 * 4096 /*epilogue tiles*/ + 1024 + 256;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + GEMM_EPI_WARPS * 4096 /*epilogue tiles*/ + 1024 + 256;
 };
 
 template <int FMT, class Epi>
@@ -348,7 +352,7 @@ gemm_split3_2cta_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_co
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     float4* epi_tiles = reinterpret_cast<float4*>(smem + GEMM2_STAGES * GEMM2_STAGE_BYTES);   // 4 x 4 KB
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GEMM2_STAGES * GEMM2_STAGE_BYTES + 4 * 4096);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GEMM2_STAGES * GEMM2_STAGE_BYTES + GEMM_EPI_WARPS * 4096);
     uint64_t* full_bar = bars;                          // [S]  (used on the leader)
     uint64_t* empty_bar = bars + GEMM2_STAGES;          // [S]  (both CTAs)
     uint64_t* tfull_bar = bars + 2 * GEMM2_STAGES;      // [2]  (both CTAs)
@@ -365,7 +369,7 @@ gemm_split3_2cta_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_co
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&mAh); ptx::prefetch_tmap(&mAl); ptx::prefetch_tmap(&mWh); ptx::prefetch_tmap(&mWl);
         for (int s = 0; s < GEMM2_STAGES; ++s) { ptx::mbar_init(&full_bar[s], 2); ptx::mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], 8); }
+        for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], 2 * GEMM_EPI_WARPS); }
         ptx::fence_barrier_init();
     }
     if (warp == 1) { ptx::tmem_alloc_2cta(tmem_slot, 512); ptx::tmem_relinquish_2cta(); }
@@ -424,7 +428,7 @@ gemm_split3_2cta_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_co
                 ptx::umma_commit_2cta(&tfull_bar[a]);
             }
         }
-    } else {                                             // ===== epilogue warps 2..5 (both CTAs) =====
+    } else {                                             // ===== epilogue warps 2..9 (both CTAs) =====
         const int quarter = warp & 3;
         int it = 0;
         for (int tile = pair; tile < total_tiles; tile += n_pairs, ++it) {
@@ -435,8 +439,9 @@ gemm_split3_2cta_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_co
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * BN;
             float4* etile = epi_tiles + (warp - 2) * 256;
+            const int chalf = (warp - 2) >> 2;                 // which half of the tile columns this warp drains
 #pragma unroll 1
-            for (int c = 0; c < BN; c += 32) {
+            for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 32) {
                 uint32_t r[32];
                 ptx::tmem_ld_32x32(taddr + c, r);
                 ptx::tmem_ld_wait();
