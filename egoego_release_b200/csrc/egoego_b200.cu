@@ -529,9 +529,11 @@ static int sample_chunk(egoego_ctx* c, const float* x_start, const float* cond_m
             cudaGraphDestroy(g);
         }
         c->graph_B = Bc; c->graph_T = T; memcpy(c->graph_key, key, sizeof(key));
-        const int64_t per_step = (c->cfg.engine == EGOEGO_ENGINE_SIMT ? (2 + 7 * c->NL) : c->tc->launches_per_denoiser()) + 2;
-        for (int i = 0; i < N; ++i) EG_CUDA(cudaGraphLaunch(c->step_graph[fmt_of_step(i)], s));
-        c->launches += per_step * N;
+        for (int i = 0; i < N; ++i) {
+            const int fmt = fmt_of_step(i);
+            EG_CUDA(cudaGraphLaunch(c->step_graph[fmt], s));
+            c->launches += (c->cfg.engine == EGOEGO_ENGINE_SIMT ? (2 + 7 * c->NL) : c->tc->launches_per_denoiser(fmt)) + 2;
+        }
     } else {
         for (int i = 0; i < N; ++i) if (one_step(s, fmt_of_step(i))) return 1;
     }

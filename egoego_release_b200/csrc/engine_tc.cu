@@ -106,10 +106,12 @@ struct TcImpl {
     std::vector<TcLayer> layers;
     Plane X, C, Hs, O, F;                       // activation planes (A operands)
     Plane Qp, Kp, VT;                           // attention operand planes (see attn_tcgen05.cuh)
+    Plane Ident;                                // fp16 identity [512,512]: residual add as extra k-blocks of the fused-LN GEMM
+    bool fuse_ln = true;                        // EGOEGO_FUSE_LN=0 keeps GEMM + LayerNorm separate in the fp16 format too
     bool attn_tc = true;                        // EGOEGO_ATTN=simt selects the fp32 CUDA-core attention (bisecting)
     float *base = nullptr, *H = nullptr, *Y = nullptr, *QKV = nullptr;
     ~TcImpl() {
-        for (Plane* p : {&Wx, &Wc, &Wout, &X, &C, &Hs, &O, &F, &Qp, &Kp, &VT}) p->release();
+        for (Plane* p : {&Wx, &Wc, &Wout, &X, &C, &Hs, &O, &F, &Qp, &Kp, &VT, &Ident}) p->release();
         for (auto& l : layers) for (Plane* p : {&l.wqkv, &l.fc, &l.w1, &l.w2}) p->release();
         for (float* p : {base, H, Y, QKV}) if (p) cudaFree(p);
     }
@@ -137,7 +139,7 @@ static int launch_gemm(TcImpl* I, const Plane& A, const Plane& W, int M, int N, 
 
 static bool use_2cta() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("EGOEGO_GEMM"); v = (e && strcmp(e, "2cta") == 0) ? 1 : 0; }   // default: 1-CTA tiles
+    if (v < 0) { const char* e = getenv("EGOEGO_GEMM"); v = (e && strcmp(e, "1cta") == 0) ? 0 : 1; }   // default: CTA-pair tiles (10-12 % faster, profiles/)
     return v == 1;
 }
 
@@ -214,6 +216,15 @@ int TcEngine::init(const TcWeights& w, cudaStream_t) {
     EG_CUDA(cudaMalloc(&I->base, M * d * 4));
     EG_CUDA(cudaMalloc(&I->H, M * d * 4));
     EG_CUDA(cudaMalloc(&I->Y, M * d * 4));
+    {   // identity "weight" of the fused residual add (fp16 1.0 on the diagonal)
+        if (I->Ident.alloc(512, 512, 256)) return 1;
+        std::vector<__half> id((size_t)512 * 512, __float2half(0.f));
+        for (int i = 0; i < 512; ++i) id[(size_t)i * 512 + i] = __float2half(1.0f);
+        EG_CUDA(cudaMemcpy(I->Ident.hi, id.data(), id.size() * 2, cudaMemcpyHostToDevice));
+        const char* fl = getenv("EGOEGO_FUSE_LN");
+        I->fuse_ln = !(fl && fl[0] == '0');
+        EG_CUDA(cudaFuncSetAttribute(gemm_ln_half_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmLnCfg::SMEM_BYTES));
+    }
     const char* am = getenv("EGOEGO_ATTN");
     I->attn_tc = !(am && strcmp(am, "simt") == 0);
     if (I->attn_tc) {
@@ -260,7 +271,21 @@ void TcEngine::stage_targets(__nv_bfloat16** hi, __nv_bfloat16** lo, __half** h1
     *hi = impl_->X.hi; *lo = impl_->X.lo; *h16 = reinterpret_cast<__half*>(impl_->X.h16); *ld = impl_->kx;
 }
 
-int TcEngine::launches_per_denoiser() const { return 2 + 7 * impl_->w.NL; }
+int TcEngine::launches_per_denoiser(int fmt) const {
+    const bool fused = fmt == FMT_HALF && impl_->fuse_ln && impl_->attn_tc;
+    return 2 + (fused ? 5 : 7) * impl_->w.NL;
+}
+
+// fp16 full-row GEMM + residual + bias + LayerNorm (gemm_ln_half_kernel); out = Hs fp16 plane (in place)
+static int launch_gemm_ln(TcImpl* I, const Plane& A, const Plane& W, int M, int K, const float* bias, const float* g,
+                          const float* b, cudaStream_t s) {
+    EG_CHECK(M % GEMM_BM == 0 && K % GEMM_BK == 0, "fused-LN gemm shape not tile-aligned");
+    const int tiles = M / GEMM_BM;
+    gemm_ln_half_kernel<<<tiles < I->sms ? tiles : I->sms, GEMM_THREADS, GemmLnCfg::SMEM_BYTES, s>>>(
+        A.m16, W.m16, I->Hs.m16, I->Ident.m16, M, K, bias, g, b, I->Hs.h16);
+    EG_CUDA(cudaGetLastError());
+    return 0;
+}
 
 template <int FMT>
 static int denoiser_impl(TcImpl* I, int B, int T, TSrc ts, const float* pmask, float* model_out, cudaStream_t s) {
@@ -269,7 +294,8 @@ static int denoiser_impl(TcImpl* I, int B, int T, TSrc ts, const float* pmask, f
     const int nqkv = 3 * H * dk;
     const int half = (FMT == FMT_HALF) ? 1 : 0;
     {
-        TcEpiStart<FMT> e{{}, I->H, I->Hs.hi, I->Hs.lo, d, I->base, I->w.pos, I->w.temb, ts, T, B};
+        const bool fused = (FMT == FMT_HALF) && I->fuse_ln && I->attn_tc && pmask == nullptr;
+        TcEpiStart<FMT> e{{}, fused ? nullptr : I->H, I->Hs.hi, I->Hs.lo, d, I->base, I->w.pos, I->w.temb, ts, T, B};
         if (gemm<FMT>(I, I->X, I->Wx, Mg, d, I->kx, e, s)) return 1;
     }
     for (int l = 0; l < I->w.NL; ++l) {
@@ -285,14 +311,23 @@ static int denoiser_impl(TcImpl* I, int B, int T, TSrc ts, const float* pmask, f
             if (gemm<FMT_SPLIT>(I, I->Hs, W.wqkv, Mg, nqkv, d, eq, s)) return 1;
             attention_simt_kernel<true><<<B * H, 256, ATT_SIMT_SMEM, s>>>(I->QKV, nqkv, nullptr, I->O.hi, I->O.lo, H * dk, H, L);
         }
-        TcEpiBiasResidF32 ef{{}, I->Y, d, W.fc_b, I->H};
-        if (gemm<FMT>(I, I->O, W.fc, Mg, d, H * dk, ef, s)) return 1;
-        layernorm512_kernel<<<M / 8, 256, 0, s>>>(I->Y, I->H, I->Hs.hi, I->Hs.lo, W.ln1_g, W.ln1_b, pmask, T, M, half);
+        const bool fused = (FMT == FMT_HALF) && I->fuse_ln && I->attn_tc && pmask == nullptr;
+        if (fused) {
+            if (launch_gemm_ln(I, I->O, W.fc, Mg, H * dk, W.fc_b, W.ln1_g, W.ln1_b, s)) return 1;
+        } else {
+            TcEpiBiasResidF32 ef{{}, I->Y, d, W.fc_b, I->H};
+            if (gemm<FMT>(I, I->O, W.fc, Mg, d, H * dk, ef, s)) return 1;
+            layernorm512_kernel<<<M / 8, 256, 0, s>>>(I->Y, I->H, I->Hs.hi, I->Hs.lo, W.ln1_g, W.ln1_b, pmask, T, M, half);
+        }
         TcEpiBiasReluSplit<FMT> e1{{}, I->F.hi, I->F.lo, d, W.b1};
         if (gemm<FMT>(I, I->Hs, W.w1, Mg, d, d, e1, s)) return 1;
-        TcEpiBiasResidF32 e2{{}, I->Y, d, W.b2, I->H};
-        if (gemm<FMT>(I, I->F, W.w2, Mg, d, d, e2, s)) return 1;
-        layernorm512_kernel<<<M / 8, 256, 0, s>>>(I->Y, I->H, I->Hs.hi, I->Hs.lo, W.ln2_g, W.ln2_b, pmask, T, M, half);
+        if (fused) {
+            if (launch_gemm_ln(I, I->F, W.w2, Mg, d, W.b2, W.ln2_g, W.ln2_b, s)) return 1;
+        } else {
+            TcEpiBiasResidF32 e2{{}, I->Y, d, W.b2, I->H};
+            if (gemm<FMT>(I, I->F, W.w2, Mg, d, d, e2, s)) return 1;
+            layernorm512_kernel<<<M / 8, 256, 0, s>>>(I->Y, I->H, I->Hs.hi, I->Hs.lo, W.ln2_g, W.ln2_b, pmask, T, M, half);
+        }
     }
     {
         TcEpiOut eo{{}, model_out, I->w.D, I->w.out_b, T, B};
@@ -307,7 +342,7 @@ int TcEngine::denoiser(int B, int T, TSrc ts, const float* pmask, float* model_o
     EG_CHECK(fmt == FMT_SPLIT || (I->attn_tc), "fp16 single-pass steps need the tensor-core attention");
     int rc = (fmt == FMT_HALF) ? denoiser_impl<FMT_HALF>(I, B, T, ts, pmask, model_out, s)
                                : denoiser_impl<FMT_SPLIT>(I, B, T, ts, pmask, model_out, s);
-    *n += launches_per_denoiser();
+    *n += launches_per_denoiser(fmt);
     return rc;
 }
 

@@ -163,7 +163,7 @@ struct TcEpiStart : EpiNoDirect {         // H = x-half GEMM + base ; row 0 = ti
         else if (l <= T) r = add4(a, ld4(base + (long long)row * ld + col));
         else             r = make_float4(0.f, 0.f, 0.f, 0.f);
         const long long o = (long long)row * ld + col;
-        *reinterpret_cast<float4*>(H + o) = r;
+        if (H) *reinterpret_cast<float4*>(H + o) = r;       // the fp32 residual copy is not needed by the fused-LN (fp16) path
         store_planes4<FMT>(Hhi + o, Hlo + o, r);
     }
 };
@@ -456,6 +456,176 @@ gemm_split3_2cta_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_co
     __syncthreads();
     ptx::cluster_sync();                                 // nobody leaves while the peer may still touch its smem / TMEM
     if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc_2cta(tmem_base, 512); }
+}
+
+// ---- full-row fp16 GEMM with fused residual + bias + LayerNorm ------------------------------------------
+// The post-LN sub-layers (attention fc, FFN w_2) are memory-bound in the fp16 format (arithmetic intensity ~100 FLOP/B
+// with separate residual / pre-LN / LayerNorm passes).  This kernel computes a whole 128 x 512 row block per CTA:
+//     acc  = A[128,K] W[512,K]^T  +  R[128,512] I[512,512]^T        (the residual enters as extra k-blocks against an
+//                                                                    identity "weight": exact, and free on the tensor core)
+//     out  = LayerNorm(acc + bias) * gamma + beta   ->  one fp16 operand plane
+// The accumulator fills all 512 TMEM columns (two N = 256 MMAs per k-step), so the LayerNorm statistics of a row are
+// available inside the CTA: three passes over TMEM in the native thread-per-row layout (mean, centred variance,
+// normalise), partial sums of the two column halves exchanged through shared memory, and a final smem transpose for
+// coalesced stores.  Replaces a GEMM + a LayerNorm kernel and two fp32 round trips per sub-layer.
+struct GemmLnCfg {
+    static constexpr int STAGES = 2;
+    static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;              // 16 KB
+    static constexpr int W_BYTES = 512 * GEMM_BK * 2;                  // 64 KB (two 256-row TMA boxes)
+    static constexpr int STAGE_BYTES = A_BYTES + W_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + GEMM_EPI_WARPS * 4096 + 2 * 2 * 128 * 4 /*row partials*/ + 1024 + 256;
+};
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_ln_half_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mW,
+                    const __grid_constant__ CUtensorMap mR, const __grid_constant__ CUtensorMap mI,
+                    int M, int K, const float* __restrict__ bias, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, __nv_bfloat16* __restrict__ out16 /* fp16 bits, [M,512] */) {
+    constexpr int STAGES = GemmLnCfg::STAGES, A_BYTES = GemmLnCfg::A_BYTES, STAGE_BYTES = GemmLnCfg::STAGE_BYTES;
+    constexpr uint32_t IDESC = ptx::make_idesc_f16(GEMM_BM, 256);
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    float4* epi_tiles = reinterpret_cast<float4*>(smem + STAGES * STAGE_BYTES);
+    float* part = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + GEMM_EPI_WARPS * 4096);     // [2 passes][2 halves][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(part + 2 * 2 * 128);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + STAGES;
+    uint64_t* tfull_bar = bars + 2 * STAGES;
+    uint64_t* tempty_bar = bars + 2 * STAGES + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2);
+
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int m_tiles = M / GEMM_BM, kb_main = K / GEMM_BK, kb_total = kb_main + 512 / GEMM_BK;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&mA); ptx::prefetch_tmap(&mW); ptx::prefetch_tmap(&mR); ptx::prefetch_tmap(&mI);
+        for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+        ptx::mbar_init(tfull_bar, 1); ptx::mbar_init(tempty_bar, 32 * GEMM_EPI_WARPS);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) { ptx::tmem_alloc(tmem_slot, 512); ptx::tmem_relinquish(); }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {                                 // ===== TMA producer =====
+            int s = 0; uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
+                const int m0 = tile * GEMM_BM;
+                for (int kb = 0; kb < kb_total; ++kb) {
+                    ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+                    uint8_t* st = smem + s * STAGE_BYTES;
+                    ptx::mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+                    if (kb < kb_main) {
+                        ptx::tma_load_2d(st, &mA, &full_bar[s], kb * GEMM_BK, m0);
+                        ptx::tma_load_2d(st + A_BYTES, &mW, &full_bar[s], kb * GEMM_BK, 0);
+                        ptx::tma_load_2d(st + A_BYTES + 32768, &mW, &full_bar[s], kb * GEMM_BK, 256);
+                    } else {                             // residual rows against the identity
+                        const int kr = (kb - kb_main) * GEMM_BK;
+                        ptx::tma_load_2d(st, &mR, &full_bar[s], kr, m0);
+                        ptx::tma_load_2d(st + A_BYTES, &mI, &full_bar[s], kr, 0);
+                        ptx::tma_load_2d(st + A_BYTES + 32768, &mI, &full_bar[s], kr, 256);
+                    }
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                                 // ===== MMA issuer =====
+            int s = 0; uint32_t ph = 0; int it = 0;
+            for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
+                ptx::mbar_wait(tempty_bar, (it & 1) ^ 1);
+                ptx::tc_fence_after();
+                for (int kb = 0; kb < kb_total; ++kb) {
+                    ptx::mbar_wait(&full_bar[s], ph);
+                    ptx::tc_fence_after();
+                    const uint32_t st = ptx::smem_u32(smem + s * STAGE_BYTES);
+                    const uint64_t dA = ptx::make_smem_desc_sw128(st);
+                    const uint64_t dW0 = ptx::make_smem_desc_sw128(st + A_BYTES), dW1 = ptx::make_smem_desc_sw128(st + A_BYTES + 32768);
+#pragma unroll
+                    for (int kk = 0; kk < GEMM_BK / 16; ++kk) {
+                        const uint64_t adv = (uint64_t)(kk * 2);
+                        ptx::umma_f16(tmem_base, dA + adv, dW0 + adv, IDESC, (kb | kk) != 0);
+                        ptx::umma_f16(tmem_base + 256, dA + adv, dW1 + adv, IDESC, (kb | kk) != 0);
+                    }
+                    ptx::umma_commit(&empty_bar[s]);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+                ptx::umma_commit(tfull_bar);
+            }
+        }
+    } else {                                             // ===== LayerNorm epilogue warps 2..9 =====
+        const int quarter = warp & 3, hf = (warp - 2) >> 2;
+        const int r = quarter * 32 + lane;               // row within the tile == TMEM lane
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + hf * 256;
+        float4* etile = epi_tiles + (warp - 2) * 256;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
+            const int m0 = tile * GEMM_BM;
+            ptx::mbar_wait(tfull_bar, it & 1);
+            ptx::tc_fence_after();
+            // pass 1: row mean of (acc + bias)
+            float sum = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < 256; c += 32) {
+                uint32_t raw[32];
+                ptx::tmem_ld_32x32(taddr + c, raw);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sum += __uint_as_float(raw[j]) + __ldg(bias + hf * 256 + c + j);
+            }
+            part[hf * 128 + r] = sum;
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+            const float mean = (part[r] + part[128 + r]) * (1.0f / 512.0f);
+            // pass 2: centred variance
+            float sq = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < 256; c += 32) {
+                uint32_t raw[32];
+                ptx::tmem_ld_32x32(taddr + c, raw);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { const float d = __uint_as_float(raw[j]) + __ldg(bias + hf * 256 + c + j) - mean; sq += d * d; }
+            }
+            part[256 + hf * 128 + r] = sq;
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+            const float rstd = rsqrtf((part[256 + r] + part[256 + 128 + r]) * (1.0f / 512.0f) + 1e-5f);
+            // pass 3: normalise, transpose, coalesced fp16 store
+#pragma unroll 1
+            for (int c = 0; c < 256; c += 32) {
+                uint32_t raw[32];
+                ptx::tmem_ld_32x32(taddr + c, raw);
+                ptx::tmem_ld_wait();
+                const int col0 = hf * 256 + c;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4 y;
+                    y.x = (__uint_as_float(raw[4 * j + 0]) + __ldg(bias + col0 + 4 * j + 0) - mean) * rstd * __ldg(gamma + col0 + 4 * j + 0) + __ldg(beta + col0 + 4 * j + 0);
+                    y.y = (__uint_as_float(raw[4 * j + 1]) + __ldg(bias + col0 + 4 * j + 1) - mean) * rstd * __ldg(gamma + col0 + 4 * j + 1) + __ldg(beta + col0 + 4 * j + 1);
+                    y.z = (__uint_as_float(raw[4 * j + 2]) + __ldg(bias + col0 + 4 * j + 2) - mean) * rstd * __ldg(gamma + col0 + 4 * j + 2) + __ldg(beta + col0 + 4 * j + 2);
+                    y.w = (__uint_as_float(raw[4 * j + 3]) + __ldg(bias + col0 + 4 * j + 3) - mean) * rstd * __ldg(gamma + col0 + 4 * j + 3) + __ldg(beta + col0 + 4 * j + 3);
+                    etile[lane * 8 + (j ^ (lane & 7))] = y;
+                }
+                __syncwarp();
+                const int jj = lane & 7;
+#pragma unroll
+                for (int i2 = 0; i2 < 8; ++i2) {
+                    const int rr = i2 * 4 + (lane >> 3);
+                    const float4 y = etile[rr * 8 + (jj ^ (rr & 7))];
+                    const long long o = (long long)(m0 + quarter * 32 + rr) * 512 + col0 + 4 * jj;
+                    store_planes4<FMT_HALF>(out16 + o, nullptr, y);
+                }
+                __syncwarp();
+            }
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(tempty_bar);
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, 512); }
 }
 
 }  // namespace egoego
