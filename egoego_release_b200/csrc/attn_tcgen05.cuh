@@ -10,7 +10,9 @@
 // Persistent CTAs (one per SM, 192 threads) loop over (window, head) items:
 //   warp 0    TMA producer, ring of 2 x 64 KB stages: 4 Q/K k-blocks then 2 V^T k-blocks per item
 //   warp 1    MMA issuer (S of item i+1 is issued right after P V of item i, overlapping its epilogue)
-//   warps 2-5 softmax (TMEM -> registers -> P hi/lo into swizzled smem) and O epilogue (TMEM -> bf16 hi/lo planes)
+//   warps 2-9 softmax (TMEM -> registers -> P planes into swizzled smem) and O epilogue (TMEM -> operand planes);
+//             two warps share each TMEM lane quarter and split the key / output columns, exchanging the row
+//             max / sum partials through shared memory
 // TMEM: S at columns [0,128), O at [128,384).
 #pragma once
 #include <cuda_fp16.h>
@@ -23,8 +25,9 @@ namespace egoego {
 constexpr int ATT_STAGE_BYTES = 65536;
 constexpr int ATT_STAGES = 2;
 constexpr int ATT_P_BYTES = 2 * 2 * 128 * 128;          // hi/lo x 2 key blocks x [128 rows x 128 B]
-constexpr int ATT_SMEM_BYTES = ATT_STAGES * ATT_STAGE_BYTES + ATT_P_BYTES + 1024 + 256;
-constexpr int ATT_THREADS = 192;
+constexpr int ATT_PART_BYTES = 2 * 2 * 128 * 4;          // row max / row sum partials of the two column halves
+constexpr int ATT_SMEM_BYTES = ATT_STAGES * ATT_STAGE_BYTES + ATT_P_BYTES + ATT_PART_BYTES + 1024 + 256;
+constexpr int ATT_THREADS = 64 + 256;                    // TMA warp, MMA warp, 8 softmax/epilogue warps
 
 template <int FMT>
 struct OStore : EpiNoDirect {              // attention output rows -> operand planes of the fc GEMM
@@ -51,7 +54,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_consta
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* p_smem = smem + ATT_STAGES * ATT_STAGE_BYTES;           // P_hi [2][128][128B], P_lo [2][128][128B]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(p_smem + ATT_P_BYTES);
+    float* part = reinterpret_cast<float*>(p_smem + ATT_P_BYTES);     // [max|sum][half][128 rows]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(p_smem + ATT_P_BYTES + ATT_PART_BYTES);
     uint64_t* full_bar = bars;          // [2]
     uint64_t* empty_bar = bars + 2;     // [2]
     uint64_t* s_full = bars + 4;        // S accumulator ready (MMA -> softmax)
@@ -66,7 +70,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_consta
         ptx::prefetch_tmap(&mQh); ptx::prefetch_tmap(&mQl); ptx::prefetch_tmap(&mKh);
         ptx::prefetch_tmap(&mKl); ptx::prefetch_tmap(&mVh); ptx::prefetch_tmap(&mVl);
         for (int s = 0; s < ATT_STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
-        ptx::mbar_init(s_full, 1); ptx::mbar_init(p_ready, 128); ptx::mbar_init(o_full, 1); ptx::mbar_init(o_free, 128);
+        ptx::mbar_init(s_full, 1); ptx::mbar_init(p_ready, 256); ptx::mbar_init(o_full, 1); ptx::mbar_init(o_free, 256);
         ptx::fence_barrier_init();
     }
     if (warp == 1) { ptx::tmem_alloc(tmem_slot, 512); ptx::tmem_relinquish(); }
@@ -153,35 +157,45 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_consta
                 if (item + (int)gridDim.x < n_items) issue_S();
             }
         }
-    } else {                                               // ===== softmax + epilogue warps 2..5 =====
-        const int quarter = warp & 3;
+    } else {                                               // ===== softmax + epilogue warps 2..9 =====
+        const int quarter = warp & 3, hf = (warp - 2) >> 2;  // TMEM lane quarter, column half
         const int r = quarter * 32 + lane;                 // query row = TMEM lane
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
         int it = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             const uint32_t iph = it & 1;
-            // ---- softmax over keys [0, L) ----
+            // ---- softmax over keys [0, L): this warp owns keys [64*hf, 64*hf + 64) of its 32 rows ----
             ptx::mbar_wait(s_full, iph);
             ptx::tc_fence_after();
-            float v[128];
+            float v[64];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < 2; ++c) {
                 uint32_t raw[32];
-                ptx::tmem_ld_32x32(lane_addr + TM_S + c * 32, raw);
+                ptx::tmem_ld_32x32(lane_addr + TM_S + hf * 64 + c * 32, raw);
                 ptx::tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[c * 32 + j] = __uint_as_float(raw[j]);
             }
+            const int k0 = hf * 64;
             float mx = -INFINITY;
 #pragma unroll
-            for (int k = 0; k < 128; ++k) { if (k >= L) v[k] = -INFINITY; mx = fmaxf(mx, v[k]); }
+            for (int k = 0; k < 64; ++k) { if (k0 + k >= L) v[k] = -INFINITY; mx = fmaxf(mx, v[k]); }
+            part[hf * 128 + r] = mx;
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+            mx = fmaxf(part[r], part[128 + r]);            // key 0 is always valid, so the row max is finite
             float sum = 0.f;
 #pragma unroll
-            for (int k = 0; k < 128; ++k) { v[k] = (k < L) ? expf(v[k] - mx) : 0.f; sum += v[k]; }
-            const float inv = 1.0f / sum;
-            // P hi/lo -> K-major SW128 smem: 16-byte chunk j (keys 8j..8j+7) of row r lands at chunk (j%8)^(r%8)
+            for (int k = 0; k < 64; ++k) {
+                const float e = (FMT == FMT_SPLIT) ? expf(v[k] - mx) : __expf(v[k] - mx);
+                v[k] = (k0 + k < L) ? e : 0.f;
+                sum += v[k];
+            }
+            part[256 + hf * 128 + r] = sum;
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+            const float inv = 1.0f / (part[256 + r] + part[256 + 128 + r]);
+            // P planes -> K-major SW128 smem: key block hf, 16-byte chunk j (keys 8j..8j+7) of row r at chunk j^(r%8)
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
+            for (int j = 0; j < 8; ++j) {
                 uint32_t ph4[4], pl4[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -196,24 +210,24 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_consta
                         ph4[q] = *reinterpret_cast<uint32_t*>(&hh); pl4[q] = 0u;
                     }
                 }
-                const int kb = j >> 3, chunk = (j & 7) ^ (r & 7);
-                uint8_t* dst = p_smem + kb * 16384 + r * 128 + chunk * 16;
+                uint8_t* dst = p_smem + hf * 16384 + r * 128 + ((j ^ (r & 7)) * 16);
                 *reinterpret_cast<uint4*>(dst) = make_uint4(ph4[0], ph4[1], ph4[2], ph4[3]);
                 if (FMT == FMT_SPLIT) *reinterpret_cast<uint4*>(dst + 2 * 16384) = make_uint4(pl4[0], pl4[1], pl4[2], pl4[3]);
             }
             ptx::fence_proxy_async();                      // generic-proxy smem writes -> visible to the tensor core
             ptx::tc_fence_before();
             ptx::mbar_arrive(p_ready);
-            // ---- O epilogue ----
+            // ---- O epilogue: this warp drains output columns [128*hf, 128*hf + 128) of its 32 rows ----
             ptx::mbar_wait(o_full, iph);
             ptx::tc_fence_after();
-            // P(i) has been consumed once o_full fired: its smem is reused as the per-warp transpose tiles of the
-            // coalesced O store (softmax of item i+1 rewrites it only after this epilogue).
+            // P(i) has been consumed once o_full fired.  Each warp reuses exactly ITS OWN 4 KB of the P buffer (the 32
+            // rows x 64 keys it wrote) as the transpose tile of the coalesced O store, so no other warp's softmax of
+            // item i+1 can overwrite a tile that is still in use.
             const int w = item / n_head, h = item % n_head;
-            float4* tile = reinterpret_cast<float4*>(p_smem) + (warp - 2) * 256;
+            float4* tile = reinterpret_cast<float4*>(p_smem + hf * 16384 + quarter * 4096);
             OStore<FMT> ost{{}, Ohi, Olo, ((long long)w * LP) * ldo + h * 256, ldo};
 #pragma unroll 1
-            for (int c = 0; c < 8; ++c) {
+            for (int c = hf * 4; c < hf * 4 + 4; ++c) {
                 uint32_t raw[32];
                 ptx::tmem_ld_32x32(lane_addr + TM_O + c * 32, raw);
                 ptx::tmem_ld_wait();
