@@ -224,6 +224,7 @@ int TcEngine::init(const TcWeights& w, cudaStream_t) {
         const char* fl = getenv("EGOEGO_FUSE_LN");
         I->fuse_ln = !(fl && fl[0] == '0');
         EG_CUDA(cudaFuncSetAttribute(gemm_ln_half_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmLnCfg::SMEM_BYTES));
+        EG_CUDA(cudaFuncSetAttribute(gemm_ln_half_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmLn2Cfg::SMEM_BYTES));
     }
     const char* am = getenv("EGOEGO_ATTN");
     I->attn_tc = !(am && strcmp(am, "simt") == 0);
@@ -280,6 +281,19 @@ int TcEngine::launches_per_denoiser(int fmt) const {
 static int launch_gemm_ln(TcImpl* I, const Plane& A, const Plane& W, int M, int K, const float* bias, const float* g,
                           const float* b, cudaStream_t s) {
     EG_CHECK(M % GEMM_BM == 0 && K % GEMM_BK == 0, "fused-LN gemm shape not tile-aligned");
+    if (use_2cta() && M % 256 == 0) {
+        const int tiles = M / 256;
+        int pairs = I->sms / 2;
+        if (tiles < pairs) pairs = tiles;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = GemmLn2Cfg::SMEM_BYTES; cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        EG_CUDA(cudaLaunchKernelEx(&cfg, gemm_ln_half_2cta_kernel, A.m16, W.m16_128, I->Hs.m16, I->Ident.m16_128, M, K, bias, g, b, I->Hs.h16));
+        return 0;
+    }
     const int tiles = M / GEMM_BM;
     gemm_ln_half_kernel<<<tiles < I->sms ? tiles : I->sms, GEMM_THREADS, GemmLnCfg::SMEM_BYTES, s>>>(
         A.m16, W.m16, I->Hs.m16, I->Ident.m16, M, K, bias, g, b, I->Hs.h16);

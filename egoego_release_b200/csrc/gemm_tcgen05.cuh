@@ -468,6 +468,67 @@ gemm_split3_2cta_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_co
 // available inside the CTA: three passes over TMEM in the native thread-per-row layout (mean, centred variance,
 // normalise), partial sums of the two column halves exchanged through shared memory, and a final smem transpose for
 // coalesced stores.  Replaces a GEMM + a LayerNorm kernel and two fp32 round trips per sub-layer.
+// LayerNorm epilogue of one 128 x 512 accumulator block held in TMEM (thread = row, two warps per lane quarter each
+// owning 256 columns): mean -> centred variance -> normalise, then smem transpose and coalesced fp16 stores.
+__device__ __forceinline__ void ln_epilogue_tile(uint32_t tmem_base, float4* epi_tiles, float* part, int warp, int lane, int m0,
+                                                 const float* __restrict__ bias, const float* __restrict__ gamma,
+                                                 const float* __restrict__ beta, __nv_bfloat16* __restrict__ out16) {
+    const int quarter = warp & 3, hf = (warp - 2) >> 2;
+    const int r = quarter * 32 + lane;               // row within the tile == TMEM lane
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + hf * 256;
+    float4* etile = epi_tiles + (warp - 2) * 256;
+    float sum = 0.f;                                 // pass 1: row mean of (acc + bias)
+#pragma unroll 1
+    for (int c = 0; c < 256; c += 32) {
+        uint32_t raw[32];
+        ptx::tmem_ld_32x32(taddr + c, raw);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sum += __uint_as_float(raw[j]) + __ldg(bias + hf * 256 + c + j);
+    }
+    part[hf * 128 + r] = sum;
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+    const float mean = (part[r] + part[128 + r]) * (1.0f / 512.0f);
+    float sq = 0.f;                                  // pass 2: centred variance
+#pragma unroll 1
+    for (int c = 0; c < 256; c += 32) {
+        uint32_t raw[32];
+        ptx::tmem_ld_32x32(taddr + c, raw);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { const float d = __uint_as_float(raw[j]) + __ldg(bias + hf * 256 + c + j) - mean; sq += d * d; }
+    }
+    part[256 + hf * 128 + r] = sq;
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+    const float rstd = rsqrtf((part[256 + r] + part[256 + 128 + r]) * (1.0f / 512.0f) + 1e-5f);
+#pragma unroll 1
+    for (int c = 0; c < 256; c += 32) {              // pass 3: normalise, transpose, coalesced fp16 store
+        uint32_t raw[32];
+        ptx::tmem_ld_32x32(taddr + c, raw);
+        ptx::tmem_ld_wait();
+        const int col0 = hf * 256 + c;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float4 y;
+            y.x = (__uint_as_float(raw[4 * j + 0]) + __ldg(bias + col0 + 4 * j + 0) - mean) * rstd * __ldg(gamma + col0 + 4 * j + 0) + __ldg(beta + col0 + 4 * j + 0);
+            y.y = (__uint_as_float(raw[4 * j + 1]) + __ldg(bias + col0 + 4 * j + 1) - mean) * rstd * __ldg(gamma + col0 + 4 * j + 1) + __ldg(beta + col0 + 4 * j + 1);
+            y.z = (__uint_as_float(raw[4 * j + 2]) + __ldg(bias + col0 + 4 * j + 2) - mean) * rstd * __ldg(gamma + col0 + 4 * j + 2) + __ldg(beta + col0 + 4 * j + 2);
+            y.w = (__uint_as_float(raw[4 * j + 3]) + __ldg(bias + col0 + 4 * j + 3) - mean) * rstd * __ldg(gamma + col0 + 4 * j + 3) + __ldg(beta + col0 + 4 * j + 3);
+            etile[lane * 8 + (j ^ (lane & 7))] = y;
+        }
+        __syncwarp();
+        const int jj = lane & 7;
+#pragma unroll
+        for (int i2 = 0; i2 < 8; ++i2) {
+            const int rr = i2 * 4 + (lane >> 3);
+            const float4 y = etile[rr * 8 + (jj ^ (rr & 7))];
+            const long long o = (long long)(m0 + quarter * 32 + rr) * 512 + col0 + 4 * jj;
+            store_planes4<FMT_HALF>(out16 + o, nullptr, y);
+        }
+        __syncwarp();
+    }
+}
+
 struct GemmLnCfg {
     static constexpr int STAGES = 2;
     static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;              // 16 KB
@@ -557,68 +618,11 @@ gemm_ln_half_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constan
             }
         }
     } else {                                             // ===== LayerNorm epilogue warps 2..9 =====
-        const int quarter = warp & 3, hf = (warp - 2) >> 2;
-        const int r = quarter * 32 + lane;               // row within the tile == TMEM lane
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + hf * 256;
-        float4* etile = epi_tiles + (warp - 2) * 256;
         int it = 0;
         for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
-            const int m0 = tile * GEMM_BM;
             ptx::mbar_wait(tfull_bar, it & 1);
             ptx::tc_fence_after();
-            // pass 1: row mean of (acc + bias)
-            float sum = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < 256; c += 32) {
-                uint32_t raw[32];
-                ptx::tmem_ld_32x32(taddr + c, raw);
-                ptx::tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; ++j) sum += __uint_as_float(raw[j]) + __ldg(bias + hf * 256 + c + j);
-            }
-            part[hf * 128 + r] = sum;
-            asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
-            const float mean = (part[r] + part[128 + r]) * (1.0f / 512.0f);
-            // pass 2: centred variance
-            float sq = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < 256; c += 32) {
-                uint32_t raw[32];
-                ptx::tmem_ld_32x32(taddr + c, raw);
-                ptx::tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; ++j) { const float d = __uint_as_float(raw[j]) + __ldg(bias + hf * 256 + c + j) - mean; sq += d * d; }
-            }
-            part[256 + hf * 128 + r] = sq;
-            asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
-            const float rstd = rsqrtf((part[256 + r] + part[256 + 128 + r]) * (1.0f / 512.0f) + 1e-5f);
-            // pass 3: normalise, transpose, coalesced fp16 store
-#pragma unroll 1
-            for (int c = 0; c < 256; c += 32) {
-                uint32_t raw[32];
-                ptx::tmem_ld_32x32(taddr + c, raw);
-                ptx::tmem_ld_wait();
-                const int col0 = hf * 256 + c;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float4 y;
-                    y.x = (__uint_as_float(raw[4 * j + 0]) + __ldg(bias + col0 + 4 * j + 0) - mean) * rstd * __ldg(gamma + col0 + 4 * j + 0) + __ldg(beta + col0 + 4 * j + 0);
-                    y.y = (__uint_as_float(raw[4 * j + 1]) + __ldg(bias + col0 + 4 * j + 1) - mean) * rstd * __ldg(gamma + col0 + 4 * j + 1) + __ldg(beta + col0 + 4 * j + 1);
-                    y.z = (__uint_as_float(raw[4 * j + 2]) + __ldg(bias + col0 + 4 * j + 2) - mean) * rstd * __ldg(gamma + col0 + 4 * j + 2) + __ldg(beta + col0 + 4 * j + 2);
-                    y.w = (__uint_as_float(raw[4 * j + 3]) + __ldg(bias + col0 + 4 * j + 3) - mean) * rstd * __ldg(gamma + col0 + 4 * j + 3) + __ldg(beta + col0 + 4 * j + 3);
-                    etile[lane * 8 + (j ^ (lane & 7))] = y;
-                }
-                __syncwarp();
-                const int jj = lane & 7;
-#pragma unroll
-                for (int i2 = 0; i2 < 8; ++i2) {
-                    const int rr = i2 * 4 + (lane >> 3);
-                    const float4 y = etile[rr * 8 + (jj ^ (rr & 7))];
-                    const long long o = (long long)(m0 + quarter * 32 + rr) * 512 + col0 + 4 * jj;
-                    store_planes4<FMT_HALF>(out16 + o, nullptr, y);
-                }
-                __syncwarp();
-            }
+            ln_epilogue_tile(tmem_base, epi_tiles, part, warp, lane, tile * GEMM_BM, bias, gamma, beta, out16);
             ptx::tc_fence_before();
             ptx::mbar_arrive(tempty_bar);
         }
@@ -626,6 +630,114 @@ gemm_ln_half_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constan
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, 512); }
+}
+
+// CTA-pair variant of the fused GEMM + LayerNorm: the pair owns 256 rows x 512 columns (cta_group::2, two N = 256 MMAs
+// per k-step); each CTA stages its own 128 A rows and HALF of the W k-block (2 x 128 rows), i.e. 48 KB instead of 80 KB
+// per k-block, three stages deep.  Every CTA still holds complete rows (128 x 512 fp32 in its TMEM), so the LayerNorm
+// epilogue is CTA-local.
+struct GemmLn2Cfg {
+    static constexpr int STAGES = 3;
+    static constexpr int T_BYTES = GEMM_BM * GEMM_BK * 2;              // 16 KB
+    static constexpr int STAGE_BYTES = 3 * T_BYTES;                    // A + two 128-row W boxes
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + GEMM_EPI_WARPS * 4096 + 2 * 2 * 128 * 4 + 1024 + 256;
+};
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_ln_half_2cta_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mW /*128-row boxes*/,
+                         const __grid_constant__ CUtensorMap mR, const __grid_constant__ CUtensorMap mI /*128-row boxes*/,
+                         int M, int K, const float* __restrict__ bias, const float* __restrict__ gamma,
+                         const float* __restrict__ beta, __nv_bfloat16* __restrict__ out16) {
+    constexpr int STAGES = GemmLn2Cfg::STAGES, T_BYTES = GemmLn2Cfg::T_BYTES, STAGE_BYTES = GemmLn2Cfg::STAGE_BYTES;
+    constexpr uint32_t IDESC = ptx::make_idesc_f16(256, 256);
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    float4* epi_tiles = reinterpret_cast<float4*>(smem + STAGES * STAGE_BYTES);
+    float* part = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + GEMM_EPI_WARPS * 4096);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(part + 2 * 2 * 128);
+    uint64_t* full_bar = bars;                 // [S] leader
+    uint64_t* empty_bar = bars + STAGES;       // [S] both
+    uint64_t* tfull_bar = bars + 2 * STAGES;   // both
+    uint64_t* tempty_bar = bars + 2 * STAGES + 1;   // leader
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2);
+
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const uint32_t rank = ptx::cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair = blockIdx.x / 2, n_pairs = gridDim.x / 2;
+    const int m_tiles = M / 256, kb_main = K / GEMM_BK, kb_total = kb_main + 512 / GEMM_BK;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&mA); ptx::prefetch_tmap(&mW); ptx::prefetch_tmap(&mR); ptx::prefetch_tmap(&mI);
+        for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 2); ptx::mbar_init(&empty_bar[s], 1); }
+        ptx::mbar_init(tfull_bar, 1); ptx::mbar_init(tempty_bar, 2 * GEMM_EPI_WARPS);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) { ptx::tmem_alloc_2cta(tmem_slot, 512); ptx::tmem_relinquish_2cta(); }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {                                 // ===== TMA producer (both CTAs) =====
+            int s = 0; uint32_t ph = 0;
+            for (int tile = pair; tile < m_tiles; tile += n_pairs) {
+                const int m0 = tile * 256 + (int)rank * 128;
+                for (int kb = 0; kb < kb_total; ++kb) {
+                    ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+                    uint8_t* st = smem + s * STAGE_BYTES;
+                    if (leader) ptx::mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
+                    else        ptx::mbar_arrive_cluster(&full_bar[s], 0);
+                    const bool main = kb < kb_main;
+                    const int kx = main ? kb * GEMM_BK : (kb - kb_main) * GEMM_BK;
+                    ptx::tma_load_2d_2cta(st, main ? &mA : &mR, &full_bar[s], kx, m0);
+                    ptx::tma_load_2d_2cta(st + T_BYTES, main ? &mW : &mI, &full_bar[s], kx, (int)rank * 128);
+                    ptx::tma_load_2d_2cta(st + 2 * T_BYTES, main ? &mW : &mI, &full_bar[s], kx, 256 + (int)rank * 128);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && leader) {                       // ===== MMA issuer (leader CTA) =====
+            int s = 0; uint32_t ph = 0; int it = 0;
+            for (int tile = pair; tile < m_tiles; tile += n_pairs, ++it) {
+                ptx::mbar_wait(tempty_bar, (it & 1) ^ 1);
+                ptx::tc_fence_after();
+                for (int kb = 0; kb < kb_total; ++kb) {
+                    ptx::mbar_wait(&full_bar[s], ph);
+                    ptx::tc_fence_after();
+                    const uint32_t st = ptx::smem_u32(smem + s * STAGE_BYTES);
+                    const uint64_t dA = ptx::make_smem_desc_sw128(st);
+                    const uint64_t dW0 = ptx::make_smem_desc_sw128(st + T_BYTES), dW1 = ptx::make_smem_desc_sw128(st + 2 * T_BYTES);
+#pragma unroll
+                    for (int kk = 0; kk < GEMM_BK / 16; ++kk) {
+                        const uint64_t adv = (uint64_t)(kk * 2);
+                        ptx::umma_f16_2cta(tmem_base, dA + adv, dW0 + adv, IDESC, (kb | kk) != 0);
+                        ptx::umma_f16_2cta(tmem_base + 256, dA + adv, dW1 + adv, IDESC, (kb | kk) != 0);
+                    }
+                    ptx::umma_commit_2cta(&empty_bar[s]);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+                ptx::umma_commit_2cta(tfull_bar);
+            }
+        }
+    } else {                                             // ===== LayerNorm epilogue warps 2..9 (both CTAs) =====
+        int it = 0;
+        for (int tile = pair; tile < m_tiles; tile += n_pairs, ++it) {
+            ptx::mbar_wait(tfull_bar, it & 1);
+            ptx::tc_fence_after();
+            ln_epilogue_tile(tmem_base, epi_tiles, part, warp, lane, tile * 256 + (int)rank * 128, bias, gamma, beta, out16);
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(tempty_bar, 0);
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync();
+    if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc_2cta(tmem_base, 512); }
 }
 
 }  // namespace egoego
