@@ -158,9 +158,10 @@ struct TcEpiStart : EpiNoDirect {         // H = x-half GEMM + base ; row 0 = ti
     __device__ __forceinline__ void apply4(int row, int col, float4 a) const {
         const int w = row / LP;
         const int l = (w < n_windows) ? row % LP : LP;      // rows of the rounding-up window are padding
+        const float4 bv = ld4(base + (long long)row * ld + col);   // unconditional: lets the loads of a chunk be batched
         float4 r;
         if (l == 0)      r = add4(ld4(temb + (long long)ts.get(w) * ld + col), ld4(pos + ld + col));
-        else if (l <= T) r = add4(a, ld4(base + (long long)row * ld + col));
+        else if (l <= T) r = add4(a, bv);
         else             r = make_float4(0.f, 0.f, 0.f, 0.f);
         const long long o = (long long)row * ld + col;
         if (H) *reinterpret_cast<float4*>(H + o) = r;       // the fp32 residual copy is not needed by the fused-LN (fp16) path

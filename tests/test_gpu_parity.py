@@ -190,3 +190,28 @@ def test_error_behaviour(params0):
     m3 = make_model(10, "simt", params0, max_batch=8)
     torch.manual_seed(5); b = m3.sample(xs, cm)
     assert torch.equal(a, b)
+
+
+def test_precision_policy_knob(golden_dir, params0):
+    """egoego_cfg.precise_last_steps: all-split, a short split tail and (for contrast) all-fp16 on the N=50 golden."""
+    import egoego_release_b200 as E
+    g = _g(golden_dir, "sample.npz")
+    N, B, seed = 50, 2, 21
+    xs = synth_x_start(100 + N, B, 120)
+    cm = O.prep_head_condition_mask(xs.shape)
+    tp = Tape(seed)
+    tape = torch.stack([tp.draw(xs.shape) for _ in range(N + 2)]).cuda()
+    ref = torch.from_numpy(g[f"n{N}_b{B}_seed{seed}"])
+    errs = {}
+    for K in (50, 20, 0):
+        m = E.CondGaussianDiffusion(d_feats=198, d_model=512, n_dec_layers=4, n_head=4, d_k=256, d_v=256, max_timesteps=121,
+                                    out_dim=198, timesteps=N, objective="pred_x0", max_batch=B, engine="tcgen05",
+                                    precise_last_steps=K)
+        m.load_state_dict(params0, strict=False)
+        m = m.cuda()
+        assert m.precise_last_steps() == K
+        m.set_noise_tape(tape)
+        errs[K] = maxabs(joints(m.sample(xs.cuda(), cm.cuda())), joints(ref))
+    print("joint error (m) by precise_last_steps:", errs)
+    assert errs[50] < 3e-4 and errs[20] < JPOS_TOL_M
+    assert errs[0] > errs[50]            # the fp16 format alone is NOT fp32-grade: the policy matters
