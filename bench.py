@@ -290,8 +290,14 @@ def main():
         dom = "fp16_single" if K_prec < N else "bf16x3_split"       # format of the steps that take most of the time
         ach = kern[dom]["algorithmic_tflops"]
         pk_burst = pk["bf16_tflops"]
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")   # dram bytes/launch from the committed ncu --set full capture
+        if os.path.exists(tp):
+            tj = json.load(open(tp))
+            if tj.get("format") == dom and tj.get("windows") == B:
+                traffic = tj.get("dram_bytes_read", 0) + tj.get("dram_bytes_write", 0)
         line["roofline"] = {"bound": "tensor", "achieved": ach, "peak": pk_burst, "unit": "TFLOP/s", "frac": ach / pk_burst,
-                            "traffic": None, "kernel": f"gemm_split3(_2cta)_kernel<{dom}, TcEpiQKVPlanes> (fused QKV projection)",
+                            "traffic": traffic, "kernel": f"gemm_split3(_2cta)_kernel<{dom}, TcEpiQKVPlanes> (fused QKV projection)",
                             "algorithmic_flops_per_launch": QKV_FLOP_PER_WINDOW_CALL * B,
                             "ms_per_launch": kern[dom]["ms_per_launch"], "issued_over_algorithmic": 1.0 if dom == "fp16_single" else 3.0,
                             "peak_source": pk_src + ", burst bf16 (kernel timed alone, 20 back-to-back launches, CUDA events)",

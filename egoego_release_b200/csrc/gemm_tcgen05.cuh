@@ -472,8 +472,8 @@ gemm_split3_2cta_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_co
 // LayerNorm epilogue of one 128 x 512 accumulator block held in TMEM (thread = row, two warps per lane quarter each
 // owning 256 columns): mean -> centred variance -> normalise, then smem transpose and coalesced fp16 stores.
 __device__ __forceinline__ void ln_epilogue_tile(uint32_t tmem_base, float4* epi_tiles, float* part, int warp, int lane, int m0,
-                                                 const float* __restrict__ bias, const float* __restrict__ gamma,
-                                                 const float* __restrict__ beta, __nv_bfloat16* __restrict__ out16) {
+                                                 const float* bias, const float* gamma, const float* beta /* shared memory */,
+                                                 __nv_bfloat16* __restrict__ out16) {
     const int quarter = warp & 3, hf = (warp - 2) >> 2;
     const int r = quarter * 32 + lane;               // row within the tile == TMEM lane
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + hf * 256;
@@ -485,7 +485,7 @@ __device__ __forceinline__ void ln_epilogue_tile(uint32_t tmem_base, float4* epi
         ptx::tmem_ld_32x32(taddr + c, raw);
         ptx::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) sum += __uint_as_float(raw[j]) + __ldg(bias + hf * 256 + c + j);
+        for (int j = 0; j < 32; ++j) sum += __uint_as_float(raw[j]) + bias[hf * 256 + c + j];
     }
     part[hf * 128 + r] = sum;
     asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
@@ -497,7 +497,7 @@ __device__ __forceinline__ void ln_epilogue_tile(uint32_t tmem_base, float4* epi
         ptx::tmem_ld_32x32(taddr + c, raw);
         ptx::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { const float d = __uint_as_float(raw[j]) + __ldg(bias + hf * 256 + c + j) - mean; sq += d * d; }
+        for (int j = 0; j < 32; ++j) { const float d = __uint_as_float(raw[j]) + bias[hf * 256 + c + j] - mean; sq += d * d; }
     }
     part[256 + hf * 128 + r] = sq;
     asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
@@ -511,10 +511,10 @@ __device__ __forceinline__ void ln_epilogue_tile(uint32_t tmem_base, float4* epi
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             float4 y;
-            y.x = (__uint_as_float(raw[4 * j + 0]) + __ldg(bias + col0 + 4 * j + 0) - mean) * rstd * __ldg(gamma + col0 + 4 * j + 0) + __ldg(beta + col0 + 4 * j + 0);
-            y.y = (__uint_as_float(raw[4 * j + 1]) + __ldg(bias + col0 + 4 * j + 1) - mean) * rstd * __ldg(gamma + col0 + 4 * j + 1) + __ldg(beta + col0 + 4 * j + 1);
-            y.z = (__uint_as_float(raw[4 * j + 2]) + __ldg(bias + col0 + 4 * j + 2) - mean) * rstd * __ldg(gamma + col0 + 4 * j + 2) + __ldg(beta + col0 + 4 * j + 2);
-            y.w = (__uint_as_float(raw[4 * j + 3]) + __ldg(bias + col0 + 4 * j + 3) - mean) * rstd * __ldg(gamma + col0 + 4 * j + 3) + __ldg(beta + col0 + 4 * j + 3);
+            y.x = (__uint_as_float(raw[4 * j + 0]) + bias[col0 + 4 * j + 0] - mean) * rstd * gamma[col0 + 4 * j + 0] + beta[col0 + 4 * j + 0];
+            y.y = (__uint_as_float(raw[4 * j + 1]) + bias[col0 + 4 * j + 1] - mean) * rstd * gamma[col0 + 4 * j + 1] + beta[col0 + 4 * j + 1];
+            y.z = (__uint_as_float(raw[4 * j + 2]) + bias[col0 + 4 * j + 2] - mean) * rstd * gamma[col0 + 4 * j + 2] + beta[col0 + 4 * j + 2];
+            y.w = (__uint_as_float(raw[4 * j + 3]) + bias[col0 + 4 * j + 3] - mean) * rstd * gamma[col0 + 4 * j + 3] + beta[col0 + 4 * j + 3];
             etile[lane * 8 + (j ^ (lane & 7))] = y;
         }
         __syncwarp();
@@ -535,7 +535,7 @@ struct GemmLnCfg {
     static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;              // 16 KB
     static constexpr int W_BYTES = 512 * GEMM_BK * 2;                  // 64 KB (two 256-row TMA boxes)
     static constexpr int STAGE_BYTES = A_BYTES + W_BYTES;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + GEMM_EPI_WARPS * 4096 + 2 * 2 * 128 * 4 /*row partials*/ + 1024 + 256;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + GEMM_EPI_WARPS * 4096 + 2 * 2 * 128 * 4 /*row partials*/ + 3 * 512 * 4 /*bias|gamma|beta*/ + 1024 + 256;
 };
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -549,7 +549,9 @@ gemm_ln_half_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constan
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     float4* epi_tiles = reinterpret_cast<float4*>(smem + STAGES * STAGE_BYTES);
     float* part = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + GEMM_EPI_WARPS * 4096);     // [2 passes][2 halves][128]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(part + 2 * 2 * 128);
+    float* vec = part + 2 * 2 * 128;                                                                 // bias | gamma | beta
+    uint64_t* bars = reinterpret_cast<uint64_t*>(vec + 3 * 512);
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) { vec[i] = bias[i]; vec[512 + i] = gamma[i]; vec[1024 + i] = beta[i]; }
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + STAGES;
     uint64_t* tfull_bar = bars + 2 * STAGES;
@@ -623,7 +625,7 @@ gemm_ln_half_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constan
         for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
             ptx::mbar_wait(tfull_bar, it & 1);
             ptx::tc_fence_after();
-            ln_epilogue_tile(tmem_base, epi_tiles, part, warp, lane, tile * GEMM_BM, bias, gamma, beta, out16);
+            ln_epilogue_tile(tmem_base, epi_tiles, part, warp, lane, tile * GEMM_BM, vec, vec + 512, vec + 1024, out16);
             ptx::tc_fence_before();
             ptx::mbar_arrive(tempty_bar);
         }
@@ -641,7 +643,7 @@ struct GemmLn2Cfg {
     static constexpr int STAGES = 3;
     static constexpr int T_BYTES = GEMM_BM * GEMM_BK * 2;              // 16 KB
     static constexpr int STAGE_BYTES = 3 * T_BYTES;                    // A + two 128-row W boxes
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + GEMM_EPI_WARPS * 4096 + 2 * 2 * 128 * 4 + 1024 + 256;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + GEMM_EPI_WARPS * 4096 + 2 * 2 * 128 * 4 + 3 * 512 * 4 + 1024 + 256;
 };
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -655,7 +657,9 @@ gemm_ln_half_2cta_kernel(const __grid_constant__ CUtensorMap mA, const __grid_co
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     float4* epi_tiles = reinterpret_cast<float4*>(smem + STAGES * STAGE_BYTES);
     float* part = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + GEMM_EPI_WARPS * 4096);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(part + 2 * 2 * 128);
+    float* vec = part + 2 * 2 * 128;                                                                 // bias | gamma | beta
+    uint64_t* bars = reinterpret_cast<uint64_t*>(vec + 3 * 512);
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) { vec[i] = bias[i]; vec[512 + i] = gamma[i]; vec[1024 + i] = beta[i]; }
     uint64_t* full_bar = bars;                 // [S] leader
     uint64_t* empty_bar = bars + STAGES;       // [S] both
     uint64_t* tfull_bar = bars + 2 * STAGES;   // both
@@ -729,7 +733,7 @@ gemm_ln_half_2cta_kernel(const __grid_constant__ CUtensorMap mA, const __grid_co
         for (int tile = pair; tile < m_tiles; tile += n_pairs, ++it) {
             ptx::mbar_wait(tfull_bar, it & 1);
             ptx::tc_fence_after();
-            ln_epilogue_tile(tmem_base, epi_tiles, part, warp, lane, tile * 256 + (int)rank * 128, bias, gamma, beta, out16);
+            ln_epilogue_tile(tmem_base, epi_tiles, part, warp, lane, tile * 256 + (int)rank * 128, vec, vec + 512, vec + 1024, out16);
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_cluster(tempty_bar, 0);
