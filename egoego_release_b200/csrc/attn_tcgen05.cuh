@@ -30,9 +30,10 @@ constexpr int ATT_SMEM_BYTES = ATT_STAGES * ATT_STAGE_BYTES + ATT_P_BYTES + ATT_
 constexpr int ATT_THREADS = 64 + 256;                    // TMA warp, MMA warp, 8 softmax/epilogue warps
 
 template <int FMT>
-struct OStore : EpiNoDirect {              // attention output rows -> operand planes of the fc GEMM
+struct OStore : EpiNoDirect, EpiNoPre {    // attention output rows -> operand planes of the fc GEMM
     __nv_bfloat16* hi; __nv_bfloat16* lo; long long base; int ld;
-    __device__ __forceinline__ void apply4(int row, int col, float4 a) const {
+    __device__ __forceinline__ float4 bias4(int) const { return make_float4(0.f, 0.f, 0.f, 0.f); }
+    __device__ __forceinline__ void apply4(int row, int col, float4 a, float4, float4) const {
         const long long o = base + (long long)row * ld + col;
         store_planes4<FMT>(hi + o, lo + o, a);
     }
@@ -225,14 +226,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_consta
             // item i+1 can overwrite a tile that is still in use.
             const int w = item / n_head, h = item % n_head;
             float4* tile = reinterpret_cast<float4*>(p_smem + hf * 16384 + quarter * 4096);
-            OStore<FMT> ost{{}, Ohi, Olo, ((long long)w * LP) * ldo + h * 256, ldo};
-#pragma unroll 1
-            for (int c = hf * 4; c < hf * 4 + 4; ++c) {
-                uint32_t raw[32];
-                ptx::tmem_ld_32x32(lane_addr + TM_O + c * 32, raw);
-                ptx::tmem_ld_wait();
-                epilogue_chunk(ost, tile, raw, lane, quarter * 32, c * 32);
-            }
+            OStore<FMT> ost{{}, {}, Ohi, Olo, ((long long)w * LP) * ldo + h * 256, ldo};
+            epilogue_drain<128>(ost, tile, lane_addr + TM_O + hf * 128, lane, quarter * 32, hf * 128, []() {});
             ptx::tc_fence_before();
             ptx::mbar_arrive(o_free);
         }
@@ -246,33 +241,33 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_consta
 // Q / K sections use the coalesced apply4 path; the V section's destination is transposed ([dim][token]), for which
 // the accumulator's native thread-per-row layout is the coalesced one (32 lanes = 32 consecutive tokens).
 template <int FMT>
-struct TcEpiQKVPlanes {
+struct TcEpiQKVPlanes : EpiNoPre {
     __nv_bfloat16 *Qh, *Ql, *Kh, *Kl, *Vh, *Vl;       // Q,K: [(w*H+h)*128 + l][256];  V^T: [(w*H+h)*256 + c][128]
     const float* bias; int n_head; float q_scale;
+    __device__ __forceinline__ float4 bias4(int col) const { return ld4(bias + col); }
     __device__ __forceinline__ bool direct(int col0) const { return col0 >= 2 * n_head * 256; }
-    __device__ __forceinline__ void apply_row(int row, int col0, const float (&v)[32]) const {
+    __device__ __forceinline__ void apply_row(int row, int col0, const float (&v)[32] /* bias already added */) const {
         const int w = row / LP, l = row % LP;
         const int hc = col0 - 2 * n_head * 256, h = hc / 256, c0 = hc % 256;
         const long long base = ((long long)(w * n_head + h) * 256 + c0) * 128 + l;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-            const float r = v[j] + bias[col0 + j];
             if (FMT == FMT_SPLIT) {
                 __nv_bfloat16 hi, lo;
-                split_bf16(r, hi, lo);
+                split_bf16(v[j], hi, lo);
                 Vh[base + (long long)j * 128] = hi;
                 Vl[base + (long long)j * 128] = lo;
             } else {
-                reinterpret_cast<__half*>(Vh)[base + (long long)j * 128] = __float2half_rn(r);
+                reinterpret_cast<__half*>(Vh)[base + (long long)j * 128] = __float2half_rn(v[j]);
             }
         }
     }
-    __device__ __forceinline__ void apply4(int row, int col, float4 a) const {
+    __device__ __forceinline__ void apply4(int row, int col, float4 a, float4 b, float4) const {
         const int w = row / LP, l = row % LP;
         const int hw = n_head * 256;
         const int sec = col >= hw ? 1 : 0, hc = col - sec * hw;
         const int h = hc >> 8, c = hc & 255;
-        a = add4(a, ld4(bias + col));
+        a = add4(a, b);
         if (sec == 0) a = make_float4(a.x * q_scale, a.y * q_scale, a.z * q_scale, a.w * q_scale);
         const long long o = ((long long)(w * n_head + h) * 128 + l) * 256 + c;
         store_planes4<FMT>((sec == 0 ? Qh : Kh) + o, (sec == 0 ? Ql : Kl) + o, a);

@@ -262,7 +262,7 @@ int TcEngine::stage(const float* src, int src_ld, int src_col0, bool cond_half, 
 
 int TcEngine::prepare_cond(int B, int T, cudaStream_t s, int64_t* n) {
     TcImpl* I = impl_;
-    TcEpiBase e{{}, I->base, I->w.d, I->w.start_b, I->w.pos, T};
+    TcEpiBase e{{}, {}, I->base, I->w.d, I->w.start_b, I->w.pos, T};
     if (gemm<FMT_SPLIT>(I, I->C, I->Wc, Mr(B), I->w.d, I->kx, e, s)) return 1;
     *n += 1;
     return 0;
@@ -315,13 +315,13 @@ static int denoiser_impl(TcImpl* I, int B, int T, TSrc ts, const float* pmask, f
     for (int l = 0; l < I->w.NL; ++l) {
         TcLayer& W = I->layers[l];
         if (I->attn_tc) {
-            TcEpiQKVPlanes<FMT> eq{I->Qp.hi, I->Qp.lo, I->Kp.hi, I->Kp.lo, I->VT.hi, I->VT.lo, W.bqkv, H, 1.0f / sqrtf((float)dk)};
+            TcEpiQKVPlanes<FMT> eq{{}, I->Qp.hi, I->Qp.lo, I->Kp.hi, I->Kp.lo, I->VT.hi, I->VT.lo, W.bqkv, H, 1.0f / sqrtf((float)dk)};
             if (gemm<FMT>(I, I->Hs, W.wqkv, Mg, nqkv, d, eq, s)) return 1;
             const int items = B * H;
             attention_tc_kernel<FMT><<<items < I->sms ? items : I->sms, ATT_THREADS, ATT_SMEM_BYTES, s>>>(
                 I->Qp.mhi, I->Qp.mlo, I->Kp.mhi, I->Kp.mlo, I->VT.mhi, I->VT.mlo, I->O.hi, I->O.lo, H * dk, items, H, L);
         } else {
-            TcEpiBiasScaleF32 eq{{}, I->QKV, nqkv, W.bqkv, H * dk, 1.0f / sqrtf((float)dk)};
+            TcEpiBiasScaleF32 eq{{}, {}, I->QKV, nqkv, W.bqkv, H * dk, 1.0f / sqrtf((float)dk)};
             if (gemm<FMT_SPLIT>(I, I->Hs, W.wqkv, Mg, nqkv, d, eq, s)) return 1;
             attention_simt_kernel<true><<<B * H, 256, ATT_SIMT_SMEM, s>>>(I->QKV, nqkv, nullptr, I->O.hi, I->O.lo, H * dk, H, L);
         }
@@ -333,7 +333,7 @@ static int denoiser_impl(TcImpl* I, int B, int T, TSrc ts, const float* pmask, f
             if (gemm<FMT>(I, I->O, W.fc, Mg, d, H * dk, ef, s)) return 1;
             layernorm512_kernel<<<M / 8, 256, 0, s>>>(I->Y, I->H, I->Hs.hi, I->Hs.lo, W.ln1_g, W.ln1_b, pmask, T, M, half);
         }
-        TcEpiBiasReluSplit<FMT> e1{{}, I->F.hi, I->F.lo, d, W.b1};
+        TcEpiBiasReluSplit<FMT> e1{{}, {}, I->F.hi, I->F.lo, d, W.b1};
         if (gemm<FMT>(I, I->Hs, W.w1, Mg, d, d, e1, s)) return 1;
         if (fused) {
             if (launch_gemm_ln(I, I->F, W.w2, Mg, d, W.b2, W.ln2_g, W.ln2_b, s)) return 1;
@@ -344,7 +344,7 @@ static int denoiser_impl(TcImpl* I, int B, int T, TSrc ts, const float* pmask, f
         }
     }
     {
-        TcEpiOut eo{{}, model_out, I->w.D, I->w.out_b, T, B};
+        TcEpiOut eo{{}, {}, model_out, I->w.D, I->w.out_b, T, B};
         if (gemm<FMT>(I, I->Hs, I->Wout, Mg, I->nout, d, eo, s)) return 1;
     }
     EG_CUDA(cudaGetLastError());
@@ -372,10 +372,10 @@ int TcEngine::time_qkv(int B, int fmt, int iters, cudaStream_t s, float* ms) {
     EG_CUDA(cudaEventCreate(&e0)); EG_CUDA(cudaEventCreate(&e1));
     auto run = [&]() -> int {
         if (fmt == FMT_HALF) {
-            TcEpiQKVPlanes<FMT_HALF> eq{I->Qp.hi, I->Qp.lo, I->Kp.hi, I->Kp.lo, I->VT.hi, I->VT.lo, W.bqkv, H, 1.0f / sqrtf((float)dk)};
+            TcEpiQKVPlanes<FMT_HALF> eq{{}, I->Qp.hi, I->Qp.lo, I->Kp.hi, I->Kp.lo, I->VT.hi, I->VT.lo, W.bqkv, H, 1.0f / sqrtf((float)dk)};
             return gemm<FMT_HALF>(I, I->Hs, W.wqkv, Mg, nqkv, d, eq, s);
         }
-        TcEpiQKVPlanes<FMT_SPLIT> eq{I->Qp.hi, I->Qp.lo, I->Kp.hi, I->Kp.lo, I->VT.hi, I->VT.lo, W.bqkv, H, 1.0f / sqrtf((float)dk)};
+        TcEpiQKVPlanes<FMT_SPLIT> eq{{}, I->Qp.hi, I->Qp.lo, I->Kp.hi, I->Kp.lo, I->VT.hi, I->VT.lo, W.bqkv, H, 1.0f / sqrtf((float)dk)};
         return gemm<FMT_SPLIT>(I, I->Hs, W.wqkv, Mg, nqkv, d, eq, s);
     };
     for (int i = 0; i < 3; ++i) if (run()) return 1;
@@ -433,7 +433,7 @@ int selftest_gemm(int M, int N, int K, unsigned long long seed, int two_cta, int
     if (PA.alloc(M, K, 128) || PW.alloc(N, K, 256)) return 1;
     split_rows_kernel<<<(unsigned)(((long long)M * K + 255) / 256), 256>>>(A, PA.hi, PA.lo, (long long)M * K);
     split_rows_kernel<<<(unsigned)(((long long)N * K + 255) / 256), 256>>>(W, PW.hi, PW.lo, (long long)N * K);
-    TcEpiPlain e{{}, C1, N, nullptr, N};
+    TcEpiPlain e{{}, {}, C1, N, nullptr, N};
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     EG_CHECK(!two_cta || M % 256 == 0, "2-CTA self test needs M % 256 == 0");

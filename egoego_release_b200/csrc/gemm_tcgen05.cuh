@@ -54,16 +54,34 @@ template <int BN, int FMT> struct GemmCfg {
 //                                           the thread=row layout is already the coalesced one.
 constexpr int EPI_TILE_BYTES = 32 * 32 * 4;              // per epilogue warp
 
+// Per-warp prefetch of the functor's per-element read-only operand (residual / base) for one 32x32 chunk, in the
+// coalesced layout; issued one chunk ahead (and before the accumulator-ready wait for chunk 0) to hide HBM latency.
+template <class Epi>
+__device__ __forceinline__ void epilogue_prefetch(const Epi& epi, float4 (&pre)[8], int lane, int row_base, int col0) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) pre[it] = epi.pre(row_base + it * 4 + (lane >> 3), col0 + 4 * (lane & 7));
+}
+
+// `bias_lane` holds the bias of the warp's whole 128-column range (lane l: columns 4l..4l+3); the values a lane needs
+// for chunk `cidx` are fetched with warp shuffles, so the epilogue issues no per-chunk global loads for the bias.
 template <class Epi>
 __device__ __forceinline__ void epilogue_chunk(const Epi& epi, float4* tile, const uint32_t (&raw)[32], int lane,
-                                               int row_base /* first row of this warp's 32 */, int col0) {
+                                               int row_base /* first row of this warp's 32 */, int col0, int cidx,
+                                               float4 bias_lane, const float4 (&pre)[8]) {
     if (epi.direct(col0)) {                                // warp-uniform
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+        for (int j = 0; j < 32; ++j) {
+            const float comp = (j & 3) == 0 ? bias_lane.x : ((j & 3) == 1 ? bias_lane.y : ((j & 3) == 2 ? bias_lane.z : bias_lane.w));
+            v[j] = __uint_as_float(raw[j]) + __shfl_sync(0xffffffffu, comp, cidx * 8 + (j >> 2));
+        }
         epi.apply_row(row_base + lane, col0, v);
         return;
     }
+    const int src = cidx * 8 + (lane & 7);
+    float4 b4;
+    b4.x = __shfl_sync(0xffffffffu, bias_lane.x, src); b4.y = __shfl_sync(0xffffffffu, bias_lane.y, src);
+    b4.z = __shfl_sync(0xffffffffu, bias_lane.z, src); b4.w = __shfl_sync(0xffffffffu, bias_lane.w, src);
 #pragma unroll
     for (int j = 0; j < 8; ++j)
         tile[lane * 8 + (j ^ (lane & 7))] = make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]),
@@ -74,14 +92,40 @@ __device__ __forceinline__ void epilogue_chunk(const Epi& epi, float4* tile, con
     for (int it = 0; it < 8; ++it) {
         const int r = it * 4 + (lane >> 3);
         const float4 acc = tile[r * 8 + (j ^ (r & 7))];
-        epi.apply4(row_base + r, col0 + 4 * j, acc);
+        epi.apply4(row_base + r, col0 + 4 * j, acc, b4, pre[it]);
     }
     __syncwarp();
+}
+
+// Drain this warp's 32 rows x NCOLS (=128) columns of an accumulator: bias in registers, operand prefetch one chunk ahead.
+// `wait_ready()` blocks until the accumulator may be read (called after the first prefetch has been issued).
+template <int NCOLS, class Epi, class Wait>
+__device__ __forceinline__ void epilogue_drain(const Epi& epi, float4* tile, uint32_t taddr, int lane, int row_base, int col_begin,
+                                               Wait wait_ready) {
+    static_assert(NCOLS == 128, "bias_lane covers exactly 32 lanes x 4 columns");
+    const float4 bias_lane = epi.bias4(col_begin + 4 * lane);
+    float4 pre[8];
+    epilogue_prefetch(epi, pre, lane, row_base, col_begin);
+    wait_ready();
+#pragma unroll 1
+    for (int c = 0; c < NCOLS / 32; ++c) {
+        float4 cur[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) cur[it] = pre[it];
+        if (c + 1 < NCOLS / 32) epilogue_prefetch(epi, pre, lane, row_base, col_begin + (c + 1) * 32);
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(taddr + c * 32, r);
+        ptx::tmem_ld_wait();
+        epilogue_chunk(epi, tile, r, lane, row_base, col_begin + c * 32, c, bias_lane, cur);
+    }
 }
 
 struct EpiNoDirect {
     __device__ __forceinline__ bool direct(int) const { return false; }
     __device__ __forceinline__ void apply_row(int, int, const float (&)[32]) const {}
+};
+struct EpiNoPre {
+    __device__ __forceinline__ float4 pre(int, int) const { return make_float4(0.f, 0.f, 0.f, 0.f); }
 };
 
 __device__ __forceinline__ void store_half8(__nv_bfloat16* dst /* fp16 bits */, const float* v) {
@@ -132,21 +176,22 @@ __device__ __forceinline__ void store_planes4(__nv_bfloat16* hi, __nv_bfloat16* 
 __device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
-struct TcEpiPlain : EpiNoDirect {         // C = acc (+ bias): self-test / generic
+struct TcEpiPlain : EpiNoDirect, EpiNoPre {   // C = acc (+ bias): self-test / generic
     float* C; int ldc; const float* bias; int n_valid;
-    __device__ __forceinline__ void apply4(int row, int col, float4 a) const {
+    __device__ __forceinline__ float4 bias4(int col) const { return bias ? ld4(bias + col) : make_float4(0.f, 0.f, 0.f, 0.f); }
+    __device__ __forceinline__ void apply4(int row, int col, float4 a, float4 b, float4) const {
         if (col >= n_valid) return;
-        if (bias) a = add4(a, ld4(bias + col));
-        *reinterpret_cast<float4*>(C + (long long)row * ldc + col) = a;
+        *reinterpret_cast<float4*>(C + (long long)row * ldc + col) = add4(a, b);
     }
 };
 
-struct TcEpiBase : EpiNoDirect {          // base = x_cond-half of start_conv + bias + positional row (constant per window)
+struct TcEpiBase : EpiNoDirect, EpiNoPre {    // base = x_cond-half of start_conv + bias + positional row (constant per window)
     float* base; int ld; const float* bias; const float* pos; int T;
-    __device__ __forceinline__ void apply4(int row, int col, float4 a) const {
+    __device__ __forceinline__ float4 bias4(int col) const { return ld4(bias + col); }
+    __device__ __forceinline__ void apply4(int row, int col, float4 a, float4 b, float4) const {
         const int l = row % LP;
         float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (l >= 1 && l <= T) r = add4(add4(a, ld4(bias + col)), ld4(pos + (long long)(l + 1) * ld + col));
+        if (l >= 1 && l <= T) r = add4(add4(a, b), ld4(pos + (long long)(l + 1) * ld + col));
         *reinterpret_cast<float4*>(base + (long long)row * ld + col) = r;
     }
 };
@@ -155,10 +200,11 @@ template <int FMT>
 struct TcEpiStart : EpiNoDirect {         // H = x-half GEMM + base ; row 0 = time token ; writes fp32 + operand planes
     float* H; __nv_bfloat16* Hhi; __nv_bfloat16* Hlo; int ld;
     const float* base; const float* pos; const float* temb; TSrc ts; int T; int n_windows;
-    __device__ __forceinline__ void apply4(int row, int col, float4 a) const {
+    __device__ __forceinline__ float4 bias4(int) const { return make_float4(0.f, 0.f, 0.f, 0.f); }
+    __device__ __forceinline__ float4 pre(int row, int col) const { return ld4(base + (long long)row * ld + col); }
+    __device__ __forceinline__ void apply4(int row, int col, float4 a, float4, float4 bv) const {
         const int w = row / LP;
         const int l = (w < n_windows) ? row % LP : LP;      // rows of the rounding-up window are padding
-        const float4 bv = ld4(base + (long long)row * ld + col);   // unconditional: lets the loads of a chunk be batched
         float4 r;
         if (l == 0)      r = add4(ld4(temb + (long long)ts.get(w) * ld + col), ld4(pos + ld + col));
         else if (l <= T) r = add4(a, bv);
@@ -169,42 +215,51 @@ struct TcEpiStart : EpiNoDirect {         // H = x-half GEMM + base ; row 0 = ti
     }
 };
 
-struct TcEpiBiasScaleF32 : EpiNoDirect {  // QKV projection -> fp32 [M, ldc] (q block pre-scaled by 1/sqrt(d_k))
+struct TcEpiBiasScaleF32 : EpiNoDirect, EpiNoPre {  // QKV projection -> fp32 [M, ldc] (q block pre-scaled by 1/sqrt(d_k))
     float* C; int ldc; const float* bias; int scale_cols; float scale;
-    __device__ __forceinline__ void apply4(int row, int col, float4 a) const {
+    __device__ __forceinline__ float4 bias4(int col) const { return ld4(bias + col); }
+    __device__ __forceinline__ void apply4(int row, int col, float4 a, float4 b, float4) const {
         const float s = col < scale_cols ? scale : 1.0f;
-        a = add4(a, ld4(bias + col));
+        a = add4(a, b);
         *reinterpret_cast<float4*>(C + (long long)row * ldc + col) = make_float4(a.x * s, a.y * s, a.z * s, a.w * s);
     }
 };
 
 struct TcEpiBiasResidF32 : EpiNoDirect {  // fc / w_2: acc + bias + residual -> fp32 (pre-LayerNorm)
     float* C; int ldc; const float* bias; const float* res;
-    __device__ __forceinline__ void apply4(int row, int col, float4 a) const {
-        const long long o = (long long)row * ldc + col;
-        *reinterpret_cast<float4*>(C + o) = add4(add4(a, ld4(bias + col)), ld4(res + o));
+    __device__ __forceinline__ float4 bias4(int col) const { return ld4(bias + col); }
+    __device__ __forceinline__ float4 pre(int row, int col) const { return ld4(res + (long long)row * ldc + col); }
+    __device__ __forceinline__ void apply4(int row, int col, float4 a, float4 b, float4 rv) const {
+        *reinterpret_cast<float4*>(C + (long long)row * ldc + col) = add4(add4(a, b), rv);
     }
 };
 
 template <int FMT>
-struct TcEpiBiasReluSplit : EpiNoDirect { // w_1: relu(acc + bias) -> operand planes (A operand of w_2)
+struct TcEpiBiasReluSplit : EpiNoDirect, EpiNoPre { // w_1: relu(acc + bias) -> operand planes (A operand of w_2)
     __nv_bfloat16* hi; __nv_bfloat16* lo; int ld; const float* bias;
-    __device__ __forceinline__ void apply4(int row, int col, float4 a) const {
-        a = add4(a, ld4(bias + col));
+    __device__ __forceinline__ float4 bias4(int col) const { return ld4(bias + col); }
+    __device__ __forceinline__ void apply4(int row, int col, float4 a, float4 b, float4) const {
+        a = add4(a, b);
         a = make_float4(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f), fmaxf(a.z, 0.f), fmaxf(a.w, 0.f));
         const long long o = (long long)row * ld + col;
         store_planes4<FMT>(hi + o, lo + o, a);
     }
 };
 
-struct TcEpiOut : EpiNoDirect {           // linear_out: tokens 1..T, first d_feats columns -> compact [B,T,d_feats]
+struct TcEpiOut : EpiNoDirect, EpiNoPre { // linear_out: tokens 1..T, first d_feats columns -> compact [B,T,d_feats]
     float* out; int d_feats; const float* bias; int T; int n_windows;
-    __device__ __forceinline__ void apply4(int row, int col, float4 a) const {
+    __device__ __forceinline__ float4 bias4(int col) const {    // bias has d_feats entries: guard the padded tail
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col < d_feats) { b.x = bias[col]; b.y = bias[col + 1]; }
+        if (col + 2 < d_feats) { b.z = bias[col + 2]; b.w = bias[col + 3]; }
+        return b;
+    }
+    __device__ __forceinline__ void apply4(int row, int col, float4 a, float4 b, float4) const {
         const int w = row / LP, l = row % LP;
         if (l < 1 || l > T || w >= n_windows || col >= d_feats) return;
         float* o = out + ((long long)w * T + (l - 1)) * d_feats + col;       // 8-byte aligned (d_feats even, col % 4 == 0)
-        *reinterpret_cast<float2*>(o) = make_float2(a.x + bias[col], a.y + bias[col + 1]);
-        if (col + 2 < d_feats) *reinterpret_cast<float2*>(o + 2) = make_float2(a.z + bias[col + 2], a.w + bias[col + 3]);
+        *reinterpret_cast<float2*>(o) = make_float2(a.x + b.x, a.y + b.y);
+        if (col + 2 < d_feats) *reinterpret_cast<float2*>(o + 2) = make_float2(a.z + b.z, a.w + b.w);
     }
 };
 
@@ -304,18 +359,11 @@ gemm_split3_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constan
             const int a = (ACC_STAGES == 2) ? (it & 1) : 0;
             const uint32_t aph = (ACC_STAGES == 2) ? ((it >> 1) & 1) : (it & 1);
             const int m0 = (tile / n_tiles) * GEMM_BM, n0 = (tile % n_tiles) * BN;
-            ptx::mbar_wait(&tfull_bar[a], aph);
-            ptx::tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * BN;
-            float4* etile = epi_tiles + (warp - 2) * 256;
             const int chalf = (warp - 2) >> 2;                 // which half of the tile columns this warp drains
-#pragma unroll 1
-            for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 32) {
-                uint32_t r[32];
-                ptx::tmem_ld_32x32(taddr + c, r);
-                ptx::tmem_ld_wait();
-                epilogue_chunk(epi, etile, r, lane, m0 + quarter * 32, n0 + c);
-            }
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * BN + chalf * (BN / 2);
+            float4* etile = epi_tiles + (warp - 2) * 256;
+            epilogue_drain<BN / 2>(epi, etile, taddr, lane, m0 + quarter * 32, n0 + chalf * (BN / 2),
+                                   [&]() { ptx::mbar_wait(&tfull_bar[a], aph); ptx::tc_fence_after(); });
             ptx::tc_fence_before();
             ptx::mbar_arrive(&tempty_bar[a]);
         }
@@ -436,18 +484,11 @@ gemm_split3_2cta_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_co
             const int a = it & 1;
             const uint32_t aph = (it >> 1) & 1;
             const int m0 = (tile / n_tiles) * 256 + (int)rank * 128, n0 = (tile % n_tiles) * BN;
-            ptx::mbar_wait(&tfull_bar[a], aph);
-            ptx::tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * BN;
-            float4* etile = epi_tiles + (warp - 2) * 256;
             const int chalf = (warp - 2) >> 2;                 // which half of the tile columns this warp drains
-#pragma unroll 1
-            for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 32) {
-                uint32_t r[32];
-                ptx::tmem_ld_32x32(taddr + c, r);
-                ptx::tmem_ld_wait();
-                epilogue_chunk(epi, etile, r, lane, m0 + quarter * 32, n0 + c);
-            }
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * BN + chalf * (BN / 2);
+            float4* etile = epi_tiles + (warp - 2) * 256;
+            epilogue_drain<BN / 2>(epi, etile, taddr, lane, m0 + quarter * 32, n0 + chalf * (BN / 2),
+                                   [&]() { ptx::mbar_wait(&tfull_bar[a], aph); ptx::tc_fence_after(); });
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_cluster(&tempty_bar[a], 0);
