@@ -106,12 +106,11 @@ struct TcImpl {
     std::vector<TcLayer> layers;
     Plane X, C, Hs, O, F;                       // activation planes (A operands)
     Plane Qp, Kp, VT;                           // attention operand planes (see attn_tcgen05.cuh)
-    Plane Ident;                                // fp16 identity [512,512]: residual add as extra k-blocks of the fused-LN GEMM
     bool fuse_ln = true;                        // EGOEGO_FUSE_LN=0 keeps GEMM + LayerNorm separate in the fp16 format too
     bool attn_tc = true;                        // EGOEGO_ATTN=simt selects the fp32 CUDA-core attention (bisecting)
     float *base = nullptr, *H = nullptr, *Y = nullptr, *QKV = nullptr;
     ~TcImpl() {
-        for (Plane* p : {&Wx, &Wc, &Wout, &X, &C, &Hs, &O, &F, &Qp, &Kp, &VT, &Ident}) p->release();
+        for (Plane* p : {&Wx, &Wc, &Wout, &X, &C, &Hs, &O, &F, &Qp, &Kp, &VT}) p->release();
         for (auto& l : layers) for (Plane* p : {&l.wqkv, &l.fc, &l.w1, &l.w2}) p->release();
         for (float* p : {base, H, Y, QKV}) if (p) cudaFree(p);
     }
@@ -216,11 +215,7 @@ int TcEngine::init(const TcWeights& w, cudaStream_t) {
     EG_CUDA(cudaMalloc(&I->base, M * d * 4));
     EG_CUDA(cudaMalloc(&I->H, M * d * 4));
     EG_CUDA(cudaMalloc(&I->Y, M * d * 4));
-    {   // identity "weight" of the fused residual add (fp16 1.0 on the diagonal)
-        if (I->Ident.alloc(512, 512, 256)) return 1;
-        std::vector<__half> id((size_t)512 * 512, __float2half(0.f));
-        for (int i = 0; i < 512; ++i) id[(size_t)i * 512 + i] = __float2half(1.0f);
-        EG_CUDA(cudaMemcpy(I->Ident.hi, id.data(), id.size() * 2, cudaMemcpyHostToDevice));
+    {
         const char* fl = getenv("EGOEGO_FUSE_LN");
         I->fuse_ln = !(fl && fl[0] == '0');
         EG_CUDA(cudaFuncSetAttribute(gemm_ln_half_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmLnCfg::SMEM_BYTES));
@@ -291,12 +286,12 @@ static int launch_gemm_ln(TcImpl* I, const Plane& A, const Plane& W, int M, int 
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        EG_CUDA(cudaLaunchKernelEx(&cfg, gemm_ln_half_2cta_kernel, A.m16, W.m16_128, I->Hs.m16, I->Ident.m16_128, M, K, bias, g, b, I->Hs.h16));
+        EG_CUDA(cudaLaunchKernelEx(&cfg, gemm_ln_half_2cta_kernel, A.m16, W.m16_128, M, K, bias, g, b, (const __nv_bfloat16*)I->Hs.h16, I->Hs.h16));
         return 0;
     }
     const int tiles = M / GEMM_BM;
     gemm_ln_half_kernel<<<tiles < I->sms ? tiles : I->sms, GEMM_THREADS, GemmLnCfg::SMEM_BYTES, s>>>(
-        A.m16, W.m16, I->Hs.m16, I->Ident.m16, M, K, bias, g, b, I->Hs.h16);
+        A.m16, W.m16, M, K, bias, g, b, (const __nv_bfloat16*)I->Hs.h16, I->Hs.h16);
     EG_CUDA(cudaGetLastError());
     return 0;
 }

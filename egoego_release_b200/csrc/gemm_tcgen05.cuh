@@ -503,31 +503,71 @@ gemm_split3_2cta_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_co
 // ---- full-row fp16 GEMM with fused residual + bias + LayerNorm ------------------------------------------
 // The post-LN sub-layers (attention fc, FFN w_2) are memory-bound in the fp16 format (arithmetic intensity ~100 FLOP/B
 // with separate residual / pre-LN / LayerNorm passes).  This kernel computes a whole 128 x 512 row block per CTA:
-//     acc  = A[128,K] W[512,K]^T  +  R[128,512] I[512,512]^T        (the residual enters as extra k-blocks against an
-//                                                                    identity "weight": exact, and free on the tensor core)
-//     out  = LayerNorm(acc + bias) * gamma + beta   ->  one fp16 operand plane
+//     acc  = A[128,K] W[512,K]^T
+//     out  = LayerNorm(acc + bias + residual) * gamma + beta   ->  one fp16 operand plane
 // The accumulator fills all 512 TMEM columns (two N = 256 MMAs per k-step), so the LayerNorm statistics of a row are
 // available inside the CTA: three passes over TMEM in the native thread-per-row layout (mean, centred variance,
 // normalise), partial sums of the two column halves exchanged through shared memory, and a final smem transpose for
 // coalesced stores.  Replaces a GEMM + a LayerNorm kernel and two fp32 round trips per sub-layer.
 // LayerNorm epilogue of one 128 x 512 accumulator block held in TMEM (thread = row, two warps per lane quarter each
-// owning 256 columns): mean -> centred variance -> normalise, then smem transpose and coalesced fp16 stores.
+// owning 256 columns).  Pass 1 adds bias and the residual (loaded COALESCED from its fp16 plane, one chunk ahead, and
+// transposed to the thread-per-row layout through the warp's smem tile), writes x = acc + bias + res back to TMEM
+// (tcgen05.st) and accumulates the row sum; pass 2 the centred variance; pass 3 normalises, transposes and stores fp16.
+// `res16` and `out16` may alias: a warp reads exactly the region it later overwrites.
+template <class Wait>
 __device__ __forceinline__ void ln_epilogue_tile(uint32_t tmem_base, float4* epi_tiles, float* part, int warp, int lane, int m0,
                                                  const float* bias, const float* gamma, const float* beta /* shared memory */,
-                                                 __nv_bfloat16* __restrict__ out16) {
+                                                 const __nv_bfloat16* res16 /* fp16 bits */, __nv_bfloat16* out16,
+                                                 Wait wait_ready) {
     const int quarter = warp & 3, hf = (warp - 2) >> 2;
     const int r = quarter * 32 + lane;               // row within the tile == TMEM lane
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + hf * 256;
     float4* etile = epi_tiles + (warp - 2) * 256;
-    float sum = 0.f;                                 // pass 1: row mean of (acc + bias)
+    const int jj = lane & 7;
+    auto load_res = [&](uint2 (&dst)[8], int c) {     // coalesced: lane -> rows i*4 + lane/8, 4 columns at 4*(lane&7)
+#pragma unroll
+        for (int i2 = 0; i2 < 8; ++i2) {
+            const int rr = i2 * 4 + (lane >> 3);
+            dst[i2] = *reinterpret_cast<const uint2*>(res16 + (long long)(m0 + quarter * 32 + rr) * 512 + hf * 256 + c + 4 * jj);
+        }
+    };
+    uint2 pre[8];
+    load_res(pre, 0);
+    wait_ready();
+    float sum = 0.f;                                 // pass 1
 #pragma unroll 1
     for (int c = 0; c < 256; c += 32) {
+        uint2 cur[8];
+#pragma unroll
+        for (int i2 = 0; i2 < 8; ++i2) cur[i2] = pre[i2];
+        if (c + 32 < 256) load_res(pre, c + 32);
         uint32_t raw[32];
         ptx::tmem_ld_32x32(taddr + c, raw);
+#pragma unroll
+        for (int i2 = 0; i2 < 8; ++i2) {             // residual chunk -> smem tile (coalesced layout, swizzled)
+            const int rr = i2 * 4 + (lane >> 3);
+            const __half2 h0 = *reinterpret_cast<const __half2*>(&cur[i2].x), h1 = *reinterpret_cast<const __half2*>(&cur[i2].y);
+            const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+            etile[rr * 8 + (jj ^ (rr & 7))] = make_float4(f0.x, f0.y, f1.x, f1.y);
+        }
+        __syncwarp();
         ptx::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) sum += __uint_as_float(raw[j]) + bias[hf * 256 + c + j];
+        for (int j = 0; j < 8; ++j) {                // own row back from the tile: thread-per-row layout
+            const float4 rv = etile[lane * 8 + (j ^ (lane & 7))];
+            const int cb = hf * 256 + c + 4 * j;
+            const float x0 = __uint_as_float(raw[4 * j + 0]) + bias[cb + 0] + rv.x;
+            const float x1 = __uint_as_float(raw[4 * j + 1]) + bias[cb + 1] + rv.y;
+            const float x2 = __uint_as_float(raw[4 * j + 2]) + bias[cb + 2] + rv.z;
+            const float x3 = __uint_as_float(raw[4 * j + 3]) + bias[cb + 3] + rv.w;
+            sum += (x0 + x1) + (x2 + x3);
+            raw[4 * j + 0] = __float_as_uint(x0); raw[4 * j + 1] = __float_as_uint(x1);
+            raw[4 * j + 2] = __float_as_uint(x2); raw[4 * j + 3] = __float_as_uint(x3);
+        }
+        ptx::tmem_st_32x32(taddr + c, raw);
+        __syncwarp();
     }
+    ptx::tmem_st_wait();
     part[hf * 128 + r] = sum;
     asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
     const float mean = (part[r] + part[128 + r]) * (1.0f / 512.0f);
@@ -538,7 +578,7 @@ __device__ __forceinline__ void ln_epilogue_tile(uint32_t tmem_base, float4* epi
         ptx::tmem_ld_32x32(taddr + c, raw);
         ptx::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { const float d = __uint_as_float(raw[j]) + bias[hf * 256 + c + j] - mean; sq += d * d; }
+        for (int j = 0; j < 32; ++j) { const float d = __uint_as_float(raw[j]) - mean; sq += d * d; }
     }
     part[256 + hf * 128 + r] = sq;
     asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
@@ -552,14 +592,13 @@ __device__ __forceinline__ void ln_epilogue_tile(uint32_t tmem_base, float4* epi
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             float4 y;
-            y.x = (__uint_as_float(raw[4 * j + 0]) + bias[col0 + 4 * j + 0] - mean) * rstd * gamma[col0 + 4 * j + 0] + beta[col0 + 4 * j + 0];
-            y.y = (__uint_as_float(raw[4 * j + 1]) + bias[col0 + 4 * j + 1] - mean) * rstd * gamma[col0 + 4 * j + 1] + beta[col0 + 4 * j + 1];
-            y.z = (__uint_as_float(raw[4 * j + 2]) + bias[col0 + 4 * j + 2] - mean) * rstd * gamma[col0 + 4 * j + 2] + beta[col0 + 4 * j + 2];
-            y.w = (__uint_as_float(raw[4 * j + 3]) + bias[col0 + 4 * j + 3] - mean) * rstd * gamma[col0 + 4 * j + 3] + beta[col0 + 4 * j + 3];
+            y.x = (__uint_as_float(raw[4 * j + 0]) - mean) * rstd * gamma[col0 + 4 * j + 0] + beta[col0 + 4 * j + 0];
+            y.y = (__uint_as_float(raw[4 * j + 1]) - mean) * rstd * gamma[col0 + 4 * j + 1] + beta[col0 + 4 * j + 1];
+            y.z = (__uint_as_float(raw[4 * j + 2]) - mean) * rstd * gamma[col0 + 4 * j + 2] + beta[col0 + 4 * j + 2];
+            y.w = (__uint_as_float(raw[4 * j + 3]) - mean) * rstd * gamma[col0 + 4 * j + 3] + beta[col0 + 4 * j + 3];
             etile[lane * 8 + (j ^ (lane & 7))] = y;
         }
         __syncwarp();
-        const int jj = lane & 7;
 #pragma unroll
         for (int i2 = 0; i2 < 8; ++i2) {
             const int rr = i2 * 4 + (lane >> 3);
@@ -581,9 +620,8 @@ struct GemmLnCfg {
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_ln_half_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mW,
-                    const __grid_constant__ CUtensorMap mR, const __grid_constant__ CUtensorMap mI,
                     int M, int K, const float* __restrict__ bias, const float* __restrict__ gamma,
-                    const float* __restrict__ beta, __nv_bfloat16* __restrict__ out16 /* fp16 bits, [M,512] */) {
+                    const float* __restrict__ beta, const __nv_bfloat16* res16, __nv_bfloat16* out16 /* fp16 bits, [M,512] */) {
     constexpr int STAGES = GemmLnCfg::STAGES, A_BYTES = GemmLnCfg::A_BYTES, STAGE_BYTES = GemmLnCfg::STAGE_BYTES;
     constexpr uint32_t IDESC = ptx::make_idesc_f16(GEMM_BM, 256);
     extern __shared__ uint8_t smem_raw[];
@@ -600,10 +638,10 @@ gemm_ln_half_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constan
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2);
 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-    const int m_tiles = M / GEMM_BM, kb_main = K / GEMM_BK, kb_total = kb_main + 512 / GEMM_BK;
+    const int m_tiles = M / GEMM_BM, kb_total = K / GEMM_BK;
 
     if (warp == 0 && lane == 0) {
-        ptx::prefetch_tmap(&mA); ptx::prefetch_tmap(&mW); ptx::prefetch_tmap(&mR); ptx::prefetch_tmap(&mI);
+        ptx::prefetch_tmap(&mA); ptx::prefetch_tmap(&mW);
         for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
         ptx::mbar_init(tfull_bar, 1); ptx::mbar_init(tempty_bar, 32 * GEMM_EPI_WARPS);
         ptx::fence_barrier_init();
@@ -623,16 +661,9 @@ gemm_ln_half_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constan
                     ptx::mbar_wait(&empty_bar[s], ph ^ 1);
                     uint8_t* st = smem + s * STAGE_BYTES;
                     ptx::mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
-                    if (kb < kb_main) {
-                        ptx::tma_load_2d(st, &mA, &full_bar[s], kb * GEMM_BK, m0);
-                        ptx::tma_load_2d(st + A_BYTES, &mW, &full_bar[s], kb * GEMM_BK, 0);
-                        ptx::tma_load_2d(st + A_BYTES + 32768, &mW, &full_bar[s], kb * GEMM_BK, 256);
-                    } else {                             // residual rows against the identity
-                        const int kr = (kb - kb_main) * GEMM_BK;
-                        ptx::tma_load_2d(st, &mR, &full_bar[s], kr, m0);
-                        ptx::tma_load_2d(st + A_BYTES, &mI, &full_bar[s], kr, 0);
-                        ptx::tma_load_2d(st + A_BYTES + 32768, &mI, &full_bar[s], kr, 256);
-                    }
+                    ptx::tma_load_2d(st, &mA, &full_bar[s], kb * GEMM_BK, m0);
+                    ptx::tma_load_2d(st + A_BYTES, &mW, &full_bar[s], kb * GEMM_BK, 0);
+                    ptx::tma_load_2d(st + A_BYTES + 32768, &mW, &full_bar[s], kb * GEMM_BK, 256);
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
             }
@@ -664,9 +695,8 @@ gemm_ln_half_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constan
     } else {                                             // ===== LayerNorm epilogue warps 2..9 =====
         int it = 0;
         for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
-            ptx::mbar_wait(tfull_bar, it & 1);
-            ptx::tc_fence_after();
-            ln_epilogue_tile(tmem_base, epi_tiles, part, warp, lane, tile * GEMM_BM, vec, vec + 512, vec + 1024, out16);
+            ln_epilogue_tile(tmem_base, epi_tiles, part, warp, lane, tile * GEMM_BM, vec, vec + 512, vec + 1024, res16, out16,
+                             [&]() { ptx::mbar_wait(tfull_bar, it & 1); ptx::tc_fence_after(); });
             ptx::tc_fence_before();
             ptx::mbar_arrive(tempty_bar);
         }
@@ -689,9 +719,8 @@ struct GemmLn2Cfg {
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_ln_half_2cta_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mW /*128-row boxes*/,
-                         const __grid_constant__ CUtensorMap mR, const __grid_constant__ CUtensorMap mI /*128-row boxes*/,
                          int M, int K, const float* __restrict__ bias, const float* __restrict__ gamma,
-                         const float* __restrict__ beta, __nv_bfloat16* __restrict__ out16) {
+                         const float* __restrict__ beta, const __nv_bfloat16* res16, __nv_bfloat16* out16) {
     constexpr int STAGES = GemmLn2Cfg::STAGES, T_BYTES = GemmLn2Cfg::T_BYTES, STAGE_BYTES = GemmLn2Cfg::STAGE_BYTES;
     constexpr uint32_t IDESC = ptx::make_idesc_f16(256, 256);
     extern __shared__ uint8_t smem_raw[];
@@ -711,10 +740,10 @@ gemm_ln_half_2cta_kernel(const __grid_constant__ CUtensorMap mA, const __grid_co
     const uint32_t rank = ptx::cluster_ctarank();
     const bool leader = rank == 0;
     const int pair = blockIdx.x / 2, n_pairs = gridDim.x / 2;
-    const int m_tiles = M / 256, kb_main = K / GEMM_BK, kb_total = kb_main + 512 / GEMM_BK;
+    const int m_tiles = M / 256, kb_total = K / GEMM_BK;
 
     if (warp == 0 && lane == 0) {
-        ptx::prefetch_tmap(&mA); ptx::prefetch_tmap(&mW); ptx::prefetch_tmap(&mR); ptx::prefetch_tmap(&mI);
+        ptx::prefetch_tmap(&mA); ptx::prefetch_tmap(&mW);
         for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 2); ptx::mbar_init(&empty_bar[s], 1); }
         ptx::mbar_init(tfull_bar, 1); ptx::mbar_init(tempty_bar, 2 * GEMM_EPI_WARPS);
         ptx::fence_barrier_init();
@@ -736,11 +765,9 @@ gemm_ln_half_2cta_kernel(const __grid_constant__ CUtensorMap mA, const __grid_co
                     uint8_t* st = smem + s * STAGE_BYTES;
                     if (leader) ptx::mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
                     else        ptx::mbar_arrive_cluster(&full_bar[s], 0);
-                    const bool main = kb < kb_main;
-                    const int kx = main ? kb * GEMM_BK : (kb - kb_main) * GEMM_BK;
-                    ptx::tma_load_2d_2cta(st, main ? &mA : &mR, &full_bar[s], kx, m0);
-                    ptx::tma_load_2d_2cta(st + T_BYTES, main ? &mW : &mI, &full_bar[s], kx, (int)rank * 128);
-                    ptx::tma_load_2d_2cta(st + 2 * T_BYTES, main ? &mW : &mI, &full_bar[s], kx, 256 + (int)rank * 128);
+                    ptx::tma_load_2d_2cta(st, &mA, &full_bar[s], kb * GEMM_BK, m0);
+                    ptx::tma_load_2d_2cta(st + T_BYTES, &mW, &full_bar[s], kb * GEMM_BK, (int)rank * 128);
+                    ptx::tma_load_2d_2cta(st + 2 * T_BYTES, &mW, &full_bar[s], kb * GEMM_BK, 256 + (int)rank * 128);
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
             }
@@ -772,9 +799,8 @@ gemm_ln_half_2cta_kernel(const __grid_constant__ CUtensorMap mA, const __grid_co
     } else {                                             // ===== LayerNorm epilogue warps 2..9 (both CTAs) =====
         int it = 0;
         for (int tile = pair; tile < m_tiles; tile += n_pairs, ++it) {
-            ptx::mbar_wait(tfull_bar, it & 1);
-            ptx::tc_fence_after();
-            ln_epilogue_tile(tmem_base, epi_tiles, part, warp, lane, tile * 256 + (int)rank * 128, vec, vec + 512, vec + 1024, out16);
+            ln_epilogue_tile(tmem_base, epi_tiles, part, warp, lane, tile * 256 + (int)rank * 128, vec, vec + 512, vec + 1024,
+                             res16, out16, [&]() { ptx::mbar_wait(tfull_bar, it & 1); ptx::tc_fence_after(); });
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_cluster(tempty_bar, 0);
