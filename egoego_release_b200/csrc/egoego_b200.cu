@@ -210,12 +210,12 @@ int egoego_create(const egoego_cfg* cfg, egoego_handle* out) {
     const char* g = getenv("EGOEGO_GRAPH");
     c->use_graph = !(g && g[0] == '0');
     // precision policy: the last `precise_last` steps (t < precise_last) run the 3-term bf16 split,
-    // earlier steps a single fp16 pass.  cfg.precise_last_steps < 0 selects the default max(ceil(N/8), 48); N = all precise.
+    // earlier steps a single fp16 pass.  cfg.precise_last_steps < 0 selects the default max(ceil(N/16), 48); N = all precise.
     {
         int pl = cfg->precise_last_steps;
         const char* e = getenv("EGOEGO_PRECISE_STEPS");
         if (e && e[0]) pl = atoi(e);
-        if (pl < 0) { pl = (cfg->timesteps + 7) / 8; if (pl < 48) pl = 48; }
+        if (pl < 0) { pl = (cfg->timesteps + 15) / 16; if (pl < 48) pl = 48; }
         if (pl > cfg->timesteps) pl = cfg->timesteps;
         c->precise_last = (cfg->engine == EGOEGO_ENGINE_TCGEN05) ? pl : cfg->timesteps;
     }

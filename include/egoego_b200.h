@@ -56,7 +56,7 @@ typedef struct egoego_cfg {
     int32_t engine;        /* EGOEGO_ENGINE_*                                          */
     int32_t precise_last_steps; /* tensor engine precision policy: the last K diffusion steps (t < K) use the
                               3-term bf16 split (fp32-grade); earlier steps one fp16 pass, whose error is damped
-                              by posterior_mean_coef1[t].  -1 = default max(ceil(timesteps/8), 48); timesteps = all steps
+                              by posterior_mean_coef1[t].  -1 = default max(ceil(timesteps/16), 48); timesteps = all steps
                               split.  The per-call entry points (denoiser_forward, p_sample_step) always split. */
 } egoego_cfg;
 
