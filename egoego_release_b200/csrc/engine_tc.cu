@@ -167,6 +167,37 @@ static int launch_gemm_2cta(TcImpl* I, const Plane& A, const Plane& W, int M, in
     return 0;
 }
 
+// A-resident CTA-pair GEMM (fp16 format, K = 512): groups of 3 N tiles per 256-row block
+template <class Epi>
+static int launch_gemm_ares(TcImpl* I, const Plane& A, const Plane& W, int M, int N, const Epi& epi, cudaStream_t s) {
+    constexpr int G = 3;
+    using Cfg = GemmAresCfg<G>;
+    static bool attr_set = false;
+    auto kern = gemm_ares_half_2cta_kernel<G, Epi>;
+    if (!attr_set) {
+        EG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    EG_CHECK(M % 256 == 0 && (N / 256) % G == 0 && N % 256 == 0, "A-resident gemm shape not tile-aligned");
+    const int items = (M / 256) * ((N / 256) / G);
+    int pairs = I->sms / 2;
+    if (items < pairs) pairs = items;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    EG_CUDA(cudaLaunchKernelEx(&cfg, kern, A.m16, W.m16_128, M, N, epi));
+    return 0;
+}
+
+static bool use_ares() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("EGOEGO_QKV_ARES"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
+
 template <int FMT, class Epi>
 static int gemm(TcImpl* I, const Plane& A, const Plane& W, int M, int N, int K, const Epi& epi, cudaStream_t s) {
     if (use_2cta() && M % 256 == 0) return launch_gemm_2cta<FMT>(I, A, W, M, N, K, epi, s);
@@ -311,7 +342,11 @@ static int denoiser_impl(TcImpl* I, int B, int T, TSrc ts, const float* pmask, f
         TcLayer& W = I->layers[l];
         if (I->attn_tc) {
             TcEpiQKVPlanes<FMT> eq{{}, I->Qp.hi, I->Qp.lo, I->Kp.hi, I->Kp.lo, I->VT.hi, I->VT.lo, W.bqkv, H, 1.0f / sqrtf((float)dk)};
-            if (gemm<FMT>(I, I->Hs, W.wqkv, Mg, nqkv, d, eq, s)) return 1;
+            if (FMT == FMT_HALF && use_2cta() && use_ares() && d == 512 && (nqkv / 256) % 3 == 0) {
+                if (launch_gemm_ares(I, I->Hs, W.wqkv, Mg, nqkv, eq, s)) return 1;
+            } else {
+                if (gemm<FMT>(I, I->Hs, W.wqkv, Mg, nqkv, d, eq, s)) return 1;
+            }
             const int items = B * H;
             attention_tc_kernel<FMT><<<items < I->sms ? items : I->sms, ATT_THREADS, ATT_SMEM_BYTES, s>>>(
                 I->Qp.mhi, I->Qp.mlo, I->Kp.mhi, I->Kp.mlo, I->VT.mhi, I->VT.mlo, I->O.hi, I->O.lo, H * dk, items, H, L);
@@ -368,6 +403,7 @@ int TcEngine::time_qkv(int B, int fmt, int iters, cudaStream_t s, float* ms) {
     auto run = [&]() -> int {
         if (fmt == FMT_HALF) {
             TcEpiQKVPlanes<FMT_HALF> eq{{}, I->Qp.hi, I->Qp.lo, I->Kp.hi, I->Kp.lo, I->VT.hi, I->VT.lo, W.bqkv, H, 1.0f / sqrtf((float)dk)};
+            if (use_2cta() && use_ares() && d == 512 && (nqkv / 256) % 3 == 0) return launch_gemm_ares(I, I->Hs, W.wqkv, Mg, nqkv, eq, s);
             return gemm<FMT_HALF>(I, I->Hs, W.wqkv, Mg, nqkv, d, eq, s);
         }
         TcEpiQKVPlanes<FMT_SPLIT> eq{{}, I->Qp.hi, I->Qp.lo, I->Kp.hi, I->Kp.lo, I->VT.hi, I->VT.lo, W.bqkv, H, 1.0f / sqrtf((float)dk)};

@@ -500,6 +500,142 @@ gemm_split3_2cta_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_co
     if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc_2cta(tmem_base, 512); }
 }
 
+// ---- A-resident CTA-pair GEMM (fp16 format, K = 512) -------------------------------------------------------
+// The plain kernels re-stream the A tile for every N tile and are bound by L2->SM operand bandwidth (~8-10 TB/s
+// measured, profiles/), not by the tensor pipe.  For the wide QKV projection (N = 3072, K = 512) a CTA pair instead keeps
+// its 256 x 512 fp16 A block RESIDENT in shared memory (128 KB per CTA) and streams only W-half tiles (16 KB per k-block)
+// through a 4-deep ring while it walks a group of G consecutive N tiles: operand bytes per output tile drop from
+// 256 KB to 128 + 128/G KB per CTA.  Work item = (256-row block, group of G N-tiles); G = 3 keeps 512 items for 74 pairs
+// (6.9 waves) instead of 128 (1.7 waves).  Accumulators stay double-buffered in TMEM, epilogue as in the other kernels.
+template <int G>
+struct GemmAresCfg {
+    static constexpr int KB = 8;                                        // K = 512
+    static constexpr int T_BYTES = GEMM_BM * GEMM_BK * 2;               // 16 KB
+    static constexpr int A_BYTES = KB * T_BYTES;                        // 128 KB resident A block
+    static constexpr int W_STAGES = 4;
+    static constexpr int SMEM_BYTES = A_BYTES + W_STAGES * T_BYTES + GEMM_EPI_WARPS * 4096 + 1024 + 256;
+};
+
+template <int G, class Epi>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_ares_half_2cta_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mW /*128-row boxes*/,
+                           int M, int N, Epi epi) {
+    using Cfg = GemmAresCfg<G>;
+    constexpr int KB = Cfg::KB, T_BYTES = Cfg::T_BYTES, WS = Cfg::W_STAGES, BN = 256;
+    constexpr uint32_t IDESC = ptx::make_idesc_f16(256, BN);
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* a_smem = smem;
+    uint8_t* w_smem = smem + Cfg::A_BYTES;
+    float4* epi_tiles = reinterpret_cast<float4*>(w_smem + WS * T_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(w_smem + WS * T_BYTES + GEMM_EPI_WARPS * 4096);
+    uint64_t* a_full = bars;                          // [KB] leader: A k-block kb of the current item landed (both CTAs)
+    uint64_t* a_empty = bars + KB;                    // [KB] both:   last MMA reading A k-block kb of the item retired
+    uint64_t* w_full = bars + 2 * KB;                 // [WS] leader
+    uint64_t* w_empty = bars + 2 * KB + WS;           // [WS] both
+    uint64_t* tfull_bar = bars + 2 * KB + 2 * WS;     // [2] both
+    uint64_t* tempty_bar = bars + 2 * KB + 2 * WS + 2;// [2] leader
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * KB + 2 * WS + 4);
+
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const uint32_t rank = ptx::cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair = blockIdx.x / 2, n_pairs = gridDim.x / 2;
+    const int n_groups = (N / BN) / G;
+    const int total_items = (M / 256) * n_groups;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&mA); ptx::prefetch_tmap(&mW);
+        for (int k = 0; k < KB; ++k) { ptx::mbar_init(&a_full[k], 2); ptx::mbar_init(&a_empty[k], 1); }
+        for (int s = 0; s < WS; ++s) { ptx::mbar_init(&w_full[s], 2); ptx::mbar_init(&w_empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], 2 * GEMM_EPI_WARPS); }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) { ptx::tmem_alloc_2cta(tmem_slot, 512); ptx::tmem_relinquish_2cta(); }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {                                 // ===== TMA producer (both CTAs) =====
+            int s = 0; uint32_t ph = 0; int it = 0;
+            for (int item = pair; item < total_items; item += n_pairs, ++it) {
+                const int m0 = (item / n_groups) * 256 + (int)rank * 128;
+                const int ng = item % n_groups;
+                for (int g = 0; g < G; ++g) {
+                    const int n0 = (ng * G + g) * BN + (int)rank * 128;
+                    for (int kb = 0; kb < KB; ++kb) {
+                        if (g == 0) {                    // the item's A block streams in behind the previous item's last tile
+                            ptx::mbar_wait(&a_empty[kb], (it & 1) ^ 1);
+                            if (leader) ptx::mbar_arrive_expect_tx(&a_full[kb], 2 * T_BYTES);
+                            else        ptx::mbar_arrive_cluster(&a_full[kb], 0);
+                            ptx::tma_load_2d_2cta(a_smem + kb * T_BYTES, &mA, &a_full[kb], kb * GEMM_BK, m0);
+                        }
+                        ptx::mbar_wait(&w_empty[s], ph ^ 1);
+                        if (leader) ptx::mbar_arrive_expect_tx(&w_full[s], 2 * T_BYTES);
+                        else        ptx::mbar_arrive_cluster(&w_full[s], 0);
+                        ptx::tma_load_2d_2cta(w_smem + s * T_BYTES, &mW, &w_full[s], kb * GEMM_BK, n0);
+                        if (++s == WS) { s = 0; ph ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && leader) {                       // ===== MMA issuer (leader CTA) =====
+            int s = 0; uint32_t ph = 0; int it = 0, tc = 0;
+            const uint32_t a_addr = ptx::smem_u32(a_smem), w_addr = ptx::smem_u32(w_smem);
+            for (int item = pair; item < total_items; item += n_pairs, ++it) {
+                for (int g = 0; g < G; ++g, ++tc) {
+                    const int a = tc & 1;
+                    ptx::mbar_wait(&tempty_bar[a], ((tc >> 1) & 1) ^ 1);
+                    ptx::tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + a * BN;
+                    for (int kb = 0; kb < KB; ++kb) {
+                        if (g == 0) ptx::mbar_wait(&a_full[kb], it & 1);
+                        ptx::mbar_wait(&w_full[s], ph);
+                        ptx::tc_fence_after();
+                        const uint64_t dA = ptx::make_smem_desc_sw128(a_addr + kb * T_BYTES);
+                        const uint64_t dW = ptx::make_smem_desc_sw128(w_addr + s * T_BYTES);
+#pragma unroll
+                        for (int kk = 0; kk < GEMM_BK / 16; ++kk)
+                            ptx::umma_f16_2cta(d_tmem, dA + (uint64_t)(kk * 2), dW + (uint64_t)(kk * 2), IDESC, (kb | kk) != 0);
+                        ptx::umma_commit_2cta(&w_empty[s]);
+                        if (g == G - 1) ptx::umma_commit_2cta(&a_empty[kb]);   // last reader of A k-block kb in this item
+                        if (++s == WS) { s = 0; ph ^= 1; }
+                    }
+                    ptx::umma_commit_2cta(&tfull_bar[a]);
+                }
+            }
+        }
+    } else {                                             // ===== epilogue warps 2..9 (both CTAs) =====
+        const int quarter = warp & 3;
+        int tc = 0;
+        for (int item = pair; item < total_items; item += n_pairs) {
+            const int m0 = (item / n_groups) * 256 + (int)rank * 128;
+            const int ng = item % n_groups;
+            for (int g = 0; g < G; ++g, ++tc) {
+                const int a = tc & 1;
+                const uint32_t aph = (tc >> 1) & 1;
+                const int n0 = (ng * G + g) * BN;
+                const int chalf = (warp - 2) >> 2;
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * BN + chalf * (BN / 2);
+                float4* etile = epi_tiles + (warp - 2) * 256;
+                epilogue_drain<BN / 2>(epi, etile, taddr, lane, m0 + quarter * 32, n0 + chalf * (BN / 2),
+                                       [&]() { ptx::mbar_wait(&tfull_bar[a], aph); ptx::tc_fence_after(); });
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive_cluster(&tempty_bar[a], 0);
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync();
+    if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc_2cta(tmem_base, 512); }
+}
+
 // ---- full-row fp16 GEMM with fused residual + bias + LayerNorm ------------------------------------------
 // The post-LN sub-layers (attention fc, FFN w_2) are memory-bound in the fp16 format (arithmetic intensity ~100 FLOP/B
 // with separate residual / pre-LN / LayerNorm passes).  This kernel computes a whole 128 x 512 row block per CTA:
