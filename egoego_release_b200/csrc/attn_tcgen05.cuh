@@ -8,7 +8,8 @@
 //   Q, K : [(window*H + head)*128 + token, 256]      (Q pre-scaled by 1/sqrt(d_k))
 //   V^T  : [(window*H + head)*256 + dim,  128 tokens]
 // Persistent CTAs (one per SM, 192 threads) loop over (window, head) items:
-//   warp 0    TMA producer, ring of 2 x 64 KB stages: 4 Q/K k-blocks then 2 V^T k-blocks per item
+//   warp 0    TMA producer, 128 KB ring (2 x 64 KB stages in split, 4 x 32 KB in fp16 format): 4 Q/K k-blocks then
+//             2 V^T k-blocks per item
 //   warp 1    MMA issuer (S of item i+1 is issued right after P V of item i, overlapping its epilogue)
 //   warps 2-9 softmax (TMEM -> registers -> P planes into swizzled smem) and O epilogue (TMEM -> operand planes);
 //             two warps share each TMEM lane quarter and split the key / output columns, exchanging the row
@@ -22,11 +23,10 @@
 
 namespace egoego {
 
-constexpr int ATT_STAGE_BYTES = 65536;
-constexpr int ATT_STAGES = 2;
+constexpr int ATT_RING_BYTES = 131072;                   // operand ring: 2 x 64 KB stages (split) or 4 x 32 KB (fp16)
 constexpr int ATT_P_BYTES = 2 * 2 * 128 * 128;          // hi/lo x 2 key blocks x [128 rows x 128 B]
 constexpr int ATT_PART_BYTES = 2 * 2 * 128 * 4;          // row max / row sum partials of the two column halves
-constexpr int ATT_SMEM_BYTES = ATT_STAGES * ATT_STAGE_BYTES + ATT_P_BYTES + ATT_PART_BYTES + 1024 + 256;
+constexpr int ATT_SMEM_BYTES = ATT_RING_BYTES + ATT_P_BYTES + ATT_PART_BYTES + 1024 + 256;
 constexpr int ATT_THREADS = 64 + 256;                    // TMA warp, MMA warp, 8 softmax/epilogue warps
 
 template <int FMT>
@@ -50,20 +50,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_consta
     constexpr uint32_t IDESC_S = (FMT == FMT_SPLIT) ? ptx::make_idesc_bf16(128, 128) : ptx::make_idesc_f16(128, 128);
     constexpr uint32_t IDESC_O = (FMT == FMT_SPLIT) ? ptx::make_idesc_bf16(128, 256) : ptx::make_idesc_f16(128, 256);
     constexpr uint32_t QK_BYTES = NP * 2 * 16384, V_BYTES = NP * 32768;
+    constexpr int ATT_STAGE_BYTES = NP * 32768;            // one k-block of Q+K planes, or of V planes
+    constexpr int ATT_STAGES = ATT_RING_BYTES / ATT_STAGE_BYTES;
+    constexpr int OFF_QL = 16384, OFF_KH = NP * 16384, OFF_KL = NP * 16384 + 16384, OFF_VL = 32768;
     constexpr uint32_t TM_S = 0, TM_O = 128;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* p_smem = smem + ATT_STAGES * ATT_STAGE_BYTES;           // P_hi [2][128][128B], P_lo [2][128][128B]
+    uint8_t* p_smem = smem + ATT_RING_BYTES;           // P_hi [2][128][128B], P_lo [2][128][128B]
     float* part = reinterpret_cast<float*>(p_smem + ATT_P_BYTES);     // [max|sum][half][128 rows]
     uint64_t* bars = reinterpret_cast<uint64_t*>(p_smem + ATT_P_BYTES + ATT_PART_BYTES);
-    uint64_t* full_bar = bars;          // [2]
-    uint64_t* empty_bar = bars + 2;     // [2]
-    uint64_t* s_full = bars + 4;        // S accumulator ready (MMA -> softmax)
-    uint64_t* p_ready = bars + 5;       // P written to smem and S drained (softmax -> MMA), 128 arrivals
-    uint64_t* o_full = bars + 6;        // O accumulator ready (MMA -> epilogue)
-    uint64_t* o_free = bars + 7;        // O drained (epilogue -> MMA), 128 arrivals
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    uint64_t* full_bar = bars;          // [ATT_STAGES <= 4]
+    uint64_t* empty_bar = bars + 4;     // [ATT_STAGES <= 4]
+    uint64_t* s_full = bars + 8;        // S accumulator ready (MMA -> softmax)
+    uint64_t* p_ready = bars + 9;       // P written to smem and S drained (softmax -> MMA), 256 arrivals
+    uint64_t* o_full = bars + 10;       // O accumulator ready (MMA -> epilogue)
+    uint64_t* o_free = bars + 11;       // O drained (epilogue -> MMA), 256 arrivals
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
 
@@ -89,9 +92,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_consta
                     uint8_t* st = smem + s * ATT_STAGE_BYTES;
                     ptx::mbar_arrive_expect_tx(&full_bar[s], QK_BYTES);
                     ptx::tma_load_2d(st, &mQh, &full_bar[s], kb * 64, item * 128);
-                    if (NP == 2) ptx::tma_load_2d(st + 16384, &mQl, &full_bar[s], kb * 64, item * 128);
-                    ptx::tma_load_2d(st + 32768, &mKh, &full_bar[s], kb * 64, item * 128);
-                    if (NP == 2) ptx::tma_load_2d(st + 49152, &mKl, &full_bar[s], kb * 64, item * 128);
+                    if (NP == 2) ptx::tma_load_2d(st + OFF_QL, &mQl, &full_bar[s], kb * 64, item * 128);
+                    ptx::tma_load_2d(st + OFF_KH, &mKh, &full_bar[s], kb * 64, item * 128);
+                    if (NP == 2) ptx::tma_load_2d(st + OFF_KL, &mKl, &full_bar[s], kb * 64, item * 128);
                     if (++s == ATT_STAGES) { s = 0; ph ^= 1; }
                 }
                 for (int kb = 0; kb < 2; ++kb) {           // V^T k-blocks of 64 keys: Vh Vl (32 KB each)
@@ -99,7 +102,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_consta
                     uint8_t* st = smem + s * ATT_STAGE_BYTES;
                     ptx::mbar_arrive_expect_tx(&full_bar[s], V_BYTES);
                     ptx::tma_load_2d(st, &mVh, &full_bar[s], kb * 64, item * 256);
-                    if (NP == 2) ptx::tma_load_2d(st + 32768, &mVl, &full_bar[s], kb * 64, item * 256);
+                    if (NP == 2) ptx::tma_load_2d(st + OFF_VL, &mVl, &full_bar[s], kb * 64, item * 256);
                     if (++s == ATT_STAGES) { s = 0; ph ^= 1; }
                 }
             }
@@ -113,8 +116,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_consta
                     ptx::mbar_wait(&full_bar[s], ph);
                     ptx::tc_fence_after();
                     const uint32_t st = ptx::smem_u32(smem + s * ATT_STAGE_BYTES);
-                    const uint64_t dQh = ptx::make_smem_desc_sw128(st), dQl = ptx::make_smem_desc_sw128(st + 16384);
-                    const uint64_t dKh = ptx::make_smem_desc_sw128(st + 32768), dKl = ptx::make_smem_desc_sw128(st + 49152);
+                    const uint64_t dQh = ptx::make_smem_desc_sw128(st), dQl = ptx::make_smem_desc_sw128(st + OFF_QL);
+                    const uint64_t dKh = ptx::make_smem_desc_sw128(st + OFF_KH), dKl = ptx::make_smem_desc_sw128(st + OFF_KL);
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) {
                         const uint64_t adv = (uint64_t)(kk * 2);
@@ -140,7 +143,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_consta
                     ptx::mbar_wait(&full_bar[s], ph);
                     ptx::tc_fence_after();
                     const uint32_t st = ptx::smem_u32(smem + s * ATT_STAGE_BYTES);
-                    const uint64_t dVh = ptx::make_smem_desc_sw128(st), dVl = ptx::make_smem_desc_sw128(st + 32768);
+                    const uint64_t dVh = ptx::make_smem_desc_sw128(st), dVl = ptx::make_smem_desc_sw128(st + OFF_VL);
                     const uint64_t dPh = ptx::make_smem_desc_sw128(p_hi + kb * 16384), dPl = ptx::make_smem_desc_sw128(p_lo + kb * 16384);
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) {

@@ -194,7 +194,7 @@ static int launch_gemm_ares(TcImpl* I, const Plane& A, const Plane& W, int M, in
 
 static bool use_ares() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("EGOEGO_QKV_ARES"); v = (e && e[0] == '0') ? 0 : 1; }
+    if (v < 0) { const char* e = getenv("EGOEGO_QKV_ARES"); v = (e && e[0] == '1') ? 1 : 0; }   // opt-in: measured slower (profiles/r1k)
     return v == 1;
 }
 
