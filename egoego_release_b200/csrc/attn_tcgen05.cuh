@@ -56,7 +56,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_consta
     constexpr uint32_t TM_S = 0, TM_O = 128;
 
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment for the 128B-swizzle tiles, computed as an OFFSET on the __shared__ array so the compiler keeps
+    // the shared address space (integer round-trips turn every access into a generic LD/ST).
+    uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* p_smem = smem + ATT_RING_BYTES;           // P_hi [2][128][128B], P_lo [2][128][128B]
     float* part = reinterpret_cast<float*>(p_smem + ATT_P_BYTES);     // [max|sum][half][128 rows]
     uint64_t* bars = reinterpret_cast<uint64_t*>(p_smem + ATT_P_BYTES + ATT_PART_BYTES);

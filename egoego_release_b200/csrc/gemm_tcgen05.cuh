@@ -278,7 +278,9 @@ gemm_split3_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constan
     constexpr int ACC_STAGES = 512 / BN >= 2 ? 2 : 1;
 
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment for the 128B-swizzle tiles, computed as an OFFSET on the __shared__ array so the compiler keeps
+    // the shared address space (integer round-trips turn every access into a generic LD/ST).
+    uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
     float4* epi_tiles = reinterpret_cast<float4*>(smem + STAGES * Cfg::STAGE_BYTES);          // 4 x 4 KB
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + GEMM_EPI_WARPS * 4096);
     uint64_t* full_bar = bars;                         // [STAGES]
@@ -399,7 +401,9 @@ gemm_split3_2cta_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_co
     constexpr int T_BYTES = GEMM_BM * GEMM_BK * 2;                   // 16 KB tile
     constexpr uint32_t IDESC = (FMT == FMT_SPLIT) ? ptx::make_idesc_bf16(256, BN) : ptx::make_idesc_f16(256, BN);
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment for the 128B-swizzle tiles, computed as an OFFSET on the __shared__ array so the compiler keeps
+    // the shared address space (integer round-trips turn every access into a generic LD/ST).
+    uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
     float4* epi_tiles = reinterpret_cast<float4*>(smem + GEMM2_STAGES * GEMM2_STAGE_BYTES);   // 4 x 4 KB
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GEMM2_STAGES * GEMM2_STAGE_BYTES + GEMM_EPI_WARPS * 4096);
     uint64_t* full_bar = bars;                          // [S]  (used on the leader)
@@ -524,7 +528,9 @@ gemm_ares_half_2cta_kernel(const __grid_constant__ CUtensorMap mA, const __grid_
     constexpr int KB = Cfg::KB, T_BYTES = Cfg::T_BYTES, WS = Cfg::W_STAGES, BN = 256;
     constexpr uint32_t IDESC = ptx::make_idesc_f16(256, BN);
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment for the 128B-swizzle tiles, computed as an OFFSET on the __shared__ array so the compiler keeps
+    // the shared address space (integer round-trips turn every access into a generic LD/ST).
+    uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* a_smem = smem;
     uint8_t* w_smem = smem + Cfg::A_BYTES;
     float4* epi_tiles = reinterpret_cast<float4*>(w_smem + WS * T_BYTES);
@@ -761,7 +767,9 @@ gemm_ln_half_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constan
     constexpr int STAGES = GemmLnCfg::STAGES, A_BYTES = GemmLnCfg::A_BYTES, STAGE_BYTES = GemmLnCfg::STAGE_BYTES;
     constexpr uint32_t IDESC = ptx::make_idesc_f16(GEMM_BM, 256);
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment for the 128B-swizzle tiles, computed as an OFFSET on the __shared__ array so the compiler keeps
+    // the shared address space (integer round-trips turn every access into a generic LD/ST).
+    uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
     float4* epi_tiles = reinterpret_cast<float4*>(smem + STAGES * STAGE_BYTES);
     float* part = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + GEMM_EPI_WARPS * 4096);     // [2 passes][2 halves][128]
     float* vec = part + 2 * 2 * 128;                                                                 // bias | gamma | beta
@@ -860,7 +868,9 @@ gemm_ln_half_2cta_kernel(const __grid_constant__ CUtensorMap mA, const __grid_co
     constexpr int STAGES = GemmLn2Cfg::STAGES, T_BYTES = GemmLn2Cfg::T_BYTES, STAGE_BYTES = GemmLn2Cfg::STAGE_BYTES;
     constexpr uint32_t IDESC = ptx::make_idesc_f16(256, 256);
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment for the 128B-swizzle tiles, computed as an OFFSET on the __shared__ array so the compiler keeps
+    // the shared address space (integer round-trips turn every access into a generic LD/ST).
+    uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
     float4* epi_tiles = reinterpret_cast<float4*>(smem + STAGES * STAGE_BYTES);
     float* part = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + GEMM_EPI_WARPS * 4096);
     float* vec = part + 2 * 2 * 128;                                                                 // bias | gamma | beta
