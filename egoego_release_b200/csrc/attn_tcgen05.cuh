@@ -70,7 +70,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_consta
     uint64_t* o_free = bars + 11;       // O drained (epilogue -> MMA), 256 arrivals
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
-    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    // Role index, not hardware warp id: the SM sub-partition arbiter favours HIGHER warp ids, so the TMA producer (role 0)
+    // and the MMA issuer (role 1) live in the two highest hardware warps and are never starved of issue slots by the
+    // epilogue warps (roles 2..9 = hardware warps 0..7, whose id % 4 selects their TMEM lane quarter).
+    const int lane = threadIdx.x % 32;
+    const int warp = (threadIdx.x / 32 + 2) % (ATT_THREADS / 32);
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&mQh); ptx::prefetch_tmap(&mQl); ptx::prefetch_tmap(&mKh);
@@ -164,7 +168,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_consta
             }
         }
     } else {                                               // ===== softmax + epilogue warps 2..9 =====
-        const int quarter = warp & 3, hf = (warp - 2) >> 2;  // TMEM lane quarter, column half
+        const int quarter = (warp - 2) & 3, hf = (warp - 2) >> 2;  // TMEM lane quarter, column half
         const int r = quarter * 32 + lane;                 // query row = TMEM lane
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
         int it = 0;
