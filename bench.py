@@ -22,7 +22,22 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLOP_PER_WINDOW_CALL = 2850.718e6      # algorithmic FLOPs per window per denoiser call (L=121)
-QKV_FLOP_PER_WINDOW_CALL = 380.633e6   # dominant kernel: fused QKV projection, per layer
+# Per-kernel algorithmic work per window per launch (L = 121 real tokens, fp16 operand format bytes;
+# weights are L2-resident and not counted).  DESIGN.md 5 carries the same table.
+_ROW = 121 * 512 * 2                   # one fp16 activation row block [121, 512]
+KERNEL_FLOPS = {"start": 24.330e6, "qkv": 380.633e6, "attention": 59.970e6, "fc_ln": 126.878e6, "w1": 63.439e6,
+                "w2_ln": 63.439e6, "out": 24.330e6, "ddpm_update": 0.0}
+KERNEL_BYTES = {"start": 120 * 198 * 2 + 121 * 512 * 4 + _ROW, "qkv": _ROW + 6 * _ROW, "attention": 6 * _ROW + 2 * _ROW,
+                "fc_ln": 2 * _ROW + _ROW + _ROW, "w1": 2 * _ROW, "w2_ln": 3 * _ROW, "out": _ROW + 120 * 198 * 4,
+                "ddpm_update": 3 * 120 * 198 * 4 + 120 * 198 * 2}
+KERNEL_LAUNCHES = {"start": 1, "qkv": 4, "attention": 4, "fc_ln": 4, "w1": 4, "w2_ln": 4, "out": 1, "ddpm_update": 1}
+KERNEL_NAMES = {"start": "gemm_split3_2cta_kernel<TcEpiStart> (x half of start_conv)",
+                "qkv": "gemm_split3_2cta_kernel<TcEpiQKVPlanes> (fused QKV projection)",
+                "attention": "attention_tc_kernel (QK^T, softmax, PV)",
+                "fc_ln": "gemm_ln_half_c4_kernel (attention fc + residual + LayerNorm)",
+                "w1": "gemm_split3_2cta_kernel<TcEpiBiasReluSplit> (FFN w_1 + ReLU)",
+                "w2_ln": "gemm_ln_half_c4_kernel (FFN w_2 + residual + LayerNorm)",
+                "out": "gemm_split3_2cta_kernel<TcEpiOut> (linear_out)", "ddpm_update": "ddpm_update_kernel"}
 
 
 def parse():
@@ -135,6 +150,54 @@ def cpu_baseline(B_cpu, T, N, budget_s):
     return {"value": B_cpu / (per_step * N), "unit": "windows/s", "cores": cores_used, "host_cores": cores, "kind": "port",
             "sample": f"oracle p_sample, B={B_cpu}, T={T}, {n} of {N} steps timed ({el:.1f} s), scaled linearly to {N} steps",
             "ms_per_denoiser_step": per_step * 1e3}
+
+
+def denoiser_latency(m, dev, T, iters=20):
+    """BASELINE metric 2: device time of one denoiser forward (egoego_denoiser_forward, 3-term split format) in us."""
+    import torch
+    out = {}
+    for B in (1, m._max_batch):
+        x = torch.randn(B, T, 396, device=dev)
+        t = torch.full((B,), 500, dtype=torch.long, device=dev)
+        for _ in range(3):
+            m.denoise_fn(x, t)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            m.denoise_fn(x, t)
+        e1.record()
+        torch.cuda.synchronize()
+        out[f"B{B}"] = e0.elapsed_time(e1) / iters * 1e3
+    out["note"] = "per call incl. staging of x/x_cond (egoego_denoiser_forward, bf16x3-split), CUDA events, eager launches"
+    return out
+
+
+def parity_vs_reference(m, dev, N):
+    """BASELINE metric 3: MPJPE / max-abs joint error (mm) of the product path against the committed golden output of the
+    UNMODIFIED reference (tests/golden/sample.npz, produced by oracle/gen_golden.py) on identical conditioning and noise
+    tape -- B=1, T=120, the bench's own 1000-step model and precision policy.  The oracle is only the checker here."""
+    import numpy as np
+    import torch
+    from oracle import egoego_oracle as O
+    from oracle.gen_golden import Tape, synth_x_start
+    key = f"n{N}_b1_seed22"
+    g = np.load(os.path.join(ROOT, "tests", "golden", "sample.npz"))
+    if key not in g.files:
+        return {"unavailable": f"no golden for {key}"}
+    xs = synth_x_start(100 + N, 1, 120)
+    cm = O.prep_head_condition_mask(xs.shape)
+    tp = Tape(22)
+    tape = torch.stack([tp.draw(xs.shape) for _ in range(N + 2)])
+    m.set_noise_tape(tape.to(dev))
+    y = m.sample(xs.to(dev), cm.to(dev)).cpu()
+    m.set_noise_tape(None)
+    ref = torch.from_numpy(g[key])
+    ds = O.MotionDataStub()
+    jy, jr = O.joints_from_model_output(ds, y), O.joints_from_model_output(ds, ref)
+    return {"mpjpe_mm": O.mpjpe_mm(jy, jr), "joint_max_abs_mm": float((jy - jr).abs().max()) * 1e3,
+            "raw_max_abs": float((y - ref).abs().max()), "tolerance_mm": 1.0,
+            "reference": "unmodified reference CPU fp32 (golden tests/golden/sample.npz), B=1 T=120 N=%d, identical noise tape" % N}
 
 
 def torch_gpu_baseline(dev, B, T, N, n_steps=12):
@@ -261,19 +324,14 @@ def main():
         return
     pk, pk_src = peaks()
     eng = a.engine or E.diffusion.DEFAULT_ENGINE
-    # dominant kernel (fused QKV projection GEMM) timed live with CUDA events on its launch stream, both operand formats
-    kern = {}
     K_prec = N
-    if eng == "tcgen05":
-        K_prec = m.precise_last_steps()
-        for tag, half in (("bf16x3_split", False), ("fp16_single", True)):
-            kms = m.time_dominant_kernel(B, half, iters=20)
-            kern[tag] = {"ms_per_launch": kms, "algorithmic_tflops": QKV_FLOP_PER_WINDOW_CALL * B / (kms * 1e-3) / 1e12}
     ms_per_step = ms / a.steps
     value = world * B / (ms_per_step / 1e3)
     e2e = world * B / (ms_h / a.steps / 1e3)
     path_tflops = value / world * N * FLOP_PER_WINDOW_CALL / 1e12          # per GPU
     peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+    if eng == "tcgen05":
+        K_prec = m.precise_last_steps()
     line = {
         "metric": "motion-windows/sec (T=120, 1000-step)", "value": value, "unit": "windows/s", "n_gpus": world,
         "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -286,22 +344,45 @@ def main():
         "path_roofline": {"bound": "tensor", "achieved": path_tflops, "peak": peak, "unit": "TFLOP/s", "frac": path_tflops / peak,
                           "scope": "whole sampling path: algorithmic 2.8507 TFLOP per 1000-step window / wall time, per GPU"},
     }
-    if kern:
-        dom = "fp16_single" if K_prec < N else "bf16x3_split"       # format of the steps that take most of the time
-        ach = kern[dom]["algorithmic_tflops"]
-        pk_burst = pk["bf16_tflops"]
+    if eng == "tcgen05":
+        # every kernel of the step timed live, in isolation (20 back-to-back launches, CUDA events on the launch stream),
+        # in the format of the steps that take most of the time; the DOMINANT kernel = largest launches x time share
+        dom_fmt = "fp16_single" if K_prec < N else "bf16x3_split"
+        half = dom_fmt == "fp16_single"
+        pk_burst, hbm = pk["bf16_tflops"], pk["hbm_gbs"]
+        kernels = {}
+        for name in m.KERNELS:
+            kms = m.time_kernel(name, B, T, half, iters=20)
+            fl, by, cnt = KERNEL_FLOPS[name] * B, KERNEL_BYTES[name] * B, KERNEL_LAUNCHES[name]
+            t_tensor, t_hbm = fl / (pk_burst * 1e12), by / (hbm * 1e9)
+            bound = "tensor" if t_tensor >= t_hbm else "hbm"
+            ach = fl / (kms * 1e-3) / 1e12 if bound == "tensor" else by / (kms * 1e-3) / 1e9
+            kernels[name] = {"launches_per_step": cnt, "ms_per_launch": kms, "bound": bound, "achieved": ach,
+                             "peak": pk_burst if bound == "tensor" else hbm, "unit": "TFLOP/s" if bound == "tensor" else "GB/s",
+                             "frac": ach / (pk_burst if bound == "tensor" else hbm),
+                             "algorithmic_flops_per_launch": fl, "algorithmic_bytes_per_launch": by}
+        tot = sum(k["launches_per_step"] * k["ms_per_launch"] for k in kernels.values())
+        for k in kernels.values():
+            k["share_of_step"] = k["launches_per_step"] * k["ms_per_launch"] / tot
+        dom = max(kernels, key=lambda n: kernels[n]["share_of_step"])
         traffic = None
         tp = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")   # dram bytes/launch from the committed ncu --set full capture
         if os.path.exists(tp):
             tj = json.load(open(tp))
-            if tj.get("format") == dom and tj.get("windows") == B:
+            if tj.get("stage") == dom and tj.get("format") == dom_fmt and tj.get("windows") == B:
                 traffic = tj.get("dram_bytes_read", 0) + tj.get("dram_bytes_write", 0)
-        line["roofline"] = {"bound": "tensor", "achieved": ach, "peak": pk_burst, "unit": "TFLOP/s", "frac": ach / pk_burst,
-                            "traffic": traffic, "kernel": f"gemm_split3(_2cta)_kernel<{dom}, TcEpiQKVPlanes> (fused QKV projection)",
-                            "algorithmic_flops_per_launch": QKV_FLOP_PER_WINDOW_CALL * B,
-                            "ms_per_launch": kern[dom]["ms_per_launch"], "issued_over_algorithmic": 1.0 if dom == "fp16_single" else 3.0,
-                            "peak_source": pk_src + ", burst bf16 (kernel timed alone, 20 back-to-back launches, CUDA events)",
-                            "other_format": {k: v for k, v in kern.items() if k != dom}}
+        d = kernels[dom]
+        line["roofline"] = {"bound": d["bound"], "achieved": d["achieved"], "peak": d["peak"], "unit": d["unit"], "frac": d["frac"],
+                            "traffic": traffic, "kernel": f"{KERNEL_NAMES[dom]} [{dom_fmt}]", "stage": dom,
+                            "share_of_step": d["share_of_step"], "ms_per_launch": d["ms_per_launch"],
+                            "algorithmic_flops_per_launch": d["algorithmic_flops_per_launch"],
+                            "algorithmic_bytes_per_launch": d["algorithmic_bytes_per_launch"],
+                            "peak_source": pk_src + ", burst figures (kernel timed alone, 20 back-to-back launches, CUDA events)"}
+        line["kernels"] = kernels
+        line["kernels_sum_ms_per_diffusion_step"] = tot
+        # the other BASELINE metrics: denoiser forward latency (one call, split format, B=1 and B=256) ...
+        line["denoiser_fwd_us"] = denoiser_latency(m, dev, T)
+        line["parity_vs_reference"] = parity_vs_reference(m, dev, N)
     else:
         line["roofline"] = dict(line["path_roofline"], traffic=None, peak_source=pk_src)
     line["cpu_baseline"] = cpu_baseline(32, T, N, a.cpu_seconds)

@@ -10,7 +10,7 @@ EXPORTS = [
     "egoego_last_error", "egoego_version", "egoego_create", "egoego_destroy", "egoego_set_tensor",
     "egoego_make_cosine_schedule", "egoego_commit_weights", "egoego_denoiser_forward", "egoego_p_sample_step",
     "egoego_sample", "egoego_sample_host", "egoego_set_skeleton", "egoego_postprocess", "egoego_fk_smpl",
-    "egoego_canonicalize_head", "egoego_tail_condition", "egoego_launch_count", "egoego_selftest_gemm", "egoego_time_dominant_kernel",
+    "egoego_canonicalize_head", "egoego_tail_condition", "egoego_launch_count", "egoego_selftest_gemm", "egoego_time_dominant_kernel", "egoego_time_kernel",
     "egoego_precise_last_steps",
 ]
 
@@ -62,6 +62,7 @@ def lib():
     L.egoego_canonicalize_head.argtypes = [vp, vp, vp, i64, i32, i32, vp, vp, vp]
     L.egoego_selftest_gemm.argtypes = [i32, i32, i32, i32, u64, i32, i32, vp, vp, vp]
     L.egoego_time_dominant_kernel.argtypes = [vp, i32, i32, i32, vp, vp]
+    L.egoego_time_kernel.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp]
     L.egoego_precise_last_steps.argtypes = [vp]
     L.egoego_tail_condition.argtypes = [vp, vp, vp, i32, i32, vp, vp]
     L.egoego_launch_count.argtypes = [vp]

@@ -156,6 +156,7 @@ static void fill_ddpm(egoego_ctx* c, DdpmArgs& a, const float* x, float* x_out, 
     a.sqrt_recip = c->sqrt_recip.as<float>(); a.sqrt_recipm1 = c->sqrt_recipm1.as<float>();
     a.objective = c->cfg.objective; a.clip = clip; a.inpaint = inpaint; a.inpaint_len = inpaint_len;
     a.stage_f32 = nullptr; a.stage_ld = 0; a.stage_hi = nullptr; a.stage_lo = nullptr; a.stage_ld16 = 0; a.stage_h16 = nullptr;
+    a.stage_mode = 2;
     if (stage_next) {
         if (c->cfg.engine == EGOEGO_ENGINE_SIMT) { a.stage_f32 = c->Ain.as<float>(); a.stage_ld = c->kin_pad; }
         else c->tc->stage_targets(&a.stage_hi, &a.stage_lo, &a.stage_h16, &a.stage_ld16);
@@ -499,7 +500,10 @@ static int sample_chunk(egoego_ctx* c, const float* x_start, const float* cond_m
     DdpmArgs a;
     fill_ddpm(c, a, xc, xc, ts, ns, 1, inpaint, inpaint_len, Bc, T, true);
 
+    // A step stages the next step's start_conv operand only in its OWN format; at the fp16 -> split switch the split
+    // planes are produced once from x_cur (restage) before the first split step.
     auto one_step = [&](cudaStream_t st, int fmt) -> int {
+        a.stage_mode = (c->cfg.engine == EGOEGO_ENGINE_SIMT) ? 2 : (fmt ? 1 : 0);
         if (run_denoiser(c, Bc, T, ts, nullptr, st, fmt)) return 1;
         ddpm_update_kernel<<<grid1d(quads, 256), 256, 0, st>>>(a);
         advance_step_kernel<<<1, 32, 0, st>>>(d_step);
@@ -531,11 +535,15 @@ static int sample_chunk(egoego_ctx* c, const float* x_start, const float* cond_m
         c->graph_B = Bc; c->graph_T = T; memcpy(c->graph_key, key, sizeof(key));
         for (int i = 0; i < N; ++i) {
             const int fmt = fmt_of_step(i);
+            if (i > 0 && fmt != fmt_of_step(i - 1) && stage_input(c, xc, D, 0, false, Bc, T, s)) return 1;
             EG_CUDA(cudaGraphLaunch(c->step_graph[fmt], s));
             c->launches += (c->cfg.engine == EGOEGO_ENGINE_SIMT ? (2 + 7 * c->NL) : c->tc->launches_per_denoiser(fmt)) + 2;
         }
     } else {
-        for (int i = 0; i < N; ++i) if (one_step(s, fmt_of_step(i))) return 1;
+        for (int i = 0; i < N; ++i) {
+            if (i > 0 && fmt_of_step(i) != fmt_of_step(i - 1) && stage_input(c, xc, D, 0, false, Bc, T, s)) return 1;
+            if (one_step(s, fmt_of_step(i))) return 1;
+        }
     }
     EG_CUDA(cudaMemcpyAsync(out, xc, (size_t)Bc * T * D * 4, cudaMemcpyDeviceToDevice, s));
     return 0;
@@ -667,11 +675,41 @@ int egoego_tail_condition(egoego_handle c, const float* gquat, const float* gjpo
 
 int64_t egoego_launch_count(egoego_handle c) { return c ? c->launches : -1; }
 
-int egoego_time_dominant_kernel(egoego_handle c, int B, int half_fmt, int iters, float* ms_per_launch, void* stream_v) {
+int egoego_time_kernel(egoego_handle c, int B, int T, int which, int half_fmt, int iters, float* ms_per_launch, void* stream_v) {
     EG_CHECK(c && ms_per_launch, "null argument");
     EG_CHECK(c->committed && c->cfg.engine == EGOEGO_ENGINE_TCGEN05, "needs a committed tensor-core engine");
+    EG_CHECK(B >= 1 && B <= c->cfg.max_batch && T >= 1 && T <= c->Tmax && iters >= 1, "bad arguments");
+    EG_CHECK(which >= 0 && which <= EGOEGO_KERNEL_DDPM_UPDATE, "unknown kernel id");
     EG_CUDA(cudaSetDevice(c->cfg.device));
-    return c->tc->time_qkv(B, half_fmt ? 1 : 0, iters, (cudaStream_t)stream_v, ms_per_launch);
+    cudaStream_t s = (cudaStream_t)stream_v;
+    if (which < EGOEGO_KERNEL_DDPM_UPDATE)
+        return c->tc->time_stage(B, T, which, half_fmt ? 1 : 0, iters, c->model_out.as<float>(), s, ms_per_launch);
+    // DDPM update (clamp + posterior mean + Philox noise + staging of the next step's A operand), t fixed at N/2
+    TSrc ts{nullptr, nullptr, c->N / 2};
+    NoiseSrc ns{};
+    ns.tape = nullptr; ns.seed = 1; ns.window_offset = 0; ns.draw_static = 2;
+    DdpmArgs a;
+    fill_ddpm(c, a, c->x_cur.as<float>(), c->x_cur.as<float>(), ts, ns, 1, nullptr, 0, B, T, true);
+    a.stage_mode = half_fmt ? 1 : 0;
+    const long long quads = ((long long)T * c->D + 3) / 4 * B;
+    cudaEvent_t e0, e1;
+    EG_CUDA(cudaEventCreate(&e0)); EG_CUDA(cudaEventCreate(&e1));
+    for (int i = 0; i < 3; ++i) ddpm_update_kernel<<<grid1d(quads, 256), 256, 0, s>>>(a);
+    EG_CUDA(cudaEventRecord(e0, s));
+    for (int i = 0; i < iters; ++i) ddpm_update_kernel<<<grid1d(quads, 256), 256, 0, s>>>(a);
+    EG_CUDA(cudaEventRecord(e1, s));
+    EG_CUDA(cudaEventSynchronize(e1));
+    EG_CUDA(cudaGetLastError());
+    float t = 0.f;
+    EG_CUDA(cudaEventElapsedTime(&t, e0, e1));
+    *ms_per_launch = t / iters;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return 0;
+}
+
+int egoego_time_dominant_kernel(egoego_handle c, int B, int half_fmt, int iters, float* ms_per_launch, void* stream_v) {
+    EG_CHECK(c, "null argument");
+    return egoego_time_kernel(c, B, c->Tmax, EGOEGO_KERNEL_QKV, half_fmt, iters, ms_per_launch, stream_v);
 }
 
 int egoego_precise_last_steps(egoego_handle c) { return c ? c->precise_last : -1; }

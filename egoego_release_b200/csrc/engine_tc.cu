@@ -108,6 +108,7 @@ struct TcImpl {
     Plane Qp, Kp, VT;                           // attention operand planes (see attn_tcgen05.cuh)
     bool fuse_ln = true;                        // EGOEGO_FUSE_LN=0 keeps GEMM + LayerNorm separate in the fp16 format too
     bool attn_tc = true;                        // EGOEGO_ATTN=simt selects the fp32 CUDA-core attention (bisecting)
+    int ln4_clusters = 0;                       // co-resident clusters of 4 for gemm_ln_half_c4_kernel (0 = use the full-row pair kernel)
     float *base = nullptr, *H = nullptr, *Y = nullptr, *QKV = nullptr;
     ~TcImpl() {
         for (Plane* p : {&Wx, &Wc, &Wout, &X, &C, &Hs, &O, &F, &Qp, &Kp, &VT}) p->release();
@@ -251,6 +252,23 @@ int TcEngine::init(const TcWeights& w, cudaStream_t) {
         I->fuse_ln = !(fl && fl[0] == '0');
         EG_CUDA(cudaFuncSetAttribute(gemm_ln_half_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmLnCfg::SMEM_BYTES));
         EG_CUDA(cudaFuncSetAttribute(gemm_ln_half_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmLn2Cfg::SMEM_BYTES));
+        EG_CUDA(cudaFuncSetAttribute(gemm_ln_half_c4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmLn4Cfg::SMEM_BYTES));
+        // column-split cluster-of-4 kernel (default; EGOEGO_LN=2cta keeps the full-row pair kernel): launch exactly as many
+        // clusters as can be co-resident (GPC boundaries may leave a few SMs without a complete cluster)
+        const char* lm = getenv("EGOEGO_LN");
+        if (!(lm && strcmp(lm, "2cta") == 0) && use_2cta()) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((I->sms / 4) * 4); cfg.blockDim = dim3(GEMM_LN4_THREADS); cfg.dynamicSmemBytes = GemmLn4Cfg::SMEM_BYTES;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            int nc = 0;
+            if (cudaOccupancyMaxActiveClusters(&nc, gemm_ln_half_c4_kernel, &cfg) == cudaSuccess && nc > 0)
+                I->ln4_clusters = nc < I->sms / 4 ? nc : I->sms / 4;
+            else
+                cudaGetLastError();
+        }
     }
     const char* am = getenv("EGOEGO_ATTN");
     I->attn_tc = !(am && strcmp(am, "simt") == 0);
@@ -307,6 +325,18 @@ int TcEngine::launches_per_denoiser(int fmt) const {
 static int launch_gemm_ln(TcImpl* I, const Plane& A, const Plane& W, int M, int K, const float* bias, const float* g,
                           const float* b, cudaStream_t s) {
     EG_CHECK(M % GEMM_BM == 0 && K % GEMM_BK == 0, "fused-LN gemm shape not tile-aligned");
+    if (I->ln4_clusters > 0 && M % 256 == 0) {
+        const int tiles = M / 256;
+        const int clusters = tiles < I->ln4_clusters ? tiles : I->ln4_clusters;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(4 * clusters); cfg.blockDim = dim3(GEMM_LN4_THREADS); cfg.dynamicSmemBytes = GemmLn4Cfg::SMEM_BYTES; cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        EG_CUDA(cudaLaunchKernelEx(&cfg, gemm_ln_half_c4_kernel, A.m16_128, W.m16_128, I->Hs.m16_128, M, K, bias, g, b));
+        return 0;
+    }
     if (use_2cta() && M % 256 == 0) {
         const int tiles = M / 256;
         int pairs = I->sms / 2;
@@ -327,53 +357,68 @@ static int launch_gemm_ln(TcImpl* I, const Plane& A, const Plane& W, int M, int 
     return 0;
 }
 
+// Stages of one denoiser call (egoego_time_kernel's `which`): 0 start, 1 QKV projection, 2 attention, 3 fc (+LN),
+// 4 w_1, 5 w_2 (+LN), 6 linear_out.  `only` < 0 runs everything; otherwise just that stage of layer 0 (timing hook).
 template <int FMT>
-static int denoiser_impl(TcImpl* I, int B, int T, TSrc ts, const float* pmask, float* model_out, cudaStream_t s) {
+static int denoiser_impl(TcImpl* I, int B, int T, TSrc ts, const float* pmask, float* model_out, cudaStream_t s, int only = -1) {
     const int M = B * LP, d = I->w.d, H = I->w.H, dk = I->w.dk, L = T + 1;
     const int Mg = Mr(B);                          // GEMM rows: whole 256-row tiles (an odd window count is rounded up)
     const int nqkv = 3 * H * dk;
     const int half = (FMT == FMT_HALF) ? 1 : 0;
-    {
-        const bool fused = (FMT == FMT_HALF) && I->fuse_ln && I->attn_tc && pmask == nullptr;
+    const bool fused = (FMT == FMT_HALF) && I->fuse_ln && I->attn_tc && pmask == nullptr;
+    auto on = [&](int stage, int l) { return only < 0 || (only == stage && l == 0); };
+    if (on(0, 0)) {
         TcEpiStart<FMT> e{{}, fused ? nullptr : I->H, I->Hs.hi, I->Hs.lo, d, I->base, I->w.pos, I->w.temb, ts, T, B};
         if (gemm<FMT>(I, I->X, I->Wx, Mg, d, I->kx, e, s)) return 1;
     }
     for (int l = 0; l < I->w.NL; ++l) {
         TcLayer& W = I->layers[l];
         if (I->attn_tc) {
-            TcEpiQKVPlanes<FMT> eq{{}, I->Qp.hi, I->Qp.lo, I->Kp.hi, I->Kp.lo, I->VT.hi, I->VT.lo, W.bqkv, H, 1.0f / sqrtf((float)dk)};
-            if (FMT == FMT_HALF && use_2cta() && use_ares() && d == 512 && (nqkv / 256) % 3 == 0) {
-                if (launch_gemm_ares(I, I->Hs, W.wqkv, Mg, nqkv, eq, s)) return 1;
-            } else {
-                if (gemm<FMT>(I, I->Hs, W.wqkv, Mg, nqkv, d, eq, s)) return 1;
+            if (on(1, l)) {
+                TcEpiQKVPlanes<FMT> eq{{}, I->Qp.hi, I->Qp.lo, I->Kp.hi, I->Kp.lo, I->VT.hi, I->VT.lo, W.bqkv, H, 1.0f / sqrtf((float)dk)};
+                if (FMT == FMT_HALF && use_2cta() && use_ares() && d == 512 && (nqkv / 256) % 3 == 0) {
+                    if (launch_gemm_ares(I, I->Hs, W.wqkv, Mg, nqkv, eq, s)) return 1;
+                } else {
+                    if (gemm<FMT>(I, I->Hs, W.wqkv, Mg, nqkv, d, eq, s)) return 1;
+                }
             }
-            const int items = B * H;
-            attention_tc_kernel<FMT><<<items < I->sms ? items : I->sms, ATT_THREADS, ATT_SMEM_BYTES, s>>>(
-                I->Qp.mhi, I->Qp.mlo, I->Kp.mhi, I->Kp.mlo, I->VT.mhi, I->VT.mlo, I->O.hi, I->O.lo, H * dk, items, H, L);
+            if (on(2, l)) {
+                const int items = B * H;
+                attention_tc_kernel<FMT><<<items < I->sms ? items : I->sms, ATT_THREADS, ATT_SMEM_BYTES, s>>>(
+                    I->Qp.mhi, I->Qp.mlo, I->Kp.mhi, I->Kp.mlo, I->VT.mhi, I->VT.mlo, I->O.hi, I->O.lo, H * dk, items, H, L);
+            }
         } else {
-            TcEpiBiasScaleF32 eq{{}, {}, I->QKV, nqkv, W.bqkv, H * dk, 1.0f / sqrtf((float)dk)};
-            if (gemm<FMT_SPLIT>(I, I->Hs, W.wqkv, Mg, nqkv, d, eq, s)) return 1;
-            attention_simt_kernel<true><<<B * H, 256, ATT_SIMT_SMEM, s>>>(I->QKV, nqkv, nullptr, I->O.hi, I->O.lo, H * dk, H, L);
+            if (on(1, l)) {
+                TcEpiBiasScaleF32 eq{{}, {}, I->QKV, nqkv, W.bqkv, H * dk, 1.0f / sqrtf((float)dk)};
+                if (gemm<FMT_SPLIT>(I, I->Hs, W.wqkv, Mg, nqkv, d, eq, s)) return 1;
+            }
+            if (on(2, l))
+                attention_simt_kernel<true><<<B * H, 256, ATT_SIMT_SMEM, s>>>(I->QKV, nqkv, nullptr, I->O.hi, I->O.lo, H * dk, H, L);
         }
-        const bool fused = (FMT == FMT_HALF) && I->fuse_ln && I->attn_tc && pmask == nullptr;
-        if (fused) {
-            if (launch_gemm_ln(I, I->O, W.fc, Mg, H * dk, W.fc_b, W.ln1_g, W.ln1_b, s)) return 1;
-        } else {
-            TcEpiBiasResidF32 ef{{}, I->Y, d, W.fc_b, I->H};
-            if (gemm<FMT>(I, I->O, W.fc, Mg, d, H * dk, ef, s)) return 1;
-            layernorm512_kernel<<<M / 8, 256, 0, s>>>(I->Y, I->H, I->Hs.hi, I->Hs.lo, W.ln1_g, W.ln1_b, pmask, T, M, half);
+        if (on(3, l)) {
+            if (fused) {
+                if (launch_gemm_ln(I, I->O, W.fc, Mg, H * dk, W.fc_b, W.ln1_g, W.ln1_b, s)) return 1;
+            } else {
+                TcEpiBiasResidF32 ef{{}, I->Y, d, W.fc_b, I->H};
+                if (gemm<FMT>(I, I->O, W.fc, Mg, d, H * dk, ef, s)) return 1;
+                layernorm512_kernel<<<M / 8, 256, 0, s>>>(I->Y, I->H, I->Hs.hi, I->Hs.lo, W.ln1_g, W.ln1_b, pmask, T, M, half);
+            }
         }
-        TcEpiBiasReluSplit<FMT> e1{{}, {}, I->F.hi, I->F.lo, d, W.b1};
-        if (gemm<FMT>(I, I->Hs, W.w1, Mg, d, d, e1, s)) return 1;
-        if (fused) {
-            if (launch_gemm_ln(I, I->F, W.w2, Mg, d, W.b2, W.ln2_g, W.ln2_b, s)) return 1;
-        } else {
-            TcEpiBiasResidF32 e2{{}, I->Y, d, W.b2, I->H};
-            if (gemm<FMT>(I, I->F, W.w2, Mg, d, d, e2, s)) return 1;
-            layernorm512_kernel<<<M / 8, 256, 0, s>>>(I->Y, I->H, I->Hs.hi, I->Hs.lo, W.ln2_g, W.ln2_b, pmask, T, M, half);
+        if (on(4, l)) {
+            TcEpiBiasReluSplit<FMT> e1{{}, {}, I->F.hi, I->F.lo, d, W.b1};
+            if (gemm<FMT>(I, I->Hs, W.w1, Mg, d, d, e1, s)) return 1;
+        }
+        if (on(5, l)) {
+            if (fused) {
+                if (launch_gemm_ln(I, I->F, W.w2, Mg, d, W.b2, W.ln2_g, W.ln2_b, s)) return 1;
+            } else {
+                TcEpiBiasResidF32 e2{{}, I->Y, d, W.b2, I->H};
+                if (gemm<FMT>(I, I->F, W.w2, Mg, d, d, e2, s)) return 1;
+                layernorm512_kernel<<<M / 8, 256, 0, s>>>(I->Y, I->H, I->Hs.hi, I->Hs.lo, W.ln2_g, W.ln2_b, pmask, T, M, half);
+            }
         }
     }
-    {
+    if (on(6, 0)) {
         TcEpiOut eo{{}, {}, model_out, I->w.D, I->w.out_b, T, B};
         if (gemm<FMT>(I, I->Hs, I->Wout, Mg, I->nout, d, eo, s)) return 1;
     }
@@ -390,24 +435,19 @@ int TcEngine::denoiser(int B, int T, TSrc ts, const float* pmask, float* model_o
     return rc;
 }
 
-// Time the dominant kernel (fused QKV projection of layer 0, attention-plane epilogue) in isolation on the engine's
-// own buffers: `iters` back-to-back launches between two CUDA events on stream `s`.
-int TcEngine::time_qkv(int B, int fmt, int iters, cudaStream_t s, float* ms) {
+// Time ONE stage of the denoiser (see denoiser_impl; layer 0's weights) in isolation on the engine's own buffers:
+// `iters` back-to-back launches between two CUDA events on stream `s`.  The workspace keeps whatever the last
+// sampling call left in it (finite activations), which the stage overwrites in place as it does inside a step.
+int TcEngine::time_stage(int B, int T, int stage, int fmt, int iters, float* model_out, cudaStream_t s, float* ms) {
     TcImpl* I = impl_;
-    EG_CHECK(I && I->attn_tc, "time_qkv needs the tensor-core attention layout");
-    EG_CHECK(B >= 1 && B <= I->w.max_batch && iters >= 1, "bad arguments");
-    const int d = I->w.d, H = I->w.H, dk = I->w.dk, nqkv = 3 * H * dk, Mg = Mr(B);
-    TcLayer& W = I->layers[0];
+    EG_CHECK(I && I->attn_tc, "time_stage needs the tensor-core attention layout");
+    EG_CHECK(B >= 1 && B <= I->w.max_batch && iters >= 1 && stage >= 0 && stage <= 6, "bad arguments");
     cudaEvent_t e0, e1;
     EG_CUDA(cudaEventCreate(&e0)); EG_CUDA(cudaEventCreate(&e1));
+    TSrc ts{nullptr, nullptr, 0};
     auto run = [&]() -> int {
-        if (fmt == FMT_HALF) {
-            TcEpiQKVPlanes<FMT_HALF> eq{{}, I->Qp.hi, I->Qp.lo, I->Kp.hi, I->Kp.lo, I->VT.hi, I->VT.lo, W.bqkv, H, 1.0f / sqrtf((float)dk)};
-            if (use_2cta() && use_ares() && d == 512 && (nqkv / 256) % 3 == 0) return launch_gemm_ares(I, I->Hs, W.wqkv, Mg, nqkv, eq, s);
-            return gemm<FMT_HALF>(I, I->Hs, W.wqkv, Mg, nqkv, d, eq, s);
-        }
-        TcEpiQKVPlanes<FMT_SPLIT> eq{{}, I->Qp.hi, I->Qp.lo, I->Kp.hi, I->Kp.lo, I->VT.hi, I->VT.lo, W.bqkv, H, 1.0f / sqrtf((float)dk)};
-        return gemm<FMT_SPLIT>(I, I->Hs, W.wqkv, Mg, nqkv, d, eq, s);
+        return fmt == FMT_HALF ? denoiser_impl<FMT_HALF>(I, B, T, ts, nullptr, model_out, s, stage)
+                               : denoiser_impl<FMT_SPLIT>(I, B, T, ts, nullptr, model_out, s, stage);
     };
     for (int i = 0; i < 3; ++i) if (run()) return 1;
     EG_CUDA(cudaEventRecord(e0, s));

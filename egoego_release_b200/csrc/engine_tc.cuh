@@ -40,7 +40,7 @@ public:
     int denoiser(int B, int T, TSrc ts, const float* pmask, float* model_out, cudaStream_t s, int64_t* n, int fmt /* FMT_SPLIT=0 | FMT_HALF=1 */);
     void stage_targets(__nv_bfloat16** hi, __nv_bfloat16** lo, __half** h16, int* ld);
     int launches_per_denoiser(int fmt = 0) const;
-    int time_qkv(int B, int fmt, int iters, cudaStream_t s, float* ms);
+    int time_stage(int B, int T, int stage, int fmt, int iters, float* model_out, cudaStream_t s, float* ms);
 private:
     TcImpl* impl_;
 };

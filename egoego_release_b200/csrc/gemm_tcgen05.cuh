@@ -978,4 +978,242 @@ gemm_ln_half_2cta_kernel(const __grid_constant__ CUtensorMap mA, const __grid_co
     if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc_2cta(tmem_base, 512); }
 }
 
+// ---- column-split fused GEMM + LayerNorm: cluster of 4 = two CTA pairs ---------------------------------
+// The full-row kernels above fill all 512 TMEM columns with ONE tile, so MMA and LayerNorm epilogue of a CTA
+// serialise (measured: tensor pipe 6 % active).  Here a cluster of four CTAs owns a 256-row block: pair p
+// (cluster ranks 2p, 2p+1; cta_group::2, M = 256) computes columns [256p, 256p+256) -- an ordinary 256 x 256
+// pair tile whose fp32 accumulator takes 256 TMEM columns, DOUBLE-BUFFERED, so the MMAs of block i+1 run under
+// the epilogue of block i.  A CTA therefore holds 128 rows x 256 columns; the row statistics of LayerNorm
+// (sum, sum of squares -- one pass) are exchanged with the CTA of the other pair that holds the same rows
+// (rank ^ 2) through distributed shared memory: st.async writes the partial into the partner's stat buffer and
+// completes transaction bytes on the partner's mbarrier (no fences).  A thread keeps its 128 x-values (acc + bias
+// + residual) in registers between the statistics and the normalise pass: one TMEM read, no TMEM write-back,
+// and the accumulator stage is released before the exchange.
+//
+// Epilogue I/O is all TMA and all in the accumulator's native thread-per-row layout (no smem transposes, no
+// LDG/STG in the epilogue warps -- ncu: the transposing version issued one instruction per 13 cycles per warp):
+// the fp16 residual block (128 rows x 256 columns = four 128B-swizzled boxes of 64 columns) is TMA-loaded into
+// shared memory, a thread reads its own row with conflict-free 16-byte loads, later overwrites the same bytes
+// with the normalised fp16 output, and a dedicated I/O warp TMA-stores each box as soon as its four warps are
+// done with it, then refills it with the NEXT block's residual.  Math runs on packed fp32x2 (FADD2 / FFMA2).
+constexpr int GEMM_LN4_THREADS = GEMM_THREADS + 32;                    // + epilogue I/O warp (role 10)
+struct GemmLn4Cfg {
+    static constexpr int STAGES = 4;
+    static constexpr int T_BYTES = GEMM_BM * GEMM_BK * 2;              // 16 KB
+    static constexpr int STAGE_BYTES = 2 * T_BYTES;                    // A rows of this CTA + its 128-row half of the pair's W tile
+    static constexpr int RES_BYTES = 4 * T_BYTES;                      // residual / output block: 4 boxes [128 rows][64 cols] fp16
+    static constexpr int STAT_BYTES = 2 * 4 * 128 * 8;                 // [tile parity][source][row] (sum, sumsq)
+    static constexpr int VEC_BYTES = 3 * 256 * 4;                      // bias | gamma | beta of this pair's 256 columns
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + RES_BYTES + STAT_BYTES + VEC_BYTES + 1024 + 256;
+};
+
+__device__ __forceinline__ float2 ld_shared_f2(const float* p) { return *reinterpret_cast<const float2*>(p); }
+
+__global__ void __launch_bounds__(GEMM_LN4_THREADS, 1)
+gemm_ln_half_c4_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mW /*128-row boxes*/,
+                       const __grid_constant__ CUtensorMap mH /* residual in / output out: [M,512] fp16, 128-row x 64-col boxes */,
+                       int M, int K, const float* __restrict__ bias, const float* __restrict__ gamma,
+                       const float* __restrict__ beta) {
+    using Cfg = GemmLn4Cfg;
+    constexpr int STAGES = Cfg::STAGES, T_BYTES = Cfg::T_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES;
+    constexpr uint32_t IDESC = ptx::make_idesc_f16(256, 256);
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* res_smem = smem + STAGES * STAGE_BYTES;                                   // 1024-aligned boxes
+    float2* stat = reinterpret_cast<float2*>(res_smem + Cfg::RES_BYTES);
+    float* vec = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(stat) + Cfg::STAT_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(vec + 3 * 256);
+    uint64_t* full_bar = bars;                         // [S] pair leader
+    uint64_t* empty_bar = bars + STAGES;               // [S] both CTAs of the pair
+    uint64_t* tfull_bar = bars + 2 * STAGES;           // [2] both
+    uint64_t* tempty_bar = bars + 2 * STAGES + 2;      // [2] pair leader
+    uint64_t* stat_bar = bars + 2 * STAGES + 4;        // [2 parities][4 lane quarters]: 64 local arrivals + 512 remote tx bytes
+    uint64_t* res_full = bars + 2 * STAGES + 12;       // [4 boxes] residual landed (I/O thread expect_tx)
+    uint64_t* out_ready = bars + 2 * STAGES + 16;      // [4 boxes] output written by the box's 4 warps
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 20);
+
+    const int lane = threadIdx.x % 32;
+    // role index: hardware warps 0..7 = epilogue roles 2..9 (warp id % 4 selects the TMEM lane quarter), hardware warps
+    // 8, 9, 10 = TMA producer (0), MMA issuer (1), epilogue I/O (10) -- see gemm_split3_kernel
+    const int hw_warp = threadIdx.x / 32;
+    const int warp = hw_warp < 8 ? hw_warp + 2 : (hw_warp == 10 ? 10 : hw_warp - 8);
+    const uint32_t rank4 = ptx::cluster_ctarank();
+    const uint32_t prank = rank4 & 1u, chalf = rank4 >> 1, leader_rank = rank4 & ~1u, partner = rank4 ^ 2u;
+    const bool leader = prank == 0;
+    const uint16_t pair_mask = (uint16_t)(3u << leader_rank);
+    const int cl = blockIdx.x / 4, n_cl = gridDim.x / 4;
+    const int m_tiles = M / 256, kb_total = K / GEMM_BK;
+
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        vec[i] = bias[chalf * 256 + i]; vec[256 + i] = gamma[chalf * 256 + i]; vec[512 + i] = beta[chalf * 256 + i];
+    }
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&mA); ptx::prefetch_tmap(&mW); ptx::prefetch_tmap(&mH);
+        for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 2); ptx::mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], 2 * GEMM_EPI_WARPS); }
+        for (int b = 0; b < 8; ++b) ptx::mbar_init(&stat_bar[b], 64);
+        for (int b = 0; b < 4; ++b) { ptx::mbar_init(&res_full[b], 1); ptx::mbar_init(&out_ready[b], 4); }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) { ptx::tmem_alloc_2cta(tmem_slot, 512); ptx::tmem_relinquish_2cta(); }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {                                 // ===== TMA producer (every CTA) =====
+            int s = 0; uint32_t ph = 0;
+            for (int tile = cl; tile < m_tiles; tile += n_cl) {
+                const int m0 = tile * 256 + (int)prank * 128;
+                const int n0 = (int)chalf * 256 + (int)prank * 128;
+                for (int kb = 0; kb < kb_total; ++kb) {
+                    ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+                    uint8_t* st = smem + s * STAGE_BYTES;
+                    if (leader) ptx::mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
+                    else        ptx::mbar_arrive_cluster(&full_bar[s], leader_rank);
+                    ptx::tma_load_2d_2cta(st, &mA, &full_bar[s], kb * GEMM_BK, m0);
+                    ptx::tma_load_2d_2cta(st + T_BYTES, &mW, &full_bar[s], kb * GEMM_BK, n0);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && leader) {                       // ===== MMA issuer (pair leaders) =====
+            int s = 0; uint32_t ph = 0; int it = 0;
+            for (int tile = cl; tile < m_tiles; tile += n_cl, ++it) {
+                const int a = it & 1;
+                ptx::mbar_wait(&tempty_bar[a], ((it >> 1) & 1) ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + a * 256;
+                for (int kb = 0; kb < kb_total; ++kb) {
+                    ptx::mbar_wait(&full_bar[s], ph);
+                    ptx::tc_fence_after();
+                    const uint32_t st = ptx::smem_u32(smem + s * STAGE_BYTES);
+                    const uint64_t dA = ptx::make_smem_desc_sw128(st), dW = ptx::make_smem_desc_sw128(st + T_BYTES);
+#pragma unroll
+                    for (int kk = 0; kk < GEMM_BK / 16; ++kk)
+                        ptx::umma_f16_2cta(d_tmem, dA + (uint64_t)(kk * 2), dW + (uint64_t)(kk * 2), IDESC, (kb | kk) != 0);
+                    ptx::umma_commit_2cta_mask(&empty_bar[s], pair_mask);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+                ptx::umma_commit_2cta_mask(&tfull_bar[a], pair_mask);
+            }
+        }
+    } else if (warp == 10) {
+        if (lane == 0) {                                 // ===== epilogue I/O: residual loads, output stores (every CTA) =====
+            const int gx = (int)chalf * 256;
+            auto load_box = [&](int b, int tile) {
+                ptx::mbar_arrive_expect_tx(&res_full[b], T_BYTES);
+                ptx::tma_load_2d(res_smem + b * T_BYTES, &mH, &res_full[b], gx + b * 64, tile * 256 + (int)prank * 128);
+            };
+            if (cl < m_tiles) { load_box(0, cl); load_box(2, cl); load_box(1, cl); load_box(3, cl); }
+            int it = 0;
+            for (int tile = cl; tile < m_tiles; tile += n_cl, ++it) {
+                const int nxt = tile + n_cl;
+#pragma unroll 1
+                for (int o = 0; o < 4; ++o) {
+                    const int b = (o & 1) * 2 + (o >> 1);              // 0, 2, 1, 3: both column halves' first box first
+                    ptx::mbar_wait(&out_ready[b], it & 1);
+                    ptx::tma_store_2d(&mH, res_smem + b * T_BYTES, gx + b * 64, tile * 256 + (int)prank * 128);
+                    ptx::tma_store_commit();
+                    if (nxt < m_tiles) { ptx::tma_store_wait_read(); load_box(b, nxt); }
+                }
+            }
+            ptx::tma_store_wait_all();
+        }
+    } else {                                             // ===== LayerNorm epilogue warps 2..9 (every CTA) =====
+        const int quarter = (warp - 2) & 3, hf = (warp - 2) >> 2;
+        const int r = quarter * 32 + lane;                // row within the CTA's 128 == TMEM lane
+        const int ccol = hf * 128;                        // this warp's first column inside the CTA's 256
+        const int src = (int)chalf * 2 + hf;              // which of the row's four partial statistics this thread owns
+        const int sw = r & 7;                             // 128B-swizzle phase of this row
+        int it = 0;
+        for (int tile = cl; tile < m_tiles; tile += n_cl, ++it) {
+            const int a = it & 1;
+            const uint32_t aph = (it >> 1) & 1;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * 256 + ccol;
+            ptx::mbar_wait(&tfull_bar[a], aph);
+            ptx::tc_fence_after();
+            float2 x[64];
+            float2 sum2 = make_float2(0.f, 0.f), sq2 = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t raw[32];
+                ptx::tmem_ld_32x32(taddr + c * 32, raw);
+                const int box = 2 * hf + (c >> 1);
+                if ((c & 1) == 0) ptx::mbar_wait(&res_full[box], it & 1);
+                const uint8_t* rrow = res_smem + box * T_BYTES + r * 128;
+                uint4 rv[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) rv[j] = *reinterpret_cast<const uint4*>(rrow + ((((c & 1) * 4 + j) ^ sw) << 4));
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t hw[4] = {rv[j].x, rv[j].y, rv[j].z, rv[j].w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int e = j * 8 + q * 2;          // column inside the chunk
+                        const float2 rs = __half22float2(*reinterpret_cast<const __half2*>(&hw[q]));
+                        const float2 bs = ld_shared_f2(vec + ccol + c * 32 + e);
+                        float2 v = __fadd2_rn(make_float2(__uint_as_float(raw[e]), __uint_as_float(raw[e + 1])), rs);
+                        v = __fadd2_rn(v, bs);
+                        x[c * 16 + j * 4 + q] = v;
+                        sum2 = __fadd2_rn(sum2, v);
+                        sq2 = __ffma2_rn(v, v, sq2);
+                    }
+                }
+            }
+            ptx::tc_fence_before();                       // accumulator stage drained: hand it back to the MMA issuer
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(&tempty_bar[a], leader_rank);
+            // ---- row statistics: four partials per row (2 pairs x 2 column halves), two of them remote ----
+            const float sum = sum2.x + sum2.y, sq = sq2.x + sq2.y;
+            const int buf = it & 1;
+            float2* mine = stat + (buf * 4 + src) * 128 + r;
+            uint64_t* sb = &stat_bar[buf * 4 + quarter];
+            *mine = make_float2(sum, sq);
+            ptx::st_async_f2(mine, sb, partner, sum, sq);
+            ptx::mbar_arrive_expect_tx(sb, 8);            // this thread's arrival + the 8 bytes its remote counterpart sends
+            ptx::mbar_wait(sb, aph);
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { const float2 p = stat[(buf * 4 + k) * 128 + r]; s1 += p.x; s2 += p.y; }
+            const float mean = s1 * (1.0f / 512.0f);
+            const float rstd = rsqrtf(fmaxf(s2 * (1.0f / 512.0f) - mean * mean, 0.f) + 1e-5f);
+            const float2 rs2 = make_float2(rstd, rstd), nm2 = make_float2(-mean * rstd, -mean * rstd);
+            // ---- normalise from registers, fp16 output over the residual bytes of the same row ----
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int box = 2 * hf + (c >> 1);
+                uint8_t* rrow = res_smem + box * T_BYTES + r * 128;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t hw[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int e = j * 8 + q * 2;
+                        const float2 g2 = ld_shared_f2(vec + 256 + ccol + c * 32 + e), b2 = ld_shared_f2(vec + 512 + ccol + c * 32 + e);
+                        float2 y = __ffma2_rn(x[c * 16 + j * 4 + q], rs2, nm2);
+                        y = __ffma2_rn(y, g2, b2);
+                        const __half2 h = __floats2half2_rn(y.x, y.y);
+                        hw[q] = *reinterpret_cast<const uint32_t*>(&h);
+                    }
+                    *reinterpret_cast<uint4*>(rrow + ((((c & 1) * 4 + j) ^ sw) << 4)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                }
+                if (c & 1) {                              // box complete for this warp: publish to the async proxy
+                    ptx::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&out_ready[box]);
+                }
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync();                                 // nobody leaves while a peer may still write its smem / TMEM
+    if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc_2cta(tmem_base, 512); }
+}
+
 }  // namespace egoego

@@ -432,6 +432,7 @@ struct DdpmArgs {
     float* stage_f32; int stage_ld;                                  // SIMT engine A operand (nullable)
     __nv_bfloat16* stage_hi; __nv_bfloat16* stage_lo; int stage_ld16; // tensor engine A operand (nullable)
     __half* stage_h16;                                                // fp16 plane for FMT_HALF steps (nullable)
+    int stage_mode;          // tensor engine planes to write: 0 = bf16 hi/lo only, 1 = fp16 only, 2 = all (next step's format unknown)
     TSrc ts; NoiseSrc ns;
     int B, T, D;
 };
@@ -446,39 +447,61 @@ static __global__ void ddpm_update_kernel(DdpmArgs a) {
     const int t = a.ts.get(w);
     const float c1 = a.coef1[t], c2 = a.coef2[t];
     const float sigma = (t == 0) ? 0.f : expf(0.5f * a.logvar[t]);
-    float nz[4];
+    const float k_mo = (a.objective == 0) ? -a.sqrt_recipm1[t] : 1.0f, k_x = (a.objective == 0) ? a.sqrt_recip[t] : 0.0f;
+    const long long i0 = (long long)w * epw + e0;
+    // float4 path: no tail quad and every window base 16-byte aligned (warp-uniform)
+    const bool vec = (epw & 3) == 0 && (((uintptr_t)a.x | (uintptr_t)a.x_out | (uintptr_t)a.model_out) & 15) == 0;
+    float nz[4], xv[4], mo[4];
     const int draw = a.ns.draw();
     if (a.ns.tape) {
+        const float* tp = a.ns.tape + (long long)draw * a.ns.draw_stride + i0;
+        if (vec && ((a.ns.draw_stride & 3) == 0) && ((uintptr_t)a.ns.tape & 15) == 0) { const float4 n = *reinterpret_cast<const float4*>(tp); nz[0] = n.x; nz[1] = n.y; nz[2] = n.z; nz[3] = n.w; }
+        else {
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
-            nz[r] = (e0 + r < epw) ? a.ns.tape[(long long)draw * a.ns.draw_stride + (long long)w * epw + e0 + r] : 0.f;
+            for (int r = 0; r < 4; ++r) nz[r] = (e0 + r < epw) ? tp[r] : 0.f;
+        }
     } else {
         float4 n = philox_normal4(a.ns.seed, a.ns.window_offset + w, (uint32_t)draw, (uint32_t)(e0 >> 2));
         nz[0] = n.x; nz[1] = n.y; nz[2] = n.z; nz[3] = n.w;
     }
+    if (vec) {
+        const float4 xq = *reinterpret_cast<const float4*>(a.x + i0), mq = *reinterpret_cast<const float4*>(a.model_out + i0);
+        xv[0] = xq.x; xv[1] = xq.y; xv[2] = xq.z; xv[3] = xq.w; mo[0] = mq.x; mo[1] = mq.y; mo[2] = mq.z; mo[3] = mq.w;
+    } else {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { const bool ok = e0 + r < epw; xv[r] = ok ? a.x[i0 + r] : 0.f; mo[r] = ok ? a.model_out[i0 + r] : 0.f; }
+    }
+    float v[4];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-        const int e = e0 + r;
-        if (e >= epw) break;
-        const long long i = (long long)w * epw + e;
-        const int f = e / a.D, c = e % a.D;
-        const float xv = a.x[i];
-        float x0 = a.model_out[i];
-        if (a.objective == 0) x0 = a.sqrt_recip[t] * xv - a.sqrt_recipm1[t] * x0;
+        float x0 = (a.objective == 0) ? (k_x * xv[r] + k_mo * mo[r]) : mo[r];
         if (a.clip) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
-        float v = c1 * x0 + c2 * xv;
-        v = v + sigma * nz[r];
-        if (a.inpaint && f < a.inpaint_len) v = a.inpaint[((long long)w * a.inpaint_len + f) * a.D + c];
-        a.x_out[i] = v;
-        if (a.stage_f32) a.stage_f32[((long long)w * LP + 1 + f) * a.stage_ld + c] = v;
+        v[r] = (c1 * x0 + c2 * xv[r]) + sigma * nz[r];
+    }
+    // d_feats is even and e0 is a multiple of 4: the pairs (e0, e0+1) and (e0+2, e0+3) never straddle a frame
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int e = e0 + 2 * h;
+        if (e >= epw) break;
+        const int f = e / a.D, c = e % a.D;
+        if (a.inpaint && f < a.inpaint_len) {
+            const float* ip = a.inpaint + ((long long)w * a.inpaint_len + f) * a.D + c;
+            v[2 * h] = ip[0]; v[2 * h + 1] = ip[1];
+        }
+        if (!vec) { a.x_out[i0 + 2 * h] = v[2 * h]; a.x_out[i0 + 2 * h + 1] = v[2 * h + 1]; }
+        if (a.stage_f32) *reinterpret_cast<float2*>(a.stage_f32 + ((long long)w * LP + 1 + f) * a.stage_ld + c) = make_float2(v[2 * h], v[2 * h + 1]);
         if (a.stage_hi) {
-            __nv_bfloat16 hi, lo;
-            split_bf16(v, hi, lo);
-            long long o = ((long long)w * LP + 1 + f) * a.stage_ld16 + c;
-            a.stage_hi[o] = hi; a.stage_lo[o] = lo;
-            if (a.stage_h16) a.stage_h16[o] = __float2half_rn(v);
+            const long long o = ((long long)w * LP + 1 + f) * a.stage_ld16 + c;
+            if (a.stage_mode != 1) {
+                __nv_bfloat16 h0, l0, h1, l1;
+                split_bf16(v[2 * h], h0, l0); split_bf16(v[2 * h + 1], h1, l1);
+                *reinterpret_cast<__nv_bfloat162*>(a.stage_hi + o) = __nv_bfloat162(h0, h1);
+                *reinterpret_cast<__nv_bfloat162*>(a.stage_lo + o) = __nv_bfloat162(l0, l1);
+            }
+            if (a.stage_h16 && a.stage_mode != 0) *reinterpret_cast<__half2*>(a.stage_h16 + o) = __floats2half2_rn(v[2 * h], v[2 * h + 1]);
         }
     }
+    if (vec) *reinterpret_cast<float4*>(a.x_out + i0) = make_float4(v[0], v[1], v[2], v[3]);
 }
 
 static __global__ void advance_step_kernel(int* d_step) { if (threadIdx.x == 0 && blockIdx.x == 0) (*d_step)++; }

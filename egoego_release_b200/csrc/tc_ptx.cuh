@@ -140,6 +140,60 @@ __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
                  ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
 
+// same with an explicit cluster CTA mask (pairs inside a larger cluster: 3 << leader_rank)
+__device__ __forceinline__ void umma_commit_2cta_mask(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+
+// ---- distributed shared memory (cluster scope) ----------------------------------------------------
+// release-arrive on the mbarrier at the same offset in CTA `cta`: orders this thread's earlier (remote) stores
+__device__ __forceinline__ void mbar_arrive_cluster_release(uint64_t* bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(smem_u32(bar)), "r"(cta) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {   // acquire at cluster scope
+    uint32_t spins = 0, ok = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) break;
+        if (++spins > (1u << 28)) { __trap(); }
+    }
+}
+__device__ __forceinline__ void st_cluster_f2(const void* local_ptr, uint32_t cta, float a, float b) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "st.shared::cluster.v2.f32 [ra], {%2, %3};\n\t}"
+        ::"r"(smem_u32(local_ptr)), "r"(cta), "f"(a), "f"(b) : "memory");
+}
+
+// remote store whose completion is signalled as 8 transaction bytes on an mbarrier of the destination CTA (no fences)
+__device__ __forceinline__ void st_async_f2(const void* local_ptr, uint64_t* local_bar, uint32_t cta, float a, float b) {
+    asm volatile(
+        "{\n\t.reg .b32 ra, rb;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %2;\n\t"
+        "mapa.shared::cluster.u32 rb, %1, %2;\n\t"
+        "st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [ra], {%3, %4}, [rb];\n\t}"
+        ::"r"(smem_u32(local_ptr)), "r"(smem_u32(local_bar)), "r"(cta), "f"(a), "f"(b) : "memory");
+}
+
+// ---- TMA store (shared -> global, bulk async-group completion) -------------------------------------
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int x, int y) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }   // smem reusable
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }         // writes performed
+
 // ---- descriptors --------------------------------------------------------------------------------
 // K-major operand tile stored as [rows][64 bf16] (128 B per row) with the 128-byte swizzle TMA writes:
 // 8-row groups are 1024 B apart (SBO), LBO is unused for swizzled K-major layouts (set to 1 like CUTLASS).

@@ -273,6 +273,20 @@ class CondGaussianDiffusion(nn.Module):
             check(_capi.lib().egoego_time_dominant_kernel(h, B, 1 if half_fmt else 0, iters, C.byref(ms), _stream(dev)))
         return float(ms.value)
 
+    KERNELS = ("start", "qkv", "attention", "fc_ln", "w1", "w2_ln", "out", "ddpm_update")
+
+    def time_kernel(self, which, B: int, T: int, half_fmt: bool, iters: int = 20) -> float:
+        """ms per launch of one kernel of the sampling step (``which``: name in KERNELS or EGOEGO_KERNEL_* id),
+        timed in isolation with CUDA events on the current stream (egoego_time_kernel)."""
+        if isinstance(which, str):
+            which = self.KERNELS.index(which)
+        h = self._handle()
+        dev = self._device()
+        ms = C.c_float()
+        with torch.cuda.device(dev):
+            check(_capi.lib().egoego_time_kernel(h, B, T, int(which), 1 if half_fmt else 0, iters, C.byref(ms), _stream(dev)))
+        return float(ms.value)
+
     def launch_count(self) -> int:
         return int(_capi.lib().egoego_launch_count(self._h)) if self._h is not None else 0
 

@@ -161,9 +161,24 @@ int  egoego_tail_condition(egoego_handle h, const float* gquat_dev, const float*
  * cumulative count of denoiser steps executed. */
 int64_t egoego_launch_count(egoego_handle h);
 
-/* Measurement hook (bench.py roofline): average device time of one launch of the dominant kernel -- the fused QKV
- * projection GEMM of layer 0 with its attention-plane epilogue -- over `iters` back-to-back launches on `stream`,
- * timed with CUDA events on that stream.  Operates on the handle's own workspace for B windows. */
+/* Measurement hook (bench.py roofline / per-kernel table): average device time of one launch of ONE kernel of the
+ * sampling step -- `which` = EGOEGO_KERNEL_* (layer 0's weights) -- over `iters` back-to-back launches on `stream`,
+ * timed with CUDA events on that stream.  Operates in place on the handle's own workspace for B windows of T frames
+ * (run a sampling call first so the workspace holds finite activations).  half_fmt selects the operand format
+ * (0 = 3-term bf16 split, 1 = single-pass fp16; for FC_LN / W2_LN the fp16 format is the fused GEMM+LayerNorm kernel,
+ * the split format times the GEMM and the LayerNorm kernel together). */
+enum {
+    EGOEGO_KERNEL_START = 0,      /* x-half of start_conv + base/time token                        */
+    EGOEGO_KERNEL_QKV = 1,        /* fused Q,K,V projection -> attention operand planes           */
+    EGOEGO_KERNEL_ATTENTION = 2,  /* QK^T, softmax, PV for all (window, head)                     */
+    EGOEGO_KERNEL_FC_LN = 3,      /* attention fc + bias + residual + LayerNorm                   */
+    EGOEGO_KERNEL_W1 = 4,         /* FFN w_1 + bias + ReLU                                        */
+    EGOEGO_KERNEL_W2_LN = 5,      /* FFN w_2 + bias + residual + LayerNorm                        */
+    EGOEGO_KERNEL_OUT = 6,        /* linear_out                                                   */
+    EGOEGO_KERNEL_DDPM_UPDATE = 7 /* clamp + posterior mean + noise + next-step operand staging   */
+};
+int  egoego_time_kernel(egoego_handle h, int B, int T, int which, int half_fmt, int iters, float* ms_per_launch, void* stream);
+/* = egoego_time_kernel(h, B, max T, EGOEGO_KERNEL_QKV, ...) (kept for older callers). */
 int  egoego_time_dominant_kernel(egoego_handle h, int B, int half_fmt, int iters, float* ms_per_launch, void* stream);
 /* Resolved precision policy: steps t < K run the 3-term split (see egoego_cfg.precise_last_steps). */
 int  egoego_precise_last_steps(egoego_handle h);

@@ -215,3 +215,44 @@ def test_precision_policy_knob(golden_dir, params0):
     print("joint error (m) by precise_last_steps:", errs)
     assert errs[50] < 3e-4 and errs[20] < JPOS_TOL_M
     assert errs[0] > errs[50]            # the fp16 format alone is NOT fp32-grade: the policy matters
+
+
+def test_fused_ln_kernels_agree(params0, monkeypatch):
+    """The column-split cluster-of-4 GEMM+LayerNorm kernel (default) against the full-row pair kernel (EGOEGO_LN=2cta) and
+    against the unfused GEMM + LayerNorm kernels (EGOEGO_FUSE_LN=0), all-fp16 steps, enough windows that every cluster
+    walks several 256-row blocks.  Differences are fp16 rounding noise (one-pass vs centred variance, summation order)."""
+    import egoego_release_b200 as E
+    N, B = 4, 160
+    xs = synth_x_start(17, B, 120).cuda()
+    cm = O.prep_head_condition_mask(xs.shape).cuda()
+    outs = {}
+    for tag, env in (("c4", {}), ("2cta", {"EGOEGO_LN": "2cta"}), ("unfused", {"EGOEGO_FUSE_LN": "0"})):
+        for k in ("EGOEGO_LN", "EGOEGO_FUSE_LN"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        m = E.CondGaussianDiffusion(d_feats=198, d_model=512, n_dec_layers=4, n_head=4, d_k=256, d_v=256, max_timesteps=121,
+                                    out_dim=198, timesteps=N, objective="pred_x0", max_batch=B, engine="tcgen05",
+                                    precise_last_steps=0)
+        m.load_state_dict(params0, strict=False)
+        m = m.cuda()
+        torch.manual_seed(3)
+        outs[tag] = m.sample(xs, cm)
+        assert torch.isfinite(outs[tag]).all()
+    d1, d2 = maxabs(outs["c4"], outs["2cta"]), maxabs(outs["c4"], outs["unfused"])
+    print(f"fused-LN kernels: c4 vs 2cta {d1:.3e}, c4 vs unfused {d2:.3e}")
+    assert d1 < 2e-2 and d2 < 2e-2
+
+
+def test_time_kernel_hook(params0):
+    """egoego_time_kernel times every kernel of the step in isolation without disturbing later sampling calls."""
+    m = make_model(8, "tcgen05", params0, max_batch=8)
+    xs = synth_x_start(5, 8, 120).cuda()
+    cm = O.prep_head_condition_mask(xs.shape).cuda()
+    torch.manual_seed(1); a = m.sample(xs, cm)
+    for name in m.KERNELS:
+        for half in (False, True):
+            ms = m.time_kernel(name, 8, 120, half, iters=2)
+            assert 0.0 < ms < 50.0, (name, half, ms)
+    torch.manual_seed(1); b = m.sample(xs, cm)
+    assert torch.equal(a, b)
