@@ -5,11 +5,12 @@
 //   S = Qh Kh^T + Qh Kl^T + Ql Kh^T           (UMMA 128x128x16, K = d_k = 256)
 //   O = Ph Vh   + Ph Vl   + Pl Vh             (UMMA 128x256x16, K = 128 keys)
 // Operand planes (written by the QKV projection epilogue, bf16, K-major):
-//   Q, K : [(window*H + head)*128 + token, 256]      (Q pre-scaled by 1/sqrt(d_k))
-//   V^T  : [(window*H + head)*256 + dim,  128 tokens]
+//   Q, K, V : [(window*H + head)*128 + token, 256]   (Q pre-scaled by 1/sqrt(d_k))
+// V keeps the projection's natural [key][dim] layout: in O = P V it is the MN-major B operand of the UMMA (N = dim is the
+// contiguous index), so the QKV epilogue writes all three sections the same coalesced way and no transposed copy exists.
 // Persistent CTAs (one per SM, 192 threads) loop over (window, head) items:
 //   warp 0    TMA producer, 128 KB ring (2 x 64 KB stages in split, 4 x 32 KB in fp16 format): 4 Q/K k-blocks then
-//             2 V^T k-blocks per item
+//             2 V k-blocks (64 keys x 256 dims as four [64 keys][64 dims] boxes) per item
 //   warp 1    MMA issuer (S of item i+1 is issued right after P V of item i, overlapping its epilogue)
 //   warps 2-9 softmax (TMEM -> registers -> P planes into swizzled smem) and O epilogue (TMEM -> operand planes);
 //             two warps share each TMEM lane quarter and split the key / output columns, exchanging the row
@@ -48,7 +49,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_consta
                     int n_items, int n_head, int L) {
     constexpr int NP = FmtTraits<FMT>::NP;            // FMT_HALF: single fp16 plane per operand, one MMA per k-step
     constexpr uint32_t IDESC_S = (FMT == FMT_SPLIT) ? ptx::make_idesc_bf16(128, 128) : ptx::make_idesc_f16(128, 128);
-    constexpr uint32_t IDESC_O = (FMT == FMT_SPLIT) ? ptx::make_idesc_bf16(128, 256) : ptx::make_idesc_f16(128, 256);
+    constexpr uint32_t IDESC_O = ((FMT == FMT_SPLIT) ? ptx::make_idesc_bf16(128, 256) : ptx::make_idesc_f16(128, 256)) | ptx::IDESC_B_MN_MAJOR;
     constexpr uint32_t QK_BYTES = NP * 2 * 16384, V_BYTES = NP * 32768;
     constexpr int ATT_STAGE_BYTES = NP * 32768;            // one k-block of Q+K planes, or of V planes
     constexpr int ATT_STAGES = ATT_RING_BYTES / ATT_STAGE_BYTES;
@@ -103,12 +104,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_consta
                     if (NP == 2) ptx::tma_load_2d(st + OFF_KL, &mKl, &full_bar[s], kb * 64, item * 128);
                     if (++s == ATT_STAGES) { s = 0; ph ^= 1; }
                 }
-                for (int kb = 0; kb < 2; ++kb) {           // V^T k-blocks of 64 keys: Vh Vl (32 KB each)
+                for (int kb = 0; kb < 2; ++kb) {           // V k-blocks of 64 keys: Vh Vl (32 KB each = 4 dim blocks x [64 keys][128 B])
                     ptx::mbar_wait(&empty_bar[s], ph ^ 1);
                     uint8_t* st = smem + s * ATT_STAGE_BYTES;
                     ptx::mbar_arrive_expect_tx(&full_bar[s], V_BYTES);
-                    ptx::tma_load_2d(st, &mVh, &full_bar[s], kb * 64, item * 256);
-                    if (NP == 2) ptx::tma_load_2d(st + OFF_VL, &mVl, &full_bar[s], kb * 64, item * 256);
+#pragma unroll
+                    for (int db = 0; db < 4; ++db) {
+                        ptx::tma_load_2d(st + db * 8192, &mVh, &full_bar[s], db * 64, item * 128 + kb * 64);
+                        if (NP == 2) ptx::tma_load_2d(st + OFF_VL + db * 8192, &mVl, &full_bar[s], db * 64, item * 128 + kb * 64);
+                    }
                     if (++s == ATT_STAGES) { s = 0; ph ^= 1; }
                 }
             }
@@ -149,15 +153,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_consta
                     ptx::mbar_wait(&full_bar[s], ph);
                     ptx::tc_fence_after();
                     const uint32_t st = ptx::smem_u32(smem + s * ATT_STAGE_BYTES);
-                    const uint64_t dVh = ptx::make_smem_desc_sw128(st), dVl = ptx::make_smem_desc_sw128(st + OFF_VL);
+                    // V: MN-major B, dim blocks 8 KB apart (LBO), 8-key groups 1 KB apart (SBO); 16 keys per UMMA = 2 KB
+                    const uint64_t dVh = ptx::make_smem_desc_mn_sw128(st, 8192, 1024), dVl = ptx::make_smem_desc_mn_sw128(st + OFF_VL, 8192, 1024);
                     const uint64_t dPh = ptx::make_smem_desc_sw128(p_hi + kb * 16384), dPl = ptx::make_smem_desc_sw128(p_lo + kb * 16384);
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) {
-                        const uint64_t adv = (uint64_t)(kk * 2);
-                        ptx::umma_f16(tmem_base + TM_O, dPh + adv, dVh + adv, IDESC_O, (kb | kk) != 0);
+                        const uint64_t adv = (uint64_t)(kk * 2), advv = (uint64_t)(kk * 128);
+                        ptx::umma_f16(tmem_base + TM_O, dPh + adv, dVh + advv, IDESC_O, (kb | kk) != 0);
                         if (NP == 2) {
-                            ptx::umma_f16(tmem_base + TM_O, dPh + adv, dVl + adv, IDESC_O, 1);
-                            ptx::umma_f16(tmem_base + TM_O, dPl + adv, dVh + adv, IDESC_O, 1);
+                            ptx::umma_f16(tmem_base + TM_O, dPh + adv, dVl + advv, IDESC_O, 1);
+                            ptx::umma_f16(tmem_base + TM_O, dPl + adv, dVh + advv, IDESC_O, 1);
                         }
                     }
                     ptx::umma_commit(&empty_bar[s]);
@@ -246,40 +251,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_consta
     if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, 512); }
 }
 
-// QKV projection epilogue writing the attention operand planes directly (one 256-wide tile = one (section, head)).
-// Q / K sections use the coalesced apply4 path; the V section's destination is transposed ([dim][token]), for which
-// the accumulator's native thread-per-row layout is the coalesced one (32 lanes = 32 consecutive tokens).
+// QKV projection epilogue writing the attention operand planes directly (one 256-wide tile = one (section, head));
+// all three sections share the layout [(w*H+h)*128 + l][256].
 template <int FMT>
-struct TcEpiQKVPlanes : EpiNoPre {
-    __nv_bfloat16 *Qh, *Ql, *Kh, *Kl, *Vh, *Vl;       // Q,K: [(w*H+h)*128 + l][256];  V^T: [(w*H+h)*256 + c][128]
+struct TcEpiQKVPlanes : EpiNoDirect, EpiNoPre {
+    __nv_bfloat16 *Qh, *Ql, *Kh, *Kl, *Vh, *Vl;
     const float* bias; int n_head; float q_scale;
     __device__ __forceinline__ float4 bias4(int col) const { return ld4(bias + col); }
-    __device__ __forceinline__ bool direct(int col0) const { return col0 >= 2 * n_head * 256; }
-    __device__ __forceinline__ void apply_row(int row, int col0, const float (&v)[32] /* bias already added */) const {
-        const int w = row / LP, l = row % LP;
-        const int hc = col0 - 2 * n_head * 256, h = hc / 256, c0 = hc % 256;
-        const long long base = ((long long)(w * n_head + h) * 256 + c0) * 128 + l;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            if (FMT == FMT_SPLIT) {
-                __nv_bfloat16 hi, lo;
-                split_bf16(v[j], hi, lo);
-                Vh[base + (long long)j * 128] = hi;
-                Vl[base + (long long)j * 128] = lo;
-            } else {
-                reinterpret_cast<__half*>(Vh)[base + (long long)j * 128] = __float2half_rn(v[j]);
-            }
-        }
-    }
     __device__ __forceinline__ void apply4(int row, int col, float4 a, float4 b, float4) const {
         const int w = row / LP, l = row % LP;
         const int hw = n_head * 256;
-        const int sec = col >= hw ? 1 : 0, hc = col - sec * hw;
+        const int sec = col / hw, hc = col - sec * hw;
         const int h = hc >> 8, c = hc & 255;
         a = add4(a, b);
         if (sec == 0) a = make_float4(a.x * q_scale, a.y * q_scale, a.z * q_scale, a.w * q_scale);
         const long long o = ((long long)(w * n_head + h) * 128 + l) * 256 + c;
-        store_planes4<FMT>((sec == 0 ? Qh : Kh) + o, (sec == 0 ? Ql : Kl) + o, a);
+        store_planes4<FMT>((sec == 0 ? Qh : (sec == 1 ? Kh : Vh)) + o, (sec == 0 ? Ql : (sec == 1 ? Kl : Vl)) + o, a);
     }
 };
 

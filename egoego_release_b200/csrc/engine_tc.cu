@@ -105,7 +105,7 @@ struct TcImpl {
     Plane Wx, Wc, Wout;
     std::vector<TcLayer> layers;
     Plane X, C, Hs, O, F;                       // activation planes (A operands)
-    Plane Qp, Kp, VT;                           // attention operand planes (see attn_tcgen05.cuh)
+    Plane Qp, Kp, VT;                           // attention operand planes (see attn_tcgen05.cuh); VT = V in [key][dim] layout, 64-row TMA boxes
     bool fuse_ln = true;                        // EGOEGO_FUSE_LN=0 keeps GEMM + LayerNorm separate in the fp16 format too
     bool attn_tc = true;                        // EGOEGO_ATTN=simt selects the fp32 CUDA-core attention (bisecting)
     int ln4_clusters = 0;                       // co-resident clusters of 4 for gemm_ln_half_c4_kernel (0 = use the full-row pair kernel)
@@ -193,9 +193,70 @@ static int launch_gemm_ares(TcImpl* I, const Plane& A, const Plane& W, int M, in
     return 0;
 }
 
+// CTA-pair fp16 GEMM with the TMA-store epilogue (default for the fp16-format QKV projection and FFN w_1;
+// EGOEGO_TMA_EPI=0 keeps the transposing epilogue)
+static bool use_tma_epi() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("EGOEGO_TMA_EPI"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1 && use_2cta();
+}
+template <class Epi>
+static int launch_gemm_tma_epi(TcImpl* I, const Plane& A, const Plane& W, int M, int N, int K, const float* bias, const Epi& epi, cudaStream_t s) {
+    static bool attr_set = false;
+    auto kern = gemm_half_tma_2cta_kernel<Epi>;
+    if (!attr_set) {
+        EG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmTmaEpiCfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    EG_CHECK(M % 256 == 0 && N % 256 == 0 && K % GEMM_BK == 0 && N <= GemmTmaEpiCfg::MAX_N, "TMA-epilogue gemm shape not supported");
+    const int tiles = (M / 256) * (N / 256);
+    int pairs = I->sms / 2;
+    if (tiles < pairs) pairs = tiles;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(GEMM_TMAEPI_THREADS); cfg.dynamicSmemBytes = GemmTmaEpiCfg::SMEM_BYTES; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    EG_CUDA(cudaLaunchKernelEx(&cfg, kern, A.m16, W.m16_128, M, N, K, bias, epi));
+    return 0;
+}
+
+// A-resident variant of the above for K = 512 and N a multiple of 3 * 256 (the QKV projection).  Opt-in (EGOEGO_QKV_ARES=1):
+// measured 104.6 us vs 100.8 us for the streaming kernel on the same box -- with the TMA epilogue the projection is bound by
+// the tensor pipe at short K (cuBLAS fp16 on this shape: 94.5 us), not by operand traffic.
+template <class Epi>
+static int launch_gemm_ares_tma(TcImpl* I, const Plane& A, const Plane& W, int M, int N, const float* bias, const Epi& epi, cudaStream_t s) {
+    constexpr int G = 3;
+    using Cfg = GemmAresTmaCfg<G>;
+    static bool attr_set = false;
+    auto kern = gemm_ares_tma_2cta_kernel<G, Epi>;
+    if (!attr_set) {
+        EG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    EG_CHECK(M % 256 == 0 && N % (256 * G) == 0, "A-resident TMA-epilogue gemm shape not tile-aligned");
+    const int items = (M / 256) * ((N / 256) / G);
+    int pairs = I->sms / 2;
+    if (items < pairs) pairs = items;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(GEMM_TMAEPI_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    EG_CUDA(cudaLaunchKernelEx(&cfg, kern, A.m16, W.m16_128, M, N, bias, epi));
+    return 0;
+}
+static bool use_ares_tma() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("EGOEGO_QKV_ARES"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+
 static bool use_ares() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("EGOEGO_QKV_ARES"); v = (e && e[0] == '1') ? 1 : 0; }   // opt-in: measured slower (profiles/r1k)
+    if (v < 0) { const char* e = getenv("EGOEGO_QKV_ARES"); v = (e && e[0] == 'o') ? 1 : 0; }   // "old": A-resident kernel with the transposing epilogue (profiles/r1k)
     return v == 1;
 }
 
@@ -275,7 +336,7 @@ int TcEngine::init(const TcWeights& w, cudaStream_t) {
     if (I->attn_tc) {
         const size_t MBe = (size_t)((w.max_batch + 1) / 2) * 2;
         if (I->Qp.alloc(MBe * H * 128, 256, 128) || I->Kp.alloc(MBe * H * 128, 256, 128) ||
-            I->VT.alloc(MBe * H * 256, 128, 256)) return 1;
+            I->VT.alloc(MBe * H * 128, 256, 64)) return 1;
         EG_CUDA(cudaFuncSetAttribute(attention_tc_kernel<FMT_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
         EG_CUDA(cudaFuncSetAttribute(attention_tc_kernel<FMT_HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
     } else {
@@ -375,8 +436,15 @@ static int denoiser_impl(TcImpl* I, int B, int T, TSrc ts, const float* pmask, f
         TcLayer& W = I->layers[l];
         if (I->attn_tc) {
             if (on(1, l)) {
-                TcEpiQKVPlanes<FMT> eq{{}, I->Qp.hi, I->Qp.lo, I->Kp.hi, I->Kp.lo, I->VT.hi, I->VT.lo, W.bqkv, H, 1.0f / sqrtf((float)dk)};
-                if (FMT == FMT_HALF && use_2cta() && use_ares() && d == 512 && (nqkv / 256) % 3 == 0) {
+                TcEpiQKVPlanes<FMT> eq{{}, {}, I->Qp.hi, I->Qp.lo, I->Kp.hi, I->Kp.lo, I->VT.hi, I->VT.lo, W.bqkv, H, 1.0f / sqrtf((float)dk)};
+                if (FMT == FMT_HALF && use_tma_epi() && Mg % 256 == 0) {
+                    TmaEpiQKV te{I->Qp.m16_128, I->Kp.m16_128, I->VT.m16_128, H, 1.0f / sqrtf((float)dk)};
+                    if (use_ares_tma() && d == 512 && nqkv % 768 == 0) {
+                        if (launch_gemm_ares_tma(I, I->Hs, W.wqkv, Mg, nqkv, W.bqkv, te, s)) return 1;
+                    } else {
+                        if (launch_gemm_tma_epi(I, I->Hs, W.wqkv, Mg, nqkv, d, W.bqkv, te, s)) return 1;
+                    }
+                } else if (FMT == FMT_HALF && use_2cta() && use_ares() && d == 512 && (nqkv / 256) % 3 == 0) {
                     if (launch_gemm_ares(I, I->Hs, W.wqkv, Mg, nqkv, eq, s)) return 1;
                 } else {
                     if (gemm<FMT>(I, I->Hs, W.wqkv, Mg, nqkv, d, eq, s)) return 1;
@@ -405,8 +473,13 @@ static int denoiser_impl(TcImpl* I, int B, int T, TSrc ts, const float* pmask, f
             }
         }
         if (on(4, l)) {
-            TcEpiBiasReluSplit<FMT> e1{{}, {}, I->F.hi, I->F.lo, d, W.b1};
-            if (gemm<FMT>(I, I->Hs, W.w1, Mg, d, d, e1, s)) return 1;
+            if (FMT == FMT_HALF && use_tma_epi() && Mg % 256 == 0) {
+                TmaEpiRelu te{I->F.m16_128};
+                if (launch_gemm_tma_epi(I, I->Hs, W.w1, Mg, d, d, W.b1, te, s)) return 1;
+            } else {
+                TcEpiBiasReluSplit<FMT> e1{{}, {}, I->F.hi, I->F.lo, d, W.b1};
+                if (gemm<FMT>(I, I->Hs, W.w1, Mg, d, d, e1, s)) return 1;
+            }
         }
         if (on(5, l)) {
             if (fused) {

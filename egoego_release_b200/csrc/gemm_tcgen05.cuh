@@ -978,6 +978,410 @@ gemm_ln_half_2cta_kernel(const __grid_constant__ CUtensorMap mA, const __grid_co
     if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc_2cta(tmem_base, 512); }
 }
 
+// ---- CTA-pair fp16 GEMM with a TMA-store epilogue ----------------------------------------------------------
+// Same main loop as gemm_split3_2cta_kernel<FMT_HALF> (256 x 256 pair tiles, cta_group::2, double-buffered TMEM), but the
+// epilogue never leaves the accumulator's thread-per-row layout: a thread adds the bias (broadcast from shared memory),
+// applies the functor on packed fp32x2, converts to fp16 and writes its row into a 128B-swizzled staging block
+// ([128 rows][256 cols] fp16 = four boxes of 64 columns) with conflict-free 16-byte stores; an I/O warp TMA-stores every box
+// as soon as its four warps have published it.  No smem transposes, no per-element address arithmetic, no STG in the
+// epilogue warps (the transposing epilogue issued ~1 instruction / 13 cycles / warp and bounded the QKV projection).
+// Functor interface:
+//   float  tile_scale(n0)                     per-tile scalar handed to apply()
+//   float2 apply(float2 acc_plus_bias, s)     element-wise epilogue
+//   void   box(row0, n0, b, map, x, y)        TMA-store destination of box b (64 columns) of the CTA's 128 x 256 block
+constexpr int GEMM_TMAEPI_THREADS = GEMM_THREADS + 32;                 // + store I/O warp (role 10)
+struct GemmTmaEpiCfg {
+    static constexpr int STAGES = 4;
+    static constexpr int T_BYTES = GEMM_BM * GEMM_BK * 2;              // 16 KB
+    static constexpr int STAGE_BYTES = 2 * T_BYTES;
+    static constexpr int OUT_BYTES = 4 * T_BYTES;                      // staging block
+    static constexpr int MAX_N = 3072;                                 // bias vector kept in shared memory
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_BYTES + MAX_N * 4 + 1024 + 256;
+};
+
+template <class Epi>
+__global__ void __launch_bounds__(GEMM_TMAEPI_THREADS, 1)
+gemm_half_tma_2cta_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mW /*128-row boxes*/,
+                          int M, int N, int K, const float* __restrict__ bias, const __grid_constant__ Epi epi) {
+    using Cfg = GemmTmaEpiCfg;
+    constexpr int STAGES = Cfg::STAGES, T_BYTES = Cfg::T_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES, BN = 256;
+    constexpr uint32_t IDESC = ptx::make_idesc_f16(256, BN);
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* out_smem = smem + STAGES * STAGE_BYTES;
+    float* vec = reinterpret_cast<float*>(out_smem + Cfg::OUT_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(vec + Cfg::MAX_N);
+    uint64_t* full_bar = bars;                          // [S] leader
+    uint64_t* empty_bar = bars + STAGES;                // [S] both
+    uint64_t* tfull_bar = bars + 2 * STAGES;            // [2] both
+    uint64_t* tempty_bar = bars + 2 * STAGES + 2;       // [2] leader
+    uint64_t* out_ready = bars + 2 * STAGES + 4;        // [4 boxes] written by the box's 4 warps
+    uint64_t* box_free = bars + 2 * STAGES + 8;         // [4 boxes] previous store has finished reading the box
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 12);
+
+    const int lane = threadIdx.x % 32;
+    const int hw_warp = threadIdx.x / 32;               // hardware warps 0..7 = epilogue roles 2..9; 8, 9, 10 = roles 0, 1, 10
+    const int warp = hw_warp < 8 ? hw_warp + 2 : (hw_warp == 10 ? 10 : hw_warp - 8);
+    const uint32_t rank = ptx::cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair = blockIdx.x / 2, n_pairs = gridDim.x / 2;
+    const int m_tiles = M / 256, n_tiles = N / BN, k_blocks = K / GEMM_BK;
+    const int total_tiles = m_tiles * n_tiles;
+
+    for (int i = threadIdx.x; i < N; i += blockDim.x) vec[i] = bias[i];
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&mA); ptx::prefetch_tmap(&mW);
+        for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 2); ptx::mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], 2 * GEMM_EPI_WARPS); }
+        for (int b = 0; b < 4; ++b) { ptx::mbar_init(&out_ready[b], 4); ptx::mbar_init(&box_free[b], 1); }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) { ptx::tmem_alloc_2cta(tmem_slot, 512); ptx::tmem_relinquish_2cta(); }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {                                 // ===== TMA producer (both CTAs) =====
+            int s = 0; uint32_t ph = 0;
+            for (int tile = pair; tile < total_tiles; tile += n_pairs) {
+                const int m0 = (tile / n_tiles) * 256 + (int)rank * 128;
+                const int n0 = (tile % n_tiles) * BN + (int)rank * 128;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+                    uint8_t* st = smem + s * STAGE_BYTES;
+                    if (leader) ptx::mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
+                    else        ptx::mbar_arrive_cluster(&full_bar[s], 0);
+                    ptx::tma_load_2d_2cta(st, &mA, &full_bar[s], kb * GEMM_BK, m0);
+                    ptx::tma_load_2d_2cta(st + T_BYTES, &mW, &full_bar[s], kb * GEMM_BK, n0);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && leader) {                       // ===== MMA issuer (leader CTA only) =====
+            int s = 0; uint32_t ph = 0; int it = 0;
+            for (int tile = pair; tile < total_tiles; tile += n_pairs, ++it) {
+                const int a = it & 1;
+                ptx::mbar_wait(&tempty_bar[a], ((it >> 1) & 1) ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + a * BN;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    ptx::mbar_wait(&full_bar[s], ph);
+                    ptx::tc_fence_after();
+                    const uint32_t st = ptx::smem_u32(smem + s * STAGE_BYTES);
+                    const uint64_t dA = ptx::make_smem_desc_sw128(st), dW = ptx::make_smem_desc_sw128(st + T_BYTES);
+#pragma unroll
+                    for (int kk = 0; kk < GEMM_BK / 16; ++kk)
+                        ptx::umma_f16_2cta(d_tmem, dA + (uint64_t)(kk * 2), dW + (uint64_t)(kk * 2), IDESC, (kb | kk) != 0);
+                    ptx::umma_commit_2cta(&empty_bar[s]);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+                ptx::umma_commit_2cta(&tfull_bar[a]);
+            }
+        }
+    } else if (warp == 10) {
+        if (lane == 0) {                                 // ===== store I/O (both CTAs) =====
+            int it = 0;
+            for (int tile = pair; tile < total_tiles; tile += n_pairs, ++it) {
+                const int row0 = (tile / n_tiles) * 256 + (int)rank * 128, n0 = (tile % n_tiles) * BN;
+#pragma unroll 1
+                for (int o = 0; o < 4; ++o) {
+                    const int b = (o & 1) * 2 + (o >> 1);              // 0, 2, 1, 3: both column halves' first box first
+                    const CUtensorMap* map; int x, y;
+                    epi.box(row0, n0, b, map, x, y);
+                    ptx::mbar_wait(&out_ready[b], it & 1);
+                    ptx::tma_store_2d(map, out_smem + b * T_BYTES, x, y);
+                    ptx::tma_store_commit();
+                    ptx::tma_store_wait_read();
+                    ptx::mbar_arrive(&box_free[b]);
+                }
+            }
+            ptx::tma_store_wait_all();
+        }
+    } else {                                             // ===== epilogue warps 2..9 (both CTAs) =====
+        const int quarter = (warp - 2) & 3, hf = (warp - 2) >> 2;
+        const int r = quarter * 32 + lane;                // row within the CTA's 128 == TMEM lane
+        const int sw = r & 7;
+        int it = 0;
+        for (int tile = pair; tile < total_tiles; tile += n_pairs, ++it) {
+            const int a = it & 1;
+            const uint32_t aph = (it >> 1) & 1;
+            const int n0 = (tile % n_tiles) * BN;
+            const float ts = epi.tile_scale(n0);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * BN + hf * 128;
+            const float* bvec = vec + n0 + hf * 128;
+            ptx::mbar_wait(&tfull_bar[a], aph);
+            ptx::tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t raw[32];
+                ptx::tmem_ld_32x32(taddr + c * 32, raw);
+                const int box = 2 * hf + (c >> 1);
+                if ((c & 1) == 0) ptx::mbar_wait(&box_free[box], (it & 1) ^ 1);
+                uint8_t* rrow = out_smem + box * T_BYTES + r * 128;
+                ptx::tmem_ld_wait();
+                if (c == 3) {                             // accumulator stage drained: hand it back to the MMA issuer
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive_cluster(&tempty_bar[a], 0);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t hw[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int e = j * 8 + q * 2;
+                        const float2 bs = *reinterpret_cast<const float2*>(bvec + c * 32 + e);
+                        float2 v = __fadd2_rn(make_float2(__uint_as_float(raw[e]), __uint_as_float(raw[e + 1])), bs);
+                        v = epi.apply(v, ts);
+                        const __half2 h = __floats2half2_rn(v.x, v.y);
+                        hw[q] = *reinterpret_cast<const uint32_t*>(&h);
+                    }
+                    *reinterpret_cast<uint4*>(rrow + ((((c & 1) * 4 + j) ^ sw) << 4)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                }
+                if (c & 1) {                              // box complete for this warp: publish to the async proxy
+                    ptx::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&out_ready[box]);
+                }
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync();
+    if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc_2cta(tmem_base, 512); }
+}
+
+// QKV projection: tile (256 rows = 2 windows, 256 columns = one (section, head)) -> plane [(w*H + h)*128 + l][256]
+struct TmaEpiQKV {
+    CUtensorMap mQ, mK, mV;                               // fp16 planes, 128-row x 64-col boxes
+    int n_head; float q_scale;
+    __device__ __forceinline__ float tile_scale(int n0) const { return n0 < n_head * 256 ? q_scale : 1.0f; }
+    __device__ __forceinline__ float2 apply(float2 v, float s) const { return make_float2(v.x * s, v.y * s); }
+    __device__ __forceinline__ void box(int row0, int n0, int b, const CUtensorMap*& m, int& x, int& y) const {
+        const int hw = n_head * 256, sec = n0 / hw, h = (n0 - sec * hw) >> 8;
+        m = sec == 0 ? &mQ : (sec == 1 ? &mK : &mV);
+        x = b * 64;
+        y = ((row0 / LP) * n_head + h) * 128;
+    }
+};
+// FFN w_1: relu(acc + bias) -> F plane [M, 512]
+struct TmaEpiRelu {
+    CUtensorMap mF;
+    __device__ __forceinline__ float tile_scale(int) const { return 1.0f; }
+    __device__ __forceinline__ float2 apply(float2 v, float) const { return make_float2(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f)); }
+    __device__ __forceinline__ void box(int row0, int n0, int b, const CUtensorMap*& m, int& x, int& y) const {
+        m = &mF; x = n0 + b * 64; y = row0;
+    }
+};
+
+// ---- A-resident CTA-pair fp16 GEMM (K = 512) with the TMA-store epilogue --------------------------------------
+// The streaming pair kernel moves 512 KB of operands per 256 x 256 tile; at the tensor rate of a pair that is ~15 TB/s of
+// L2 -> SM traffic chip-wide, above what the L2 delivers (~10 TB/s), so the wide QKV projection (N = 3072) is L2-bound.
+// Here a pair keeps its 256 x 512 fp16 A block resident in shared memory (128 KB per CTA) for a group of G consecutive N
+// tiles and streams only its W halves (16 KB per k-block per CTA, 4-deep ring): 341 KB per tile at G = 3.  Work item =
+// (256-row block, group of G N tiles): 512 items for 74 pairs.  Epilogue as in gemm_half_tma_2cta_kernel, but with one
+// 16 KB staging box per column half (the A block leaves no room for four): a warp writes the first 64 columns of its
+// half, the I/O warp stores them, and the second 64 columns reuse the box once the store has read it.
+template <int G>
+struct GemmAresTmaCfg {
+    static constexpr int KB = 8;                                        // K = 512
+    static constexpr int T_BYTES = GEMM_BM * GEMM_BK * 2;               // 16 KB
+    static constexpr int A_BYTES = KB * T_BYTES;                        // 128 KB resident A block
+    static constexpr int W_STAGES = 4;
+    static constexpr int OUT_BYTES = 2 * T_BYTES;                       // one staging box per column half
+    static constexpr int SMEM_BYTES = A_BYTES + W_STAGES * T_BYTES + OUT_BYTES + 1024 + 256;
+};
+
+template <int G, class Epi>
+__global__ void __launch_bounds__(GEMM_TMAEPI_THREADS, 1)
+gemm_ares_tma_2cta_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mW /*128-row boxes*/,
+                          int M, int N, const float* __restrict__ bias, const __grid_constant__ Epi epi) {
+    using Cfg = GemmAresTmaCfg<G>;
+    constexpr int KB = Cfg::KB, T_BYTES = Cfg::T_BYTES, WS = Cfg::W_STAGES, BN = 256;
+    constexpr uint32_t IDESC = ptx::make_idesc_f16(256, BN);
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* a_smem = smem;
+    uint8_t* w_smem = smem + Cfg::A_BYTES;
+    uint8_t* out_smem = w_smem + WS * T_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(out_smem + Cfg::OUT_BYTES);
+    uint64_t* a_full = bars;                          // [KB] leader: A k-block kb of the current item landed (both CTAs)
+    uint64_t* a_empty = bars + KB;                    // [KB] both:   last MMA reading A k-block kb of the item retired
+    uint64_t* w_full = bars + 2 * KB;                 // [WS] leader
+    uint64_t* w_empty = bars + 2 * KB + WS;           // [WS] both
+    uint64_t* tfull_bar = bars + 2 * KB + 2 * WS;     // [2] both
+    uint64_t* tempty_bar = bars + 2 * KB + 2 * WS + 2;// [2] leader
+    uint64_t* out_ready = bars + 2 * KB + 2 * WS + 4; // [2 column halves] staging box written by its 4 warps
+    uint64_t* box_free = bars + 2 * KB + 2 * WS + 6;  // [2] store has finished reading the box
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * KB + 2 * WS + 8);
+
+    const int lane = threadIdx.x % 32;
+    const int hw_warp = threadIdx.x / 32;               // hardware warps 0..7 = epilogue roles 2..9; 8, 9, 10 = roles 0, 1, 10
+    const int warp = hw_warp < 8 ? hw_warp + 2 : (hw_warp == 10 ? 10 : hw_warp - 8);
+    const uint32_t rank = ptx::cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair = blockIdx.x / 2, n_pairs = gridDim.x / 2;
+    const int n_groups = (N / BN) / G;
+    const int total_items = (M / 256) * n_groups;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&mA); ptx::prefetch_tmap(&mW);
+        for (int k = 0; k < KB; ++k) { ptx::mbar_init(&a_full[k], 2); ptx::mbar_init(&a_empty[k], 1); }
+        for (int s = 0; s < WS; ++s) { ptx::mbar_init(&w_full[s], 2); ptx::mbar_init(&w_empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], 2 * GEMM_EPI_WARPS); }
+        for (int b = 0; b < 2; ++b) { ptx::mbar_init(&out_ready[b], 4); ptx::mbar_init(&box_free[b], 1); }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) { ptx::tmem_alloc_2cta(tmem_slot, 512); ptx::tmem_relinquish_2cta(); }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {                                 // ===== TMA producer (both CTAs) =====
+            int s = 0; uint32_t ph = 0; int it = 0;
+            for (int item = pair; item < total_items; item += n_pairs, ++it) {
+                const int m0 = (item / n_groups) * 256 + (int)rank * 128;
+                const int ng = item % n_groups;
+                for (int g = 0; g < G; ++g) {
+                    const int n0 = (ng * G + g) * BN + (int)rank * 128;
+                    for (int kb = 0; kb < KB; ++kb) {
+                        if (g == 0) {                    // the item's A block streams in behind the previous item's last tile
+                            ptx::mbar_wait(&a_empty[kb], (it & 1) ^ 1);
+                            if (leader) ptx::mbar_arrive_expect_tx(&a_full[kb], 2 * T_BYTES);
+                            else        ptx::mbar_arrive_cluster(&a_full[kb], 0);
+                            ptx::tma_load_2d_2cta(a_smem + kb * T_BYTES, &mA, &a_full[kb], kb * GEMM_BK, m0);
+                        }
+                        ptx::mbar_wait(&w_empty[s], ph ^ 1);
+                        if (leader) ptx::mbar_arrive_expect_tx(&w_full[s], 2 * T_BYTES);
+                        else        ptx::mbar_arrive_cluster(&w_full[s], 0);
+                        ptx::tma_load_2d_2cta(w_smem + s * T_BYTES, &mW, &w_full[s], kb * GEMM_BK, n0);
+                        if (++s == WS) { s = 0; ph ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && leader) {                       // ===== MMA issuer (leader CTA) =====
+            int s = 0; uint32_t ph = 0; int it = 0, tc = 0;
+            const uint32_t a_addr = ptx::smem_u32(a_smem), w_addr = ptx::smem_u32(w_smem);
+            for (int item = pair; item < total_items; item += n_pairs, ++it) {
+                for (int g = 0; g < G; ++g, ++tc) {
+                    const int a = tc & 1;
+                    ptx::mbar_wait(&tempty_bar[a], ((tc >> 1) & 1) ^ 1);
+                    ptx::tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + a * BN;
+                    for (int kb = 0; kb < KB; ++kb) {
+                        if (g == 0) ptx::mbar_wait(&a_full[kb], it & 1);
+                        ptx::mbar_wait(&w_full[s], ph);
+                        ptx::tc_fence_after();
+                        const uint64_t dA = ptx::make_smem_desc_sw128(a_addr + kb * T_BYTES);
+                        const uint64_t dW = ptx::make_smem_desc_sw128(w_addr + s * T_BYTES);
+#pragma unroll
+                        for (int kk = 0; kk < GEMM_BK / 16; ++kk)
+                            ptx::umma_f16_2cta(d_tmem, dA + (uint64_t)(kk * 2), dW + (uint64_t)(kk * 2), IDESC, (kb | kk) != 0);
+                        ptx::umma_commit_2cta(&w_empty[s]);
+                        if (g == G - 1) ptx::umma_commit_2cta(&a_empty[kb]);   // last reader of A k-block kb in this item
+                        if (++s == WS) { s = 0; ph ^= 1; }
+                    }
+                    ptx::umma_commit_2cta(&tfull_bar[a]);
+                }
+            }
+        }
+    } else if (warp == 10) {
+        if (lane == 0) {                                 // ===== store I/O (both CTAs) =====
+            uint32_t u = 0;                              // box use counter (two uses per tile)
+            for (int item = pair; item < total_items; item += n_pairs) {
+                const int row0 = (item / n_groups) * 256 + (int)rank * 128;
+                const int ng = item % n_groups;
+                for (int g = 0; g < G; ++g) {
+                    const int n0 = (ng * G + g) * BN;
+#pragma unroll 1
+                    for (int half = 0; half < 2; ++half, ++u) {
+#pragma unroll 1
+                        for (int hf = 0; hf < 2; ++hf) {
+                            const CUtensorMap* map; int x, y;
+                            epi.box(row0, n0, 2 * hf + half, map, x, y);
+                            ptx::mbar_wait(&out_ready[hf], u & 1);
+                            ptx::tma_store_2d(map, out_smem + hf * T_BYTES, x, y);
+                            ptx::tma_store_commit();
+                            ptx::tma_store_wait_read();
+                            ptx::mbar_arrive(&box_free[hf]);
+                        }
+                    }
+                }
+            }
+            ptx::tma_store_wait_all();
+        }
+    } else {                                             // ===== epilogue warps 2..9 (both CTAs) =====
+        const int quarter = (warp - 2) & 3, hf = (warp - 2) >> 2;
+        const int r = quarter * 32 + lane;
+        const int sw = r & 7;
+        uint8_t* rrow = out_smem + hf * T_BYTES + r * 128;
+        int tc = 0; uint32_t u = 0;
+        for (int item = pair; item < total_items; item += n_pairs) {
+            const int ng = item % n_groups;
+            for (int g = 0; g < G; ++g, ++tc) {
+                const int a = tc & 1;
+                const uint32_t aph = (tc >> 1) & 1;
+                const int n0 = (ng * G + g) * BN;
+                const float ts = epi.tile_scale(n0);
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * BN + hf * 128;
+                const float* bsrc = bias + n0 + hf * 128;
+                ptx::mbar_wait(&tfull_bar[a], aph);
+                ptx::tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t raw[32];
+                    ptx::tmem_ld_32x32(taddr + c * 32, raw);
+                    float4 bq[8];                             // warp-uniform addresses: one L1 sector per load
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) bq[j] = ld4(bsrc + c * 32 + 4 * j);
+                    if ((c & 1) == 0) { ptx::mbar_wait(&box_free[hf], (u & 1) ^ 1); }
+                    ptx::tmem_ld_wait();
+                    if (c == 3) {                             // accumulator stage drained: hand it back to the MMA issuer
+                        ptx::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive_cluster(&tempty_bar[a], 0);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint32_t hw[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int e = j * 8 + q * 2;
+                            const float4 b4 = bq[e >> 2];
+                            const float2 bs = (e & 2) ? make_float2(b4.z, b4.w) : make_float2(b4.x, b4.y);
+                            float2 v = __fadd2_rn(make_float2(__uint_as_float(raw[e]), __uint_as_float(raw[e + 1])), bs);
+                            v = epi.apply(v, ts);
+                            const __half2 h = __floats2half2_rn(v.x, v.y);
+                            hw[q] = *reinterpret_cast<const uint32_t*>(&h);
+                        }
+                        *reinterpret_cast<uint4*>(rrow + ((((c & 1) * 4 + j) ^ sw) << 4)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                    }
+                    if (c & 1) {                              // 64 columns complete for this warp: publish to the async proxy
+                        ptx::fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive(&out_ready[hf]);
+                        ++u;
+                    }
+                }
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync();
+    if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc_2cta(tmem_base, 512); }
+}
+
 // ---- column-split fused GEMM + LayerNorm: cluster of 4 = two CTA pairs ---------------------------------
 // The full-row kernels above fill all 512 TMEM columns with ONE tile, so MMA and LayerNorm epilogue of a CTA
 // serialise (measured: tensor pipe 6 % active).  Here a cluster of four CTAs owns a 256-row block: pair p

@@ -206,6 +206,19 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;                          // layout type SWIZZLE_128B
     return d;
 }
+// MN-major operand tile (the operand's M/N index is the contiguous one): blocks of 64 elements (128 B, 128-byte swizzle)
+// along MN are `lbo_bytes` apart, groups of 8 K-rows (8 x 128 B) are `sbo_bytes` apart -- the canonical layout
+// ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units.  Used for V in P V (V stays [key][dim], no transposed copy).
+__device__ __forceinline__ uint64_t make_smem_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+constexpr uint32_t IDESC_B_MN_MAJOR = 1u << 16;       // instruction-descriptor bit: B operand is MN-major
 // kind::f16 instruction descriptor: fp32 accumulate, bf16 A/B, both K-major, shape M x N (K = 16).
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
