@@ -251,6 +251,270 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_consta
     if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, 512); }
 }
 
+// ---- fp16-format attention, software-pipelined -------------------------------------------------------------
+// ncu on attention_tc_kernel<FMT_HALF> (8.4 us per item): softmax 48 %, transposing O epilogue 34 %, waiting for P V 16 %,
+// waiting for S 12 % -- the eight softmax/epilogue warps are the critical path and sit idle while the tensor core runs.
+// This kernel keeps the same per-item math but
+//   * double-buffers S in TMEM ([0,128) / [384,512)) and P in shared memory, so softmax(i+1) runs while P V(i) executes:
+//       MMA order  S(0) S(1) | PV(0) S(2) | PV(1) S(3) ...      (TMA ring order QK0 QK1 | V0 QK2 | V1 QK3 ...)
+//       warps      softmax(0) | softmax(1) Oepi(0) | softmax(2) Oepi(1) ...
+//   * softmax: invalid keys are masked per group of 8 (warp-uniform), exp via ex2.approx on packed fp32x2 arguments
+//     (a masked -inf logit gives exp = 0 without a select), tree reductions;
+//   * O epilogue in the accumulator's thread-per-row layout: fp16 rows into a 128B-swizzled staging box (one 16 KB box per
+//     column half, used twice per item), TMA-stored by an I/O warp -- no smem transposes, no STG.
+constexpr int ATT2_THREADS = ATT_THREADS + 32;           // + store I/O warp (role 10)
+constexpr int ATT2_SMEM_BYTES = ATT_RING_BYTES + 2 * 32768 /*P x2*/ + 32768 /*O staging*/ + ATT_PART_BYTES + 256;
+
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+__global__ void __launch_bounds__(ATT2_THREADS, 1)
+attention_half_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUtensorMap mK,
+                      const __grid_constant__ CUtensorMap mV /* 64-row boxes */, const __grid_constant__ CUtensorMap mO /* [M, H*256] fp16, 128-row x 64-col boxes */,
+                      int n_items, int n_head, int L) {
+    constexpr uint32_t IDESC_S = ptx::make_idesc_f16(128, 128);
+    constexpr uint32_t IDESC_O = ptx::make_idesc_f16(128, 256) | ptx::IDESC_B_MN_MAJOR;
+    constexpr int STAGE = 32768, STAGES = ATT_RING_BYTES / STAGE;           // 4
+    constexpr uint32_t TM_O = 128;
+    extern __shared__ __align__(1024) uint8_t smem_att2[];
+    uint8_t* smem = smem_att2;
+    uint8_t* p_smem = smem + ATT_RING_BYTES;             // P[2]: [2 key blocks][128 rows][128 B] each
+    uint8_t* o_smem = p_smem + 2 * 32768;                // O staging: one [128 rows][64 cols] fp16 box per column half
+    float* part = reinterpret_cast<float*>(o_smem + 32768);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(part) + ATT_PART_BYTES);
+    uint64_t* full_bar = bars;          // [4]
+    uint64_t* empty_bar = bars + 4;     // [4]
+    uint64_t* s_full = bars + 8;        // [2] S buffer ready (MMA -> softmax)
+    uint64_t* p_ready = bars + 10;      // [2] P buffer written and S buffer drained (softmax -> MMA), 256 arrivals
+    uint64_t* o_full = bars + 12;       // O accumulator ready (MMA -> epilogue)
+    uint64_t* o_free = bars + 13;       // O drained (epilogue -> MMA), 8 arrivals
+    uint64_t* out_ready = bars + 14;    // [2 column halves] staging box written by its 4 warps
+    uint64_t* box_free = bars + 16;     // [2] store has finished reading the box
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+
+    const int lane = threadIdx.x % 32;
+    const int hw_warp = threadIdx.x / 32;               // hardware warps 0..7 = softmax/epilogue roles 2..9; 8, 9, 10 = roles 0, 1, 10
+    const int warp = hw_warp < 8 ? hw_warp + 2 : (hw_warp == 10 ? 10 : hw_warp - 8);
+    if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();   // swizzled tiles need the declared 1024-byte alignment
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&mQ); ptx::prefetch_tmap(&mK); ptx::prefetch_tmap(&mV); ptx::prefetch_tmap(&mO);
+        for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+        for (int b = 0; b < 2; ++b) {
+            ptx::mbar_init(&s_full[b], 1); ptx::mbar_init(&p_ready[b], 256);
+            ptx::mbar_init(&out_ready[b], 4); ptx::mbar_init(&box_free[b], 1);
+        }
+        ptx::mbar_init(o_full, 1); ptx::mbar_init(o_free, 8);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) { ptx::tmem_alloc(tmem_slot, 512); ptx::tmem_relinquish(); }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int n_mine = blockIdx.x < n_items ? (n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;   // items of this CTA
+    auto item_of = [&](int j) { return (int)blockIdx.x + j * (int)gridDim.x; };
+
+    if (warp == 0) {
+        if (lane == 0) {                                   // ===== TMA producer: QK(0) QK(1) | V(0) QK(2) | V(1) QK(3) ... =====
+            int s = 0; uint32_t ph = 0;
+            auto load_qk = [&](int item) {
+                for (int kb = 0; kb < 4; ++kb) {
+                    ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+                    uint8_t* st = smem + s * STAGE;
+                    ptx::mbar_arrive_expect_tx(&full_bar[s], STAGE);
+                    ptx::tma_load_2d(st, &mQ, &full_bar[s], kb * 64, item * 128);
+                    ptx::tma_load_2d(st + 16384, &mK, &full_bar[s], kb * 64, item * 128);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+            };
+            auto load_v = [&](int item) {
+                for (int kb = 0; kb < 2; ++kb) {
+                    ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+                    uint8_t* st = smem + s * STAGE;
+                    ptx::mbar_arrive_expect_tx(&full_bar[s], STAGE);
+#pragma unroll
+                    for (int db = 0; db < 4; ++db) ptx::tma_load_2d(st + db * 8192, &mV, &full_bar[s], db * 64, item * 128 + kb * 64);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+            };
+            if (n_mine > 0) load_qk(item_of(0));
+            if (n_mine > 1) load_qk(item_of(1));
+            for (int j = 0; j < n_mine; ++j) {
+                load_v(item_of(j));
+                if (j + 2 < n_mine) load_qk(item_of(j + 2));
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                                   // ===== MMA issuer =====
+            int s = 0; uint32_t ph = 0;
+            const uint32_t p_addr = ptx::smem_u32(p_smem);
+            auto issue_S = [&](int j) {
+                const uint32_t tm_s = tmem_base + ((j & 1) ? 384u : 0u);
+                for (int kb = 0; kb < 4; ++kb) {
+                    ptx::mbar_wait(&full_bar[s], ph);
+                    ptx::tc_fence_after();
+                    const uint32_t st = ptx::smem_u32(smem + s * STAGE);
+                    const uint64_t dQ = ptx::make_smem_desc_sw128(st), dK = ptx::make_smem_desc_sw128(st + 16384);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        ptx::umma_f16(tm_s, dQ + (uint64_t)(kk * 2), dK + (uint64_t)(kk * 2), IDESC_S, (kb | kk) != 0);
+                    ptx::umma_commit(&empty_bar[s]);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+                ptx::umma_commit(&s_full[j & 1]);
+            };
+            if (n_mine > 0) issue_S(0);
+            if (n_mine > 1) issue_S(1);
+            for (int j = 0; j < n_mine; ++j) {
+                ptx::mbar_wait(&p_ready[j & 1], (j >> 1) & 1);   // P(j) in smem, S buffer j&1 drained
+                ptx::mbar_wait(o_free, (j & 1) ^ 1);             // O of item j-1 drained
+                ptx::tc_fence_after();
+                for (int kb = 0; kb < 2; ++kb) {
+                    ptx::mbar_wait(&full_bar[s], ph);
+                    ptx::tc_fence_after();
+                    const uint32_t st = ptx::smem_u32(smem + s * STAGE);
+                    const uint64_t dV = ptx::make_smem_desc_mn_sw128(st, 8192, 1024);
+                    const uint64_t dP = ptx::make_smem_desc_sw128(p_addr + (j & 1) * 32768 + kb * 16384);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        ptx::umma_f16(tmem_base + TM_O, dP + (uint64_t)(kk * 2), dV + (uint64_t)(kk * 128), IDESC_O, (kb | kk) != 0);
+                    ptx::umma_commit(&empty_bar[s]);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+                ptx::umma_commit(o_full);
+                if (j + 2 < n_mine) issue_S(j + 2);
+            }
+        }
+    } else if (warp == 10) {
+        if (lane == 0) {                                   // ===== store I/O =====
+            uint32_t u = 0;
+            for (int j = 0; j < n_mine; ++j) {
+                const int item = item_of(j), w = item / n_head, h = item % n_head;
+#pragma unroll 1
+                for (int half = 0; half < 2; ++half, ++u) {
+#pragma unroll 1
+                    for (int hf = 0; hf < 2; ++hf) {
+                        ptx::mbar_wait(&out_ready[hf], u & 1);
+                        ptx::tma_store_2d(&mO, o_smem + hf * 16384, h * 256 + hf * 128 + half * 64, w * LP);
+                        ptx::tma_store_commit();
+                        ptx::tma_store_wait_read();
+                        ptx::mbar_arrive(&box_free[hf]);
+                    }
+                }
+            }
+            ptx::tma_store_wait_all();
+        }
+    } else {                                               // ===== softmax + epilogue warps 2..9 =====
+        const int quarter = (warp - 2) & 3, hf = (warp - 2) >> 2;  // TMEM lane quarter, key / output-column half
+        const int r = quarter * 32 + lane;                 // query row = TMEM lane
+        const int sw = r & 7;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        const int k0 = hf * 64;
+        const int nvalid = L - k0 < 0 ? 0 : (L - k0 > 64 ? 64 : L - k0);     // valid keys of this warp's 64 (warp-uniform)
+        const float kLog2e = 1.4426950408889634f;
+        auto softmax = [&](int j) {
+            const int b = j & 1;
+            ptx::mbar_wait(&s_full[b], (j >> 1) & 1);
+            ptx::tc_fence_after();
+            float2 v[32];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t raw[32];
+                ptx::tmem_ld_32x32(lane_addr + (b ? 384u : 0u) + hf * 64 + c * 32, raw);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int q = 0; q < 16; ++q) v[c * 16 + q] = make_float2(__uint_as_float(raw[2 * q]), __uint_as_float(raw[2 * q + 1]));
+            }
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {                  // mask invalid keys, one warp-uniform decision per group of 8
+                if (g * 8 + 8 > nvalid) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (g * 8 + 2 * q >= nvalid) v[g * 4 + q].x = -INFINITY;
+                        if (g * 8 + 2 * q + 1 >= nvalid) v[g * 4 + q].y = -INFINITY;
+                    }
+                }
+            }
+            float m8[8];
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+                m8[g] = fmaxf(fmaxf(fmaxf(v[g * 4].x, v[g * 4].y), fmaxf(v[g * 4 + 1].x, v[g * 4 + 1].y)),
+                              fmaxf(fmaxf(v[g * 4 + 2].x, v[g * 4 + 2].y), fmaxf(v[g * 4 + 3].x, v[g * 4 + 3].y)));
+            float mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
+            part[hf * 128 + r] = mx;
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+            mx = fmaxf(part[r], part[128 + r]);            // key 0 is always valid, so the row max is finite
+            const float2 l2 = make_float2(kLog2e, kLog2e), c2 = make_float2(-mx * kLog2e, -mx * kLog2e);
+            float2 acc[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+                const float2 a = __ffma2_rn(v[q], l2, c2);                  // (s - max) * log2(e); -inf stays -inf -> exp = 0
+                v[q] = make_float2(ex2_approx(a.x), ex2_approx(a.y));
+                acc[q & 3] = __fadd2_rn(acc[q & 3], v[q]);
+            }
+            const float2 t2 = __fadd2_rn(__fadd2_rn(acc[0], acc[1]), __fadd2_rn(acc[2], acc[3]));
+            part[256 + hf * 128 + r] = t2.x + t2.y;
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+            const float inv = 1.0f / (part[256 + r] + part[256 + 128 + r]);
+            const float2 i2 = make_float2(inv, inv);
+            uint8_t* prow = p_smem + b * 32768 + hf * 16384 + r * 128;      // key block hf of P[b], row r
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+                uint32_t hw[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float2 pv = __fmul2_rn(v[jj * 4 + q], i2);
+                    const __half2 hh = __floats2half2_rn(pv.x, pv.y);
+                    hw[q] = *reinterpret_cast<const uint32_t*>(&hh);
+                }
+                *reinterpret_cast<uint4*>(prow + ((jj ^ sw) << 4)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            }
+            ptx::fence_proxy_async();                      // generic-proxy smem writes -> visible to the tensor core
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(&p_ready[b]);
+        };
+        uint32_t u = 0;
+        uint8_t* orow = o_smem + hf * 16384 + r * 128;
+        if (n_mine > 0) softmax(0);
+        for (int j = 0; j < n_mine; ++j) {
+            if (j + 1 < n_mine) softmax(j + 1);            // overlaps P V(j) on the tensor core
+            ptx::mbar_wait(o_full, j & 1);
+            ptx::tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {                  // this warp's 128 output columns, 32 at a time
+                uint32_t raw[32];
+                ptx::tmem_ld_32x32(lane_addr + TM_O + hf * 128 + c * 32, raw);
+                if ((c & 1) == 0) ptx::mbar_wait(&box_free[hf], (u & 1) ^ 1);
+                ptx::tmem_ld_wait();
+                if (c == 3) {                              // O drained: the next P V may overwrite it
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(o_free);
+                }
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    uint32_t hw[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const __half2 hh = __floats2half2_rn(__uint_as_float(raw[jj * 8 + 2 * q]), __uint_as_float(raw[jj * 8 + 2 * q + 1]));
+                        hw[q] = *reinterpret_cast<const uint32_t*>(&hh);
+                    }
+                    *reinterpret_cast<uint4*>(orow + ((((c & 1) * 4 + jj) ^ sw) << 4)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                }
+                if (c & 1) {
+                    ptx::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&out_ready[hf]);
+                    ++u;
+                }
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, 512); }
+}
+
 // QKV projection epilogue writing the attention operand planes directly (one 256-wide tile = one (section, head));
 // all three sections share the layout [(w*H+h)*128 + l][256].
 template <int FMT>

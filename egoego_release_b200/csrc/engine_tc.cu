@@ -108,6 +108,7 @@ struct TcImpl {
     Plane Qp, Kp, VT;                           // attention operand planes (see attn_tcgen05.cuh); VT = V in [key][dim] layout, 64-row TMA boxes
     bool fuse_ln = true;                        // EGOEGO_FUSE_LN=0 keeps GEMM + LayerNorm separate in the fp16 format too
     bool attn_tc = true;                        // EGOEGO_ATTN=simt selects the fp32 CUDA-core attention (bisecting)
+    bool attn_v2 = true;                        // fp16 steps: software-pipelined attention_half_kernel (EGOEGO_ATTN=v1: attention_tc_kernel<FMT_HALF>)
     int ln4_clusters = 0;                       // co-resident clusters of 4 for gemm_ln_half_c4_kernel (0 = use the full-row pair kernel)
     float *base = nullptr, *H = nullptr, *Y = nullptr, *QKV = nullptr;
     ~TcImpl() {
@@ -339,6 +340,8 @@ int TcEngine::init(const TcWeights& w, cudaStream_t) {
             I->VT.alloc(MBe * H * 128, 256, 64)) return 1;
         EG_CUDA(cudaFuncSetAttribute(attention_tc_kernel<FMT_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
         EG_CUDA(cudaFuncSetAttribute(attention_tc_kernel<FMT_HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+        EG_CUDA(cudaFuncSetAttribute(attention_half_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT2_SMEM_BYTES));
+        I->attn_v2 = !(am && strcmp(am, "v1") == 0);
     } else {
         EG_CUDA(cudaMalloc(&I->QKV, M * 3 * H * dk * 4));
         EG_CUDA(cudaFuncSetAttribute(attention_simt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SIMT_SMEM));
@@ -452,8 +455,12 @@ static int denoiser_impl(TcImpl* I, int B, int T, TSrc ts, const float* pmask, f
             }
             if (on(2, l)) {
                 const int items = B * H;
-                attention_tc_kernel<FMT><<<items < I->sms ? items : I->sms, ATT_THREADS, ATT_SMEM_BYTES, s>>>(
-                    I->Qp.mhi, I->Qp.mlo, I->Kp.mhi, I->Kp.mlo, I->VT.mhi, I->VT.mlo, I->O.hi, I->O.lo, H * dk, items, H, L);
+                if (FMT == FMT_HALF && I->attn_v2)
+                    attention_half_kernel<<<items < I->sms ? items : I->sms, ATT2_THREADS, ATT2_SMEM_BYTES, s>>>(
+                        I->Qp.m16, I->Kp.m16, I->VT.m16, I->O.m16_128, items, H, L);
+                else
+                    attention_tc_kernel<FMT><<<items < I->sms ? items : I->sms, ATT_THREADS, ATT_SMEM_BYTES, s>>>(
+                        I->Qp.mhi, I->Qp.mlo, I->Kp.mhi, I->Kp.mlo, I->VT.mhi, I->VT.mlo, I->O.hi, I->O.lo, H * dk, items, H, L);
             }
         } else {
             if (on(1, l)) {
