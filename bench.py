@@ -32,10 +32,10 @@ KERNEL_BYTES = {"start": 120 * 198 * 2 + 121 * 512 * 4 + _ROW, "qkv": _ROW + 6 *
                 "ddpm_update": 3 * 120 * 198 * 4 + 120 * 198 * 2}
 KERNEL_LAUNCHES = {"start": 1, "qkv": 4, "attention": 4, "fc_ln": 4, "w1": 4, "w2_ln": 4, "out": 1, "ddpm_update": 1}
 KERNEL_NAMES = {"start": "gemm_split3_2cta_kernel<TcEpiStart> (x half of start_conv)",
-                "qkv": "gemm_split3_2cta_kernel<TcEpiQKVPlanes> (fused QKV projection)",
-                "attention": "attention_tc_kernel (QK^T, softmax, PV)",
+                "qkv": "gemm_half_tma_2cta_kernel<TmaEpiQKV> (fused QKV projection, TMA-store epilogue)",
+                "attention": "attention_half_kernel (QK^T, softmax, PV; software-pipelined)",
                 "fc_ln": "gemm_ln_half_c4_kernel (attention fc + residual + LayerNorm)",
-                "w1": "gemm_split3_2cta_kernel<TcEpiBiasReluSplit> (FFN w_1 + ReLU)",
+                "w1": "gemm_half_tma_2cta_kernel<TmaEpiRelu> (FFN w_1 + ReLU)",
                 "w2_ln": "gemm_ln_half_c4_kernel (FFN w_2 + residual + LayerNorm)",
                 "out": "gemm_split3_2cta_kernel<TcEpiOut> (linear_out)", "ddpm_update": "ddpm_update_kernel"}
 

@@ -89,6 +89,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_consta
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ptx::grid_dep_launch();
+    ptx::grid_dep_wait();                                // prologue above overlaps the previous kernel's tail (PDL)
 
     if (warp == 0) {
         if (lane == 0) {                                   // ===== TMA producer =====
@@ -311,6 +313,8 @@ attention_half_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_const
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ptx::grid_dep_launch();
+    ptx::grid_dep_wait();                                // prologue above overlaps the previous kernel's tail (PDL)
     const int n_mine = blockIdx.x < n_items ? (n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;   // items of this CTA
     auto item_of = [&](int j) { return (int)blockIdx.x + j * (int)gridDim.x; };
 

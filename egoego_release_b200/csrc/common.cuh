@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <cstdlib>
 #include <string>
 #include <vector>
 #include <map>
@@ -30,6 +31,35 @@ void set_error(const std::string& msg);
              ::egoego::set_error(std::string(#call) + ": " + cudaGetErrorString(_e) + \
                                  " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"); \
              return 1; } } while (0)
+
+// Launch configuration with optional thread-block cluster and programmatic dependent launch (PDL, see tc_ptx.cuh).
+// PDL is on for every kernel of the sampling step unless EGOEGO_PDL=0.
+inline bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("EGOEGO_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
+struct LaunchCfg {
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute at[2];
+    LaunchCfg(unsigned grid, unsigned block, size_t smem, cudaStream_t s, int cluster = 1, bool pdl = true) {
+        cfg = cudaLaunchConfig_t{};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+        int n = 0;
+        if (cluster > 1) {
+            at[n].id = cudaLaunchAttributeClusterDimension;
+            at[n].val.clusterDim.x = cluster; at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = 1;
+            ++n;
+        }
+        if (pdl && pdl_enabled()) {
+            at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[n].val.programmaticStreamSerializationAllowed = 1;
+            ++n;
+        }
+        cfg.attrs = at; cfg.numAttrs = n;
+    }
+    LaunchCfg(const LaunchCfg&) = delete;
+};
 
 // ---------------------------------------------------------------------------------------------
 // Which diffusion step a window is at.  Loop mode: t = t_start - *d_step (device counter advanced

@@ -505,8 +505,9 @@ static int sample_chunk(egoego_ctx* c, const float* x_start, const float* cond_m
     auto one_step = [&](cudaStream_t st, int fmt) -> int {
         a.stage_mode = (c->cfg.engine == EGOEGO_ENGINE_SIMT) ? 2 : (fmt ? 1 : 0);
         if (run_denoiser(c, Bc, T, ts, nullptr, st, fmt)) return 1;
-        ddpm_update_kernel<<<grid1d(quads, 256), 256, 0, st>>>(a);
-        advance_step_kernel<<<1, 32, 0, st>>>(d_step);
+        LaunchCfg ld((unsigned)((quads + 255) / 256), 256, 0, st), la(1, 32, 0, st);
+        EG_CUDA(cudaLaunchKernelEx(&ld.cfg, ddpm_update_kernel, a));
+        EG_CUDA(cudaLaunchKernelEx(&la.cfg, advance_step_kernel, d_step));
         c->launches += 2;
         EG_CUDA(cudaGetLastError());
         return 0;

@@ -132,9 +132,9 @@ static int launch_gemm(TcImpl* I, const Plane& A, const Plane& W, int M, int N, 
     EG_CHECK(M % GEMM_BM == 0 && N % BN == 0 && K % GEMM_BK == 0, "gemm shape not tile-aligned");
     const int tiles = (M / GEMM_BM) * (N / BN);
     const int grid = tiles < I->sms ? tiles : I->sms;
-    if (FMT == FMT_SPLIT) kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(A.mhi, A.mlo, W.mhi, W.mlo, M, N, K, epi);
-    else                  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(A.m16, A.m16, W.m16, W.m16, M, N, K, epi);
-    EG_CUDA(cudaGetLastError());
+    LaunchCfg lc(grid, GEMM_THREADS, Cfg::SMEM_BYTES, s);
+    if (FMT == FMT_SPLIT) { EG_CUDA(cudaLaunchKernelEx(&lc.cfg, kern, A.mhi, A.mlo, W.mhi, W.mlo, M, N, K, epi)); }
+    else                  { EG_CUDA(cudaLaunchKernelEx(&lc.cfg, kern, A.m16, A.m16, W.m16, W.m16, M, N, K, epi)); }
     return 0;
 }
 
@@ -158,14 +158,9 @@ static int launch_gemm_2cta(TcImpl* I, const Plane& A, const Plane& W, int M, in
     const int tiles = (M / 256) * (N / 256);
     int pairs = I->sms / 2;
     if (tiles < pairs) pairs = tiles;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = GEMM2_SMEM_BYTES; cfg.stream = s;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    if (FMT == FMT_SPLIT) { EG_CUDA(cudaLaunchKernelEx(&cfg, kern, A.mhi, A.mlo, W.mhi128, W.mlo128, M, N, K, epi)); }
-    else                  { EG_CUDA(cudaLaunchKernelEx(&cfg, kern, A.m16, A.m16, W.m16_128, W.m16_128, M, N, K, epi)); }
+    LaunchCfg lc(2 * pairs, GEMM_THREADS, GEMM2_SMEM_BYTES, s, 2);
+    if (FMT == FMT_SPLIT) { EG_CUDA(cudaLaunchKernelEx(&lc.cfg, kern, A.mhi, A.mlo, W.mhi128, W.mlo128, M, N, K, epi)); }
+    else                  { EG_CUDA(cudaLaunchKernelEx(&lc.cfg, kern, A.m16, A.m16, W.m16_128, W.m16_128, M, N, K, epi)); }
     return 0;
 }
 
@@ -184,13 +179,8 @@ static int launch_gemm_ares(TcImpl* I, const Plane& A, const Plane& W, int M, in
     const int items = (M / 256) * ((N / 256) / G);
     int pairs = I->sms / 2;
     if (items < pairs) pairs = items;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = s;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    EG_CUDA(cudaLaunchKernelEx(&cfg, kern, A.m16, W.m16_128, M, N, epi));
+    LaunchCfg lc(2 * pairs, GEMM_THREADS, Cfg::SMEM_BYTES, s, 2);
+    EG_CUDA(cudaLaunchKernelEx(&lc.cfg, kern, A.m16, W.m16_128, M, N, epi));
     return 0;
 }
 
@@ -213,13 +203,8 @@ static int launch_gemm_tma_epi(TcImpl* I, const Plane& A, const Plane& W, int M,
     const int tiles = (M / 256) * (N / 256);
     int pairs = I->sms / 2;
     if (tiles < pairs) pairs = tiles;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(GEMM_TMAEPI_THREADS); cfg.dynamicSmemBytes = GemmTmaEpiCfg::SMEM_BYTES; cfg.stream = s;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    EG_CUDA(cudaLaunchKernelEx(&cfg, kern, A.m16, W.m16_128, M, N, K, bias, epi));
+    LaunchCfg lc(2 * pairs, GEMM_TMAEPI_THREADS, GemmTmaEpiCfg::SMEM_BYTES, s, 2);
+    EG_CUDA(cudaLaunchKernelEx(&lc.cfg, kern, A.m16, W.m16_128, M, N, K, bias, epi));
     return 0;
 }
 
@@ -240,13 +225,8 @@ static int launch_gemm_ares_tma(TcImpl* I, const Plane& A, const Plane& W, int M
     const int items = (M / 256) * ((N / 256) / G);
     int pairs = I->sms / 2;
     if (items < pairs) pairs = items;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(GEMM_TMAEPI_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = s;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    EG_CUDA(cudaLaunchKernelEx(&cfg, kern, A.m16, W.m16_128, M, N, bias, epi));
+    LaunchCfg lc(2 * pairs, GEMM_TMAEPI_THREADS, Cfg::SMEM_BYTES, s, 2);
+    EG_CUDA(cudaLaunchKernelEx(&lc.cfg, kern, A.m16, W.m16_128, M, N, bias, epi));
     return 0;
 }
 static bool use_ares_tma() {
@@ -392,32 +372,21 @@ static int launch_gemm_ln(TcImpl* I, const Plane& A, const Plane& W, int M, int 
     if (I->ln4_clusters > 0 && M % 256 == 0) {
         const int tiles = M / 256;
         const int clusters = tiles < I->ln4_clusters ? tiles : I->ln4_clusters;
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(4 * clusters); cfg.blockDim = dim3(GEMM_LN4_THREADS); cfg.dynamicSmemBytes = GemmLn4Cfg::SMEM_BYTES; cfg.stream = s;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        EG_CUDA(cudaLaunchKernelEx(&cfg, gemm_ln_half_c4_kernel, A.m16_128, W.m16_128, I->Hs.m16_128, M, K, bias, g, b));
+        LaunchCfg lc(4 * clusters, GEMM_LN4_THREADS, GemmLn4Cfg::SMEM_BYTES, s, 4);
+        EG_CUDA(cudaLaunchKernelEx(&lc.cfg, gemm_ln_half_c4_kernel, A.m16_128, W.m16_128, I->Hs.m16_128, M, K, bias, g, b));
         return 0;
     }
     if (use_2cta() && M % 256 == 0) {
         const int tiles = M / 256;
         int pairs = I->sms / 2;
         if (tiles < pairs) pairs = tiles;
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = GemmLn2Cfg::SMEM_BYTES; cfg.stream = s;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        EG_CUDA(cudaLaunchKernelEx(&cfg, gemm_ln_half_2cta_kernel, A.m16, W.m16_128, M, K, bias, g, b, (const __nv_bfloat16*)I->Hs.h16, I->Hs.h16));
+        LaunchCfg lc(2 * pairs, GEMM_THREADS, GemmLn2Cfg::SMEM_BYTES, s, 2);
+        EG_CUDA(cudaLaunchKernelEx(&lc.cfg, gemm_ln_half_2cta_kernel, A.m16, W.m16_128, M, K, bias, g, b, (const __nv_bfloat16*)I->Hs.h16, I->Hs.h16));
         return 0;
     }
     const int tiles = M / GEMM_BM;
-    gemm_ln_half_kernel<<<tiles < I->sms ? tiles : I->sms, GEMM_THREADS, GemmLnCfg::SMEM_BYTES, s>>>(
-        A.m16, W.m16, M, K, bias, g, b, (const __nv_bfloat16*)I->Hs.h16, I->Hs.h16);
-    EG_CUDA(cudaGetLastError());
+    LaunchCfg lc(tiles < I->sms ? tiles : I->sms, GEMM_THREADS, GemmLnCfg::SMEM_BYTES, s);
+    EG_CUDA(cudaLaunchKernelEx(&lc.cfg, gemm_ln_half_kernel, A.m16, W.m16, M, K, bias, g, b, (const __nv_bfloat16*)I->Hs.h16, I->Hs.h16));
     return 0;
 }
 
@@ -455,12 +424,14 @@ static int denoiser_impl(TcImpl* I, int B, int T, TSrc ts, const float* pmask, f
             }
             if (on(2, l)) {
                 const int items = B * H;
-                if (FMT == FMT_HALF && I->attn_v2)
-                    attention_half_kernel<<<items < I->sms ? items : I->sms, ATT2_THREADS, ATT2_SMEM_BYTES, s>>>(
-                        I->Qp.m16, I->Kp.m16, I->VT.m16, I->O.m16_128, items, H, L);
-                else
-                    attention_tc_kernel<FMT><<<items < I->sms ? items : I->sms, ATT_THREADS, ATT_SMEM_BYTES, s>>>(
-                        I->Qp.mhi, I->Qp.mlo, I->Kp.mhi, I->Kp.mlo, I->VT.mhi, I->VT.mlo, I->O.hi, I->O.lo, H * dk, items, H, L);
+                if (FMT == FMT_HALF && I->attn_v2) {
+                    LaunchCfg lc(items < I->sms ? items : I->sms, ATT2_THREADS, ATT2_SMEM_BYTES, s);
+                    EG_CUDA(cudaLaunchKernelEx(&lc.cfg, attention_half_kernel, I->Qp.m16, I->Kp.m16, I->VT.m16, I->O.m16_128, items, H, L));
+                } else {
+                    LaunchCfg lc(items < I->sms ? items : I->sms, ATT_THREADS, ATT_SMEM_BYTES, s);
+                    EG_CUDA(cudaLaunchKernelEx(&lc.cfg, attention_tc_kernel<FMT>, I->Qp.mhi, I->Qp.mlo, I->Kp.mhi, I->Kp.mlo, I->VT.mhi, I->VT.mlo,
+                                               I->O.hi, I->O.lo, H * dk, items, H, L));
+                }
             }
         } else {
             if (on(1, l)) {
@@ -476,7 +447,8 @@ static int denoiser_impl(TcImpl* I, int B, int T, TSrc ts, const float* pmask, f
             } else {
                 TcEpiBiasResidF32 ef{{}, I->Y, d, W.fc_b, I->H};
                 if (gemm<FMT>(I, I->O, W.fc, Mg, d, H * dk, ef, s)) return 1;
-                layernorm512_kernel<<<M / 8, 256, 0, s>>>(I->Y, I->H, I->Hs.hi, I->Hs.lo, W.ln1_g, W.ln1_b, pmask, T, M, half);
+                LaunchCfg ll(M / 8, 256, 0, s);
+                EG_CUDA(cudaLaunchKernelEx(&ll.cfg, layernorm512_kernel, (const float*)I->Y, I->H, I->Hs.hi, I->Hs.lo, W.ln1_g, W.ln1_b, pmask, T, M, half));
             }
         }
         if (on(4, l)) {
@@ -494,7 +466,8 @@ static int denoiser_impl(TcImpl* I, int B, int T, TSrc ts, const float* pmask, f
             } else {
                 TcEpiBiasResidF32 e2{{}, I->Y, d, W.b2, I->H};
                 if (gemm<FMT>(I, I->F, W.w2, Mg, d, d, e2, s)) return 1;
-                layernorm512_kernel<<<M / 8, 256, 0, s>>>(I->Y, I->H, I->Hs.hi, I->Hs.lo, W.ln2_g, W.ln2_b, pmask, T, M, half);
+                LaunchCfg ll(M / 8, 256, 0, s);
+                EG_CUDA(cudaLaunchKernelEx(&ll.cfg, layernorm512_kernel, (const float*)I->Y, I->H, I->Hs.hi, I->Hs.lo, W.ln2_g, W.ln2_b, pmask, T, M, half));
             }
         }
     }

@@ -308,6 +308,8 @@ gemm_split3_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constan
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ptx::grid_dep_launch();
+    ptx::grid_dep_wait();                                // prologue above overlaps the previous kernel's tail (PDL)
 
     if (warp == 0) {
         if (lane == 0) {                                 // ===== TMA producer =====
@@ -439,6 +441,8 @@ gemm_split3_2cta_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_co
     ptx::cluster_sync();                                 // peer's barriers are initialised before any remote arrive
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ptx::grid_dep_launch();
+    ptx::grid_dep_wait();                                // prologue above overlaps the previous kernel's tail (PDL)
 
     if (warp == 0) {
         if (lane == 0) {                                 // ===== TMA producer (both CTAs) =====
@@ -575,6 +579,8 @@ gemm_ares_half_2cta_kernel(const __grid_constant__ CUtensorMap mA, const __grid_
     ptx::cluster_sync();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ptx::grid_dep_launch();
+    ptx::grid_dep_wait();                                // prologue above overlaps the previous kernel's tail (PDL)
 
     if (warp == 0) {
         if (lane == 0) {                                 // ===== TMA producer (both CTAs) =====
@@ -811,6 +817,8 @@ gemm_ln_half_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constan
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ptx::grid_dep_launch();
+    ptx::grid_dep_wait();                                // prologue above overlaps the previous kernel's tail (PDL)
 
     if (warp == 0) {
         if (lane == 0) {                                 // ===== TMA producer =====
@@ -920,6 +928,8 @@ gemm_ln_half_2cta_kernel(const __grid_constant__ CUtensorMap mA, const __grid_co
     ptx::cluster_sync();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ptx::grid_dep_launch();
+    ptx::grid_dep_wait();                                // prologue above overlaps the previous kernel's tail (PDL)
 
     if (warp == 0) {
         if (lane == 0) {                                 // ===== TMA producer (both CTAs) =====
@@ -1042,6 +1052,8 @@ gemm_half_tma_2cta_kernel(const __grid_constant__ CUtensorMap mA, const __grid_c
     ptx::cluster_sync();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ptx::grid_dep_launch();
+    ptx::grid_dep_wait();                                // prologue above overlaps the previous kernel's tail (PDL)
 
     if (warp == 0) {
         if (lane == 0) {                                 // ===== TMA producer (both CTAs) =====
@@ -1243,6 +1255,8 @@ gemm_ares_tma_2cta_kernel(const __grid_constant__ CUtensorMap mA, const __grid_c
     ptx::cluster_sync();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ptx::grid_dep_launch();
+    ptx::grid_dep_wait();                                // prologue above overlaps the previous kernel's tail (PDL)
 
     if (warp == 0) {
         if (lane == 0) {                                 // ===== TMA producer (both CTAs) =====
@@ -1465,6 +1479,8 @@ gemm_ln_half_c4_kernel(const __grid_constant__ CUtensorMap mA, const __grid_cons
     ptx::cluster_sync();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ptx::grid_dep_launch();
+    ptx::grid_dep_wait();                                // prologue above overlaps the previous kernel's tail (PDL)
 
     if (warp == 0) {
         if (lane == 0) {                                 // ===== TMA producer (every CTA) =====

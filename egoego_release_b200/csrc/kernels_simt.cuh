@@ -270,6 +270,8 @@ static __global__ void __launch_bounds__(256) layernorm512_kernel(const float* _
                                                            const float* __restrict__ beta,
                                                            const float* __restrict__ row_mask, int T, int M,
                                                            int half_fmt /* 1: write one fp16 plane into Hhi */) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");          // PDL (no-op without the launch attribute)
     const int row = blockIdx.x * 8 + threadIdx.x / 32, lane = threadIdx.x % 32;
     if (row >= M) return;
     const float4* y4 = reinterpret_cast<const float4*>(Y + (long long)row * 512);
@@ -438,6 +440,8 @@ struct DdpmArgs {
 };
 
 static __global__ void ddpm_update_kernel(DdpmArgs a) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");          // PDL: everything below reads the previous kernel's output
     const long long epw = (long long)a.T * a.D;
     const long long quads_pw = (epw + 3) / 4;
     long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -504,6 +508,10 @@ static __global__ void ddpm_update_kernel(DdpmArgs a) {
     if (vec) *reinterpret_cast<float4*>(a.x_out + i0) = make_float4(v[0], v[1], v[2], v[3]);
 }
 
-static __global__ void advance_step_kernel(int* d_step) { if (threadIdx.x == 0 && blockIdx.x == 0) (*d_step)++; }
+static __global__ void advance_step_kernel(int* d_step) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (threadIdx.x == 0 && blockIdx.x == 0) (*d_step)++;
+}
 
 }  // namespace egoego

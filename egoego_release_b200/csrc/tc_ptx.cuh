@@ -41,6 +41,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// ---- programmatic dependent launch ------------------------------------------------------------------
+// Kernels of the sampling step are launched with cudaLaunchAttributeProgrammaticStreamSerialization: a kernel's CTAs may
+// become resident and run their prologue (barrier init, TMEM allocation, tensor-map prefetch, constant loads) while the
+// previous kernel drains.  grid_dep_wait() blocks until the previous kernel has completed and its writes are visible; it must
+// precede every access to data another kernel of the stream produces or still reads.  Without the launch attribute both are no-ops.
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- TMA ----------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
