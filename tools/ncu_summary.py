@@ -8,6 +8,7 @@ KEYS = [
     "gpu__time_duration.sum", "sm__cycles_elapsed.max", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
     "launch__shared_mem_per_block_dynamic",
     "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg", "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
     "sm__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__compute_memory_throughput.avg.pct_of_peak_sustained_elapsed",
     "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
     "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
@@ -36,6 +37,12 @@ def main(path, title):
                     if v != "":
                         print(f"| {k} | {v} | {u} |")
                     break
+        try:   # tcgen05 issue time: the hmma sub-pipe counter sums the SM's 4 sub-partitions; the pct metric above does not track it
+            hm = float(d[[h for h in hdr if h.endswith("sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg")][0]][1].replace(",", ""))
+            cy = float(d[[h for h in hdr if h.endswith("sm__cycles_elapsed.max")][0]][1].replace(",", ""))
+            print(f"| derived: hmma sub-pipe active / (4 x elapsed cycles) | {hm / (4 * cy) * 100:.1f} | % |")
+        except Exception:
+            pass
         print()
 
 
