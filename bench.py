@@ -30,14 +30,14 @@ KERNEL_FLOPS = {"start": 24.330e6, "qkv": 380.633e6, "attention": 59.970e6, "fc_
 KERNEL_BYTES = {"start": 120 * 198 * 2 + 121 * 512 * 4 + _ROW, "qkv": _ROW + 6 * _ROW, "attention": 6 * _ROW + 2 * _ROW,
                 "fc_ln": 2 * _ROW + _ROW + _ROW, "w1": 2 * _ROW, "w2_ln": 3 * _ROW, "out": _ROW + 120 * 198 * 4,
                 "ddpm_update": 3 * 120 * 198 * 4 + 120 * 198 * 2}
-KERNEL_LAUNCHES = {"start": 1, "qkv": 4, "attention": 4, "fc_ln": 4, "w1": 4, "w2_ln": 4, "out": 1, "ddpm_update": 1}
 KERNEL_NAMES = {"start": "gemm_split3_2cta_kernel<TcEpiStart> (x half of start_conv)",
                 "qkv": "gemm_half_tma_2cta_kernel<TmaEpiQKV> (fused QKV projection, TMA-store epilogue)",
                 "attention": "attention_half_kernel (QK^T, softmax, PV; software-pipelined)",
                 "fc_ln": "gemm_ln_half_c4_kernel (attention fc + residual + LayerNorm)",
                 "w1": "gemm_half_tma_2cta_kernel<TmaEpiRelu> (FFN w_1 + ReLU)",
                 "w2_ln": "gemm_ln_half_c4_kernel (FFN w_2 + residual + LayerNorm)",
-                "out": "gemm_split3_2cta_kernel<TcEpiOut> (linear_out)", "ddpm_update": "ddpm_update_kernel"}
+                "out": "gemm_split3_2cta_kernel<TcEpiOutDdpm> (linear_out + fused DDPM update; TcEpiOut + ddpm_update_kernel if EGOEGO_FUSE_DDPM=0)",
+                "ddpm_update": "ddpm_update_kernel"}
 
 
 def parse():
@@ -351,9 +351,15 @@ def main():
         half = dom_fmt == "fp16_single"
         pk_burst, hbm = pk["bf16_tflops"], pk["hbm_gbs"]
         kernels = {}
+        fused_ddpm = m.launches_per_step("ddpm_update") == 0
         for name in m.KERNELS:
+            cnt = m.launches_per_step(name)
+            if cnt == 0:
+                continue
             kms = m.time_kernel(name, B, T, half, iters=20)
-            fl, by, cnt = KERNEL_FLOPS[name] * B, KERNEL_BYTES[name] * B, KERNEL_LAUNCHES[name]
+            fl, by = KERNEL_FLOPS[name] * B, KERNEL_BYTES[name] * B
+            if name == "out" and fused_ddpm:       # linear_out + DDPM update in one kernel: model_out never touches HBM
+                by = (_ROW + KERNEL_BYTES["ddpm_update"] - 120 * 198 * 4) * B
             t_tensor, t_hbm = fl / (pk_burst * 1e12), by / (hbm * 1e9)
             bound = "tensor" if t_tensor >= t_hbm else "hbm"
             ach = fl / (kms * 1e-3) / 1e12 if bound == "tensor" else by / (kms * 1e-3) / 1e9

@@ -11,7 +11,7 @@ EXPORTS = [
     "egoego_make_cosine_schedule", "egoego_commit_weights", "egoego_denoiser_forward", "egoego_p_sample_step",
     "egoego_sample", "egoego_sample_host", "egoego_set_skeleton", "egoego_postprocess", "egoego_fk_smpl",
     "egoego_canonicalize_head", "egoego_tail_condition", "egoego_launch_count", "egoego_selftest_gemm", "egoego_time_dominant_kernel", "egoego_time_kernel",
-    "egoego_precise_last_steps",
+    "egoego_precise_last_steps", "egoego_eval_metrics", "egoego_launches_per_step",
 ]
 
 ENGINE_TCGEN05, ENGINE_SIMT = 0, 1
@@ -64,7 +64,9 @@ def lib():
     L.egoego_time_dominant_kernel.argtypes = [vp, i32, i32, i32, vp, vp]
     L.egoego_time_kernel.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp]
     L.egoego_precise_last_steps.argtypes = [vp]
+    L.egoego_launches_per_step.argtypes = [vp, i32]
     L.egoego_tail_condition.argtypes = [vp, vp, vp, i32, i32, vp, vp]
+    L.egoego_eval_metrics.argtypes = [i32, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp]
     L.egoego_launch_count.argtypes = [vp]
     L.egoego_launch_count.restype = i64
     for name in EXPORTS:

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <cstdlib>
 #include <string>
@@ -84,6 +85,24 @@ struct NoiseSrc {
     unsigned long long seed;
     unsigned long long window_offset;
     __device__ __forceinline__ int draw() const { return draw_static + (d_step ? *d_step : 0); }
+};
+
+// One DDPM update (p_sample after the denoiser): arguments of ddpm_update_kernel and of the linear_out epilogue that fuses it.
+struct DdpmArgs {
+    const float* model_out;  // [B,T,D]
+    const float* x;          // [B,T,D]
+    float* x_out;            // [B,T,D] (may alias x)
+    const float* coef1; const float* coef2; const float* logvar;
+    const float* sqrt_recip; const float* sqrt_recipm1;
+    int objective;           // 0 pred_noise, 1 pred_x0
+    int clip;
+    const float* inpaint; int inpaint_len;
+    float* stage_f32; int stage_ld;                                  // SIMT engine A operand (nullable)
+    __nv_bfloat16* stage_hi; __nv_bfloat16* stage_lo; int stage_ld16; // tensor engine A operand (nullable)
+    __half* stage_h16;                                                // fp16 plane for FMT_HALF steps (nullable)
+    int stage_mode;          // tensor engine planes to write: 0 = bf16 hi/lo only, 1 = fp16 only, 2 = all (next step's format unknown)
+    TSrc ts; NoiseSrc ns;
+    int B, T, D;
 };
 
 __device__ __forceinline__ uint32_t mulhilo32(uint32_t a, uint32_t b, uint32_t* hi) {

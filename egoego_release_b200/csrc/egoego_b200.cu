@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "kernels_simt.cuh"
 #include "postprocess.cuh"
+#include "metrics.cuh"
 #include "engine_tc.cuh"
 
 namespace egoego {
@@ -62,6 +63,8 @@ struct egoego_ctx {
     int graph_B = -1, graph_T = -1; const void* graph_key[4] = {nullptr};
     int precise_last = 0;                  // steps t < precise_last use the 3-term split; earlier steps single-pass fp16
     bool use_graph = true;
+    bool fuse_ddpm = false;                // EGOEGO_FUSE_DDPM=1: DDPM update in linear_out's epilogue.  Opt-in: measured 90 us vs 17.6 + 32.9 us for
+                                           // linear_out + ddpm_update_kernel at B = 256 (8 epilogue warps per SM are too few for the Philox work)
     int64_t launches = 0;
     std::unique_ptr<TcEngine> tc;
 };
@@ -107,10 +110,11 @@ static int denoiser_simt(egoego_ctx* c, int B, int T, TSrc ts, const float* pmas
     return 0;
 }
 
-static int run_denoiser(egoego_ctx* c, int B, int T, TSrc ts, const float* pmask, cudaStream_t s, int fmt = 0) {
+static int run_denoiser(egoego_ctx* c, int B, int T, TSrc ts, const float* pmask, cudaStream_t s, int fmt = 0,
+                        const DdpmArgs* fuse = nullptr) {
     if (c->cfg.engine == EGOEGO_ENGINE_SIMT) return denoiser_simt(c, B, T, ts, pmask, s);
     int64_t n = 0;
-    int rc = c->tc->denoiser(B, T, ts, pmask, c->model_out.as<float>(), s, &n, fmt);
+    int rc = c->tc->denoiser(B, T, ts, pmask, c->model_out.as<float>(), s, &n, fmt, fuse);
     c->launches += n;
     return rc;
 }
@@ -208,6 +212,7 @@ int egoego_create(const egoego_cfg* cfg, egoego_handle* out) {
     c->N = cfg->timesteps; c->Tmax = cfg->max_timesteps - 1;
     c->kin_pad = ((2 * c->D + 15) / 16) * 16;
     c->layers.resize(c->NL);
+    { const char* fd = getenv("EGOEGO_FUSE_DDPM"); c->fuse_ddpm = fd && fd[0] == '1'; }
     const char* g = getenv("EGOEGO_GRAPH");
     c->use_graph = !(g && g[0] == '0');
     // precision policy: the last `precise_last` steps (t < precise_last) run the 3-term bf16 split,
@@ -502,13 +507,14 @@ static int sample_chunk(egoego_ctx* c, const float* x_start, const float* cond_m
 
     // A step stages the next step's start_conv operand only in its OWN format; at the fp16 -> split switch the split
     // planes are produced once from x_cur (restage) before the first split step.
+    const bool fused = c->fuse_ddpm && c->cfg.engine == EGOEGO_ENGINE_TCGEN05;   // DDPM update in the epilogue of linear_out
     auto one_step = [&](cudaStream_t st, int fmt) -> int {
         a.stage_mode = (c->cfg.engine == EGOEGO_ENGINE_SIMT) ? 2 : (fmt ? 1 : 0);
-        if (run_denoiser(c, Bc, T, ts, nullptr, st, fmt)) return 1;
+        if (run_denoiser(c, Bc, T, ts, nullptr, st, fmt, fused ? &a : nullptr)) return 1;
         LaunchCfg ld((unsigned)((quads + 255) / 256), 256, 0, st), la(1, 32, 0, st);
-        EG_CUDA(cudaLaunchKernelEx(&ld.cfg, ddpm_update_kernel, a));
+        if (!fused) { EG_CUDA(cudaLaunchKernelEx(&ld.cfg, ddpm_update_kernel, a)); c->launches++; }
         EG_CUDA(cudaLaunchKernelEx(&la.cfg, advance_step_kernel, d_step));
-        c->launches += 2;
+        c->launches += 1;
         EG_CUDA(cudaGetLastError());
         return 0;
     };
@@ -538,7 +544,7 @@ static int sample_chunk(egoego_ctx* c, const float* x_start, const float* cond_m
             const int fmt = fmt_of_step(i);
             if (i > 0 && fmt != fmt_of_step(i - 1) && stage_input(c, xc, D, 0, false, Bc, T, s)) return 1;
             EG_CUDA(cudaGraphLaunch(c->step_graph[fmt], s));
-            c->launches += (c->cfg.engine == EGOEGO_ENGINE_SIMT ? (2 + 7 * c->NL) : c->tc->launches_per_denoiser(fmt)) + 2;
+            c->launches += (c->cfg.engine == EGOEGO_ENGINE_SIMT ? (2 + 7 * c->NL) : c->tc->launches_per_denoiser(fmt)) + (fused ? 1 : 2);
         }
     } else {
         for (int i = 0; i < N; ++i) {
@@ -650,6 +656,20 @@ int egoego_fk_smpl(egoego_handle c, const float* root, const float* aa, int64_t 
     return 0;
 }
 
+int egoego_eval_metrics(int device, const float* gt_quat, const float* gt_jpos, const float* gt_floor,
+                        const float* pred_quat, const float* pred_jpos, const float* pred_floor,
+                        int B, int T, float* out, void* stream_v) {
+    EG_CHECK(gt_quat && gt_jpos && gt_floor && pred_quat && pred_jpos && pred_floor && out, "null argument");
+    EG_CHECK(B >= 1 && T >= 3, "eval metrics need B >= 1 sequences of T >= 3 frames (accelerations use 3 frames)");
+    int ndev = 0;
+    EG_CHECK(cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0, "no CUDA device: libegoego_b200 has no CPU fallback");
+    EG_CHECK(device >= 0 && device < ndev, "bad device ordinal");
+    EG_CUDA(cudaSetDevice(device));
+    eval_metrics_kernel<<<B, MET_WARPS * 32, 0, (cudaStream_t)stream_v>>>(gt_quat, gt_jpos, gt_floor, pred_quat, pred_jpos, pred_floor, T, out);
+    EG_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int egoego_canonicalize_head(egoego_handle c, const float* head_pos, const float* head_quat, int64_t stride_frames,
                              int B, int T, float* x_start, float* recover_quat, void* stream_v) {
     EG_CHECK(c && head_pos && head_quat && x_start, "null argument");
@@ -683,8 +703,6 @@ int egoego_time_kernel(egoego_handle c, int B, int T, int which, int half_fmt, i
     EG_CHECK(which >= 0 && which <= EGOEGO_KERNEL_DDPM_UPDATE, "unknown kernel id");
     EG_CUDA(cudaSetDevice(c->cfg.device));
     cudaStream_t s = (cudaStream_t)stream_v;
-    if (which < EGOEGO_KERNEL_DDPM_UPDATE)
-        return c->tc->time_stage(B, T, which, half_fmt ? 1 : 0, iters, c->model_out.as<float>(), s, ms_per_launch);
     // DDPM update (clamp + posterior mean + Philox noise + staging of the next step's A operand), t fixed at N/2
     TSrc ts{nullptr, nullptr, c->N / 2};
     NoiseSrc ns{};
@@ -692,6 +710,9 @@ int egoego_time_kernel(egoego_handle c, int B, int T, int which, int half_fmt, i
     DdpmArgs a;
     fill_ddpm(c, a, c->x_cur.as<float>(), c->x_cur.as<float>(), ts, ns, 1, nullptr, 0, B, T, true);
     a.stage_mode = half_fmt ? 1 : 0;
+    if (which < EGOEGO_KERNEL_DDPM_UPDATE)   // linear_out is timed as the sampling loop runs it: with the fused DDPM epilogue when that is on
+        return c->tc->time_stage(B, T, which, half_fmt ? 1 : 0, iters, c->model_out.as<float>(), s, ms_per_launch,
+                                 (which == EGOEGO_KERNEL_OUT && c->fuse_ddpm) ? &a : nullptr);
     const long long quads = ((long long)T * c->D + 3) / 4 * B;
     cudaEvent_t e0, e1;
     EG_CUDA(cudaEventCreate(&e0)); EG_CUDA(cudaEventCreate(&e1));
@@ -714,6 +735,13 @@ int egoego_time_dominant_kernel(egoego_handle c, int B, int half_fmt, int iters,
 }
 
 int egoego_precise_last_steps(egoego_handle c) { return c ? c->precise_last : -1; }
+
+int egoego_launches_per_step(egoego_handle c, int which) {
+    if (!c || which < 0 || which > EGOEGO_KERNEL_DDPM_UPDATE) return -1;
+    if (which == EGOEGO_KERNEL_START || which == EGOEGO_KERNEL_OUT) return 1;
+    if (which == EGOEGO_KERNEL_DDPM_UPDATE) return (c->fuse_ddpm && c->cfg.engine == EGOEGO_ENGINE_TCGEN05) ? 0 : 1;
+    return c->NL;
+}
 
 int egoego_selftest_gemm(int device, int M, int N, int K, uint64_t seed, int two_cta, int half_fmt, float* max_abs_err, float* max_abs_ref, float* ms) {
     EG_CHECK(max_abs_err && max_abs_ref && ms, "null argument");

@@ -390,10 +390,84 @@ static int launch_gemm_ln(TcImpl* I, const Plane& A, const Plane& W, int M, int 
     return 0;
 }
 
+// linear_out with the DDPM update of the sampling loop in its epilogue (p_mean_variance / q_posterior / p_sample,
+// egoego/model/transformer_cond_diffusion_model.py:216-256): x0 = acc + bias (pred_x0) -> clamp -> posterior mean -> + sigma * noise
+// -> in-paint -> x_out (fp32, compact) and the next step's start_conv operand plane(s).  Same arithmetic and the same
+// Philox stream (window, draw, flat element quad) as ddpm_update_kernel; model_out is never written.
+template <int FMT>
+struct TcEpiOutDdpm : EpiNoDirect, EpiNoPre {
+    DdpmArgs a; const float* bias; int n_windows;
+    __device__ __forceinline__ float4 bias4(int col) const {
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col < a.D) { b.x = bias[col]; b.y = bias[col + 1]; }
+        if (col + 2 < a.D) { b.z = bias[col + 2]; b.w = bias[col + 3]; }
+        return b;
+    }
+    __device__ __forceinline__ void apply4(int row, int col, float4 acc, float4 b, float4) const {
+        const int w = row / LP, l = row % LP;
+        if (l < 1 || l > a.T || w >= n_windows || col >= a.D) return;
+        const int f = l - 1, e0 = f * a.D + col;                      // flat element inside the window (even)
+        const bool four = col + 2 < a.D;
+        const long long i0 = (long long)w * a.T * a.D + e0;
+        const int t = a.ts.get(w);
+        const float c1 = a.coef1[t], c2 = a.coef2[t];
+        const float sigma = (t == 0) ? 0.f : expf(0.5f * a.logvar[t]);
+        const float k_mo = (a.objective == 0) ? -a.sqrt_recipm1[t] : 1.0f, k_x = (a.objective == 0) ? a.sqrt_recip[t] : 0.0f;
+        float mo[4] = {acc.x + b.x, acc.y + b.y, acc.z + b.z, acc.w + b.w};
+        float xv[4] = {0.f, 0.f, 0.f, 0.f}, nz[4] = {0.f, 0.f, 0.f, 0.f};
+        { const float2 q = *reinterpret_cast<const float2*>(a.x + i0); xv[0] = q.x; xv[1] = q.y; }
+        if (four) { const float2 q = *reinterpret_cast<const float2*>(a.x + i0 + 2); xv[2] = q.x; xv[3] = q.y; }
+        const int draw = a.ns.draw();
+        if (a.ns.tape) {
+            const float* tp = a.ns.tape + (long long)draw * a.ns.draw_stride + i0;
+            nz[0] = tp[0]; nz[1] = tp[1];
+            if (four) { nz[2] = tp[2]; nz[3] = tp[3]; }
+        } else if (sigma != 0.f) {
+            // elements are grouped in quads of the flat window index; rows with odd f start in the middle of a quad
+            const float4 n0 = philox_normal4(a.ns.seed, a.ns.window_offset + w, (uint32_t)draw, (uint32_t)(e0 >> 2));
+            if ((e0 & 2) == 0) { nz[0] = n0.x; nz[1] = n0.y; nz[2] = n0.z; nz[3] = n0.w; }
+            else {
+                nz[0] = n0.z; nz[1] = n0.w;
+                if (four) { const float4 n1 = philox_normal4(a.ns.seed, a.ns.window_offset + w, (uint32_t)draw, (uint32_t)(e0 >> 2) + 1u); nz[2] = n1.x; nz[3] = n1.y; }
+            }
+        }
+        float v[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            float x0 = (a.objective == 0) ? (k_x * xv[r] + k_mo * mo[r]) : mo[r];
+            if (a.clip) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
+            v[r] = (c1 * x0 + c2 * xv[r]) + sigma * nz[r];
+        }
+        if (a.inpaint && f < a.inpaint_len) {
+            const float* ip = a.inpaint + ((long long)w * a.inpaint_len + f) * a.D + col;
+            v[0] = ip[0]; v[1] = ip[1];
+            if (four) { v[2] = ip[2]; v[3] = ip[3]; }
+        }
+        *reinterpret_cast<float2*>(a.x_out + i0) = make_float2(v[0], v[1]);
+        if (four) *reinterpret_cast<float2*>(a.x_out + i0 + 2) = make_float2(v[2], v[3]);
+        const long long o = ((long long)w * LP + l) * a.stage_ld16 + col;      // plane columns [D, ld16) stay zero
+        if (FMT == FMT_SPLIT) {
+            __nv_bfloat16 h0, l0, h1, l1;
+            split_bf16(v[0], h0, l0); split_bf16(v[1], h1, l1);
+            *reinterpret_cast<__nv_bfloat162*>(a.stage_hi + o) = __nv_bfloat162(h0, h1);
+            *reinterpret_cast<__nv_bfloat162*>(a.stage_lo + o) = __nv_bfloat162(l0, l1);
+            if (four) {
+                split_bf16(v[2], h0, l0); split_bf16(v[3], h1, l1);
+                *reinterpret_cast<__nv_bfloat162*>(a.stage_hi + o + 2) = __nv_bfloat162(h0, h1);
+                *reinterpret_cast<__nv_bfloat162*>(a.stage_lo + o + 2) = __nv_bfloat162(l0, l1);
+            }
+        } else {
+            *reinterpret_cast<__half2*>(a.stage_h16 + o) = __floats2half2_rn(v[0], v[1]);
+            if (four) *reinterpret_cast<__half2*>(a.stage_h16 + o + 2) = __floats2half2_rn(v[2], v[3]);
+        }
+    }
+};
+
 // Stages of one denoiser call (egoego_time_kernel's `which`): 0 start, 1 QKV projection, 2 attention, 3 fc (+LN),
 // 4 w_1, 5 w_2 (+LN), 6 linear_out.  `only` < 0 runs everything; otherwise just that stage of layer 0 (timing hook).
 template <int FMT>
-static int denoiser_impl(TcImpl* I, int B, int T, TSrc ts, const float* pmask, float* model_out, cudaStream_t s, int only = -1) {
+static int denoiser_impl(TcImpl* I, int B, int T, TSrc ts, const float* pmask, float* model_out, cudaStream_t s, int only = -1,
+                         const DdpmArgs* fuse = nullptr) {
     const int M = B * LP, d = I->w.d, H = I->w.H, dk = I->w.dk, L = T + 1;
     const int Mg = Mr(B);                          // GEMM rows: whole 256-row tiles (an odd window count is rounded up)
     const int nqkv = 3 * H * dk;
@@ -472,18 +546,25 @@ static int denoiser_impl(TcImpl* I, int B, int T, TSrc ts, const float* pmask, f
         }
     }
     if (on(6, 0)) {
-        TcEpiOut eo{{}, {}, model_out, I->w.D, I->w.out_b, T, B};
-        if (gemm<FMT>(I, I->Hs, I->Wout, Mg, I->nout, d, eo, s)) return 1;
+        if (fuse) {
+            TcEpiOutDdpm<FMT> eo{{}, {}, *fuse, I->w.out_b, B};
+            if (gemm<FMT>(I, I->Hs, I->Wout, Mg, I->nout, d, eo, s)) return 1;
+        } else {
+            TcEpiOut eo{{}, {}, model_out, I->w.D, I->w.out_b, T, B};
+            if (gemm<FMT>(I, I->Hs, I->Wout, Mg, I->nout, d, eo, s)) return 1;
+        }
     }
     EG_CUDA(cudaGetLastError());
     return 0;
 }
 
-int TcEngine::denoiser(int B, int T, TSrc ts, const float* pmask, float* model_out, cudaStream_t s, int64_t* n, int fmt) {
+int TcEngine::denoiser(int B, int T, TSrc ts, const float* pmask, float* model_out, cudaStream_t s, int64_t* n, int fmt, const DdpmArgs* fuse) {
     TcImpl* I = impl_;
     EG_CHECK(fmt == FMT_SPLIT || (I->attn_tc), "fp16 single-pass steps need the tensor-core attention");
-    int rc = (fmt == FMT_HALF) ? denoiser_impl<FMT_HALF>(I, B, T, ts, pmask, model_out, s)
-                               : denoiser_impl<FMT_SPLIT>(I, B, T, ts, pmask, model_out, s);
+    EG_CHECK(!fuse || (fuse->stage_ld16 == I->kx && (fmt == FMT_HALF ? fuse->stage_h16 != nullptr : (fuse->stage_hi && fuse->stage_lo))),
+             "fused DDPM update needs the engine's own staging planes");
+    int rc = (fmt == FMT_HALF) ? denoiser_impl<FMT_HALF>(I, B, T, ts, pmask, model_out, s, -1, fuse)
+                               : denoiser_impl<FMT_SPLIT>(I, B, T, ts, pmask, model_out, s, -1, fuse);
     *n += launches_per_denoiser(fmt);
     return rc;
 }
@@ -491,7 +572,7 @@ int TcEngine::denoiser(int B, int T, TSrc ts, const float* pmask, float* model_o
 // Time ONE stage of the denoiser (see denoiser_impl; layer 0's weights) in isolation on the engine's own buffers:
 // `iters` back-to-back launches between two CUDA events on stream `s`.  The workspace keeps whatever the last
 // sampling call left in it (finite activations), which the stage overwrites in place as it does inside a step.
-int TcEngine::time_stage(int B, int T, int stage, int fmt, int iters, float* model_out, cudaStream_t s, float* ms) {
+int TcEngine::time_stage(int B, int T, int stage, int fmt, int iters, float* model_out, cudaStream_t s, float* ms, const DdpmArgs* fuse) {
     TcImpl* I = impl_;
     EG_CHECK(I && I->attn_tc, "time_stage needs the tensor-core attention layout");
     EG_CHECK(B >= 1 && B <= I->w.max_batch && iters >= 1 && stage >= 0 && stage <= 6, "bad arguments");
@@ -499,8 +580,8 @@ int TcEngine::time_stage(int B, int T, int stage, int fmt, int iters, float* mod
     EG_CUDA(cudaEventCreate(&e0)); EG_CUDA(cudaEventCreate(&e1));
     TSrc ts{nullptr, nullptr, 0};
     auto run = [&]() -> int {
-        return fmt == FMT_HALF ? denoiser_impl<FMT_HALF>(I, B, T, ts, nullptr, model_out, s, stage)
-                               : denoiser_impl<FMT_SPLIT>(I, B, T, ts, nullptr, model_out, s, stage);
+        return fmt == FMT_HALF ? denoiser_impl<FMT_HALF>(I, B, T, ts, nullptr, model_out, s, stage, fuse)
+                               : denoiser_impl<FMT_SPLIT>(I, B, T, ts, nullptr, model_out, s, stage, fuse);
     };
     for (int i = 0; i < 3; ++i) if (run()) return 1;
     EG_CUDA(cudaEventRecord(e0, s));

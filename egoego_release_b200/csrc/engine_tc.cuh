@@ -37,10 +37,13 @@ public:
     // base[M, d] = x_cond-half of start_conv + bias + positional rows (constant over the loop)
     int prepare_cond(int B, int T, cudaStream_t s, int64_t* n);
     // one denoiser call; expects the x half staged; writes model_out[B, T, D]
-    int denoiser(int B, int T, TSrc ts, const float* pmask, float* model_out, cudaStream_t s, int64_t* n, int fmt /* FMT_SPLIT=0 | FMT_HALF=1 */);
+    // `fuse` != nullptr: the DDPM update of the sampling loop runs in the epilogue of linear_out (x_out / next-step operand
+    // planes are written instead of model_out; no ddpm_update_kernel launch is needed afterwards)
+    int denoiser(int B, int T, TSrc ts, const float* pmask, float* model_out, cudaStream_t s, int64_t* n, int fmt /* FMT_SPLIT=0 | FMT_HALF=1 */,
+                 const DdpmArgs* fuse = nullptr);
     void stage_targets(__nv_bfloat16** hi, __nv_bfloat16** lo, __half** h16, int* ld);
     int launches_per_denoiser(int fmt = 0) const;
-    int time_stage(int B, int T, int stage, int fmt, int iters, float* model_out, cudaStream_t s, float* ms);
+    int time_stage(int B, int T, int stage, int fmt, int iters, float* model_out, cudaStream_t s, float* ms, const DdpmArgs* fuse = nullptr);
 private:
     TcImpl* impl_;
 };

@@ -422,22 +422,6 @@ static __global__ void stage_rows_split_kernel(__nv_bfloat16* __restrict__ Ahi, 
 
 // DDPM update (p_mean_variance tail + p_sample, transformer_cond_diffusion_model.py:235-256) fused with
 // the in-paint overwrite (:395-397) and the staging of the next step's GEMM A operand.
-struct DdpmArgs {
-    const float* model_out;  // [B,T,D]
-    const float* x;          // [B,T,D]
-    float* x_out;            // [B,T,D] (may alias x)
-    const float* coef1; const float* coef2; const float* logvar;
-    const float* sqrt_recip; const float* sqrt_recipm1;
-    int objective;           // 0 pred_noise, 1 pred_x0
-    int clip;
-    const float* inpaint; int inpaint_len;
-    float* stage_f32; int stage_ld;                                  // SIMT engine A operand (nullable)
-    __nv_bfloat16* stage_hi; __nv_bfloat16* stage_lo; int stage_ld16; // tensor engine A operand (nullable)
-    __half* stage_h16;                                                // fp16 plane for FMT_HALF steps (nullable)
-    int stage_mode;          // tensor engine planes to write: 0 = bf16 hi/lo only, 1 = fp16 only, 2 = all (next step's format unknown)
-    TSrc ts; NoiseSrc ns;
-    int B, T, D;
-};
 
 static __global__ void ddpm_update_kernel(DdpmArgs a) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");

@@ -287,6 +287,13 @@ class CondGaussianDiffusion(nn.Module):
             check(_capi.lib().egoego_time_kernel(h, B, T, int(which), 1 if half_fmt else 0, iters, C.byref(ms), _stream(dev)))
         return float(ms.value)
 
+    def launches_per_step(self, which) -> int:
+        """How often kernel ``which`` runs in one step of the sampling loop (``ddpm_update``: 0 when the DDPM update is
+        fused into linear_out's epilogue, EGOEGO_FUSE_DDPM=1)."""
+        if isinstance(which, str):
+            which = self.KERNELS.index(which)
+        return int(_capi.lib().egoego_launches_per_step(self._handle(), int(which)))
+
     def launch_count(self) -> int:
         return int(_capi.lib().egoego_launch_count(self._h)) if self._h is not None else 0
 

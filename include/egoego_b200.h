@@ -157,6 +157,19 @@ int  egoego_canonicalize_head(egoego_handle h, const float* head_pos_dev, const 
 int  egoego_tail_condition(egoego_handle h, const float* gquat_dev, const float* gjpos_dev, int B, int n,
                            float* inpaint_out_dev, void* stream);
 
+/* Post-sampling evaluation of B sequences of T frames (T >= 3) -- compute_metrics_for_smpl,
+ * kinpoly/scripts/eval_metrics_imu_rec.py:264-342 (called from eval_stage2.py:192), with what it calls
+ * (compute_accel :66-77, compute_error_accel :79-107, compute_foot_sliding_for_smpl :222-262, get_root_matrix /
+ * get_frobenious_norm(_rot_only) kinpoly/relive/utils/metrics.py:15-24,64-82).  Inputs are device pointers:
+ * global joint rotations quat[B,T,22,4] (wxyz, need not be unit) and positions jpos[B,T,22,3] of ground truth and
+ * prediction, floor heights floor[B] each.  out_dev[B,35] = root_trans_dist, accel_pred, accel_gt, accel_err, pred_fs,
+ * gt_fs, head_trans_dist, root_dist, root_rot_dist, mpjpe, mpjpe_wo_hand, head_dist, head_rot_dist, single_jpe[22]
+ * (mm for distances / accelerations / sliding, Frobenius norms unitless).  No handle: needs only the device. */
+#define EGOEGO_METRICS_OUT 35
+int  egoego_eval_metrics(int device, const float* gt_quat_dev, const float* gt_jpos_dev, const float* gt_floor_dev,
+                         const float* pred_quat_dev, const float* pred_jpos_dev, const float* pred_floor_dev,
+                         int B, int T, float* out_dev, void* stream);
+
 /* Introspection for tests/bench: number of kernels launched by this handle since creation, and the
  * cumulative count of denoiser steps executed. */
 int64_t egoego_launch_count(egoego_handle h);
@@ -180,6 +193,10 @@ enum {
 int  egoego_time_kernel(egoego_handle h, int B, int T, int which, int half_fmt, int iters, float* ms_per_launch, void* stream);
 /* = egoego_time_kernel(h, B, max T, EGOEGO_KERNEL_QKV, ...) (kept for older callers). */
 int  egoego_time_dominant_kernel(egoego_handle h, int B, int half_fmt, int iters, float* ms_per_launch, void* stream);
+/* How many times kernel `which` is launched in one step of the sampling loop (EGOEGO_KERNEL_DDPM_UPDATE: 0 when the
+ * tensor engine runs the DDPM update in the epilogue of linear_out -- opt-in, EGOEGO_FUSE_DDPM=1 -- and
+ * EGOEGO_KERNEL_OUT then times that fused kernel). */
+int  egoego_launches_per_step(egoego_handle h, int which);
 /* Resolved precision policy: steps t < K run the 3-term split (see egoego_cfg.precise_last_steps). */
 int  egoego_precise_last_steps(egoego_handle h);
 

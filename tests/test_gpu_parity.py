@@ -244,12 +244,44 @@ def test_fused_ln_kernels_agree(params0, monkeypatch):
     assert d1 < 2e-2 and d2 < 2e-2
 
 
+@pytest.mark.parametrize("K", [12, 0])
+def test_fused_ddpm_epilogue_matches_ddpm_kernel(params0, monkeypatch, K):
+    """linear_out with the DDPM update in its epilogue (EGOEGO_FUSE_DDPM=1) against linear_out + ddpm_update_kernel (default):
+    same arithmetic and the same Philox stream element for element, in both operand formats, with in-painting, an odd
+    window count and a short window (T = 30).  Differences are at most fp32 contraction noise amplified over the steps."""
+    import egoego_release_b200 as E
+    N = 12
+    for B, T in ((5, 120), (2, 30)):
+        xs = synth_x_start(23, B, T).cuda()
+        cm = O.prep_head_condition_mask(xs.shape).cuda()
+        inpaint = torch.rand(B, 10, 198, device="cuda") * 2 - 1
+        outs = {}
+        for tag, val in (("fused", "1"), ("kernel", "0")):
+            monkeypatch.setenv("EGOEGO_FUSE_DDPM", val)
+            m = E.CondGaussianDiffusion(d_feats=198, d_model=512, n_dec_layers=4, n_head=4, d_k=256, d_v=256, max_timesteps=121,
+                                        out_dim=198, timesteps=N, objective="pred_x0", max_batch=B, engine="tcgen05",
+                                        precise_last_steps=K)
+            m.load_state_dict(params0, strict=False)
+            m = m.cuda()
+            assert m.launches_per_step("ddpm_update") == (0 if val == "1" else 1)
+            torch.manual_seed(7)
+            plain = m.sample(xs, cm)
+            torch.manual_seed(7)
+            painted = m.p_sample_loop(xs.shape, xs, cm, inpaint=inpaint)
+            outs[tag] = (plain, painted)
+        for a, b in zip(outs["fused"], outs["kernel"]):
+            assert torch.isfinite(a).all()
+            assert maxabs(a, b) < (5e-5 if K else 5e-3), (B, T, K, maxabs(a, b))
+        assert torch.equal(outs["fused"][1][:, :10], inpaint)
+
+
 def test_time_kernel_hook(params0):
     """egoego_time_kernel times every kernel of the step in isolation without disturbing later sampling calls."""
     m = make_model(8, "tcgen05", params0, max_batch=8)
     xs = synth_x_start(5, 8, 120).cuda()
     cm = O.prep_head_condition_mask(xs.shape).cuda()
     torch.manual_seed(1); a = m.sample(xs, cm)
+    assert [m.launches_per_step(n) for n in m.KERNELS] == [1, 4, 4, 4, 4, 4, 1, 1]
     for name in m.KERNELS:
         for half in (False, True):
             ms = m.time_kernel(name, 8, 120, half, iters=2)

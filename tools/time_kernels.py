@@ -23,11 +23,13 @@ m.sample(xs, cm)
 torch.cuda.synchronize()
 if os.environ.get("PROF_ONLY"):
     sys.exit(0)
-cnt = {"start": 1, "qkv": 4, "attention": 4, "fc_ln": 4, "w1": 4, "w2_ln": 4, "out": 1, "ddpm_update": 1}
+cnt = {n: m.launches_per_step(n) for n in m.KERNELS}
 for half in (True, False):
     tot = 0.0
     row = []
     for name in m.KERNELS:
+        if cnt[name] == 0:
+            continue
         ms = min(m.time_kernel(name, B, 120, half, iters=iters) for _ in range(3))
         tot += cnt[name] * ms
         row.append(f"{name} {ms * 1e3:.1f}")
