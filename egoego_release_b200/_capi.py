@@ -12,6 +12,9 @@ EXPORTS = [
     "egoego_sample", "egoego_sample_host", "egoego_set_skeleton", "egoego_postprocess", "egoego_fk_smpl",
     "egoego_canonicalize_head", "egoego_tail_condition", "egoego_launch_count", "egoego_selftest_gemm", "egoego_time_dominant_kernel", "egoego_time_kernel",
     "egoego_precise_last_steps", "egoego_eval_metrics", "egoego_launches_per_step",
+    "egoego_seqnet_create", "egoego_seqnet_destroy", "egoego_seqnet_set_tensor", "egoego_seqnet_commit", "egoego_seqnet_forward",
+    "egoego_seqnet_launch_count", "egoego_va2rot", "egoego_rescale_slam", "egoego_slam_features", "egoego_apply_floor_normal",
+    "egoego_rigid_apply",
 ]
 
 ENGINE_TCGEN05, ENGINE_SIMT = 0, 1
@@ -21,6 +24,12 @@ class Cfg(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "d_feats", "d_model", "n_head", "n_dec_layers", "d_k", "d_v", "max_timesteps", "timesteps",
         "objective", "max_batch", "device", "engine", "precise_last_steps")]
+
+
+class SeqNetCfg(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("d_feats", "d_model", "n_head", "n_layers", "d_k", "d_v", "window", "max_batch", "device",
+                                         "n_heads")] + [("head_n_hidden", C.c_int32 * 2), ("head_hidden", (C.c_int32 * 3) * 2),
+                                                        ("head_out", C.c_int32 * 2)]
 
 
 class Rng(C.Structure):
@@ -69,8 +78,22 @@ def lib():
     L.egoego_eval_metrics.argtypes = [i32, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp]
     L.egoego_launch_count.argtypes = [vp]
     L.egoego_launch_count.restype = i64
+    f32 = C.c_float
+    L.egoego_seqnet_create.argtypes = [C.POINTER(SeqNetCfg), C.POINTER(vp)]
+    L.egoego_seqnet_destroy.argtypes = [vp]
+    L.egoego_seqnet_destroy.restype = None
+    L.egoego_seqnet_set_tensor.argtypes = [vp, C.c_char_p, vp, i64]
+    L.egoego_seqnet_commit.argtypes = [vp]
+    L.egoego_seqnet_forward.argtypes = [vp, vp, i32, i32, vp, vp, vp, i32, vp]
+    L.egoego_seqnet_launch_count.argtypes = [vp]
+    L.egoego_seqnet_launch_count.restype = i64
+    L.egoego_va2rot.argtypes = [i32, vp, vp, i32, i32, f32, vp, vp]
+    L.egoego_rescale_slam.argtypes = [i32, vp, i32, vp, i32, f32, vp, vp, vp]
+    L.egoego_slam_features.argtypes = [i32, vp, vp, i32, i32, i32, vp, vp]
+    L.egoego_apply_floor_normal.argtypes = [i32, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp]
+    L.egoego_rigid_apply.argtypes = [i32, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp]
     for name in EXPORTS:
-        if name not in ("egoego_last_error", "egoego_launch_count"):
+        if name not in ("egoego_last_error", "egoego_launch_count", "egoego_seqnet_destroy", "egoego_seqnet_launch_count"):
             getattr(L, name).restype = i32
     _lib = L
     return L

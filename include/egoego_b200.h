@@ -170,6 +170,55 @@ int  egoego_eval_metrics(int device, const float* gt_quat_dev, const float* gt_j
                          const float* pred_quat_dev, const float* pred_jpos_dev, const float* pred_floor_dev,
                          int B, int T, float* out_dev, void* stream);
 
+/* ---- Stage-1 networks (shipped configuration --input_of_feats) ---------------------------------
+ * A "sequence net" is the reference's Decoder used WITHOUT a leading token (egoego/model/transformer_module.py:172-226,
+ * use_full_attention=True, row padding mask) followed by up to two MLP heads (egoego/model/mlp.py:4-27: ReLU after every
+ * affine layer, then one Linear).  HeadFormer (egoego/model/head_estimation_transformer.py:50-100: d_feats 512, window 60,
+ * heads va[1024,512,256]->3 and dist[1024,512,256]->1) and HeadNormalFormer (head_normal_estimation_transformer.py:64-106:
+ * d_feats 18, window 120, head normal[512,256]->3 on token 0) are two instances.  fp32 CUDA-core kernels (batch 1, <= 120
+ * tokens: latency-bound).  Tensor names (host fp32, reference layouts): "start_conv.weight" [d_model,d_feats],
+ * "start_conv.bias", "position_vec.weight" [(window+1),d_model], "layer_stack.<l>.self_attn.{w_q,w_k,w_v,fc,layer_norm}.{weight,bias}",
+ * "layer_stack.<l>.pos_ffn.{w_1,w_2,layer_norm}.{weight,bias}", "head<h>.affine_layers.<j>.{weight,bias}", "head<h>.fc.{weight,bias}". */
+typedef struct egoego_seqnet_ctx* egoego_seqnet;
+typedef struct egoego_seqnet_cfg {
+    int32_t d_feats, d_model /* 256 */, n_head, n_layers, d_k /* 256 */, d_v /* 256 */, window /* <= 128 */, max_batch, device;
+    int32_t n_heads;              /* 0..2 */
+    int32_t head_n_hidden[2];     /* 1..3 hidden layers per head */
+    int32_t head_hidden[2][3];    /* hidden sizes (multiples of 16) */
+    int32_t head_out[2];          /* output size of the head's final Linear */
+} egoego_seqnet_cfg;
+int  egoego_seqnet_create(const egoego_seqnet_cfg* cfg, egoego_seqnet* out);
+void egoego_seqnet_destroy(egoego_seqnet h);
+int  egoego_seqnet_set_tensor(egoego_seqnet h, const char* name, const float* host_data, int64_t numel);
+int  egoego_seqnet_commit(egoego_seqnet h);
+/* feats_dev[B,T,d_feats] (T <= window; the window is zero-padded and every position attended to, exactly like the reference)
+ * -> decoder output dec_out_dev[B,window,d_model] (nullable) and the heads' outputs head<h>_out_dev[B,T,out] (nullable), or
+ * [B,out] of token 0 only when token0_only != 0 (HeadNormalFormer.forward :158). */
+int  egoego_seqnet_forward(egoego_seqnet h, const float* feats_dev, int B, int T, float* dec_out_dev, float* head0_out_dev,
+                           float* head1_out_dev, int token0_only, void* stream);
+int64_t egoego_seqnet_launch_count(egoego_seqnet h);
+/* HeadFormer.va2rot (:102-124): q0[B,4] (wxyz), angular velocities va[B,T,3] -> out[B,T+1,4]. */
+int  egoego_va2rot(int device, const float* q0_dev, const float* va_dev, int B, int T, float dt, float* out_dev, void* stream);
+/* HeadFormer.cal_scale_for_slam_w_pred_scale (:184-212) for one sequence: slam_trans[n_pose,3], predicted per-step
+ * distances dist[n_dist] (divided by dist_scale) -> re-scaled trajectory trans_out[n_pose,3], scale_out[1]. */
+int  egoego_rescale_slam(int device, const float* slam_trans_dev, int n_pose, const float* dist_dev, int n_dist, float dist_scale,
+                         float* trans_out_dev, float* scale_out_dev, void* stream);
+/* HeadNormalFormer input features (:128-137): rot_mat[B,n_pose_stride,3,3], trans[B,n_pose_stride,3], first n_pose poses
+ * -> feats[B,n_pose-1,18]. */
+int  egoego_slam_features(int device, const float* rot_mat_dev, const float* trans_dev, int B, int n_pose_stride, int n_pose,
+                          float* feats_dev, void* stream);
+/* HeadNormalFormer.forward_for_eval :219-250 (before the xy-plane alignment): rotation taking normal[B,3] to +z
+ * (:47-62), applied with scale[B] to the SLAM translations (re-integrated from pose 0) and rotations.  Outputs nullable:
+ * trans_out[B,n_pose,3], rot_out[B,n_pose,3,3], quat_out[B,n_pose,4] (wxyz), align_rot_out[B,3,3]. */
+int  egoego_apply_floor_normal(int device, const float* normal_dev, const float* scale_dev, const float* rot_mat_dev,
+                               const float* trans_dev, int B, int n_pose, float* trans_out_dev, float* rot_out_dev,
+                               float* quat_out_dev, float* align_rot_out_dev, void* stream);
+
+/* De-heading step of HeadNormalFormer.forward_for_eval (:268-276) with a given rotation rot3x3[B,3,3] (the xy-plane
+ * alignment): rot_out = R rot_mat, trans_out = R (trans - trans[:,0]) + offset[B,3] (offset nullable); quat_out wxyz. */
+int  egoego_rigid_apply(int device, const float* rot3x3_dev, const float* offset_dev, const float* rot_mat_dev, const float* trans_dev,
+                        int B, int n_pose, float* trans_out_dev, float* rot_out_dev, float* quat_out_dev, void* stream);
+
 /* Introspection for tests/bench: number of kernels launched by this handle since creation, and the
  * cumulative count of denoiser steps executed. */
 int64_t egoego_launch_count(egoego_handle h);

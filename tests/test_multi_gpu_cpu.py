@@ -44,9 +44,9 @@ def test_sharded_sampling_equals_single_process(B):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, B, q)) for r in range(2)]
     for p in procs:
         p.start()
-    out = q.get(timeout=120)
+    out = q.get(timeout=300)
     for p in procs:
-        p.join(timeout=60)
+        p.join(timeout=180)
         assert p.exitcode == 0
     g = torch.Generator().manual_seed(0)
     xs = torch.randn(B, 6, 198, generator=g)

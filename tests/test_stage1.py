@@ -1,0 +1,145 @@
+"""Stage-1 networks: the oracle against goldens of the unmodified reference modules, the host mirror's
+state_dict layout, and (GPU) the CUDA path through the C ABI against the same goldens.
+Tolerances: network outputs are fp32 sums over K <= 1024 in a different order than PyTorch's -> 2e-4 abs on head pose /
+normals (values are O(1)); geometry-only kernels 1e-5."""
+import argparse
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import rotations as R
+from oracle import stage1 as S
+
+HEAD_CASES = [(31, 139), (32, 45), (33, 60)]
+NORMAL_CASES = [(41, 139), (42, 50), (43, 120)]
+OPT = argparse.Namespace(window=60, n_dec_layers=2, n_head=4, d_k=256, d_v=256, d_model=256, input_of_feats=True, freeze_of_cnn=True,
+                         dist_scale=10.0, normal_window=120, normal_n_dec_layers=2, normal_n_head=4, normal_d_k=256, normal_d_v=256,
+                         normal_d_model=256)
+
+
+@pytest.fixture(scope="module")
+def gold(golden_dir):
+    return dict(np.load(os.path.join(golden_dir, "stage1.npz")))
+
+
+@pytest.mark.parametrize("seed,T", HEAD_CASES)
+def test_oracle_headformer_vs_reference_golden(seed, T, gold):
+    p = S.init_params(7, S.CFG_HEAD)
+    feats, head_pose, slam_trans, _ = S.synth_stage1_inputs(seed, T)
+    with torch.no_grad():
+        pose, scale = S.headformer_forward_for_eval(p, feats, slam_trans, head_pose[:, 0, 3:])
+    assert np.abs(pose.numpy() - gold[f"head_s{seed}_T{T}_pose"]).max() < 2e-6
+    assert abs(float(scale) - float(gold[f"head_s{seed}_T{T}_scale"])) < 1e-6
+
+
+@pytest.mark.parametrize("seed,T", NORMAL_CASES)
+def test_oracle_headnormal_vs_reference_golden(seed, T, gold):
+    p = S.init_params(8, S.CFG_NORMAL)
+    _, head_pose, slam_trans, slam_rot = S.synth_stage1_inputs(seed, T)
+    with torch.no_grad():
+        normal = S.headnormal_forward(p, slam_rot, slam_trans)
+        ta, arm, _ = S.apply_normal_and_scale(normal, torch.tensor(2.5 + 0.1 * seed), slam_rot, slam_trans)
+    assert np.abs(normal.numpy() - gold[f"normal_s{seed}_T{T}_normal"]).max() < 2e-6
+    ta = ta - ta[:, 0:1] + head_pose[:, 0:1, :3]            # the golden went through the identity xy alignment + re-anchoring
+    assert np.abs(ta.numpy() - gold[f"normal_s{seed}_T{T}_trans"]).max() < 2e-6
+    assert np.abs(arm.numpy() - gold[f"normal_s{seed}_T{T}_rot"]).max() < 2e-6
+
+
+def test_mirror_state_dict_matches_reference_layout():
+    from egoego_release_b200 import HeadFormer, HeadNormalFormer
+    for cls, cfg, kw in ((HeadFormer, S.CFG_HEAD, {}), (HeadNormalFormer, S.CFG_NORMAL, {"eval_whole_pipeline": True})):
+        m = cls(OPT, "cpu", **kw)
+        p = S.init_params(1, cfg)
+        sd = m.state_dict()
+        assert set(sd) == set(p)
+        for k, v in p.items():
+            assert tuple(sd[k].shape) == tuple(v.shape), k
+        m.load_state_dict(p, strict=True)
+    with pytest.raises(NotImplementedError):
+        HeadFormer(argparse.Namespace(**{**vars(OPT), "input_of_feats": False}), "cpu")
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only behaviour")
+def test_stage1_has_no_cpu_fallback():
+    from egoego_release_b200 import EgoEgoError, HeadFormer
+    m = HeadFormer(OPT, "cpu")
+    feats, head_pose, slam_trans, _ = S.synth_stage1_inputs(1, 10)
+    with pytest.raises(EgoEgoError):
+        m.forward_for_eval({"of": feats, "aligned_slam_trans": slam_trans, "head_pose": head_pose})
+
+
+def test_umeyama_restatement_recovers_a_known_similarity():
+    from egoego_release_b200.stage1 import umeyama_alignment
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=(3, 50))
+    Rz = R.axis_angle_to_matrix(torch.tensor([[0.0, 0.0, 0.7]]))[0].double().numpy()
+    y = 1.7 * Rz @ x + np.array([[0.3], [-0.2], [1.0]])
+    r, t, c = umeyama_alignment(x, y, True)
+    assert np.abs(r - Rz).max() < 1e-6 and abs(c - 1.7) < 1e-6 and np.abs(t - [0.3, -0.2, 1.0]).max() < 1e-6   # Rz comes from an fp32 matrix
+
+
+# ---- GPU ------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,T", HEAD_CASES)
+def test_gpu_headformer_vs_reference_golden(seed, T, gold):
+    from egoego_release_b200 import HeadFormer
+    m = HeadFormer(OPT, "cuda:0")
+    m.load_state_dict(S.init_params(7, S.CFG_HEAD), strict=True)
+    m = m.cuda()
+    feats, head_pose, slam_trans, _ = S.synth_stage1_inputs(seed, T)
+    res = m.forward_for_eval({"of": feats, "aligned_slam_trans": slam_trans, "head_pose": head_pose})
+    pose = res["head_pose"].cpu().numpy()
+    ref = gold[f"head_s{seed}_T{T}_pose"]
+    assert pose.shape == ref.shape
+    err = np.abs(pose - ref).max()
+    print(f"HeadFormer T={T}: head pose max-abs {err:.2e}, scale {float(res['pred_scale']):.6f} vs {float(gold[f'head_s{seed}_T{T}_scale']):.6f}")
+    assert err < 2e-4
+    assert abs(float(res["pred_scale"]) - float(gold[f"head_s{seed}_T{T}_scale"])) < 2e-4 * abs(float(gold[f"head_s{seed}_T{T}_scale"])) + 1e-6
+    assert m.launch_count() > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,T", NORMAL_CASES)
+def test_gpu_headnormal_vs_reference_golden(seed, T, gold):
+    from egoego_release_b200 import HeadNormalFormer
+    m = HeadNormalFormer(OPT, "cuda:0", eval_whole_pipeline=True)
+    m.load_state_dict(S.init_params(8, S.CFG_NORMAL), strict=True)
+    m = m.cuda()
+    _, head_pose, slam_trans, slam_rot = S.synth_stage1_inputs(seed, T)
+    data = {"head_rot_mat": slam_rot, "head_trans": slam_trans, "seq_len": torch.tensor(slam_trans.shape[1]).float()[None],
+            "ori_head_pose": head_pose}
+    normal = m.forward(data)["pred_normal"].cpu().numpy()
+    assert np.abs(normal - gold[f"normal_s{seed}_T{T}_normal"]).max() < 2e-4
+    ev = m.forward_for_eval(data, pred_scale=torch.tensor(2.5 + 0.1 * seed), xy_align=lambda est, ref: np.eye(3))
+    et = np.abs(ev["head_trans"].cpu().numpy() - gold[f"normal_s{seed}_T{T}_trans"]).max()
+    er = np.abs(ev["head_rot_mat"].cpu().numpy() - gold[f"normal_s{seed}_T{T}_rot"]).max()
+    print(f"HeadNormalFormer T={T}: trans max-abs {et:.2e}, rot max-abs {er:.2e}")
+    assert et < 5e-4 and er < 5e-4             # the predicted normal (2e-4) feeds the rotation of a trajectory a few metres long
+    q = ev["head_pose"][0, :, 3:].cpu()
+    assert np.abs(R.quaternion_to_matrix(q).numpy() - ev["head_rot_mat"][0].cpu().numpy()).max() < 1e-5
+
+
+@pytest.mark.gpu
+def test_gpu_stage1_geometry_kernels_vs_oracle():
+    from egoego_release_b200 import HeadFormer, HeadNormalFormer
+    hf = HeadFormer(OPT, "cuda:0").cuda()
+    rng = np.random.default_rng(3)
+    q0 = torch.from_numpy(rng.normal(size=(5, 4)).astype(np.float32))
+    q0 = q0 / q0.norm(dim=1, keepdim=True)
+    va = torch.from_numpy(rng.normal(0, 2.0, size=(5, 70, 3)).astype(np.float32))
+    assert (hf.va2rot(q0, va).cpu() - S.va2rot(q0, va)).abs().max() < 1e-5
+    slam = torch.from_numpy(np.cumsum(rng.normal(0, 0.02, size=(90, 3)), axis=0).astype(np.float32))
+    for n_dist in (89, 60, 120):
+        dist = torch.from_numpy(rng.uniform(0.1, 0.3, size=(n_dist,)).astype(np.float32))
+        t_gpu, s_gpu = hf.cal_scale_for_slam_w_pred_scale(slam, dist)
+        t_ref, s_ref = S.cal_scale_for_slam_w_pred_scale(slam, dist)
+        assert abs(float(s_gpu) - float(s_ref)) < 1e-5 * abs(float(s_ref)) and (t_gpu.cpu() - t_ref).abs().max() < 1e-4
+    nf = HeadNormalFormer(OPT, "cuda:0", eval_whole_pipeline=True).cuda()
+    _, _, slam_trans, slam_rot = S.synth_stage1_inputs(9, 40)
+    normal = torch.tensor([[0.2, -0.3, 0.9]])
+    ta, arm, aq, ra = nf.apply_normal_and_scale(normal, torch.tensor(1.3), slam_rot, slam_trans)
+    ta_r, arm_r, aq_r = S.apply_normal_and_scale(normal, torch.tensor(1.3), slam_rot, slam_trans)
+    assert (ta.cpu() - ta_r).abs().max() < 1e-5 and (arm.cpu() - arm_r).abs().max() < 1e-5 and (aq.cpu() - aq_r).abs().max() < 1e-5
+    assert np.abs(ra[0].cpu().numpy() - S.cal_rotation_from_floor_normal(normal[0].double().numpy())).max() < 1e-6
