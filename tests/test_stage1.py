@@ -143,3 +143,52 @@ def test_gpu_stage1_geometry_kernels_vs_oracle():
     ta_r, arm_r, aq_r = S.apply_normal_and_scale(normal, torch.tensor(1.3), slam_rot, slam_trans)
     assert (ta.cpu() - ta_r).abs().max() < 1e-5 and (arm.cpu() - arm_r).abs().max() < 1e-5 and (aq.cpu() - aq_r).abs().max() < 1e-5
     assert np.abs(ra[0].cpu().numpy() - S.cal_rotation_from_floor_normal(normal[0].double().numpy())).max() < 1e-6
+
+
+@pytest.mark.gpu
+def test_gpu_full_pipeline_config4(params0):
+    """BASELINE config 4: HeadNet + GravityNet -> stage-2 sliding-window diffusion -> FK, one sequence of 139 frames.
+    Stage 1 is checked against the oracle's composition of the same steps (run_egoego.py:102-135); stage 2 against a direct
+    call with the same head pose and seed (bit-exact: the pipeline adds no arithmetic of its own) and against the metrics
+    kernel's invariants."""
+    import egoego_release_b200 as E
+    from egoego_release_b200 import pipeline as P
+    from helpers import make_model
+    hf = E.HeadFormer(OPT, "cuda:0"); hf.load_state_dict(S.init_params(7, S.CFG_HEAD)); hf = hf.cuda()
+    gn = E.HeadNormalFormer(OPT, "cuda:0", eval_whole_pipeline=True); gn.load_state_dict(S.init_params(8, S.CFG_NORMAL)); gn = gn.cuda()
+    dm = make_model(20, "tcgen05", params0, max_batch=2)
+    ds = E.MotionDataStub().bind(dm)
+    feats, head_pose, slam_trans, slam_rot = S.synth_stage1_inputs(77, 139)
+    data = {"of": feats, "aligned_slam_trans": slam_trans, "head_pose": head_pose, "ori_slam_trans": slam_trans * 1.9,
+            "ori_slam_rot_mat": slam_rot}
+    ident = lambda est, ref: np.eye(3)
+    torch.manual_seed(5)
+    out = P.run_egoego(hf, gn, dm, ds, data, sample_bs=2, xy_align=ident)
+    # ---- stage 1 vs the oracle's composition ----
+    with torch.no_grad():
+        pose1, scale = S.headformer_forward_for_eval(S.init_params(7, S.CFG_HEAD), feats, slam_trans, head_pose[:, 0, 3:])
+        ot = slam_trans * 1.9
+        ot = ot - ot[:, 0:1]
+        normal = S.headnormal_forward(S.init_params(8, S.CFG_NORMAL), slam_rot, ot)
+        ta, _, _ = S.apply_normal_and_scale(normal, scale, slam_rot, ot)
+        ta = ta - ta[:, 0:1] + head_pose[:, 0:1, :3]
+        n = min(ta.shape[1], pose1.shape[1])
+        hp = torch.cat((ta[:, :n], pose1[:, :n, 3:]), -1).clone()
+        hp[0, :, :2] -= hp[0, 0:1, :2].clone()
+        hp[0, :, :3] += head_pose[0, 0:1, :3] - hp[0, 0:1, :3]
+        hp[0, :, 2] -= 0.13
+    err = (out["head_pose"].cpu() - hp).abs().max()
+    print(f"pipeline stage-1 head pose vs oracle: max-abs {float(err):.2e} over {hp.shape[1]} frames")
+    assert err < 5e-4
+    # ---- stage 2: same head pose + seed through the public API directly ----
+    torch.manual_seed(5)
+    s1 = P.estimate_head_pose(hf, gn, data, xy_align=ident)
+    direct = P.generate_full_body(dm, ds, s1["head_pose"], sample_bs=2)
+    for k in ("local_aa", "root_trans", "global_jpos"):
+        assert torch.equal(out[k], direct[k]), k
+    T2 = out["global_jpos"].shape[1]
+    assert tuple(out["local_aa"].shape) == (2, T2, 22, 3) and T2 >= 130 and torch.isfinite(out["global_jpos"]).all()
+    assert out["global_jpos"][:, 0, 15, :2].abs().max() < 1e-5           # first-frame head at x = y = 0
+    # the generated head follows the conditioning head trajectory (stage 2 is conditioned on it)
+    m = E.compute_metrics_batch(out["global_jrot"], out["global_jpos"], torch.zeros(2), out["global_jrot"], out["global_jpos"], torch.zeros(2))
+    assert float(m[:, 9].abs().max()) == 0.0
