@@ -200,6 +200,60 @@ def parity_vs_reference(m, dev, N):
             "reference": "unmodified reference CPU fp32 (golden tests/golden/sample.npz), B=1 T=120 N=%d, identical noise tape" % N}
 
 
+def next_rows(dev, B, T, pk):
+    """SURVEY.md 8f rows built beside the hot path, each measured on the device with CUDA events:
+    the evaluation-metrics kernel (HBM-bound: algorithmic bytes = 2 x T x 22 x 7 floats read per sequence) and the stage-1
+    networks (latency: one 139-frame sequence, the demo's length, through HeadFormer / HeadNormalFormer forward_for_eval)."""
+    import argparse
+    import numpy as np
+    import torch
+    import egoego_release_b200 as E
+    from oracle import stage1 as S
+    out = {}
+
+    def timed(fn, iters):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    nseq = 8 * B                                     # 2048 sequences: 300 MB of inputs, larger than the 126 MB L2
+    gq = torch.randn(nseq, T, 22, 4, device=dev); gj = torch.randn(nseq, T, 22, 3, device=dev)
+    pq = torch.randn(nseq, T, 22, 4, device=dev); pj = gj + 0.01 * torch.randn(nseq, T, 22, 3, device=dev)
+    fl = torch.zeros(nseq, device=dev)
+    ms = timed(lambda: E.compute_metrics_batch(gq, gj, fl, pq, pj, fl), 10)
+    by = nseq * T * 22 * 7 * 4 * 2
+    out["eval_metrics"] = {"kernel": "eval_metrics_kernel (compute_metrics_for_smpl)", "sequences": nseq, "ms_per_launch": ms, "bound": "hbm",
+                           "algorithmic_bytes_per_launch": by, "achieved": by / (ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                           "frac": by / (ms * 1e-3) / 1e9 / pk["hbm_gbs"], "sequences_per_s": nseq / (ms * 1e-3)}
+    del gq, gj, pq, pj
+    opt = argparse.Namespace(window=60, n_dec_layers=2, n_head=4, d_k=256, d_v=256, d_model=256, input_of_feats=True, freeze_of_cnn=True,
+                             dist_scale=10.0, normal_window=120, normal_n_dec_layers=2, normal_n_head=4, normal_d_k=256, normal_d_v=256,
+                             normal_d_model=256)
+    hf = E.HeadFormer(opt, dev); hf.load_state_dict(S.init_params(7, S.CFG_HEAD)); hf = hf.to(dev)
+    gn = E.HeadNormalFormer(opt, dev, eval_whole_pipeline=True); gn.load_state_dict(S.init_params(8, S.CFG_NORMAL)); gn = gn.to(dev)
+    feats, head_pose, slam_trans, slam_rot = [t.to(dev) for t in S.synth_stage1_inputs(77, 139)]
+    d1 = {"of": feats, "aligned_slam_trans": slam_trans, "head_pose": head_pose}
+    d2 = {"head_rot_mat": slam_rot, "head_trans": slam_trans, "ori_head_pose": head_pose}
+    sc = torch.tensor(1.0, device=dev)
+    ident = lambda a, b: np.eye(3)
+    l0 = hf.launch_count()
+    t1 = timed(lambda: hf.forward_for_eval(d1), 10)
+    out["stage1"] = {"sequence_frames": 139, "headformer_forward_for_eval_us": t1 * 1e3,
+                     "headnormalformer_forward_us": timed(lambda: gn.forward(d2), 10) * 1e3,
+                     "headnormalformer_forward_for_eval_us": timed(lambda: gn.forward_for_eval(d2, sc, xy_align=ident), 10) * 1e3,
+                     "note": "fp32 CUDA-core sequence nets (d_model 256, 2 layers), eager launches incl. host glue; forward_for_eval of "
+                             "HeadNormalFormer includes its device->host copy of the trajectory for the xy alignment callable",
+                     "headformer_launches_per_call": (hf.launch_count() - l0) // 13}
+    return out
+
+
 def torch_gpu_baseline(dev, B, T, N, n_steps=12):
     """The reference's own arithmetic (oracle port: same op sequence) as stock PyTorch eager fp32 on this B200 --
     the denominator of north_star's ">= 10x the reference single-GPU PyTorch sampling throughput"."""
@@ -392,6 +446,11 @@ def main():
     else:
         line["roofline"] = dict(line["path_roofline"], traffic=None, peak_source=pk_src)
     line["cpu_baseline"] = cpu_baseline(32, T, N, a.cpu_seconds)
+    if world == 1:
+        try:
+            line["next_rows"] = next_rows(dev, B, T, pk)
+        except Exception as ex:   # reported extras only; never masks the headline numbers
+            line["next_rows"] = {"error": repr(ex)[:200]}
     if world == 1 and not os.environ.get("EGOEGO_BENCH_SKIP_TORCH"):
         del m
         torch.cuda.empty_cache()
