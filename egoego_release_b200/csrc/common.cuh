@@ -70,9 +70,11 @@ struct TSrc {
     const long long* t_arr;   // [B] or nullptr
     const int*       d_step;  // device counter or nullptr
     int              t_start;
+    int              t_max;   // timesteps - 1: a caller-supplied t outside [0, t_max] is clamped (tables have `timesteps` rows;
+                              // the reference fails with a device-side assert there, this library must not fault the GPU)
     __device__ __forceinline__ int get(int w) const {
-        if (t_arr) return (int)t_arr[w];
-        return t_start - (d_step ? *d_step : 0);
+        const int t = t_arr ? (int)t_arr[w] : t_start - (d_step ? *d_step : 0);
+        return min(max(t, 0), t_max);
     }
 };
 

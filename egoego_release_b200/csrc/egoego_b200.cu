@@ -443,7 +443,7 @@ int egoego_denoiser_forward(egoego_handle c, const float* x_all, const int64_t* 
         if (stage_input(c, xa, 2 * c->D, c->D, true, Bc, T, s)) return 1;
         if (prepare_cond(c, Bc, T, s)) return 1;
         if (stage_input(c, xa, 2 * c->D, 0, false, Bc, T, s)) return 1;
-        TSrc ts{reinterpret_cast<const long long*>(t_dev) + b0, nullptr, 0};
+        TSrc ts{reinterpret_cast<const long long*>(t_dev) + b0, nullptr, 0, c->N - 1};
         if (run_denoiser(c, Bc, T, ts, pmask ? pmask + (size_t)b0 * (T + 1) : nullptr, s)) return 1;
         EG_CUDA(cudaMemcpyAsync(out + (size_t)b0 * T * c->D, c->model_out.p, (size_t)Bc * T * c->D * 4, cudaMemcpyDeviceToDevice, s));
     }
@@ -467,7 +467,7 @@ int egoego_p_sample_step(egoego_handle c, const float* x, const int64_t* t_dev, 
         if (stage_input(c, x_cond + off, D, 0, true, Bc, T, s)) return 1;
         if (prepare_cond(c, Bc, T, s)) return 1;
         if (stage_input(c, x + off, D, 0, false, Bc, T, s)) return 1;
-        TSrc ts{reinterpret_cast<const long long*>(t_dev) + b0, nullptr, 0};
+        TSrc ts{reinterpret_cast<const long long*>(t_dev) + b0, nullptr, 0, c->N - 1};
         if (run_denoiser(c, Bc, T, ts, pmask ? pmask + (size_t)b0 * (T + 1) : nullptr, s)) return 1;
         NoiseSrc ns{};
         if (noise) { ns.tape = noise + off; ns.draw_stride = 0; ns.draw_static = 0; }
@@ -499,7 +499,7 @@ static int sample_chunk(egoego_ctx* c, const float* x_start, const float* cond_m
     if (prepare_cond(c, Bc, T, s)) return 1;
     if (stage_input(c, xc, D, 0, false, Bc, T, s)) return 1;
     EG_CUDA(cudaMemsetAsync(d_step, 0, sizeof(int), s));
-    TSrc ts{nullptr, d_step, N - 1};
+    TSrc ts{nullptr, d_step, N - 1, N - 1};
     NoiseSrc ns = ns_base;
     ns.d_step = d_step; ns.draw_static = 2;
     DdpmArgs a;
@@ -704,7 +704,7 @@ int egoego_time_kernel(egoego_handle c, int B, int T, int which, int half_fmt, i
     EG_CUDA(cudaSetDevice(c->cfg.device));
     cudaStream_t s = (cudaStream_t)stream_v;
     // DDPM update (clamp + posterior mean + Philox noise + staging of the next step's A operand), t fixed at N/2
-    TSrc ts{nullptr, nullptr, c->N / 2};
+    TSrc ts{nullptr, nullptr, c->N / 2, c->N - 1};
     NoiseSrc ns{};
     ns.tape = nullptr; ns.seed = 1; ns.window_offset = 0; ns.draw_static = 2;
     DdpmArgs a;

@@ -578,7 +578,7 @@ int TcEngine::time_stage(int B, int T, int stage, int fmt, int iters, float* mod
     EG_CHECK(B >= 1 && B <= I->w.max_batch && iters >= 1 && stage >= 0 && stage <= 6, "bad arguments");
     cudaEvent_t e0, e1;
     EG_CUDA(cudaEventCreate(&e0)); EG_CUDA(cudaEventCreate(&e1));
-    TSrc ts{nullptr, nullptr, 0};
+    TSrc ts{nullptr, nullptr, 0, 0};
     auto run = [&]() -> int {
         return fmt == FMT_HALF ? denoiser_impl<FMT_HALF>(I, B, T, ts, nullptr, model_out, s, stage, fuse)
                                : denoiser_impl<FMT_SPLIT>(I, B, T, ts, nullptr, model_out, s, stage, fuse);

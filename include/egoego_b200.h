@@ -97,7 +97,8 @@ int  egoego_make_cosine_schedule(egoego_handle h);
  * Must be called after the last set_tensor and before any compute call. */
 int  egoego_commit_weights(egoego_handle h, void* stream);
 
-/* out[B,T,d_feats] = denoise_fn(x_all[B,T,2*d_feats], t[B])   (t: int64 device array, 0 <= t < timesteps)
+/* out[B,T,d_feats] = denoise_fn(x_all[B,T,2*d_feats], t[B])   (t: int64 device array, 0 <= t < timesteps; values outside
+ * that range are clamped on the device -- the timestep-embedding and schedule tables have `timesteps` rows)
  * padding_mask: NULL or float [B,T+1] (1 = keep, 0 = zero the row after every sub-layer). */
 int  egoego_denoiser_forward(egoego_handle h, const float* x_all_dev, const int64_t* t_dev,
                              const float* padding_mask_dev, int B, int T, float* out_dev, void* stream);

@@ -183,6 +183,13 @@ def test_error_behaviour(params0):
                                  max_timesteps=121, out_dim=198, timesteps=10, objective="pred_v").cuda()
     with pytest.raises(ValueError):
         m2.p_sample(x[:, :120], torch.zeros(1, dtype=torch.long, device="cuda"), x[:, :120])
+    # a timestep outside [0, timesteps) must not fault the GPU (the embedding / schedule tables have `timesteps` rows): clamped
+    src = torch.randn(2, 120, 396, device="cuda")
+    for eng_m in (m, make_model(10, "tcgen05", params0, max_batch=2)):
+        hi = eng_m.denoise_fn(src, torch.full((2,), 10 ** 6, dtype=torch.long, device="cuda"))
+        lo = eng_m.denoise_fn(src, torch.full((2,), -5, dtype=torch.long, device="cuda"))
+        assert torch.equal(hi, eng_m.denoise_fn(src, torch.full((2,), 9, dtype=torch.long, device="cuda")))
+        assert torch.equal(lo, eng_m.denoise_fn(src, torch.zeros(2, dtype=torch.long, device="cuda")))
     # chunking: B > max_batch is processed in chunks and equals the one-shot result of a larger engine
     xs = synth_x_start(9, 5, 30).cuda()
     cm = O.prep_head_condition_mask(xs.shape).cuda()
