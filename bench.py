@@ -202,7 +202,7 @@ def parity_vs_reference(m, dev, N):
 
 def next_rows(dev, B, T, pk):
     """SURVEY.md 8f rows built beside the hot path, each measured on the device with CUDA events:
-    the evaluation-metrics kernel (HBM-bound: algorithmic bytes = 2 x T x 22 x 7 floats read per sequence) and the stage-1
+    the evaluation-metrics kernel (HBM-bound: algorithmic bytes = joint positions + root/head quaternions of gt and pred) and the stage-1
     networks (latency: one 139-frame sequence, the demo's length, through HeadFormer / HeadNormalFormer forward_for_eval)."""
     import argparse
     import numpy as np
@@ -228,7 +228,7 @@ def next_rows(dev, B, T, pk):
     pq = torch.randn(nseq, T, 22, 4, device=dev); pj = gj + 0.01 * torch.randn(nseq, T, 22, 3, device=dev)
     fl = torch.zeros(nseq, device=dev)
     ms = timed(lambda: E.compute_metrics_batch(gq, gj, fl, pq, pj, fl), 10)
-    by = nseq * T * 22 * 7 * 4 * 2
+    by = nseq * T * (22 * 3 + 2 * 4) * 4 * 2         # positions of 22 joints + quaternions of root and head, gt and pred
     out["eval_metrics"] = {"kernel": "eval_metrics_kernel (compute_metrics_for_smpl)", "sequences": nseq, "ms_per_launch": ms, "bound": "hbm",
                            "algorithmic_bytes_per_launch": by, "achieved": by / (ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                            "frac": by / (ms * 1e-3) / 1e9 / pk["hbm_gbs"], "sequences_per_s": nseq / (ms * 1e-3)}

@@ -5,7 +5,8 @@
 // compute_accel / compute_error_accel (:66-107), compute_foot_sliding_for_smpl (:222-262), get_root_matrix /
 // get_frobenious_norm(_rot_only) (kinpoly/relive/utils/metrics.py:15-24,64-82), quaternion_matrix
 // (kinpoly/relive/utils/transformation.py:1346-1370: wxyz, normalised, identity below _EPS).
-// HBM-bound: reads 2 x T x 22 x 7 floats per sequence (~148 KB at T = 120), writes 35 floats.
+// HBM-bound: reads the joint positions (2 x T x 22 x 3 floats) and the root / head quaternions (2 x T x 2 x 4 floats) of a
+// sequence (~71 KB at T = 120), writes 35 floats.
 #pragma once
 #include "common.cuh"
 
@@ -14,8 +15,6 @@ namespace egoego {
 constexpr int MET_SCALARS = 13;                 // order = oracle/metrics.py KEYS
 constexpr int MET_OUT = MET_SCALARS + NJ;       // + single_jpe[22]
 constexpr int MET_WARPS = 8;
-
-struct Pose34 { double r[9]; double t[3]; };
 
 // quaternion_matrix: rotation of a (not necessarily unit) wxyz quaternion, identity when |q|^2 < 4 eps
 __device__ __forceinline__ void quat_matrix64(const float* q, double* R) {
@@ -62,7 +61,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // gt_quat/pred_quat [B,T,22,4], gt_jpos/pred_jpos [B,T,22,3], floors [B] (gt, pred); out [B, MET_OUT]
-static __global__ void __launch_bounds__(MET_WARPS * 32)
+static __global__ void __launch_bounds__(MET_WARPS * 32, 3)
 eval_metrics_kernel(const float* __restrict__ gt_quat, const float* __restrict__ gt_jpos, const float* __restrict__ gt_floor,
                     const float* __restrict__ pred_quat, const float* __restrict__ pred_jpos, const float* __restrict__ pred_floor,
                     int T, float* __restrict__ out) {
@@ -95,15 +94,12 @@ eval_metrics_kernel(const float* __restrict__ gt_quat, const float* __restrict__
             dn += d * d;
         }
         if (jl) jpe += (double)sqrtf(dn);
-        // translation errors of root (lane 0) and head (lane 15) + pose-matrix distances
+        // translation errors of root (lane 0) and head (lane 15)
         if (lane == 0 || lane == HEAD_IDX) {
             float d2 = 0.f;
 #pragma unroll
             for (int c = 0; c < 3; ++c) { const float d = p0[c] - g0[c]; d2 += d * d; }
-            double full, rot;
-            frob_pair(pq + ((long long)t * NJ + lane) * 4, p0, gq + ((long long)t * NJ + lane) * 4, g0, &full, &rot);
-            if (lane == 0) { s_root_t += (double)sqrtf(d2); s_root_d += full; s_root_r += rot; }
-            else           { s_head_t += (double)sqrtf(d2); s_head_d += full; s_head_r += rot; }
+            if (lane == 0) s_root_t += (double)sqrtf(d2); else s_head_t += (double)sqrtf(d2);
         }
         // accelerations over frames t, t+1, t+2 (T - 2 terms), mean over the 22 joints
         if (t + 2 < T) {
@@ -131,10 +127,22 @@ eval_metrics_kernel(const float* __restrict__ gt_quat, const float* __restrict__
             if (zg < hfoot) s_fs_g += (double)fabsf(sqrtf((g1x - g0[0]) * (g1x - g0[0]) + (g1y - g0[1]) * (g1y - g0[1])) * (2.f - exp2f(zg / hfoot)));
         }
     }
+    // pose-matrix distances (fp64, ~300 flops per pose pair): a second pass with lane = (frame, root | head), so all 32 lanes
+    // carry fp64 work instead of two lanes per frame holding up their warp
+    for (int t0 = warp * 16; t0 < T; t0 += MET_WARPS * 16) {
+        const int t = t0 + (lane & 15), j = lane < 16 ? 0 : HEAD_IDX;
+        if (t < T) {
+            const long long o = (long long)t * NJ + j;
+            const float pp[3] = {pj[o * 3], pj[o * 3 + 1], pj[o * 3 + 2]}, gp[3] = {gj[o * 3], gj[o * 3 + 1], gj[o * 3 + 2]};
+            double full, rot;
+            frob_pair(pq + o * 4, pp, gq + o * 4, gp, &full, &rot);
+            if (lane < 16) { s_root_d += full; s_root_r += rot; } else { s_head_d += full; s_head_r += rot; }
+        }
+    }
+    s_root_d = warp_sum(s_root_d); s_root_r = warp_sum(s_root_r); s_head_d = warp_sum(s_head_d); s_head_r = warp_sum(s_head_r);
     // warp-level assembly: scalars into red[warp][0..12], per-joint jpe sums into red[warp][13 + joint]
     const double fs_p = warp_sum(s_fs_p), fs_g = warp_sum(s_fs_g);
-    const double head_t = __shfl_sync(0xffffffffu, s_head_t, HEAD_IDX), head_d = __shfl_sync(0xffffffffu, s_head_d, HEAD_IDX),
-                 head_r = __shfl_sync(0xffffffffu, s_head_r, HEAD_IDX);
+    const double head_t = __shfl_sync(0xffffffffu, s_head_t, HEAD_IDX), head_d = s_head_d, head_r = s_head_r;
     if (lane == 0) {
         double* r = red[warp];
         r[0] = s_root_t; r[1] = s_acc_p; r[2] = s_acc_g; r[3] = s_acc_e; r[4] = fs_p; r[5] = fs_g; r[6] = head_t;
