@@ -1,5 +1,5 @@
 // Post-sampling evaluation metrics on the device: one block per sequence, one warp per frame,
-// lane = joint; fp64 accumulation, one pass over gt/pred joint positions [T,22,3] and global quaternions [T,22,4].
+// lane = joint; per-term arithmetic in fp32 (the reference's arrays are float32), accumulation over frames in fp64.
 //
 // Follows compute_metrics_for_smpl (kinpoly/scripts/eval_metrics_imu_rec.py:264-342) and what it calls:
 // compute_accel / compute_error_accel (:66-107), compute_foot_sliding_for_smpl (:222-262), get_root_matrix /
@@ -15,45 +15,53 @@ namespace egoego {
 constexpr int MET_SCALARS = 13;                 // order = oracle/metrics.py KEYS
 constexpr int MET_OUT = MET_SCALARS + NJ;       // + single_jpe[22]
 constexpr int MET_WARPS = 8;
+constexpr int MET_CHUNK = 32;                   // frames per shared-memory chunk
 
-// quaternion_matrix: rotation of a (not necessarily unit) wxyz quaternion, identity when |q|^2 < 4 eps
-__device__ __forceinline__ void quat_matrix64(const float* q, double* R) {
-    const double w = q[0], x = q[1], y = q[2], z = q[3];
-    const double n = w * w + x * x + y * y + z * z;
-    if (n < 8.881784197001252e-16) { R[0] = R[4] = R[8] = 1.0; R[1] = R[2] = R[3] = R[5] = R[6] = R[7] = 0.0; return; }
-    const double s = 2.0 / n;
-    R[0] = 1.0 - s * (y * y + z * z); R[1] = s * (x * y - z * w);       R[2] = s * (x * z + y * w);
-    R[3] = s * (x * y + z * w);       R[4] = 1.0 - s * (x * x + z * z); R[5] = s * (y * z - x * w);
-    R[6] = s * (x * z - y * w);       R[7] = s * (y * z + x * w);       R[8] = 1.0 - s * (x * x + y * y);
+// quaternion_matrix: rotation of a (not necessarily unit) wxyz quaternion, identity when |q|^2 < 4 eps(double).
+// fp32: the inputs are fp32 and the distances below are O(1e-3 .. 1); fp64 issue rate would bound the whole kernel
+// (measured: 209 us with fp64 pose algebra for 2048 sequences)
+__device__ __forceinline__ void quat_matrix32(const float* q, float* R) {
+    const float w = q[0], x = q[1], y = q[2], z = q[3];
+    const float n = w * w + x * x + y * y + z * z;
+    if (n < 8.881784197001252e-16f) { R[0] = R[4] = R[8] = 1.f; R[1] = R[2] = R[3] = R[5] = R[6] = R[7] = 0.f; return; }
+    const float s = 2.0f / n;
+    R[0] = 1.0f - s * (y * y + z * z); R[1] = s * (x * y - z * w);        R[2] = s * (x * z + y * w);
+    R[3] = s * (x * y + z * w);        R[4] = 1.0f - s * (x * x + z * z); R[5] = s * (y * z - x * w);
+    R[6] = s * (x * z - y * w);        R[7] = s * (y * z + x * w);        R[8] = 1.0f - s * (x * x + y * y);
 }
 
 // || I - X Y^-1 ||_F for rigid X = [Rx tx], Y = [Ry ty] (Y^-1 = [Ry^T, -Ry^T ty]); rot_only drops the translation column
 __device__ __forceinline__ void frob_pair(const float* qx, const float* tx, const float* qy, const float* ty,
-                                          double* full, double* rot) {
-    double Rx[9], Ry[9], E[9];
-    quat_matrix64(qx, Rx); quat_matrix64(qy, Ry);
-    double acc = 0.0;
+                                          float* full, float* rot) {
+    float Rx[9], Ry[9], E[9];
+    quat_matrix32(qx, Rx); quat_matrix32(qy, Ry);
+    float acc = 0.f;
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-            double e = 0.0;
+            float e = 0.f;
 #pragma unroll
-            for (int k = 0; k < 3; ++k) e += Rx[i * 3 + k] * Ry[j * 3 + k];       // Rx Ry^T
+            for (int k = 0; k < 3; ++k) e = fmaf(Rx[i * 3 + k], Ry[j * 3 + k], e);       // Rx Ry^T
             E[i * 3 + j] = e;
-            const double d = (i == j ? 1.0 : 0.0) - e;
-            acc += d * d;
+            const float d = (i == j ? 1.0f : 0.0f) - e;
+            acc = fmaf(d, d, acc);
         }
-    *rot = sqrt(acc);
-    double tacc = 0.0;
+    *rot = sqrtf(acc);
+    float tacc = 0.f;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-        const double d = (double)tx[i] - (E[i * 3] * (double)ty[0] + E[i * 3 + 1] * (double)ty[1] + E[i * 3 + 2] * (double)ty[2]);
-        tacc += d * d;
+        const float d = tx[i] - (E[i * 3] * ty[0] + E[i * 3 + 1] * ty[1] + E[i * 3 + 2] * ty[2]);
+        tacc = fmaf(d, d, tacc);
     }
-    *full = sqrt(acc + tacc);
+    *full = sqrtf(acc + tacc);
 }
 
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -61,11 +69,18 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // gt_quat/pred_quat [B,T,22,4], gt_jpos/pred_jpos [B,T,22,3], floors [B] (gt, pred); out [B, MET_OUT]
+// ncu (round 1): the first version spent ~440 instructions per frame per warp (divergent two- and four-lane branches with
+// sqrt / exp2 / divisions executed by whole warps, three warp reductions per frame) and was issue-bound at 190 us for 2048
+// sequences.  Now every branch-specific quantity has its own lane mapping:
+//   pass A  lane = joint            MPJPE terms, acceleration terms (per-lane sums over frames, reduced once at the end)
+//   pass B  lane = (frame, root|head)        translation errors and pose-matrix distances
+//   pass C  lane = (frame, foot joint)       foot sliding
 static __global__ void __launch_bounds__(MET_WARPS * 32, 3)
 eval_metrics_kernel(const float* __restrict__ gt_quat, const float* __restrict__ gt_jpos, const float* __restrict__ gt_floor,
                     const float* __restrict__ pred_quat, const float* __restrict__ pred_jpos, const float* __restrict__ pred_floor,
                     int T, float* __restrict__ out) {
     __shared__ double red[MET_WARPS][MET_OUT];
+    __shared__ float sp[2][(MET_CHUNK + 2) * NJ * 3];     // [pred | gt] joint positions of the current chunk
     const int b = blockIdx.x, warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const bool jl = lane < NJ;
     const float* gq = gt_quat + (long long)b * T * NJ * 4;
@@ -73,76 +88,81 @@ eval_metrics_kernel(const float* __restrict__ gt_quat, const float* __restrict__
     const float* gj = gt_jpos + (long long)b * T * NJ * 3;
     const float* pj = pred_jpos + (long long)b * T * NJ * 3;
     const float gfl = gt_floor[b], pfl = pred_floor[b];
-    // per-thread partials: lane-owned (jpe of joint `lane`, foot sliding of the lane's foot joint) and warp-level (lane 0)
     double jpe = 0.0, s_acc_p = 0.0, s_acc_g = 0.0, s_acc_e = 0.0, s_fs_p = 0.0, s_fs_g = 0.0;
     double s_root_t = 0.0, s_head_t = 0.0, s_root_d = 0.0, s_root_r = 0.0, s_head_d = 0.0, s_head_r = 0.0;
-    const float hfoot = (lane == 7 || lane == 8) ? 0.08f : 0.04f;
-    const bool foot = lane == 7 || lane == 8 || lane == 10 || lane == 11;
+    const int lj = jl ? lane : 0;                        // lanes >= 22 shadow joint 0 (their results are discarded)
 
-    for (int t = warp; t < T; t += MET_WARPS) {
-        float p0[3] = {0, 0, 0}, g0[3] = {0, 0, 0};
-        if (jl) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) { p0[c] = pj[((long long)t * NJ + lane) * 3 + c]; g0[c] = gj[((long long)t * NJ + lane) * 3 + c]; }
+    for (int c0 = 0; c0 < T; c0 += MET_CHUNK) {
+        const int nload = min(MET_CHUNK + 2, T - c0) * NJ * 3;
+        __syncthreads();                                   // previous chunk fully consumed
+        for (int i = threadIdx.x; i < nload; i += MET_WARPS * 32) {
+            sp[0][i] = pj[(long long)c0 * NJ * 3 + i];
+            sp[1][i] = gj[(long long)c0 * NJ * 3 + i];
         }
-        // MPJPE: root-relative (fp32 subtraction like the reference's torch tensors), norm in fp32 -> fp64 sum
-        float dn = 0.f;
+        __syncthreads();
+        const int t_end = min(c0 + MET_CHUNK, T);
+        // ---- pass A: lane = joint ----
+        for (int t = c0 + warp; t < t_end; t += MET_WARPS) {
+            const float* P = sp[0] + (t - c0) * NJ * 3;
+            const float* G = sp[1] + (t - c0) * NJ * 3;
+            float p0[3], g0[3], dn = 0.f;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float pr = p0[c] - __shfl_sync(0xffffffffu, p0[c], 0), gr = g0[c] - __shfl_sync(0xffffffffu, g0[c], 0);
-            const float d = pr - gr;
-            dn += d * d;
-        }
-        if (jl) jpe += (double)sqrtf(dn);
-        // translation errors of root (lane 0) and head (lane 15)
-        if (lane == 0 || lane == HEAD_IDX) {
-            float d2 = 0.f;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) { const float d = p0[c] - g0[c]; d2 += d * d; }
-            if (lane == 0) s_root_t += (double)sqrtf(d2); else s_head_t += (double)sqrtf(d2);
-        }
-        // accelerations over frames t, t+1, t+2 (T - 2 terms), mean over the 22 joints
-        if (t + 2 < T) {
-            float ap = 0.f, ag = 0.f, ae = 0.f;
-            if (jl) {
+            for (int c = 0; c < 3; ++c) {
+                p0[c] = P[lj * 3 + c]; g0[c] = G[lj * 3 + c];
+                const float d = (p0[c] - P[c]) - (g0[c] - G[c]);      // root-relative, fp32 like the reference's tensors
+                dn = fmaf(d, d, dn);
+            }
+            jpe += (double)sqrtf(dn);
+            if (t + 2 < T) {                               // warp-uniform
+                float ap = 0.f, ag = 0.f, ae = 0.f;
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    const float p1 = pj[((long long)(t + 1) * NJ + lane) * 3 + c], p2 = pj[((long long)(t + 2) * NJ + lane) * 3 + c];
-                    const float g1 = gj[((long long)(t + 1) * NJ + lane) * 3 + c], g2 = gj[((long long)(t + 2) * NJ + lane) * 3 + c];
+                    const float p1 = P[(NJ + lj) * 3 + c], p2 = P[(2 * NJ + lj) * 3 + c], g1 = G[(NJ + lj) * 3 + c], g2 = G[(2 * NJ + lj) * 3 + c];
                     const float a_p = (p2 - p1) - (p1 - p0[c]), a_g = (g2 - g1) - (g1 - g0[c]);       // compute_accel: diff of velocities
                     const float e_p = p0[c] - 2.f * p1 + p2, e_g = g0[c] - 2.f * g1 + g2;             // compute_error_accel form
-                    ap += a_p * a_p; ag += a_g * a_g; ae += (e_p - e_g) * (e_p - e_g);
+                    ap = fmaf(a_p, a_p, ap); ag = fmaf(a_g, a_g, ag); ae = fmaf(e_p - e_g, e_p - e_g, ae);
                 }
+                s_acc_p += (double)sqrtf(ap); s_acc_g += (double)sqrtf(ag); s_acc_e += (double)sqrtf(ae);   // per joint; /22 at the end
             }
-            const double wp = warp_sum(jl ? (double)sqrtf(ap) : 0.0), wg = warp_sum(jl ? (double)sqrtf(ag) : 0.0),
-                         we = warp_sum(jl ? (double)sqrtf(ae) : 0.0);
-            if (lane == 0) { s_acc_p += wp / NJ; s_acc_g += wg / NJ; s_acc_e += we / NJ; }
         }
-        // foot sliding (frames t, t+1): |disp_xy| * (2 - 2^(z/H)) where z < H, heights relative to the floor
-        if (foot && t + 1 < T) {
-            const float p1x = pj[((long long)(t + 1) * NJ + lane) * 3], p1y = pj[((long long)(t + 1) * NJ + lane) * 3 + 1];
-            const float g1x = gj[((long long)(t + 1) * NJ + lane) * 3], g1y = gj[((long long)(t + 1) * NJ + lane) * 3 + 1];
-            const float zp = p0[2] - pfl, zg = g0[2] - gfl;
-            if (zp < hfoot) s_fs_p += (double)fabsf(sqrtf((p1x - p0[0]) * (p1x - p0[0]) + (p1y - p0[1]) * (p1y - p0[1])) * (2.f - exp2f(zp / hfoot)));
-            if (zg < hfoot) s_fs_g += (double)fabsf(sqrtf((g1x - g0[0]) * (g1x - g0[0]) + (g1y - g0[1]) * (g1y - g0[1])) * (2.f - exp2f(zg / hfoot)));
+        // ---- pass B: lane = (frame, root | head): translation errors + pose-matrix distances (quaternions from global) ----
+        for (int t0 = c0 + warp * 16; t0 < t_end; t0 += MET_WARPS * 16) {
+            const int t = t0 + (lane & 15), j = lane < 16 ? 0 : HEAD_IDX;
+            if (t < t_end) {
+                const float* P = sp[0] + ((t - c0) * NJ + j) * 3;
+                const float* G = sp[1] + ((t - c0) * NJ + j) * 3;
+                const float pp[3] = {P[0], P[1], P[2]}, gp[3] = {G[0], G[1], G[2]};
+                const float dx = pp[0] - gp[0], dy = pp[1] - gp[1], dz = pp[2] - gp[2];
+                const float te = sqrtf(dx * dx + dy * dy + dz * dz);
+                float full, rot;
+                const long long o = (long long)t * NJ + j;
+                frob_pair(pq + o * 4, pp, gq + o * 4, gp, &full, &rot);
+                if (lane < 16) { s_root_t += (double)te; s_root_d += (double)full; s_root_r += (double)rot; }
+                else           { s_head_t += (double)te; s_head_d += (double)full; s_head_r += (double)rot; }
+            }
+        }
+        // ---- pass C: lane = (frame, foot joint): |disp_xy| (2 - 2^(z/H)) where z < H, heights relative to the floor ----
+        for (int t0 = c0 + warp * 8; t0 < t_end; t0 += MET_WARPS * 8) {
+            const int t = t0 + (lane & 7), f = lane >> 3;                  // f: l ankle, l toe, r ankle, r toe
+            if (t < t_end && t + 1 < T) {
+                const int j = f == 0 ? 7 : (f == 1 ? 10 : (f == 2 ? 8 : 11));
+                const float h = (f & 1) ? 0.04f : 0.08f;
+                const float* P = sp[0] + ((t - c0) * NJ + j) * 3;
+                const float* G = sp[1] + ((t - c0) * NJ + j) * 3;
+                const float zp = P[2] - pfl, zg = G[2] - gfl;
+                const float dpx = P[NJ * 3] - P[0], dpy = P[NJ * 3 + 1] - P[1], dgx = G[NJ * 3] - G[0], dgy = G[NJ * 3 + 1] - G[1];
+                if (zp < h) s_fs_p += (double)fabsf(sqrtf(dpx * dpx + dpy * dpy) * (2.f - exp2f(zp / h)));
+                if (zg < h) s_fs_g += (double)fabsf(sqrtf(dgx * dgx + dgy * dgy) * (2.f - exp2f(zg / h)));
+            }
         }
     }
-    // pose-matrix distances (fp64, ~300 flops per pose pair): a second pass with lane = (frame, root | head), so all 32 lanes
-    // carry fp64 work instead of two lanes per frame holding up their warp
-    for (int t0 = warp * 16; t0 < T; t0 += MET_WARPS * 16) {
-        const int t = t0 + (lane & 15), j = lane < 16 ? 0 : HEAD_IDX;
-        if (t < T) {
-            const long long o = (long long)t * NJ + j;
-            const float pp[3] = {pj[o * 3], pj[o * 3 + 1], pj[o * 3 + 2]}, gp[3] = {gj[o * 3], gj[o * 3 + 1], gj[o * 3 + 2]};
-            double full, rot;
-            frob_pair(pq + o * 4, pp, gq + o * 4, gp, &full, &rot);
-            if (lane < 16) { s_root_d += full; s_root_r += rot; } else { s_head_d += full; s_head_r += rot; }
-        }
-    }
+    if (!jl) { jpe = 0.0; s_acc_p = 0.0; s_acc_g = 0.0; s_acc_e = 0.0; }
+    s_acc_p = warp_sum(s_acc_p) / NJ; s_acc_g = warp_sum(s_acc_g) / NJ; s_acc_e = warp_sum(s_acc_e) / NJ;
+    s_root_t = warp_sum(s_root_t); s_head_t = warp_sum(s_head_t);
     s_root_d = warp_sum(s_root_d); s_root_r = warp_sum(s_root_r); s_head_d = warp_sum(s_head_d); s_head_r = warp_sum(s_head_r);
     // warp-level assembly: scalars into red[warp][0..12], per-joint jpe sums into red[warp][13 + joint]
     const double fs_p = warp_sum(s_fs_p), fs_g = warp_sum(s_fs_g);
-    const double head_t = __shfl_sync(0xffffffffu, s_head_t, HEAD_IDX), head_d = s_head_d, head_r = s_head_r;
+    const double head_t = s_head_t, head_d = s_head_d, head_r = s_head_r;
     if (lane == 0) {
         double* r = red[warp];
         r[0] = s_root_t; r[1] = s_acc_p; r[2] = s_acc_g; r[3] = s_acc_e; r[4] = fs_p; r[5] = fs_g; r[6] = head_t;
