@@ -254,6 +254,38 @@ def next_rows(dev, B, T, pk):
     return out
 
 
+def config1_latency(dev, T):
+    """BASELINE configs[0] shape on the GPU: ONE window, T=120, a 50-step schedule (the reference's CPU-runnable case; the
+    survey probe measured 0.68 s on 8 CPU cores) -- latency of sample() through the host mirror, CUDA events, plus B=1 at the
+    full 1000-step schedule."""
+    import torch
+    import egoego_release_b200 as E
+    from oracle import egoego_oracle as O
+    out = {}
+    xs, cm = synth_inputs(1, T)
+    xs, cm = xs.to(dev), cm.to(dev)
+    for N in (50, 1000):
+        m = E.CondGaussianDiffusion(d_feats=198, d_model=512, n_dec_layers=4, n_head=4, d_k=256, d_v=256, max_timesteps=121,
+                                    out_dim=198, timesteps=N, objective="pred_x0", loss_type="l1", max_batch=1)
+        m.load_state_dict(O.init_params(0), strict=False)
+        m = m.to(dev)
+        for _ in range(2):
+            m.sample(xs, cm)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        reps = 5 if N == 50 else 2
+        for _ in range(reps):
+            m.sample(xs, cm)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        out[f"B1_T{T}_N{N}"] = {"ms_per_sample_call": ms, "windows_per_s": 1e3 / ms, "us_per_diffusion_step": ms * 1e3 / N,
+                                "precise_last_steps": m.precise_last_steps()}
+        del m
+    return out
+
+
 def torch_gpu_baseline(dev, B, T, N, n_steps=12):
     """The reference's own arithmetic (oracle port: same op sequence) as stock PyTorch eager fp32 on this B200 --
     the denominator of north_star's ">= 10x the reference single-GPU PyTorch sampling throughput"."""
@@ -393,7 +425,7 @@ def main():
         "dtype": (f"fp16 single-pass for t>={K_prec}, bf16x3-split for t<{K_prec} (fp32 accumulate)" if K_prec < N else
                   "bf16x3-split (fp32 accumulate)") if eng == "tcgen05" else "f32",
         "data": "synthetic", "config": dict(cfg, engine=eng, precise_last_steps=K_prec),
-        "e2e": {"value": e2e, "unit": "windows/s", "h2d_bytes_per_step": 2 * B * T * D * 4, "d2h_bytes_per_step": B * T * D * 4},
+        "e2e": {"value": e2e, "unit": "windows/s", "h2d_bytes_per_step": 2 * B * T * D * 4 * world, "d2h_bytes_per_step": B * T * D * 4 * world},
         "gpu_launches": int(launches), "clocks": clocks,
         "path_roofline": {"bound": "tensor", "achieved": path_tflops, "peak": peak, "unit": "TFLOP/s", "frac": path_tflops / peak,
                           "scope": "whole sampling path: algorithmic 2.8507 TFLOP per 1000-step window / wall time, per GPU"},
@@ -449,6 +481,7 @@ def main():
     if world == 1:
         try:
             line["next_rows"] = next_rows(dev, B, T, pk)
+            line["single_window_latency"] = config1_latency(dev, T)
         except Exception as ex:   # reported extras only; never masks the headline numbers
             line["next_rows"] = {"error": repr(ex)[:200]}
     if world == 1 and not os.environ.get("EGOEGO_BENCH_SKIP_TORCH"):

@@ -82,10 +82,10 @@ class Tape:
         torch.randn, torch.randn_like = self._r, self._rl
 
 
-def build_model(M, params, timesteps):
+def build_model(M, params, timesteps, objective="pred_x0"):
     m = M.CondGaussianDiffusion(d_feats=198, d_model=512, n_dec_layers=4, n_head=4, d_k=256, d_v=256,
                                 max_timesteps=121, out_dim=198, timesteps=timesteps,
-                                objective="pred_x0", loss_type="l1")
+                                objective=objective, loss_type="l1")
     missing, unexpected = m.load_state_dict(params, strict=False)
     assert not unexpected, unexpected
     assert all(k in O.make_schedule(10) for k in missing), missing  # only schedule buffers
@@ -105,6 +105,27 @@ def synth_x_start(seed, B, T):
     return torch.from_numpy(x)
 
 
+def gen_pred_noise(M, params, out):
+    """(vii) the constructor's default objective, `pred_noise` (transformer_cond_diffusion_model.py:233-236; no shipped script
+    uses it): sample() at N=20, B=2, and three p_sample steps.  Kept in its own file so the other goldens stay byte-identical."""
+    res = {}
+    m = build_model(M, params, 20, objective="pred_noise")
+    xs = synth_x_start(171, 2, 120)
+    cm = O.prep_head_condition_mask(xs.shape)
+    with Tape(71):
+        res["sample_n20_b2_seed71"] = m.sample(xs, cm).numpy()
+    m.eval()                                   # p_sample does not toggle eval itself (sample() does): dropout off
+    rng = Tape(72)
+    x, xc = rng.draw((2, 30, 198)), rng.draw((2, 30, 198))
+    seq = []
+    for t in (12, 7, 0):   # well-conditioned steps: at t = N-1 the cosine schedule has 1/abar ~ 1e5 and x0 amplifies fp32 rounding
+        with rng:
+            x = m.p_sample(x, torch.full((2,), t, dtype=torch.long), xc)
+        seq.append(x.numpy().copy())
+    res["p_sample_t30"] = np.stack(seq)
+    np.savez(os.path.join(out, "pred_noise.npz"), **res)
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     M = import_reference()
@@ -112,6 +133,10 @@ def main():
     os.makedirs(out, exist_ok=True)
     params = O.init_params(seed=0)
     ds = O.MotionDataStub()
+    if "--only-pred-noise" in sys.argv:
+        gen_pred_noise(M, params, out)
+        print("wrote pred_noise.npz")
+        return
 
     # (iv) schedule buffers, N=1000 and N=50
     for N in (1000, 50):
@@ -183,6 +208,7 @@ def main():
     with Tape(51):
         aa, root = m50.sample_sliding_window_w_canonical(ds, hp[:, :, :3], hp[:, :, 3:], x_start=data, cond_mask=cm)
     np.savez(os.path.join(out, "sliding_window.npz"), aa=aa.numpy(), root=root.numpy())
+    gen_pred_noise(M, params, out)
     print("goldens written:", sorted(os.listdir(out)))
 
 

@@ -100,6 +100,33 @@ def test_sample_1000_steps_vs_golden(engine, golden_dir, params0):
     assert jerr < JPOS_TOL_M
 
 
+@pytest.mark.parametrize("engine", ENGINES)
+def test_pred_noise_objective_vs_golden(engine, golden_dir, params0):
+    """objective='pred_noise' (the reference constructor's default, :233-236): x0 = sqrt(1/abar) x - sqrt(1/abar - 1) eps."""
+    import egoego_release_b200 as E
+    g = _g(golden_dir, "pred_noise.npz")
+    N, B = 20, 2
+    m = E.CondGaussianDiffusion(d_feats=198, d_model=512, n_dec_layers=4, n_head=4, d_k=256, d_v=256, max_timesteps=121,
+                                out_dim=198, timesteps=N, objective="pred_noise", max_batch=B, engine=engine)
+    m.load_state_dict(params0, strict=False)
+    m = m.cuda()
+    xs = synth_x_start(171, B, 120)
+    cm = O.prep_head_condition_mask(xs.shape)
+    tp = Tape(71)
+    m.set_noise_tape(torch.stack([tp.draw(xs.shape) for _ in range(N + 2)]).cuda())
+    y = m.sample(xs.cuda(), cm.cuda())
+    ref = torch.from_numpy(g["sample_n20_b2_seed71"])
+    raw, jerr = maxabs(y, ref), maxabs(joints(y), joints(ref))
+    print(f"[{engine}] pred_noise sample N=20: raw max-abs {raw:.3e}, joint max-abs {jerr * 1e3:.4f} mm")
+    assert jerr < JPOS_TOL_M
+    m.set_noise_tape(None)
+    rng = Tape(72)
+    x, xc = rng.draw((2, 30, 198)).cuda(), rng.draw((2, 30, 198)).cuda()
+    for k, t in enumerate((12, 7, 0)):
+        x = m.p_sample(x, torch.full((2,), t, dtype=torch.long, device="cuda"), xc, noise=rng.draw(x.shape).cuda())
+        assert maxabs(x, g["p_sample_t30"][k]) < (2e-4 if engine == "simt" else 2e-3), (t, maxabs(x, g["p_sample_t30"][k]))
+
+
 def test_postprocess_vs_golden(golden_dir, params0):
     import egoego_release_b200 as E
     g = _g(golden_dir, "postprocess.npz")
