@@ -72,6 +72,8 @@ struct egoego_ctx {
 namespace egoego {
 
 static inline dim3 grid1d(long long n, int bs) { return dim3((unsigned)((n + bs - 1) / bs)); }
+// ddpm_update_kernel: x = quads (4 consecutive elements) of one window in blocks of 256 threads, y = window
+static inline dim3 ddpm_grid(int T, int D, int B) { return dim3((unsigned)(((T * D + 3) / 4 + 255) / 256), (unsigned)B); }
 
 // ---- SIMT engine: one denoiser call.  Expects Ain staged; writes model_out[B,T,D]. ---------------
 static int denoiser_simt(egoego_ctx* c, int B, int T, TSrc ts, const float* pmask, cudaStream_t s) {
@@ -195,7 +197,7 @@ int egoego_create(const egoego_cfg* cfg, egoego_handle* out) {
     EG_CHECK(cfg->d_feats >= 1 && cfg->d_feats <= 256 && cfg->d_feats % 2 == 0, "d_feats must be even and <= 256");
     EG_CHECK(cfg->timesteps >= 1, "timesteps must be >= 1");
     EG_CHECK(cfg->objective == 0 || cfg->objective == 1, "objective must be 0 (pred_noise) or 1 (pred_x0)");
-    EG_CHECK(cfg->max_batch >= 1, "max_batch must be >= 1");
+    EG_CHECK(cfg->max_batch >= 1 && cfg->max_batch <= 65535, "max_batch must be in [1, 65535]");
     EG_CHECK(cfg->engine == EGOEGO_ENGINE_TCGEN05 || cfg->engine == EGOEGO_ENGINE_SIMT, "unknown engine");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -475,8 +477,7 @@ int egoego_p_sample_step(egoego_handle c, const float* x, const int64_t* t_dev, 
         DdpmArgs a;
         fill_ddpm(c, a, x + off, x_out + off, ts, ns, clip, inpaint ? inpaint + (size_t)b0 * inpaint_len * D : nullptr,
                   inpaint_len, Bc, T, false);
-        long long quads = ((long long)T * D + 3) / 4 * Bc;
-        ddpm_update_kernel<<<grid1d(quads, 256), 256, 0, s>>>(a);
+        ddpm_update_kernel<<<ddpm_grid(T, D, Bc), 256, 0, s>>>(a);
         c->launches++;
         EG_CUDA(cudaGetLastError());
     }
@@ -511,7 +512,8 @@ static int sample_chunk(egoego_ctx* c, const float* x_start, const float* cond_m
     auto one_step = [&](cudaStream_t st, int fmt) -> int {
         a.stage_mode = (c->cfg.engine == EGOEGO_ENGINE_SIMT) ? 2 : (fmt ? 1 : 0);
         if (run_denoiser(c, Bc, T, ts, nullptr, st, fmt, fused ? &a : nullptr)) return 1;
-        LaunchCfg ld((unsigned)((quads + 255) / 256), 256, 0, st), la(1, 32, 0, st);
+        LaunchCfg ld(1, 256, 0, st), la(1, 32, 0, st);
+        ld.cfg.gridDim = ddpm_grid(T, D, Bc);
         if (!fused) { EG_CUDA(cudaLaunchKernelEx(&ld.cfg, ddpm_update_kernel, a)); c->launches++; }
         EG_CUDA(cudaLaunchKernelEx(&la.cfg, advance_step_kernel, d_step));
         c->launches += 1;
@@ -713,12 +715,11 @@ int egoego_time_kernel(egoego_handle c, int B, int T, int which, int half_fmt, i
     if (which < EGOEGO_KERNEL_DDPM_UPDATE)   // linear_out is timed as the sampling loop runs it: with the fused DDPM epilogue when that is on
         return c->tc->time_stage(B, T, which, half_fmt ? 1 : 0, iters, c->model_out.as<float>(), s, ms_per_launch,
                                  (which == EGOEGO_KERNEL_OUT && c->fuse_ddpm) ? &a : nullptr);
-    const long long quads = ((long long)T * c->D + 3) / 4 * B;
     cudaEvent_t e0, e1;
     EG_CUDA(cudaEventCreate(&e0)); EG_CUDA(cudaEventCreate(&e1));
-    for (int i = 0; i < 3; ++i) ddpm_update_kernel<<<grid1d(quads, 256), 256, 0, s>>>(a);
+    for (int i = 0; i < 3; ++i) ddpm_update_kernel<<<ddpm_grid(T, c->D, B), 256, 0, s>>>(a);
     EG_CUDA(cudaEventRecord(e0, s));
-    for (int i = 0; i < iters; ++i) ddpm_update_kernel<<<grid1d(quads, 256), 256, 0, s>>>(a);
+    for (int i = 0; i < iters; ++i) ddpm_update_kernel<<<ddpm_grid(T, c->D, B), 256, 0, s>>>(a);
     EG_CUDA(cudaEventRecord(e1, s));
     EG_CUDA(cudaEventSynchronize(e1));
     EG_CUDA(cudaGetLastError());

@@ -426,12 +426,12 @@ static __global__ void stage_rows_split_kernel(__nv_bfloat16* __restrict__ Ahi, 
 static __global__ void ddpm_update_kernel(DdpmArgs a) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");          // PDL: everything below reads the previous kernel's output
-    const long long epw = (long long)a.T * a.D;
-    const long long quads_pw = (epw + 3) / 4;
-    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= quads_pw * a.B) return;
-    const int w = (int)(gid / quads_pw);
-    const int e0 = (int)(gid % quads_pw) * 4;
+    // 32-bit index arithmetic throughout (the kernel is issue-bound: 64-bit divisions cost more than the Philox rounds);
+    // grid = (quads of one window, windows)
+    const int epw = a.T * a.D;
+    const int w = blockIdx.y;
+    const int e0 = (int)(blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (e0 >= epw) return;
     const int t = a.ts.get(w);
     const float c1 = a.coef1[t], c2 = a.coef2[t];
     const float sigma = (t == 0) ? 0.f : expf(0.5f * a.logvar[t]);
@@ -467,11 +467,13 @@ static __global__ void ddpm_update_kernel(DdpmArgs a) {
         v[r] = (c1 * x0 + c2 * xv[r]) + sigma * nz[r];
     }
     // d_feats is even and e0 is a multiple of 4: the pairs (e0, e0+1) and (e0+2, e0+3) never straddle a frame
+    const int f0 = (int)((unsigned)e0 / (unsigned)a.D), c0 = e0 - f0 * a.D;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         const int e = e0 + 2 * h;
         if (e >= epw) break;
-        const int f = e / a.D, c = e % a.D;
+        const bool wrap = c0 + 2 * h >= a.D;             // the second pair may start the next frame (d_feats is even)
+        const int f = f0 + (wrap ? 1 : 0), c = c0 + 2 * h - (wrap ? a.D : 0);
         if (a.inpaint && f < a.inpaint_len) {
             const float* ip = a.inpaint + ((long long)w * a.inpaint_len + f) * a.D + c;
             v[2 * h] = ip[0]; v[2 * h + 1] = ip[1];
