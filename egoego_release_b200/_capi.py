@@ -14,7 +14,8 @@ EXPORTS = [
     "egoego_precise_last_steps", "egoego_eval_metrics", "egoego_launches_per_step",
     "egoego_seqnet_create", "egoego_seqnet_destroy", "egoego_seqnet_set_tensor", "egoego_seqnet_commit", "egoego_seqnet_forward",
     "egoego_seqnet_launch_count", "egoego_va2rot", "egoego_rescale_slam", "egoego_slam_features", "egoego_apply_floor_normal",
-    "egoego_rigid_apply",
+    "egoego_rigid_apply", "egoego_resnet18_create", "egoego_resnet18_destroy", "egoego_resnet18_set_tensor", "egoego_resnet18_commit",
+    "egoego_resnet18_forward", "egoego_resnet18_launch_count",
 ]
 
 ENGINE_TCGEN05, ENGINE_SIMT = 0, 1
@@ -92,8 +93,17 @@ def lib():
     L.egoego_slam_features.argtypes = [i32, vp, vp, i32, i32, i32, vp, vp]
     L.egoego_apply_floor_normal.argtypes = [i32, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp]
     L.egoego_rigid_apply.argtypes = [i32, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp]
+    L.egoego_resnet18_create.argtypes = [i32, i32, C.POINTER(vp)]
+    L.egoego_resnet18_destroy.argtypes = [vp]
+    L.egoego_resnet18_destroy.restype = None
+    L.egoego_resnet18_set_tensor.argtypes = [vp, C.c_char_p, vp, i64]
+    L.egoego_resnet18_commit.argtypes = [vp]
+    L.egoego_resnet18_forward.argtypes = [vp, vp, i32, vp, vp]
+    L.egoego_resnet18_launch_count.argtypes = [vp]
+    L.egoego_resnet18_launch_count.restype = i64
     for name in EXPORTS:
-        if name not in ("egoego_last_error", "egoego_launch_count", "egoego_seqnet_destroy", "egoego_seqnet_launch_count"):
+        if name not in ("egoego_last_error", "egoego_launch_count", "egoego_seqnet_destroy", "egoego_seqnet_launch_count",
+                        "egoego_resnet18_destroy", "egoego_resnet18_launch_count"):
             getattr(L, name).restype = i32
     _lib = L
     return L

@@ -6,8 +6,9 @@ so ``load_state_dict(ckpt['transformer_encoder_state_dict'])`` and the calls in 
 All arithmetic runs in libegoego_b200 (csrc/stage1.cu) through the C ABI (``egoego_seqnet_*``, ``egoego_va2rot`` ...):
 there is no PyTorch / CPU fallback, CPU tensors are moved to the module's CUDA device.
 
-Not built (and why): the ResNet-18 optical-flow encoder (``input_of_feats=False``; the shipped pipeline feeds pre-extracted
-512-d RAFT features), training losses, and evo's Umeyama xy-plane fit inside ``HeadNormalFormer.forward_for_eval`` (evo is a
+``HeadFormer(opt)`` with ``opt.input_of_feats=False`` runs the ResNet-18 optical-flow encoder (egoego/model/resnet.py) in
+csrc/resnet.cu (inference, eval-mode BatchNorm folded into fused conv+bias+residual+ReLU kernels).
+Not built (and why): training losses, and evo's Umeyama xy-plane fit inside ``HeadNormalFormer.forward_for_eval`` (evo is a
 third-party dependency that is absent here) -- that one step is a host callable ``xy_align`` (default: evo when importable,
 else the restated published algorithm, "parity unpinned").
 """
@@ -139,6 +140,21 @@ class _SeqNetModule(nn.Module):
         return dec, outs
 
 
+class _ResNetParams(nn.Module):
+    """Parameter holder with the state_dict layout of egoego/model/resnet.py's ``ResNet`` (``resnet.*`` = torchvision's
+    resnet18 with ``fc`` -> out_dim).  Never run through PyTorch: the forward pass is csrc/resnet.cu."""
+
+    def __init__(self, out_dim):
+        super().__init__()
+        try:
+            from torchvision import models
+        except ImportError as ex:                        # the reference needs torchvision for this path too
+            raise EgoEgoError("the ResNet-18 flow encoder needs torchvision for its parameter container") from ex
+        self.out_dim = out_dim
+        self.resnet = models.resnet18(weights=None)
+        self.resnet.fc = nn.Linear(self.resnet.fc.in_features, out_dim)
+
+
 class HeadFormer(_SeqNetModule):
     """HeadNet (egoego/model/head_estimation_transformer.py:48-308): optical-flow features -> head angular velocity
     (integrated to rotations) and per-frame travelled distance (fixes the scale of the SLAM trajectory)."""
@@ -152,14 +168,65 @@ class HeadFormer(_SeqNetModule):
         self.cnn_fdim = 512
         self.transformer_window_size = opt.window
         self.input_of_feats = getattr(opt, "input_of_feats", True)
-        if not self.input_of_feats:
-            raise NotImplementedError("the ResNet-18 optical-flow encoder is not part of the B200 path: extract the 512-d "
-                                      "features off line and pass --input_of_feats (scripts/test_egoego_pipeline.sh)")
+        self._cnn_h = None
+        self._cnn_sig = None
+        if not self.input_of_feats:                      # raw optical flow: ResNet-18 encoder (inference only; always frozen here)
+            self.cnn = _ResNetParams(self.cnn_fdim)
+            self.freeze_of_cnn = getattr(opt, "freeze_of_cnn", True)
         self._init_net(self.cnn_fdim, opt.d_model, opt.n_dec_layers, opt.n_head, opt.d_k, opt.d_v, opt.window)
         self.action_va_mlp = _MLPParams(opt.d_model, self._heads[0][1])
         self.action_va_fc = nn.Linear(256, 3)
         self.action_dist_mlp = _MLPParams(opt.d_model, self._heads[1][1])
         self.action_dist_fc = nn.Linear(256, 1)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_cnn_h", None) is not None:
+                _capi.lib().egoego_resnet18_destroy(self._cnn_h)
+        except Exception:
+            pass
+        super().__del__()
+
+    def _cnn_handle(self):
+        dev = self._cuda_device()
+        sd = self.cnn.state_dict()
+        sig = (dev.index or 0, tuple((k, v._version, v.data_ptr()) for k, v in sd.items()))
+        if self._cnn_h is not None and sig == self._cnn_sig:
+            return self._cnn_h
+        L = _capi.lib()
+        if self._cnn_h is not None:
+            L.egoego_resnet18_destroy(self._cnn_h)
+            self._cnn_h = None
+        h = C.c_void_p()
+        check(L.egoego_resnet18_create(dev.index or 0, self.cnn_fdim, C.byref(h)))
+        try:
+            for k, v in sd.items():
+                if not k.startswith("resnet.") or k.endswith("num_batches_tracked"):
+                    continue
+                t = v.detach().to("cpu", torch.float32).contiguous()
+                check(L.egoego_resnet18_set_tensor(h, k[len("resnet."):].encode(), t.data_ptr(), t.numel()))
+            check(L.egoego_resnet18_commit(h))
+        except Exception:
+            L.egoego_resnet18_destroy(h)
+            raise
+        self._cnn_h, self._cnn_sig = h, sig
+        return h
+
+    @torch.no_grad()
+    def _input_features(self, data):
+        """:215-224: pre-extracted features [B,T,512], or raw flow [B,T,224,224,2] through the ResNet-18 encoder (eval-mode
+        BatchNorm; the reference appends one zero channel, which the kernel's channel padding subsumes)."""
+        dev = self._cuda_device()
+        of = _f32(data["of"], dev)
+        if self.input_of_feats:
+            return of
+        if of.dim() != 5 or tuple(of.shape[2:]) != (224, 224, 2):
+            raise ValueError("optical flow must be [B,T,224,224,2]")
+        B, T = of.shape[:2]
+        feats = torch.empty(B * T, self.cnn_fdim, device=dev)
+        with torch.cuda.device(dev):
+            check(_capi.lib().egoego_resnet18_forward(self._cnn_handle(), of.data_ptr(), B * T, feats.data_ptr(), _stream(dev)))
+        return feats.reshape(B, T, self.cnn_fdim)
 
     @torch.no_grad()
     def va2rot(self, curr_rot, pred_head_vels, dt=1 / 30):
@@ -205,7 +272,7 @@ class HeadFormer(_SeqNetModule):
     def forward(self, data):
         """:126-182 for sequences of at most one window: head_va, head_rot_quat [B,T+1,4], head_dist_scalar."""
         dev = self._cuda_device()
-        feats = _f32(data["of"], dev)
+        feats = self._input_features(data)
         if feats.shape[1] > self.transformer_window_size:
             raise ValueError("forward() takes one window; use forward_for_eval for longer sequences")
         va, dist = self._va_dist(feats)
@@ -220,7 +287,7 @@ class HeadFormer(_SeqNetModule):
         """:214-308.  data: 'of' [1,T,512], 'aligned_slam_trans' [1,T+1,3], 'head_pose' [1,T+1,7] (first quaternion used)
         -> {'head_pose': [1,T'',7], 'pred_scale': 0-d tensor}."""
         dev = self._cuda_device()
-        feats = _f32(data["of"], dev)
+        feats = self._input_features(data)
         va, dist = self._va_dist(feats)
         # the reference integrates block by block, restarting from the previous block's last rotation: one continuous scan
         quat = self.va2rot(_f32(data["head_pose"], dev)[:, 0, 3:], va)

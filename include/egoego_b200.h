@@ -220,6 +220,19 @@ int  egoego_apply_floor_normal(int device, const float* normal_dev, const float*
 int  egoego_rigid_apply(int device, const float* rot3x3_dev, const float* offset_dev, const float* rot_mat_dev, const float* trans_dev,
                         int B, int n_pose, float* trans_out_dev, float* rot_out_dev, float* quat_out_dev, void* stream);
 
+/* ResNet-18 optical-flow encoder of HeadNet (HeadFormer with input_of_feats=False): egoego/model/resnet.py:5-23 (torchvision
+ * resnet18 with fc -> out_dim) as called from head_estimation_transformer.py:216-224 on [T,224,224,2] flow + one zero channel.
+ * eval() semantics (BatchNorm with running statistics, folded into the convolutions at commit).  Tensor names = the
+ * state_dict keys of the wrapped torchvision model ("conv1.weight", "bn1.running_mean", "layer2.0.downsample.0.weight", ...,
+ * "fc.weight"), host fp32.  forward: flow_dev[N,224,224,2] -> feats_dev[N,out_dim]. */
+typedef struct egoego_resnet_ctx* egoego_resnet;
+int  egoego_resnet18_create(int device, int out_dim, egoego_resnet* out);
+void egoego_resnet18_destroy(egoego_resnet h);
+int  egoego_resnet18_set_tensor(egoego_resnet h, const char* name, const float* host_data, int64_t numel);
+int  egoego_resnet18_commit(egoego_resnet h);
+int  egoego_resnet18_forward(egoego_resnet h, const float* flow_dev, int N, float* feats_dev, void* stream);
+int64_t egoego_resnet18_launch_count(egoego_resnet h);
+
 /* Introspection for tests/bench: number of kernels launched by this handle since creation, and the
  * cumulative count of denoiser steps executed. */
 int64_t egoego_launch_count(egoego_handle h);

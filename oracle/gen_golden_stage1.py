@@ -98,6 +98,17 @@ def main():
             ta = ta - ta[:, 0:1] + head_pose[:, 0:1, :3]
             print(f"HeadNormalFormer seed {seed} T {T}: normal max-abs {float((mine - fwd).abs().max()):.2e}, "
                   f"trans {float((ta - ev['head_trans']).abs().max()):.2e}, rot {float((arm - ev['head_rot_mat']).abs().max()):.2e}")
+        # ResNet-18 optical-flow encoder: the reference's own wrapper class (egoego/model/resnet.py) around torchvision's resnet18
+        from egoego.model.resnet import ResNet
+        cnn = ResNet(512, running_stats=False, pretrained=False)
+        pr = S.init_resnet_params(9)
+        cnn.load_state_dict(pr, strict=True)
+        cnn.eval()
+        flow = S.synth_flow(51, 3)
+        feats = cnn(S.flow_to_cnn_input(flow))
+        out["resnet_s51_T3_feats"] = feats.numpy()
+        print(f"ResNet-18: restatement vs reference max-abs {float((S.resnet18_forward(pr, S.flow_to_cnn_input(flow)) - feats).abs().max()):.2e} "
+              f"(features in [{float(feats.min()):.3f}, {float(feats.max()):.3f}])")
     np.savez(os.path.join(ROOT, "tests", "golden", "stage1.npz"), **out)
     print("wrote tests/golden/stage1.npz", {k: v.shape for k, v in out.items()})
 

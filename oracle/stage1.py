@@ -229,3 +229,75 @@ def synth_stage1_inputs(seed: int, T: int):
     slam_rot = R.quaternion_to_matrix(R.quaternion_multiply(tiltq.expand(T + 1, 4), quat))
     slam_trans = torch.matmul(R.quaternion_to_matrix(tiltq)[0], slam_trans[:, :, None])[:, :, 0]
     return torch.from_numpy(feats), head_pose, slam_trans[None].contiguous(), slam_rot[None].contiguous()
+
+
+# ---- ResNet-18 optical-flow encoder (HeadFormer with input_of_feats=False) ---------------------------------------------------
+RESNET_PLANES = (64, 128, 256, 512)
+
+
+def init_resnet_params(seed: int, out_dim: int = 512) -> Dict[str, torch.Tensor]:
+    """Seeded weights with the state_dict layout of egoego/model/resnet.py's ``ResNet`` (keys ``resnet.*``: torchvision's
+    resnet18 with ``fc`` -> out_dim), incl. non-trivial BatchNorm running statistics (a trained checkpoint has them)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    p: Dict[str, torch.Tensor] = {}
+
+    def conv(name, cout, cin, k):
+        p[name + ".weight"] = _uniform(rng, (cout, cin, k, k), math.sqrt(2.0 / (cin * k * k)))
+
+    def bn(name, c):
+        p[name + ".weight"] = 1.0 + _uniform(rng, (c,), 0.1)
+        p[name + ".bias"] = _uniform(rng, (c,), 0.1)
+        p[name + ".running_mean"] = _uniform(rng, (c,), 0.2)
+        p[name + ".running_var"] = 1.0 + _uniform(rng, (c,), 0.2).abs()
+        p[name + ".num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
+
+    conv("resnet.conv1", 64, 3, 7); bn("resnet.bn1", 64)
+    inpl = 64
+    for L, planes in enumerate(RESNET_PLANES):
+        for blk in range(2):
+            pre = f"resnet.layer{L + 1}.{blk}."
+            stride = 2 if (L > 0 and blk == 0) else 1
+            conv(pre + "conv1", planes, inpl, 3); bn(pre + "bn1", planes)
+            conv(pre + "conv2", planes, planes, 3); bn(pre + "bn2", planes)
+            if stride != 1 or inpl != planes:
+                conv(pre + "downsample.0", planes, inpl, 1); bn(pre + "downsample.1", planes)
+            inpl = planes
+    bound = 1.0 / math.sqrt(512)
+    p["resnet.fc.weight"] = _uniform(rng, (out_dim, 512), bound / math.sqrt(3.0))
+    p["resnet.fc.bias"] = _uniform(rng, (out_dim,), bound / math.sqrt(3.0))
+    return p
+
+
+def resnet18_forward(p, x: torch.Tensor) -> torch.Tensor:
+    """torchvision resnet18 in eval mode (BatchNorm with running statistics), as egoego/model/resnet.py:16-17 runs it.
+    x [N,3,224,224] -> [N,out_dim]."""
+    def bn(name, h):
+        return F.batch_norm(h, p[name + ".running_mean"], p[name + ".running_var"], p[name + ".weight"], p[name + ".bias"], False, 0.0, 1e-5)
+
+    h = F.relu(bn("resnet.bn1", F.conv2d(x, p["resnet.conv1.weight"], None, 2, 3)))
+    h = F.max_pool2d(h, 3, 2, 1)
+    inpl = 64
+    for L, planes in enumerate(RESNET_PLANES):
+        for blk in range(2):
+            pre = f"resnet.layer{L + 1}.{blk}."
+            stride = 2 if (L > 0 and blk == 0) else 1
+            idt = h
+            o = F.relu(bn(pre + "bn1", F.conv2d(h, p[pre + "conv1.weight"], None, stride, 1)))
+            o = bn(pre + "bn2", F.conv2d(o, p[pre + "conv2.weight"], None, 1, 1))
+            if stride != 1 or inpl != planes:
+                idt = bn(pre + "downsample.1", F.conv2d(h, p[pre + "downsample.0.weight"], None, stride, 0))
+            h = F.relu(o + idt)
+            inpl = planes
+    h = F.adaptive_avg_pool2d(h, 1).flatten(1)
+    return F.linear(h, p["resnet.fc.weight"], p["resnet.fc.bias"])
+
+
+def flow_to_cnn_input(of: torch.Tensor) -> torch.Tensor:
+    """head_estimation_transformer.py:218-223: [B,T,224,224,2] -> zero third channel -> [B*T,3,224,224]."""
+    of = torch.cat((of, torch.zeros(of.shape[:-1] + (1,))), dim=-1)
+    return of.reshape(-1, 224, 224, 3).permute(0, 3, 1, 2)
+
+
+def synth_flow(seed: int, T: int) -> torch.Tensor:
+    rng = np.random.default_rng(seed)
+    return torch.from_numpy(rng.normal(0, 1, (1, T, 224, 224, 2)).astype(np.float32))

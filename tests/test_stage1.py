@@ -57,8 +57,18 @@ def test_mirror_state_dict_matches_reference_layout():
         for k, v in p.items():
             assert tuple(sd[k].shape) == tuple(v.shape), k
         m.load_state_dict(p, strict=True)
-    with pytest.raises(NotImplementedError):
-        HeadFormer(argparse.Namespace(**{**vars(OPT), "input_of_feats": False}), "cpu")
+    # raw-optical-flow variant: the ResNet-18 encoder's parameters appear under cnn.resnet.* exactly like the reference's
+    m = HeadFormer(argparse.Namespace(**{**vars(OPT), "input_of_feats": False}), "cpu")
+    p = {**S.init_params(1, S.CFG_HEAD), **{"cnn." + k: v for k, v in S.init_resnet_params(2).items()}}
+    assert set(m.state_dict()) == set(p)
+    m.load_state_dict(p, strict=True)
+
+
+def test_oracle_resnet_vs_reference_golden(gold):
+    with torch.no_grad():
+        feats = S.resnet18_forward(S.init_resnet_params(9), S.flow_to_cnn_input(S.synth_flow(51, 3)))
+    ref = gold["resnet_s51_T3_feats"]
+    assert np.abs(feats.numpy() - ref).max() < 1e-4 * np.abs(ref).max()
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only behaviour")
@@ -192,3 +202,32 @@ def test_gpu_full_pipeline_config4(params0):
     # the generated head follows the conditioning head trajectory (stage 2 is conditioned on it)
     m = E.compute_metrics_batch(out["global_jrot"], out["global_jpos"], torch.zeros(2), out["global_jrot"], out["global_jpos"], torch.zeros(2))
     assert float(m[:, 9].abs().max()) == 0.0
+
+
+@pytest.mark.gpu
+def test_gpu_resnet_encoder_and_raw_flow_headformer(gold):
+    """HeadFormer with input_of_feats=False: [1,T,224,224,2] flow -> ResNet-18 (csrc/resnet.cu) -> the same sequence net.
+    Features vs the golden of the reference's ResNet class (1e-3 of the feature range: 20 fp32 conv layers in a different
+    summation order), then the whole forward_for_eval vs the oracle's composition."""
+    from egoego_release_b200 import HeadFormer
+    opt = argparse.Namespace(**{**vars(OPT), "input_of_feats": False})
+    m = HeadFormer(opt, "cuda:0")
+    ph, pr = S.init_params(7, S.CFG_HEAD), S.init_resnet_params(9)
+    m.load_state_dict({**ph, **{"cnn." + k: v for k, v in pr.items()}}, strict=True)
+    m = m.cuda()
+    flow = S.synth_flow(51, 3)
+    feats = m._input_features({"of": flow}).cpu().numpy()[0]
+    ref = gold["resnet_s51_T3_feats"]
+    err = np.abs(feats - ref).max() / np.abs(ref).max()
+    print(f"ResNet-18 features: max-abs error {err:.2e} of the feature range")
+    assert err < 1e-3
+    # 19 frames (two encoder chunks of 16 + 3) through the whole HeadNet
+    flow = S.synth_flow(52, 19)
+    _, head_pose, slam_trans, _ = S.synth_stage1_inputs(52, 19)
+    res = m.forward_for_eval({"of": flow, "aligned_slam_trans": slam_trans, "head_pose": head_pose})
+    with torch.no_grad():
+        f_ref = S.resnet18_forward(pr, S.flow_to_cnn_input(flow))[None]
+        pose_ref, scale_ref = S.headformer_forward_for_eval(ph, f_ref, slam_trans, head_pose[:, 0, 3:])
+    perr = (res["head_pose"].cpu() - pose_ref).abs().max()
+    print(f"raw-flow HeadFormer: head pose max-abs {float(perr):.2e}, scale {float(res['pred_scale']):.5f} vs {float(scale_ref):.5f}")
+    assert perr < 2e-3 and abs(float(res["pred_scale"]) - float(scale_ref)) < 2e-3 * abs(float(scale_ref)) + 1e-5
