@@ -251,6 +251,19 @@ def next_rows(dev, B, T, pk):
                      "note": "fp32 CUDA-core sequence nets (d_model 256, 2 layers), eager launches incl. host glue; forward_for_eval of "
                              "HeadNormalFormer includes its device->host copy of the trajectory for the xy alignment callable",
                      "headformer_launches_per_call": (hf.launch_count() - l0) // 13}
+    # HeadNet with raw optical flow: ResNet-18 encoder (1.814 GFLOP per 224 x 224 frame, multiply-add = 2) on the demo's 139 frames
+    try:
+        opt2 = argparse.Namespace(**{**vars(opt), "input_of_feats": False})
+        hf2 = E.HeadFormer(opt2, dev)
+        hf2.load_state_dict({**S.init_params(7, S.CFG_HEAD), **{"cnn." + k: v for k, v in S.init_resnet_params(9).items()}})
+        hf2 = hf2.to(dev)
+        flow = torch.randn(1, 139, 224, 224, 2, device=dev)
+        ms = timed(lambda: hf2._input_features({"of": flow}), 5)
+        out["resnet18_encoder"] = {"frames": 139, "ms_per_call": ms, "frames_per_s": 139 / (ms * 1e-3), "bound": "fp32 CUDA cores",
+                                   "achieved": 139 * 1.814e9 / (ms * 1e-3) / 1e12, "unit": "TFLOP/s",
+                                   "note": "implicit-GEMM conv kernels with folded BatchNorm and fused bias + residual + ReLU epilogues (csrc/resnet.cu)"}
+    except Exception as ex:
+        out["resnet18_encoder"] = {"error": repr(ex)[:200]}
     return out
 
 
