@@ -23,14 +23,17 @@ struct ConvDesc { int Cin, Cout, kh, kw, stride, pad, Hin, Win, Hout, Wout; };
 
 // X NHWC [N,Hin,Win,Cin] (Cin % 4 == 0), Wf [Cout, Kpad] with k = (ky*kw + kx)*Cin + ci zero-padded to Kpad % 16 == 0,
 // Y / resid [M, Cout] (= NHWC of the output), M = N*Hout*Wout
-template <bool RELU, bool RESID>
+// BN = 128 or 64 output channels per tile (the 64-channel stem / layer1 convolutions are 64 % of the FLOPs: a 128-wide tile would
+// waste half of its columns on them)
+template <bool RELU, bool RESID, int BN>
 __global__ void __launch_bounds__(256) conv_igemm_kernel(const float* __restrict__ X, const float* __restrict__ Wf,
                                                          const float* __restrict__ bias, const float* __restrict__ resid,
                                                          float* __restrict__ Y, ConvDesc d, int M, int K, int Kpad) {
+    constexpr int NG = BN / 64;                         // column groups of 4 per thread (tx*4 + 64*g)
     __shared__ __align__(16) float As[16][128 + 4];
-    __shared__ __align__(16) float Bs[16][128 + 4];
+    __shared__ __align__(16) float Bs[16][BN + 4];
     const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
-    const int m0 = blockIdx.y * 128, n0 = blockIdx.x * 128;
+    const int m0 = blockIdx.y * 128, n0 = blockIdx.x * BN;
     // the two tile rows this thread gathers: r = tid / 4 and 64 + tid / 4
     const float* xb[2]; int iy0[2], ix0[2]; bool rv[2];
 #pragma unroll
@@ -43,11 +46,11 @@ __global__ void __launch_bounds__(256) conv_igemm_kernel(const float* __restrict
         iy0[it] = oy * d.stride - d.pad; ix0[it] = ox * d.stride - d.pad;
     }
     const int k4 = (tid % 4) * 4;
-    float acc[8][8];
+    float acc[8][4 * NG];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < 4 * NG; ++j) acc[i][j] = 0.f;
 
     for (int k0 = 0; k0 < Kpad; k0 += 16) {
         const int k = k0 + k4;
@@ -60,22 +63,24 @@ __global__ void __launch_bounds__(256) conv_igemm_kernel(const float* __restrict
             if (rv[it] && k < K && iy >= 0 && iy < d.Hin && ix >= 0 && ix < d.Win)
                 a = *reinterpret_cast<const float4*>(xb[it] + ((long long)iy * d.Win + ix) * d.Cin + ci);
             As[k4 + 0][r] = a.x; As[k4 + 1][r] = a.y; As[k4 + 2][r] = a.z; As[k4 + 3][r] = a.w;
-            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (n0 + r < d.Cout) b = *reinterpret_cast<const float4*>(Wf + (long long)(n0 + r) * Kpad + k0 + k4);
-            Bs[k4 + 0][r] = b.x; Bs[k4 + 1][r] = b.y; Bs[k4 + 2][r] = b.z; Bs[k4 + 3][r] = b.w;
+            if (it < NG) {
+                float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (n0 + r < d.Cout) b = *reinterpret_cast<const float4*>(Wf + (long long)(n0 + r) * Kpad + k0 + k4);
+                Bs[k4 + 0][r] = b.x; Bs[k4 + 1][r] = b.y; Bs[k4 + 2][r] = b.z; Bs[k4 + 3][r] = b.w;
+            }
         }
         __syncthreads();
 #pragma unroll
         for (int kk = 0; kk < 16; ++kk) {
-            float a[8], b[8];
+            float a[8], b[4 * NG];
             *reinterpret_cast<float4*>(&a[0]) = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
             *reinterpret_cast<float4*>(&a[4]) = *reinterpret_cast<const float4*>(&As[kk][64 + ty * 4]);
-            *reinterpret_cast<float4*>(&b[0]) = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
-            *reinterpret_cast<float4*>(&b[4]) = *reinterpret_cast<const float4*>(&Bs[kk][64 + tx * 4]);
+#pragma unroll
+            for (int g = 0; g < NG; ++g) *reinterpret_cast<float4*>(&b[4 * g]) = *reinterpret_cast<const float4*>(&Bs[kk][64 * g + tx * 4]);
 #pragma unroll
             for (int i = 0; i < 8; ++i)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                for (int j = 0; j < 4 * NG; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
         }
         __syncthreads();
     }
@@ -85,7 +90,7 @@ __global__ void __launch_bounds__(256) conv_igemm_kernel(const float* __restrict
         const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
         if (m >= M) continue;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < NG; ++h) {
             const int c = n0 + h * 64 + tx * 4;
             if (c >= d.Cout) continue;
             const float4 bv = *reinterpret_cast<const float4*>(bias + c);
@@ -159,7 +164,7 @@ struct RnConv { ConvDesc d; int K, Kpad; RnBuf w, b; };
 using namespace egoego;
 
 struct egoego_resnet_ctx {
-    int device = 0, out_dim = 512, chunk = 16;
+    int device = 0, out_dim = 512, chunk = 64;      // frames per pass: 4 x 205 MB of activation buffers, >= 100 CTAs in the deepest layers
     std::map<std::string, std::vector<float>> staged;
     bool committed = false;
     std::vector<std::unique_ptr<RnConv>> convs;      // conv1, then per block: conv1, conv2, (downsample)
@@ -195,8 +200,13 @@ static int rn_fold(egoego_resnet_ctx* c, const std::string& conv, const std::str
 template <bool RELU, bool RESID>
 static int rn_conv(egoego_resnet_ctx* c, const RnConv& cv, const float* x, const float* resid, float* y, int N, cudaStream_t s) {
     const int M = N * cv.d.Hout * cv.d.Wout;
-    dim3 grid((cv.d.Cout + 127) / 128, (M + 127) / 128);
-    conv_igemm_kernel<RELU, RESID><<<grid, 256, 0, s>>>(x, cv.w.p, cv.b.p, resid, y, cv.d, M, cv.K, cv.Kpad);
+    if (cv.d.Cout <= 64) {
+        dim3 grid((cv.d.Cout + 63) / 64, (M + 127) / 128);
+        conv_igemm_kernel<RELU, RESID, 64><<<grid, 256, 0, s>>>(x, cv.w.p, cv.b.p, resid, y, cv.d, M, cv.K, cv.Kpad);
+    } else {
+        dim3 grid((cv.d.Cout + 127) / 128, (M + 127) / 128);
+        conv_igemm_kernel<RELU, RESID, 128><<<grid, 256, 0, s>>>(x, cv.w.p, cv.b.p, resid, y, cv.d, M, cv.K, cv.Kpad);
+    }
     c->launches++;
     return 0;
 }

@@ -31,5 +31,11 @@ if [ -n "$FULL" ]; then
             -o $OUT/${TAG}_prof_$K python tools/time_kernels.py 256 > $OUT/${TAG}_ncu_$K.log 2>&1
         echo "ncu full $K rc=$?"
     done
+    timeout 300 ncu --set full --clock-control none --import-source on -k regex:eval_metrics -s 3 -c 1 -f \
+        -o $OUT/${TAG}_prof_eval_metrics python tools/time_metrics.py > $OUT/${TAG}_ncu_eval_metrics.log 2>&1
+    echo "ncu full eval_metrics rc=$?"
+    timeout 300 ncu --set full --clock-control none --import-source on -k regex:conv_igemm -s 24 -c 3 -f \
+        -o $OUT/${TAG}_prof_conv_igemm python tools/time_resnet.py > $OUT/${TAG}_ncu_conv_igemm.log 2>&1
+    echo "ncu full conv_igemm rc=$?"
 fi
 ls -la $OUT | tail -20
