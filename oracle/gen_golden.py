@@ -126,6 +126,33 @@ def gen_pred_noise(M, params, out):
     np.savez(os.path.join(out, "pred_noise.npz"), **res)
 
 
+def synth_head_pose(seed, B, T):
+    """Seeded head trajectories [B,T,7] (xyz + wxyz): random-walk position around z = 1.6 m, yaw-dominant random-walk rotation."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    pos = np.cumsum(rng.normal(0, 0.01, (B, T, 3)), axis=1).astype(np.float32) + np.float32([0, 0, 1.6])
+    aa = np.stack([rng.normal(0, 0.05, (B, T)), rng.normal(0, 0.05, (B, T)), np.cumsum(rng.normal(0, 0.03, (B, T)), axis=1)], -1).astype(np.float32)
+    quat = R.axis_angle_to_quaternion(torch.from_numpy(aa))
+    return torch.cat((torch.from_numpy(pos), quat), -1)
+
+
+def gen_sliding_edge(M, params, out):
+    """(viii) window-length edge cases of p_sample_loop_sliding_window_w_canonical (:329-467), batch of 2 sequences, N = 20:
+    121 frames (second window = the 10-frame overlap + ONE new frame, the shortest the loop produces) and 250 frames (three
+    windows: 120, 120, 30)."""
+    ds = O.MotionDataStub()
+    m20 = build_model(M, params, 20)
+    res = {}
+    for T, seed in ((121, 61), (250, 62)):
+        hp = synth_head_pose(seed, 2, T)
+        data = torch.zeros(2, T, 198)
+        cm = O.prep_head_condition_mask(data.shape)
+        with Tape(seed):
+            aa, root = m20.sample_sliding_window_w_canonical(ds, hp[:, :, :3], hp[:, :, 3:], x_start=data, cond_mask=cm)
+        res[f"T{T}_aa"], res[f"T{T}_root"] = aa.numpy(), root.numpy()
+        print("sliding edge", T, tuple(aa.shape))
+    np.savez(os.path.join(out, "sliding_window_edge.npz"), **res)
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     M = import_reference()
@@ -133,6 +160,9 @@ def main():
     os.makedirs(out, exist_ok=True)
     params = O.init_params(seed=0)
     ds = O.MotionDataStub()
+    if "--only-sliding-edge" in sys.argv:
+        gen_sliding_edge(M, params, out)
+        return
     if "--only-pred-noise" in sys.argv:
         gen_pred_noise(M, params, out)
         print("wrote pred_noise.npz")
@@ -209,6 +239,7 @@ def main():
         aa, root = m50.sample_sliding_window_w_canonical(ds, hp[:, :, :3], hp[:, :, 3:], x_start=data, cond_mask=cm)
     np.savez(os.path.join(out, "sliding_window.npz"), aa=aa.numpy(), root=root.numpy())
     gen_pred_noise(M, params, out)
+    gen_sliding_edge(M, params, out)
     print("goldens written:", sorted(os.listdir(out)))
 
 

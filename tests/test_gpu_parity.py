@@ -10,7 +10,7 @@ import torch
 
 from oracle import egoego_oracle as O
 from oracle import rotations as R
-from oracle.gen_golden import Tape, synth_x_start
+from oracle.gen_golden import Tape, synth_head_pose, synth_x_start
 from helpers import ENGINES, joints, make_model, maxabs
 
 pytestmark = pytest.mark.gpu
@@ -173,6 +173,25 @@ def test_sliding_window_vs_golden(engine, golden_dir, params0):
     _, j_got = ods.fk_smpl(root.cpu().reshape(-1, 3), aa.cpu().reshape(-1, 22, 3))
     _, j_ref = ods.fk_smpl(torch.from_numpy(g["root"]).reshape(-1, 3), torch.from_numpy(g["aa"]).reshape(-1, 22, 3))
     assert (j_got - j_ref).abs().max() < JPOS_TOL_M
+
+
+@pytest.mark.parametrize("T,seed", [(121, 61), (250, 62)])
+def test_sliding_window_edge_lengths_vs_golden(T, seed, golden_dir, params0):
+    """Trailing window of 11 frames (10 of overlap + 1 new: 12 tokens) and a three-window sequence, batch of 2, tcgen05 engine."""
+    import egoego_release_b200 as E
+    g = _g(golden_dir, "sliding_window_edge.npz")
+    m = make_model(20, "tcgen05", params0)
+    ds = E.MotionDataStub().bind(m)
+    hp = synth_head_pose(seed, 2, T).cuda()
+    tp = Tape(seed)
+    aa, root = E.full_body_gen_cond_head_pose_sliding_window(m, ds, hp, noise_fn=tp.draw)
+    assert tuple(aa.shape) == tuple(g[f"T{T}_aa"].shape)
+    ods = O.MotionDataStub()
+    _, j_got = ods.fk_smpl(root.cpu().reshape(-1, 3), aa.cpu().reshape(-1, 22, 3))
+    _, j_ref = ods.fk_smpl(torch.from_numpy(g[f"T{T}_root"]).reshape(-1, 3), torch.from_numpy(g[f"T{T}_aa"]).reshape(-1, 22, 3))
+    err = float((j_got - j_ref).abs().max())
+    print(f"sliding window T={T}: joint max-abs {err * 1e3:.4f} mm")
+    assert err < JPOS_TOL_M
 
 
 @pytest.mark.parametrize("engine", ENGINES)
