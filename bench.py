@@ -275,11 +275,12 @@ def config1_latency(dev, T):
     import egoego_release_b200 as E
     from oracle import egoego_oracle as O
     out = {}
-    xs, cm = synth_inputs(1, T)
-    xs, cm = xs.to(dev), cm.to(dev)
-    for N in (50, 1000):
+    # (B, N): one window at the 50-step and the full schedule; B = 32 = --diffusion_batch_size of scripts/test_egoego_pipeline.sh
+    for Bw, N in ((1, 50), (1, 1000), (32, 1000)):
+        xs, cm = synth_inputs(Bw, T)
+        xs, cm = xs.to(dev), cm.to(dev)
         m = E.CondGaussianDiffusion(d_feats=198, d_model=512, n_dec_layers=4, n_head=4, d_k=256, d_v=256, max_timesteps=121,
-                                    out_dim=198, timesteps=N, objective="pred_x0", loss_type="l1", max_batch=1)
+                                    out_dim=198, timesteps=N, objective="pred_x0", loss_type="l1", max_batch=Bw)
         m.load_state_dict(O.init_params(0), strict=False)
         m = m.to(dev)
         for _ in range(2):
@@ -293,8 +294,8 @@ def config1_latency(dev, T):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
-        out[f"B1_T{T}_N{N}"] = {"ms_per_sample_call": ms, "windows_per_s": 1e3 / ms, "us_per_diffusion_step": ms * 1e3 / N,
-                                "precise_last_steps": m.precise_last_steps()}
+        out[f"B{Bw}_T{T}_N{N}"] = {"ms_per_sample_call": ms, "windows_per_s": Bw * 1e3 / ms, "us_per_diffusion_step": ms * 1e3 / N,
+                                   "precise_last_steps": m.precise_last_steps()}
         del m
     return out
 
