@@ -71,6 +71,8 @@ struct egoego_ctx {
 
 namespace egoego {
 
+void train_release(egoego_ctx* c);     // frees the training workspace of a handle (defined with the training step below)
+
 static inline dim3 grid1d(long long n, int bs) { return dim3((unsigned)((n + bs - 1) / bs)); }
 // ddpm_update_kernel: x = quads (4 consecutive elements) of one window in blocks of 256 threads, y = window
 static inline dim3 ddpm_grid(int T, int D, int B) { return dim3((unsigned)(((T * D + 3) / 4 + 255) / 256), (unsigned)B); }
@@ -243,6 +245,7 @@ int egoego_destroy(egoego_handle c) {
     if (!c) return 0;
     cudaSetDevice(c->cfg.device);
     cudaDeviceSynchronize();
+    train_release(c);
     for (auto& g : c->step_graph) if (g) cudaGraphExecDestroy(g);
     DevBuf* bufs[] = {&c->start_w, &c->start_b, &c->pos, &c->out_w, &c->out_b, &c->t_w1, &c->t_b1, &c->t_w2, &c->t_b2,
                       &c->temb, &c->coef1, &c->coef2, &c->logvar, &c->sqrt_recip, &c->sqrt_recipm1, &c->Ain, &c->Hbuf,
@@ -750,6 +753,247 @@ int egoego_selftest_gemm(int device, int M, int N, int K, uint64_t seed, int two
     EG_CHECK(cudaGetDeviceCount(&ndev) == cudaSuccess && device >= 0 && device < ndev, "no such CUDA device");
     EG_CUDA(cudaSetDevice(device));
     return selftest_gemm(M, N, K, seed, two_cta, half_fmt, max_abs_err, max_abs_ref, ms);
+}
+
+}  // extern "C"
+
+// ================================================================================================
+// Training step: see train.cuh
+// ================================================================================================
+#include "train.cuh"
+
+namespace egoego {
+
+struct TrainLayerBufs { DevBuf QKV, O, Y1, st1, H1, F, Y2, st2; };
+
+struct TrainWs {
+    int B = 0;                                   // windows the workspace is sized for
+    std::vector<DevBuf> Hin;                     // NL + 1 residual streams [M,512]
+    std::vector<TrainLayerBufs> L;
+    DevBuf OUT, dOUT, dH, dH1, dY, dF, dO, dQKV, Ta, Tb, WT, gp, bp, loss;
+    std::map<std::string, DevBuf> grads;         // fused / padded gradient buffers
+};
+
+static std::map<egoego_ctx*, std::unique_ptr<TrainWs>> g_train;
+
+void train_release(egoego_ctx* c) {
+    auto it = g_train.find(c);
+    if (it == g_train.end()) return;
+    if (TrainWs* w = it->second.get()) {
+        for (auto& h : w->Hin) h.release();
+        for (auto& l : w->L) for (DevBuf* b : {&l.QKV, &l.O, &l.Y1, &l.st1, &l.H1, &l.F, &l.Y2, &l.st2}) b->release();
+        for (DevBuf* b : {&w->OUT, &w->dOUT, &w->dH, &w->dH1, &w->dY, &w->dF, &w->dO, &w->dQKV, &w->Ta, &w->Tb, &w->WT, &w->gp, &w->bp, &w->loss}) b->release();
+        for (auto& kv : w->grads) kv.second.release();
+    }
+    g_train.erase(it);
+}
+
+template <class Epi>
+static void tr_gemm(const float* A, int lda, const float* W, int ldw, int rows, int N, int K, const Epi& e, cudaStream_t s) {
+    sgemm_tn_kernel<<<dim3((N + 127) / 128, rows / 128), 256, 0, s>>>(A, lda, W, ldw, N, K, e);
+}
+static void tr_transpose(const float* src, int R, int C, int ld, float* dst, int ldo, cudaStream_t s) {
+    tr_transpose_kernel<<<dim3((C + 31) / 32, (R + 31) / 32), dim3(32, 8), 0, s>>>(src, R, C, ld, dst, ldo);
+}
+static void tr_colsum(const float* X, int M, int C, int ld, float* out, cudaStream_t s) {
+    tr_colsum_kernel<<<(C + 31) / 32, dim3(32, 8), 0, s>>>(X, M, C, ld, out, 1.0f);
+}
+// g [rowsW, Kd] = dY^T [rowsW, M] X [M, Kd]  (dY [M, ldy] with rowsW valid columns, X [M, ldx] with Kd valid columns)
+static void tr_weight_grad(TrainWs* w, const float* dY, int ldy, int rowsW, const float* X, int ldx, int Kd, int M, float* g, int ldg, cudaStream_t s) {
+    const int rp = ((rowsW + 127) / 128) * 128;
+    tr_transpose(dY, M, rowsW, ldy, w->Ta.as<float>(), M, s);          // [rowsW, M]; rows rowsW..rp of Ta may hold stale data: harmless,
+    tr_transpose(X, M, Kd, ldx, w->Tb.as<float>(), M, s);              // the matching output rows land in the padded part of g
+    tr_gemm(w->Ta.as<float>(), M, w->Tb.as<float>(), M, rp, Kd, M, EpiPlainBias{g, ldg, nullptr}, s);
+}
+
+static int train_alloc(egoego_ctx* c, TrainWs* w, int B) {
+    if (w->B >= B) return 0;
+    const size_t M = (size_t)B * LP, d = c->d, nq = 3 * c->H * c->dk, hd = c->H * c->dk;
+    w->Hin.resize(c->NL + 1); w->L.resize(c->NL);
+    for (auto& h : w->Hin) if (h.alloc(M * d * 4)) return 1;
+    for (auto& l : w->L)
+        if (l.QKV.alloc(M * nq * 4) || l.O.alloc(M * hd * 4) || l.Y1.alloc(M * d * 4) || l.st1.alloc(M * 2 * 4) || l.H1.alloc(M * d * 4) ||
+            l.F.alloc(M * d * 4) || l.Y2.alloc(M * d * 4) || l.st2.alloc(M * 2 * 4)) return 1;
+    if (w->OUT.alloc(M * 256 * 4) || w->dOUT.alloc(M * 256 * 4) || w->dH.alloc(M * d * 4) || w->dH1.alloc(M * d * 4) || w->dY.alloc(M * d * 4) ||
+        w->dF.alloc(M * d * 4) || w->dO.alloc(M * hd * 4) || w->dQKV.alloc(M * nq * 4) || w->Ta.alloc(nq * M * 4) || w->Tb.alloc(hd * M * 4) ||
+        w->WT.alloc(nq * d * 4) || w->gp.alloc(M * d * 4) || w->bp.alloc(M * d * 4) || w->loss.alloc(8)) return 1;
+    if (c->Ain.bytes < M * c->kin_pad * 4 && c->Ain.alloc(M * c->kin_pad * 4)) return 1;
+    auto G = [&](const std::string& k, size_t n) -> int { return w->grads[k].alloc(n * 4); };
+    if (G("start_w", (size_t)d * c->kin_pad) || G("start_b", d) || G("out_w", (size_t)256 * d) || G("out_b", 256) ||
+        G("t_w1", 256 * 64) || G("t_b1", 256) || G("t_w2", d * 256) || G("t_b2", d)) return 1;
+    for (int l = 0; l < c->NL; ++l) {
+        const std::string p = "L" + std::to_string(l) + ".";
+        if (G(p + "wqkv", nq * d) || G(p + "bqkv", nq) || G(p + "fc_w", d * hd) || G(p + "fc_b", d) || G(p + "ln1_g", d) || G(p + "ln1_b", d) ||
+            G(p + "w1", d * d) || G(p + "b1", d) || G(p + "w2", d * d) || G(p + "b2", d) || G(p + "ln2_g", d) || G(p + "ln2_b", d)) return 1;
+    }
+    w->B = B;
+    return 0;
+}
+
+}  // namespace egoego
+
+extern "C" {
+
+int egoego_train_step(egoego_handle c, const float* x_start, const float* cond_mask, const float* pmask, const int64_t* t_dev,
+                      const float* noise, const float* cond_noise, const float* sqrt_ac, const float* sqrt_1mac, const float* weight,
+                      int loss_l2, int B, int T, float* loss_out, void* stream_v) {
+    if (check_ready(c, B, T)) return 1;
+    EG_CHECK(x_start && cond_mask && t_dev && noise && cond_noise && sqrt_ac && sqrt_1mac && weight && loss_out, "null argument");
+    EG_CHECK(c->cfg.engine == EGOEGO_ENGINE_SIMT, "the training step runs on the fp32 engine: create the handle with EGOEGO_ENGINE_SIMT");
+    EG_CHECK(c->d == 512 && c->dk == 256, "training step is specialised for d_model = 512, d_k = 256");
+    EG_CHECK(B <= c->cfg.max_batch, "training batch exceeds cfg.max_batch");
+    EG_CUDA(cudaSetDevice(c->cfg.device));
+    {
+        static bool attr = false;
+        if (!attr) { EG_CUDA(cudaFuncSetAttribute(attention_bwd_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_BWD_SMEM)); attr = true; }
+    }
+    cudaStream_t s = (cudaStream_t)stream_v;
+    std::unique_ptr<TrainWs>& wp = g_train[c];
+    if (!wp) wp.reset(new TrainWs());
+    TrainWs* w = wp.get();
+    if (train_alloc(c, w, B)) return 1;
+    const int M = B * LP, d = c->d, H = c->H, dk = c->dk, nq = 3 * H * dk, hd = H * dk, D = c->D, L = T + 1, KP = c->kin_pad;
+    const long long nel = (long long)B * T * D;
+    const float qs = 1.0f / sqrtf((float)dk);
+    auto nblk = [](long long n) { return (unsigned)((n + 255) / 256); };
+    TSrc ts{reinterpret_cast<const long long*>(t_dev), nullptr, 0, c->N - 1};
+
+    // ---------------- forward ----------------
+    EG_CUDA(cudaMemsetAsync(c->Ain.p, 0, (size_t)M * KP * 4, s));
+    tr_prep_kernel<<<nblk(nel), 256, 0, s>>>(x_start, cond_mask, noise, cond_noise, sqrt_ac, sqrt_1mac, c->Ain.as<float>(), KP, B, T, D);
+    tr_gemm(c->Ain.as<float>(), KP, c->start_w.as<float>(), KP, M, d, KP,
+            EpiStart{w->Hin[0].as<float>(), d, c->start_b.as<float>(), nullptr, c->pos.as<float>(), c->temb.as<float>(), ts, T}, s);
+    for (int l = 0; l < c->NL; ++l) {
+        LayerW& W = c->layers[l];
+        TrainLayerBufs& b = w->L[l];
+        float* Hin = w->Hin[l].as<float>();
+        tr_gemm(Hin, d, W.wqkv.as<float>(), d, M, nq, d, EpiBiasScale{b.QKV.as<float>(), nq, W.bqkv.as<float>(), hd, qs}, s);
+        attention_simt_kernel<false><<<B * H, 256, ATT_SIMT_SMEM, s>>>(b.QKV.as<float>(), nq, b.O.as<float>(), nullptr, nullptr, hd, H, L);
+        tr_gemm(b.O.as<float>(), hd, W.fc_w.as<float>(), hd, M, d, hd, EpiBiasResid{b.Y1.as<float>(), d, W.fc_b.as<float>(), Hin}, s);
+        tr_ln_fwd_kernel<<<M / 8, 256, 0, s>>>(b.Y1.as<float>(), b.H1.as<float>(), b.st1.as<float>(), W.ln1_g.as<float>(), W.ln1_b.as<float>(), pmask, T, M);
+        tr_gemm(b.H1.as<float>(), d, W.w1.as<float>(), d, M, d, d, EpiBiasRelu{b.F.as<float>(), d, W.b1.as<float>()}, s);
+        tr_gemm(b.F.as<float>(), d, W.w2.as<float>(), d, M, d, d, EpiBiasResid{b.Y2.as<float>(), d, W.b2.as<float>(), b.H1.as<float>()}, s);
+        tr_ln_fwd_kernel<<<M / 8, 256, 0, s>>>(b.Y2.as<float>(), w->Hin[l + 1].as<float>(), b.st2.as<float>(), W.ln2_g.as<float>(), W.ln2_b.as<float>(), pmask, T, M);
+    }
+    tr_gemm(w->Hin[c->NL].as<float>(), d, c->out_w.as<float>(), d, M, D, d, EpiPlainBias{w->OUT.as<float>(), 256, c->out_b.as<float>()}, s);
+    EG_CUDA(cudaMemsetAsync(w->dOUT.p, 0, (size_t)M * 256 * 4, s));
+    EG_CUDA(cudaMemsetAsync(w->loss.p, 0, 8, s));
+    tr_loss_kernel<<<nblk(nel), 256, 0, s>>>(w->OUT.as<float>(), 256, c->cfg.objective == 0 ? noise : x_start, pmask, weight, loss_l2, B, T, D,
+                                             w->loss.as<double>(), w->dOUT.as<float>());
+
+    // ---------------- backward ----------------
+    auto G = [&](const std::string& k) { return w->grads[k].as<float>(); };
+    float *dH = w->dH.as<float>(), *dH1 = w->dH1.as<float>(), *dY = w->dY.as<float>(), *dF = w->dF.as<float>(), *WT = w->WT.as<float>();
+    // linear_out (:102,139): out = H[:, 1:] Wout^T + b
+    tr_weight_grad(w, w->dOUT.as<float>(), 256, D, w->Hin[c->NL].as<float>(), d, d, M, G("out_w"), d, s);
+    tr_colsum(w->dOUT.as<float>(), M, D, 256, G("out_b"), s);
+    EG_CUDA(cudaMemsetAsync(WT, 0, (size_t)d * 256 * 4, s));
+    tr_transpose(c->out_w.as<float>(), D, d, d, WT, 256, s);                              // Wout^T [512, 256]
+    tr_gemm(w->dOUT.as<float>(), 256, WT, 256, M, d, 256, EpiPlainBias{dH, d, nullptr}, s);
+    for (int l = c->NL - 1; l >= 0; --l) {
+        LayerW& W = c->layers[l];
+        TrainLayerBufs& b = w->L[l];
+        const std::string p = "L" + std::to_string(l) + ".";
+        // ---- FFN (transformer_module.py:98-116): H2 = LN2(F W2^T + b2 + H1) * pm, F = relu(H1 W1^T + b1)
+        tr_ln_bwd_kernel<<<M / 8, 256, 0, s>>>(dH, b.Y2.as<float>(), b.st2.as<float>(), W.ln2_g.as<float>(), pmask, T, M, dY, w->gp.as<float>(), w->bp.as<float>());
+        tr_colsum(w->gp.as<float>(), M, d, d, G(p + "ln2_g"), s);
+        tr_colsum(w->bp.as<float>(), M, d, d, G(p + "ln2_b"), s);
+        tr_colsum(dY, M, d, d, G(p + "b2"), s);
+        tr_weight_grad(w, dY, d, d, b.F.as<float>(), d, d, M, G(p + "w2"), d, s);
+        tr_transpose(W.w2.as<float>(), d, d, d, WT, d, s);
+        tr_gemm(dY, d, WT, d, M, d, d, EpiPlainBias{dF, d, nullptr}, s);
+        tr_relu_bwd_kernel<<<nblk((long long)M * d), 256, 0, s>>>(dF, b.F.as<float>(), (long long)M * d);
+        tr_colsum(dF, M, d, d, G(p + "b1"), s);
+        tr_weight_grad(w, dF, d, d, b.H1.as<float>(), d, d, M, G(p + "w1"), d, s);
+        EG_CUDA(cudaMemcpyAsync(dH1, dY, (size_t)M * d * 4, cudaMemcpyDeviceToDevice, s));      // residual branch
+        tr_transpose(W.w1.as<float>(), d, d, d, WT, d, s);
+        tr_gemm(dF, d, WT, d, M, d, d, EpiAccum{dH1, d}, s);
+        // ---- attention block (:61-95): H1 = LN1(O Wfc^T + bfc + Hin) * pm
+        tr_ln_bwd_kernel<<<M / 8, 256, 0, s>>>(dH1, b.Y1.as<float>(), b.st1.as<float>(), W.ln1_g.as<float>(), pmask, T, M, dY, w->gp.as<float>(), w->bp.as<float>());
+        tr_colsum(w->gp.as<float>(), M, d, d, G(p + "ln1_g"), s);
+        tr_colsum(w->bp.as<float>(), M, d, d, G(p + "ln1_b"), s);
+        tr_colsum(dY, M, d, d, G(p + "fc_b"), s);
+        tr_weight_grad(w, dY, d, d, b.O.as<float>(), hd, hd, M, G(p + "fc_w"), hd, s);
+        tr_transpose(W.fc_w.as<float>(), d, hd, hd, WT, d, s);                              // Wfc^T [1024, 512]
+        tr_gemm(dY, d, WT, d, M, hd, d, EpiPlainBias{w->dO.as<float>(), hd, nullptr}, s);
+        attention_bwd_simt_kernel<<<B * H, 256, ATT_BWD_SMEM, s>>>(b.QKV.as<float>(), nq, w->dO.as<float>(), hd, w->dQKV.as<float>(), H, L, qs);
+        tr_colsum(w->dQKV.as<float>(), M, nq, nq, G(p + "bqkv"), s);
+        tr_weight_grad(w, w->dQKV.as<float>(), nq, nq, w->Hin[l].as<float>(), d, d, M, G(p + "wqkv"), d, s);
+        EG_CUDA(cudaMemcpyAsync(dH, dY, (size_t)M * d * 4, cudaMemcpyDeviceToDevice, s));       // residual branch
+        tr_transpose(W.wqkv.as<float>(), nq, d, d, WT, nq, s);                              // Wqkv^T [512, 3072]
+        tr_gemm(w->dQKV.as<float>(), nq, WT, nq, M, d, nq, EpiAccum{dH, d}, s);
+    }
+    // ---- time token (:105-116,122-123) and start_conv (transformer_module.py:203)
+    for (const char* k : {"t_w1", "t_b1", "t_w2", "t_b2"}) EG_CUDA(cudaMemsetAsync(w->grads[k].p, 0, w->grads[k].bytes, s));
+    tr_time_bwd_kernel<<<B, 256, 0, s>>>(dH, reinterpret_cast<const long long*>(t_dev), c->t_w1.as<float>(), c->t_b1.as<float>(), c->t_w2.as<float>(),
+                                         G("t_w1"), G("t_b1"), G("t_w2"), G("t_b2"), d);
+    tr_frame_rows_kernel<<<nblk((long long)M * d), 256, 0, s>>>(dH, dY, T, M, d);
+    tr_colsum(dY, M, d, d, G("start_b"), s);
+    tr_weight_grad(w, dY, d, d, c->Ain.as<float>(), KP, KP, M, G("start_w"), KP, s);
+    {   // loss scalar (double accumulator) -> float
+        double h = 0.0;
+        EG_CUDA(cudaMemcpyAsync(&h, w->loss.p, 8, cudaMemcpyDeviceToHost, s));
+        EG_CUDA(cudaStreamSynchronize(s));
+        const float f = (float)h;
+        EG_CUDA(cudaMemcpyAsync(loss_out, &f, 4, cudaMemcpyHostToDevice, s));
+        EG_CUDA(cudaStreamSynchronize(s));
+    }
+    c->launches += 40 * c->NL + 20;
+    EG_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// Gradient of the tensor `name` (reference state_dict key, e.g. "denoise_fn.motion_transformer.layer_stack.2.self_attn.w_k.weight")
+// from the last egoego_train_step, copied to dst_dev[numel] in the reference's layout.
+int egoego_train_get_grad(egoego_handle c, const char* name_in, float* dst, int64_t numel, void* stream_v) {
+    EG_CHECK(c && name_in && dst, "null argument");
+    auto it = g_train.find(c);
+    EG_CHECK(it != g_train.end() && it->second && it->second->B > 0, "egoego_train_step has not been called on this handle");
+    TrainWs* w = it->second.get();
+    cudaStream_t s = (cudaStream_t)stream_v;
+    std::string name(name_in);
+    for (const char* pre : {"ema_model.", "model.", "module."})
+        if (name.rfind(pre, 0) == 0) name = name.substr(strlen(pre));
+    const int d = c->d, hd = c->H * c->dk, D = c->D;
+    const float* src = nullptr; int64_t rows = 1, cols = 0, ld = 0;
+    auto G = [&](const std::string& k) { return w->grads[k].as<float>(); };
+    const std::string pre = "denoise_fn.motion_transformer.";
+    if (name == pre + "start_conv.weight") { src = G("start_w"); rows = d; cols = 2 * D; ld = c->kin_pad; }
+    else if (name == pre + "start_conv.bias") { src = G("start_b"); cols = d; }
+    else if (name == "denoise_fn.linear_out.weight") { src = G("out_w"); rows = D; cols = d; ld = d; }
+    else if (name == "denoise_fn.linear_out.bias") { src = G("out_b"); cols = D; }
+    else if (name == "denoise_fn.time_mlp.1.weight") { src = G("t_w1"); cols = 256 * 64; }
+    else if (name == "denoise_fn.time_mlp.1.bias") { src = G("t_b1"); cols = 256; }
+    else if (name == "denoise_fn.time_mlp.3.weight") { src = G("t_w2"); cols = (int64_t)d * 256; }
+    else if (name == "denoise_fn.time_mlp.3.bias") { src = G("t_b2"); cols = d; }
+    else if (name.rfind(pre + "layer_stack.", 0) == 0) {
+        const std::string rest = name.substr((pre + "layer_stack.").size());
+        const size_t dot = rest.find('.');
+        EG_CHECK(dot != std::string::npos, "unknown tensor: " + name);
+        const int l = atoi(rest.substr(0, dot).c_str());
+        EG_CHECK(l >= 0 && l < c->NL, "layer index out of range: " + name);
+        const std::string k = rest.substr(dot + 1), p = "L" + std::to_string(l) + ".";
+        const char* secs[3] = {"w_q", "w_k", "w_v"};
+        for (int sct = 0; sct < 3; ++sct) {
+            if (k == std::string("self_attn.") + secs[sct] + ".weight") { src = G(p + "wqkv") + (size_t)sct * hd * d; cols = (int64_t)hd * d; }
+            if (k == std::string("self_attn.") + secs[sct] + ".bias") { src = G(p + "bqkv") + (size_t)sct * hd; cols = hd; }
+        }
+        if (k == "self_attn.fc.weight") { src = G(p + "fc_w"); cols = (int64_t)d * hd; }
+        else if (k == "self_attn.fc.bias") { src = G(p + "fc_b"); cols = d; }
+        else if (k == "self_attn.layer_norm.weight") { src = G(p + "ln1_g"); cols = d; }
+        else if (k == "self_attn.layer_norm.bias") { src = G(p + "ln1_b"); cols = d; }
+        else if (k == "pos_ffn.w_1.weight") { src = G(p + "w1"); cols = (int64_t)d * d; }
+        else if (k == "pos_ffn.w_1.bias") { src = G(p + "b1"); cols = d; }
+        else if (k == "pos_ffn.w_2.weight") { src = G(p + "w2"); cols = (int64_t)d * d; }
+        else if (k == "pos_ffn.w_2.bias") { src = G(p + "b2"); cols = d; }
+        else if (k == "pos_ffn.layer_norm.weight") { src = G(p + "ln2_g"); cols = d; }
+        else if (k == "pos_ffn.layer_norm.bias") { src = G(p + "ln2_b"); cols = d; }
+    }
+    EG_CHECK(src != nullptr, "no gradient for tensor: " + name);
+    EG_CHECK(rows * cols == numel, "tensor '" + name + "': expected " + std::to_string(rows * cols) + " elements, got " + std::to_string(numel));
+    if (rows == 1 || ld == cols) { EG_CUDA(cudaMemcpyAsync(dst, src, (size_t)numel * 4, cudaMemcpyDeviceToDevice, s)); }
+    else { EG_CUDA(cudaMemcpy2DAsync(dst, (size_t)cols * 4, src, (size_t)ld * 4, (size_t)cols * 4, (size_t)rows, cudaMemcpyDeviceToDevice, s)); }
+    return 0;
 }
 
 }  // extern "C"

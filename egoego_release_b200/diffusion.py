@@ -202,6 +202,8 @@ class CondGaussianDiffusion(nn.Module):
         try:
             if self._h is not None:
                 _capi.lib().egoego_destroy(self._h)
+            if getattr(self, "_ht", None) is not None:
+                _capi.lib().egoego_destroy(self._ht)
         except Exception:
             pass
 
@@ -209,7 +211,7 @@ class CondGaussianDiffusion(nn.Module):
     # deep-copies the model, trainer_amass_cond_motion_diffusion.py:58) and re-create lazily in the copy
     def __getstate__(self):
         st = dict(self.__dict__)
-        for k in ("_h", "_h_device", "_weights_sig", "_skeleton_sig", "_noise_tape", "_tape_keepalive"):
+        for k in ("_h", "_h_device", "_weights_sig", "_skeleton_sig", "_noise_tape", "_tape_keepalive", "_ht", "_ht_sig", "_ht_device"):
             st[k] = None
         return st
 
@@ -540,13 +542,92 @@ class CondGaussianDiffusion(nn.Module):
         return res
 
     # ------------------------------------------------------------------------------------------
-    # training-side methods of the reference class: out of scope of this path
+    # training-side methods of the reference class: loss AND gradients come from the CUDA library
+    # (egoego_train_step: forward with saved activations + backward kernels); torch.autograd only carries the parameter
+    # gradients to .grad so the reference's optimizer / EMA / GradScaler code runs unchanged.  Dropout is identity.
     # ------------------------------------------------------------------------------------------
     def q_sample(self, x_start, t, noise=None):
-        raise NotImplementedError("training (q_sample / p_losses / forward) is outside the B200 sampling path")
+        """:557-563 (device tensors; the same arithmetic runs inside egoego_train_step)."""
+        noise = torch.randn_like(x_start) if noise is None else noise
+        sa = self.sqrt_alphas_cumprod.gather(-1, t).reshape(-1, 1, 1)
+        sb = self.sqrt_one_minus_alphas_cumprod.gather(-1, t).reshape(-1, 1, 1)
+        return sa * x_start + sb * noise
 
-    def p_losses(self, *a, **k):
-        raise NotImplementedError("training (q_sample / p_losses / forward) is outside the B200 sampling path")
+    def _train_handle(self, B):
+        """A second, fp32 (SIMT) engine handle for training; weights are re-committed whenever a parameter changed."""
+        dev = self._device()
+        L = _capi.lib()
+        if getattr(self, "_ht", None) is None or self._ht_batch < B or self._ht_device != dev:
+            if getattr(self, "_ht", None) is not None:
+                L.egoego_destroy(self._ht)
+            cfg = Cfg(timesteps=self.num_timesteps, objective=1 if self.objective == 'pred_x0' else 0, max_batch=int(B),
+                      device=dev.index if dev.index is not None else torch.cuda.current_device(), engine=_capi.ENGINE_SIMT,
+                      precise_last_steps=-1, **self._cfg)
+            h = C.c_void_p()
+            check(L.egoego_create(C.byref(cfg), C.byref(h)))
+            self._ht, self._ht_batch, self._ht_device, self._ht_sig = h, int(B), dev, None
+        sig = self._signature()
+        if sig != self._ht_sig:
+            with torch.cuda.device(dev):
+                for k, v in self.state_dict().items():
+                    t = _f32c(v.detach().float(), dev)
+                    check(L.egoego_set_tensor(self._ht, k.encode(), _ptr(t), t.numel(), 1))
+                check(L.egoego_commit_weights(self._ht, _stream(dev)))
+            self._ht_sig = sig
+        return self._ht
+
+    def p_losses(self, x_start, cond_mask, t, noise=None, padding_mask=None, cond_noise=None):
+        """:574-605.  Returns the scalar loss; ``loss.backward()`` fills ``.grad`` of every trainable parameter with the
+        gradients computed by the CUDA backward pass.  ``cond_noise`` (optional) replaces the second Gaussian draw."""
+        if self.objective not in ('pred_noise', 'pred_x0'):
+            raise ValueError(f'unknown objective {self.objective}')
+        if self.loss_type not in ('l1', 'l2'):
+            raise ValueError(f'invalid loss type {self.loss_type}')
+        dev = self._device()
+        x_start = _f32c(x_start, dev)
+        cond_mask = _f32c(cond_mask, dev)
+        noise = torch.randn_like(x_start) if noise is None else _f32c(noise, dev)
+        cond_noise = torch.randn_like(x_start) if cond_noise is None else _f32c(cond_noise, dev)
+        t = t.to(device=dev, dtype=torch.int64).contiguous()
+        B, T, _ = x_start.shape
+        pm = None if padding_mask is None else _f32c(padding_mask.reshape(B, T + 1), dev)
+        names, params = zip(*[(k, v) for k, v in self.named_parameters() if v.requires_grad])
+        return _TrainStepFn.apply(self, names, x_start, cond_mask, pm, t, noise, cond_noise, *params)
 
     def forward(self, x_start, cond_mask, padding_mask=None):
-        raise NotImplementedError("training (q_sample / p_losses / forward) is outside the B200 sampling path")
+        """:617-625: t ~ U{0..N-1} per sample, then p_losses."""
+        bs = x_start.shape[0]
+        t = torch.randint(0, self.num_timesteps, (bs,), device=x_start.device).long()
+        return self.p_losses(x_start, cond_mask, t, padding_mask=padding_mask)
+
+
+class _TrainStepFn(torch.autograd.Function):
+    """One call of egoego_train_step; backward hands the gradients stored in the engine handle to autograd."""
+
+    @staticmethod
+    def forward(ctx, model, names, x_start, cond_mask, pm, t, noise, cond_noise, *params):
+        dev = x_start.device
+        B, T, _ = x_start.shape
+        h = model._train_handle(B)
+        sa = model.sqrt_alphas_cumprod.gather(-1, t).contiguous()
+        sb = model.sqrt_one_minus_alphas_cumprod.gather(-1, t).contiguous()
+        wt = model.p2_loss_weight.gather(-1, t).contiguous()
+        loss = torch.empty(1, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            check(_capi.lib().egoego_train_step(h, _ptr(x_start), _ptr(cond_mask), _ptr(pm), _ptr(t), _ptr(noise), _ptr(cond_noise), _ptr(sa),
+                                                _ptr(sb), _ptr(wt), 1 if model.loss_type == 'l2' else 0, B, T, _ptr(loss), _stream(dev)))
+        ctx.model, ctx.names, ctx.shapes, ctx.handle = model, names, [tuple(p.shape) for p in params], h
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, gout):
+        model, dev = ctx.model, gout.device
+        if model._ht is not ctx.handle:
+            raise EgoEgoError("the training handle changed between forward and backward")
+        grads = []
+        with torch.cuda.device(dev):
+            for name, shape in zip(ctx.names, ctx.shapes):
+                g = torch.empty(shape, device=dev, dtype=torch.float32)
+                check(_capi.lib().egoego_train_get_grad(ctx.handle, name.encode(), _ptr(g), g.numel(), _stream(dev)))
+                grads.append(g * gout)
+        return (None,) * 8 + tuple(grads)

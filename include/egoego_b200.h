@@ -233,6 +233,20 @@ int  egoego_resnet18_commit(egoego_resnet h);
 int  egoego_resnet18_forward(egoego_resnet h, const float* flow_dev, int N, float* feats_dev, void* stream);
 int64_t egoego_resnet18_launch_count(egoego_resnet h);
 
+/* Training step of the denoiser: CondGaussianDiffusion.forward / p_losses
+ * (egoego/model/transformer_cond_diffusion_model.py:557-625) -- q_sample, conditioning, denoiser forward with saved activations,
+ * L1 (loss_l2 = 0) or L2 loss with the padding mask and per-sample weight, and the backward pass through every layer.
+ * Handles created with EGOEGO_ENGINE_SIMT only (fp32); weights = the last egoego_commit_weights.  Dropout is identity (the
+ * parity bar is the reference in eval() mode, oracle/training.py).  All pointers are device pointers:
+ * x_start / cond_mask / noise / cond_noise [B,T,d_feats], padding_mask float [B,T+1] or NULL, t int64 [B],
+ * sqrt_ac = sqrt_alphas_cumprod[t], sqrt_1mac = sqrt_one_minus_alphas_cumprod[t], weight = p2_loss_weight[t] (each float [B]).
+ * loss_out_dev[1] receives the scalar loss; gradients stay in the handle until the next call and are read with
+ * egoego_train_get_grad(name = reference state_dict key, dst_dev[numel] in the reference's layout). */
+int  egoego_train_step(egoego_handle h, const float* x_start_dev, const float* cond_mask_dev, const float* padding_mask_dev,
+                       const int64_t* t_dev, const float* noise_dev, const float* cond_noise_dev, const float* sqrt_ac_dev,
+                       const float* sqrt_1mac_dev, const float* weight_dev, int loss_l2, int B, int T, float* loss_out_dev, void* stream);
+int  egoego_train_get_grad(egoego_handle h, const char* name, float* dst_dev, int64_t numel, void* stream);
+
 /* Introspection for tests/bench: number of kernels launched by this handle since creation, and the
  * cumulative count of denoiser steps executed. */
 int64_t egoego_launch_count(egoego_handle h);

@@ -11,7 +11,7 @@ PositionwiseFeedForward while training) is NOT part of this restatement: torch's
 implementation, so parity for the training row is defined with the modules in eval() mode (dropout = identity), which is how
 tests/golden/training.npz is generated from the unmodified reference (oracle/gen_golden_training.py).
 
-STATUS: oracle + goldens only.  The CUDA training step (backward kernels) is not built -- DESIGN.md section 7.
+The CUDA training step (egoego_train_step, csrc/train.cuh) is held to the same goldens: tests/test_training_oracle.py.
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import this module.
 """
 from typing import Dict, Optional
