@@ -264,6 +264,41 @@ def next_rows(dev, B, T, pk):
                                    "note": "implicit-GEMM conv kernels with folded BatchNorm and fused bias + residual + ReLU epilogues (csrc/resnet.cu)"}
     except Exception as ex:
         out["resnet18_encoder"] = {"error": repr(ex)[:200]}
+    # training step (BASELINE config 5 shape per GPU: batch 32, T = 120): loss + backward through the CUDA library vs the same
+    # objective in PyTorch eager autograd on this GPU (oracle port of the reference's op sequence, fp32; dropout off in both)
+    try:
+        from oracle import egoego_oracle as O
+        from oracle import training as TR
+        Bt = 32
+        mt = E.CondGaussianDiffusion(d_feats=198, d_model=512, n_dec_layers=4, n_head=4, d_k=256, d_v=256, max_timesteps=121,
+                                     out_dim=198, timesteps=1000, objective="pred_x0", loss_type="l1", max_batch=Bt)
+        mt.load_state_dict(O.init_params(0), strict=False)
+        mt = mt.to(dev)
+        x0 = torch.rand(Bt, T, 198, device=dev) * 2 - 1
+        cmk = O.prep_head_condition_mask(x0.shape).to(dev)
+        pmk = (torch.arange(T + 1, device=dev)[None, :] < torch.randint(31, T + 2, (Bt, 1), device=dev))[:, None, :]
+        tt = torch.randint(0, 1000, (Bt,), device=dev)
+
+        def ours():
+            mt.zero_grad(set_to_none=True)
+            mt.p_losses(x0, cmk, tt, padding_mask=pmk).backward()
+
+        ms_ours = timed(ours, 5)
+        pg = {k: (v.to(dev).requires_grad_(True) if v.is_floating_point() and "position_vec" not in k else v.to(dev)) for k, v in O.init_params(0).items()}
+        sched = {k: v.to(dev) for k, v in O.make_schedule(1000).items()}
+
+        def torch_eager():
+            for v in pg.values():
+                v.grad = None
+            TR.p_losses(pg, sched, x0, cmk, tt, torch.randn_like(x0), torch.randn_like(x0), pmk).backward()
+
+        ms_torch = timed(torch_eager, 5)
+        out["train_step"] = {"batch": Bt, "ms_per_step_ours": ms_ours, "ms_per_step_torch_eager_fp32": ms_torch,
+                             "samples_per_s_ours": Bt / (ms_ours * 1e-3), "samples_per_s_torch_eager_fp32": Bt / (ms_torch * 1e-3),
+                             "note": "forward + loss + backward (no optimizer); ours = egoego_train_step (fp32 CUDA-core kernels, weights re-committed "
+                                     "only when they change) through loss.backward(); torch = oracle op sequence with autograd on the same GPU"}
+    except Exception as ex:
+        out["train_step"] = {"error": repr(ex)[:300]}
     return out
 
 

@@ -770,7 +770,7 @@ struct TrainWs {
     int B = 0;                                   // windows the workspace is sized for
     std::vector<DevBuf> Hin;                     // NL + 1 residual streams [M,512]
     std::vector<TrainLayerBufs> L;
-    DevBuf OUT, dOUT, dH, dH1, dY, dF, dO, dQKV, Ta, Tb, WT, gp, bp, loss;
+    DevBuf OUT, dOUT, dH, dH1, dY, dF, dO, dQKV, Ta, Tb, WT, gp, bp, loss, Tmp;
     std::map<std::string, DevBuf> grads;         // fused / padded gradient buffers
 };
 
@@ -782,15 +782,42 @@ void train_release(egoego_ctx* c) {
     if (TrainWs* w = it->second.get()) {
         for (auto& h : w->Hin) h.release();
         for (auto& l : w->L) for (DevBuf* b : {&l.QKV, &l.O, &l.Y1, &l.st1, &l.H1, &l.F, &l.Y2, &l.st2}) b->release();
-        for (DevBuf* b : {&w->OUT, &w->dOUT, &w->dH, &w->dH1, &w->dY, &w->dF, &w->dO, &w->dQKV, &w->Ta, &w->Tb, &w->WT, &w->gp, &w->bp, &w->loss}) b->release();
+        for (DevBuf* b : {&w->OUT, &w->dOUT, &w->dH, &w->dH1, &w->dY, &w->dF, &w->dO, &w->dQKV, &w->Ta, &w->Tb, &w->WT, &w->gp, &w->bp, &w->loss, &w->Tmp}) b->release();
         for (auto& kv : w->grads) kv.second.release();
     }
     g_train.erase(it);
 }
 
+// products of the training step: tensor cores (tc_gemm_f32: 3-term bf16 split, fp32-grade) by default, the fp32 CUDA-core
+// sgemm with EGOEGO_TRAIN_GEMM=simt (bisecting).  Epilogue functors of the validation engine are applied by an element-wise
+// pass over the raw product in the tensor-core path.
+static bool train_use_tc() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("EGOEGO_TRAIN_GEMM"); v = (e && strcmp(e, "simt") == 0) ? 0 : 1; }
+    return v == 1;
+}
 template <class Epi>
-static void tr_gemm(const float* A, int lda, const float* W, int ldw, int rows, int N, int K, const Epi& e, cudaStream_t s) {
-    sgemm_tn_kernel<<<dim3((N + 127) / 128, rows / 128), 256, 0, s>>>(A, lda, W, ldw, N, K, e);
+static __global__ void tr_epi_kernel(const float* __restrict__ C, int ldc, int rows, int N, Epi e) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)rows * N) return;
+    const int r = (int)(i / N), c = (int)(i % N);
+    e(r, c, C[(long long)r * ldc + c]);
+}
+template <class Epi>
+static int tr_gemm(TrainWs* w, const float* A, int lda, const float* W, int ldw, int rows, int N, int K, const Epi& e, cudaStream_t s) {
+    if (!train_use_tc()) { sgemm_tn_kernel<<<dim3((N + 127) / 128, rows / 128), 256, 0, s>>>(A, lda, W, ldw, N, K, e); return 0; }
+    const int ldt = ((N + 3) / 4) * 4;
+    if (tc_gemm_f32(A, lda, W, ldw, rows, N, K, w->Tmp.as<float>(), ldt, ldt, 0, s)) return 1;
+    tr_epi_kernel<<<(unsigned)(((long long)rows * N + 255) / 256), 256, 0, s>>>(w->Tmp.as<float>(), ldt, rows, N, e);
+    return 0;
+}
+// C (= or +=) A W^T without an epilogue (N % 4 == 0)
+static int tr_gemm_plain(const float* A, int lda, const float* W, int ldw, int rows, int N, int K, float* C, int ldc, bool acc, cudaStream_t s) {
+    if (train_use_tc()) return tc_gemm_f32(A, lda, W, ldw, rows, N, K, C, ldc, N, acc ? 1 : 0, s);
+    const int rp = ((rows + 127) / 128) * 128;
+    if (acc) sgemm_tn_kernel<<<dim3((N + 127) / 128, rp / 128), 256, 0, s>>>(A, lda, W, ldw, N, K, EpiAccum{C, ldc});
+    else     sgemm_tn_kernel<<<dim3((N + 127) / 128, rp / 128), 256, 0, s>>>(A, lda, W, ldw, N, K, EpiPlainBias{C, ldc, nullptr});
+    return 0;
 }
 static void tr_transpose(const float* src, int R, int C, int ld, float* dst, int ldo, cudaStream_t s) {
     tr_transpose_kernel<<<dim3((C + 31) / 32, (R + 31) / 32), dim3(32, 8), 0, s>>>(src, R, C, ld, dst, ldo);
@@ -799,16 +826,15 @@ static void tr_colsum(const float* X, int M, int C, int ld, float* out, cudaStre
     tr_colsum_kernel<<<(C + 31) / 32, dim3(32, 8), 0, s>>>(X, M, C, ld, out, 1.0f);
 }
 // g [rowsW, Kd] = dY^T [rowsW, M] X [M, Kd]  (dY [M, ldy] with rowsW valid columns, X [M, ldx] with Kd valid columns)
-static void tr_weight_grad(TrainWs* w, const float* dY, int ldy, int rowsW, const float* X, int ldx, int Kd, int M, float* g, int ldg, cudaStream_t s) {
-    const int rp = ((rowsW + 127) / 128) * 128;
-    tr_transpose(dY, M, rowsW, ldy, w->Ta.as<float>(), M, s);          // [rowsW, M]; rows rowsW..rp of Ta may hold stale data: harmless,
-    tr_transpose(X, M, Kd, ldx, w->Tb.as<float>(), M, s);              // the matching output rows land in the padded part of g
-    tr_gemm(w->Ta.as<float>(), M, w->Tb.as<float>(), M, rp, Kd, M, EpiPlainBias{g, ldg, nullptr}, s);
+static int tr_weight_grad(TrainWs* w, const float* dY, int ldy, int rowsW, const float* X, int ldx, int Kd, int M, float* g, int ldg, cudaStream_t s) {
+    tr_transpose(dY, M, rowsW, ldy, w->Ta.as<float>(), M, s);          // [rowsW, M] (SIMT path: rows up to the next multiple of 128 may hold
+    tr_transpose(X, M, Kd, ldx, w->Tb.as<float>(), M, s);              // stale data; their products land in the padded rows of g)
+    return tr_gemm_plain(w->Ta.as<float>(), M, w->Tb.as<float>(), M, rowsW, Kd, M, g, ldg, false, s);
 }
 
 static int train_alloc(egoego_ctx* c, TrainWs* w, int B) {
     if (w->B >= B) return 0;
-    const size_t M = (size_t)B * LP, d = c->d, nq = 3 * c->H * c->dk, hd = c->H * c->dk;
+    const size_t M = (size_t)((B + 1) / 2) * 2 * LP, d = c->d, nq = 3 * c->H * c->dk, hd = c->H * c->dk;   // rows rounded to the 256-row tile grid
     w->Hin.resize(c->NL + 1); w->L.resize(c->NL);
     for (auto& h : w->Hin) if (h.alloc(M * d * 4)) return 1;
     for (auto& l : w->L)
@@ -816,7 +842,7 @@ static int train_alloc(egoego_ctx* c, TrainWs* w, int B) {
             l.F.alloc(M * d * 4) || l.Y2.alloc(M * d * 4) || l.st2.alloc(M * 2 * 4)) return 1;
     if (w->OUT.alloc(M * 256 * 4) || w->dOUT.alloc(M * 256 * 4) || w->dH.alloc(M * d * 4) || w->dH1.alloc(M * d * 4) || w->dY.alloc(M * d * 4) ||
         w->dF.alloc(M * d * 4) || w->dO.alloc(M * hd * 4) || w->dQKV.alloc(M * nq * 4) || w->Ta.alloc(nq * M * 4) || w->Tb.alloc(hd * M * 4) ||
-        w->WT.alloc(nq * d * 4) || w->gp.alloc(M * d * 4) || w->bp.alloc(M * d * 4) || w->loss.alloc(8)) return 1;
+        w->WT.alloc(nq * d * 4) || w->gp.alloc(M * d * 4) || w->bp.alloc(M * d * 4) || w->loss.alloc(8) || w->Tmp.alloc(M * nq * 4)) return 1;
     if (c->Ain.bytes < M * c->kin_pad * 4 && c->Ain.alloc(M * c->kin_pad * 4)) return 1;
     auto G = [&](const std::string& k, size_t n) -> int { return w->grads[k].alloc(n * 4); };
     if (G("start_w", (size_t)d * c->kin_pad) || G("start_b", d) || G("out_w", (size_t)256 * d) || G("out_b", 256) ||
@@ -861,21 +887,21 @@ int egoego_train_step(egoego_handle c, const float* x_start, const float* cond_m
     // ---------------- forward ----------------
     EG_CUDA(cudaMemsetAsync(c->Ain.p, 0, (size_t)M * KP * 4, s));
     tr_prep_kernel<<<nblk(nel), 256, 0, s>>>(x_start, cond_mask, noise, cond_noise, sqrt_ac, sqrt_1mac, c->Ain.as<float>(), KP, B, T, D);
-    tr_gemm(c->Ain.as<float>(), KP, c->start_w.as<float>(), KP, M, d, KP,
-            EpiStart{w->Hin[0].as<float>(), d, c->start_b.as<float>(), nullptr, c->pos.as<float>(), c->temb.as<float>(), ts, T}, s);
+    if (tr_gemm(w, c->Ain.as<float>(), KP, c->start_w.as<float>(), KP, M, d, KP,
+                EpiStart{w->Hin[0].as<float>(), d, c->start_b.as<float>(), nullptr, c->pos.as<float>(), c->temb.as<float>(), ts, T}, s)) return 1;
     for (int l = 0; l < c->NL; ++l) {
         LayerW& W = c->layers[l];
         TrainLayerBufs& b = w->L[l];
         float* Hin = w->Hin[l].as<float>();
-        tr_gemm(Hin, d, W.wqkv.as<float>(), d, M, nq, d, EpiBiasScale{b.QKV.as<float>(), nq, W.bqkv.as<float>(), hd, qs}, s);
+        if (tr_gemm(w, Hin, d, W.wqkv.as<float>(), d, M, nq, d, EpiBiasScale{b.QKV.as<float>(), nq, W.bqkv.as<float>(), hd, qs}, s)) return 1;
         attention_simt_kernel<false><<<B * H, 256, ATT_SIMT_SMEM, s>>>(b.QKV.as<float>(), nq, b.O.as<float>(), nullptr, nullptr, hd, H, L);
-        tr_gemm(b.O.as<float>(), hd, W.fc_w.as<float>(), hd, M, d, hd, EpiBiasResid{b.Y1.as<float>(), d, W.fc_b.as<float>(), Hin}, s);
+        if (tr_gemm(w, b.O.as<float>(), hd, W.fc_w.as<float>(), hd, M, d, hd, EpiBiasResid{b.Y1.as<float>(), d, W.fc_b.as<float>(), Hin}, s)) return 1;
         tr_ln_fwd_kernel<<<M / 8, 256, 0, s>>>(b.Y1.as<float>(), b.H1.as<float>(), b.st1.as<float>(), W.ln1_g.as<float>(), W.ln1_b.as<float>(), pmask, T, M);
-        tr_gemm(b.H1.as<float>(), d, W.w1.as<float>(), d, M, d, d, EpiBiasRelu{b.F.as<float>(), d, W.b1.as<float>()}, s);
-        tr_gemm(b.F.as<float>(), d, W.w2.as<float>(), d, M, d, d, EpiBiasResid{b.Y2.as<float>(), d, W.b2.as<float>(), b.H1.as<float>()}, s);
+        if (tr_gemm(w, b.H1.as<float>(), d, W.w1.as<float>(), d, M, d, d, EpiBiasRelu{b.F.as<float>(), d, W.b1.as<float>()}, s)) return 1;
+        if (tr_gemm(w, b.F.as<float>(), d, W.w2.as<float>(), d, M, d, d, EpiBiasResid{b.Y2.as<float>(), d, W.b2.as<float>(), b.H1.as<float>()}, s)) return 1;
         tr_ln_fwd_kernel<<<M / 8, 256, 0, s>>>(b.Y2.as<float>(), w->Hin[l + 1].as<float>(), b.st2.as<float>(), W.ln2_g.as<float>(), W.ln2_b.as<float>(), pmask, T, M);
     }
-    tr_gemm(w->Hin[c->NL].as<float>(), d, c->out_w.as<float>(), d, M, D, d, EpiPlainBias{w->OUT.as<float>(), 256, c->out_b.as<float>()}, s);
+    if (tr_gemm(w, w->Hin[c->NL].as<float>(), d, c->out_w.as<float>(), d, M, D, d, EpiPlainBias{w->OUT.as<float>(), 256, c->out_b.as<float>()}, s)) return 1;
     EG_CUDA(cudaMemsetAsync(w->dOUT.p, 0, (size_t)M * 256 * 4, s));
     EG_CUDA(cudaMemsetAsync(w->loss.p, 0, 8, s));
     tr_loss_kernel<<<nblk(nel), 256, 0, s>>>(w->OUT.as<float>(), 256, c->cfg.objective == 0 ? noise : x_start, pmask, weight, loss_l2, B, T, D,
@@ -885,11 +911,11 @@ int egoego_train_step(egoego_handle c, const float* x_start, const float* cond_m
     auto G = [&](const std::string& k) { return w->grads[k].as<float>(); };
     float *dH = w->dH.as<float>(), *dH1 = w->dH1.as<float>(), *dY = w->dY.as<float>(), *dF = w->dF.as<float>(), *WT = w->WT.as<float>();
     // linear_out (:102,139): out = H[:, 1:] Wout^T + b
-    tr_weight_grad(w, w->dOUT.as<float>(), 256, D, w->Hin[c->NL].as<float>(), d, d, M, G("out_w"), d, s);
+    if (tr_weight_grad(w, w->dOUT.as<float>(), 256, D, w->Hin[c->NL].as<float>(), d, d, M, G("out_w"), d, s)) return 1;
     tr_colsum(w->dOUT.as<float>(), M, D, 256, G("out_b"), s);
     EG_CUDA(cudaMemsetAsync(WT, 0, (size_t)d * 256 * 4, s));
     tr_transpose(c->out_w.as<float>(), D, d, d, WT, 256, s);                              // Wout^T [512, 256]
-    tr_gemm(w->dOUT.as<float>(), 256, WT, 256, M, d, 256, EpiPlainBias{dH, d, nullptr}, s);
+    if (tr_gemm_plain(w->dOUT.as<float>(), 256, WT, 256, M, d, 256, dH, d, false, s)) return 1;
     for (int l = c->NL - 1; l >= 0; --l) {
         LayerW& W = c->layers[l];
         TrainLayerBufs& b = w->L[l];
@@ -899,29 +925,29 @@ int egoego_train_step(egoego_handle c, const float* x_start, const float* cond_m
         tr_colsum(w->gp.as<float>(), M, d, d, G(p + "ln2_g"), s);
         tr_colsum(w->bp.as<float>(), M, d, d, G(p + "ln2_b"), s);
         tr_colsum(dY, M, d, d, G(p + "b2"), s);
-        tr_weight_grad(w, dY, d, d, b.F.as<float>(), d, d, M, G(p + "w2"), d, s);
+        if (tr_weight_grad(w, dY, d, d, b.F.as<float>(), d, d, M, G(p + "w2"), d, s)) return 1;
         tr_transpose(W.w2.as<float>(), d, d, d, WT, d, s);
-        tr_gemm(dY, d, WT, d, M, d, d, EpiPlainBias{dF, d, nullptr}, s);
+        if (tr_gemm_plain(dY, d, WT, d, M, d, d, dF, d, false, s)) return 1;
         tr_relu_bwd_kernel<<<nblk((long long)M * d), 256, 0, s>>>(dF, b.F.as<float>(), (long long)M * d);
         tr_colsum(dF, M, d, d, G(p + "b1"), s);
-        tr_weight_grad(w, dF, d, d, b.H1.as<float>(), d, d, M, G(p + "w1"), d, s);
+        if (tr_weight_grad(w, dF, d, d, b.H1.as<float>(), d, d, M, G(p + "w1"), d, s)) return 1;
         EG_CUDA(cudaMemcpyAsync(dH1, dY, (size_t)M * d * 4, cudaMemcpyDeviceToDevice, s));      // residual branch
         tr_transpose(W.w1.as<float>(), d, d, d, WT, d, s);
-        tr_gemm(dF, d, WT, d, M, d, d, EpiAccum{dH1, d}, s);
+        if (tr_gemm_plain(dF, d, WT, d, M, d, d, dH1, d, true, s)) return 1;
         // ---- attention block (:61-95): H1 = LN1(O Wfc^T + bfc + Hin) * pm
         tr_ln_bwd_kernel<<<M / 8, 256, 0, s>>>(dH1, b.Y1.as<float>(), b.st1.as<float>(), W.ln1_g.as<float>(), pmask, T, M, dY, w->gp.as<float>(), w->bp.as<float>());
         tr_colsum(w->gp.as<float>(), M, d, d, G(p + "ln1_g"), s);
         tr_colsum(w->bp.as<float>(), M, d, d, G(p + "ln1_b"), s);
         tr_colsum(dY, M, d, d, G(p + "fc_b"), s);
-        tr_weight_grad(w, dY, d, d, b.O.as<float>(), hd, hd, M, G(p + "fc_w"), hd, s);
+        if (tr_weight_grad(w, dY, d, d, b.O.as<float>(), hd, hd, M, G(p + "fc_w"), hd, s)) return 1;
         tr_transpose(W.fc_w.as<float>(), d, hd, hd, WT, d, s);                              // Wfc^T [1024, 512]
-        tr_gemm(dY, d, WT, d, M, hd, d, EpiPlainBias{w->dO.as<float>(), hd, nullptr}, s);
+        if (tr_gemm_plain(dY, d, WT, d, M, hd, d, w->dO.as<float>(), hd, false, s)) return 1;
         attention_bwd_simt_kernel<<<B * H, 256, ATT_BWD_SMEM, s>>>(b.QKV.as<float>(), nq, w->dO.as<float>(), hd, w->dQKV.as<float>(), H, L, qs);
         tr_colsum(w->dQKV.as<float>(), M, nq, nq, G(p + "bqkv"), s);
-        tr_weight_grad(w, w->dQKV.as<float>(), nq, nq, w->Hin[l].as<float>(), d, d, M, G(p + "wqkv"), d, s);
+        if (tr_weight_grad(w, w->dQKV.as<float>(), nq, nq, w->Hin[l].as<float>(), d, d, M, G(p + "wqkv"), d, s)) return 1;
         EG_CUDA(cudaMemcpyAsync(dH, dY, (size_t)M * d * 4, cudaMemcpyDeviceToDevice, s));       // residual branch
         tr_transpose(W.wqkv.as<float>(), nq, d, d, WT, nq, s);                              // Wqkv^T [512, 3072]
-        tr_gemm(w->dQKV.as<float>(), nq, WT, nq, M, d, nq, EpiAccum{dH, d}, s);
+        if (tr_gemm_plain(w->dQKV.as<float>(), nq, WT, nq, M, d, nq, dH, d, true, s)) return 1;
     }
     // ---- time token (:105-116,122-123) and start_conv (transformer_module.py:203)
     for (const char* k : {"t_w1", "t_b1", "t_w2", "t_b2"}) EG_CUDA(cudaMemsetAsync(w->grads[k].p, 0, w->grads[k].bytes, s));
@@ -929,7 +955,7 @@ int egoego_train_step(egoego_handle c, const float* x_start, const float* cond_m
                                          G("t_w1"), G("t_b1"), G("t_w2"), G("t_b2"), d);
     tr_frame_rows_kernel<<<nblk((long long)M * d), 256, 0, s>>>(dH, dY, T, M, d);
     tr_colsum(dY, M, d, d, G("start_b"), s);
-    tr_weight_grad(w, dY, d, d, c->Ain.as<float>(), KP, KP, M, G("start_w"), KP, s);
+    if (tr_weight_grad(w, dY, d, d, c->Ain.as<float>(), KP, KP, M, G("start_w"), KP, s)) return 1;
     {   // loss scalar (double accumulator) -> float
         double h = 0.0;
         EG_CUDA(cudaMemcpyAsync(&h, w->loss.p, 8, cudaMemcpyDeviceToHost, s));

@@ -620,6 +620,56 @@ __global__ void maxdiff_kernel(const float* a, const float* b, long long n, floa
     if ((threadIdx.x & 31) == 0) { atomicMax(reinterpret_cast<int*>(out), __float_as_int(d)); atomicMax(reinterpret_cast<int*>(out) + 1, __float_as_int(m)); }
 }
 
+// ---- generic fp32 product on the tensor cores (training step) ------------------------------------------------------
+// C[M, N] (= or +=) A[M, K] W[N, K]^T for fp32 row-major operands in device memory: both are split into bf16 hi/lo planes
+// (zero-padded to the tile grid: rows to 256, K to 64) and multiplied with the 3-term split CTA-pair kernel -- fp32-grade
+// results at tensor-core speed.  Planes (with their TMA maps) are cached per padded shape and role.
+__global__ void split_pad_kernel(const float* __restrict__ src, int rows, int cols, int ld, __nv_bfloat16* __restrict__ hi,
+                                 __nv_bfloat16* __restrict__ lo, int rows_pad, int cols_pad) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)rows_pad * cols_pad) return;
+    const int r = (int)(i / cols_pad), c = (int)(i % cols_pad);
+    const float v = (r < rows && c < cols) ? src[(long long)r * ld + c] : 0.f;
+    split_bf16(v, hi[i], lo[i]);
+}
+
+struct TcGemmCache {
+    std::map<std::pair<long long, int>, std::unique_ptr<Plane>> planes;     // (rows_pad << 20 | cols_pad, role) -> plane
+    TcImpl I;
+    bool init = false;
+    ~TcGemmCache() { for (auto& kv : planes) kv.second->release(); }
+};
+static TcGemmCache g_tcg;
+
+int tc_gemm_f32(const float* A, int lda, const float* W, int ldw, int M, int N, int K, float* C, int ldc, int n_valid, int accumulate,
+                cudaStream_t s) {
+    EG_CHECK(M >= 1 && N >= 1 && K >= 1 && n_valid % 4 == 0 && ldc % 4 == 0, "tc_gemm_f32: bad shape");
+    if (!g_tcg.init) {
+        int dev = 0;
+        EG_CUDA(cudaGetDevice(&dev));
+        EG_CUDA(cudaDeviceGetAttribute(&g_tcg.I.sms, cudaDevAttrMultiProcessorCount, dev));
+        g_tcg.init = true;
+    }
+    const int Mp = ((M + 255) / 256) * 256, Np = ((N + 255) / 256) * 256, Kp = ((K + 63) / 64) * 64;
+    auto plane = [&](int rows, int cols, int role, uint32_t box) -> Plane* {
+        auto key = std::make_pair(((long long)rows << 20) | cols, role);
+        auto it = g_tcg.planes.find(key);
+        if (it != g_tcg.planes.end()) return it->second.get();
+        std::unique_ptr<Plane> p(new Plane());
+        if (p->alloc(rows, cols, box)) return nullptr;
+        Plane* raw = p.get();
+        g_tcg.planes[key] = std::move(p);
+        return raw;
+    };
+    Plane* PA = plane(Mp, Kp, 0, 128);
+    Plane* PW = plane(Np, Kp, 1, 256);
+    EG_CHECK(PA && PW, "tc_gemm_f32: plane allocation failed");
+    split_pad_kernel<<<(unsigned)(((long long)Mp * Kp + 255) / 256), 256, 0, s>>>(A, M, K, lda, PA->hi, PA->lo, Mp, Kp);
+    split_pad_kernel<<<(unsigned)(((long long)Np * Kp + 255) / 256), 256, 0, s>>>(W, N, K, ldw, PW->hi, PW->lo, Np, Kp);
+    TcEpiPlainAcc e{{}, C, ldc, n_valid, accumulate};
+    return launch_gemm_2cta<FMT_SPLIT>(&g_tcg.I, *PA, *PW, Mp, Np, Kp, e, s);
+}
+
 struct EpiStore { float* C; int ldc; __device__ void operator()(int r, int c, float a) const { C[(long long)r * ldc + c] = a; } };
 
 int selftest_gemm(int M, int N, int K, unsigned long long seed, int two_cta, int half_fmt, float* max_abs_err, float* max_abs_ref, float* ms) {

@@ -48,6 +48,11 @@ private:
     TcImpl* impl_;
 };
 
+// C[M, N] (= or +=) A[M, K] W[N, K]^T, fp32 row-major device operands, on the tensor cores (3-term bf16 split, fp32 accumulate).
+// C must have ceil(M / 256) * 256 rows of ldc floats; columns [0, n_valid) are written (n_valid % 4 == 0 <= ldc).
+int tc_gemm_f32(const float* A, int lda, const float* W, int ldw, int M, int N, int K, float* C, int ldc, int n_valid, int accumulate,
+                cudaStream_t s);
+
 // tcgen05 split GEMM vs fp32 SIMT GEMM on random data (C = A W^T, no epilogue); returns max |err|, max |ref|, ms/launch.
 int selftest_gemm(int M, int N, int K, unsigned long long seed, int two_cta, int half_fmt, float* max_abs_err, float* max_abs_ref, float* ms);
 

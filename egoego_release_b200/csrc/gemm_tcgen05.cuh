@@ -185,6 +185,18 @@ struct TcEpiPlain : EpiNoDirect, EpiNoPre {   // C = acc (+ bias): self-test / g
     }
 };
 
+struct TcEpiPlainAcc : EpiNoDirect {         // C = acc (accumulate == 0) or C += acc: generic products of the training step
+    float* C; int ldc; int n_valid; int accumulate;
+    __device__ __forceinline__ float4 bias4(int) const { return make_float4(0.f, 0.f, 0.f, 0.f); }
+    __device__ __forceinline__ float4 pre(int row, int col) const {
+        return (accumulate && col < n_valid) ? *reinterpret_cast<const float4*>(C + (long long)row * ldc + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __device__ __forceinline__ void apply4(int row, int col, float4 a, float4, float4 old) const {
+        if (col >= n_valid) return;
+        *reinterpret_cast<float4*>(C + (long long)row * ldc + col) = add4(a, old);
+    }
+};
+
 struct TcEpiBase : EpiNoDirect, EpiNoPre {    // base = x_cond-half of start_conv + bias + positional row (constant per window)
     float* base; int ld; const float* bias; const float* pos; int T;
     __device__ __forceinline__ float4 bias4(int col) const { return ld4(bias + col); }

@@ -2,8 +2,10 @@
 // activations, L1/L2 loss with the padding mask, and the full backward pass -- gradients of all 72 parameter tensors.
 //
 // Follows CondGaussianDiffusion.forward / p_losses / q_sample (egoego/model/transformer_cond_diffusion_model.py:557-625) and the
-// modules they run (transformer_module.py:61-142,188-226; time_mlp :105-116).  fp32 CUDA-core kernels (sgemm_tn_kernel for
-// every product; operands of the weight-gradient products are transposed explicitly), a recomputing attention backward.
+// modules they run (transformer_module.py:61-142,188-226; time_mlp :105-116).  All 53 matrix products of a step run on the
+// tensor cores through tc_gemm_f32 (3-term bf16 split, fp32-grade; engine_tc.cu) -- EGOEGO_TRAIN_GEMM=simt keeps the fp32
+// CUDA-core sgemm for bisecting; operands of the weight-gradient products are transposed explicitly; attention forward /
+// backward (the backward recomputes P) are fp32 CUDA-core kernels.
 // Dropout is not applied (identity): the parity bar of this row is the reference with its modules in eval() mode
 // (oracle/training.py) -- torch's dropout stream cannot be reproduced outside torch.
 //

@@ -32,8 +32,8 @@ def test_training_loss_and_gradients_vs_reference_golden(tag, B, T, seed, with_p
 @pytest.mark.parametrize("tag,B,T,seed,with_pm", CASES)
 def test_gpu_training_step_vs_reference_golden(tag, B, T, seed, with_pm, golden_dir, params0):
     """CondGaussianDiffusion.p_losses on the device (egoego_train_step: fp32 forward + backward kernels) against the loss and
-    the gradient fingerprints of the unmodified reference (eval-mode dropout).  Tolerance 1e-3 of each tensor's gradient norm
-    (fp32 sums in a different order; the weight-gradient products reduce over B*128 rows)."""
+    the gradient fingerprints of the unmodified reference (eval-mode dropout).  Tolerances are fractions of each tensor's
+    gradient norm (products run as 3-term bf16 splits on the tensor cores and reduce over B*128 rows in a different order)."""
     import torch
     import egoego_release_b200 as E
     g = dict(np.load(os.path.join(golden_dir, "training.npz")))
@@ -55,7 +55,9 @@ def test_gpu_training_step_vs_reference_golden(tag, B, T, seed, with_pm, golden_
         scale = max(abs(ref[0]), abs(ref[1]), 1e-6)
         err = float(np.abs(v.numpy() - ref).max() / scale)
         worst = max(worst, (err, k))
-        assert err < 1e-3, (k, err, v.numpy()[:4], ref[:4])
+        # the `sum` entry cancels over up to 1.5 M signed elements: 2e-3 of the norm; norm and the eight sampled values: 5e-4
+        assert err < 2e-3, (k, err, v.numpy()[:4], ref[:4])
+        assert abs(v.numpy()[0] - ref[0]) < 5e-4 * scale and np.abs(v.numpy()[2:] - ref[2:]).max() < 5e-4 * scale, (k, v.numpy()[:4], ref[:4])
     print(f"[{tag}] loss {float(loss.detach()):.6f} vs {float(g[f'{tag}_loss']):.6f}; worst gradient fingerprint error {worst[0]:.2e} of its norm ({worst[1]})")
     # a small gradient-descent step through a stock torch optimizer lowers the loss on the same batch: the gradients point downhill
     # and the engine picks up the updated parameters
