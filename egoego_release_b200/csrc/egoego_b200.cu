@@ -63,6 +63,7 @@ struct egoego_ctx {
     int graph_B = -1, graph_T = -1; const void* graph_key[4] = {nullptr};
     int precise_last = 0;                  // steps t < precise_last use the 3-term split; earlier steps single-pass fp16
     bool use_graph = true;
+    bool temb_dirty = false;               // time_mlp weights were updated in place (egoego_update_tensor_device): rebuild the table before use
     bool fuse_ddpm = false;                // EGOEGO_FUSE_DDPM=1: DDPM update in linear_out's epilogue.  Opt-in: measured 90 us vs 17.6 + 32.9 us for
                                            // linear_out + ddpm_update_kernel at B = 256 (8 epilogue warps per SM are too few for the Philox work)
     int64_t launches = 0;
@@ -884,6 +885,10 @@ int egoego_train_step(egoego_handle c, const float* x_start, const float* cond_m
     auto nblk = [](long long n) { return (unsigned)((n + 255) / 256); };
     TSrc ts{reinterpret_cast<const long long*>(t_dev), nullptr, 0, c->N - 1};
 
+    if (c->temb_dirty) {
+        time_table_kernel<<<c->N, 256, 0, s>>>(c->t_w1.as<float>(), c->t_b1.as<float>(), c->t_w2.as<float>(), c->t_b2.as<float>(), c->temb.as<float>(), d);
+        c->temb_dirty = false;
+    }
     // ---------------- forward ----------------
     EG_CUDA(cudaMemsetAsync(c->Ain.p, 0, (size_t)M * KP * 4, s));
     tr_prep_kernel<<<nblk(nel), 256, 0, s>>>(x_start, cond_mask, noise, cond_noise, sqrt_ac, sqrt_1mac, c->Ain.as<float>(), KP, B, T, D);
@@ -956,16 +961,66 @@ int egoego_train_step(egoego_handle c, const float* x_start, const float* cond_m
     tr_frame_rows_kernel<<<nblk((long long)M * d), 256, 0, s>>>(dH, dY, T, M, d);
     tr_colsum(dY, M, d, d, G("start_b"), s);
     if (tr_weight_grad(w, dY, d, d, c->Ain.as<float>(), KP, KP, M, G("start_w"), KP, s)) return 1;
-    {   // loss scalar (double accumulator) -> float
-        double h = 0.0;
-        EG_CUDA(cudaMemcpyAsync(&h, w->loss.p, 8, cudaMemcpyDeviceToHost, s));
-        EG_CUDA(cudaStreamSynchronize(s));
-        const float f = (float)h;
-        EG_CUDA(cudaMemcpyAsync(loss_out, &f, 4, cudaMemcpyHostToDevice, s));
-        EG_CUDA(cudaStreamSynchronize(s));
-    }
+    tr_loss_finish_kernel<<<1, 1, 0, s>>>(w->loss.as<double>(), loss_out);      // fp64 accumulator -> the caller's float, no host round trip
     c->launches += 40 * c->NL + 20;
     EG_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// In-place device-to-device refresh of ONE parameter tensor of a committed fp32 (SIMT-engine) handle -- what an optimizer step
+// needs between two training steps (a full egoego_set_tensor + egoego_commit_weights round trip goes through host staging and
+// re-allocates the workspace).  src_dev: fp32 device pointer in the reference's layout.
+int egoego_update_tensor_device(egoego_handle c, const char* name_in, const float* src, int64_t numel, void* stream_v) {
+    EG_CHECK(c && name_in && src, "null argument");
+    EG_CHECK(c->committed && c->cfg.engine == EGOEGO_ENGINE_SIMT, "needs a committed EGOEGO_ENGINE_SIMT handle");
+    EG_CUDA(cudaSetDevice(c->cfg.device));
+    cudaStream_t s = (cudaStream_t)stream_v;
+    std::string name(name_in);
+    for (const char* pre : {"ema_model.", "model.", "module."})
+        if (name.rfind(pre, 0) == 0) name = name.substr(strlen(pre));
+    const int d = c->d, hd = c->H * c->dk, D = c->D;
+    float* dst = nullptr; int64_t expect = 0;
+    const std::string pre = "denoise_fn.motion_transformer.";
+    if (name == pre + "start_conv.weight") {
+        EG_CHECK(numel == (int64_t)d * 2 * D, "tensor '" + name + "': wrong size");
+        EG_CUDA(cudaMemcpy2DAsync(c->start_w.p, (size_t)c->kin_pad * 4, src, (size_t)2 * D * 4, (size_t)2 * D * 4, d, cudaMemcpyDeviceToDevice, s));
+        return 0;
+    }
+    if (name == pre + "start_conv.bias") { dst = c->start_b.as<float>(); expect = d; }
+    else if (name == pre + "position_vec.weight") { dst = c->pos.as<float>(); expect = (int64_t)(c->cfg.max_timesteps + 1) * d; }
+    else if (name == "denoise_fn.linear_out.weight") { dst = c->out_w.as<float>(); expect = (int64_t)D * d; }
+    else if (name == "denoise_fn.linear_out.bias") { dst = c->out_b.as<float>(); expect = D; }
+    else if (name == "denoise_fn.time_mlp.1.weight") { dst = c->t_w1.as<float>(); expect = 256 * 64; c->temb_dirty = true; }
+    else if (name == "denoise_fn.time_mlp.1.bias") { dst = c->t_b1.as<float>(); expect = 256; c->temb_dirty = true; }
+    else if (name == "denoise_fn.time_mlp.3.weight") { dst = c->t_w2.as<float>(); expect = (int64_t)d * 256; c->temb_dirty = true; }
+    else if (name == "denoise_fn.time_mlp.3.bias") { dst = c->t_b2.as<float>(); expect = d; c->temb_dirty = true; }
+    else if (name.rfind(pre + "layer_stack.", 0) == 0) {
+        const std::string rest = name.substr((pre + "layer_stack.").size());
+        const size_t dot = rest.find('.');
+        EG_CHECK(dot != std::string::npos, "unknown tensor: " + name);
+        const int l = atoi(rest.substr(0, dot).c_str());
+        EG_CHECK(l >= 0 && l < c->NL, "layer index out of range: " + name);
+        LayerW& L = c->layers[l];
+        const std::string k = rest.substr(dot + 1);
+        const char* secs[3] = {"w_q", "w_k", "w_v"};
+        for (int sct = 0; sct < 3; ++sct) {
+            if (k == std::string("self_attn.") + secs[sct] + ".weight") { dst = L.wqkv.as<float>() + (size_t)sct * hd * d; expect = (int64_t)hd * d; }
+            if (k == std::string("self_attn.") + secs[sct] + ".bias") { dst = L.bqkv.as<float>() + (size_t)sct * hd; expect = hd; }
+        }
+        if (k == "self_attn.fc.weight") { dst = L.fc_w.as<float>(); expect = (int64_t)d * hd; }
+        else if (k == "self_attn.fc.bias") { dst = L.fc_b.as<float>(); expect = d; }
+        else if (k == "self_attn.layer_norm.weight") { dst = L.ln1_g.as<float>(); expect = d; }
+        else if (k == "self_attn.layer_norm.bias") { dst = L.ln1_b.as<float>(); expect = d; }
+        else if (k == "pos_ffn.w_1.weight") { dst = L.w1.as<float>(); expect = (int64_t)d * d; }
+        else if (k == "pos_ffn.w_1.bias") { dst = L.b1.as<float>(); expect = d; }
+        else if (k == "pos_ffn.w_2.weight") { dst = L.w2.as<float>(); expect = (int64_t)d * d; }
+        else if (k == "pos_ffn.w_2.bias") { dst = L.b2.as<float>(); expect = d; }
+        else if (k == "pos_ffn.layer_norm.weight") { dst = L.ln2_g.as<float>(); expect = d; }
+        else if (k == "pos_ffn.layer_norm.bias") { dst = L.ln2_b.as<float>(); expect = d; }
+    }
+    if (!dst) return 0;                                  // schedule buffers etc.: not used by the training step
+    EG_CHECK(expect == numel, "tensor '" + name + "': expected " + std::to_string(expect) + " elements, got " + std::to_string(numel));
+    EG_CUDA(cudaMemcpyAsync(dst, src, (size_t)numel * 4, cudaMemcpyDeviceToDevice, s));
     return 0;
 }
 

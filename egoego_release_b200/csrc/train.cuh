@@ -181,6 +181,8 @@ static __global__ void tr_loss_kernel(const float* __restrict__ out, int ldo, co
     if (threadIdx.x == 0) atomicAdd(loss, red[0]);
 }
 
+static __global__ void tr_loss_finish_kernel(const double* __restrict__ acc, float* __restrict__ out) { *out = (float)*acc; }
+
 // time MLP backward (:105-116,122-123): d temb[b] = dH0[row b*128]; recompute emb / pre / gelu from t; accumulate parameter grads
 static __global__ void __launch_bounds__(256) tr_time_bwd_kernel(const float* __restrict__ dH0, const long long* __restrict__ t_arr,
                                                                  const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,

@@ -569,10 +569,18 @@ class CondGaussianDiffusion(nn.Module):
         sig = self._signature()
         if sig != self._ht_sig:
             with torch.cuda.device(dev):
-                for k, v in self.state_dict().items():
-                    t = _f32c(v.detach().float(), dev)
-                    check(L.egoego_set_tensor(self._ht, k.encode(), _ptr(t), t.numel(), 1))
-                check(L.egoego_commit_weights(self._ht, _stream(dev)))
+                if self._ht_sig is None:                 # first use: full commit (host staging, workspace allocation)
+                    for k, v in self.state_dict().items():
+                        t = _f32c(v.detach().float(), dev)
+                        check(L.egoego_set_tensor(self._ht, k.encode(), _ptr(t), t.numel(), 1))
+                    check(L.egoego_commit_weights(self._ht, _stream(dev)))
+                else:                                    # after an optimizer step: device-to-device refresh of what changed
+                    old = dict((k, (p, ver)) for k, p, ver in self._ht_sig)
+                    for k, v in self.named_parameters():
+                        if old.get(k) == (v.data_ptr(), v._version):
+                            continue
+                        t = _f32c(v.detach(), dev)
+                        check(L.egoego_update_tensor_device(self._ht, k.encode(), _ptr(t), t.numel(), _stream(dev)))
             self._ht_sig = sig
         return self._ht
 

@@ -246,6 +246,10 @@ int  egoego_train_step(egoego_handle h, const float* x_start_dev, const float* c
                        const int64_t* t_dev, const float* noise_dev, const float* cond_noise_dev, const float* sqrt_ac_dev,
                        const float* sqrt_1mac_dev, const float* weight_dev, int loss_l2, int B, int T, float* loss_out_dev, void* stream);
 int  egoego_train_get_grad(egoego_handle h, const char* name, float* dst_dev, int64_t numel, void* stream);
+/* Device-to-device refresh of one parameter tensor (reference state_dict key, reference layout) of a committed
+ * EGOEGO_ENGINE_SIMT handle: what an optimizer step needs between two training steps (no host staging, no re-allocation;
+ * the timestep-embedding table is rebuilt lazily when a time_mlp tensor changed). */
+int  egoego_update_tensor_device(egoego_handle h, const char* name, const float* src_dev, int64_t numel, void* stream);
 
 /* Introspection for tests/bench: number of kernels launched by this handle since creation, and the
  * cumulative count of denoiser steps executed. */
