@@ -15,7 +15,7 @@ EXPORTS = [
     "egoego_seqnet_create", "egoego_seqnet_destroy", "egoego_seqnet_set_tensor", "egoego_seqnet_commit", "egoego_seqnet_forward",
     "egoego_seqnet_launch_count", "egoego_va2rot", "egoego_rescale_slam", "egoego_slam_features", "egoego_apply_floor_normal",
     "egoego_rigid_apply", "egoego_resnet18_create", "egoego_resnet18_destroy", "egoego_resnet18_set_tensor", "egoego_resnet18_commit",
-    "egoego_resnet18_forward", "egoego_resnet18_launch_count", "egoego_train_step", "egoego_train_get_grad", "egoego_update_tensor_device",
+    "egoego_resnet18_forward", "egoego_resnet18_launch_count", "egoego_train_step", "egoego_train_get_grad", "egoego_update_tensor_device", "egoego_train_get_grads", "egoego_update_tensors_device",
 ]
 
 ENGINE_TCGEN05, ENGINE_SIMT = 0, 1
@@ -96,6 +96,8 @@ def lib():
     L.egoego_train_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp]
     L.egoego_train_get_grad.argtypes = [vp, C.c_char_p, vp, i64, vp]
     L.egoego_update_tensor_device.argtypes = [vp, C.c_char_p, vp, i64, vp]
+    L.egoego_train_get_grads.argtypes = [vp, i32, vp, vp, vp, vp]
+    L.egoego_update_tensors_device.argtypes = [vp, i32, vp, vp, vp, vp]
     L.egoego_resnet18_create.argtypes = [i32, i32, C.POINTER(vp)]
     L.egoego_resnet18_destroy.argtypes = [vp]
     L.egoego_resnet18_destroy.restype = None

@@ -823,8 +823,11 @@ static int tr_gemm_plain(const float* A, int lda, const float* W, int ldw, int r
 static void tr_transpose(const float* src, int R, int C, int ld, float* dst, int ldo, cudaStream_t s) {
     tr_transpose_kernel<<<dim3((C + 31) / 32, (R + 31) / 32), dim3(32, 8), 0, s>>>(src, R, C, ld, dst, ldo);
 }
+static float* g_cs_part = nullptr;      // [TR_CS_RB, 3072] partial column sums (one training step at a time per process)
 static void tr_colsum(const float* X, int M, int C, int ld, float* out, cudaStream_t s) {
-    tr_colsum_kernel<<<(C + 31) / 32, dim3(32, 8), 0, s>>>(X, M, C, ld, out, 1.0f);
+    if (!g_cs_part) cudaMalloc(&g_cs_part, (size_t)TR_CS_RB * 3072 * sizeof(float));
+    tr_colsum_part_kernel<<<dim3((C + 31) / 32, TR_CS_RB), dim3(32, 8), 0, s>>>(X, M, C, ld, g_cs_part);
+    tr_colsum_final_kernel<<<(C + 127) / 128, 128, 0, s>>>(g_cs_part, C, out);
 }
 // g [rowsW, Kd] = dY^T [rowsW, M] X [M, Kd]  (dY [M, ldy] with rowsW valid columns, X [M, ldx] with Kd valid columns)
 static int tr_weight_grad(TrainWs* w, const float* dY, int ldy, int rowsW, const float* X, int ldx, int Kd, int M, float* g, int ldg, cudaStream_t s) {
@@ -1074,6 +1077,18 @@ int egoego_train_get_grad(egoego_handle c, const char* name_in, float* dst, int6
     EG_CHECK(rows * cols == numel, "tensor '" + name + "': expected " + std::to_string(rows * cols) + " elements, got " + std::to_string(numel));
     if (rows == 1 || ld == cols) { EG_CUDA(cudaMemcpyAsync(dst, src, (size_t)numel * 4, cudaMemcpyDeviceToDevice, s)); }
     else { EG_CUDA(cudaMemcpy2DAsync(dst, (size_t)cols * 4, src, (size_t)ld * 4, (size_t)cols * 4, (size_t)rows, cudaMemcpyDeviceToDevice, s)); }
+    return 0;
+}
+
+// batched forms (one FFI call per step instead of one per tensor)
+int egoego_train_get_grads(egoego_handle c, int n, const char* const* names, float* const* dsts, const int64_t* numels, void* stream_v) {
+    EG_CHECK(n >= 0 && (n == 0 || (names && dsts && numels)), "null argument");
+    for (int i = 0; i < n; ++i) if (egoego_train_get_grad(c, names[i], dsts[i], numels[i], stream_v)) return 1;
+    return 0;
+}
+int egoego_update_tensors_device(egoego_handle c, int n, const char* const* names, const float* const* srcs, const int64_t* numels, void* stream_v) {
+    EG_CHECK(n >= 0 && (n == 0 || (names && srcs && numels)), "null argument");
+    for (int i = 0; i < n; ++i) if (egoego_update_tensor_device(c, names[i], srcs[i], numels[i], stream_v)) return 1;
     return 0;
 }
 

@@ -626,11 +626,29 @@ __global__ void maxdiff_kernel(const float* a, const float* b, long long n, floa
 // results at tensor-core speed.  Planes (with their TMA maps) are cached per padded shape and role.
 __global__ void split_pad_kernel(const float* __restrict__ src, int rows, int cols, int ld, __nv_bfloat16* __restrict__ hi,
                                  __nv_bfloat16* __restrict__ lo, int rows_pad, int cols_pad) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (long long)rows_pad * cols_pad) return;
-    const int r = (int)(i / cols_pad), c = (int)(i % cols_pad);
-    const float v = (r < rows && c < cols) ? src[(long long)r * ld + c] : 0.f;
-    split_bf16(v, hi[i], lo[i]);
+    // four consecutive columns per thread (cols_pad % 64 == 0); float4 loads when the source row allows it
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int qpr = cols_pad / 4;
+    if (q >= (long long)rows_pad * qpr) return;
+    const int r = (int)(q / qpr), c = (int)(q % qpr) * 4;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (r < rows) {
+        const float* p = src + (long long)r * ld + c;
+        if (c + 3 < cols && ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+            const float4 f = *reinterpret_cast<const float4*>(p);
+            v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (c + j < cols) v[j] = p[j];
+        }
+    }
+    __nv_bfloat16 h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) split_bf16(v[j], h[j], l[j]);
+    const long long o = (long long)r * cols_pad + c;
+    __nv_bfloat162 h01(h[0], h[1]), h23(h[2], h[3]), l01(l[0], l[1]), l23(l[2], l[3]);
+    *reinterpret_cast<uint2*>(hi + o) = make_uint2(*reinterpret_cast<uint32_t*>(&h01), *reinterpret_cast<uint32_t*>(&h23));
+    *reinterpret_cast<uint2*>(lo + o) = make_uint2(*reinterpret_cast<uint32_t*>(&l01), *reinterpret_cast<uint32_t*>(&l23));
 }
 
 struct TcGemmCache {
@@ -664,8 +682,8 @@ int tc_gemm_f32(const float* A, int lda, const float* W, int ldw, int M, int N, 
     Plane* PA = plane(Mp, Kp, 0, 128);
     Plane* PW = plane(Np, Kp, 1, 256);
     EG_CHECK(PA && PW, "tc_gemm_f32: plane allocation failed");
-    split_pad_kernel<<<(unsigned)(((long long)Mp * Kp + 255) / 256), 256, 0, s>>>(A, M, K, lda, PA->hi, PA->lo, Mp, Kp);
-    split_pad_kernel<<<(unsigned)(((long long)Np * Kp + 255) / 256), 256, 0, s>>>(W, N, K, ldw, PW->hi, PW->lo, Np, Kp);
+    split_pad_kernel<<<(unsigned)(((long long)Mp * Kp / 4 + 255) / 256), 256, 0, s>>>(A, M, K, lda, PA->hi, PA->lo, Mp, Kp);
+    split_pad_kernel<<<(unsigned)(((long long)Np * Kp / 4 + 255) / 256), 256, 0, s>>>(W, N, K, ldw, PW->hi, PW->lo, Np, Kp);
     TcEpiPlainAcc e{{}, C, ldc, n_valid, accumulate};
     return launch_gemm_2cta<FMT_SPLIT>(&g_tcg.I, *PA, *PW, Mp, Np, Kp, e, s);
 }

@@ -125,20 +125,30 @@ static __global__ void __launch_bounds__(256) tr_ln_bwd_kernel(const float* __re
     }
 }
 
-// column sums of X [M, C] (ld) -> out[C] (+= if accumulate): one block per 32 columns, 8 row lanes, fp32 tree
-static __global__ void tr_colsum_kernel(const float* __restrict__ X, int M, int C, int ld, float* __restrict__ out, float scale) {
-    __shared__ float part[8][33];
-    const int c = blockIdx.x * 32 + threadIdx.x;
+// column sums of X [M, C] (ld): two deterministic stages -- partial[rb][c] over TR_CS_RB row blocks (enough CTAs to fill the
+// GPU: a bias gradient reduces 4096 rows x 512..3072 columns), then the sum over the row blocks
+constexpr int TR_CS_RB = 64;
+static __global__ void tr_colsum_part_kernel(const float* __restrict__ X, int M, int C, int ld, float* __restrict__ part /*[TR_CS_RB, C]*/) {
+    __shared__ float red[8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x, rb = blockIdx.y;
+    const int r0 = (int)((long long)M * rb / TR_CS_RB), r1 = (int)((long long)M * (rb + 1) / TR_CS_RB);
     float s = 0.f;
-    if (c < C) for (int r = threadIdx.y; r < M; r += 8) s += X[(long long)r * ld + c];
-    part[threadIdx.y][threadIdx.x] = s;
+    if (c < C) for (int r = r0 + threadIdx.y; r < r1; r += 8) s += X[(long long)r * ld + c];
+    red[threadIdx.y][threadIdx.x] = s;
     __syncthreads();
     if (threadIdx.y == 0 && c < C) {
         float t = 0.f;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) t += part[k][threadIdx.x];
-        out[c] = t * scale;
+        for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+        part[(long long)rb * C + c] = t;
     }
+}
+static __global__ void tr_colsum_final_kernel(const float* __restrict__ part, int C, float* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float t = 0.f;
+    for (int rb = 0; rb < TR_CS_RB; ++rb) t += part[(long long)rb * C + c];
+    out[c] = t;
 }
 
 static __global__ void tr_relu_bwd_kernel(float* __restrict__ dF, const float* __restrict__ F, long long n) {

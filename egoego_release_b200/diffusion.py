@@ -576,11 +576,13 @@ class CondGaussianDiffusion(nn.Module):
                     check(L.egoego_commit_weights(self._ht, _stream(dev)))
                 else:                                    # after an optimizer step: device-to-device refresh of what changed
                     old = dict((k, (p, ver)) for k, p, ver in self._ht_sig)
-                    for k, v in self.named_parameters():
-                        if old.get(k) == (v.data_ptr(), v._version):
-                            continue
-                        t = _f32c(v.detach(), dev)
-                        check(L.egoego_update_tensor_device(self._ht, k.encode(), _ptr(t), t.numel(), _stream(dev)))
+                    ch = [(k, _f32c(v.detach(), dev)) for k, v in self.named_parameters() if old.get(k) != (v.data_ptr(), v._version)]
+                    if ch:
+                        n = len(ch)
+                        names = (C.c_char_p * n)(*[k.encode() for k, _ in ch])
+                        ptrs = (C.c_void_p * n)(*[t.data_ptr() for _, t in ch])
+                        nums = (C.c_int64 * n)(*[t.numel() for _, t in ch])
+                        check(L.egoego_update_tensors_device(self._ht, n, names, ptrs, nums, _stream(dev)))
             self._ht_sig = sig
         return self._ht
 
@@ -632,10 +634,17 @@ class _TrainStepFn(torch.autograd.Function):
         model, dev = ctx.model, gout.device
         if model._ht is not ctx.handle:
             raise EgoEgoError("the training handle changed between forward and backward")
-        grads = []
+        numels = [int(torch.Size(sh).numel()) for sh in ctx.shapes]
+        flat = torch.empty(sum(numels), device=dev, dtype=torch.float32)      # one buffer, one FFI call; gradients are views into it
+        n = len(numels)
+        offs = [0]
+        for k in numels:
+            offs.append(offs[-1] + k)
+        names = (C.c_char_p * n)(*[nm.encode() for nm in ctx.names])
+        ptrs = (C.c_void_p * n)(*[flat.data_ptr() + 4 * o for o in offs[:-1]])
+        nums = (C.c_int64 * n)(*numels)
         with torch.cuda.device(dev):
-            for name, shape in zip(ctx.names, ctx.shapes):
-                g = torch.empty(shape, device=dev, dtype=torch.float32)
-                check(_capi.lib().egoego_train_get_grad(ctx.handle, name.encode(), _ptr(g), g.numel(), _stream(dev)))
-                grads.append(g * gout)
+            check(_capi.lib().egoego_train_get_grads(ctx.handle, n, names, ptrs, nums, _stream(dev)))
+        flat.mul_(gout)
+        grads = [flat[offs[i]:offs[i + 1]].view(ctx.shapes[i]) for i in range(n)]
         return (None,) * 8 + tuple(grads)

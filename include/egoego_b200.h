@@ -250,6 +250,9 @@ int  egoego_train_get_grad(egoego_handle h, const char* name, float* dst_dev, in
  * EGOEGO_ENGINE_SIMT handle: what an optimizer step needs between two training steps (no host staging, no re-allocation;
  * the timestep-embedding table is rebuilt lazily when a time_mlp tensor changed). */
 int  egoego_update_tensor_device(egoego_handle h, const char* name, const float* src_dev, int64_t numel, void* stream);
+/* Batched forms of the two calls above (one FFI call per training step instead of one per tensor). */
+int  egoego_train_get_grads(egoego_handle h, int n, const char* const* names, float* const* dst_dev, const int64_t* numels, void* stream);
+int  egoego_update_tensors_device(egoego_handle h, int n, const char* const* names, const float* const* src_dev, const int64_t* numels, void* stream);
 
 /* Introspection for tests/bench: number of kernels launched by this handle since creation, and the
  * cumulative count of denoiser steps executed. */
