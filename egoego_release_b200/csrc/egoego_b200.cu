@@ -771,7 +771,7 @@ struct TrainWs {
     int B = 0;                                   // windows the workspace is sized for
     std::vector<DevBuf> Hin;                     // NL + 1 residual streams [M,512]
     std::vector<TrainLayerBufs> L;
-    DevBuf OUT, dOUT, dH, dH1, dY, dF, dO, dQKV, Ta, Tb, WT, gp, bp, loss, Tmp;
+    DevBuf OUT, dOUT, dH, dH1, dY, dF, dO, dQKV, Ta, Tb, WT, gp, bp, loss, Tmp, temb_b, iota;
     std::map<std::string, DevBuf> grads;         // fused / padded gradient buffers
 };
 
@@ -783,7 +783,7 @@ void train_release(egoego_ctx* c) {
     if (TrainWs* w = it->second.get()) {
         for (auto& h : w->Hin) h.release();
         for (auto& l : w->L) for (DevBuf* b : {&l.QKV, &l.O, &l.Y1, &l.st1, &l.H1, &l.F, &l.Y2, &l.st2}) b->release();
-        for (DevBuf* b : {&w->OUT, &w->dOUT, &w->dH, &w->dH1, &w->dY, &w->dF, &w->dO, &w->dQKV, &w->Ta, &w->Tb, &w->WT, &w->gp, &w->bp, &w->loss, &w->Tmp}) b->release();
+        for (DevBuf* b : {&w->OUT, &w->dOUT, &w->dH, &w->dH1, &w->dY, &w->dF, &w->dO, &w->dQKV, &w->Ta, &w->Tb, &w->WT, &w->gp, &w->bp, &w->loss, &w->Tmp, &w->temb_b, &w->iota}) b->release();
         for (auto& kv : w->grads) kv.second.release();
     }
     g_train.erase(it);
@@ -846,7 +846,9 @@ static int train_alloc(egoego_ctx* c, TrainWs* w, int B) {
             l.F.alloc(M * d * 4) || l.Y2.alloc(M * d * 4) || l.st2.alloc(M * 2 * 4)) return 1;
     if (w->OUT.alloc(M * 256 * 4) || w->dOUT.alloc(M * 256 * 4) || w->dH.alloc(M * d * 4) || w->dH1.alloc(M * d * 4) || w->dY.alloc(M * d * 4) ||
         w->dF.alloc(M * d * 4) || w->dO.alloc(M * hd * 4) || w->dQKV.alloc(M * nq * 4) || w->Ta.alloc(nq * M * 4) || w->Tb.alloc(hd * M * 4) ||
-        w->WT.alloc(nq * d * 4) || w->gp.alloc(M * d * 4) || w->bp.alloc(M * d * 4) || w->loss.alloc(8) || w->Tmp.alloc(M * nq * 4)) return 1;
+        w->WT.alloc(nq * d * 4) || w->gp.alloc(M * d * 4) || w->bp.alloc(M * d * 4) || w->loss.alloc(8) || w->Tmp.alloc(M * nq * 4) || w->temb_b.alloc((size_t)B * d * 4) ||
+        w->iota.alloc((size_t)B * 8)) return 1;
+    tr_iota_kernel<<<(B + 255) / 256, 256>>>(w->iota.as<long long>(), B);
     if (c->Ain.bytes < M * c->kin_pad * 4 && c->Ain.alloc(M * c->kin_pad * 4)) return 1;
     auto G = [&](const std::string& k, size_t n) -> int { return w->grads[k].alloc(n * 4); };
     if (G("start_w", (size_t)d * c->kin_pad) || G("start_b", d) || G("out_w", (size_t)256 * d) || G("out_b", 256) ||
@@ -886,17 +888,17 @@ int egoego_train_step(egoego_handle c, const float* x_start, const float* cond_m
     const long long nel = (long long)B * T * D;
     const float qs = 1.0f / sqrtf((float)dk);
     auto nblk = [](long long n) { return (unsigned)((n + 255) / 256); };
-    TSrc ts{reinterpret_cast<const long long*>(t_dev), nullptr, 0, c->N - 1};
 
-    if (c->temb_dirty) {
-        time_table_kernel<<<c->N, 256, 0, s>>>(c->t_w1.as<float>(), c->t_b1.as<float>(), c->t_w2.as<float>(), c->t_b2.as<float>(), c->temb.as<float>(), d);
-        c->temb_dirty = false;
-    }
+    // the batch's own timestep embeddings from the CURRENT time_mlp weights; the start epilogue indexes them by window (the
+    // sampler's full table stays stale until the next egoego_commit_weights -- training handles never sample)
+    tr_time_fwd_kernel<<<B, 256, 0, s>>>(reinterpret_cast<const long long*>(t_dev), c->t_w1.as<float>(), c->t_b1.as<float>(), c->t_w2.as<float>(),
+                                         c->t_b2.as<float>(), w->temb_b.as<float>(), d);
+    TSrc ts_b{w->iota.as<long long>(), nullptr, 0, B - 1};
     // ---------------- forward ----------------
     EG_CUDA(cudaMemsetAsync(c->Ain.p, 0, (size_t)M * KP * 4, s));
     tr_prep_kernel<<<nblk(nel), 256, 0, s>>>(x_start, cond_mask, noise, cond_noise, sqrt_ac, sqrt_1mac, c->Ain.as<float>(), KP, B, T, D);
     if (tr_gemm(w, c->Ain.as<float>(), KP, c->start_w.as<float>(), KP, M, d, KP,
-                EpiStart{w->Hin[0].as<float>(), d, c->start_b.as<float>(), nullptr, c->pos.as<float>(), c->temb.as<float>(), ts, T}, s)) return 1;
+                EpiStart{w->Hin[0].as<float>(), d, c->start_b.as<float>(), nullptr, c->pos.as<float>(), w->temb_b.as<float>(), ts_b, T}, s)) return 1;
     for (int l = 0; l < c->NL; ++l) {
         LayerW& W = c->layers[l];
         TrainLayerBufs& b = w->L[l];
