@@ -531,8 +531,8 @@ def main():
         line["parity_vs_reference"] = parity_vs_reference(m, dev, N)
     else:
         line["roofline"] = dict(line["path_roofline"], traffic=None, peak_source=pk_src)
-    line["cpu_baseline"] = cpu_baseline(32, T, N, a.cpu_seconds)
-    if world == 1:
+    if world == 1:                                       # reported baseline: rank 0 at N = 1 only
+        line["cpu_baseline"] = cpu_baseline(32, T, N, a.cpu_seconds)
         try:
             line["next_rows"] = next_rows(dev, B, T, pk)
             line["single_window_latency"] = config1_latency(dev, T)

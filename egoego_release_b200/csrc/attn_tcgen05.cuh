@@ -30,12 +30,18 @@ constexpr int ATT_PART_BYTES = 2 * 2 * 128 * 4;          // row max / row sum pa
 constexpr int ATT_SMEM_BYTES = ATT_RING_BYTES + ATT_P_BYTES + ATT_PART_BYTES + 1024 + 256;
 constexpr int ATT_THREADS = 64 + 256;                    // TMA warp, MMA warp, 8 softmax/epilogue warps
 
+// Split format: the probabilities are handed to the tensor core as P * 2^11 (exact scaling), so that the lo plane of a
+// typical p ~ 1/L is a NORMAL fp16 (22 significand bits for p >= 2^-14 instead of an absolute 3e-8); the O epilogue
+// multiplies the accumulator by 2^-11 (exact).  p <= 1 keeps P * 2^11 <= 2048, far inside the fp16 range.
+constexpr float ATT_P_SCALE = 2048.0f;
+
 template <int FMT>
 struct OStore : EpiNoDirect, EpiNoPre {    // attention output rows -> operand planes of the fc GEMM
     __nv_bfloat16* hi; __nv_bfloat16* lo; long long base; int ld;
     __device__ __forceinline__ float4 bias4(int) const { return make_float4(0.f, 0.f, 0.f, 0.f); }
     __device__ __forceinline__ void apply4(int row, int col, float4 a, float4, float4) const {
         const long long o = base + (long long)row * ld + col;
+        if (FMT == FMT_SPLIT) { constexpr float r = 1.0f / ATT_P_SCALE; a.x *= r; a.y *= r; a.z *= r; a.w *= r; }
         store_planes4<FMT>(hi + o, lo + o, a);
     }
 };
@@ -48,8 +54,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_consta
                     __nv_bfloat16* __restrict__ Ohi, __nv_bfloat16* __restrict__ Olo, int ldo,
                     int n_items, int n_head, int L) {
     constexpr int NP = FmtTraits<FMT>::NP;            // FMT_HALF: single fp16 plane per operand, one MMA per k-step
-    constexpr uint32_t IDESC_S = (FMT == FMT_SPLIT) ? ptx::make_idesc_bf16(128, 128) : ptx::make_idesc_f16(128, 128);
-    constexpr uint32_t IDESC_O = ((FMT == FMT_SPLIT) ? ptx::make_idesc_bf16(128, 256) : ptx::make_idesc_f16(128, 256)) | ptx::IDESC_B_MN_MAJOR;
+    static_assert(FMT == FMT_SPLIT || FMT == FMT_HALF, "attention operands are fp16 planes (hi/lo pair or single)");
+    constexpr uint32_t IDESC_S = ptx::make_idesc_f16(128, 128);
+    constexpr uint32_t IDESC_O = ptx::make_idesc_f16(128, 256) | ptx::IDESC_B_MN_MAJOR;
     constexpr uint32_t QK_BYTES = NP * 2 * 16384, V_BYTES = NP * 32768;
     constexpr int ATT_STAGE_BYTES = NP * 32768;            // one k-block of Q+K planes, or of V planes
     constexpr int ATT_STAGES = ATT_RING_BYTES / ATT_STAGE_BYTES;
@@ -209,7 +216,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_consta
             }
             part[256 + hf * 128 + r] = sum;
             asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
-            const float inv = 1.0f / (part[256 + r] + part[256 + 128 + r]);
+            const float inv = ((FMT == FMT_SPLIT) ? ATT_P_SCALE : 1.0f) / (part[256 + r] + part[256 + 128 + r]);
             // P planes -> K-major SW128 smem: key block hf, 16-byte chunk j (keys 8j..8j+7) of row r at chunk j^(r%8)
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -218,8 +225,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_consta
                 for (int q = 0; q < 4; ++q) {
                     if (FMT == FMT_SPLIT) {
                         __nv_bfloat16 h0, l0, h1, l1;
-                        split_bf16(v[8 * j + 2 * q] * inv, h0, l0);
-                        split_bf16(v[8 * j + 2 * q + 1] * inv, h1, l1);
+                        split_f16(v[8 * j + 2 * q] * inv, h0, l0);
+                        split_f16(v[8 * j + 2 * q + 1] * inv, h1, l1);
                         __nv_bfloat162 hh(h0, h1), ll(l0, l1);
                         ph4[q] = *reinterpret_cast<uint32_t*>(&hh); pl4[q] = *reinterpret_cast<uint32_t*>(&ll);
                     } else {

@@ -155,10 +155,23 @@ __device__ __forceinline__ float noise_at(const NoiseSrc& ns, int draw, int w, l
     return r == 0 ? n.x : (r == 1 ? n.y : (r == 2 ? n.z : n.w));
 }
 
-// bf16 hi/lo split of an fp32 value: v ~= hi + lo with |v - hi - lo| <= 2^-17 |v|.
+// bf16 hi/lo split of an fp32 value: v ~= hi + lo with |v - hi - lo| <= 2^-17 |v| over the whole fp32 exponent range
+// (training-step products: gradients are far below the fp16 range).
 __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
     hi = __float2bfloat16_rn(v);
     lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+// fp16 hi/lo split of an fp32 value (sampling path, FMT_SPLIT): hi = fp16(v), lo = fp16(v - hi), both kept as raw 16-bit
+// patterns in the plane storage type.  |v - hi - lo| <= max(2^-23 |v|, 2^-25): 22 significand bits where lo is a normal
+// fp16 (|v| >= 2^-3), an absolute 3e-8 below (lo subnormal) -- 2^6 (activations) to 2^3 (weights ~ 0.03) tighter than the
+// bf16 pair at the same tensor-core cost.  Operands of the sampler are O(1) (the single-plane fp16 format of the early
+// steps relies on the same range), so the fp16 exponent range is not a constraint here.
+__device__ __forceinline__ void split_f16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+    const __half h = __float2half_rn(v);
+    const __half l = __float2half_rn(v - __half2float(h));
+    hi = __ushort_as_bfloat16(__half_as_ushort(h));
+    lo = __ushort_as_bfloat16(__half_as_ushort(l));
 }
 
 }  // namespace egoego

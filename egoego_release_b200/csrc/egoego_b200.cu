@@ -59,7 +59,9 @@ struct egoego_ctx {
     Skeleton sk{}; bool have_sk = false;
     cudaStream_t own_stream = nullptr;
     cudaEvent_t ev_in = nullptr, ev_out = nullptr;
-    cudaGraphExec_t step_graph[2] = {nullptr, nullptr};   // [FMT_SPLIT, FMT_HALF]
+    // one captured step per format: [0] = FMT_SPLIT, [1 + r] = FMT_HALF reading dithered weight set r (engine_tc.cu, upload_weight)
+    static constexpr int MAX_WEIGHT_SETS = 16;
+    cudaGraphExec_t step_graph[1 + MAX_WEIGHT_SETS] = {};
     int graph_B = -1, graph_T = -1; const void* graph_key[4] = {nullptr};
     int precise_last = 0;                  // steps t < precise_last use the 3-term split; earlier steps single-pass fp16
     bool use_graph = true;
@@ -525,37 +527,46 @@ static int sample_chunk(egoego_ctx* c, const float* x_start, const float* cond_m
         return 0;
     };
     auto fmt_of_step = [&](int i) -> int { return (N - 1 - i) >= c->precise_last ? 1 : 0; };   // i-th executed step has t = N-1-i
+    // single-pass fp16 steps cycle through the dithered fp16 weight sets so that the weight rounding averages out over steps
+    const int n_sets = (c->cfg.engine == EGOEGO_ENGINE_TCGEN05 && c->tc) ? std::min(c->tc->n_weight_sets(), (int)egoego_ctx::MAX_WEIGHT_SETS) : 1;
+    auto slot_of_step = [&](int i) -> int { return fmt_of_step(i) ? 1 + (i % n_sets) : 0; };
+    auto select_set = [&](int slot) { if (c->tc) c->tc->use_weight_set(slot > 0 ? slot - 1 : 0); };
     const void* key[4] = {ns.tape, inpaint, (const void*)(uintptr_t)(ns.seed ^ (ns.window_offset * 0x9E3779B97F4A7C15ull)),
                           (const void*)(uintptr_t)(((uint64_t)inpaint_len << 32) ^ (uint64_t)ns.draw_stride)};
     if (c->use_graph) {
         bool reuse = c->graph_B == Bc && c->graph_T == T && !memcmp(key, c->graph_key, sizeof(key));
         if (!reuse) for (auto& g : c->step_graph) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
-        for (int fmt = 0; fmt < 2; ++fmt) {
+        for (int slot = 0; slot < 1 + n_sets; ++slot) {
             bool needed = false;
-            for (int i = 0; i < N && !needed; ++i) needed = fmt_of_step(i) == fmt;
-            if (!needed || c->step_graph[fmt]) continue;
+            for (int i = 0; i < N && !needed; ++i) needed = slot_of_step(i) == slot;
+            if (!needed || c->step_graph[slot]) continue;
             cudaGraph_t g = nullptr;
             int64_t before = c->launches;
+            select_set(slot);                           // tensor maps are kernel arguments: captured by value
             EG_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-            int rc = one_step(s, fmt);
+            int rc = one_step(s, slot ? 1 : 0);
             cudaError_t ce = cudaStreamEndCapture(s, &g);
             c->launches = before;                       // captured, not launched
+            select_set(0);
             EG_CHECK(rc == 0, std::string("capture failed: ") + g_err);
             EG_CUDA(ce);
-            EG_CUDA(cudaGraphInstantiate(&c->step_graph[fmt], g, 0));
+            EG_CUDA(cudaGraphInstantiate(&c->step_graph[slot], g, 0));
             cudaGraphDestroy(g);
         }
         c->graph_B = Bc; c->graph_T = T; memcpy(c->graph_key, key, sizeof(key));
         for (int i = 0; i < N; ++i) {
             const int fmt = fmt_of_step(i);
             if (i > 0 && fmt != fmt_of_step(i - 1) && stage_input(c, xc, D, 0, false, Bc, T, s)) return 1;
-            EG_CUDA(cudaGraphLaunch(c->step_graph[fmt], s));
+            EG_CUDA(cudaGraphLaunch(c->step_graph[slot_of_step(i)], s));
             c->launches += (c->cfg.engine == EGOEGO_ENGINE_SIMT ? (2 + 7 * c->NL) : c->tc->launches_per_denoiser(fmt)) + (fused ? 1 : 2);
         }
     } else {
         for (int i = 0; i < N; ++i) {
             if (i > 0 && fmt_of_step(i) != fmt_of_step(i - 1) && stage_input(c, xc, D, 0, false, Bc, T, s)) return 1;
-            if (one_step(s, fmt_of_step(i))) return 1;
+            select_set(slot_of_step(i));
+            int rc = one_step(s, fmt_of_step(i));
+            select_set(0);
+            if (rc) return 1;
         }
     }
     EG_CUDA(cudaMemcpyAsync(out, xc, (size_t)Bc * T * D * 4, cudaMemcpyDeviceToDevice, s));

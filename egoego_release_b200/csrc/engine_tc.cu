@@ -2,6 +2,7 @@
 // LayerNorm, attention; see gemm_tcgen05.cuh for the GEMM kernel.
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <cmath>
 #include <cstring>
 #include <cstdlib>
 #include <memory>
@@ -42,7 +43,7 @@ static int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t co
     return 0;
 }
 
-struct Plane {                 // a bf16 hi/lo pair with its TMA maps
+struct Plane {                 // a 16-bit hi/lo pair (fp16 in the sampler, bf16 in tc_gemm_f32) with its TMA maps
     __nv_bfloat16 *hi = nullptr, *lo = nullptr;
     CUtensorMap mhi, mlo;
     CUtensorMap mhi128, mlo128;     // 128-row boxes (per-CTA half of a W tile in the 2-CTA GEMM)
@@ -70,27 +71,79 @@ struct Plane {                 // a bf16 hi/lo pair with its TMA maps
         return 0;
     }
     uint32_t box = 128;
-    void release() { if (hi) cudaFree(hi); if (lo) cudaFree(lo); if (own16 && h16) cudaFree(h16); hi = lo = h16 = nullptr; }
+    // Weights only: R fp16 planes, each rounded with its own dither offset (see upload_weight); use_set(r) makes set r the
+    // plane FMT_HALF launches read (the maps are passed to kernels by value, so this is a host-side switch).
+    std::vector<__nv_bfloat16*> set16;
+    std::vector<CUtensorMap> set_m16, set_m16_128;
+    void use_set(int r) {
+        if (set16.empty()) return;
+        r %= (int)set16.size();
+        h16 = set16[r]; m16 = set_m16[r]; m16_128 = set_m16_128[r];
+    }
+    void release() {
+        if (hi) cudaFree(hi); if (lo) cudaFree(lo); if (own16 && h16) cudaFree(h16);
+        for (auto* p : set16) cudaFree(p);
+        set16.clear(); set_m16.clear(); set_m16_128.clear();
+        hi = lo = h16 = nullptr;
+    }
 };
+
+// Number of dithered fp16 weight sets of the single-pass format (EGOEGO_WEIGHT_SETS, default 8; 1 = plain round-to-nearest).
+// Why: in the fp16 steps the ACTIVATION rounding is harmless (fresh, zero-mean every step) but the WEIGHT rounding is the
+// same perturbation of the network at every step, and the sampler integrates it coherently over hundreds of steps
+// (tools/rounding_study.py: weights-only rounding reproduces the whole fp16-step error, activations-only sits on the fp32
+// floor).  Set r rounds W + u_r ulp16(W) to nearest with u_r = (bitrev(r) + 1/2) / R - 1/2; step i of the loop uses set
+// i mod R, so over any R consecutive steps the mean rounded weight is within ulp16 / (2R) of W instead of ulp16 / 2.
+static int weight_sets() {                          // read at every weight commit (not cached: tools compare settings in one process)
+    const char* e = getenv("EGOEGO_WEIGHT_SETS");
+    int v = e ? atoi(e) : 8;
+    if (v < 1) v = 1;
+    if (v > 16) v = 16;
+    return v;
+}
+static float dither_offset(int r, int R) {
+    if (R <= 1) return 0.f;
+    int rev = r;
+    if ((R & (R - 1)) == 0) {                       // power of two: bit-reversed order spreads consecutive steps
+        rev = 0;
+        for (int b = 1, x = r; b < R; b <<= 1, x >>= 1) rev = (rev << 1) | (x & 1);
+    }
+    return ((float)rev + 0.5f) / (float)R - 0.5f;
+}
+static __half dither_round(float v, float u) {
+    if (u == 0.f || v == 0.f) return __float2half_rn(v);
+    int e = 0;
+    (void)frexpf(v, &e);                            // |v| = m 2^e, m in [0.5, 1): fp16 spacing 2^(e-11), 2^-24 once subnormal
+    const int q = e - 11 < -24 ? -24 : e - 11;
+    return __float2half_rn(v + u * ldexpf(1.0f, q));
+}
 
 // Host fp32 [rows, src_ld] (columns [col0, col0+ncols)) -> zero-padded [rows_pad, cols_pad] hi/lo planes.
 static int upload_weight(Plane& p, const float* w, int rows, int src_ld, int col0, int ncols, int rows_pad, int cols_pad, uint32_t box_rows) {
     if (p.alloc(rows_pad, cols_pad, box_rows)) return 1;
-    std::vector<__nv_bfloat16> hi((size_t)rows_pad * cols_pad, __float2bfloat16(0.f)), lo(hi);
+    std::vector<__half> hi((size_t)rows_pad * cols_pad, __float2half(0.f)), lo(hi);      // fp16 hi/lo pair (split_f16)
     for (int r = 0; r < rows; ++r)
         for (int c = 0; c < ncols; ++c) {
             float v = w[(size_t)r * src_ld + col0 + c];
-            __nv_bfloat16 h = __float2bfloat16_rn(v);
+            __half h = __float2half_rn(v);
             hi[(size_t)r * cols_pad + c] = h;
-            lo[(size_t)r * cols_pad + c] = __float2bfloat16_rn(v - __bfloat162float(h));
+            lo[(size_t)r * cols_pad + c] = __float2half_rn(v - __half2float(h));
         }
     EG_CUDA(cudaMemcpy(p.hi, hi.data(), hi.size() * 2, cudaMemcpyHostToDevice));
     EG_CUDA(cudaMemcpy(p.lo, lo.data(), lo.size() * 2, cudaMemcpyHostToDevice));
-    if (p.alloc16()) return 1;
+    const int R = weight_sets();
     std::vector<__half> h16((size_t)rows_pad * cols_pad, __float2half(0.f));
-    for (int r = 0; r < rows; ++r)
-        for (int c = 0; c < ncols; ++c) h16[(size_t)r * cols_pad + c] = __float2half_rn(w[(size_t)r * src_ld + col0 + c]);
-    EG_CUDA(cudaMemcpy(p.h16, h16.data(), h16.size() * 2, cudaMemcpyHostToDevice));
+    p.set16.assign(R, nullptr); p.set_m16.resize(R); p.set_m16_128.resize(R);
+    for (int k = 0; k < R; ++k) {
+        const float u = dither_offset(k, R);
+        for (int r = 0; r < rows; ++r)
+            for (int c = 0; c < ncols; ++c) h16[(size_t)r * cols_pad + c] = dither_round(w[(size_t)r * src_ld + col0 + c], u);
+        EG_CUDA(cudaMalloc(&p.set16[k], h16.size() * 2));
+        EG_CUDA(cudaMemcpy(p.set16[k], h16.data(), h16.size() * 2, cudaMemcpyHostToDevice));
+        if (make_map(&p.set_m16[k], p.set16[k], rows_pad, cols_pad, box_rows) || make_map(&p.set_m16_128[k], p.set16[k], rows_pad, cols_pad, 128)) return 1;
+    }
+    p.own16 = false;
+    p.use_set(0);
     return 0;
 }
 
@@ -133,7 +186,7 @@ static int launch_gemm(TcImpl* I, const Plane& A, const Plane& W, int M, int N, 
     const int tiles = (M / GEMM_BM) * (N / BN);
     const int grid = tiles < I->sms ? tiles : I->sms;
     LaunchCfg lc(grid, GEMM_THREADS, Cfg::SMEM_BYTES, s);
-    if (FMT == FMT_SPLIT) { EG_CUDA(cudaLaunchKernelEx(&lc.cfg, kern, A.mhi, A.mlo, W.mhi, W.mlo, M, N, K, epi)); }
+    if (fmt_is_split(FMT)) { EG_CUDA(cudaLaunchKernelEx(&lc.cfg, kern, A.mhi, A.mlo, W.mhi, W.mlo, M, N, K, epi)); }
     else                  { EG_CUDA(cudaLaunchKernelEx(&lc.cfg, kern, A.m16, A.m16, W.m16, W.m16, M, N, K, epi)); }
     return 0;
 }
@@ -159,7 +212,7 @@ static int launch_gemm_2cta(TcImpl* I, const Plane& A, const Plane& W, int M, in
     int pairs = I->sms / 2;
     if (tiles < pairs) pairs = tiles;
     LaunchCfg lc(2 * pairs, GEMM_THREADS, GEMM2_SMEM_BYTES, s, 2);
-    if (FMT == FMT_SPLIT) { EG_CUDA(cudaLaunchKernelEx(&lc.cfg, kern, A.mhi, A.mlo, W.mhi128, W.mlo128, M, N, K, epi)); }
+    if (fmt_is_split(FMT)) { EG_CUDA(cudaLaunchKernelEx(&lc.cfg, kern, A.mhi, A.mlo, W.mhi128, W.mlo128, M, N, K, epi)); }
     else                  { EG_CUDA(cudaLaunchKernelEx(&lc.cfg, kern, A.m16, A.m16, W.m16_128, W.m16_128, M, N, K, epi)); }
     return 0;
 }
@@ -356,6 +409,14 @@ int TcEngine::prepare_cond(int B, int T, cudaStream_t s, int64_t* n) {
     return 0;
 }
 
+int TcEngine::n_weight_sets() const { return impl_ && !impl_->Wx.set16.empty() ? (int)impl_->Wx.set16.size() : 1; }
+void TcEngine::use_weight_set(int r) {
+    TcImpl* I = impl_;
+    if (!I) return;
+    for (Plane* p : {&I->Wx, &I->Wc, &I->Wout}) p->use_set(r);
+    for (auto& l : I->layers) for (Plane* p : {&l.wqkv, &l.fc, &l.w1, &l.w2}) p->use_set(r);
+}
+
 void TcEngine::stage_targets(__nv_bfloat16** hi, __nv_bfloat16** lo, __half** h16, int* ld) {
     *hi = impl_->X.hi; *lo = impl_->X.lo; *h16 = reinterpret_cast<__half*>(impl_->X.h16); *ld = impl_->kx;
 }
@@ -448,11 +509,11 @@ struct TcEpiOutDdpm : EpiNoDirect, EpiNoPre {
         const long long o = ((long long)w * LP + l) * a.stage_ld16 + col;      // plane columns [D, ld16) stay zero
         if (FMT == FMT_SPLIT) {
             __nv_bfloat16 h0, l0, h1, l1;
-            split_bf16(v[0], h0, l0); split_bf16(v[1], h1, l1);
+            split_f16(v[0], h0, l0); split_f16(v[1], h1, l1);
             *reinterpret_cast<__nv_bfloat162*>(a.stage_hi + o) = __nv_bfloat162(h0, h1);
             *reinterpret_cast<__nv_bfloat162*>(a.stage_lo + o) = __nv_bfloat162(l0, l1);
             if (four) {
-                split_bf16(v[2], h0, l0); split_bf16(v[3], h1, l1);
+                split_f16(v[2], h0, l0); split_f16(v[3], h1, l1);
                 *reinterpret_cast<__nv_bfloat162*>(a.stage_hi + o + 2) = __nv_bfloat162(h0, h1);
                 *reinterpret_cast<__nv_bfloat162*>(a.stage_lo + o + 2) = __nv_bfloat162(l0, l1);
             }
@@ -605,7 +666,7 @@ __global__ void fill_uniform_kernel(float* p, long long n, unsigned long long se
 __global__ void split_rows_kernel(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, long long n) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    split_bf16(src[i], hi[i], lo[i]);
+    split_f16(src[i], hi[i], lo[i]);
 }
 __global__ void to_half_kernel(const float* src, __half* dst, long long n) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -685,7 +746,7 @@ int tc_gemm_f32(const float* A, int lda, const float* W, int ldw, int M, int N, 
     split_pad_kernel<<<(unsigned)(((long long)Mp * Kp / 4 + 255) / 256), 256, 0, s>>>(A, M, K, lda, PA->hi, PA->lo, Mp, Kp);
     split_pad_kernel<<<(unsigned)(((long long)Np * Kp / 4 + 255) / 256), 256, 0, s>>>(W, N, K, ldw, PW->hi, PW->lo, Np, Kp);
     TcEpiPlainAcc e{{}, C, ldc, n_valid, accumulate};
-    return launch_gemm_2cta<FMT_SPLIT>(&g_tcg.I, *PA, *PW, Mp, Np, Kp, e, s);
+    return launch_gemm_2cta<FMT_SPLIT_BF16>(&g_tcg.I, *PA, *PW, Mp, Np, Kp, e, s);
 }
 
 struct EpiStore { float* C; int ldc; __device__ void operator()(int r, int c, float a) const { C[(long long)r * ldc + c] = a; } };

@@ -27,19 +27,22 @@ constexpr int GEMM_EPI_WARPS = 8;                  // two warps per TMEM lane qu
 constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
 
 // Operand format of a GEMM / attention launch:
-//   FMT_SPLIT  bf16 hi/lo planes, three MMAs per k-step (fp32-grade; the default everywhere)
-//   FMT_HALF   one fp16 plane, one MMA per k-step (used only for the early, high-noise diffusion steps whose
-//              error is damped by posterior_mean_coef1 -- see DESIGN.md "Precision policy")
-enum { FMT_SPLIT = 0, FMT_HALF = 1 };
+//   FMT_SPLIT       fp16 hi/lo planes (split_f16), three MMAs per k-step (fp32-grade; the default everywhere)
+//   FMT_HALF        one fp16 plane, one MMA per k-step (used only for the early, high-noise diffusion steps whose
+//                   error is damped by posterior_mean_coef1 -- see DESIGN.md "Precision policy")
+//   FMT_SPLIT_BF16  bf16 hi/lo planes (split_bf16), three MMAs per k-step: the training step's products, whose
+//                   gradients need the fp32 exponent range (tc_gemm_f32); same kernels, bf16 instruction descriptor
+enum { FMT_SPLIT = 0, FMT_HALF = 1, FMT_SPLIT_BF16 = 2 };
+__host__ __device__ constexpr bool fmt_is_split(int fmt) { return fmt != FMT_HALF; }
 template <int FMT> struct FmtTraits {
-    static constexpr int NP = (FMT == FMT_SPLIT) ? 2 : 1;                       // operand planes per matrix
-    static constexpr int MMAS = (FMT == FMT_SPLIT) ? 3 : 1;                     // MMAs per k-step
+    static constexpr int NP = fmt_is_split(FMT) ? 2 : 1;                        // operand planes per matrix
+    static constexpr int MMAS = fmt_is_split(FMT) ? 3 : 1;                      // MMAs per k-step
 };
 
 template <int BN, int FMT> struct GemmCfg {
     static constexpr int NP = FmtTraits<FMT>::NP;
     static constexpr int STAGE_BYTES = NP * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2);   // A planes then W planes
-    static constexpr int STAGES = (FMT == FMT_SPLIT) ? 2 : 4;
+    static constexpr int STAGES = fmt_is_split(FMT) ? 2 : 4;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + GEMM_EPI_WARPS * 4096 /*epilogue tiles*/ + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -143,7 +146,7 @@ __device__ __forceinline__ void store_split8(__nv_bfloat16* hi, __nv_bfloat16* l
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         __nv_bfloat16 h0, l0, h1, l1;
-        split_bf16(v[2 * q], h0, l0); split_bf16(v[2 * q + 1], h1, l1);
+        split_f16(v[2 * q], h0, l0); split_f16(v[2 * q + 1], h1, l1);
         __nv_bfloat162 hh(h0, h1), ll(l0, l1);
         ph[q] = *reinterpret_cast<uint32_t*>(&hh); pl[q] = *reinterpret_cast<uint32_t*>(&ll);
     }
@@ -153,15 +156,17 @@ __device__ __forceinline__ void store_split8(__nv_bfloat16* hi, __nv_bfloat16* l
 
 template <int FMT>
 __device__ __forceinline__ void store_planes8(__nv_bfloat16* hi, __nv_bfloat16* lo, const float* v) {
+    static_assert(FMT != FMT_SPLIT_BF16, "operand planes written by epilogues are fp16 (sampling path)");
     if (FMT == FMT_SPLIT) store_split8(hi, lo, v); else store_half8(hi, v);
 }
 
 // 4 consecutive values -> operand plane(s): 8 bytes per plane
 template <int FMT>
 __device__ __forceinline__ void store_planes4(__nv_bfloat16* hi, __nv_bfloat16* lo, float4 v) {
+    static_assert(FMT != FMT_SPLIT_BF16, "operand planes written by epilogues are fp16 (sampling path)");
     if (FMT == FMT_SPLIT) {
         __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
-        split_bf16(v.x, h0, l0); split_bf16(v.y, h1, l1); split_bf16(v.z, h2, l2); split_bf16(v.w, h3, l3);
+        split_f16(v.x, h0, l0); split_f16(v.y, h1, l1); split_f16(v.z, h2, l2); split_f16(v.w, h3, l3);
         __nv_bfloat162 a0(h0, h1), a1(h2, h3), b0(l0, l1), b1(l2, l3);
         *reinterpret_cast<uint2*>(hi) = make_uint2(*reinterpret_cast<uint32_t*>(&a0), *reinterpret_cast<uint32_t*>(&a1));
         *reinterpret_cast<uint2*>(lo) = make_uint2(*reinterpret_cast<uint32_t*>(&b0), *reinterpret_cast<uint32_t*>(&b1));
@@ -286,7 +291,7 @@ gemm_split3_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constan
     constexpr int STAGES = Cfg::STAGES;
     constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
     constexpr int W_BYTES = BN * GEMM_BK * 2;
-    constexpr uint32_t IDESC = (FMT == FMT_SPLIT) ? ptx::make_idesc_bf16(GEMM_BM, BN) : ptx::make_idesc_f16(GEMM_BM, BN);
+    constexpr uint32_t IDESC = (FMT == FMT_SPLIT_BF16) ? ptx::make_idesc_bf16(GEMM_BM, BN) : ptx::make_idesc_f16(GEMM_BM, BN);
     constexpr int ACC_STAGES = 512 / BN >= 2 ? 2 : 1;
 
     extern __shared__ uint8_t smem_raw[];
@@ -402,7 +407,7 @@ gemm_split3_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constan
 // accumulator through remote arrives on the leader's `tmem_empty` barrier.
 template <int FMT> struct Gemm2Cfg {
     static constexpr int NP = FmtTraits<FMT>::NP;
-    static constexpr int STAGES = (FMT == FMT_SPLIT) ? 3 : 6;
+    static constexpr int STAGES = fmt_is_split(FMT) ? 3 : 6;
     static constexpr int STAGE_BYTES = 2 * NP * GEMM_BM * GEMM_BK * 2;     // A planes + W-half planes, 16 KB each
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + GEMM_EPI_WARPS * 4096 /*epilogue tiles*/ + 1024 + 256;
 };
@@ -417,7 +422,7 @@ gemm_split3_2cta_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_co
     constexpr int GEMM2_STAGES = Gemm2Cfg<FMT>::STAGES;
     constexpr int GEMM2_STAGE_BYTES = Gemm2Cfg<FMT>::STAGE_BYTES;
     constexpr int T_BYTES = GEMM_BM * GEMM_BK * 2;                   // 16 KB tile
-    constexpr uint32_t IDESC = (FMT == FMT_SPLIT) ? ptx::make_idesc_bf16(256, BN) : ptx::make_idesc_f16(256, BN);
+    constexpr uint32_t IDESC = (FMT == FMT_SPLIT_BF16) ? ptx::make_idesc_bf16(256, BN) : ptx::make_idesc_f16(256, BN);
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment for the 128B-swizzle tiles, computed as an OFFSET on the __shared__ array so the compiler keeps
     // the shared address space (integer round-trips turn every access into a generic LD/ST).

@@ -245,8 +245,8 @@ __global__ void __launch_bounds__(256) attention_simt_kernel(const float* __rest
                 const long long o = obase + (long long)(ty * 8 + i) * ldo + q * 64 + tx * 4;
                 if (SPLIT) {
                     __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
-                    split_bf16(acc[i][q * 4 + 0], h0, l0); split_bf16(acc[i][q * 4 + 1], h1, l1);
-                    split_bf16(acc[i][q * 4 + 2], h2, l2); split_bf16(acc[i][q * 4 + 3], h3, l3);
+                    split_f16(acc[i][q * 4 + 0], h0, l0); split_f16(acc[i][q * 4 + 1], h1, l1);
+                    split_f16(acc[i][q * 4 + 2], h2, l2); split_f16(acc[i][q * 4 + 3], h3, l3);
                     __nv_bfloat162 a0(h0, h1), a1(h2, h3), b0(l0, l1), b1(l2, l3);
                     *reinterpret_cast<uint2*>(Ohi + o) = make_uint2(*reinterpret_cast<uint32_t*>(&a0), *reinterpret_cast<uint32_t*>(&a1));
                     *reinterpret_cast<uint2*>(Olo + o) = make_uint2(*reinterpret_cast<uint32_t*>(&b0), *reinterpret_cast<uint32_t*>(&b1));
@@ -310,7 +310,7 @@ static __global__ void __launch_bounds__(256) layernorm512_kernel(const float* _
             reinterpret_cast<uint2*>(Hhi + (long long)row * 512)[lane + 32 * j] = ph;
         } else if (Hhi) {
             __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
-            split_bf16(o.x, h0, l0); split_bf16(o.y, h1, l1); split_bf16(o.z, h2, l2); split_bf16(o.w, h3, l3);
+            split_f16(o.x, h0, l0); split_f16(o.y, h1, l1); split_f16(o.z, h2, l2); split_f16(o.w, h3, l3);
             __nv_bfloat162 hh0(h0, h1), hh1(h2, h3), ll0(l0, l1), ll1(l2, l3);
             uint2 ph, pl;
             ph.x = *reinterpret_cast<uint32_t*>(&hh0); ph.y = *reinterpret_cast<uint32_t*>(&hh1);
@@ -414,7 +414,7 @@ static __global__ void stage_rows_split_kernel(__nv_bfloat16* __restrict__ Ahi, 
     long long ft = gid / ncols;
     int f = (int)(ft % T), w = (int)(ft / T);
     __nv_bfloat16 hi, lo;
-    split_bf16(src[((long long)w * T + f) * src_ld + src_col0 + c], hi, lo);
+    split_f16(src[((long long)w * T + f) * src_ld + src_col0 + c], hi, lo);
     long long o = ((long long)w * LP + 1 + f) * lda + c;
     Ahi[o] = hi; Alo[o] = lo;
     if (A16) A16[o] = __float2half_rn(src[((long long)w * T + f) * src_ld + src_col0 + c]);
@@ -484,7 +484,7 @@ static __global__ void ddpm_update_kernel(DdpmArgs a) {
             const long long o = ((long long)w * LP + 1 + f) * a.stage_ld16 + c;
             if (a.stage_mode != 1) {
                 __nv_bfloat16 h0, l0, h1, l1;
-                split_bf16(v[2 * h], h0, l0); split_bf16(v[2 * h + 1], h1, l1);
+                split_f16(v[2 * h], h0, l0); split_f16(v[2 * h + 1], h1, l1);
                 *reinterpret_cast<__nv_bfloat162*>(a.stage_hi + o) = __nv_bfloat162(h0, h1);
                 *reinterpret_cast<__nv_bfloat162*>(a.stage_lo + o) = __nv_bfloat162(l0, l1);
             }

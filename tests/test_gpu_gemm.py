@@ -1,4 +1,4 @@
-"""tcgen05 3-term bf16-split GEMM primitive against the fp32 CUDA-core GEMM (both on the device, random data),
+"""tcgen05 3-term fp16-split (hi/lo planes) GEMM primitive against the fp32 CUDA-core GEMM (both on the device, random data),
 through the C ABI self-test entry point."""
 import ctypes as C
 
@@ -21,10 +21,10 @@ def test_split_gemm_matches_fp32(M, N, K, two_cta, half_fmt):
     err, ref, ms = C.c_float(), C.c_float(), C.c_float()
     _capi.check(L.egoego_selftest_gemm(0, M, N, K, 42, two_cta, half_fmt, C.byref(err), C.byref(ref), C.byref(ms)))
     tf = 2.0 * M * N * K / (ms.value * 1e-3) / 1e12
-    print(f"{'fp16x1' if half_fmt else 'bf16x3'}-gemm[{2 if two_cta else 1}cta] {M}x{N}x{K}: max|err| {err.value:.3e} (max|ref| {ref.value:.3f}), {ms.value * 1e3:.1f} us, "
+    print(f"{'fp16x1' if half_fmt else 'fp16x3'}-gemm[{2 if two_cta else 1}cta] {M}x{N}x{K}: max|err| {err.value:.3e} (max|ref| {ref.value:.3f}), {ms.value * 1e3:.1f} us, "
           f"{tf:.1f} algorithmic TFLOP/s ({(1 if half_fmt else 3) * tf:.1f} issued)")
     assert ref.value > 0.1
     if half_fmt:   # single fp16 pass: operands rounded to 11 bits
         assert err.value < 2e-3 * ref.value
-    else:          # fp32-grade: the split drops only the lo*lo term (~2^-16 relative per product)
-        assert err.value < 2e-5 * ref.value + 1e-5
+    else:          # fp32-grade: fp16 hi/lo operands (>= 19 bits for these magnitudes), the split drops only the lo*lo term
+        assert err.value < 1e-5 * ref.value + 2e-6     # measured 2.4e-6 (K = 512) .. 6.0e-6 (K = 1024) of max|ref|, incl. the fp32 reference's own rounding

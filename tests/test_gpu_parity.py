@@ -270,6 +270,36 @@ def test_precision_policy_knob(golden_dir, params0):
     assert errs[0] > errs[50]            # the fp16 format alone is NOT fp32-grade: the policy matters
 
 
+def test_full_size_policy_vs_fp32_engines(params0):
+    """BASELINE configs[1] at FULL size and length (B = 256, T = 120, N = 1000, Philox noise): the default precision policy
+    against (a) the same engine with every step in the 3-term split format, all 256 windows, and (b) the independent fp32
+    CUDA-core engine on a 16-window shard (same seed; streams are keyed by the global window id, so the shard is comparable
+    with the same windows of the full batch).  Joint positions within the north-star bar of 1e-3 m for every window."""
+    import egoego_release_b200 as E
+    N, B, SHARD = 1000, 256, 16
+    xs = synth_x_start(31, B, 120).cuda()
+    cm = O.prep_head_condition_mask(xs.shape).cuda()
+
+    def run(engine, K, nw):
+        m = E.CondGaussianDiffusion(d_feats=198, d_model=512, n_dec_layers=4, n_head=4, d_k=256, d_v=256, max_timesteps=121,
+                                    out_dim=198, timesteps=N, objective="pred_x0", max_batch=nw, engine=engine,
+                                    precise_last_steps=K)
+        m.load_state_dict(params0, strict=False)
+        m = m.cuda()
+        torch.manual_seed(4242)
+        return m.sample(xs[:nw], cm[:nw])
+
+    y_def = run("tcgen05", -1, B)
+    y_split = run("tcgen05", N, B)
+    y_simt = run("simt", N, SHARD)
+    assert torch.isfinite(y_def).all() and y_def.abs().max() <= 1.0
+    j_def = joints(y_def)
+    e_split = maxabs(j_def, joints(y_split))
+    e_simt = maxabs(j_def[:SHARD], joints(y_simt))
+    print(f"full size, default policy: vs all-split {e_split * 1e3:.4f} mm (256 windows), vs fp32 simt {e_simt * 1e3:.4f} mm ({SHARD} windows)")
+    assert e_split < JPOS_TOL_M and e_simt < JPOS_TOL_M
+
+
 def test_fused_ln_kernels_agree(params0, monkeypatch):
     """The column-split cluster-of-4 GEMM+LayerNorm kernel (default) against the full-row pair kernel (EGOEGO_LN=2cta) and
     against the unfused GEMM + LayerNorm kernels (EGOEGO_FUSE_LN=0), all-fp16 steps, enough windows that every cluster
