@@ -6,7 +6,7 @@ OUT=gpurun_out
 mkdir -p $OUT
 export TQDM_DISABLE=1
 python -c "import __graft_entry__ as g; g.build()" > $OUT/${TAG}_build.log 2>&1 || { tail -20 $OUT/${TAG}_build.log; exit 1; }
-PARITY_FLOOR_QUICK=1 timeout 100 python tools/parity_floor.py 64 1000:8 63:8 63:1 32:8 125:8 > $OUT/${TAG}_parity_floor.txt 2>&1
+PARITY_FLOOR_QUICK=1 timeout 100 python tools/parity_floor.py 64 63:8 63:1 63:16 32:8 125:8 > $OUT/${TAG}_parity_floor.txt 2>&1
 echo "parity_floor rc=$? t=$SECONDS"; grep tcgen05 $OUT/${TAG}_parity_floor.txt | cut -c1-200
 timeout 170 python -m pytest tests -m gpu -q -s > $OUT/${TAG}_tests_full.log 2>&1
 echo "tests rc=$? t=$SECONDS"; tail -4 $OUT/${TAG}_tests_full.log > $OUT/${TAG}_tests.log; cat $OUT/${TAG}_tests.log
