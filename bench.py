@@ -169,7 +169,7 @@ def denoiser_latency(m, dev, T, iters=20):
         e1.record()
         torch.cuda.synchronize()
         out[f"B{B}"] = e0.elapsed_time(e1) / iters * 1e3
-    out["note"] = "per call incl. staging of x/x_cond (egoego_denoiser_forward, bf16x3-split), CUDA events, eager launches"
+    out["note"] = "per call incl. staging of x/x_cond (egoego_denoiser_forward, fp16 hi/lo 3-term split), CUDA events, eager launches"
     return out
 
 
@@ -381,7 +381,7 @@ def main():
     cfg = {"workload": f"configs[1]: batch={B}/GPU T={T} {N}-step sampling, random-init denoiser (oracle.init_params seed 0), "
                        "synthetic head-pose cond", "windows_per_gpu": B, "T": T, "diffusion_steps": N, "d_feats": D,
            "parallelism": f"windows sharded over {world} GPU(s), one all-gather of finished windows" if world > 1 else "single GPU",
-           "l2": "per-step working set (bf16/fp32 activation planes for 256 windows, >1 GB) exceeds the 126 MB L2; no flush"}
+           "l2": "per-step working set (fp16/fp32 activation planes for 256 windows, >1 GB) exceeds the 126 MB L2; no flush"}
 
     if a.impl == "reference":
         if rank != 0:
@@ -470,15 +470,17 @@ def main():
     e2e = world * B / (ms_h / a.steps / 1e3)
     path_tflops = value / world * N * FLOP_PER_WINDOW_CALL / 1e12          # per GPU
     peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+    W_sets = 1
     if eng == "tcgen05":
         K_prec = m.precise_last_steps()
+        W_sets = m.weight_sets()
     line = {
         "metric": "motion-windows/sec (T=120, 1000-step)", "value": value, "unit": "windows/s", "n_gpus": world,
         "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None,
-        "dtype": (f"fp16 single-pass for t>={K_prec}, bf16x3-split for t<{K_prec} (fp32 accumulate)" if K_prec < N else
-                  "bf16x3-split (fp32 accumulate)") if eng == "tcgen05" else "f32",
-        "data": "synthetic", "config": dict(cfg, engine=eng, precise_last_steps=K_prec),
+        "dtype": (f"fp16 single-pass (dithered weight sets x{W_sets}) for t>={K_prec}, fp16 hi/lo 3-term split for t<{K_prec} (fp32 accumulate)"
+                  if K_prec < N else "fp16 hi/lo 3-term split (fp32 accumulate)") if eng == "tcgen05" else "f32",
+        "data": "synthetic", "config": dict(cfg, engine=eng, precise_last_steps=K_prec, weight_sets=W_sets),
         "e2e": {"value": e2e, "unit": "windows/s", "h2d_bytes_per_step": 2 * B * T * D * 4 * world, "d2h_bytes_per_step": B * T * D * 4 * world},
         "gpu_launches": int(launches), "clocks": clocks,
         "path_roofline": {"bound": "tensor", "achieved": path_tflops, "peak": peak, "unit": "TFLOP/s", "frac": path_tflops / peak,
@@ -487,7 +489,7 @@ def main():
     if eng == "tcgen05":
         # every kernel of the step timed live, in isolation (20 back-to-back launches, CUDA events on the launch stream),
         # in the format of the steps that take most of the time; the DOMINANT kernel = largest launches x time share
-        dom_fmt = "fp16_single" if K_prec < N else "bf16x3_split"
+        dom_fmt = "fp16_single" if K_prec < N else "fp16x3_split"
         half = dom_fmt == "fp16_single"
         pk_burst, hbm = pk["bf16_tflops"], pk["hbm_gbs"]
         kernels = {}

@@ -751,6 +751,7 @@ int egoego_time_dominant_kernel(egoego_handle c, int B, int half_fmt, int iters,
 }
 
 int egoego_precise_last_steps(egoego_handle c) { return c ? c->precise_last : -1; }
+int egoego_weight_sets(egoego_handle c) { return (c && c->cfg.engine == EGOEGO_ENGINE_TCGEN05 && c->tc) ? c->tc->n_weight_sets() : 1; }
 
 int egoego_launches_per_step(egoego_handle c, int which) {
     if (!c || which < 0 || which > EGOEGO_KERNEL_DDPM_UPDATE) return -1;

@@ -266,6 +266,10 @@ class CondGaussianDiffusion(nn.Module):
         """Resolved precision policy of the engine: diffusion steps t < K use the 3-term split."""
         return int(_capi.lib().egoego_precise_last_steps(self._handle()))
 
+    def weight_sets(self) -> int:
+        """Number of dithered fp16 weight sets the single-pass steps cycle through (EGOEGO_WEIGHT_SETS, default 8)."""
+        return int(_capi.lib().egoego_weight_sets(self._handle()))
+
     def time_dominant_kernel(self, B: int, half_fmt: bool, iters: int = 20) -> float:
         """ms per launch of the fused QKV projection kernel (CUDA events on the current stream)."""
         h = self._handle()

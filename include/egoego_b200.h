@@ -283,6 +283,11 @@ int  egoego_time_dominant_kernel(egoego_handle h, int B, int half_fmt, int iters
 int  egoego_launches_per_step(egoego_handle h, int which);
 /* Resolved precision policy: steps t < K run the 3-term split (see egoego_cfg.precise_last_steps). */
 int  egoego_precise_last_steps(egoego_handle h);
+/* Number R of dithered fp16 weight sets the single-pass steps cycle through (env EGOEGO_WEIGHT_SETS at weight commit,
+ * default 8, 1 = plain round-to-nearest; always 1 for the fp32 engine).  Step i of the loop reads set i mod R, so the fp16
+ * rounding of the weights -- the only rounding of those steps that survives to the final sample -- averages out over steps
+ * (DESIGN.md 4). */
+int  egoego_weight_sets(egoego_handle h);
 
 /* Self test of the tensor-core GEMM primitive: C = A W^T (A[M,K], W[N,K] random fp32) computed by the
  * tcgen05 3-term bf16-split kernel and by the fp32 CUDA-core kernel; reports max |difference|, max |reference|
