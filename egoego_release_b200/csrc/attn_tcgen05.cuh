@@ -1,10 +1,10 @@
 // Fused self-attention of one (window, head) on the tensor cores: S = Q K^T, row softmax over the first L
 // keys, O = P V -- S and P never leave the SM.
 //
-// Every product uses the same 3-term bf16 hi/lo split as the GEMMs (fp32-grade results):
+// Every product uses the same 3-term fp16 hi/lo split as the GEMMs (fp32-grade results):
 //   S = Qh Kh^T + Qh Kl^T + Ql Kh^T           (UMMA 128x128x16, K = d_k = 256)
 //   O = Ph Vh   + Ph Vl   + Pl Vh             (UMMA 128x256x16, K = 128 keys)
-// Operand planes (written by the QKV projection epilogue, bf16, K-major):
+// Operand planes (written by the QKV projection epilogue, fp16 hi/lo, K-major):
 //   Q, K, V : [(window*H + head)*128 + token, 256]   (Q pre-scaled by 1/sqrt(d_k))
 // V keeps the projection's natural [key][dim] layout: in O = P V it is the MN-major B operand of the UMMA (N = dim is the
 // contiguous index), so the QKV epilogue writes all three sections the same coalesced way and no transposed copy exists.

@@ -102,7 +102,7 @@ struct DdpmArgs {
     float* stage_f32; int stage_ld;                                  // SIMT engine A operand (nullable)
     __nv_bfloat16* stage_hi; __nv_bfloat16* stage_lo; int stage_ld16; // tensor engine A operand (nullable)
     __half* stage_h16;                                                // fp16 plane for FMT_HALF steps (nullable)
-    int stage_mode;          // tensor engine planes to write: 0 = bf16 hi/lo only, 1 = fp16 only, 2 = all (next step's format unknown)
+    int stage_mode;          // tensor engine planes to write: 0 = fp16 hi/lo pair only, 1 = single fp16 plane only, 2 = all (next step's format unknown)
     TSrc ts; NoiseSrc ns;
     int B, T, D;
 };

@@ -222,7 +222,7 @@ int egoego_create(const egoego_cfg* cfg, egoego_handle* out) {
     { const char* fd = getenv("EGOEGO_FUSE_DDPM"); c->fuse_ddpm = fd && fd[0] == '1'; }
     const char* g = getenv("EGOEGO_GRAPH");
     c->use_graph = !(g && g[0] == '0');
-    // precision policy: the last `precise_last` steps (t < precise_last) run the 3-term bf16 split,
+    // precision policy: the last `precise_last` steps (t < precise_last) run the 3-term fp16 hi/lo split,
     // earlier steps a single fp16 pass.  cfg.precise_last_steps < 0 selects the default max(ceil(N/16), 48); N = all precise.
     {
         int pl = cfg->precise_last_steps;

@@ -1,4 +1,4 @@
-// Tensor-core engine: tcgen05/TMA split-bf16 GEMMs for every projection of the denoiser, warp-level
+// Tensor-core engine: tcgen05/TMA 3-term split GEMMs (fp16 hi/lo planes) for every projection of the denoiser, warp-level
 // LayerNorm, attention; see gemm_tcgen05.cuh for the GEMM kernel.
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -28,7 +28,7 @@ static PFN_encodeTiled get_encode() {
     return fn;
 }
 
-// 2D bf16 row-major [rows, cols] tensor, box = [box_rows, 64 cols], 128-byte swizzle.
+// 2D 16-bit (fp16 / bf16: the copy engine does not care) row-major [rows, cols] tensor, box = [box_rows, 64 cols], 128-byte swizzle.
 static int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
     PFN_encodeTiled enc = get_encode();
     EG_CHECK(enc, "cuTensorMapEncodeTiled entry point not available");

@@ -1,5 +1,5 @@
 // Tensor-core engine (EGOEGO_ENGINE_TCGEN05): interface used by egoego_b200.cu.
-// Implementation: engine_tc.cu (tcgen05 + TMA GEMMs with a 3-term bf16 hi/lo split).
+// Implementation: engine_tc.cu (tcgen05 + TMA GEMMs with a 3-term fp16 hi/lo split).
 #pragma once
 #include <vector>
 #include <cuda_fp16.h>
@@ -32,7 +32,7 @@ public:
     int init(const TcWeights& w, cudaStream_t s);
     // zero the padded A-operand planes for B windows
     int clear_staging(int B, cudaStream_t s);
-    // scatter compact rows into the bf16 hi/lo A-operand planes (x half or x_cond half)
+    // scatter compact rows into the fp16 hi/lo A-operand planes (x half or x_cond half)
     int stage(const float* src, int src_ld, int src_col0, bool cond_half, int B, int T, cudaStream_t s, int64_t* n);
     // base[M, d] = x_cond-half of start_conv + bias + positional rows (constant over the loop)
     int prepare_cond(int B, int T, cudaStream_t s, int64_t* n);

@@ -1,10 +1,11 @@
 // Split-precision GEMM on the 5th-generation tensor cores.
 //
-//   D[M,N] = A[M,K] * W[N,K]^T   with   A = A_hi + A_lo,  W = W_hi + W_lo  (bf16 planes, K-major)
+//   D[M,N] = A[M,K] * W[N,K]^T   with   A = A_hi + A_lo,  W = W_hi + W_lo  (fp16 planes in the sampler, bf16 in the training step; K-major)
 //   D ~= A_hi W_hi^T + A_hi W_lo^T + A_lo W_hi^T     (three tcgen05.mma per k-step, one fp32 accumulator)
 //
-// which reproduces fp32 GEMM results to ~2^-16 relative (single-pass bf16/fp16/tf32
-// miss the 1e-3 m parity bar; the 3-term split meets it with 8x margin).  The four operand planes of a
+// which reproduces fp32 GEMM results to ~3e-6 of max|D| with fp16 planes (bounded by the tensor core's own fp32
+// accumulation; ~2^-16 relative with bf16 planes).  SURVEY.md 0.5 / 8d: single-pass bf16/fp16/tf32 on every step
+// miss the 1e-3 m parity bar; the 3-term split meets it with 30x margin on the 1000-step golden.  The four operand planes of a
 // k-block share one pipeline stage, so the split moves 4 tiles per 3 MMAs (better bytes/FLOP than a plain
 // bf16 GEMM).
 //

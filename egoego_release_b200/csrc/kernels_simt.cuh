@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(256) attention_simt_kernel(const float* __rest
 // ---------------------------------------------------------------------------------------------
 // LayerNorm over d_model = 512 (eps 1e-5, biased variance), one warp per row, float4 loads.
 // Optional row mask (padding_mask, [B, T+1]) multiplies the normalised row (DecoderLayer :135,139).
-// Optionally also emits the bf16 hi/lo planes consumed by the tensor-core engine.
+// Optionally also emits the fp16 hi/lo planes consumed by the tensor-core engine.
 // ---------------------------------------------------------------------------------------------
 static __global__ void __launch_bounds__(256) layernorm512_kernel(const float* __restrict__ Y, float* __restrict__ H,
                                                            __nv_bfloat16* __restrict__ Hhi,
@@ -402,7 +402,7 @@ static __global__ void stage_rows_f32_kernel(float* __restrict__ Ain, int lda, i
     Ain[((long long)w * LP + 1 + f) * lda + col0 + c] = src[((long long)w * T + f) * src_ld + src_col0 + c];
 }
 
-// Same, into bf16 hi/lo planes (tensor-core engine A operand).
+// Same, into fp16 hi/lo planes (tensor-core engine A operand).
 static __global__ void stage_rows_split_kernel(__nv_bfloat16* __restrict__ Ahi, __nv_bfloat16* __restrict__ Alo,
                                         __half* __restrict__ A16 /* nullable: extra fp16 plane */, int lda,
                                         const float* __restrict__ src, int src_ld, int src_col0, int ncols,

@@ -55,13 +55,13 @@ typedef struct egoego_cfg {
     int32_t device;        /* CUDA ordinal                                             */
     int32_t engine;        /* EGOEGO_ENGINE_*                                          */
     int32_t precise_last_steps; /* tensor engine precision policy: the last K diffusion steps (t < K) use the
-                              3-term bf16 split (fp32-grade); earlier steps one fp16 pass, whose error is damped
-                              by posterior_mean_coef1[t].  -1 = default max(ceil(timesteps/16), 48); timesteps = all steps
+                              3-term fp16 hi/lo split (fp32-grade); earlier steps one fp16 pass over dithered weight
+                              copies (egoego_weight_sets), whose error is damped by posterior_mean_coef1[t].  -1 = default max(ceil(timesteps/16), 48); timesteps = all steps
                               split.  The per-call entry points (denoiser_forward, p_sample_step) always split. */
 } egoego_cfg;
 
 enum {
-    EGOEGO_ENGINE_TCGEN05 = 0, /* tcgen05/TMA GEMMs, 3-term bf16 hi/lo split, fp32 accumulate (default) */
+    EGOEGO_ENGINE_TCGEN05 = 0, /* tcgen05/TMA GEMMs, 3-term fp16 hi/lo split, fp32 accumulate (default) */
     EGOEGO_ENGINE_SIMT    = 1  /* fp32 CUDA-core GEMMs: validation / bisecting engine               */
 };
 
@@ -93,7 +93,7 @@ int  egoego_set_tensor(egoego_handle h, const char* name, const float* data, int
 /* Computes the schedule buffers from cfg.timesteps (cosine schedule, fp64 then cast), for callers
  * without the reference's registered buffers. */
 int  egoego_make_cosine_schedule(egoego_handle h);
-/* Packs weights for the engine (fused QKV, bf16 hi/lo planes, timestep-embedding table, TMA maps).
+/* Packs weights for the engine (fused QKV, fp16 hi/lo planes + dithered fp16 copies, timestep-embedding table, TMA maps).
  * Must be called after the last set_tensor and before any compute call. */
 int  egoego_commit_weights(egoego_handle h, void* stream);
 
@@ -262,7 +262,7 @@ int64_t egoego_launch_count(egoego_handle h);
  * sampling step -- `which` = EGOEGO_KERNEL_* (layer 0's weights) -- over `iters` back-to-back launches on `stream`,
  * timed with CUDA events on that stream.  Operates in place on the handle's own workspace for B windows of T frames
  * (run a sampling call first so the workspace holds finite activations).  half_fmt selects the operand format
- * (0 = 3-term bf16 split, 1 = single-pass fp16; for FC_LN / W2_LN the fp16 format is the fused GEMM+LayerNorm kernel,
+ * (0 = 3-term fp16 hi/lo split, 1 = single-pass fp16; for FC_LN / W2_LN the fp16 format is the fused GEMM+LayerNorm kernel,
  * the split format times the GEMM and the LayerNorm kernel together). */
 enum {
     EGOEGO_KERNEL_START = 0,      /* x-half of start_conv + base/time token                        */
@@ -290,7 +290,7 @@ int  egoego_precise_last_steps(egoego_handle h);
 int  egoego_weight_sets(egoego_handle h);
 
 /* Self test of the tensor-core GEMM primitive: C = A W^T (A[M,K], W[N,K] random fp32) computed by the
- * tcgen05 3-term bf16-split kernel and by the fp32 CUDA-core kernel; reports max |difference|, max |reference|
+ * tcgen05 3-term fp16 hi/lo split kernel and by the fp32 CUDA-core kernel; reports max |difference|, max |reference|
  * and the average device time of one tcgen05 launch in milliseconds.  M%128 == N%256 == K%64 == 0.
  * two_cta != 0 selects the CTA-pair kernel (cta_group::2, 256x256 tiles; needs M%256 == 0); half_fmt != 0 the
  * single-pass fp16 operand format (errors are then fp16-grade, ~1e-3 relative). */
