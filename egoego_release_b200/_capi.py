@@ -11,7 +11,7 @@ EXPORTS = [
     "egoego_make_cosine_schedule", "egoego_commit_weights", "egoego_denoiser_forward", "egoego_p_sample_step",
     "egoego_sample", "egoego_sample_host", "egoego_set_skeleton", "egoego_postprocess", "egoego_fk_smpl",
     "egoego_canonicalize_head", "egoego_tail_condition", "egoego_launch_count", "egoego_selftest_gemm", "egoego_time_dominant_kernel", "egoego_time_kernel",
-    "egoego_precise_last_steps", "egoego_weight_sets", "egoego_eval_metrics", "egoego_launches_per_step",
+    "egoego_precise_last_steps", "egoego_weight_sets", "egoego_dither_weights_f16", "egoego_eval_metrics", "egoego_launches_per_step",
     "egoego_seqnet_create", "egoego_seqnet_destroy", "egoego_seqnet_set_tensor", "egoego_seqnet_commit", "egoego_seqnet_forward",
     "egoego_seqnet_launch_count", "egoego_va2rot", "egoego_rescale_slam", "egoego_slam_features", "egoego_apply_floor_normal",
     "egoego_rigid_apply", "egoego_resnet18_create", "egoego_resnet18_destroy", "egoego_resnet18_set_tensor", "egoego_resnet18_commit",
@@ -75,6 +75,7 @@ def lib():
     L.egoego_time_kernel.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp]
     L.egoego_precise_last_steps.argtypes = [vp]
     L.egoego_weight_sets.argtypes = [vp]
+    L.egoego_dither_weights_f16.argtypes = [vp, C.c_int64, i32, i32, vp]
     L.egoego_launches_per_step.argtypes = [vp, i32]
     L.egoego_tail_condition.argtypes = [vp, vp, vp, i32, i32, vp, vp]
     L.egoego_eval_metrics.argtypes = [i32, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp]

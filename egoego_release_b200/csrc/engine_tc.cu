@@ -118,6 +118,14 @@ static __half dither_round(float v, float u) {
     return __float2half_rn(v + u * ldexpf(1.0f, q));
 }
 
+void dither_weights_host(const float* w, long long n, int r, int R, unsigned short* out) {
+    const float u = dither_offset(r, R);
+    for (long long i = 0; i < n; ++i) {
+        const __half h = dither_round(w[i], u);
+        memcpy(&out[i], &h, 2);
+    }
+}
+
 // Host fp32 [rows, src_ld] (columns [col0, col0+ncols)) -> zero-padded [rows_pad, cols_pad] hi/lo planes.
 static int upload_weight(Plane& p, const float* w, int rows, int src_ld, int col0, int ncols, int rows_pad, int cols_pad, uint32_t box_rows) {
     if (p.alloc(rows_pad, cols_pad, box_rows)) return 1;

@@ -56,6 +56,9 @@ private:
 int tc_gemm_f32(const float* A, int lda, const float* W, int ldw, int M, int N, int K, float* C, int ldc, int n_valid, int accumulate,
                 cudaStream_t s);
 
+// Host-side rounding of fp32 weights to the r-th of R dithered fp16 copies (bit patterns), exactly as the weight commit does.
+void dither_weights_host(const float* w, long long n, int r, int R, unsigned short* out);
+
 // tcgen05 split GEMM vs fp32 SIMT GEMM on random data (C = A W^T, no epilogue); returns max |err|, max |ref|, ms/launch.
 int selftest_gemm(int M, int N, int K, unsigned long long seed, int two_cta, int half_fmt, float* max_abs_err, float* max_abs_ref, float* ms);
 

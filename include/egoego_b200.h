@@ -288,6 +288,9 @@ int  egoego_precise_last_steps(egoego_handle h);
  * rounding of the weights -- the only rounding of those steps that survives to the final sample -- averages out over steps
  * (DESIGN.md 4). */
 int  egoego_weight_sets(egoego_handle h);
+/* Host-only helper (no GPU needed): the fp16 bit patterns of copy `set` of `n_sets` for n fp32 weights, exactly as
+ * egoego_commit_weights rounds them: RN_fp16(w + u ulp16(w)), u = (bitrev(set) + 1/2) / n_sets - 1/2 (u = 0 for n_sets = 1). */
+int  egoego_dither_weights_f16(const float* w, int64_t n, int set, int n_sets, uint16_t* out);
 
 /* Self test of the tensor-core GEMM primitive: C = A W^T (A[M,K], W[N,K] random fp32) computed by the
  * tcgen05 3-term fp16 hi/lo split kernel and by the fp32 CUDA-core kernel; reports max |difference|, max |reference|

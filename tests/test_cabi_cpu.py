@@ -89,3 +89,34 @@ def test_mirror_survives_deepcopy_and_pickle():
     for c in (copy.deepcopy(m), pickle.loads(pickle.dumps(m))):
         assert c.denoise_fn._owner() is c and c._h is None
         assert set(c.state_dict()) == set(m.state_dict())
+
+
+def test_dithered_weight_sets_host_rounding(lib):
+    """The host rounding behind the dithered fp16 weight copies (engine_tc.cu: dither_round / dither_offset):
+    one set = plain round-to-nearest; every copy stays within one fp16 ulp of the weight; the MEAN over the R copies is
+    ~8x (R = 8) closer to the fp32 weight than plain rounding -- the property the sampler relies on to average the weight
+    rounding out over steps."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    w = ((rng.random(50000, dtype=np.float32) * 2 - 1) * np.float32(0.0442)).astype(np.float32)
+    w[:4] = [0.0, 0.75, -0.375, 6.0e-6]                                  # fp16-exact values (not at a binade edge) and a subnormal-range weight
+
+    def copy(r, R):
+        out = np.zeros(w.size, np.uint16)
+        rc = lib.egoego_dither_weights_f16(w.ctypes.data_as(C.c_void_p), w.size, r, R, out.ctypes.data_as(C.c_void_p))
+        assert rc == 0
+        return out.view(np.float16).astype(np.float32)
+
+    plain = w.astype(np.float16).astype(np.float32)
+    assert np.array_equal(copy(0, 1), plain)
+    _, e = np.frexp(w)
+    ulp = np.ldexp(np.float32(1), np.maximum(e - 11, -24)).astype(np.float32)
+    R = 8
+    sets = [copy(r, R) for r in range(R)]
+    assert len({s.tobytes() for s in sets}) == R                          # the copies differ
+    for s in sets:
+        assert np.all(np.abs(s - w) <= ulp * 1.0001)
+        assert np.array_equal(s[:3], w[:3])                               # fp16-exact weights inside a binade are never moved
+    rms = lambda x: float(np.sqrt(np.mean(((x - w) / ulp) ** 2)))
+    assert rms(plain) > 0.25 and rms(np.mean(sets, 0)) < 0.05             # 0.29 ulp -> 0.036 ulp
+    assert lib.egoego_dither_weights_f16(w.ctypes.data_as(C.c_void_p), w.size, 8, 8, None) != 0
