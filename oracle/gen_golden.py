@@ -153,6 +153,18 @@ def gen_sliding_edge(M, params, out):
     np.savez(os.path.join(out, "sliding_window_edge.npz"), **res)
 
 
+def gen_sample_extra(M, params, out):
+    """(ix) a second full-length golden: sample() of the unmodified reference at N = 1000 on FOUR windows with their own
+    conditioning and noise (seed 23) -- the 1000-step parity claim does not rest on a single window."""
+    N, B, seed = 1000, 4, 23
+    m = build_model(M, params, N)
+    xs = synth_x_start(2100, B, 120)
+    cm = O.prep_head_condition_mask(xs.shape)
+    with Tape(seed):
+        y = m.sample(xs, cm)
+    np.savez(os.path.join(out, "sample_extra.npz"), **{f"n{N}_b{B}_seed{seed}": y.numpy()})
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     M = import_reference()
@@ -160,6 +172,10 @@ def main():
     os.makedirs(out, exist_ok=True)
     params = O.init_params(seed=0)
     ds = O.MotionDataStub()
+    if "--only-sample-extra" in sys.argv:
+        gen_sample_extra(M, params, out)
+        print("wrote sample_extra.npz")
+        return
     if "--only-sliding-edge" in sys.argv:
         gen_sliding_edge(M, params, out)
         return
@@ -240,6 +256,7 @@ def main():
     np.savez(os.path.join(out, "sliding_window.npz"), aa=aa.numpy(), root=root.numpy())
     gen_pred_noise(M, params, out)
     gen_sliding_edge(M, params, out)
+    gen_sample_extra(M, params, out)
     print("goldens written:", sorted(os.listdir(out)))
 
 

@@ -101,6 +101,24 @@ def test_sample_1000_steps_vs_golden(engine, golden_dir, params0):
 
 
 @pytest.mark.parametrize("engine", ENGINES)
+def test_sample_1000_steps_four_windows_vs_golden(engine, golden_dir, params0):
+    """Second full-length golden of the unmodified reference: four windows, own conditioning and noise (seed 23)."""
+    g = _g(golden_dir, "sample_extra.npz")
+    N, B, seed = 1000, 4, 23
+    m = make_model(N, engine, params0)
+    xs = synth_x_start(2100, B, 120)
+    cm = O.prep_head_condition_mask(xs.shape)
+    tp = Tape(seed)
+    tape = torch.stack([tp.draw(xs.shape) for _ in range(N + 2)])
+    m.set_noise_tape(tape.cuda())
+    y = m.sample(xs.cuda(), cm.cuda())
+    ref = torch.from_numpy(g[f"n{N}_b{B}_seed{seed}"])
+    jerr = maxabs(joints(y), joints(ref))
+    print(f"[{engine}] sample N=1000 B=4: raw max-abs {maxabs(y, ref):.3e}, joint max-abs {jerr * 1e3:.4f} mm")
+    assert jerr < JPOS_TOL_M
+
+
+@pytest.mark.parametrize("engine", ENGINES)
 def test_pred_noise_objective_vs_golden(engine, golden_dir, params0):
     """objective='pred_noise' (the reference constructor's default, :233-236): x0 = sqrt(1/abar) x - sqrt(1/abar - 1) eps."""
     import egoego_release_b200 as E
