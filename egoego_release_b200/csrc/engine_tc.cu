@@ -179,16 +179,28 @@ struct TcImpl {
     }
 };
 
+// First use of a kernel on each device of the process (one process per GPU is the deployment, but egoego_cfg.device allows more).
+struct PerDeviceOnce {
+    bool done[64] = {};
+    bool need() {
+        int d = 0;
+        if (cudaGetDevice(&d) != cudaSuccess) return true;
+        d &= 63;
+        if (done[d]) return false;
+        done[d] = true;
+        return true;
+    }
+};
+
 static inline int Mr(int B) { return ((B + 1) / 2) * 2 * LP; }
 
 template <int BN, int FMT, class Epi>
 static int launch_gemm(TcImpl* I, const Plane& A, const Plane& W, int M, int N, int K, const Epi& epi, cudaStream_t s) {
     using Cfg = GemmCfg<BN, FMT>;
-    static bool attr_set = false;
+    static PerDeviceOnce attr_once;          // opt-in shared-memory size is a per-device function attribute
     auto kern = gemm_split3_kernel<BN, FMT, Epi>;
-    if (!attr_set) {
+    if (attr_once.need()) {
         EG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr_set = true;
     }
     EG_CHECK(M % GEMM_BM == 0 && N % BN == 0 && K % GEMM_BK == 0, "gemm shape not tile-aligned");
     const int tiles = (M / GEMM_BM) * (N / BN);
@@ -208,12 +220,11 @@ static bool use_2cta() {
 // 2-CTA (cluster of 2, cta_group::2) launch: 256 x 256 tiles per CTA pair.
 template <int FMT, class Epi>
 static int launch_gemm_2cta(TcImpl* I, const Plane& A, const Plane& W, int M, int N, int K, const Epi& epi, cudaStream_t s) {
-    static bool attr_set = false;
+    static PerDeviceOnce attr_once;          // opt-in shared-memory size is a per-device function attribute
     auto kern = gemm_split3_2cta_kernel<FMT, Epi>;
     constexpr int GEMM2_SMEM_BYTES = Gemm2Cfg<FMT>::SMEM_BYTES;
-    if (!attr_set) {
+    if (attr_once.need()) {
         EG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_BYTES));
-        attr_set = true;
     }
     EG_CHECK(M % 256 == 0 && N % 256 == 0 && K % GEMM_BK == 0, "2-CTA gemm shape not tile-aligned");
     const int tiles = (M / 256) * (N / 256);
@@ -230,11 +241,10 @@ template <class Epi>
 static int launch_gemm_ares(TcImpl* I, const Plane& A, const Plane& W, int M, int N, const Epi& epi, cudaStream_t s) {
     constexpr int G = 3;
     using Cfg = GemmAresCfg<G>;
-    static bool attr_set = false;
+    static PerDeviceOnce attr_once;          // opt-in shared-memory size is a per-device function attribute
     auto kern = gemm_ares_half_2cta_kernel<G, Epi>;
-    if (!attr_set) {
+    if (attr_once.need()) {
         EG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr_set = true;
     }
     EG_CHECK(M % 256 == 0 && (N / 256) % G == 0 && N % 256 == 0, "A-resident gemm shape not tile-aligned");
     const int items = (M / 256) * ((N / 256) / G);
@@ -254,11 +264,10 @@ static bool use_tma_epi() {
 }
 template <class Epi>
 static int launch_gemm_tma_epi(TcImpl* I, const Plane& A, const Plane& W, int M, int N, int K, const float* bias, const Epi& epi, cudaStream_t s) {
-    static bool attr_set = false;
+    static PerDeviceOnce attr_once;          // opt-in shared-memory size is a per-device function attribute
     auto kern = gemm_half_tma_2cta_kernel<Epi>;
-    if (!attr_set) {
+    if (attr_once.need()) {
         EG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmTmaEpiCfg::SMEM_BYTES));
-        attr_set = true;
     }
     EG_CHECK(M % 256 == 0 && N % 256 == 0 && K % GEMM_BK == 0 && N <= GemmTmaEpiCfg::MAX_N, "TMA-epilogue gemm shape not supported");
     const int tiles = (M / 256) * (N / 256);
@@ -276,11 +285,10 @@ template <class Epi>
 static int launch_gemm_ares_tma(TcImpl* I, const Plane& A, const Plane& W, int M, int N, const float* bias, const Epi& epi, cudaStream_t s) {
     constexpr int G = 3;
     using Cfg = GemmAresTmaCfg<G>;
-    static bool attr_set = false;
+    static PerDeviceOnce attr_once;          // opt-in shared-memory size is a per-device function attribute
     auto kern = gemm_ares_tma_2cta_kernel<G, Epi>;
-    if (!attr_set) {
+    if (attr_once.need()) {
         EG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr_set = true;
     }
     EG_CHECK(M % 256 == 0 && N % (256 * G) == 0, "A-resident TMA-epilogue gemm shape not tile-aligned");
     const int items = (M / 256) * ((N / 256) / G);
@@ -731,15 +739,15 @@ static TcGemmCache g_tcg;
 int tc_gemm_f32(const float* A, int lda, const float* W, int ldw, int M, int N, int K, float* C, int ldc, int n_valid, int accumulate,
                 cudaStream_t s) {
     EG_CHECK(M >= 1 && N >= 1 && K >= 1 && n_valid % 4 == 0 && ldc % 4 == 0, "tc_gemm_f32: bad shape");
+    int dev = 0;
+    EG_CUDA(cudaGetDevice(&dev));
     if (!g_tcg.init) {
-        int dev = 0;
-        EG_CUDA(cudaGetDevice(&dev));
         EG_CUDA(cudaDeviceGetAttribute(&g_tcg.I.sms, cudaDevAttrMultiProcessorCount, dev));
         g_tcg.init = true;
     }
     const int Mp = ((M + 255) / 256) * 256, Np = ((N + 255) / 256) * 256, Kp = ((K + 63) / 64) * 64;
     auto plane = [&](int rows, int cols, int role, uint32_t box) -> Plane* {
-        auto key = std::make_pair(((long long)rows << 20) | cols, role);
+        auto key = std::make_pair(((long long)rows << 20) | cols, role + 2 * dev);      // planes live on the device that made them
         auto it = g_tcg.planes.find(key);
         if (it != g_tcg.planes.end()) return it->second.get();
         std::unique_ptr<Plane> p(new Plane());
