@@ -21,14 +21,23 @@ def shard_range(global_batch: int, world: int, rank: int) -> Tuple[int, int]:
 
 
 def sample_sharded(sample_fn: Callable[[torch.Tensor, torch.Tensor, int], torch.Tensor], x_start: torch.Tensor,
-                   cond_mask: torch.Tensor, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+                   cond_mask: torch.Tensor, group: Optional[dist.ProcessGroup] = None,
+                   post_fn: Optional[Callable[[torch.Tensor, int], torch.Tensor]] = None) -> torch.Tensor:
     """``x_start`` / ``cond_mask`` hold the GLOBAL batch on every rank; each rank samples its shard with
-    ``sample_fn(x_shard, mask_shard, window_offset)`` and all ranks return the full [B, T, D] result."""
+    ``sample_fn(x_shard, mask_shard, window_offset)`` and all ranks return the full [B, T, D] result.
+
+    ``post_fn(local_windows, window_offset) -> Tensor[count, ...]`` (optional) runs on the rank's own windows BEFORE the
+    gather, so the single collective moves the post-processed result (e.g. the SMPL parameters of ``smpl_post_fn``: 69 floats
+    per frame instead of 198 -- BASELINE configs[2])."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     B = x_start.shape[0]
     start, count = shard_range(B, world, rank)
     local = sample_fn(x_start[start:start + count], cond_mask[start:start + count], start)
+    if post_fn is not None:
+        local = post_fn(local, start)
+        if local.shape[0] != count:
+            raise ValueError(f"post_fn must keep one row per window: got {local.shape[0]} for {count} windows")
     if world == 1:
         return local
     if B % world == 0:
@@ -53,3 +62,21 @@ def model_sample_fn(model) -> Callable[[torch.Tensor, torch.Tensor, int], torch.
         finally:
             model.window_offset = 0
     return fn
+
+
+def smpl_post_fn(model, ds, recover_rot_quat=None) -> Callable[[torch.Tensor, int], torch.Tensor]:
+    """Adapter for ``sample_sharded(post_fn=...)``: convert_model_res_to_data on the rank's windows (device kernel), packed as
+    [count, T, 69] = local joint axis-angles (22 x 3) followed by the root translation (3) -- the "generated SMPL params" that
+    BASELINE configs[2] gathers.  ``recover_rot_quat`` is indexed by GLOBAL window id ([B, 1, 1, 4] or [B, 4]); None = identity."""
+    def fn(windows, offset):
+        rq = None
+        if recover_rot_quat is not None:
+            rq = torch.as_tensor(recover_rot_quat).reshape(-1, 4)[offset:offset + windows.shape[0]]
+        aa, root, _head = model.postprocess(ds, windows, rq)
+        return torch.cat((aa.reshape(aa.shape[0], aa.shape[1], 66), root), dim=-1)
+    return fn
+
+
+def unpack_smpl(packed: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """[B, T, 69] from ``smpl_post_fn`` -> (local_aa [B, T, 22, 3], root_trans [B, T, 3])."""
+    return packed[..., :66].reshape(packed.shape[0], packed.shape[1], 22, 3), packed[..., 66:]

@@ -237,6 +237,24 @@ def test_philox_mode_properties_full_size(engine, params0):
     assert m.launch_count() > 0
 
 
+def test_sharded_smpl_params_single_rank(params0):
+    """parallel.sample_sharded(post_fn=smpl_post_fn): the rank post-processes its own windows on the device and the one
+    gather moves SMPL parameters (BASELINE configs[2]); with one rank it must equal sample() + postprocess()."""
+    import egoego_release_b200 as E
+    from egoego_release_b200.parallel import model_sample_fn, sample_sharded, smpl_post_fn, unpack_smpl
+    m = make_model(8, "tcgen05", params0, max_batch=4)
+    ds = E.MotionDataStub().bind(m)
+    xs = synth_x_start(17, 4, 120).cuda()
+    cm = O.prep_head_condition_mask(xs.shape).cuda()
+    torch.manual_seed(77)
+    packed = sample_sharded(model_sample_fn(m), xs, cm, post_fn=smpl_post_fn(m, ds))
+    torch.manual_seed(77)
+    aa, root, _ = m.postprocess(ds, m.sample(xs, cm))
+    aa2, root2 = unpack_smpl(packed)
+    assert packed.shape == (4, 120, 69)
+    assert torch.equal(aa2, aa) and torch.equal(root2, root)
+
+
 def test_error_behaviour(params0):
     import egoego_release_b200 as E
     m = make_model(10, "simt", params0, max_batch=2)

@@ -17,6 +17,12 @@ def _fake_sample(xs, cm, offset):
     return xs * (1 - cm) + cm * torch.sin(ids + torch.arange(xs.shape[2]).float().view(1, 1, -1))
 
 
+def _fake_post(windows, offset):
+    """Stand-in for smpl_post_fn: a per-window reduction to 69 channels that also depends on the global window id."""
+    ids = torch.arange(offset, offset + windows.shape[0], dtype=torch.float32).view(-1, 1, 1)
+    return windows[..., :69] * 2.0 + ids
+
+
 def _worker(rank, world, port, B, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -24,8 +30,9 @@ def _worker(rank, world, port, B, q):
     xs = torch.randn(B, 6, 198, generator=g)
     cm = (torch.rand(B, 6, 198, generator=g) > 0.5).float()
     out = sample_sharded(_fake_sample, xs, cm)
+    packed = sample_sharded(_fake_sample, xs, cm, post_fn=_fake_post)
     if rank == 0:
-        q.put(out)
+        q.put((out, packed))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -44,7 +51,7 @@ def test_sharded_sampling_equals_single_process(B):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, B, q)) for r in range(2)]
     for p in procs:
         p.start()
-    out = q.get(timeout=300)
+    out, packed = q.get(timeout=300)
     for p in procs:
         p.join(timeout=180)
         assert p.exitcode == 0
@@ -52,6 +59,7 @@ def test_sharded_sampling_equals_single_process(B):
     xs = torch.randn(B, 6, 198, generator=g)
     cm = (torch.rand(B, 6, 198, generator=g) > 0.5).float()
     assert torch.equal(out, _fake_sample(xs, cm, 0))
+    assert packed.shape == (B, 6, 69) and torch.equal(packed, _fake_post(_fake_sample(xs, cm, 0), 0))    # gather of post-processed params
 
 
 def test_shard_range_partitions():
