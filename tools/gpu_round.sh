@@ -25,6 +25,9 @@ timeout 300 python bench.py --impl reference --steps 1 --warmup 0 > $OUT/${TAG}_
 EGOEGO_BENCH_SKIP_TORCH=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 400 --csv --log-file $OUT/${TAG}_launches.csv \
     python bench.py --steps 1 --warmup 1 --diffusion-steps 100 --cpu-seconds 1 > $OUT/${TAG}_ncu_bench.log 2>&1
 echo "launch list rc=$?"
+# precision of the default policy at scale (64 windows x 1000 steps vs PyTorch fp32 of the reference op sequence on one noise tape)
+PARITY_FLOOR_QUICK=1 timeout 120 python tools/parity_floor.py 64 1000 63 > $OUT/${TAG}_parity_floor.txt 2>&1
+echo "parity floor rc=$?"; grep tcgen05 $OUT/${TAG}_parity_floor.txt | cut -c1-170
 if [ -n "$FULL" ]; then
     for K in gemm_half_tma_2cta_kernel attention_half_kernel gemm_ln_half_c4_kernel; do
         PROF_ONLY=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:$K -s 8 -c 2 -f \
