@@ -528,9 +528,15 @@ static int sample_chunk(egoego_ctx* c, const float* x_start, const float* cond_m
     };
     auto fmt_of_step = [&](int i) -> int { return (N - 1 - i) >= c->precise_last ? 1 : 0; };   // i-th executed step has t = N-1-i
     // single-pass fp16 steps cycle through the dithered fp16 weight sets so that the weight rounding averages out over steps
-    const int n_sets = (c->cfg.engine == EGOEGO_ENGINE_TCGEN05 && c->tc) ? std::min(c->tc->n_weight_sets(), (int)egoego_ctx::MAX_WEIGHT_SETS) : 1;
+    // (slot 0 = split step, slot 1 + r = fp16 step reading copy r).  Averaging needs several full cycles: a run of fewer than
+    // 4 R fp16 steps reads the plain round-to-nearest copy instead (a single dithered copy is up to one ulp off, plain RN half).
+    int n_sets = (c->cfg.engine == EGOEGO_ENGINE_TCGEN05 && c->tc) ? std::min(c->tc->n_weight_sets(), (int)egoego_ctx::MAX_WEIGHT_SETS) : 1;
+    int n_half = 0;
+    for (int i = 0; i < N; ++i) n_half += fmt_of_step(i);
+    const bool dither = n_sets > 1 && n_half >= 4 * n_sets;
+    if (!dither) n_sets = 1;
     auto slot_of_step = [&](int i) -> int { return fmt_of_step(i) ? 1 + (i % n_sets) : 0; };
-    auto select_set = [&](int slot) { if (c->tc) c->tc->use_weight_set(slot > 0 ? slot - 1 : 0); };
+    auto select_set = [&](int slot) { if (c->tc) c->tc->use_weight_set((dither && slot > 0) ? slot - 1 : -1); };
     const void* key[4] = {ns.tape, inpaint, (const void*)(uintptr_t)(ns.seed ^ (ns.window_offset * 0x9E3779B97F4A7C15ull)),
                           (const void*)(uintptr_t)(((uint64_t)inpaint_len << 32) ^ (uint64_t)ns.draw_stride)};
     if (c->use_graph) {

@@ -75,8 +75,9 @@ struct Plane {                 // a 16-bit hi/lo pair (fp16 in the sampler, bf16
     // plane FMT_HALF launches read (the maps are passed to kernels by value, so this is a host-side switch).
     std::vector<__nv_bfloat16*> set16;
     std::vector<CUtensorMap> set_m16, set_m16_128;
-    void use_set(int r) {
+    void use_set(int r) {                              // r < 0: the plain round-to-nearest copy (= the hi plane of the pair)
         if (set16.empty()) return;
+        if (r < 0) { h16 = hi; m16 = mhi; m16_128 = mhi128; return; }
         r %= (int)set16.size();
         h16 = set16[r]; m16 = set_m16[r]; m16_128 = set_m16_128[r];
     }
@@ -151,7 +152,7 @@ static int upload_weight(Plane& p, const float* w, int rows, int src_ld, int col
         if (make_map(&p.set_m16[k], p.set16[k], rows_pad, cols_pad, box_rows) || make_map(&p.set_m16_128[k], p.set16[k], rows_pad, cols_pad, 128)) return 1;
     }
     p.own16 = false;
-    p.use_set(0);
+    p.use_set(-1);                                       // outside the sampling loop FMT_HALF launches read the plain RN copy
     return 0;
 }
 

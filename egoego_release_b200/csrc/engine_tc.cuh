@@ -43,7 +43,8 @@ public:
                  const DdpmArgs* fuse = nullptr);
     void stage_targets(__nv_bfloat16** hi, __nv_bfloat16** lo, __half** h16, int* ld);
     int launches_per_denoiser(int fmt = 0) const;
-    // dithered fp16 weight sets of the single-pass format: the sampling loop uses set (step index mod n) for step i
+    // dithered fp16 weight sets of the single-pass format: the sampling loop uses set (step index mod n) for step i;
+    // r < 0 selects the plain round-to-nearest copy (the default outside the loop)
     int n_weight_sets() const;
     void use_weight_set(int r);
     int time_stage(int B, int T, int stage, int fmt, int iters, float* model_out, cudaStream_t s, float* ms, const DdpmArgs* fuse = nullptr);

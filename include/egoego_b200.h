@@ -286,7 +286,8 @@ int  egoego_precise_last_steps(egoego_handle h);
 /* Number R of dithered fp16 weight sets the single-pass steps cycle through (env EGOEGO_WEIGHT_SETS at weight commit,
  * default 8, 1 = plain round-to-nearest; always 1 for the fp32 engine).  Step i of the loop reads set i mod R, so the fp16
  * rounding of the weights -- the only rounding of those steps that survives to the final sample -- averages out over steps
- * (DESIGN.md 4). */
+ * (DESIGN.md 4).  A loop with fewer than 4 R single-pass steps reads the plain round-to-nearest copy instead (too few steps
+ * to average over). */
 int  egoego_weight_sets(egoego_handle h);
 /* Host-only helper (no GPU needed): the fp16 bit patterns of copy `set` of `n_sets` for n fp32 weights, exactly as
  * egoego_commit_weights rounds them: RN_fp16(w + u ulp16(w)), u = (bitrev(set) + 1/2) / n_sets - 1/2 (u = 0 for n_sets = 1). */
