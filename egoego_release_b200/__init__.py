@@ -8,13 +8,13 @@ compute_metrics_for_smpl (kinpoly/scripts/eval_metrics_imu_rec.py) -- same bound
 The numeric path lives in lib/libegoego_b200.so (C ABI: include/egoego_b200.h); importing this package
 never falls back to PyTorch math -- using it without the built library or without a B200 raises.
 """
-from ._capi import EgoEgoError  # noqa: F401
+from ._capi import EgoEgoError, PRECISE_ALL_FP16  # noqa: F401
 from .diffusion import CondGaussianDiffusion, TransformerDiffusionModel  # noqa: F401
 from .motion_data import MotionDataStub  # noqa: F401
 from .stage1 import HeadFormer, HeadNormalFormer  # noqa: F401
 from .eval_metrics import compute_metrics_for_smpl, compute_metrics_batch  # noqa: F401
 from .trainer_glue import prep_head_condition_mask, prep_padding_mask, full_body_gen_cond_head_pose_sliding_window  # noqa: F401
 
-__all__ = ["CondGaussianDiffusion", "TransformerDiffusionModel", "MotionDataStub", "EgoEgoError", "HeadFormer", "HeadNormalFormer",
+__all__ = ["PRECISE_ALL_FP16", "CondGaussianDiffusion", "TransformerDiffusionModel", "MotionDataStub", "EgoEgoError", "HeadFormer", "HeadNormalFormer",
            "compute_metrics_for_smpl", "compute_metrics_batch",
            "prep_head_condition_mask", "prep_padding_mask", "full_body_gen_cond_head_pose_sliding_window"]

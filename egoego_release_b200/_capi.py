@@ -16,9 +16,11 @@ EXPORTS = [
     "egoego_seqnet_launch_count", "egoego_va2rot", "egoego_rescale_slam", "egoego_slam_features", "egoego_apply_floor_normal",
     "egoego_rigid_apply", "egoego_resnet18_create", "egoego_resnet18_destroy", "egoego_resnet18_set_tensor", "egoego_resnet18_commit",
     "egoego_resnet18_forward", "egoego_resnet18_launch_count", "egoego_train_step", "egoego_train_get_grad", "egoego_update_tensor_device", "egoego_train_get_grads", "egoego_update_tensors_device",
+    "egoego_tensors_checksum",
 ]
 
 ENGINE_TCGEN05, ENGINE_SIMT = 0, 1
+PRECISE_ALL_FP16 = -2     # egoego_cfg.precise_last_steps: explicit opt-out of the precision policy (EGOEGO_PRECISE_ALL_FP16)
 
 
 class Cfg(C.Structure):
@@ -80,6 +82,7 @@ def lib():
     L.egoego_tail_condition.argtypes = [vp, vp, vp, i32, i32, vp, vp]
     L.egoego_eval_metrics.argtypes = [i32, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp]
     L.egoego_launch_count.argtypes = [vp]
+    L.egoego_tensors_checksum.argtypes = [i32, i32, vp, vp, vp, vp]
     L.egoego_launch_count.restype = i64
     f32 = C.c_float
     L.egoego_seqnet_create.argtypes = [C.POINTER(SeqNetCfg), C.POINTER(vp)]
@@ -119,3 +122,21 @@ def lib():
 def check(rc: int):
     if rc != 0:
         raise EgoEgoError(lib().egoego_last_error().decode())
+
+
+def content_checksum(tensors, device) -> int:
+    """64-bit content checksum of CUDA fp32 tensors (egoego_tensors_checksum: one kernel + an 8-byte read-back).
+    The mirrors add it to their (data_ptr, _version) signatures: in-place edits through ``.data`` (ema_pytorch's
+    ``copy_`` / ``lerp_``, trainer_amass_cond_motion_diffusion.py:179-192) do not bump torch's version counters."""
+    import torch
+    ts = [t for t in tensors if t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() > 0]
+    if not ts:
+        return 0
+    n = len(ts)
+    ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in ts])
+    nums = (C.c_int64 * n)(*[t.numel() for t in ts])
+    out = C.c_uint64(0)
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    with torch.cuda.device(device):
+        check(lib().egoego_tensors_checksum(idx, n, ptrs, nums, C.byref(out), C.c_void_p(torch.cuda.current_stream(device).cuda_stream)))
+    return int(out.value)

@@ -175,6 +175,25 @@ static void fill_ddpm(egoego_ctx* c, DdpmArgs& a, const float* x, float* x_out, 
     a.ts = ts; a.ns = ns; a.B = B; a.T = T; a.D = c->D;
 }
 
+
+// ---- content checksum of a set of device tensors (weight-staleness check of the host mirror) ----------------------
+// One launch over all tensors: every 32-bit word contributes word * (2 * global_index + 1) to a wrapping 64-bit sum, so a
+// change of any single bit of any element changes the result.  The table of (pointer, words) travels as a kernel argument.
+constexpr int CHK_MAX_TENSORS = 128;
+struct ChkTable { const uint32_t* p[CHK_MAX_TENSORS]; unsigned long long n[CHK_MAX_TENSORS]; unsigned long long start[CHK_MAX_TENSORS]; int count; };
+__global__ void tensors_checksum_kernel(const __grid_constant__ ChkTable tab, unsigned long long* out) {
+    unsigned long long acc = 0;
+    for (int t = blockIdx.y; t < tab.count; t += gridDim.y) {
+        const uint32_t* p = tab.p[t];
+        const unsigned long long n = tab.n[t], base = tab.start[t];
+        for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x)
+            acc += (unsigned long long)p[i] * (2ull * (base + i) + 1ull);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
 static int check_ready(egoego_ctx* c, int B, int T) {
     EG_CHECK(c != nullptr, "null handle");
     EG_CHECK(c->committed, "egoego_commit_weights has not been called");
@@ -223,12 +242,16 @@ int egoego_create(const egoego_cfg* cfg, egoego_handle* out) {
     const char* g = getenv("EGOEGO_GRAPH");
     c->use_graph = !(g && g[0] == '0');
     // precision policy: the last `precise_last` steps (t < precise_last) run the 3-term fp16 hi/lo split,
-    // earlier steps a single fp16 pass.  cfg.precise_last_steps < 0 selects the default max(ceil(N/16), 48); N = all precise.
+    // earlier steps a single fp16 pass.  cfg.precise_last_steps: 0 (the value of a zero-initialised egoego_cfg) and -1 select
+    // the default max(ceil(N/16), 48); K > 0 = K split steps (K >= N: every step); EGOEGO_PRECISE_ALL_FP16 (-2) is the only
+    // way to run every step single-pass -- out of tolerance, kept for measurements.
     {
         int pl = cfg->precise_last_steps;
         const char* e = getenv("EGOEGO_PRECISE_STEPS");
         if (e && e[0]) pl = atoi(e);
-        if (pl < 0) { pl = (cfg->timesteps + 15) / 16; if (pl < 48) pl = 48; }
+        EG_CHECK(pl >= EGOEGO_PRECISE_ALL_FP16, "precise_last_steps must be >= 0, -1 (default) or EGOEGO_PRECISE_ALL_FP16");
+        if (pl == EGOEGO_PRECISE_ALL_FP16) pl = 0;
+        else if (pl <= 0) { pl = (cfg->timesteps + 15) / 16; if (pl < 48) pl = 48; }
         if (pl > cfg->timesteps) pl = cfg->timesteps;
         c->precise_last = (cfg->engine == EGOEGO_ENGINE_TCGEN05) ? pl : cfg->timesteps;
     }
@@ -718,6 +741,36 @@ int egoego_tail_condition(egoego_handle c, const float* gquat, const float* gjpo
 }
 
 int64_t egoego_launch_count(egoego_handle c) { return c ? c->launches : -1; }
+
+int egoego_tensors_checksum(int device, int n, const void* const* ptrs_dev, const int64_t* numels, uint64_t* out_host, void* stream_v) {
+    EG_CHECK(ptrs_dev && numels && out_host && n >= 0, "null argument");
+    int ndev = 0;
+    EG_CHECK(cudaGetDeviceCount(&ndev) == cudaSuccess && device >= 0 && device < ndev, "no such CUDA device");
+    EG_CUDA(cudaSetDevice(device));
+    cudaStream_t s = (cudaStream_t)stream_v;
+    static thread_local unsigned long long* d_acc[64] = {};
+    unsigned long long*& acc = d_acc[device & 63];
+    if (!acc) EG_CUDA(cudaMalloc(&acc, 8));
+    EG_CUDA(cudaMemsetAsync(acc, 0, 8, s));
+    unsigned long long start = 0;
+    for (int t0 = 0; t0 < n; t0 += CHK_MAX_TENSORS) {
+        ChkTable tab{};
+        tab.count = std::min(CHK_MAX_TENSORS, n - t0);
+        for (int t = 0; t < tab.count; ++t) {
+            EG_CHECK(numels[t0 + t] >= 0 && (ptrs_dev[t0 + t] || numels[t0 + t] == 0), "egoego_tensors_checksum: bad tensor");
+            tab.p[t] = reinterpret_cast<const uint32_t*>(ptrs_dev[t0 + t]); tab.n[t] = (unsigned long long)numels[t0 + t]; tab.start[t] = start;
+            start += tab.n[t];
+        }
+        tensors_checksum_kernel<<<dim3(64, (unsigned)std::min(tab.count, 32)), 256, 0, s>>>(tab, acc);
+        EG_CUDA(cudaGetLastError());
+    }
+    unsigned long long h = 0;
+    EG_CUDA(cudaMemcpyAsync(&h, acc, 8, cudaMemcpyDeviceToHost, s));
+    EG_CUDA(cudaStreamSynchronize(s));
+    *out_host = h;
+    return 0;
+}
+
 
 int egoego_time_kernel(egoego_handle c, int B, int T, int which, int half_fmt, int iters, float* ms_per_launch, void* stream_v) {
     EG_CHECK(c && ms_per_launch, "null argument");

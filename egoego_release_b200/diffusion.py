@@ -183,7 +183,8 @@ class CondGaussianDiffusion(nn.Module):
         self._cfg = dict(d_feats=d_feats, d_model=d_model, n_head=n_head, n_dec_layers=n_dec_layers, d_k=d_k, d_v=d_v,
                          max_timesteps=max_timesteps)
         self._max_batch = int(max_batch)
-        self._precise_last_steps = int(precise_last_steps)   # -1: default policy ceil(N/4); N: every step 3-term split
+        # 0 / -1: default policy max(ceil(N/16), 48) split steps; K > 0: K split steps (>= N: all); PRECISE_ALL_FP16: none
+        self._precise_last_steps = int(precise_last_steps)
         eng = engine or os.environ.get("EGOEGO_ENGINE", DEFAULT_ENGINE)
         if eng not in ("tcgen05", "simt"):
             raise ValueError(f"unknown engine {eng}")
@@ -228,7 +229,34 @@ class CondGaussianDiffusion(nn.Module):
         return dev
 
     def _signature(self):
-        return tuple((k, v.data_ptr(), v._version) for k, v in self.state_dict(keep_vars=True).items())
+        """(data_ptr, _version) of every tensor PLUS a content checksum computed on the device: writes through ``.data``
+        (``p.data.copy_`` / ``lerp_``: what ema_pytorch's update does) leave ``_version`` untouched, so the version
+        counters alone would let the engine keep sampling with stale packed weights."""
+        sd = self.state_dict(keep_vars=True)
+        dev = self.betas.device
+        chk = _capi.content_checksum([v.detach() for v in sd.values()], dev) if dev.type == "cuda" else 0
+        return tuple((k, v.data_ptr(), v._version) for k, v in sd.items()) + (("__content__", chk, 0),)
+
+    # ema_pytorch.EMA.state_dict() (what the reference saves under 'ema', trainer_amass_cond_motion_diffusion.py:100-106)
+    # carries 'ema_model.<key>', 'online_model.<key>', 'initted', 'step'; DataParallel / DDP add 'module.'.
+    _WRAPPER_PREFIXES = ("ema_model.", "module.", "model.")
+
+    def load_state_dict(self, state_dict, strict: bool = True, **kw):
+        """Accepts the reference's checkpoints as they are on disk: plain keys (``denoise_fn.*``, the 'model' entry) and
+        wrapped ones (the 'ema' entry: ``ema_model.denoise_fn.*`` next to ``online_model.*`` / ``initted`` / ``step``).
+        A dict without a single ``denoise_fn.*`` tensor is an error even with ``strict=False`` -- silently keeping the
+        random initialisation is never what the caller meant."""
+        sd = dict(state_dict)
+        for pre in self._WRAPPER_PREFIXES:
+            if any(k.startswith(pre + "denoise_fn.") for k in sd):
+                sd = {k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)}
+                break
+        if not any(k.startswith("denoise_fn.") for k in sd):
+            raise KeyError("load_state_dict: no 'denoise_fn.*' tensor found (keys look like "
+                           f"{sorted(state_dict)[:3]}); expected the reference's 'model' or 'ema' checkpoint entry")
+        res = super().load_state_dict(sd, strict=strict, **kw)
+        self._weights_sig = None
+        return res
 
     def _handle(self):
         dev = self._device()
@@ -407,7 +435,16 @@ class CondGaussianDiffusion(nn.Module):
     # ------------------------------------------------------------------------------------------
     def _set_skeleton(self, ds):
         h = self._handle()
-        parents = np.ascontiguousarray(np.asarray(ds.parents if hasattr(ds, "parents") else ds.get_smpl_parents(), dtype=np.int32))
+        # The reference's AMASSDataset has no parents attribute (get_smpl_parents is a module-level function that reads the
+        # licensed model.npz, egoego/data/amass_diffusion_dataset.py:83-90): fall back to the packaged 22-joint SMPL kintree.
+        if hasattr(ds, "parents"):
+            par = ds.parents
+        elif hasattr(ds, "get_smpl_parents"):
+            par = ds.get_smpl_parents()
+        else:
+            from .motion_data import smpl22_parents
+            par = smpl22_parents()
+        parents = np.ascontiguousarray(np.asarray(par, dtype=np.int32)[:22])
         off = np.ascontiguousarray(ds.rest_human_offsets.detach().cpu().numpy().reshape(-1).astype(np.float32))
         jmin = np.ascontiguousarray(ds.global_jpos_min.detach().cpu().numpy().reshape(-1).astype(np.float32))
         jmax = np.ascontiguousarray(ds.global_jpos_max.detach().cpu().numpy().reshape(-1).astype(np.float32))
@@ -581,6 +618,8 @@ class CondGaussianDiffusion(nn.Module):
                 else:                                    # after an optimizer step: device-to-device refresh of what changed
                     old = dict((k, (p, ver)) for k, p, ver in self._ht_sig)
                     ch = [(k, _f32c(v.detach(), dev)) for k, v in self.named_parameters() if old.get(k) != (v.data_ptr(), v._version)]
+                    if not ch:                           # only the content checksum moved (.data edits): refresh every parameter
+                        ch = [(k, _f32c(v.detach(), dev)) for k, v in self.named_parameters()]
                     if ch:
                         n = len(ch)
                         names = (C.c_char_p * n)(*[k.encode() for k, _ in ch])

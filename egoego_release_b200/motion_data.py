@@ -17,6 +17,12 @@ import torch
 ASSET_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "assets")
 
 
+def smpl22_parents() -> np.ndarray:
+    """The 22-joint SMPL kinematic tree (parents[0] = -1) shipped in assets/smpl22_skeleton.json; what the reference's
+    ``get_smpl_parents()`` returns from the licensed SMPL-H ``model.npz`` (amass_diffusion_dataset.py:83-90)."""
+    return np.asarray(json.load(open(os.path.join(ASSET_DIR, "smpl22_skeleton.json")))["parents"], dtype=np.int64)
+
+
 class MotionDataStub:
     def __init__(self, device="cpu"):
         sk = json.load(open(os.path.join(ASSET_DIR, "smpl22_skeleton.json")))

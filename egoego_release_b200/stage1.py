@@ -76,7 +76,9 @@ class _SeqNetModule(nn.Module):
 
     def _handle(self):
         dev = self._cuda_device()
-        sig = (dev.index or 0, tuple((k, v._version, v.data_ptr()) for k, v in self.state_dict().items()))
+        sd_now = self.state_dict()
+        sig = (dev.index or 0, tuple((k, v._version, v.data_ptr()) for k, v in sd_now.items()),
+               _capi.content_checksum(list(sd_now.values()), dev))         # .data edits do not bump _version (see _capi.content_checksum)
         if self._h is not None and sig == self._sig:
             return self._h
         L = _capi.lib()
@@ -190,7 +192,8 @@ class HeadFormer(_SeqNetModule):
     def _cnn_handle(self):
         dev = self._cuda_device()
         sd = self.cnn.state_dict()
-        sig = (dev.index or 0, tuple((k, v._version, v.data_ptr()) for k, v in sd.items()))
+        sig = (dev.index or 0, tuple((k, v._version, v.data_ptr()) for k, v in sd.items()),
+               _capi.content_checksum(list(sd.values()), dev))
         if self._cnn_h is not None and sig == self._cnn_sig:
             return self._cnn_h
         L = _capi.lib()

@@ -56,9 +56,14 @@ typedef struct egoego_cfg {
     int32_t engine;        /* EGOEGO_ENGINE_*                                          */
     int32_t precise_last_steps; /* tensor engine precision policy: the last K diffusion steps (t < K) use the
                               3-term fp16 hi/lo split (fp32-grade); earlier steps one fp16 pass over dithered weight
-                              copies (egoego_weight_sets), whose error is damped by posterior_mean_coef1[t].  -1 = default max(ceil(timesteps/16), 48); timesteps = all steps
-                              split.  The per-call entry points (denoiser_forward, p_sample_step) always split. */
+                              copies (egoego_weight_sets), whose error is damped by posterior_mean_coef1[t].
+                              0 (a zero-initialised cfg) or -1 = default max(ceil(timesteps/16), 48); K >= timesteps = all
+                              steps split; EGOEGO_PRECISE_ALL_FP16 = every step single-pass (30 mm worst-window error:
+                              measurements only).  The per-call entry points (denoiser_forward, p_sample_step) always split. */
 } egoego_cfg;
+
+/* explicit opt-out of the precision policy (egoego_cfg.precise_last_steps): no split steps at all */
+#define EGOEGO_PRECISE_ALL_FP16 (-2)
 
 enum {
     EGOEGO_ENGINE_TCGEN05 = 0, /* tcgen05/TMA GEMMs, 3-term fp16 hi/lo split, fp32 accumulate (default) */
@@ -257,6 +262,12 @@ int  egoego_update_tensors_device(egoego_handle h, int n, const char* const* nam
 /* Introspection for tests/bench: number of kernels launched by this handle since creation, and the
  * cumulative count of denoiser steps executed. */
 int64_t egoego_launch_count(egoego_handle h);
+
+/* Content checksum of n device tensors of 32-bit elements (fp32 parameters): wrapping 64-bit sum of word * (2 * index + 1)
+ * over the concatenation, one kernel launch + one 8-byte read-back (synchronises `stream`).  The host mirror uses it to
+ * notice in-place parameter edits that bypass torch's version counters (p.data.copy_ / lerp_, as ema_pytorch does:
+ * trainer_amass_cond_motion_diffusion.py:179-192) before it reuses the engine's packed weights.  No handle needed. */
+int  egoego_tensors_checksum(int device, int n, const void* const* ptrs_dev, const int64_t* numels, uint64_t* out_host, void* stream);
 
 /* Measurement hook (bench.py roofline / per-kernel table): average device time of one launch of ONE kernel of the
  * sampling step -- `which` = EGOEGO_KERNEL_* (layer 0's weights) -- over `iters` back-to-back launches on `stream`,

@@ -292,18 +292,18 @@ def test_precision_policy_knob(golden_dir, params0):
     tape = torch.stack([tp.draw(xs.shape) for _ in range(N + 2)]).cuda()
     ref = torch.from_numpy(g[f"n{N}_b{B}_seed{seed}"])
     errs = {}
-    for K in (50, 20, 0):
+    for K in (50, 20, E.PRECISE_ALL_FP16):
         m = E.CondGaussianDiffusion(d_feats=198, d_model=512, n_dec_layers=4, n_head=4, d_k=256, d_v=256, max_timesteps=121,
                                     out_dim=198, timesteps=N, objective="pred_x0", max_batch=B, engine="tcgen05",
                                     precise_last_steps=K)
         m.load_state_dict(params0, strict=False)
         m = m.cuda()
-        assert m.precise_last_steps() == K
+        assert m.precise_last_steps() == max(K, 0)
         m.set_noise_tape(tape)
         errs[K] = maxabs(joints(m.sample(xs.cuda(), cm.cuda())), joints(ref))
     print("joint error (m) by precise_last_steps:", errs)
     assert errs[50] < 3e-4 and errs[20] < JPOS_TOL_M
-    assert errs[0] > errs[50]            # the fp16 format alone is NOT fp32-grade: the policy matters
+    assert errs[E.PRECISE_ALL_FP16] > errs[50]            # the fp16 format alone is NOT fp32-grade: the policy matters
 
 
 def test_full_size_policy_vs_fp32_engines(params0):
@@ -352,7 +352,7 @@ def test_fused_ln_kernels_agree(params0, monkeypatch):
             monkeypatch.setenv(k, v)
         m = E.CondGaussianDiffusion(d_feats=198, d_model=512, n_dec_layers=4, n_head=4, d_k=256, d_v=256, max_timesteps=121,
                                     out_dim=198, timesteps=N, objective="pred_x0", max_batch=B, engine="tcgen05",
-                                    precise_last_steps=0)
+                                    precise_last_steps=E.PRECISE_ALL_FP16)
         m.load_state_dict(params0, strict=False)
         m = m.cuda()
         torch.manual_seed(3)
@@ -363,7 +363,7 @@ def test_fused_ln_kernels_agree(params0, monkeypatch):
     assert d1 < 2e-2 and d2 < 2e-2
 
 
-@pytest.mark.parametrize("K", [12, 0])
+@pytest.mark.parametrize("K", [12, -2])
 def test_fused_ddpm_epilogue_matches_ddpm_kernel(params0, monkeypatch, K):
     """linear_out with the DDPM update in its epilogue (EGOEGO_FUSE_DDPM=1) against linear_out + ddpm_update_kernel (default):
     same arithmetic and the same Philox stream element for element, in both operand formats, with in-painting, an odd
@@ -390,7 +390,7 @@ def test_fused_ddpm_epilogue_matches_ddpm_kernel(params0, monkeypatch, K):
             outs[tag] = (plain, painted)
         for a, b in zip(outs["fused"], outs["kernel"]):
             assert torch.isfinite(a).all()
-            assert maxabs(a, b) < (5e-5 if K else 5e-3), (B, T, K, maxabs(a, b))
+            assert maxabs(a, b) < (5e-5 if K > 0 else 5e-3), (B, T, K, maxabs(a, b))
         assert torch.equal(outs["fused"][1][:, :10], inpaint)
 
 
@@ -407,3 +407,108 @@ def test_time_kernel_hook(params0):
             assert 0.0 < ms < 50.0, (name, half, ms)
     torch.manual_seed(1); b = m.sample(xs, cm)
     assert torch.equal(a, b)
+
+
+@pytest.mark.gpu
+def test_zero_initialised_cfg_selects_default_policy(params0):
+    """C-ABI level: an egoego_cfg whose precise_last_steps was left at zero runs the DEFAULT precision
+    policy (max(ceil(N/16), 48) split steps), not the all-fp16 mode, and meets the 1 mm bar on the 1000-step golden."""
+    import ctypes as C
+    from egoego_release_b200 import _capi
+    L = _capi.lib()
+    for N, want in ((1000, 63), (50, 48), (2000, 125)):
+        cfg = _capi.Cfg(d_feats=198, d_model=512, n_head=4, n_dec_layers=4, d_k=256, d_v=256, max_timesteps=121,
+                        timesteps=N, objective=1, max_batch=2, device=0, engine=0)         # precise_last_steps zero-filled
+        assert cfg.precise_last_steps == 0
+        h = C.c_void_p()
+        _capi.check(L.egoego_create(C.byref(cfg), C.byref(h)))
+        assert L.egoego_precise_last_steps(h) == want
+        L.egoego_destroy(h)
+    import egoego_release_b200 as E
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "sample.npz"))
+    N, B, seed = 1000, 1, 22
+    m = E.CondGaussianDiffusion(d_feats=198, d_model=512, n_dec_layers=4, n_head=4, d_k=256, d_v=256, max_timesteps=121,
+                                out_dim=198, timesteps=N, objective="pred_x0", max_batch=B, engine="tcgen05", precise_last_steps=0)
+    m.load_state_dict(params0, strict=False)
+    m = m.cuda()
+    assert m.precise_last_steps() == 63
+    xs = synth_x_start(100 + N, B, 120)
+    cm = O.prep_head_condition_mask(xs.shape)
+    tp = Tape(seed)
+    m.set_noise_tape(torch.stack([tp.draw(xs.shape) for _ in range(N + 2)]).cuda())
+    err = maxabs(joints(m.sample(xs.cuda(), cm.cuda())), joints(torch.from_numpy(g[f"n{N}_b{B}_seed{seed}"])))
+    print(f"zero-valued precise_last_steps: joint max-abs {err * 1e3:.4f} mm")
+    assert err < JPOS_TOL_M
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["seed1", "seed2", "trained_like"])
+def test_sample_1000_steps_other_weight_sets_vs_golden(golden_dir, name):
+    """the default precision policy against 1000-step goldens of the UNMODIFIED reference on three
+    further weight sets (two more random initialisations and a 'trained-like' one: linear_out scaled by 0.3, LayerNorm gains
+    spread 0.3), 8 windows each with their own conditioning and noise tape (oracle/gen_golden_weightsets.py).  The bar is
+    the north star's 1 mm on every joint of every window; the target written in the verdict is 0.5 mm."""
+    import egoego_release_b200 as E
+    from oracle.gen_golden_weightsets import WEIGHT_SETS, N, B, T
+    kw, cseed, tseed = WEIGHT_SETS[name]
+    ref = torch.from_numpy(_g(golden_dir, f"sample_ws_{name}.npz")[f"n{N}_b{B}"])
+    params = O.init_params(**kw)
+    m = E.CondGaussianDiffusion(d_feats=198, d_model=512, n_dec_layers=4, n_head=4, d_k=256, d_v=256, max_timesteps=121,
+                                out_dim=198, timesteps=N, objective="pred_x0", max_batch=B, engine="tcgen05")
+    m.load_state_dict(params, strict=False)
+    m = m.cuda()
+    xs = synth_x_start(cseed, B, T)
+    cm = O.prep_head_condition_mask(xs.shape)
+    tp = Tape(tseed)
+    m.set_noise_tape(torch.stack([tp.draw(xs.shape) for _ in range(N + 2)]).cuda())
+    y = m.sample(xs.cuda(), cm.cuda())
+    jy, jr = joints(y), joints(ref)
+    per_window = (jy - jr).abs().reshape(B, -1).max(dim=1).values
+    mpjpe = float((jy - jr).norm(dim=-1).mean())
+    print(f"weight set {name}: joint max-abs per window (mm) {[round(float(v) * 1e3, 4) for v in per_window]}, mean {mpjpe * 1e3:.4f} mm, "
+          f"raw max-abs {maxabs(y, ref):.3e}")
+    assert float(per_window.max()) < 0.5e-3, (name, per_window)
+
+
+@pytest.mark.gpu
+def test_data_edits_refresh_engine_weights(params0):
+    """in-place edits through ``.data`` (what ema_pytorch's update does) leave ``_version`` at its old value; the
+    mirror's content checksum must still notice and re-pack the engine's weights."""
+    m = make_model(6, "tcgen05", params0, max_batch=2)
+    xs = synth_x_start(9, 2, 120).cuda()
+    cm = O.prep_head_condition_mask(xs.shape).cuda()
+    torch.manual_seed(11); a = m.sample(xs, cm)
+    torch.manual_seed(11); a2 = m.sample(xs, cm)
+    assert torch.equal(a, a2)
+    w = m.denoise_fn.linear_out.weight
+    v0 = w._version
+    w.data.mul_(0.5)
+    m.denoise_fn.linear_out.bias.data.lerp_(torch.zeros_like(m.denoise_fn.linear_out.bias), 0.5)
+    assert w._version == v0                        # the situation the checksum exists for
+    torch.manual_seed(11); b = m.sample(xs, cm)
+    assert not torch.equal(a, b)
+    ref = make_model(6, "tcgen05", {k: (v * 0.5 if k.startswith("denoise_fn.linear_out.") else v) for k, v in params0.items()}, max_batch=2)
+    torch.manual_seed(11); c = ref.sample(xs, cm)
+    assert torch.equal(b, c)
+
+
+@pytest.mark.gpu
+def test_duck_typed_dataset_without_parents(params0):
+    """the reference's AMASSDataset exposes rest_human_offsets / global_jpos_min / global_jpos_max / fk_smpl and the
+    normalise methods but NO parents table; post-processing must fall back to the packaged 22-joint kintree."""
+    import egoego_release_b200 as E
+    stub = E.MotionDataStub()
+
+    class RefLikeDataset:            # only what egoego/data/amass_diffusion_dataset.py's class has
+        rest_human_offsets = stub.rest_human_offsets
+        global_jpos_min = stub.global_jpos_min
+        global_jpos_max = stub.global_jpos_max
+        normalize_jpos_min_max = stub.normalize_jpos_min_max
+        de_normalize_jpos_min_max = stub.de_normalize_jpos_min_max
+
+    m = make_model(4, "tcgen05", params0, max_batch=2)
+    x = (torch.rand(2, 16, 198, device="cuda") * 2 - 1)
+    a = m.postprocess(RefLikeDataset(), x, None, with_fk=True)
+    b = m.postprocess(stub, x, None, with_fk=True)
+    for u, v in zip(a, b):
+        assert torch.equal(u, v)
