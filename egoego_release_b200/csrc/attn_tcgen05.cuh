@@ -279,7 +279,7 @@ __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.
 __global__ void __launch_bounds__(ATT2_THREADS, 1)
 attention_half_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUtensorMap mK,
                       const __grid_constant__ CUtensorMap mV /* 64-row boxes */, const __grid_constant__ CUtensorMap mO /* [M, H*256] fp16, 128-row x 64-col boxes */,
-                      int n_items, int n_head, int L) {
+                      int n_items, int n_head, int L, int rev /* 1: walk the items from the last window to the first (L2 zig-zag) */) {
     constexpr uint32_t IDESC_S = ptx::make_idesc_f16(128, 128);
     constexpr uint32_t IDESC_O = ptx::make_idesc_f16(128, 256) | ptx::IDESC_B_MN_MAJOR;
     constexpr int STAGE = 32768, STAGES = ATT_RING_BYTES / STAGE;           // 4
@@ -323,7 +323,7 @@ attention_half_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_const
     ptx::grid_dep_launch();
     ptx::grid_dep_wait();                                // prologue above overlaps the previous kernel's tail (PDL)
     const int n_mine = blockIdx.x < n_items ? (n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;   // items of this CTA
-    auto item_of = [&](int j) { return (int)blockIdx.x + j * (int)gridDim.x; };
+    auto item_of = [&](int j) { const int i = (int)blockIdx.x + j * (int)gridDim.x; return rev ? n_items - 1 - i : i; };
 
     if (warp == 0) {
         if (lane == 0) {                                   // ===== TMA producer: QK(0) QK(1) | V(0) QK(2) | V(1) QK(3) ... =====

@@ -172,6 +172,12 @@ struct TcImpl {
     bool attn_tc = true;                        // EGOEGO_ATTN=simt selects the fp32 CUDA-core attention (bisecting)
     bool attn_v2 = true;                        // fp16 steps: software-pipelined attention_half_kernel (EGOEGO_ATTN=v1: attention_tc_kernel<FMT_HALF>)
     int ln4_clusters = 0;                       // co-resident clusters of 4 for gemm_ln_half_c4_kernel (0 = use the full-row pair kernel)
+    // L2 zig-zag (EGOEGO_ZIGZAG, default on): consecutive kernels of a step walk the windows in OPPOSITE directions, so a
+    // kernel starts with the rows its producer wrote last -- the part of its input that is still in the 126 MB L2 (the
+    // per-kernel working set at 256 windows is 100-270 MB, so a same-direction walk misses everywhere).
+    bool zigzag = true;
+    int dir = 0;                                // direction of the next kernel launched (0 = ascending windows)
+    int next_dir() { const int d = zigzag ? dir : 0; dir ^= 1; return d; }
     float *base = nullptr, *H = nullptr, *Y = nullptr, *QKV = nullptr;
     ~TcImpl() {
         for (Plane* p : {&Wx, &Wc, &Wout, &X, &C, &Hs, &O, &F, &Qp, &Kp, &VT}) p->release();
@@ -232,8 +238,9 @@ static int launch_gemm_2cta(TcImpl* I, const Plane& A, const Plane& W, int M, in
     int pairs = I->sms / 2;
     if (tiles < pairs) pairs = tiles;
     LaunchCfg lc(2 * pairs, GEMM_THREADS, GEMM2_SMEM_BYTES, s, 2);
-    if (fmt_is_split(FMT)) { EG_CUDA(cudaLaunchKernelEx(&lc.cfg, kern, A.mhi, A.mlo, W.mhi128, W.mlo128, M, N, K, epi)); }
-    else                  { EG_CUDA(cudaLaunchKernelEx(&lc.cfg, kern, A.m16, A.m16, W.m16_128, W.m16_128, M, N, K, epi)); }
+    const int rev = I->next_dir();
+    if (fmt_is_split(FMT)) { EG_CUDA(cudaLaunchKernelEx(&lc.cfg, kern, A.mhi, A.mlo, W.mhi128, W.mlo128, M, N, K, epi, rev)); }
+    else                  { EG_CUDA(cudaLaunchKernelEx(&lc.cfg, kern, A.m16, A.m16, W.m16_128, W.m16_128, M, N, K, epi, rev)); }
     return 0;
 }
 
@@ -275,7 +282,7 @@ static int launch_gemm_tma_epi(TcImpl* I, const Plane& A, const Plane& W, int M,
     int pairs = I->sms / 2;
     if (tiles < pairs) pairs = tiles;
     LaunchCfg lc(2 * pairs, GEMM_TMAEPI_THREADS, GemmTmaEpiCfg::SMEM_BYTES, s, 2);
-    EG_CUDA(cudaLaunchKernelEx(&lc.cfg, kern, A.m16, W.m16_128, M, N, K, bias, epi));
+    EG_CUDA(cudaLaunchKernelEx(&lc.cfg, kern, A.m16, W.m16_128, M, N, K, bias, epi, I->next_dir()));
     return 0;
 }
 
@@ -382,6 +389,7 @@ int TcEngine::init(const TcWeights& w, cudaStream_t) {
                 cudaGetLastError();
         }
     }
+    { const char* zz = getenv("EGOEGO_ZIGZAG"); I->zigzag = !(zz && zz[0] == '0'); }
     const char* am = getenv("EGOEGO_ATTN");
     I->attn_tc = !(am && strcmp(am, "simt") == 0);
     if (I->attn_tc) {
@@ -451,7 +459,7 @@ static int launch_gemm_ln(TcImpl* I, const Plane& A, const Plane& W, int M, int 
         const int tiles = M / 256;
         const int clusters = tiles < I->ln4_clusters ? tiles : I->ln4_clusters;
         LaunchCfg lc(4 * clusters, GEMM_LN4_THREADS, GemmLn4Cfg::SMEM_BYTES, s, 4);
-        EG_CUDA(cudaLaunchKernelEx(&lc.cfg, gemm_ln_half_c4_kernel, A.m16_128, W.m16_128, I->Hs.m16_128, M, K, bias, g, b));
+        EG_CUDA(cudaLaunchKernelEx(&lc.cfg, gemm_ln_half_c4_kernel, A.m16_128, W.m16_128, I->Hs.m16_128, M, K, bias, g, b, I->next_dir()));
         return 0;
     }
     if (use_2cta() && M % 256 == 0) {
@@ -552,6 +560,7 @@ static int denoiser_impl(TcImpl* I, int B, int T, TSrc ts, const float* pmask, f
     const int half = (FMT == FMT_HALF) ? 1 : 0;
     const bool fused = (FMT == FMT_HALF) && I->fuse_ln && I->attn_tc && pmask == nullptr;
     auto on = [&](int stage, int l) { return only < 0 || (only == stage && l == 0); };
+    I->dir = 0;                                    // a call always starts ascending: 22 kernels per call, so replayed graphs stay in phase
     if (on(0, 0)) {
         TcEpiStart<FMT> e{{}, fused ? nullptr : I->H, I->Hs.hi, I->Hs.lo, d, I->base, I->w.pos, I->w.temb, ts, T, B};
         if (gemm<FMT>(I, I->X, I->Wx, Mg, d, I->kx, e, s)) return 1;
@@ -578,7 +587,7 @@ static int denoiser_impl(TcImpl* I, int B, int T, TSrc ts, const float* pmask, f
                 const int items = B * H;
                 if (FMT == FMT_HALF && I->attn_v2) {
                     LaunchCfg lc(items < I->sms ? items : I->sms, ATT2_THREADS, ATT2_SMEM_BYTES, s);
-                    EG_CUDA(cudaLaunchKernelEx(&lc.cfg, attention_half_kernel, I->Qp.m16, I->Kp.m16, I->VT.m16, I->O.m16_128, items, H, L));
+                    EG_CUDA(cudaLaunchKernelEx(&lc.cfg, attention_half_kernel, I->Qp.m16, I->Kp.m16, I->VT.m16, I->O.m16_128, items, H, L, I->next_dir()));
                 } else {
                     LaunchCfg lc(items < I->sms ? items : I->sms, ATT_THREADS, ATT_SMEM_BYTES, s);
                     EG_CUDA(cudaLaunchKernelEx(&lc.cfg, attention_tc_kernel<FMT>, I->Qp.mhi, I->Qp.mlo, I->Kp.mhi, I->Kp.mlo, I->VT.mhi, I->VT.mlo,

@@ -417,7 +417,7 @@ template <int FMT, class Epi>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_split3_2cta_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl,
                         const __grid_constant__ CUtensorMap mWh, const __grid_constant__ CUtensorMap mWl,   // W maps: 128-row boxes
-                        int M, int N, int K, Epi epi) {
+                        int M, int N, int K, Epi epi, int rev = 0 /* 1: walk the tiles from the last row block to the first (L2 zig-zag) */) {
     constexpr int BN = 256;
     constexpr int NP = Gemm2Cfg<FMT>::NP;
     constexpr int GEMM2_STAGES = Gemm2Cfg<FMT>::STAGES;
@@ -465,7 +465,8 @@ gemm_split3_2cta_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_co
     if (warp == 0) {
         if (lane == 0) {                                 // ===== TMA producer (both CTAs) =====
             int s = 0; uint32_t ph = 0;
-            for (int tile = pair; tile < total_tiles; tile += n_pairs) {
+            for (int tl = pair; tl < total_tiles; tl += n_pairs) {
+                const int tile = rev ? total_tiles - 1 - tl : tl;
                 const int m0 = (tile / n_tiles) * 256 + (int)rank * 128;
                 const int n0 = (tile % n_tiles) * BN + (int)rank * 128;
                 for (int kb = 0; kb < k_blocks; ++kb) {
@@ -514,7 +515,8 @@ gemm_split3_2cta_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_co
     } else {                                             // ===== epilogue warps 2..9 (both CTAs) =====
         const int quarter = (warp - 2) & 3;
         int it = 0;
-        for (int tile = pair; tile < total_tiles; tile += n_pairs, ++it) {
+        for (int tl = pair; tl < total_tiles; tl += n_pairs, ++it) {
+            const int tile = rev ? total_tiles - 1 - tl : tl;
             const int a = it & 1;
             const uint32_t aph = (it >> 1) & 1;
             const int m0 = (tile / n_tiles) * 256 + (int)rank * 128, n0 = (tile % n_tiles) * BN;
@@ -1030,7 +1032,7 @@ struct GemmTmaEpiCfg {
 template <class Epi>
 __global__ void __launch_bounds__(GEMM_TMAEPI_THREADS, 1)
 gemm_half_tma_2cta_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mW /*128-row boxes*/,
-                          int M, int N, int K, const float* __restrict__ bias, const __grid_constant__ Epi epi) {
+                          int M, int N, int K, const float* __restrict__ bias, const __grid_constant__ Epi epi, int rev) {
     using Cfg = GemmTmaEpiCfg;
     constexpr int STAGES = Cfg::STAGES, T_BYTES = Cfg::T_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES, BN = 256;
     constexpr uint32_t IDESC = ptx::make_idesc_f16(256, BN);
@@ -1076,7 +1078,8 @@ gemm_half_tma_2cta_kernel(const __grid_constant__ CUtensorMap mA, const __grid_c
     if (warp == 0) {
         if (lane == 0) {                                 // ===== TMA producer (both CTAs) =====
             int s = 0; uint32_t ph = 0;
-            for (int tile = pair; tile < total_tiles; tile += n_pairs) {
+            for (int tl = pair; tl < total_tiles; tl += n_pairs) {
+                const int tile = rev ? total_tiles - 1 - tl : tl;
                 const int m0 = (tile / n_tiles) * 256 + (int)rank * 128;
                 const int n0 = (tile % n_tiles) * BN + (int)rank * 128;
                 for (int kb = 0; kb < k_blocks; ++kb) {
@@ -1115,7 +1118,8 @@ gemm_half_tma_2cta_kernel(const __grid_constant__ CUtensorMap mA, const __grid_c
     } else if (warp == 10) {
         if (lane == 0) {                                 // ===== store I/O (both CTAs) =====
             int it = 0;
-            for (int tile = pair; tile < total_tiles; tile += n_pairs, ++it) {
+            for (int tl = pair; tl < total_tiles; tl += n_pairs, ++it) {
+                const int tile = rev ? total_tiles - 1 - tl : tl;
                 const int row0 = (tile / n_tiles) * 256 + (int)rank * 128, n0 = (tile % n_tiles) * BN;
 #pragma unroll 1
                 for (int o = 0; o < 4; ++o) {
@@ -1136,7 +1140,8 @@ gemm_half_tma_2cta_kernel(const __grid_constant__ CUtensorMap mA, const __grid_c
         const int r = quarter * 32 + lane;                // row within the CTA's 128 == TMEM lane
         const int sw = r & 7;
         int it = 0;
-        for (int tile = pair; tile < total_tiles; tile += n_pairs, ++it) {
+        for (int tl = pair; tl < total_tiles; tl += n_pairs, ++it) {
+            const int tile = rev ? total_tiles - 1 - tl : tl;
             const int a = it & 1;
             const uint32_t aph = (it >> 1) & 1;
             const int n0 = (tile % n_tiles) * BN;
@@ -1449,7 +1454,7 @@ __global__ void __launch_bounds__(GEMM_LN4_THREADS, 1)
 gemm_ln_half_c4_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mW /*128-row boxes*/,
                        const __grid_constant__ CUtensorMap mH /* residual in / output out: [M,512] fp16, 128-row x 64-col boxes */,
                        int M, int K, const float* __restrict__ bias, const float* __restrict__ gamma,
-                       const float* __restrict__ beta) {
+                       const float* __restrict__ beta, int rev) {
     using Cfg = GemmLn4Cfg;
     constexpr int STAGES = Cfg::STAGES, T_BYTES = Cfg::T_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES;
     constexpr uint32_t IDESC = ptx::make_idesc_f16(256, 256);
@@ -1503,7 +1508,8 @@ gemm_ln_half_c4_kernel(const __grid_constant__ CUtensorMap mA, const __grid_cons
     if (warp == 0) {
         if (lane == 0) {                                 // ===== TMA producer (every CTA) =====
             int s = 0; uint32_t ph = 0;
-            for (int tile = cl; tile < m_tiles; tile += n_cl) {
+            for (int tl = cl; tl < m_tiles; tl += n_cl) {
+                const int tile = rev ? m_tiles - 1 - tl : tl;
                 const int m0 = tile * 256 + (int)prank * 128;
                 const int n0 = (int)chalf * 256 + (int)prank * 128;
                 for (int kb = 0; kb < kb_total; ++kb) {
@@ -1546,17 +1552,19 @@ gemm_ln_half_c4_kernel(const __grid_constant__ CUtensorMap mA, const __grid_cons
                 ptx::mbar_arrive_expect_tx(&res_full[b], T_BYTES);
                 ptx::tma_load_2d(res_smem + b * T_BYTES, &mH, &res_full[b], gx + b * 64, tile * 256 + (int)prank * 128);
             };
-            if (cl < m_tiles) { load_box(0, cl); load_box(2, cl); load_box(1, cl); load_box(3, cl); }
+            auto tmap = [&](int tl) { return rev ? m_tiles - 1 - tl : tl; };
+            if (cl < m_tiles) { const int t0 = tmap(cl); load_box(0, t0); load_box(2, t0); load_box(1, t0); load_box(3, t0); }
             int it = 0;
-            for (int tile = cl; tile < m_tiles; tile += n_cl, ++it) {
-                const int nxt = tile + n_cl;
+            for (int tl = cl; tl < m_tiles; tl += n_cl, ++it) {
+                const int tile = tmap(tl);
+                const int nxt = tl + n_cl;
 #pragma unroll 1
                 for (int o = 0; o < 4; ++o) {
                     const int b = (o & 1) * 2 + (o >> 1);              // 0, 2, 1, 3: both column halves' first box first
                     ptx::mbar_wait(&out_ready[b], it & 1);
                     ptx::tma_store_2d(&mH, res_smem + b * T_BYTES, gx + b * 64, tile * 256 + (int)prank * 128);
                     ptx::tma_store_commit();
-                    if (nxt < m_tiles) { ptx::tma_store_wait_read(); load_box(b, nxt); }
+                    if (nxt < m_tiles) { ptx::tma_store_wait_read(); load_box(b, tmap(nxt)); }
                 }
             }
             ptx::tma_store_wait_all();
