@@ -12,9 +12,10 @@ from ._capi import EgoEgoError, PRECISE_ALL_FP16  # noqa: F401
 from .diffusion import CondGaussianDiffusion, TransformerDiffusionModel  # noqa: F401
 from .motion_data import MotionDataStub  # noqa: F401
 from .stage1 import HeadFormer, HeadNormalFormer  # noqa: F401
-from .eval_metrics import compute_metrics_for_smpl, compute_metrics_batch  # noqa: F401
+from .eval_metrics import (compute_metrics_for_smpl, compute_metrics_batch, determine_floor_height_and_contacts,  # noqa: F401
+                           floor_contacts_batch)
 from .trainer_glue import prep_head_condition_mask, prep_padding_mask, full_body_gen_cond_head_pose_sliding_window  # noqa: F401
 
 __all__ = ["PRECISE_ALL_FP16", "CondGaussianDiffusion", "TransformerDiffusionModel", "MotionDataStub", "EgoEgoError", "HeadFormer", "HeadNormalFormer",
-           "compute_metrics_for_smpl", "compute_metrics_batch",
+           "compute_metrics_for_smpl", "compute_metrics_batch", "determine_floor_height_and_contacts", "floor_contacts_batch",
            "prep_head_condition_mask", "prep_padding_mask", "full_body_gen_cond_head_pose_sliding_window"]

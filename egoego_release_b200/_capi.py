@@ -16,7 +16,7 @@ EXPORTS = [
     "egoego_seqnet_launch_count", "egoego_va2rot", "egoego_rescale_slam", "egoego_slam_features", "egoego_apply_floor_normal",
     "egoego_rigid_apply", "egoego_resnet18_create", "egoego_resnet18_destroy", "egoego_resnet18_set_tensor", "egoego_resnet18_commit",
     "egoego_resnet18_forward", "egoego_resnet18_launch_count", "egoego_train_step", "egoego_train_get_grad", "egoego_update_tensor_device", "egoego_train_get_grads", "egoego_update_tensors_device",
-    "egoego_tensors_checksum",
+    "egoego_tensors_checksum", "egoego_floor_contacts",
 ]
 
 ENGINE_TCGEN05, ENGINE_SIMT = 0, 1
@@ -82,6 +82,7 @@ def lib():
     L.egoego_tail_condition.argtypes = [vp, vp, vp, i32, i32, vp, vp]
     L.egoego_eval_metrics.argtypes = [i32, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp]
     L.egoego_launch_count.argtypes = [vp]
+    L.egoego_floor_contacts.argtypes = [i32, vp, i32, i32, i32, vp, vp, vp, vp]
     L.egoego_tensors_checksum.argtypes = [i32, i32, vp, vp, vp, vp]
     L.egoego_launch_count.restype = i64
     f32 = C.c_float

@@ -9,6 +9,7 @@
 #include "kernels_simt.cuh"
 #include "postprocess.cuh"
 #include "metrics.cuh"
+#include "floor.cuh"
 #include "engine_tc.cuh"
 
 namespace egoego {
@@ -75,6 +76,12 @@ struct egoego_ctx {
 namespace egoego {
 
 void train_release(egoego_ctx* c);     // frees the training workspace of a handle (defined with the training step below)
+
+// largest opt-in dynamic shared-memory size requested so far per device (function attributes are per device)
+struct PerDeviceMax {
+    size_t v[64] = {};
+    bool raise(int dev, size_t want) { dev &= 63; if (want <= v[dev]) return false; v[dev] = want; return true; }
+};
 
 static inline dim3 grid1d(long long n, int bs) { return dim3((unsigned)((n + bs - 1) / bs)); }
 // ddpm_update_kernel: x = quads (4 consecutive elements) of one window in blocks of 256 threads, y = window
@@ -712,6 +719,23 @@ int egoego_eval_metrics(int device, const float* gt_quat, const float* gt_jpos, 
     EG_CHECK(device >= 0 && device < ndev, "bad device ordinal");
     EG_CUDA(cudaSetDevice(device));
     eval_metrics_kernel<<<B, MET_WARPS * 32, 0, (cudaStream_t)stream_v>>>(gt_quat, gt_jpos, gt_floor, pred_quat, pred_jpos, pred_floor, T, out);
+    EG_CUDA(cudaGetLastError());
+    return 0;
+}
+
+
+int egoego_floor_contacts(int device, const float* jpos, int B, int T, int fps, float* floor_out, float* contacts, int* discard, void* stream_v) {
+    EG_CHECK(jpos && floor_out, "null argument");
+    EG_CHECK(B >= 1 && T >= 2 && T <= FLOOR_MAX_T, "floor height needs B >= 1 sequences of 2 <= T <= 2048 frames");
+    int ndev = 0;
+    EG_CHECK(cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0, "no CUDA device: libegoego_b200 has no CPU fallback");
+    EG_CHECK(device >= 0 && device < ndev, "bad device ordinal");
+    EG_CUDA(cudaSetDevice(device));
+    const size_t smem = floor_smem_bytes(T);
+    static PerDeviceMax smem_set;
+    if (smem > 48 * 1024 && smem_set.raise(device, smem))
+        EG_CUDA(cudaFuncSetAttribute(floor_contacts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    floor_contacts_kernel<<<B, FLOOR_THREADS, smem, (cudaStream_t)stream_v>>>(jpos, T, fps, floor_out, contacts, discard);
     EG_CUDA(cudaGetLastError());
     return 0;
 }

@@ -68,3 +68,31 @@ def compute_metrics_for_smpl(gt_global_quat, gt_global_jpos, gt_floor_height, pr
     for i in range(single.numel()):
         res["jpe_%d" % i] = float(single[i])
     return res
+
+
+def floor_contacts_batch(body_joint_seq, fps: int = 30):
+    """[B,T,22,3] CUDA tensor of global joint positions (z up) -> (offset_floor_height [B] float32, contacts [B,T,22] float32,
+    discard [B] bool), all on the device, one kernel launch (csrc/floor.cuh)."""
+    dev = body_joint_seq.device if torch.is_tensor(body_joint_seq) else torch.device("cpu")
+    j = _dev32(body_joint_seq, dev, "body_joint_seq")
+    if j.dim() != 4 or j.shape[2:] != (22, 3):
+        raise ValueError("joint positions must be [B,T,22,3]")
+    B, T = j.shape[:2]
+    if T < 2:
+        raise IndexError("need at least 2 frames (the reference indexes the last frame difference)")
+    fl = torch.empty(B, device=dev, dtype=torch.float32)
+    ct = torch.empty(B, T, 22, device=dev, dtype=torch.float32)
+    dc = torch.empty(B, device=dev, dtype=torch.int32)
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    check(lib().egoego_floor_contacts(dev.index or 0, j.data_ptr(), B, T, int(fps), fl.data_ptr(), ct.data_ptr(), dc.data_ptr(), stream))
+    return fl, ct, dc.bool()
+
+
+def determine_floor_height_and_contacts(body_joint_seq, fps):
+    """Reference signature (utils/data_utils/process_amass_dataset.py:160): ONE sequence N x 22 x 3 (CUDA tensor; the reference
+    takes the numpy copy of it) -> (offset_floor_height: float, contacts: N x 22 numpy array, discard_seq: bool)."""
+    if not torch.is_tensor(body_joint_seq) or body_joint_seq.device.type != "cuda":
+        raise EgoEgoError("determine_floor_height_and_contacts: egoego_release_b200 evaluates on the GPU only (no CPU fallback); "
+                          "pass the CUDA tensor instead of its .cpu().numpy() copy")
+    fl, ct, dc = floor_contacts_batch(body_joint_seq[None], fps)
+    return float(fl[0]), ct[0].double().cpu().numpy(), bool(dc[0])

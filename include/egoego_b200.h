@@ -176,6 +176,15 @@ int  egoego_eval_metrics(int device, const float* gt_quat_dev, const float* gt_j
                          const float* pred_quat_dev, const float* pred_jpos_dev, const float* pred_floor_dev,
                          int B, int T, float* out_dev, void* stream);
 
+/* Floor height and contact labels of B sequences -- determine_floor_height_and_contacts,
+ * utils/data_utils/process_amass_dataset.py:160-317 (+ detect_joint_contact :319-328), the host-side numpy + sklearn.DBSCAN step
+ * eval_stage2.py:131,189 / eval_egoego.py:331,395 run before every metrics call.  jpos_dev[B,T,22,3] global joint positions
+ * (z up), 2 <= T <= 2048.  floor_out_dev[B] = the function's first return value (smallest cluster median of the static toe
+ * heights minus 0.01; 0 when no toe sample is static); contacts_out_dev[B,T,22] (nullable) its second (1.0 / 0.0 on feet, toes,
+ * hands, knees); discard_out_dev[B] int32 (nullable) its third (terrain heuristic).  No handle: needs only the device. */
+int  egoego_floor_contacts(int device, const float* jpos_dev, int B, int T, int fps, float* floor_out_dev, float* contacts_out_dev,
+                           int32_t* discard_out_dev, void* stream);
+
 /* ---- Stage-1 networks (shipped configuration --input_of_feats) ---------------------------------
  * A "sequence net" is the reference's Decoder used WITHOUT a leading token (egoego/model/transformer_module.py:172-226,
  * use_full_attention=True, row padding mask) followed by up to two MLP heads (egoego/model/mlp.py:4-27: ReLU after every
