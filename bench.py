@@ -251,6 +251,17 @@ def next_rows(dev, B, T, pk):
                      "note": "fp32 CUDA-core sequence nets (d_model 256, 2 layers), eager launches incl. host glue; forward_for_eval of "
                              "HeadNormalFormer includes its device->host copy of the trajectory for the xy alignment callable",
                      "headformer_launches_per_call": (hf.launch_count() - l0) // 13}
+    # the same two networks as stock PyTorch on this GPU (oracle port of the reference modules' op sequence, fp32 eager)
+    try:
+        ph = {k: v.to(dev) for k, v in S.init_params(7, S.CFG_HEAD).items()}
+        pn = {k: v.to(dev) for k, v in S.init_params(8, S.CFG_NORMAL).items()}
+        q0 = head_pose[:, 0, 3:]
+        ot = slam_trans - slam_trans[:, 0:1]
+        with torch.no_grad():
+            out["stage1"]["torch_eager_headformer_forward_for_eval_us"] = timed(lambda: S.headformer_forward_for_eval(ph, feats, slam_trans, q0), 10) * 1e3
+            out["stage1"]["torch_eager_headnormalformer_forward_us"] = timed(lambda: S.headnormal_forward(pn, slam_rot, ot), 10) * 1e3
+    except Exception as ex:
+        out["stage1"]["torch_eager_error"] = repr(ex)[:200]
     # HeadNet with raw optical flow: ResNet-18 encoder (1.814 GFLOP per 224 x 224 frame, multiply-add = 2) on the demo's 139 frames
     try:
         opt2 = argparse.Namespace(**{**vars(opt), "input_of_feats": False})
@@ -259,49 +270,28 @@ def next_rows(dev, B, T, pk):
         hf2 = hf2.to(dev)
         flow = torch.randn(1, 139, 224, 224, 2, device=dev)
         ms = timed(lambda: hf2._input_features({"of": flow}), 5)
-        out["resnet18_encoder"] = {"frames": 139, "ms_per_call": ms, "frames_per_s": 139 / (ms * 1e-3), "bound": "fp32 CUDA cores",
+        out["resnet18_encoder"] = {"frames": 139, "ms_per_call": ms, "frames_per_s": 139 / (ms * 1e-3),
                                    "achieved": 139 * 1.814e9 / (ms * 1e-3) / 1e12, "unit": "TFLOP/s",
-                                   "note": "implicit-GEMM conv kernels with folded BatchNorm and fused bias + residual + ReLU epilogues (csrc/resnet.cu)"}
+                                   "note": "convolutions with folded BatchNorm and fused bias + residual + ReLU epilogues (csrc/resnet.cu)"}
+        # the reference's ResNet class as stock PyTorch on this GPU: cuDNN convolutions, fp32 with and without TF32 (torch's default
+        # for convolutions is allow_tf32 = True -- the reference's real numerics on a GPU)
+        pr = {k: v.to(dev) for k, v in S.init_resnet_params(9).items()}
+        xin = S.flow_to_cnn_input(flow.cpu()).to(dev)
+        for tag, tf32 in (("cudnn_tf32_default", True), ("cudnn_fp32", False)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            with torch.no_grad():
+                mt = timed(lambda: S.resnet18_forward(pr, xin), 5)
+            out["resnet18_encoder"]["torch_" + tag] = {"ms_per_call": mt, "frames_per_s": 139 / (mt * 1e-3)}
+        torch.backends.cudnn.allow_tf32 = True
     except Exception as ex:
         out["resnet18_encoder"] = {"error": repr(ex)[:200]}
-    # training step (BASELINE config 5 shape per GPU: batch 32, T = 120): loss + backward through the CUDA library vs the same
-    # objective in PyTorch eager autograd on this GPU (oracle port of the reference's op sequence, fp32; dropout off in both)
+    # training step (BASELINE configs[4] shape per GPU: batch 32, T = 120, train() mode with dropout): the reference Trainer's
+    # loop body -- autocast(fp16) + GradScaler + Adam -- through egoego_train_step vs the reference's op sequence as stock PyTorch
+    # under the same autocast on this GPU (tools/train_bench.py; the 8-GPU DDP run of the same tool is profiles/r2*_train_ddp*.json)
     try:
-        from oracle import egoego_oracle as O
-        from oracle import training as TR
-        Bt = 32
-        mt = E.CondGaussianDiffusion(d_feats=198, d_model=512, n_dec_layers=4, n_head=4, d_k=256, d_v=256, max_timesteps=121,
-                                     out_dim=198, timesteps=1000, objective="pred_x0", loss_type="l1", max_batch=Bt)
-        mt.load_state_dict(O.init_params(0), strict=False)
-        mt = mt.to(dev)
-        x0 = torch.rand(Bt, T, 198, device=dev) * 2 - 1
-        cmk = O.prep_head_condition_mask(x0.shape).to(dev)
-        pmk = (torch.arange(T + 1, device=dev)[None, :] < torch.randint(31, T + 2, (Bt, 1), device=dev))[:, None, :]
-        tt = torch.randint(0, 1000, (Bt,), device=dev)
-
-        opt_o = torch.optim.SGD(mt.parameters(), lr=1e-6)
-
-        def ours():
-            opt_o.zero_grad(set_to_none=True)
-            mt.p_losses(x0, cmk, tt, padding_mask=pmk).backward()
-            opt_o.step()                                  # weights change every step: the engine's copies are refreshed device-to-device
-
-        ms_ours = timed(ours, 5)
-        pg = {k: (v.to(dev).requires_grad_(True) if v.is_floating_point() and "position_vec" not in k else v.to(dev)) for k, v in O.init_params(0).items()}
-        sched = {k: v.to(dev) for k, v in O.make_schedule(1000).items()}
-
-        opt_t = torch.optim.SGD([v for v in pg.values() if v.requires_grad], lr=1e-6)
-
-        def torch_eager():
-            opt_t.zero_grad(set_to_none=True)
-            TR.p_losses(pg, sched, x0, cmk, tt, torch.randn_like(x0), torch.randn_like(x0), pmk).backward()
-            opt_t.step()
-
-        ms_torch = timed(torch_eager, 5)
-        out["train_step"] = {"batch": Bt, "ms_per_step_ours": ms_ours, "ms_per_step_torch_eager_fp32": ms_torch,
-                             "samples_per_s_ours": Bt / (ms_ours * 1e-3), "samples_per_s_torch_eager_fp32": Bt / (ms_torch * 1e-3),
-                             "note": "forward + loss + backward + torch.optim.SGD step; ours = egoego_train_step (tensor-core split products, fp32-grade) "
-                                     "through loss.backward(); torch = oracle op sequence with autograd, fp32, on the same GPU"}
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import train_bench
+        out["train_step"] = train_bench.run_arms(dev, 32, T, steps=10, warmup=3)
     except Exception as ex:
         out["train_step"] = {"error": repr(ex)[:300]}
     return out
@@ -337,6 +327,79 @@ def config1_latency(dev, T):
         out[f"B{Bw}_T{T}_N{N}"] = {"ms_per_sample_call": ms, "windows_per_s": Bw * 1e3 / ms, "us_per_diffusion_step": ms * 1e3 / N,
                                    "precise_last_steps": m.precise_last_steps()}
         del m
+    return out
+
+
+def all_split_ms(dev, xs, cm, B, T, N):
+    """One sample() of the bench workload with precise_last_steps = N (all 3-term split), CUDA events."""
+    import torch
+    import egoego_release_b200 as E
+    from oracle import egoego_oracle as O
+    m = E.CondGaussianDiffusion(d_feats=198, d_model=512, n_dec_layers=4, n_head=4, d_k=256, d_v=256, max_timesteps=121,
+                                out_dim=198, timesteps=N, objective="pred_x0", loss_type="l1", max_batch=B, precise_last_steps=N)
+    m.load_state_dict(O.init_params(0), strict=False)
+    m = m.to(dev)
+    n_warm = max(1, min(20, N // 10))
+    mw = E.CondGaussianDiffusion(d_feats=198, d_model=512, n_dec_layers=4, n_head=4, d_k=256, d_v=256, max_timesteps=121,
+                                 out_dim=198, timesteps=n_warm, objective="pred_x0", loss_type="l1", max_batch=B, precise_last_steps=n_warm)
+    mw.load_state_dict(O.init_params(0), strict=False)
+    mw.to(dev).sample(xs, cm)                                  # warm-up: a short all-split loop (kernels, planes, graph capture path)
+    del mw
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    m.sample(xs, cm)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1)
+
+
+def pipeline_config4(dev):
+    """BASELINE configs[3]: the full EgoEgo pipeline on one B200 -- HeadNet + GravityNet on a 139-frame sequence (the demo's
+    length) -> stage-2 sliding-window diffusion (2 windows x 1000 steps, sample batch 32 = scripts/test_egoego_pipeline.sh) ->
+    FK -> floor height + evaluation metrics, end to end through pipeline.run_egoego; CUDA events around whole calls."""
+    import argparse
+    import numpy as np
+    import torch
+    import egoego_release_b200 as E
+    from egoego_release_b200 import pipeline as P
+    from oracle import egoego_oracle as O
+    from oracle import stage1 as S
+    out = {}
+    opt = argparse.Namespace(window=60, n_dec_layers=2, n_head=4, d_k=256, d_v=256, d_model=256, input_of_feats=True, freeze_of_cnn=True,
+                             dist_scale=10.0, normal_window=120, normal_n_dec_layers=2, normal_n_head=4, normal_d_k=256, normal_d_v=256,
+                             normal_d_model=256)
+    hf = E.HeadFormer(opt, dev); hf.load_state_dict(S.init_params(7, S.CFG_HEAD)); hf = hf.to(dev)
+    gn = E.HeadNormalFormer(opt, dev, eval_whole_pipeline=True); gn.load_state_dict(S.init_params(8, S.CFG_NORMAL)); gn = gn.to(dev)
+    feats, head_pose, slam_trans, slam_rot = S.synth_stage1_inputs(77, 139)
+    data = {"of": feats, "aligned_slam_trans": slam_trans, "head_pose": head_pose, "ori_slam_trans": slam_trans * 1.9, "ori_slam_rot_mat": slam_rot}
+    ident = lambda est, ref: np.eye(3)
+    for bs in (1, 32):
+        dm = E.CondGaussianDiffusion(d_feats=198, d_model=512, n_dec_layers=4, n_head=4, d_k=256, d_v=256, max_timesteps=121,
+                                     out_dim=198, timesteps=1000, objective="pred_x0", loss_type="l1", max_batch=bs)
+        dm.load_state_dict(O.init_params(0), strict=False)
+        dm = dm.to(dev)
+        ds = E.MotionDataStub().bind(dm)
+
+        def run():
+            o = P.run_egoego(hf, gn, dm, ds, data, sample_bs=bs, xy_align=ident)
+            fl, _, _ = E.floor_contacts_batch(o["global_jpos"], 30)
+            return E.compute_metrics_batch(o["global_jrot"], o["global_jpos"], fl, o["global_jrot"], o["global_jpos"], fl)
+
+        run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res = run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        out[f"sample_bs{bs}"] = {"ms_per_sequence_call": ms, "sequences_per_s": bs * 1e3 / ms, "frames": 139, "windows_per_sequence": 2,
+                                 "diffusion_steps_per_window": 1000, "finite": bool(torch.isfinite(res).all())}
+        del dm
+    out["note"] = ("stage 1 (HeadFormer + HeadNormalFormer forward_for_eval) -> sliding-window stage 2 -> FK -> floor height -> metrics, all on "
+                   "the device; the two windows of a sequence are sequentially dependent (10-frame overlap in-painting), so the time is "
+                   "2 x 1000 diffusion steps at batch = sample_bs")
     return out
 
 
@@ -380,7 +443,8 @@ def main():
     T, D, N, B = 120, 198, a.diffusion_steps, a.batch
     cfg = {"workload": f"configs[1]: batch={B}/GPU T={T} {N}-step sampling, random-init denoiser (oracle.init_params seed 0), "
                        "synthetic head-pose cond", "windows_per_gpu": B, "T": T, "diffusion_steps": N, "d_feats": D,
-           "parallelism": f"windows sharded over {world} GPU(s), one all-gather of finished windows" if world > 1 else "single GPU",
+           "parallelism": (f"configs[2]: windows sharded over {world} GPU(s), per-rank post-processing, ONE all-gather of the generated SMPL "
+                           "parameters (69 floats per frame)") if world > 1 else "single GPU",
            "l2": "per-step working set (fp16/fp32 activation planes for 256 windows, >1 GB) exceeds the 126 MB L2; no flush"}
 
     if a.impl == "reference":
@@ -416,19 +480,24 @@ def main():
     cm_h = cm_h[rank * B:(rank + 1) * B].contiguous().pin_memory()
     out_h = torch.empty(B, T, D).pin_memory()
     xs, cm = xs_h.to(dev), cm_h.to(dev)
-    gathered = torch.empty(world * B, T, D, device=dev) if world > 1 else None
+    # configs[2]: the ONE collective of the path gathers the generated SMPL parameters (22 local axis-angles + root translation =
+    # 69 floats per frame, 8.5 MB per rank at 256 windows) -- each rank post-processes its own windows first (parallel.smpl_post_fn)
+    from egoego_release_b200 import parallel as PAR
+    ds = E.MotionDataStub().bind(m)
+    post = PAR.smpl_post_fn(m, ds)
+    gathered = torch.empty(world * B, T, 69, device=dev) if world > 1 else None
     torch.manual_seed(1234)
 
     def step_device():
         y = m.sample(xs, cm)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, y)
+            dist.all_gather_into_tensor(gathered, post(y, rank * B).contiguous())
         return y
 
     def step_host():
         y = m.sample_host(xs_h, cm_h, out=out_h)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, y.to(dev, non_blocking=True))
+            dist.all_gather_into_tensor(gathered, post(y.to(dev, non_blocking=True), rank * B).contiguous())
         return y
 
     def timed(fn, k):
@@ -458,6 +527,29 @@ def main():
     step_host()                                          # warm the host path (staging buffers)
     ms_h, _ = timed(step_host, a.steps)
 
+    # shard invariance, checked on the device at every N > 1 ("8-GPU output == 1-GPU output window for window"):
+    # with a fixed seed, rank 0 re-samples the LAST rank's shard (same conditioning, Philox streams keyed by the global window id)
+    # and compares its SMPL parameters bit for bit with what the all-gather delivered from that rank.
+    shard_check = None
+    if world > 1:
+        torch.manual_seed(777)                           # every rank draws the same sampling seed from torch's generator
+        y = m.sample(xs, cm)
+        dist.all_gather_into_tensor(gathered, post(y, rank * B).contiguous())
+        xs_all, cm_all = synth_inputs(B * world, T)
+        if rank == 0:
+            r = world - 1
+            m.window_offset = r * B
+            torch.manual_seed(777)
+            y_r = m.sample(xs_all[r * B:(r + 1) * B].to(dev), cm_all[r * B:(r + 1) * B].to(dev))
+            m.window_offset = 0
+            mine = post(y_r, r * B)
+            theirs = gathered[r * B:(r + 1) * B]
+            import hashlib
+            shard_check = {"rank_checked": r, "bit_identical": bool(torch.equal(mine, theirs)),
+                           "max_abs_diff": float((mine - theirs).abs().max()),
+                           "sha256_gathered_smpl_params": hashlib.sha256(gathered.cpu().numpy().tobytes()).hexdigest()[:16],
+                           "gathered_bytes_per_rank": int(B * T * 69 * 4)}
+        dist.barrier()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -482,7 +574,7 @@ def main():
                   if K_prec < N else "fp16 hi/lo 3-term split (fp32 accumulate)") if eng == "tcgen05" else "f32",
         "data": "synthetic", "config": dict(cfg, engine=eng, precise_last_steps=K_prec, weight_sets=W_sets),
         "e2e": {"value": e2e, "unit": "windows/s", "h2d_bytes_per_step": 2 * B * T * D * 4 * world, "d2h_bytes_per_step": B * T * D * 4 * world},
-        "gpu_launches": int(launches), "clocks": clocks,
+        "gpu_launches": int(launches), "clocks": clocks, "shard_check": shard_check,
         "path_roofline": {"bound": "tensor", "achieved": path_tflops, "peak": peak, "unit": "TFLOP/s", "frac": path_tflops / peak,
                           "scope": "whole sampling path: algorithmic 2.8507 TFLOP per 1000-step window / wall time, per GPU"},
     }
@@ -509,6 +601,38 @@ def main():
                              "peak": pk_burst if bound == "tensor" else hbm, "unit": "TFLOP/s" if bound == "tensor" else "GB/s",
                              "frac": ach / (pk_burst if bound == "tensor" else hbm),
                              "algorithmic_flops_per_launch": fl, "algorithmic_bytes_per_launch": by}
+        # once-per-sample kernels of the path (not in the step sum): post-processing + FK on the finished windows
+        try:
+            ds_k = E.MotionDataStub().bind(m)
+            yk = torch.rand(B, T, D, device=dev) * 2 - 1
+
+            def _timed(fn, iters=20):
+                for _ in range(3):
+                    fn()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(iters):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
+                return e0.elapsed_time(e1) / iters
+
+            aa_k, root_k, _h = m.postprocess(ds_k, yk, None)
+            post_ms = _timed(lambda: m.postprocess(ds_k, yk, None, with_fk=True))
+            fk_ms = _timed(lambda: m.fk_smpl(ds_k, root_k.reshape(-1, 3), aa_k.reshape(-1, 22, 3)))
+            post_by = B * T * (198 + 66 + 3 + 3 + 66 + 88) * 4          # read x; write aa, root, head, jpos, gquat
+            fk_by = B * T * (3 + 66 + 88 + 66) * 4
+            line["once_per_sample_kernels"] = {
+                "postprocess_fk": {"kernel": "postprocess_kernel (convert_model_res_to_data + FK)", "ms_per_launch": post_ms, "bound": "hbm",
+                                   "algorithmic_bytes_per_launch": post_by, "achieved": post_by / (post_ms * 1e-3) / 1e9, "peak": hbm,
+                                   "unit": "GB/s", "frac": post_by / (post_ms * 1e-3) / 1e9 / hbm},
+                "fk_smpl": {"kernel": "fk_smpl_kernel", "ms_per_launch": fk_ms, "bound": "hbm", "algorithmic_bytes_per_launch": fk_by,
+                            "achieved": fk_by / (fk_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s", "frac": fk_by / (fk_ms * 1e-3) / 1e9 / hbm},
+                "note": "one launch per sample() call (1000 diffusion steps); transcendental-heavy (6D -> matrix -> quaternion -> axis-angle per joint), "
+                        "issue-bound at a few % of the HBM roofline (profiles/r2a_postprocess_kernel_full.md) and < 0.02 % of a sample() call"}
+        except Exception as ex:
+            line["once_per_sample_kernels"] = {"error": repr(ex)[:200]}
         tot = sum(k["launches_per_step"] * k["ms_per_launch"] for k in kernels.values())
         for k in kernels.values():
             k["share_of_step"] = k["launches_per_step"] * k["ms_per_launch"] / tot
@@ -533,11 +657,21 @@ def main():
         line["parity_vs_reference"] = parity_vs_reference(m, dev, N)
     else:
         line["roofline"] = dict(line["path_roofline"], traffic=None, peak_source=pk_src)
+    if world == 1 and eng == "tcgen05":
+        # the same workload with EVERY step in the fp32-grade 3-term split format (precise_last_steps = N): what the path costs
+        # without the step-adaptive precision policy
+        try:
+            ms_split = all_split_ms(dev, xs, cm, B, T, N)
+            line["all_split_windows_per_s"] = B / (ms_split * 1e-3)
+            line["all_split_ms_per_step"] = ms_split
+        except Exception as ex:
+            line["all_split_windows_per_s"] = {"error": repr(ex)[:200]}
     if world == 1:                                       # reported baseline: rank 0 at N = 1 only
         line["cpu_baseline"] = cpu_baseline(32, T, N, a.cpu_seconds)
         try:
             line["next_rows"] = next_rows(dev, B, T, pk)
             line["single_window_latency"] = config1_latency(dev, T)
+            line["pipeline_config4"] = pipeline_config4(dev)
         except Exception as ex:   # reported extras only; never masks the headline numbers
             line["next_rows"] = {"error": repr(ex)[:200]}
     if world == 1 and not os.environ.get("EGOEGO_BENCH_SKIP_TORCH"):

@@ -16,7 +16,7 @@ EXPORTS = [
     "egoego_seqnet_launch_count", "egoego_va2rot", "egoego_rescale_slam", "egoego_slam_features", "egoego_apply_floor_normal",
     "egoego_rigid_apply", "egoego_resnet18_create", "egoego_resnet18_destroy", "egoego_resnet18_set_tensor", "egoego_resnet18_commit",
     "egoego_resnet18_forward", "egoego_resnet18_launch_count", "egoego_train_step", "egoego_train_get_grad", "egoego_update_tensor_device", "egoego_train_get_grads", "egoego_update_tensors_device",
-    "egoego_tensors_checksum", "egoego_floor_contacts",
+    "egoego_tensors_checksum", "egoego_floor_contacts", "egoego_train_set_dropout",
 ]
 
 ENGINE_TCGEN05, ENGINE_SIMT = 0, 1
@@ -101,6 +101,7 @@ def lib():
     L.egoego_rigid_apply.argtypes = [i32, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp]
     L.egoego_train_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp]
     L.egoego_train_get_grad.argtypes = [vp, C.c_char_p, vp, i64, vp]
+    L.egoego_train_set_dropout.argtypes = [vp, C.c_double, u64]
     L.egoego_update_tensor_device.argtypes = [vp, C.c_char_p, vp, i64, vp]
     L.egoego_train_get_grads.argtypes = [vp, i32, vp, vp, vp, vp]
     L.egoego_update_tensors_device.argtypes = [vp, i32, vp, vp, vp, vp]

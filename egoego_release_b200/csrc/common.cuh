@@ -155,6 +155,32 @@ __device__ __forceinline__ float noise_at(const NoiseSrc& ns, int draw, int w, l
     return r == 0 ? n.x : (r == 1 ? n.y : (r == 2 ? n.z : n.w));
 }
 
+// ---------------------------------------------------------------------------------------------
+// Dropout of the training step (nn.Dropout(0.1) on the attention probabilities, the fc output and the FFN output of every
+// DecoderLayer: egoego/model/transformer_module.py:53,59,84,92,105,113).  torch's own dropout stream cannot be reproduced, so
+// the masks are a counter-based function of (seed, stream, element index) that the CPU oracle restates bit for bit
+// (oracle/training.py: dropout_keep): Philox4x32-10 with counter (index / 4, index >> 34, stream, 'DROP') and key = seed; element
+// i keeps its value iff component i % 4 of the output is below thresh = floor((1 - p) 2^32).  Kept values are scaled by 1 / (1 - p).
+//   stream = 4 * layer + site;  site 0: attention probabilities, index ((b H + h) 128 + query) 128 + key
+//                               site 1 / 2: fc / FFN output, index (b 128 + token) 512 + channel      (token 0 = time token)
+// ---------------------------------------------------------------------------------------------
+struct DropCfg {
+    unsigned long long seed;
+    uint32_t thresh;      // keep iff philox word < thresh
+    float scale;          // 1 / (1 - p)
+    int on;               // 0: identity (eval mode)
+};
+__device__ __forceinline__ uint4 drop_words(const DropCfg& d, uint32_t stream, unsigned long long quad) {
+    return philox4x32_10(make_uint4((uint32_t)quad, (uint32_t)(quad >> 32), stream, 0x44524f50u),
+                         make_uint2((uint32_t)d.seed, (uint32_t)(d.seed >> 32)));
+}
+__device__ __forceinline__ float drop_factor(const DropCfg& d, uint32_t stream, unsigned long long idx) {
+    if (!d.on) return 1.0f;
+    const uint4 r = drop_words(d, stream, idx >> 2);
+    const uint32_t w = (idx & 3) == 0 ? r.x : ((idx & 3) == 1 ? r.y : ((idx & 3) == 2 ? r.z : r.w));
+    return w < d.thresh ? d.scale : 0.0f;
+}
+
 // bf16 hi/lo split of an fp32 value: v ~= hi + lo with |v - hi - lo| <= 2^-17 |v| over the whole fp32 exponent range
 // (training-step products: gradients are far below the fp16 range).
 __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {

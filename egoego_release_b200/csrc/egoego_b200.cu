@@ -70,6 +70,8 @@ struct egoego_ctx {
     bool fuse_ddpm = false;                // EGOEGO_FUSE_DDPM=1: DDPM update in linear_out's epilogue.  Opt-in: measured 90 us vs 17.6 + 32.9 us for
                                            // linear_out + ddpm_update_kernel at B = 256 (8 epilogue warps per SM are too few for the Philox work)
     int64_t launches = 0;
+    double drop_p = 0.0;                   // training step: dropout probability (0 = eval-mode semantics) and mask seed
+    unsigned long long drop_seed = 0;      // (egoego_train_set_dropout)
     std::unique_ptr<TcEngine> tc;
 };
 
@@ -871,7 +873,7 @@ struct TrainWs {
     int B = 0;                                   // windows the workspace is sized for
     std::vector<DevBuf> Hin;                     // NL + 1 residual streams [M,512]
     std::vector<TrainLayerBufs> L;
-    DevBuf OUT, dOUT, dH, dH1, dY, dF, dO, dQKV, Ta, Tb, WT, gp, bp, loss, Tmp, temb_b, iota;
+    DevBuf OUT, dOUT, dH, dH1, dY, dZ, dF, dO, dQKV, Ta, Tb, WT, gp, bp, loss, Tmp, temb_b, iota;
     std::map<std::string, DevBuf> grads;         // fused / padded gradient buffers
 };
 
@@ -883,7 +885,7 @@ void train_release(egoego_ctx* c) {
     if (TrainWs* w = it->second.get()) {
         for (auto& h : w->Hin) h.release();
         for (auto& l : w->L) for (DevBuf* b : {&l.QKV, &l.O, &l.Y1, &l.st1, &l.H1, &l.F, &l.Y2, &l.st2}) b->release();
-        for (DevBuf* b : {&w->OUT, &w->dOUT, &w->dH, &w->dH1, &w->dY, &w->dF, &w->dO, &w->dQKV, &w->Ta, &w->Tb, &w->WT, &w->gp, &w->bp, &w->loss, &w->Tmp, &w->temb_b, &w->iota}) b->release();
+        for (DevBuf* b : {&w->OUT, &w->dOUT, &w->dH, &w->dH1, &w->dY, &w->dZ, &w->dF, &w->dO, &w->dQKV, &w->Ta, &w->Tb, &w->WT, &w->gp, &w->bp, &w->loss, &w->Tmp, &w->temb_b, &w->iota}) b->release();
         for (auto& kv : w->grads) kv.second.release();
     }
     g_train.erase(it);
@@ -944,7 +946,7 @@ static int train_alloc(egoego_ctx* c, TrainWs* w, int B) {
     for (auto& l : w->L)
         if (l.QKV.alloc(M * nq * 4) || l.O.alloc(M * hd * 4) || l.Y1.alloc(M * d * 4) || l.st1.alloc(M * 2 * 4) || l.H1.alloc(M * d * 4) ||
             l.F.alloc(M * d * 4) || l.Y2.alloc(M * d * 4) || l.st2.alloc(M * 2 * 4)) return 1;
-    if (w->OUT.alloc(M * 256 * 4) || w->dOUT.alloc(M * 256 * 4) || w->dH.alloc(M * d * 4) || w->dH1.alloc(M * d * 4) || w->dY.alloc(M * d * 4) ||
+    if (w->OUT.alloc(M * 256 * 4) || w->dOUT.alloc(M * 256 * 4) || w->dH.alloc(M * d * 4) || w->dH1.alloc(M * d * 4) || w->dY.alloc(M * d * 4) || w->dZ.alloc(M * d * 4) ||
         w->dF.alloc(M * d * 4) || w->dO.alloc(M * hd * 4) || w->dQKV.alloc(M * nq * 4) || w->Ta.alloc(nq * M * 4) || w->Tb.alloc(hd * M * 4) ||
         w->WT.alloc(nq * d * 4) || w->gp.alloc(M * d * 4) || w->bp.alloc(M * d * 4) || w->loss.alloc(8) || w->Tmp.alloc(M * nq * 4) || w->temb_b.alloc((size_t)B * d * 4) ||
         w->iota.alloc((size_t)B * 8)) return 1;
@@ -988,6 +990,9 @@ int egoego_train_step(egoego_handle c, const float* x_start, const float* cond_m
     const long long nel = (long long)B * T * D;
     const float qs = 1.0f / sqrtf((float)dk);
     auto nblk = [](long long n) { return (unsigned)((n + 255) / 256); };
+    // dropout of the three sites per layer (common.cuh: DropCfg); p = 0 keeps the eval-mode semantics
+    DropCfg drop{c->drop_seed, 0u, 1.0f, 0};
+    if (c->drop_p > 0.0) { drop.on = 1; drop.thresh = (uint32_t)((1.0 - c->drop_p) * 4294967296.0); drop.scale = (float)(1.0 / (1.0 - c->drop_p)); }
 
     // the batch's own timestep embeddings from the CURRENT time_mlp weights; the start epilogue indexes them by window (the
     // sampler's full table stays stale until the next egoego_commit_weights -- training handles never sample)
@@ -1004,11 +1009,11 @@ int egoego_train_step(egoego_handle c, const float* x_start, const float* cond_m
         TrainLayerBufs& b = w->L[l];
         float* Hin = w->Hin[l].as<float>();
         if (tr_gemm(w, Hin, d, W.wqkv.as<float>(), d, M, nq, d, EpiBiasScale{b.QKV.as<float>(), nq, W.bqkv.as<float>(), hd, qs}, s)) return 1;
-        attention_simt_kernel<false><<<B * H, 256, ATT_SIMT_SMEM, s>>>(b.QKV.as<float>(), nq, b.O.as<float>(), nullptr, nullptr, hd, H, L);
-        if (tr_gemm(w, b.O.as<float>(), hd, W.fc_w.as<float>(), hd, M, d, hd, EpiBiasResid{b.Y1.as<float>(), d, W.fc_b.as<float>(), Hin}, s)) return 1;
+        attention_simt_kernel<false><<<B * H, 256, ATT_SIMT_SMEM, s>>>(b.QKV.as<float>(), nq, b.O.as<float>(), nullptr, nullptr, hd, H, L, drop, 4u * l + 0u);
+        if (tr_gemm(w, b.O.as<float>(), hd, W.fc_w.as<float>(), hd, M, d, hd, EpiBiasDropResid{b.Y1.as<float>(), d, W.fc_b.as<float>(), Hin, drop, 4u * l + 1u}, s)) return 1;
         tr_ln_fwd_kernel<<<M / 8, 256, 0, s>>>(b.Y1.as<float>(), b.H1.as<float>(), b.st1.as<float>(), W.ln1_g.as<float>(), W.ln1_b.as<float>(), pmask, T, M);
         if (tr_gemm(w, b.H1.as<float>(), d, W.w1.as<float>(), d, M, d, d, EpiBiasRelu{b.F.as<float>(), d, W.b1.as<float>()}, s)) return 1;
-        if (tr_gemm(w, b.F.as<float>(), d, W.w2.as<float>(), d, M, d, d, EpiBiasResid{b.Y2.as<float>(), d, W.b2.as<float>(), b.H1.as<float>()}, s)) return 1;
+        if (tr_gemm(w, b.F.as<float>(), d, W.w2.as<float>(), d, M, d, d, EpiBiasDropResid{b.Y2.as<float>(), d, W.b2.as<float>(), b.H1.as<float>(), drop, 4u * l + 2u}, s)) return 1;
         tr_ln_fwd_kernel<<<M / 8, 256, 0, s>>>(b.Y2.as<float>(), w->Hin[l + 1].as<float>(), b.st2.as<float>(), W.ln2_g.as<float>(), W.ln2_b.as<float>(), pmask, T, M);
     }
     if (tr_gemm(w, w->Hin[c->NL].as<float>(), d, c->out_w.as<float>(), d, M, D, d, EpiPlainBias{w->OUT.as<float>(), 256, c->out_b.as<float>()}, s)) return 1;
@@ -1034,10 +1039,13 @@ int egoego_train_step(egoego_handle c, const float* x_start, const float* cond_m
         tr_ln_bwd_kernel<<<M / 8, 256, 0, s>>>(dH, b.Y2.as<float>(), b.st2.as<float>(), W.ln2_g.as<float>(), pmask, T, M, dY, w->gp.as<float>(), w->bp.as<float>());
         tr_colsum(w->gp.as<float>(), M, d, d, G(p + "ln2_g"), s);
         tr_colsum(w->bp.as<float>(), M, d, d, G(p + "ln2_b"), s);
-        tr_colsum(dY, M, d, d, G(p + "b2"), s);
-        if (tr_weight_grad(w, dY, d, d, b.F.as<float>(), d, d, M, G(p + "w2"), d, s)) return 1;
+        // through dropout(F W2^T + b2): dZ = dY o mask (the residual branch below keeps dY)
+        const float* dZ2 = dY;
+        if (drop.on) { tr_dropout_bwd_kernel<<<nblk((long long)M * d / 4), 256, 0, s>>>(dY, w->dZ.as<float>(), (long long)M * d, drop, 4u * l + 2u); dZ2 = w->dZ.as<float>(); }
+        tr_colsum(dZ2, M, d, d, G(p + "b2"), s);
+        if (tr_weight_grad(w, dZ2, d, d, b.F.as<float>(), d, d, M, G(p + "w2"), d, s)) return 1;
         tr_transpose(W.w2.as<float>(), d, d, d, WT, d, s);
-        if (tr_gemm_plain(dY, d, WT, d, M, d, d, dF, d, false, s)) return 1;
+        if (tr_gemm_plain(dZ2, d, WT, d, M, d, d, dF, d, false, s)) return 1;
         tr_relu_bwd_kernel<<<nblk((long long)M * d), 256, 0, s>>>(dF, b.F.as<float>(), (long long)M * d);
         tr_colsum(dF, M, d, d, G(p + "b1"), s);
         if (tr_weight_grad(w, dF, d, d, b.H1.as<float>(), d, d, M, G(p + "w1"), d, s)) return 1;
@@ -1048,11 +1056,13 @@ int egoego_train_step(egoego_handle c, const float* x_start, const float* cond_m
         tr_ln_bwd_kernel<<<M / 8, 256, 0, s>>>(dH1, b.Y1.as<float>(), b.st1.as<float>(), W.ln1_g.as<float>(), pmask, T, M, dY, w->gp.as<float>(), w->bp.as<float>());
         tr_colsum(w->gp.as<float>(), M, d, d, G(p + "ln1_g"), s);
         tr_colsum(w->bp.as<float>(), M, d, d, G(p + "ln1_b"), s);
-        tr_colsum(dY, M, d, d, G(p + "fc_b"), s);
-        if (tr_weight_grad(w, dY, d, d, b.O.as<float>(), hd, hd, M, G(p + "fc_w"), hd, s)) return 1;
+        const float* dZ1 = dY;                                                              // through dropout(O Wfc^T + bfc)
+        if (drop.on) { tr_dropout_bwd_kernel<<<nblk((long long)M * d / 4), 256, 0, s>>>(dY, w->dZ.as<float>(), (long long)M * d, drop, 4u * l + 1u); dZ1 = w->dZ.as<float>(); }
+        tr_colsum(dZ1, M, d, d, G(p + "fc_b"), s);
+        if (tr_weight_grad(w, dZ1, d, d, b.O.as<float>(), hd, hd, M, G(p + "fc_w"), hd, s)) return 1;
         tr_transpose(W.fc_w.as<float>(), d, hd, hd, WT, d, s);                              // Wfc^T [1024, 512]
-        if (tr_gemm_plain(dY, d, WT, d, M, hd, d, w->dO.as<float>(), hd, false, s)) return 1;
-        attention_bwd_simt_kernel<<<B * H, 256, ATT_BWD_SMEM, s>>>(b.QKV.as<float>(), nq, w->dO.as<float>(), hd, w->dQKV.as<float>(), H, L, qs);
+        if (tr_gemm_plain(dZ1, d, WT, d, M, hd, d, w->dO.as<float>(), hd, false, s)) return 1;
+        attention_bwd_simt_kernel<<<B * H, 256, ATT_BWD_SMEM, s>>>(b.QKV.as<float>(), nq, w->dO.as<float>(), hd, w->dQKV.as<float>(), H, L, qs, drop, 4u * l + 0u);
         tr_colsum(w->dQKV.as<float>(), M, nq, nq, G(p + "bqkv"), s);
         if (tr_weight_grad(w, w->dQKV.as<float>(), nq, nq, w->Hin[l].as<float>(), d, d, M, G(p + "wqkv"), d, s)) return 1;
         EG_CUDA(cudaMemcpyAsync(dH, dY, (size_t)M * d * 4, cudaMemcpyDeviceToDevice, s));       // residual branch
@@ -1069,6 +1079,15 @@ int egoego_train_step(egoego_handle c, const float* x_start, const float* cond_m
     tr_loss_finish_kernel<<<1, 1, 0, s>>>(w->loss.as<double>(), loss_out);      // fp64 accumulator -> the caller's float, no host round trip
     c->launches += 40 * c->NL + 20;
     EG_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// Dropout of the following egoego_train_step calls: p = 0 -> identity (the reference's eval() mode), p = 0.1 -> nn.Dropout(0.1) at
+// the three sites of every DecoderLayer with Philox masks keyed by `seed` (common.cuh: DropCfg; oracle/training.py restates them).
+int egoego_train_set_dropout(egoego_handle c, double p, uint64_t seed) {
+    EG_CHECK(c, "null handle");
+    EG_CHECK(p >= 0.0 && p < 1.0, "dropout probability must be in [0, 1)");
+    c->drop_p = p; c->drop_seed = seed;
     return 0;
 }
 

@@ -43,6 +43,8 @@ static int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t co
     return 0;
 }
 
+int tc_make_map16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) { return make_map(m, base, rows, cols, box_rows); }
+
 struct Plane {                 // a 16-bit hi/lo pair (fp16 in the sampler, bf16 in tc_gemm_f32) with its TMA maps
     __nv_bfloat16 *hi = nullptr, *lo = nullptr;
     CUtensorMap mhi, mlo;
@@ -171,7 +173,7 @@ struct TcImpl {
     bool fuse_ln = true;                        // EGOEGO_FUSE_LN=0 keeps GEMM + LayerNorm separate in the fp16 format too
     bool attn_tc = true;                        // EGOEGO_ATTN=simt selects the fp32 CUDA-core attention (bisecting)
     bool attn_v2 = true;                        // fp16 steps: software-pipelined attention_half_kernel (EGOEGO_ATTN=v1: attention_tc_kernel<FMT_HALF>)
-    int ln4_clusters = 0;                       // co-resident clusters of 4 for gemm_ln_half_c4_kernel (0 = use the full-row pair kernel)
+    int ln4_clusters = 0;                       // co-resident clusters of 4 for gemm_ln_half_c4_kernel (0 = unfused GEMM + LayerNorm)
     // L2 zig-zag (EGOEGO_ZIGZAG, default on): consecutive kernels of a step walk the windows in OPPOSITE directions, so a
     // kernel starts with the rows its producer wrote last -- the part of its input that is still in the 126 MB L2 (the
     // per-kernel working set at 256 windows is 100-270 MB, so a same-direction walk misses everywhere).
@@ -244,25 +246,6 @@ static int launch_gemm_2cta(TcImpl* I, const Plane& A, const Plane& W, int M, in
     return 0;
 }
 
-// A-resident CTA-pair GEMM (fp16 format, K = 512): groups of 3 N tiles per 256-row block
-template <class Epi>
-static int launch_gemm_ares(TcImpl* I, const Plane& A, const Plane& W, int M, int N, const Epi& epi, cudaStream_t s) {
-    constexpr int G = 3;
-    using Cfg = GemmAresCfg<G>;
-    static PerDeviceOnce attr_once;          // opt-in shared-memory size is a per-device function attribute
-    auto kern = gemm_ares_half_2cta_kernel<G, Epi>;
-    if (attr_once.need()) {
-        EG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    }
-    EG_CHECK(M % 256 == 0 && (N / 256) % G == 0 && N % 256 == 0, "A-resident gemm shape not tile-aligned");
-    const int items = (M / 256) * ((N / 256) / G);
-    int pairs = I->sms / 2;
-    if (items < pairs) pairs = items;
-    LaunchCfg lc(2 * pairs, GEMM_THREADS, Cfg::SMEM_BYTES, s, 2);
-    EG_CUDA(cudaLaunchKernelEx(&lc.cfg, kern, A.m16, W.m16_128, M, N, epi));
-    return 0;
-}
-
 // CTA-pair fp16 GEMM with the TMA-store epilogue (default for the fp16-format QKV projection and FFN w_1;
 // EGOEGO_TMA_EPI=0 keeps the transposing epilogue)
 static bool use_tma_epi() {
@@ -284,38 +267,6 @@ static int launch_gemm_tma_epi(TcImpl* I, const Plane& A, const Plane& W, int M,
     LaunchCfg lc(2 * pairs, GEMM_TMAEPI_THREADS, GemmTmaEpiCfg::SMEM_BYTES, s, 2);
     EG_CUDA(cudaLaunchKernelEx(&lc.cfg, kern, A.m16, W.m16_128, M, N, K, bias, epi, I->next_dir()));
     return 0;
-}
-
-// A-resident variant of the above for K = 512 and N a multiple of 3 * 256 (the QKV projection).  Opt-in (EGOEGO_QKV_ARES=1):
-// measured 104.6 us vs 100.8 us for the streaming kernel on the same box -- with the TMA epilogue the projection is bound by
-// the tensor pipe at short K (cuBLAS fp16 on this shape: 94.5 us), not by operand traffic.
-template <class Epi>
-static int launch_gemm_ares_tma(TcImpl* I, const Plane& A, const Plane& W, int M, int N, const float* bias, const Epi& epi, cudaStream_t s) {
-    constexpr int G = 3;
-    using Cfg = GemmAresTmaCfg<G>;
-    static PerDeviceOnce attr_once;          // opt-in shared-memory size is a per-device function attribute
-    auto kern = gemm_ares_tma_2cta_kernel<G, Epi>;
-    if (attr_once.need()) {
-        EG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    }
-    EG_CHECK(M % 256 == 0 && N % (256 * G) == 0, "A-resident TMA-epilogue gemm shape not tile-aligned");
-    const int items = (M / 256) * ((N / 256) / G);
-    int pairs = I->sms / 2;
-    if (items < pairs) pairs = items;
-    LaunchCfg lc(2 * pairs, GEMM_TMAEPI_THREADS, Cfg::SMEM_BYTES, s, 2);
-    EG_CUDA(cudaLaunchKernelEx(&lc.cfg, kern, A.m16, W.m16_128, M, N, bias, epi));
-    return 0;
-}
-static bool use_ares_tma() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("EGOEGO_QKV_ARES"); v = (e && e[0] == '1') ? 1 : 0; }
-    return v == 1;
-}
-
-static bool use_ares() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("EGOEGO_QKV_ARES"); v = (e && e[0] == 'o') ? 1 : 0; }   // "old": A-resident kernel with the transposing epilogue (profiles/r1k)
-    return v == 1;
 }
 
 template <int FMT, class Epi>
@@ -369,13 +320,10 @@ int TcEngine::init(const TcWeights& w, cudaStream_t) {
     {
         const char* fl = getenv("EGOEGO_FUSE_LN");
         I->fuse_ln = !(fl && fl[0] == '0');
-        EG_CUDA(cudaFuncSetAttribute(gemm_ln_half_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmLnCfg::SMEM_BYTES));
-        EG_CUDA(cudaFuncSetAttribute(gemm_ln_half_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmLn2Cfg::SMEM_BYTES));
         EG_CUDA(cudaFuncSetAttribute(gemm_ln_half_c4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmLn4Cfg::SMEM_BYTES));
-        // column-split cluster-of-4 kernel (default; EGOEGO_LN=2cta keeps the full-row pair kernel): launch exactly as many
-        // clusters as can be co-resident (GPC boundaries may leave a few SMs without a complete cluster)
-        const char* lm = getenv("EGOEGO_LN");
-        if (!(lm && strcmp(lm, "2cta") == 0) && use_2cta()) {
+        // column-split cluster-of-4 kernel: launch exactly as many clusters as can be co-resident (GPC boundaries may leave a few
+        // SMs without a complete cluster); if the query fails the fp16 steps fall back to the unfused GEMM + LayerNorm kernels
+        if (use_2cta()) {
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3((I->sms / 4) * 4); cfg.blockDim = dim3(GEMM_LN4_THREADS); cfg.dynamicSmemBytes = GemmLn4Cfg::SMEM_BYTES;
             cudaLaunchAttribute at[1];
@@ -388,6 +336,7 @@ int TcEngine::init(const TcWeights& w, cudaStream_t) {
             else
                 cudaGetLastError();
         }
+        if (I->ln4_clusters == 0) I->fuse_ln = false;
     }
     { const char* zz = getenv("EGOEGO_ZIGZAG"); I->zigzag = !(zz && zz[0] == '0'); }
     const char* am = getenv("EGOEGO_ATTN");
@@ -451,28 +400,14 @@ int TcEngine::launches_per_denoiser(int fmt) const {
     return 2 + (fused ? 5 : 7) * impl_->w.NL;
 }
 
-// fp16 full-row GEMM + residual + bias + LayerNorm (gemm_ln_half_kernel); out = Hs fp16 plane (in place)
+// fp16 GEMM + residual + bias + LayerNorm (gemm_ln_half_c4_kernel); residual in / output out = the Hs fp16 plane (in place)
 static int launch_gemm_ln(TcImpl* I, const Plane& A, const Plane& W, int M, int K, const float* bias, const float* g,
                           const float* b, cudaStream_t s) {
-    EG_CHECK(M % GEMM_BM == 0 && K % GEMM_BK == 0, "fused-LN gemm shape not tile-aligned");
-    if (I->ln4_clusters > 0 && M % 256 == 0) {
-        const int tiles = M / 256;
-        const int clusters = tiles < I->ln4_clusters ? tiles : I->ln4_clusters;
-        LaunchCfg lc(4 * clusters, GEMM_LN4_THREADS, GemmLn4Cfg::SMEM_BYTES, s, 4);
-        EG_CUDA(cudaLaunchKernelEx(&lc.cfg, gemm_ln_half_c4_kernel, A.m16_128, W.m16_128, I->Hs.m16_128, M, K, bias, g, b, I->next_dir()));
-        return 0;
-    }
-    if (use_2cta() && M % 256 == 0) {
-        const int tiles = M / 256;
-        int pairs = I->sms / 2;
-        if (tiles < pairs) pairs = tiles;
-        LaunchCfg lc(2 * pairs, GEMM_THREADS, GemmLn2Cfg::SMEM_BYTES, s, 2);
-        EG_CUDA(cudaLaunchKernelEx(&lc.cfg, gemm_ln_half_2cta_kernel, A.m16, W.m16_128, M, K, bias, g, b, (const __nv_bfloat16*)I->Hs.h16, I->Hs.h16));
-        return 0;
-    }
-    const int tiles = M / GEMM_BM;
-    LaunchCfg lc(tiles < I->sms ? tiles : I->sms, GEMM_THREADS, GemmLnCfg::SMEM_BYTES, s);
-    EG_CUDA(cudaLaunchKernelEx(&lc.cfg, gemm_ln_half_kernel, A.m16, W.m16, M, K, bias, g, b, (const __nv_bfloat16*)I->Hs.h16, I->Hs.h16));
+    EG_CHECK(M % 256 == 0 && K % GEMM_BK == 0 && I->ln4_clusters > 0, "fused-LN gemm shape not tile-aligned");
+    const int tiles = M / 256;
+    const int clusters = tiles < I->ln4_clusters ? tiles : I->ln4_clusters;
+    LaunchCfg lc(4 * clusters, GEMM_LN4_THREADS, GemmLn4Cfg::SMEM_BYTES, s, 4);
+    EG_CUDA(cudaLaunchKernelEx(&lc.cfg, gemm_ln_half_c4_kernel, A.m16_128, W.m16_128, I->Hs.m16_128, M, K, bias, g, b, I->next_dir()));
     return 0;
 }
 
@@ -572,13 +507,7 @@ static int denoiser_impl(TcImpl* I, int B, int T, TSrc ts, const float* pmask, f
                 TcEpiQKVPlanes<FMT> eq{{}, {}, I->Qp.hi, I->Qp.lo, I->Kp.hi, I->Kp.lo, I->VT.hi, I->VT.lo, W.bqkv, H, 1.0f / sqrtf((float)dk)};
                 if (FMT == FMT_HALF && use_tma_epi() && Mg % 256 == 0) {
                     TmaEpiQKV te{I->Qp.m16_128, I->Kp.m16_128, I->VT.m16_128, H, 1.0f / sqrtf((float)dk)};
-                    if (use_ares_tma() && d == 512 && nqkv % 768 == 0) {
-                        if (launch_gemm_ares_tma(I, I->Hs, W.wqkv, Mg, nqkv, W.bqkv, te, s)) return 1;
-                    } else {
-                        if (launch_gemm_tma_epi(I, I->Hs, W.wqkv, Mg, nqkv, d, W.bqkv, te, s)) return 1;
-                    }
-                } else if (FMT == FMT_HALF && use_2cta() && use_ares() && d == 512 && (nqkv / 256) % 3 == 0) {
-                    if (launch_gemm_ares(I, I->Hs, W.wqkv, Mg, nqkv, eq, s)) return 1;
+                    if (launch_gemm_tma_epi(I, I->Hs, W.wqkv, Mg, nqkv, d, W.bqkv, te, s)) return 1;
                 } else {
                     if (gemm<FMT>(I, I->Hs, W.wqkv, Mg, nqkv, d, eq, s)) return 1;
                 }

@@ -2,6 +2,7 @@
 // Implementation: engine_tc.cu (tcgen05 + TMA GEMMs with a 3-term fp16 hi/lo split).
 #pragma once
 #include <vector>
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include "common.cuh"
 
@@ -56,6 +57,9 @@ private:
 // C must have ceil(M / 256) * 256 rows of ldc floats; columns [0, n_valid) are written (n_valid % 4 == 0 <= ldc).
 int tc_gemm_f32(const float* A, int lda, const float* W, int ldw, int M, int N, int K, float* C, int ldc, int n_valid, int accumulate,
                 cudaStream_t s);
+
+// TMA map of a row-major 16-bit [rows, cols] tensor with [box_rows, 64]-element boxes and the 128-byte swizzle (engine_tc.cu)
+int tc_make_map16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows);
 
 // Host-side rounding of fp32 weights to the r-th of R dithered fp16 copies (bit patterns), exactly as the weight commit does.
 void dither_weights_host(const float* w, long long n, int r, int R, unsigned short* out);

@@ -52,6 +52,14 @@ struct EpiBiasResid {        // fc / w_2: acc + bias + residual (pre-LayerNorm)
     }
 };
 
+struct EpiBiasDropResid {    // training: dropout(acc + bias) + residual (transformer_module.py:92,113)
+    float* C; int ldc; const float* bias; const float* res; DropCfg drop; uint32_t stream;
+    __device__ __forceinline__ void operator()(int row, int col, float acc) const {
+        const float v = (acc + bias[col]) * drop_factor(drop, stream, (unsigned long long)row * 512ull + (unsigned long long)col);
+        C[(long long)row * ldc + col] = v + res[(long long)row * ldc + col];
+    }
+};
+
 struct EpiOut {              // linear_out on tokens 1..T -> compact [B,T,d_feats]
     float* out; int d_feats; const float* bias; int T;
     __device__ __forceinline__ void operator()(int row, int col, float acc) const {
@@ -128,7 +136,8 @@ template <bool SPLIT>
 __global__ void __launch_bounds__(256) attention_simt_kernel(const float* __restrict__ QKV, int ldq,
                                                              float* __restrict__ O, __nv_bfloat16* __restrict__ Ohi,
                                                              __nv_bfloat16* __restrict__ Olo, int ldo,
-                                                             int n_head, int L) {
+                                                             int n_head, int L, DropCfg drop = DropCfg{0, 0, 1.0f, 0},
+                                                             uint32_t drop_stream = 0) {
     constexpr int DH = 256;
     extern __shared__ __align__(16) float sm[];
     float (*S)[129] = reinterpret_cast<float (*)[129]>(sm);
@@ -206,6 +215,16 @@ __global__ void __launch_bounds__(256) attention_simt_kernel(const float* __rest
         }
     }
     __syncthreads();
+    if (drop.on) {   // training: dropout on the attention probabilities (transformer_module.py:84), one Philox call per 4 keys
+        const unsigned long long base = (unsigned long long)blockIdx.x * 128ull * 128ull;     // blockIdx.x = b * H + h
+        for (int q = tid; q < 128 * 32; q += 256) {
+            const int r = q >> 5, c4 = (q & 31) * 4;
+            const uint4 wd = drop_words(drop, drop_stream, (base + (unsigned long long)r * 128ull + c4) >> 2);
+            S[r][c4 + 0] *= wd.x < drop.thresh ? drop.scale : 0.f; S[r][c4 + 1] *= wd.y < drop.thresh ? drop.scale : 0.f;
+            S[r][c4 + 2] *= wd.z < drop.thresh ? drop.scale : 0.f; S[r][c4 + 3] *= wd.w < drop.thresh ? drop.scale : 0.f;
+        }
+        __syncthreads();
+    }
     {   // phase 3: O[128][256] = P[128][128] V[128][256]; thread owns 8 rows x 16 cols
         float (*Vs)[256] = reinterpret_cast<float (*)[256]>(tile);
         float acc[8][16];

@@ -3,9 +3,10 @@
 // [T, 224, 224, 2] optical flow padded with a zero third channel.  Inference only (eval(): BatchNorm uses running statistics).
 //
 // One kernel per convolution: implicit GEMM over NHWC activations (C[M = N*Ho*Wo, Cout] = im2col(X) * W^T, gathered on the
-// fly -- no materialised im2col), 128 x 128 x 16 fp32 tiles like sgemm_tn_kernel, with BatchNorm folded into the weights at
-// commit and bias + residual add + ReLU fused in the epilogue.  fp32 CUDA cores: the encoder is the secondary part of the
-// path (1.8 GFLOP per frame once per sequence, against 2.85 TFLOP per window in stage 2).
+// fly), BatchNorm folded into the weights at commit and bias + residual add + ReLU fused in the epilogue.  Two engines:
+//   default            conv_tc_kernel (conv_tcgen05.cuh): tcgen05 tensor cores, fp16 operands (the operand rounding of the reference's
+//                      own cuDNN-TF32 GPU path), fp32 accumulate, fp32 residual stream
+//   EGOEGO_RESNET=simt conv_igemm_kernel below: fp32 CUDA cores, 128 x 128 x 16 tiles (validation / bisecting)
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -16,6 +17,8 @@
 
 #include "common.cuh"
 #include "kernels_simt.cuh"
+#include "engine_tc.cuh"
+#include "conv_tcgen05.cuh"
 
 namespace egoego {
 
@@ -146,6 +149,14 @@ static __global__ void rn_avgpool_kernel(const float* __restrict__ X, float* __r
     Y[i] = s / (float)HW;
 }
 
+static __global__ void rn_half_to_float_kernel(const __half* __restrict__ x, float* __restrict__ y, long long n) {
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= n) return;
+    const uint2 v = *reinterpret_cast<const uint2*>(x + i);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+    *reinterpret_cast<float4*>(y + i) = make_float4(a.x, a.y, b.x, b.y);
+}
+
 struct RnEpiFc { float* out; int ld; const float* bias; int n_rows;
     __device__ __forceinline__ void operator()(int row, int col, float acc) const { if (row < n_rows) out[(long long)row * ld + col] = acc + bias[col]; } };
 
@@ -157,7 +168,12 @@ struct RnBuf {
     ~RnBuf() { release(); }
 };
 
-struct RnConv { ConvDesc d; int K, Kpad; RnBuf w, b; };
+struct RnConv {
+    ConvDesc d; int K, Kpad; RnBuf w, b;
+    // tensor-core path: fp16 weights [Cout, K64] (K padded to 64; the stem uses k = tap * 4 + channel, K64 = 256), their TMA map
+    __half* w16 = nullptr; CUtensorMap map; int K64 = 0, BN = 64;
+    ~RnConv() { if (w16) cudaFree(w16); }
+};
 
 }  // namespace egoego
 
@@ -170,6 +186,11 @@ struct egoego_resnet_ctx {
     std::vector<std::unique_ptr<RnConv>> convs;      // conv1, then per block: conv1, conv2, (downsample)
     RnBuf fc_w, fc_b, buf[4], in4, pooled;
     int64_t launches = 0;
+    bool tc = true;                                  // tensor-core engine (EGOEGO_RESNET=simt: fp32 CUDA cores)
+    __half* a16[3] = {nullptr, nullptr, nullptr};    // fp16 NHWC activations (conv inputs)
+    __half* col16 = nullptr;                         // stem im2col [chunk * 112 * 112, 256]
+    float* r32[3] = {nullptr, nullptr, nullptr};     // fp32 residual stream (block outputs / downsample outputs)
+    ~egoego_resnet_ctx() { for (auto* p : a16) if (p) cudaFree(p); for (auto* p : r32) if (p) cudaFree(p); if (col16) cudaFree(col16); }
 };
 
 static const int RN_PLANES[4] = {64, 128, 256, 512};
@@ -194,6 +215,45 @@ static int rn_fold(egoego_resnet_ctx* c, const std::string& conv, const std::str
                     wf[(size_t)o * out->Kpad + (ky * kw + kx) * Cin_pad + ci] = (float)((double)(*w)[(((size_t)o * Cin + ci) * kh + ky) * kw + kx] * s);
     }
     if (out->w.upload(wf) || out->b.upload(bf)) return 1;
+    if (c->tc) {                                     // fp16 copy with K padded to 64 (same (ky, kx, ci) order) + TMA map of BN-row boxes
+        out->K64 = ((out->K + 63) / 64) * 64;
+        out->BN = Cout >= 256 ? 256 : Cout;
+        std::vector<__half> wh((size_t)Cout * out->K64, __float2half(0.f));
+        for (int o = 0; o < Cout; ++o)
+            for (int k = 0; k < out->K; ++k) wh[(size_t)o * out->K64 + k] = __float2half_rn(wf[(size_t)o * out->Kpad + k]);
+        if (out->w16) { cudaFree(out->w16); out->w16 = nullptr; }
+        EG_CUDA(cudaMalloc(&out->w16, wh.size() * 2));
+        EG_CUDA(cudaMemcpy(out->w16, wh.data(), wh.size() * 2, cudaMemcpyHostToDevice));
+        if (tc_make_map16(&out->map, out->w16, Cout, out->K64, out->BN)) return 1;
+    }
+    return 0;
+}
+
+// tensor-core convolution launch: x16 NHWC fp16 (or the stem's im2col matrix with `dense` = its row length), optional fp32 identity,
+// outputs fp32 and / or fp16
+static int rn_conv_tc(egoego_resnet_ctx* c, const RnConv& cv, const __half* x16, int dense_k, const float* resid, float* y32, __half* y16,
+                      bool relu, int N, cudaStream_t s) {
+    const int M = N * cv.d.Hout * cv.d.Wout;
+    ConvTcDesc d{cv.d.Cin, cv.d.Cout, cv.d.kh, cv.d.kw, cv.d.stride, cv.d.pad, cv.d.Hin, cv.d.Win, cv.d.Hout, cv.d.Wout};
+    if (dense_k) d = ConvTcDesc{dense_k, cv.d.Cout, 1, 1, 1, 0, cv.d.Hout, cv.d.Wout, cv.d.Hout, cv.d.Wout};
+    EG_CHECK(d.Cin % 64 == 0 && cv.K64 % 64 == 0, "tensor-core convolution needs Cin % 64 == 0");
+    ConvTcEpi e{{}, cv.b.p, resid, y32, y16, cv.d.Cout, M, relu ? 1 : 0};
+    const int tiles = ((M + 127) / 128) * ((cv.d.Cout + cv.BN - 1) / cv.BN);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    const int grid = tiles < sms ? tiles : sms;
+    static bool attr[64] = {};
+    if (!attr[c->device & 63]) {
+        EG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<64>::SMEM_BYTES));
+        EG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<128>::SMEM_BYTES));
+        EG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<256>::SMEM_BYTES));
+        attr[c->device & 63] = true;
+    }
+    const int kb = cv.K64 / 64;
+    if (cv.BN == 64)       conv_tc_kernel<64><<<grid, CONV_TC_THREADS, ConvTcCfg<64>::SMEM_BYTES, s>>>(x16, cv.map, d, M, kb, e);
+    else if (cv.BN == 128) conv_tc_kernel<128><<<grid, CONV_TC_THREADS, ConvTcCfg<128>::SMEM_BYTES, s>>>(x16, cv.map, d, M, kb, e);
+    else                   conv_tc_kernel<256><<<grid, CONV_TC_THREADS, ConvTcCfg<256>::SMEM_BYTES, s>>>(x16, cv.map, d, M, kb, e);
+    c->launches++;
     return 0;
 }
 
@@ -221,6 +281,8 @@ int egoego_resnet18_create(int device, int out_dim, egoego_resnet* out) {
     EG_CHECK(device >= 0 && device < ndev, "bad device ordinal");
     egoego_resnet_ctx* c = new egoego_resnet_ctx();
     c->device = device; c->out_dim = out_dim;
+    { const char* e = getenv("EGOEGO_RESNET"); c->tc = !(e && strcmp(e, "simt") == 0); }
+    if (c->tc) c->chunk = 160;                       // whole demo sequences (139 frames) in one pass: ~2.3 GB of activation buffers
     *out = c;
     return 0;
 }
@@ -266,8 +328,17 @@ int egoego_resnet18_commit(egoego_resnet c) {
     EG_CHECK((int64_t)fw->second.size() == (int64_t)c->out_dim * 512 && (int)fb->second.size() == c->out_dim, "bad fc size");
     if (c->fc_w.upload(fw->second) || c->fc_b.upload(fb->second)) return 1;
     const size_t act = (size_t)c->chunk * 112 * 112 * 64;                 // largest activation of a chunk (stem output)
-    for (auto& b : c->buf) if (b.alloc(act)) return 1;
-    if (c->in4.alloc((size_t)c->chunk * 224 * 224 * 4) || c->pooled.alloc((size_t)128 * 512)) return 1;
+    if (c->tc) {
+        const size_t act56 = (size_t)c->chunk * 56 * 56 * 64;              // largest activation after the max-pool
+        for (auto*& p : c->a16) { if (p) cudaFree(p); EG_CUDA(cudaMalloc(&p, act * 2)); }
+        for (auto*& p : c->r32) { if (p) cudaFree(p); EG_CUDA(cudaMalloc(&p, act56 * 4)); }
+        if (c->col16) cudaFree(c->col16);
+        EG_CUDA(cudaMalloc(&c->col16, (size_t)c->chunk * 112 * 112 * 256 * 2));
+        if (c->pooled.alloc((size_t)256 * 512)) return 1;
+    } else {
+        for (auto& b : c->buf) if (b.alloc(act)) return 1;
+        if (c->in4.alloc((size_t)c->chunk * 224 * 224 * 4) || c->pooled.alloc((size_t)128 * 512)) return 1;
+    }
     c->committed = true;
     return 0;
 }
@@ -277,7 +348,47 @@ int egoego_resnet18_forward(egoego_resnet c, const float* flow, int N, float* fe
     EG_CHECK(c->committed, "egoego_resnet18_commit has not been called");
     EG_CUDA(cudaSetDevice(c->device));
     cudaStream_t s = (cudaStream_t)stream_v;
-    for (int f0 = 0; f0 < N; f0 += c->chunk) {
+    for (int f0 = 0; c->tc && f0 < N; f0 += c->chunk) {
+        const int n = std::min(c->chunk, N - f0);
+        size_t ci = 0;
+        // stem: explicit im2col (3 input channels) -> tensor-core GEMM + BN + ReLU -> fp16 [n,112,112,64] -> max-pool -> [n,56,56,64]
+        const long long M1 = (long long)n * 112 * 112;
+        rn_stem_im2col_kernel<<<(unsigned)((M1 * 64 + 255) / 256), 256, 0, s>>>(flow + (long long)f0 * 224 * 224 * 2, c->col16, M1);
+        if (rn_conv_tc(c, *c->convs[ci++], c->col16, 256, nullptr, nullptr, c->a16[1], true, n, s)) return 1;
+        {
+            const long long tot = (long long)n * 56 * 56 * 8;
+            rn_maxpool16_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(c->a16[1], c->a16[0], n, 112, 112, 64, 56, 56);
+        }
+        // residual stream: x16 (conv input, fp16) + x32 (identity, fp32; the max-pool output is exactly representable in fp16, so the
+        // first block's identity is read from x16 through a one-off conversion below)
+        __half *x16 = c->a16[0], *y16 = c->a16[1], *t16 = c->a16[2];
+        float *x32 = c->r32[0], *y32 = c->r32[1], *d32 = c->r32[2];
+        {
+            const long long tot = (long long)n * 56 * 56 * 64;
+            rn_half_to_float_kernel<<<(unsigned)((tot / 4 + 255) / 256), 256, 0, s>>>(x16, x32, tot);
+        }
+        int inpl = 64;
+        for (int L = 0; L < 4; ++L)
+            for (int blk = 0; blk < 2; ++blk) {
+                const int planes = RN_PLANES[L], stride = (L > 0 && blk == 0) ? 2 : 1;
+                const RnConv& c1 = *c->convs[ci++];
+                const RnConv& c2 = *c->convs[ci++];
+                const float* identity = x32;
+                if (rn_conv_tc(c, c1, x16, 0, nullptr, nullptr, t16, true, n, s)) return 1;              // conv1 + BN + ReLU -> fp16
+                if (stride != 1 || inpl != planes) {
+                    if (rn_conv_tc(c, *c->convs[ci++], x16, 0, nullptr, d32, nullptr, false, n, s)) return 1;   // downsample conv + BN -> fp32
+                    identity = d32;
+                }
+                if (rn_conv_tc(c, c2, t16, 0, identity, y32, y16, true, n, s)) return 1;                 // conv2 + BN + identity + ReLU -> fp32 + fp16
+                std::swap(x16, y16); std::swap(x32, y32);
+                inpl = planes;
+            }
+        rn_avgpool_kernel<<<(n * 512 + 255) / 256, 256, 0, s>>>(x32, c->pooled.p, n, 49, 512);
+        RnEpiFc e{feats + (long long)f0 * c->out_dim, c->out_dim, c->fc_b.p, n};
+        sgemm_tn_kernel<<<dim3((c->out_dim + 127) / 128, (n + 127) / 128), 256, 0, s>>>(c->pooled.p, 512, c->fc_w.p, 512, c->out_dim, 512, e);
+        c->launches += 5;
+    }
+    for (int f0 = 0; !c->tc && f0 < N; f0 += c->chunk) {
         const int n = std::min(c->chunk, N - f0);
         const long long npix = (long long)n * 224 * 224;
         rn_pad_flow_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, s>>>(flow + (long long)f0 * 224 * 224 * 2, c->in4.p, npix);

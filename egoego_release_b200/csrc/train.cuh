@@ -331,7 +331,8 @@ __device__ __forceinline__ void tr_store_pv(float* __restrict__ dst, int ld, con
 }
 
 static __global__ void __launch_bounds__(256) attention_bwd_simt_kernel(const float* __restrict__ QKV, int ldq, const float* __restrict__ dO, int ldo,
-                                                                        float* __restrict__ dQKV, int n_head, int L, float scale) {
+                                                                        float* __restrict__ dQKV, int n_head, int L, float scale,
+                                                                        DropCfg drop, uint32_t drop_stream) {
     constexpr int DH = 256;
     extern __shared__ __align__(16) float sm[];
     float (*P)[129] = reinterpret_cast<float (*)[129]>(sm);
@@ -383,6 +384,19 @@ static __global__ void __launch_bounds__(256) attention_bwd_simt_kernel(const fl
             for (int j = 0; j < 8; ++j) Dm[i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4)][j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4)] = acc[i][j];
     }
     __syncthreads();
+    // dropout on the probabilities (forward: O = (P o m) V): d(P o m) = dO V^T, so dP = (dO V^T) o m -- the same Philox words
+    // as the forward kernel; the softmax backward below uses the UN-dropped P, dV further down the dropped one
+    auto drop_pass = [&](float (*X)[129]) {
+        const unsigned long long base = (unsigned long long)blockIdx.x * 128ull * 128ull;
+        for (int q = tid; q < 128 * 32; q += 256) {
+            const int r = q >> 5, c4 = (q & 31) * 4;
+            const uint4 wd = drop_words(drop, drop_stream, (base + (unsigned long long)r * 128ull + c4) >> 2);
+            X[r][c4 + 0] *= wd.x < drop.thresh ? drop.scale : 0.f; X[r][c4 + 1] *= wd.y < drop.thresh ? drop.scale : 0.f;
+            X[r][c4 + 2] *= wd.z < drop.thresh ? drop.scale : 0.f; X[r][c4 + 3] *= wd.w < drop.thresh ? drop.scale : 0.f;
+        }
+        __syncthreads();
+    };
+    if (drop.on) drop_pass(Dm);
     {   // dS = P (dP - rowsum(dP P)) in place in Dm
         const int warp = tid / 32, lane = tid % 32;
         for (int r = warp; r < 128; r += 8) {
@@ -396,10 +410,22 @@ static __global__ void __launch_bounds__(256) attention_bwd_simt_kernel(const fl
         }
     }
     __syncthreads();
+    if (drop.on) drop_pass(P);                                                                            // P o m for dV
     float acc[8][16];
-    tr_tile_pv<true>(P, dOh, ldo, tile, acc, tid, tx, ty);    tr_store_pv(dV, ldq, acc, 1.0f, tx, ty);     // dV = P^T dO
+    tr_tile_pv<true>(P, dOh, ldo, tile, acc, tid, tx, ty);    tr_store_pv(dV, ldq, acc, 1.0f, tx, ty);     // dV = (P o m)^T dO
     tr_tile_pv<false>(Dm, Kp, ldq, tile, acc, tid, tx, ty);   tr_store_pv(dQ, ldq, acc, scale, tx, ty);    // d q_unscaled = (dS K) scale
     tr_tile_pv<true>(Dm, Q, ldq, tile, acc, tid, tx, ty);     tr_store_pv(dK, ldq, acc, 1.0f, tx, ty);     // dK = dS^T Q_scaled
+}
+
+// dZ = dY o m: gradient through dropout(acc + bias) of the fc / FFN output (the residual branch keeps dY)
+static __global__ void tr_dropout_bwd_kernel(const float* __restrict__ dY, float* __restrict__ dZ, long long n, DropCfg drop, uint32_t stream) {
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // quads of 4 consecutive channels
+    if (q * 4 >= n) return;
+    const uint4 wd = drop_words(drop, stream, (unsigned long long)q);
+    float4 v = *reinterpret_cast<const float4*>(dY + q * 4);
+    v.x *= wd.x < drop.thresh ? drop.scale : 0.f; v.y *= wd.y < drop.thresh ? drop.scale : 0.f;
+    v.z *= wd.z < drop.thresh ? drop.scale : 0.f; v.w *= wd.w < drop.thresh ? drop.scale : 0.f;
+    *reinterpret_cast<float4*>(dZ + q * 4) = v;
 }
 
 }  // namespace egoego

@@ -585,7 +585,8 @@ class CondGaussianDiffusion(nn.Module):
     # ------------------------------------------------------------------------------------------
     # training-side methods of the reference class: loss AND gradients come from the CUDA library
     # (egoego_train_step: forward with saved activations + backward kernels); torch.autograd only carries the parameter
-    # gradients to .grad so the reference's optimizer / EMA / GradScaler code runs unchanged.  Dropout is identity.
+    # gradients to .grad so the reference's optimizer / EMA / GradScaler code runs unchanged.  Dropout (train() mode) uses
+    # counter-based Philox masks re-derived in the backward pass (include/egoego_b200.h: egoego_train_set_dropout).
     # ------------------------------------------------------------------------------------------
     def q_sample(self, x_start, t, noise=None):
         """:557-563 (device tensors; the same arithmetic runs inside egoego_train_step)."""
@@ -629,9 +630,14 @@ class CondGaussianDiffusion(nn.Module):
             self._ht_sig = sig
         return self._ht
 
-    def p_losses(self, x_start, cond_mask, t, noise=None, padding_mask=None, cond_noise=None):
+    DROPOUT_P = 0.1     # nn.Dropout(0.1) at the three sites of every DecoderLayer (transformer_module.py:53,59,105)
+
+    def p_losses(self, x_start, cond_mask, t, noise=None, padding_mask=None, cond_noise=None, dropout_seed=None):
         """:574-605.  Returns the scalar loss; ``loss.backward()`` fills ``.grad`` of every trainable parameter with the
-        gradients computed by the CUDA backward pass.  ``cond_noise`` (optional) replaces the second Gaussian draw."""
+        gradients computed by the CUDA backward pass.  ``cond_noise`` (optional) replaces the second Gaussian draw.
+        While ``denoise_fn`` is in train() mode the step applies the reference's dropout (p = 0.1, three sites per layer) with
+        counter-based Philox masks; their seed is drawn from torch's generator (so ``torch.manual_seed`` makes a step
+        reproducible) unless ``dropout_seed`` is given.  In eval() mode dropout is the identity, as in the reference."""
         if self.objective not in ('pred_noise', 'pred_x0'):
             raise ValueError(f'unknown objective {self.objective}')
         if self.loss_type not in ('l1', 'l2'):
@@ -645,6 +651,11 @@ class CondGaussianDiffusion(nn.Module):
         B, T, _ = x_start.shape
         pm = None if padding_mask is None else _f32c(padding_mask.reshape(B, T + 1), dev)
         names, params = zip(*[(k, v) for k, v in self.named_parameters() if v.requires_grad])
+        if self.denoise_fn.training:
+            seed = int(dropout_seed) if dropout_seed is not None else int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+            self._dropout = (self.DROPOUT_P, seed)
+        else:
+            self._dropout = (0.0, 0)
         return _TrainStepFn.apply(self, names, x_start, cond_mask, pm, t, noise, cond_noise, *params)
 
     def forward(self, x_start, cond_mask, padding_mask=None):
@@ -666,7 +677,9 @@ class _TrainStepFn(torch.autograd.Function):
         sb = model.sqrt_one_minus_alphas_cumprod.gather(-1, t).contiguous()
         wt = model.p2_loss_weight.gather(-1, t).contiguous()
         loss = torch.empty(1, device=dev, dtype=torch.float32)
+        dp, dseed = getattr(model, "_dropout", (0.0, 0))
         with torch.cuda.device(dev):
+            check(_capi.lib().egoego_train_set_dropout(h, float(dp), int(dseed)))
             check(_capi.lib().egoego_train_step(h, _ptr(x_start), _ptr(cond_mask), _ptr(pm), _ptr(t), _ptr(noise), _ptr(cond_noise), _ptr(sa),
                                                 _ptr(sb), _ptr(wt), 1 if model.loss_type == 'l2' else 0, B, T, _ptr(loss), _stream(dev)))
         ctx.model, ctx.names, ctx.shapes, ctx.handle = model, names, [tuple(p.shape) for p in params], h

@@ -250,8 +250,8 @@ int64_t egoego_resnet18_launch_count(egoego_resnet h);
 /* Training step of the denoiser: CondGaussianDiffusion.forward / p_losses
  * (egoego/model/transformer_cond_diffusion_model.py:557-625) -- q_sample, conditioning, denoiser forward with saved activations,
  * L1 (loss_l2 = 0) or L2 loss with the padding mask and per-sample weight, and the backward pass through every layer.
- * Handles created with EGOEGO_ENGINE_SIMT only (fp32); weights = the last egoego_commit_weights.  Dropout is identity (the
- * parity bar is the reference in eval() mode, oracle/training.py).  All pointers are device pointers:
+ * Handles created with EGOEGO_ENGINE_SIMT only (fp32); weights = the last egoego_commit_weights.  Dropout follows
+ * egoego_train_set_dropout (default p = 0: the reference in eval() mode).  All pointers are device pointers:
  * x_start / cond_mask / noise / cond_noise [B,T,d_feats], padding_mask float [B,T+1] or NULL, t int64 [B],
  * sqrt_ac = sqrt_alphas_cumprod[t], sqrt_1mac = sqrt_one_minus_alphas_cumprod[t], weight = p2_loss_weight[t] (each float [B]).
  * loss_out_dev[1] receives the scalar loss; gradients stay in the handle until the next call and are read with
@@ -260,6 +260,13 @@ int  egoego_train_step(egoego_handle h, const float* x_start_dev, const float* c
                        const int64_t* t_dev, const float* noise_dev, const float* cond_noise_dev, const float* sqrt_ac_dev,
                        const float* sqrt_1mac_dev, const float* weight_dev, int loss_l2, int B, int T, float* loss_out_dev, void* stream);
 int  egoego_train_get_grad(egoego_handle h, const char* name, float* dst_dev, int64_t numel, void* stream);
+/* Dropout of the following egoego_train_step calls on this handle -- nn.Dropout(0.1) on the attention probabilities, the fc output
+ * and the FFN output of every DecoderLayer while the reference module is in train() mode (egoego/model/transformer_module.py:53,59,
+ * 84,92,105,113).  p = 0 (default) is the eval()-mode identity.  Masks are counter-based: element i of stream 4*layer + site keeps its
+ * value (scaled by 1/(1-p)) iff word i%4 of Philox4x32-10(counter = (i/4, i>>34, stream, 0x44524f50), key = seed) < floor((1-p) 2^32);
+ * site 0 index ((b H + h) 128 + query) 128 + key, sites 1 / 2 index (b 128 + token) 512 + channel.  The same masks are re-derived
+ * in the backward pass, so no mask tensor is stored. */
+int  egoego_train_set_dropout(egoego_handle h, double p, uint64_t seed);
 /* Device-to-device refresh of one parameter tensor (reference state_dict key, reference layout) of a committed
  * EGOEGO_ENGINE_SIMT handle: what an optimizer step needs between two training steps (no host staging, no re-allocation;
  * the timestep-embedding table is rebuilt lazily when a time_mlp tensor changed). */

@@ -337,16 +337,17 @@ def test_full_size_policy_vs_fp32_engines(params0):
 
 
 def test_fused_ln_kernels_agree(params0, monkeypatch):
-    """The column-split cluster-of-4 GEMM+LayerNorm kernel (default) against the full-row pair kernel (EGOEGO_LN=2cta) and
-    against the unfused GEMM + LayerNorm kernels (EGOEGO_FUSE_LN=0), all-fp16 steps, enough windows that every cluster
-    walks several 256-row blocks.  Differences are fp16 rounding noise (one-pass vs centred variance, summation order)."""
+    """The column-split cluster-of-4 GEMM+LayerNorm kernel (default) against the unfused GEMM + LayerNorm kernels
+    (EGOEGO_FUSE_LN=0), and the L2 zig-zag tile order (default) against the plain ascending order (EGOEGO_ZIGZAG=0, which must be
+    bit-identical: tiles are independent), all-fp16 steps, enough windows that every cluster walks several 256-row blocks.
+    Fused vs unfused differences are fp16 rounding noise (one-pass vs centred variance, summation order)."""
     import egoego_release_b200 as E
     N, B = 4, 160
     xs = synth_x_start(17, B, 120).cuda()
     cm = O.prep_head_condition_mask(xs.shape).cuda()
     outs = {}
-    for tag, env in (("c4", {}), ("2cta", {"EGOEGO_LN": "2cta"}), ("unfused", {"EGOEGO_FUSE_LN": "0"})):
-        for k in ("EGOEGO_LN", "EGOEGO_FUSE_LN"):
+    for tag, env in (("c4", {}), ("nozigzag", {"EGOEGO_ZIGZAG": "0"}), ("unfused", {"EGOEGO_FUSE_LN": "0"})):
+        for k in ("EGOEGO_ZIGZAG", "EGOEGO_FUSE_LN"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -358,9 +359,10 @@ def test_fused_ln_kernels_agree(params0, monkeypatch):
         torch.manual_seed(3)
         outs[tag] = m.sample(xs, cm)
         assert torch.isfinite(outs[tag]).all()
-    d1, d2 = maxabs(outs["c4"], outs["2cta"]), maxabs(outs["c4"], outs["unfused"])
-    print(f"fused-LN kernels: c4 vs 2cta {d1:.3e}, c4 vs unfused {d2:.3e}")
-    assert d1 < 2e-2 and d2 < 2e-2
+    assert torch.equal(outs["c4"], outs["nozigzag"])
+    d2 = maxabs(outs["c4"], outs["unfused"])
+    print(f"fused-LN kernel: c4 vs unfused {d2:.3e}; zig-zag vs ascending tile order: bit-identical")
+    assert d2 < 2e-2
 
 
 @pytest.mark.parametrize("K", [12, -2])

@@ -205,11 +205,18 @@ def test_gpu_full_pipeline_config4(params0):
 
 
 @pytest.mark.gpu
-def test_gpu_resnet_encoder_and_raw_flow_headformer(gold):
+@pytest.mark.parametrize("engine", ["tcgen05", "simt"])
+def test_gpu_resnet_encoder_and_raw_flow_headformer(gold, engine, monkeypatch):
     """HeadFormer with input_of_feats=False: [1,T,224,224,2] flow -> ResNet-18 (csrc/resnet.cu) -> the same sequence net.
-    Features vs the golden of the reference's ResNet class (1e-3 of the feature range: 20 fp32 conv layers in a different
-    summation order), then the whole forward_for_eval vs the oracle's composition."""
+    Features vs the golden of the reference's ResNet class, then the whole forward_for_eval vs the oracle's composition.
+    Two engines: the tensor-core convolutions (default; fp16 operands = the operand rounding of the reference's own cuDNN-TF32 GPU
+    path, fp32 accumulation and residual stream) and the fp32 CUDA-core kernels (EGOEGO_RESNET=simt).  Tolerance: 1e-3 of the
+    feature range for both (20 conv layers in a different summation order / with 11-bit operands)."""
     from egoego_release_b200 import HeadFormer
+    if engine == "simt":
+        monkeypatch.setenv("EGOEGO_RESNET", "simt")
+    else:
+        monkeypatch.delenv("EGOEGO_RESNET", raising=False)
     opt = argparse.Namespace(**{**vars(OPT), "input_of_feats": False})
     m = HeadFormer(opt, "cuda:0")
     ph, pr = S.init_params(7, S.CFG_HEAD), S.init_resnet_params(9)
@@ -219,7 +226,7 @@ def test_gpu_resnet_encoder_and_raw_flow_headformer(gold):
     feats = m._input_features({"of": flow}).cpu().numpy()[0]
     ref = gold["resnet_s51_T3_feats"]
     err = np.abs(feats - ref).max() / np.abs(ref).max()
-    print(f"ResNet-18 features: max-abs error {err:.2e} of the feature range")
+    print(f"ResNet-18 features [{engine}]: max-abs error {err:.2e} of the feature range")
     assert err < 1e-3
     # 19 frames (two encoder chunks of 16 + 3) through the whole HeadNet
     flow = S.synth_flow(52, 19)
@@ -229,5 +236,5 @@ def test_gpu_resnet_encoder_and_raw_flow_headformer(gold):
         f_ref = S.resnet18_forward(pr, S.flow_to_cnn_input(flow))[None]
         pose_ref, scale_ref = S.headformer_forward_for_eval(ph, f_ref, slam_trans, head_pose[:, 0, 3:])
     perr = (res["head_pose"].cpu() - pose_ref).abs().max()
-    print(f"raw-flow HeadFormer: head pose max-abs {float(perr):.2e}, scale {float(res['pred_scale']):.5f} vs {float(scale_ref):.5f}")
+    print(f"raw-flow HeadFormer [{engine}]: head pose max-abs {float(perr):.2e}, scale {float(res['pred_scale']):.5f} vs {float(scale_ref):.5f}")
     assert perr < 2e-3 and abs(float(res["pred_scale"]) - float(scale_ref)) < 2e-3 * abs(float(scale_ref)) + 1e-5

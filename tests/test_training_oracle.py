@@ -1,6 +1,8 @@
 """Training objective: the oracle's p_losses + autograd gradients against loss / gradient fingerprints of
-the unmodified reference (eval-mode modules: dropout is identity, see oracle/training.py), and the CUDA training step
-(egoego_train_step through the host mirror's p_losses / loss.backward()) against the same goldens."""
+the unmodified reference -- in eval() mode (dropout = identity) and in train() mode with the product's counter-based dropout masks
+injected into the reference's own nn.Dropout modules (oracle/gen_golden_training.py) -- and the CUDA training step
+(egoego_train_step through the host mirror's p_losses / loss.backward()) against the same goldens AND, tensor by tensor, against
+the oracle's full gradients."""
 import os
 
 import numpy as np
@@ -8,14 +10,17 @@ import pytest
 
 from oracle import egoego_oracle as O
 from oracle import training as TR
-from oracle.gen_golden_training import CASES, case_inputs
+from oracle.gen_golden_training import CASES, DROP_CASES, case_inputs
+
+ALL_CASES = [c + (None,) for c in CASES] + list(DROP_CASES)
 
 
-@pytest.mark.parametrize("tag,B,T,seed,with_pm", CASES)
-def test_training_loss_and_gradients_vs_reference_golden(tag, B, T, seed, with_pm, golden_dir, params0):
+@pytest.mark.parametrize("tag,B,T,seed,with_pm,dseed", ALL_CASES)
+def test_training_loss_and_gradients_vs_reference_golden(tag, B, T, seed, with_pm, dseed, golden_dir, params0):
     g = dict(np.load(os.path.join(golden_dir, "training.npz")))
     x_start, cm, t, noise, cond_noise, pm = case_inputs(seed, B, T, with_pm)
-    loss, grads = TR.loss_and_grads(params0, O.make_schedule(1000), x_start, cm, t, noise, cond_noise, pm)
+    drop = None if dseed is None else TR.DropoutMasks(dseed, 0.1)
+    loss, grads = TR.loss_and_grads(params0, O.make_schedule(1000), x_start, cm, t, noise, cond_noise, pm, dropout=drop)
     assert abs(float(loss) - float(g[f"{tag}_loss"])) < 1e-6
     summ = TR.grad_summary(grads)
     keys = [k[len(tag) + 1:] for k in g if k.startswith(tag + "|")]
@@ -28,12 +33,29 @@ def test_training_loss_and_gradients_vs_reference_golden(tag, B, T, seed, with_p
         assert float(loss) > 0
 
 
+def test_philox_known_answers_and_mask_statistics():
+    """The numpy Philox4x32-10 behind the dropout masks against the Random123 known-answer vectors (the same three the device
+    function is held to through the gradient tests), and the keep rate of a mask."""
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        got = TR.philox4x32_10(*[[c] for c in ctr], *key)
+        assert tuple(int(v[0]) for v in got) == want
+    keep = TR.dropout_keep(99, 6, np.arange(400000))
+    assert abs(keep.mean() - 0.9) < 2e-3
+    assert not np.array_equal(keep, TR.dropout_keep(99, 7, np.arange(400000)))      # streams differ
+    f = TR.DropoutMasks(5)(2, 1, (2, 121, 512))
+    assert set(np.unique(f.numpy()).tolist()) == {0.0, float(np.float32(1.0 / 0.9))}
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("tag,B,T,seed,with_pm", CASES)
-def test_gpu_training_step_vs_reference_golden(tag, B, T, seed, with_pm, golden_dir, params0):
+@pytest.mark.parametrize("tag,B,T,seed,with_pm,dseed", ALL_CASES)
+def test_gpu_training_step_vs_reference_golden(tag, B, T, seed, with_pm, dseed, golden_dir, params0):
     """CondGaussianDiffusion.p_losses on the device (egoego_train_step: fp32 forward + backward kernels) against the loss and
-    the gradient fingerprints of the unmodified reference (eval-mode dropout).  Tolerances are fractions of each tensor's
-    gradient norm (products run as 3-term bf16 splits on the tensor cores and reduce over B*128 rows in a different order)."""
+    the gradient fingerprints of the unmodified reference -- eval() mode, and train() mode with the same dropout masks -- and
+    against the FULL gradient tensors of the oracle (torch autograd on the CPU, same masks).  Tolerances are fractions of each
+    tensor's gradient norm (products run as 3-term bf16 splits on the tensor cores and reduce over B*128 rows in a different order)."""
     import torch
     import egoego_release_b200 as E
     g = dict(np.load(os.path.join(golden_dir, "training.npz")))
@@ -41,9 +63,10 @@ def test_gpu_training_step_vs_reference_golden(tag, B, T, seed, with_pm, golden_
                                 out_dim=198, timesteps=1000, objective="pred_x0", loss_type="l1", max_batch=4)
     m.load_state_dict(params0, strict=False)
     m = m.cuda()
+    m.train(dseed is not None)                      # eval(): dropout is the identity, exactly like the reference
     x_start, cm, t, noise, cond_noise, pm = case_inputs(seed, B, T, with_pm)
     loss = m.p_losses(x_start.cuda(), cm.cuda(), t.cuda(), noise=noise.cuda(), padding_mask=None if pm is None else pm.cuda(),
-                      cond_noise=cond_noise.cuda())
+                      cond_noise=cond_noise.cuda(), dropout_seed=dseed)
     assert abs(float(loss.detach()) - float(g[f"{tag}_loss"])) < 2e-5, (float(loss.detach()), float(g[f"{tag}_loss"]))
     loss.backward()
     grads = {k: v.grad.detach().cpu() for k, v in m.named_parameters() if v.grad is not None}
@@ -59,11 +82,21 @@ def test_gpu_training_step_vs_reference_golden(tag, B, T, seed, with_pm, golden_
         assert err < 2e-3, (k, err, v.numpy()[:4], ref[:4])
         assert abs(v.numpy()[0] - ref[0]) < 5e-4 * scale and np.abs(v.numpy()[2:] - ref[2:]).max() < 5e-4 * scale, (k, v.numpy()[:4], ref[:4])
     print(f"[{tag}] loss {float(loss.detach()):.6f} vs {float(g[f'{tag}_loss']):.6f}; worst gradient fingerprint error {worst[0]:.2e} of its norm ({worst[1]})")
+    # full tensors: every element of every gradient against the oracle's autograd result (same inputs, same dropout masks)
+    drop = None if dseed is None else TR.DropoutMasks(dseed, 0.1)
+    _, og = TR.loss_and_grads(params0, O.make_schedule(1000), x_start, cm, t, noise, cond_noise, pm, dropout=drop)
+    worst_full = (0.0, "")
+    for k, gv in grads.items():
+        ref = og[k]
+        rel = float((gv - ref).abs().max() / max(float(ref.abs().max()), 1e-7))
+        worst_full = max(worst_full, (rel, k))
+        assert rel < 2e-3, (k, rel)                 # max element error relative to the tensor's largest gradient entry
+    print(f"[{tag}] full-tensor gradients vs oracle autograd: worst max-abs error {worst_full[0]:.2e} of the tensor's max ({worst_full[1]})")
     # a small gradient-descent step through a stock torch optimizer lowers the loss on the same batch: the gradients point downhill
     # and the engine picks up the updated parameters
     opt = torch.optim.SGD(m.parameters(), lr=1e-3)
     opt.step()
     loss2 = m.p_losses(x_start.cuda(), cm.cuda(), t.cuda(), noise=noise.cuda(), padding_mask=None if pm is None else pm.cuda(),
-                       cond_noise=cond_noise.cuda())
+                       cond_noise=cond_noise.cuda(), dropout_seed=dseed)
     print(f"[{tag}] loss after one SGD step: {float(loss2.detach()):.6f} (before {float(loss.detach()):.6f})")
     assert float(loss2.detach()) < float(loss.detach())

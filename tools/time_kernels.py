@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Per-kernel device times of one sampling step (egoego_time_kernel), both operand formats:
-    python tools/time_kernels.py [B] [iters]        (environment switches such as EGOEGO_LN=2cta apply)"""
+    python tools/time_kernels.py [B] [iters]        (environment switches such as EGOEGO_FUSE_LN=0 apply)"""
 import os
 import sys
 
