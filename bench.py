@@ -339,12 +339,7 @@ def all_split_ms(dev, xs, cm, B, T, N):
                                 out_dim=198, timesteps=N, objective="pred_x0", loss_type="l1", max_batch=B, precise_last_steps=N)
     m.load_state_dict(O.init_params(0), strict=False)
     m = m.to(dev)
-    n_warm = max(1, min(20, N // 10))
-    mw = E.CondGaussianDiffusion(d_feats=198, d_model=512, n_dec_layers=4, n_head=4, d_k=256, d_v=256, max_timesteps=121,
-                                 out_dim=198, timesteps=n_warm, objective="pred_x0", loss_type="l1", max_batch=B, precise_last_steps=n_warm)
-    mw.load_state_dict(O.init_params(0), strict=False)
-    mw.to(dev).sample(xs, cm)                                  # warm-up: a short all-split loop (kernels, planes, graph capture path)
-    del mw
+    m.sample(xs, cm)                                           # first call of THIS handle: weight commit, graph capture
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

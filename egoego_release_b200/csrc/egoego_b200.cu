@@ -836,6 +836,13 @@ int egoego_time_dominant_kernel(egoego_handle c, int B, int half_fmt, int iters,
 }
 
 int egoego_precise_last_steps(egoego_handle c) { return c ? c->precise_last : -1; }
+int egoego_engine_info(egoego_handle c, char* buf, int n) {
+    EG_CHECK(c && buf && n > 0, "null argument");
+    std::string s = (c->cfg.engine == EGOEGO_ENGINE_TCGEN05 && c->tc) ? c->tc->info() : std::string(c->cfg.engine == EGOEGO_ENGINE_SIMT ? "engine=simt" : "engine=tcgen05 (weights not committed)");
+    s += " precise_last_steps=" + std::to_string(c->precise_last);
+    snprintf(buf, (size_t)n, "%s", s.c_str());
+    return 0;
+}
 int egoego_dither_weights_f16(const float* w, int64_t n, int set, int n_sets, uint16_t* out) {
     EG_CHECK(w && out && n >= 0 && n_sets >= 1 && n_sets <= 16 && set >= 0 && set < n_sets, "egoego_dither_weights_f16: bad arguments");
     dither_weights_host(w, (long long)n, set, n_sets, out);

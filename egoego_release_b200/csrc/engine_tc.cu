@@ -51,6 +51,7 @@ struct Plane {                 // a 16-bit hi/lo pair (fp16 in the sampler, bf16
     CUtensorMap mhi128, mlo128;     // 128-row boxes (per-CTA half of a W tile in the 2-CTA GEMM)
     __nv_bfloat16* h16 = nullptr;   // fp16 plane for FMT_HALF launches: a separate buffer (weights, X) or an alias of `hi`
     CUtensorMap m16, m16_128;
+    CUtensorMap mhi64, m16_64;      // 64-row boxes: the multicast halves of the cluster-of-8 GEMM (gemm_half_tma_2cta_kernel<.., true>)
     bool own16 = false;
     size_t rows = 0, cols = 0;
     int alloc(size_t r, size_t c, uint32_t box_rows) {
@@ -60,8 +61,8 @@ struct Plane {                 // a 16-bit hi/lo pair (fp16 in the sampler, bf16
         EG_CUDA(cudaMemset(hi, 0, r * c * 2));
         EG_CUDA(cudaMemset(lo, 0, r * c * 2));
         if (make_map(&mhi, hi, r, c, box_rows) || make_map(&mlo, lo, r, c, box_rows)) return 1;
-        if (make_map(&mhi128, hi, r, c, 128) || make_map(&mlo128, lo, r, c, 128)) return 1;
-        h16 = hi; m16 = mhi; m16_128 = mhi128; own16 = false;       // activations: the fp16 plane reuses the hi buffer
+        if (make_map(&mhi128, hi, r, c, 128) || make_map(&mlo128, lo, r, c, 128) || make_map(&mhi64, hi, r, c, 64)) return 1;
+        h16 = hi; m16 = mhi; m16_128 = mhi128; m16_64 = mhi64; own16 = false;       // activations: the fp16 plane reuses the hi buffer
         box = box_rows;
         return 0;
     }
@@ -69,24 +70,24 @@ struct Plane {                 // a 16-bit hi/lo pair (fp16 in the sampler, bf16
         EG_CUDA(cudaMalloc(&h16, rows * cols * 2));
         EG_CUDA(cudaMemset(h16, 0, rows * cols * 2));
         own16 = true;
-        if (make_map(&m16, h16, rows, cols, box) || make_map(&m16_128, h16, rows, cols, 128)) return 1;
+        if (make_map(&m16, h16, rows, cols, box) || make_map(&m16_128, h16, rows, cols, 128) || make_map(&m16_64, h16, rows, cols, 64)) return 1;
         return 0;
     }
     uint32_t box = 128;
     // Weights only: R fp16 planes, each rounded with its own dither offset (see upload_weight); use_set(r) makes set r the
     // plane FMT_HALF launches read (the maps are passed to kernels by value, so this is a host-side switch).
     std::vector<__nv_bfloat16*> set16;
-    std::vector<CUtensorMap> set_m16, set_m16_128;
+    std::vector<CUtensorMap> set_m16, set_m16_128, set_m16_64;
     void use_set(int r) {                              // r < 0: the plain round-to-nearest copy (= the hi plane of the pair)
         if (set16.empty()) return;
-        if (r < 0) { h16 = hi; m16 = mhi; m16_128 = mhi128; return; }
+        if (r < 0) { h16 = hi; m16 = mhi; m16_128 = mhi128; m16_64 = mhi64; return; }
         r %= (int)set16.size();
-        h16 = set16[r]; m16 = set_m16[r]; m16_128 = set_m16_128[r];
+        h16 = set16[r]; m16 = set_m16[r]; m16_128 = set_m16_128[r]; m16_64 = set_m16_64[r];
     }
     void release() {
         if (hi) cudaFree(hi); if (lo) cudaFree(lo); if (own16 && h16) cudaFree(h16);
         for (auto* p : set16) cudaFree(p);
-        set16.clear(); set_m16.clear(); set_m16_128.clear();
+        set16.clear(); set_m16.clear(); set_m16_128.clear(); set_m16_64.clear();
         hi = lo = h16 = nullptr;
     }
 };
@@ -144,14 +145,15 @@ static int upload_weight(Plane& p, const float* w, int rows, int src_ld, int col
     EG_CUDA(cudaMemcpy(p.lo, lo.data(), lo.size() * 2, cudaMemcpyHostToDevice));
     const int R = weight_sets();
     std::vector<__half> h16((size_t)rows_pad * cols_pad, __float2half(0.f));
-    p.set16.assign(R, nullptr); p.set_m16.resize(R); p.set_m16_128.resize(R);
+    p.set16.assign(R, nullptr); p.set_m16.resize(R); p.set_m16_128.resize(R); p.set_m16_64.resize(R);
     for (int k = 0; k < R; ++k) {
         const float u = dither_offset(k, R);
         for (int r = 0; r < rows; ++r)
             for (int c = 0; c < ncols; ++c) h16[(size_t)r * cols_pad + c] = dither_round(w[(size_t)r * src_ld + col0 + c], u);
         EG_CUDA(cudaMalloc(&p.set16[k], h16.size() * 2));
         EG_CUDA(cudaMemcpy(p.set16[k], h16.data(), h16.size() * 2, cudaMemcpyHostToDevice));
-        if (make_map(&p.set_m16[k], p.set16[k], rows_pad, cols_pad, box_rows) || make_map(&p.set_m16_128[k], p.set16[k], rows_pad, cols_pad, 128)) return 1;
+        if (make_map(&p.set_m16[k], p.set16[k], rows_pad, cols_pad, box_rows) || make_map(&p.set_m16_128[k], p.set16[k], rows_pad, cols_pad, 128) ||
+            make_map(&p.set_m16_64[k], p.set16[k], rows_pad, cols_pad, 64)) return 1;
     }
     p.own16 = false;
     p.use_set(-1);                                       // outside the sampling loop FMT_HALF launches read the plain RN copy
@@ -177,6 +179,7 @@ struct TcImpl {
     // L2 zig-zag (EGOEGO_ZIGZAG, default on): consecutive kernels of a step walk the windows in OPPOSITE directions, so a
     // kernel starts with the rows its producer wrote last -- the part of its input that is still in the 126 MB L2 (the
     // per-kernel working set at 256 windows is 100-270 MB, so a same-direction walk misses everywhere).
+    int c8_clusters = 0;                        // co-resident clusters of 8 for the multicast GEMM (EGOEGO_GEMM_C8=1; 0 = off)
     bool zigzag = true;
     int dir = 0;                                // direction of the next kernel launched (0 = ascending windows)
     int next_dir() { const int d = zigzag ? dir : 0; dir ^= 1; return d; }
@@ -253,8 +256,35 @@ static bool use_tma_epi() {
     if (v < 0) { const char* e = getenv("EGOEGO_TMA_EPI"); v = (e && e[0] == '0') ? 0 : 1; }
     return v == 1 && use_2cta();
 }
+// cluster-of-8 variant (2 x 2 CTA pairs, A and W multicast): co-resident clusters on this device, 0 if the launch is not possible
+template <class Epi>
+static int c8_query(TcImpl* I) {
+    auto kern = gemm_half_tma_2cta_kernel<Epi, true>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmTmaEpiCfg::SMEM_BYTES) != cudaSuccess) { cudaGetLastError(); return 0; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((I->sms / 8) * 8); cfg.blockDim = dim3(GEMM_TMAEPI_THREADS); cfg.dynamicSmemBytes = GemmTmaEpiCfg::SMEM_BYTES;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 8; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int nc = 0;
+    if (cudaOccupancyMaxActiveClusters(&nc, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return nc < I->sms / 8 ? nc : I->sms / 8;
+}
+template <class Epi>
+static int launch_gemm_tma_c8(TcImpl* I, const Plane& A, const Plane& W, int M, int N, int K, const float* bias, const Epi& epi, cudaStream_t s) {
+    auto kern = gemm_half_tma_2cta_kernel<Epi, true>;
+    EG_CHECK(M % 512 == 0 && N % 512 == 0 && K % GEMM_BK == 0 && N <= GemmTmaEpiCfg::MAX_N && I->c8_clusters > 0, "cluster-of-8 gemm shape not supported");
+    const int super_tiles = (M / 512) * (N / 512);
+    const int clusters = super_tiles < I->c8_clusters ? super_tiles : I->c8_clusters;
+    LaunchCfg lc(8 * clusters, GEMM_TMAEPI_THREADS, GemmTmaEpiCfg::SMEM_BYTES, s, 8);
+    EG_CUDA(cudaLaunchKernelEx(&lc.cfg, kern, A.m16_64, W.m16_64, M, N, K, bias, epi, I->next_dir()));
+    return 0;
+}
+
 template <class Epi>
 static int launch_gemm_tma_epi(TcImpl* I, const Plane& A, const Plane& W, int M, int N, int K, const float* bias, const Epi& epi, cudaStream_t s) {
+    if (I->c8_clusters > 0 && M % 512 == 0 && N % 512 == 0) return launch_gemm_tma_c8(I, A, W, M, N, K, bias, epi, s);
     static PerDeviceOnce attr_once;          // opt-in shared-memory size is a per-device function attribute
     auto kern = gemm_half_tma_2cta_kernel<Epi>;
     if (attr_once.need()) {
@@ -339,6 +369,14 @@ int TcEngine::init(const TcWeights& w, cudaStream_t) {
         if (I->ln4_clusters == 0) I->fuse_ln = false;
     }
     { const char* zz = getenv("EGOEGO_ZIGZAG"); I->zigzag = !(zz && zz[0] == '0'); }
+    {   // cluster-of-8 multicast GEMM for the QKV projection and w_1 (opt-in until measured: EGOEGO_GEMM_C8=1)
+        const char* c8 = getenv("EGOEGO_GEMM_C8");
+        I->c8_clusters = 0;
+        if (c8 && c8[0] == '1' && use_2cta()) {
+            const int a = c8_query<TmaEpiQKV>(I), b = c8_query<TmaEpiRelu>(I);
+            I->c8_clusters = a < b ? a : b;
+        }
+    }
     const char* am = getenv("EGOEGO_ATTN");
     I->attn_tc = !(am && strcmp(am, "simt") == 0);
     if (I->attn_tc) {
@@ -381,6 +419,13 @@ int TcEngine::prepare_cond(int B, int T, cudaStream_t s, int64_t* n) {
     if (gemm<FMT_SPLIT>(I, I->C, I->Wc, Mr(B), I->w.d, I->kx, e, s)) return 1;
     *n += 1;
     return 0;
+}
+
+std::string TcEngine::info() const {
+    const TcImpl* I = impl_;
+    if (!I) return "engine=tcgen05 (not initialised)";
+    return "engine=tcgen05 sms=" + std::to_string(I->sms) + " ln4_clusters=" + std::to_string(I->ln4_clusters) + " c8_clusters=" + std::to_string(I->c8_clusters) +
+           " zigzag=" + std::to_string(I->zigzag ? 1 : 0) + " fuse_ln=" + std::to_string(I->fuse_ln ? 1 : 0) + " weight_sets=" + std::to_string(n_weight_sets());
 }
 
 int TcEngine::n_weight_sets() const { return impl_ && !impl_->Wx.set16.empty() ? (int)impl_->Wx.set16.size() : 1; }

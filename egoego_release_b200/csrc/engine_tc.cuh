@@ -49,6 +49,8 @@ public:
     int n_weight_sets() const;
     void use_weight_set(int r);
     int time_stage(int B, int T, int stage, int fmt, int iters, float* model_out, cudaStream_t s, float* ms, const DdpmArgs* fuse = nullptr);
+    // "key=value ..." description of the resolved kernel choices (cluster counts, zig-zag, fused LN)
+    std::string info() const;
 private:
     TcImpl* impl_;
 };

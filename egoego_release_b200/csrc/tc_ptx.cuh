@@ -128,6 +128,13 @@ __device__ __forceinline__ void tma_load_2d_2cta(void* smem_dst, const CUtensorM
         "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(x), "r"(y) : "memory");
 }
+// Same, multicast: the box lands at the same CTA-relative offset in every CTA of `cta_mask` (cluster ranks), and each destination
+// pair's LEADER barrier (peer bit cleared, as above) is credited with the bytes that landed in that destination CTA.
+__device__ __forceinline__ void tma_load_2d_2cta_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int x, int y, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(x), "r"(y), "h"(cta_mask) : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_2cta(uint32_t* smem_dst, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
 }

@@ -294,6 +294,12 @@ class CondGaussianDiffusion(nn.Module):
         """Resolved precision policy of the engine: diffusion steps t < K use the 3-term split."""
         return int(_capi.lib().egoego_precise_last_steps(self._handle()))
 
+    def engine_info(self) -> str:
+        """Resolved kernel choices of the engine ("engine=tcgen05 sms=148 ln4_clusters=33 c8_clusters=0 zigzag=1 ...")."""
+        buf = C.create_string_buffer(512)
+        check(_capi.lib().egoego_engine_info(self._handle(), buf, 512))
+        return buf.value.decode()
+
     def weight_sets(self) -> int:
         """Number of dithered fp16 weight sets the single-pass steps cycle through (EGOEGO_WEIGHT_SETS, default 8)."""
         return int(_capi.lib().egoego_weight_sets(self._handle()))
@@ -608,26 +614,23 @@ class CondGaussianDiffusion(nn.Module):
             h = C.c_void_p()
             check(L.egoego_create(C.byref(cfg), C.byref(h)))
             self._ht, self._ht_batch, self._ht_device, self._ht_sig = h, int(B), dev, None
-        sig = self._signature()
-        if sig != self._ht_sig:
-            with torch.cuda.device(dev):
-                if self._ht_sig is None:                 # first use: full commit (host staging, workspace allocation)
-                    for k, v in self.state_dict().items():
-                        t = _f32c(v.detach().float(), dev)
-                        check(L.egoego_set_tensor(self._ht, k.encode(), _ptr(t), t.numel(), 1))
-                    check(L.egoego_commit_weights(self._ht, _stream(dev)))
-                else:                                    # after an optimizer step: device-to-device refresh of what changed
-                    old = dict((k, (p, ver)) for k, p, ver in self._ht_sig)
-                    ch = [(k, _f32c(v.detach(), dev)) for k, v in self.named_parameters() if old.get(k) != (v.data_ptr(), v._version)]
-                    if not ch:                           # only the content checksum moved (.data edits): refresh every parameter
-                        ch = [(k, _f32c(v.detach(), dev)) for k, v in self.named_parameters()]
-                    if ch:
-                        n = len(ch)
-                        names = (C.c_char_p * n)(*[k.encode() for k, _ in ch])
-                        ptrs = (C.c_void_p * n)(*[t.data_ptr() for _, t in ch])
-                        nums = (C.c_int64 * n)(*[t.numel() for _, t in ch])
-                        check(L.egoego_update_tensors_device(self._ht, n, names, ptrs, nums, _stream(dev)))
-            self._ht_sig = sig
+        with torch.cuda.device(dev):
+            if self._ht_sig is None:                     # first use: full commit (host staging, workspace allocation)
+                for k, v in self.state_dict().items():
+                    t = _f32c(v.detach().float(), dev)
+                    check(L.egoego_set_tensor(self._ht, k.encode(), _ptr(t), t.numel(), 1))
+                check(L.egoego_commit_weights(self._ht, _stream(dev)))
+                self._ht_sig = True
+            else:
+                # every later call: device-to-device refresh of EVERY parameter (72 small async copies, 44 MB, no host sync).  An
+                # optimizer step changes all of them anyway, and an unconditional refresh also picks up edits that bypass torch's
+                # version counters (p.data.copy_ / lerp_) without the host round trip a content checksum would need.
+                ch = [(k, _f32c(v.detach(), dev)) for k, v in self.named_parameters()]
+                n = len(ch)
+                names = (C.c_char_p * n)(*[k.encode() for k, _ in ch])
+                ptrs = (C.c_void_p * n)(*[t.data_ptr() for _, t in ch])
+                nums = (C.c_int64 * n)(*[t.numel() for _, t in ch])
+                check(L.egoego_update_tensors_device(self._ht, n, names, ptrs, nums, _stream(dev)))
         return self._ht
 
     DROPOUT_P = 0.1     # nn.Dropout(0.1) at the three sites of every DecoderLayer (transformer_module.py:53,59,105)

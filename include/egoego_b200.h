@@ -310,6 +310,9 @@ int  egoego_time_dominant_kernel(egoego_handle h, int B, int half_fmt, int iters
 int  egoego_launches_per_step(egoego_handle h, int which);
 /* Resolved precision policy: steps t < K run the 3-term split (see egoego_cfg.precise_last_steps). */
 int  egoego_precise_last_steps(egoego_handle h);
+/* Human-readable "key=value ..." line of the engine's resolved kernel choices (co-resident cluster counts of the cluster-of-4
+ * GEMM+LayerNorm and the cluster-of-8 multicast GEMM, zig-zag tile order, weight sets, precise_last_steps), for logs and bench lines. */
+int  egoego_engine_info(egoego_handle h, char* buf, int buf_len);
 /* Number R of dithered fp16 weight sets the single-pass steps cycle through (env EGOEGO_WEIGHT_SETS at weight commit,
  * default 8, 1 = plain round-to-nearest; always 1 for the fp32 engine).  Step i of the loop reads set i mod R, so the fp16
  * rounding of the weights -- the only rounding of those steps that survives to the final sample -- averages out over steps

@@ -97,9 +97,9 @@ def mlp_head(p, head: str, x: torch.Tensor, cfg: Dict) -> torch.Tensor:
 def pad_window(x: torch.Tensor, window: int):
     """[B, T<=window, D] -> zero-padded [B, window, D] and the padding mask [B, window]."""
     B, T, D = x.shape
-    out = torch.zeros(B, window, D, dtype=x.dtype)
+    out = torch.zeros(B, window, D, dtype=x.dtype, device=x.device)
     out[:, :T] = x
-    mask = (torch.arange(window)[None, :] < T).expand(B, window)
+    mask = (torch.arange(window, device=x.device)[None, :] < T).expand(B, window)
     return out, mask
 
 

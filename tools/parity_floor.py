@@ -8,7 +8,8 @@ Runs: (1) the reference op sequence (oracle port) as stock PyTorch eager fp32 on
 (5) the tensor-core engine for several policies K.  Every run is compared with (1) and with (3): raw max-abs of the
 normalised sample, joint positions (oracle FK, metres -> mm): max, mean, per-window-max percentiles, windows over 1 mm.
 usage: python tools/parity_floor.py [B] [K[:R] ...]      (R = number of dithered fp16 weight sets, EGOEGO_WEIGHT_SETS)
-env PARITY_FLOOR_QUICK=1 skips the fp64 and chunked torch runs."""
+env PARITY_FLOOR_QUICK=1 skips the fp64 and chunked torch runs; PARITY_FLOOR_WEIGHTS=seed1|seed2|trained_like selects one of the
+weight sets of oracle/gen_golden_weightsets.py instead of oracle.init_params(0)."""
 import math
 import os
 import sys
@@ -37,7 +38,13 @@ g.manual_seed(777)
 tape = torch.randn(N + 2, B, T, 198, device=dev, generator=g)
 xs = synth_x_start(33, B, T).to(dev)
 cm = O.prep_head_condition_mask(xs.shape).to(dev)
-params = O.init_params(0)
+WS = os.environ.get("PARITY_FLOOR_WEIGHTS", "")
+if WS:
+    from oracle.gen_golden_weightsets import WEIGHT_SETS  # noqa: E402
+    params = O.init_params(**WEIGHT_SETS[WS][0])
+    print(f"weights: {WS} {WEIGHT_SETS[WS][0]}", flush=True)
+else:
+    params = O.init_params(0)
 
 
 _time_embed32 = O.time_embed
