@@ -62,6 +62,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_consta
     constexpr int ATT_STAGES = ATT_RING_BYTES / ATT_STAGE_BYTES;
     constexpr int OFF_QL = 16384, OFF_KH = NP * 16384, OFF_KL = NP * 16384 + 16384, OFF_VL = 32768;
     constexpr uint32_t TM_S = 0, TM_O = 128;
+    // split format: the cross terms of S (Qh Kl^T + Ql Kh^T, 2^-11 of the magnitude) accumulate in their own TMEM columns and are
+    // added in the softmax -- the tensor core truncates its fp32 accumulator after every MMA, and the hi*hi accumulator then sees a
+    // third of the accumulations (same reasoning as the dual-accumulator GEMM, gemm_tcgen05.cuh)
+    constexpr uint32_t TM_S2 = 384;
 
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment for the 128B-swizzle tiles, computed as an OFFSET on the __shared__ array so the compiler keeps
@@ -142,8 +146,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_consta
                         const uint64_t adv = (uint64_t)(kk * 2);
                         ptx::umma_f16(tmem_base + TM_S, dQh + adv, dKh + adv, IDESC_S, (kb | kk) != 0);
                         if (NP == 2) {
-                            ptx::umma_f16(tmem_base + TM_S, dQh + adv, dKl + adv, IDESC_S, 1);
-                            ptx::umma_f16(tmem_base + TM_S, dQl + adv, dKh + adv, IDESC_S, 1);
+                            ptx::umma_f16(tmem_base + TM_S2, dQh + adv, dKl + adv, IDESC_S, (kb | kk) != 0);
+                            ptx::umma_f16(tmem_base + TM_S2, dQl + adv, dKh + adv, IDESC_S, 1);
                         }
                     }
                     ptx::umma_commit(&empty_bar[s]);
@@ -196,9 +200,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mQh, const __grid_consta
             for (int c = 0; c < 2; ++c) {
                 uint32_t raw[32];
                 ptx::tmem_ld_32x32(lane_addr + TM_S + hf * 64 + c * 32, raw);
-                ptx::tmem_ld_wait();
+                if (NP == 2) {
+                    uint32_t raw2[32];
+                    ptx::tmem_ld_32x32(lane_addr + TM_S2 + hf * 64 + c * 32, raw2);
+                    ptx::tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[c * 32 + j] = __uint_as_float(raw[j]);
+                    for (int j = 0; j < 32; ++j) v[c * 32 + j] = __uint_as_float(raw[j]) + __uint_as_float(raw2[j]);
+                } else {
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[c * 32 + j] = __uint_as_float(raw[j]);
+                }
             }
             const int k0 = hf * 64;
             float mx = -INFINITY;

@@ -179,6 +179,7 @@ struct TcImpl {
     // L2 zig-zag (EGOEGO_ZIGZAG, default on): consecutive kernels of a step walk the windows in OPPOSITE directions, so a
     // kernel starts with the rows its producer wrote last -- the part of its input that is still in the 126 MB L2 (the
     // per-kernel working set at 256 windows is 100-270 MB, so a same-direction walk misses everywhere).
+    bool dual_acc = true;                       // sampler engines: dual-accumulator split GEMMs (the selftest / training instances set it per call)
     int c8_clusters = 0;                        // co-resident clusters of 8 for the multicast GEMM (EGOEGO_GEMM_C8=1; 0 = off)
     bool zigzag = true;
     int dir = 0;                                // direction of the next kernel launched (0 = ascending windows)
@@ -229,9 +230,35 @@ static bool use_2cta() {
     return v == 1;
 }
 
+// dual-accumulator split GEMM (hi*hi and the cross terms in separate TMEM accumulators, see gemm_split3_2cta_kernel): default for the
+// 3-term steps of the sampler; EGOEGO_SPLIT_DUAL=0 restores the single accumulator
+static bool use_dual_acc() {
+    const char* e = getenv("EGOEGO_SPLIT_DUAL");          // read per launch: tools compare both settings in one process
+    return !(e && e[0] == '0');
+}
+template <int FMT, class Epi>
+static int launch_gemm_2cta_dual(TcImpl* I, const Plane& A, const Plane& W, int M, int N, int K, const Epi& epi, cudaStream_t s) {
+    static PerDeviceOnce attr_once;
+    auto kern = gemm_split3_2cta_kernel<FMT, Epi, true>;
+    constexpr int GEMM2_SMEM_BYTES = Gemm2Cfg<FMT>::SMEM_BYTES;
+    if (attr_once.need()) {
+        EG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_BYTES));
+    }
+    const int tiles = (M / 256) * (N / 256);
+    int pairs = I->sms / 2;
+    if (tiles < pairs) pairs = tiles;
+    LaunchCfg lc(2 * pairs, GEMM_THREADS, GEMM2_SMEM_BYTES, s, 2);
+    EG_CUDA(cudaLaunchKernelEx(&lc.cfg, kern, A.mhi, A.mlo, W.mhi128, W.mlo128, M, N, K, epi, I->next_dir()));
+    return 0;
+}
+
 // 2-CTA (cluster of 2, cta_group::2) launch: 256 x 256 tiles per CTA pair.
 template <int FMT, class Epi>
 static int launch_gemm_2cta(TcImpl* I, const Plane& A, const Plane& W, int M, int N, int K, const Epi& epi, cudaStream_t s) {
+    EG_CHECK(M % 256 == 0 && N % 256 == 0 && K % GEMM_BK == 0, "2-CTA gemm shape not tile-aligned");
+    if constexpr (FMT == FMT_SPLIT) {
+        if (I->dual_acc && use_dual_acc()) return launch_gemm_2cta_dual<FMT>(I, A, W, M, N, K, epi, s);
+    }
     static PerDeviceOnce attr_once;          // opt-in shared-memory size is a per-device function attribute
     auto kern = gemm_split3_2cta_kernel<FMT, Epi>;
     constexpr int GEMM2_SMEM_BYTES = Gemm2Cfg<FMT>::SMEM_BYTES;

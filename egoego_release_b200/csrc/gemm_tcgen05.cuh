@@ -103,9 +103,11 @@ __device__ __forceinline__ void epilogue_chunk(const Epi& epi, float4* tile, con
 
 // Drain this warp's 32 rows x NCOLS (=128) columns of an accumulator: bias in registers, operand prefetch one chunk ahead.
 // `wait_ready()` blocks until the accumulator may be read (called after the first prefetch has been issued).
+// `taddr2` != 0: a second accumulator of the same shape is added to the first (fp32, round to nearest) before the epilogue runs --
+// the cross-term accumulator of the dual-accumulator split GEMM.
 template <int NCOLS, class Epi, class Wait>
 __device__ __forceinline__ void epilogue_drain(const Epi& epi, float4* tile, uint32_t taddr, int lane, int row_base, int col_begin,
-                                               Wait wait_ready) {
+                                               Wait wait_ready, uint32_t taddr2 = 0) {
     static_assert(NCOLS == 128, "bias_lane covers exactly 32 lanes x 4 columns");
     const float4 bias_lane = epi.bias4(col_begin + 4 * lane);
     float4 pre[8];
@@ -119,7 +121,15 @@ __device__ __forceinline__ void epilogue_drain(const Epi& epi, float4* tile, uin
         if (c + 1 < NCOLS / 32) epilogue_prefetch(epi, pre, lane, row_base, col_begin + (c + 1) * 32);
         uint32_t r[32];
         ptx::tmem_ld_32x32(taddr + c * 32, r);
-        ptx::tmem_ld_wait();
+        if (taddr2) {
+            uint32_t r2[32];
+            ptx::tmem_ld_32x32(taddr2 + c * 32, r2);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]));
+        } else {
+            ptx::tmem_ld_wait();
+        }
         epilogue_chunk(epi, tile, r, lane, row_base, col_begin + c * 32, c, bias_lane, cur);
     }
 }
@@ -413,13 +423,21 @@ template <int FMT> struct Gemm2Cfg {
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + GEMM_EPI_WARPS * 4096 /*epilogue tiles*/ + 1024 + 256;
 };
 
-template <int FMT, class Epi>
+// DUAL = true (split formats only): the hi*hi products accumulate in one TMEM accumulator and the two cross terms (hi*lo, lo*hi:
+// 2^-11 of the magnitude) in a second one; the epilogue adds them in fp32.  The tensor core TRUNCATES its fp32 accumulator after
+// every MMA (measured: ~28 ulp on a K = 512 three-term product, i.e. ~0.3 ulp per accumulation, all of one sign), and that bias is
+// the same at every diffusion step -- the sampler integrates it like it integrated the fp16 weight rounding.  With
+// two accumulators the significant one sees a third of the accumulations (K/16 instead of 3K/16) and the truncation of the cross
+// accumulator is 2^-11 smaller.  Cost: both accumulators of a 256-column tile fill the 512 TMEM columns, so the epilogue of tile
+// i no longer overlaps the main loop of tile i + 1 (used for the 3-term steps only, whose main loop is three times longer).
+template <int FMT, class Epi, bool DUAL = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_split3_2cta_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl,
                         const __grid_constant__ CUtensorMap mWh, const __grid_constant__ CUtensorMap mWl,   // W maps: 128-row boxes
                         int M, int N, int K, Epi epi, int rev = 0 /* 1: walk the tiles from the last row block to the first (L2 zig-zag) */) {
     constexpr int BN = 256;
     constexpr int NP = Gemm2Cfg<FMT>::NP;
+    static_assert(!DUAL || NP == 2, "the dual-accumulator variant is for the 3-term split formats");
     constexpr int GEMM2_STAGES = Gemm2Cfg<FMT>::STAGES;
     constexpr int GEMM2_STAGE_BYTES = Gemm2Cfg<FMT>::STAGE_BYTES;
     constexpr int T_BYTES = GEMM_BM * GEMM_BK * 2;                   // 16 KB tile
@@ -486,11 +504,12 @@ gemm_split3_2cta_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_co
         if (lane == 0 && leader) {                       // ===== MMA issuer (leader CTA only) =====
             int s = 0; uint32_t ph = 0; int it = 0;
             for (int tile = pair; tile < total_tiles; tile += n_pairs, ++it) {
-                const int a = it & 1;
-                const uint32_t aph = (it >> 1) & 1;
+                const int a = DUAL ? 0 : (it & 1);
+                const uint32_t aph = DUAL ? (it & 1) : ((it >> 1) & 1);
                 ptx::mbar_wait(&tempty_bar[a], aph ^ 1);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + a * BN;
+                const uint32_t d_cross = DUAL ? tmem_base + BN : d_tmem;
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     ptx::mbar_wait(&full_bar[s], ph);
                     ptx::tc_fence_after();
@@ -502,8 +521,8 @@ gemm_split3_2cta_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_co
                         const uint64_t adv = (uint64_t)(kk * 2);
                         ptx::umma_f16_2cta(d_tmem, dAh + adv, dWh + adv, IDESC, (kb | kk) != 0);
                         if (NP == 2) {
-                            ptx::umma_f16_2cta(d_tmem, dAh + adv, dWl + adv, IDESC, 1);
-                            ptx::umma_f16_2cta(d_tmem, dAl + adv, dWh + adv, IDESC, 1);
+                            ptx::umma_f16_2cta(d_cross, dAh + adv, dWl + adv, IDESC, DUAL ? (uint32_t)((kb | kk) != 0) : 1u);
+                            ptx::umma_f16_2cta(d_cross, dAl + adv, dWh + adv, IDESC, 1);
                         }
                     }
                     ptx::umma_commit_2cta(&empty_bar[s]);
@@ -517,14 +536,14 @@ gemm_split3_2cta_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_co
         int it = 0;
         for (int tl = pair; tl < total_tiles; tl += n_pairs, ++it) {
             const int tile = rev ? total_tiles - 1 - tl : tl;
-            const int a = it & 1;
-            const uint32_t aph = (it >> 1) & 1;
+            const int a = DUAL ? 0 : (it & 1);
+            const uint32_t aph = DUAL ? (it & 1) : ((it >> 1) & 1);
             const int m0 = (tile / n_tiles) * 256 + (int)rank * 128, n0 = (tile % n_tiles) * BN;
             const int chalf = (warp - 2) >> 2;                 // which half of the tile columns this warp drains
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * BN + chalf * (BN / 2);
             float4* etile = epi_tiles + (warp - 2) * 256;
             epilogue_drain<BN / 2>(epi, etile, taddr, lane, m0 + quarter * 32, n0 + chalf * (BN / 2),
-                                   [&]() { ptx::mbar_wait(&tfull_bar[a], aph); ptx::tc_fence_after(); });
+                                   [&]() { ptx::mbar_wait(&tfull_bar[a], aph); ptx::tc_fence_after(); }, DUAL ? taddr + BN : 0u);
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_cluster(&tempty_bar[a], 0);
