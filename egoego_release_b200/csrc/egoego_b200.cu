@@ -60,9 +60,11 @@ struct egoego_ctx {
     Skeleton sk{}; bool have_sk = false;
     cudaStream_t own_stream = nullptr;
     cudaEvent_t ev_in = nullptr, ev_out = nullptr;
-    // one captured step per format: [0] = FMT_SPLIT, [1 + r] = FMT_HALF reading dithered weight set r (engine_tc.cu, upload_weight)
+    // one captured step per format: [0] = FMT_SPLIT with dual accumulators (the last `dual_last` steps), [1 + r] = FMT_HALF reading
+    // dithered weight set r (engine_tc.cu, upload_weight), [1 + MAX_WEIGHT_SETS] = FMT_SPLIT with a single accumulator
     static constexpr int MAX_WEIGHT_SETS = 16;
-    cudaGraphExec_t step_graph[1 + MAX_WEIGHT_SETS] = {};
+    cudaGraphExec_t step_graph[2 + MAX_WEIGHT_SETS] = {};
+    int dual_last = 16;                    // steps t < dual_last run the dual-accumulator split GEMMs (EGOEGO_DUAL_STEPS; >= N: every split step)
     int graph_B = -1, graph_T = -1; const void* graph_key[4] = {nullptr};
     int precise_last = 0;                  // steps t < precise_last use the 3-term split; earlier steps single-pass fp16
     bool use_graph = true;
@@ -264,6 +266,7 @@ int egoego_create(const egoego_cfg* cfg, egoego_handle* out) {
         if (pl > cfg->timesteps) pl = cfg->timesteps;
         c->precise_last = (cfg->engine == EGOEGO_ENGINE_TCGEN05) ? pl : cfg->timesteps;
     }
+    { const char* e = getenv("EGOEGO_DUAL_STEPS"); if (e && e[0]) c->dual_last = atoi(e); if (c->dual_last < 0) c->dual_last = 0; }
     if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming) != cudaSuccess) {
@@ -559,30 +562,41 @@ static int sample_chunk(egoego_ctx* c, const float* x_start, const float* cond_m
         return 0;
     };
     auto fmt_of_step = [&](int i) -> int { return (N - 1 - i) >= c->precise_last ? 1 : 0; };   // i-th executed step has t = N-1-i
+    // The 3-term split steps come in two kinds: the last `dual_last` steps (t < dual_last) keep hi*hi and the cross terms in separate
+    // TMEM accumulators (the tensor core's truncating fp32 accumulation is a bias that is the same at every step; an error made at
+    // step t reaches the final sample scaled by ~1/(t (t+1)), so only the last steps need the tighter, 18 % slower kernels).
+    const bool tc_engine = c->cfg.engine == EGOEGO_ENGINE_TCGEN05 && c->tc;
+    auto dual_of_step = [&](int i) -> bool { return tc_engine && (N - 1 - i) < c->dual_last; };
     // single-pass fp16 steps cycle through the dithered fp16 weight sets so that the weight rounding averages out over steps
-    // (slot 0 = split step, slot 1 + r = fp16 step reading copy r).  Averaging needs several full cycles: a run of fewer than
-    // 4 R fp16 steps reads the plain round-to-nearest copy instead (a single dithered copy is up to one ulp off, plain RN half).
-    int n_sets = (c->cfg.engine == EGOEGO_ENGINE_TCGEN05 && c->tc) ? std::min(c->tc->n_weight_sets(), (int)egoego_ctx::MAX_WEIGHT_SETS) : 1;
+    // (slot 0 = dual split step, slot 1 + r = fp16 step reading copy r, last slot = single-accumulator split step).  Averaging needs
+    // several full cycles: a run of fewer than 4 R fp16 steps reads the plain round-to-nearest copy instead (a single dithered copy
+    // is up to one ulp off, plain RN half).
+    int n_sets = tc_engine ? std::min(c->tc->n_weight_sets(), (int)egoego_ctx::MAX_WEIGHT_SETS) : 1;
     int n_half = 0;
     for (int i = 0; i < N; ++i) n_half += fmt_of_step(i);
     const bool dither = n_sets > 1 && n_half >= 4 * n_sets;
     if (!dither) n_sets = 1;
-    auto slot_of_step = [&](int i) -> int { return fmt_of_step(i) ? 1 + (i % n_sets) : 0; };
-    auto select_set = [&](int slot) { if (c->tc) c->tc->use_weight_set((dither && slot > 0) ? slot - 1 : -1); };
+    constexpr int SLOT_SINGLE = 1 + egoego_ctx::MAX_WEIGHT_SETS;
+    auto slot_of_step = [&](int i) -> int { return fmt_of_step(i) ? 1 + (i % n_sets) : ((tc_engine && !dual_of_step(i)) ? SLOT_SINGLE : 0); };
+    auto select_set = [&](int slot) {
+        if (!c->tc) return;
+        c->tc->use_weight_set((dither && slot > 0 && slot < SLOT_SINGLE) ? slot - 1 : -1);
+        c->tc->set_dual_acc(slot != SLOT_SINGLE);
+    };
     const void* key[4] = {ns.tape, inpaint, (const void*)(uintptr_t)(ns.seed ^ (ns.window_offset * 0x9E3779B97F4A7C15ull)),
                           (const void*)(uintptr_t)(((uint64_t)inpaint_len << 32) ^ (uint64_t)ns.draw_stride)};
     if (c->use_graph) {
         bool reuse = c->graph_B == Bc && c->graph_T == T && !memcmp(key, c->graph_key, sizeof(key));
         if (!reuse) for (auto& g : c->step_graph) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
-        for (int slot = 0; slot < 1 + n_sets; ++slot) {
+        for (int slot = 0; slot <= SLOT_SINGLE; ++slot) {
             bool needed = false;
             for (int i = 0; i < N && !needed; ++i) needed = slot_of_step(i) == slot;
             if (!needed || c->step_graph[slot]) continue;
             cudaGraph_t g = nullptr;
             int64_t before = c->launches;
-            select_set(slot);                           // tensor maps are kernel arguments: captured by value
+            select_set(slot);                           // tensor maps and the accumulator mode are launch-time choices: captured by value
             EG_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-            int rc = one_step(s, slot ? 1 : 0);
+            int rc = one_step(s, (slot >= 1 && slot < SLOT_SINGLE) ? 1 : 0);
             cudaError_t ce = cudaStreamEndCapture(s, &g);
             c->launches = before;                       // captured, not launched
             select_set(0);
@@ -839,7 +853,7 @@ int egoego_precise_last_steps(egoego_handle c) { return c ? c->precise_last : -1
 int egoego_engine_info(egoego_handle c, char* buf, int n) {
     EG_CHECK(c && buf && n > 0, "null argument");
     std::string s = (c->cfg.engine == EGOEGO_ENGINE_TCGEN05 && c->tc) ? c->tc->info() : std::string(c->cfg.engine == EGOEGO_ENGINE_SIMT ? "engine=simt" : "engine=tcgen05 (weights not committed)");
-    s += " precise_last_steps=" + std::to_string(c->precise_last);
+    s += " precise_last_steps=" + std::to_string(c->precise_last) + " dual_accumulator_steps=" + std::to_string(std::min(c->dual_last, c->precise_last));
     snprintf(buf, (size_t)n, "%s", s.c_str());
     return 0;
 }

@@ -456,6 +456,7 @@ std::string TcEngine::info() const {
 }
 
 int TcEngine::n_weight_sets() const { return impl_ && !impl_->Wx.set16.empty() ? (int)impl_->Wx.set16.size() : 1; }
+void TcEngine::set_dual_acc(bool on) { if (impl_) impl_->dual_acc = on; }
 void TcEngine::use_weight_set(int r) {
     TcImpl* I = impl_;
     if (!I) return;

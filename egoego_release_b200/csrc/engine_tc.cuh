@@ -48,6 +48,8 @@ public:
     // r < 0 selects the plain round-to-nearest copy (the default outside the loop)
     int n_weight_sets() const;
     void use_weight_set(int r);
+    // 3-term split launches: hi*hi and the cross terms in separate TMEM accumulators (true, the default) or in one (false)
+    void set_dual_acc(bool on);
     int time_stage(int B, int T, int stage, int fmt, int iters, float* model_out, cudaStream_t s, float* ms, const DdpmArgs* fuse = nullptr);
     // "key=value ..." description of the resolved kernel choices (cluster counts, zig-zag, fused LN)
     std::string info() const;
