@@ -70,6 +70,46 @@ struct EpiOut {              // linear_out on tokens 1..T -> compact [B,T,d_feat
 };
 
 // ---------------------------------------------------------------------------------------------
+// Small-M SGEMM: same contract as sgemm_tn_kernel below with 32 x 32 x 32 tiles (2 x 2 per thread, M % 32 == 0, K % 32 == 0): the
+// stage-1 sequence nets run one 128-row window at a time, where 128 x 128 tiles leave all but 2-24 of the 148 SMs idle and
+// each CTA walks the whole K alone (latency-bound: ~37 us for K = 1024); 16x more, 16x lighter CTAs finish in a few us.
+// The fmaf chain over k is in the same order as in sgemm_tn_kernel, so results are bit-identical to it.
+// ---------------------------------------------------------------------------------------------
+template <class Epi>
+__global__ void __launch_bounds__(256) sgemm_tn_small_kernel(const float* __restrict__ A, int lda,
+                                                             const float* __restrict__ W, int ldw,
+                                                             int N, int K, Epi epi) {
+    __shared__ __align__(16) float As[32][32 + 4];
+    __shared__ __align__(16) float Bs[32][32 + 4];
+    const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+    const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+    float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+    const int r = tid / 8, k4 = (tid % 8) * 4;            // one float4 of A and of W per thread and k-block
+    for (int k0 = 0; k0 < K; k0 += 32) {
+        const float4 a = *reinterpret_cast<const float4*>(A + (long long)(m0 + r) * lda + k0 + k4);
+        As[k4 + 0][r] = a.x; As[k4 + 1][r] = a.y; As[k4 + 2][r] = a.z; As[k4 + 3][r] = a.w;
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (n0 + r < N) b = *reinterpret_cast<const float4*>(W + (long long)(n0 + r) * ldw + k0 + k4);
+        Bs[k4 + 0][r] = b.x; Bs[k4 + 1][r] = b.y; Bs[k4 + 2][r] = b.z; Bs[k4 + 3][r] = b.w;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+            const float a0 = As[k][ty * 2], a1 = As[k][ty * 2 + 1], b0 = Bs[k][tx * 2], b1 = Bs[k][tx * 2 + 1];
+            acc[0][0] = fmaf(a0, b0, acc[0][0]); acc[0][1] = fmaf(a0, b1, acc[0][1]);
+            acc[1][0] = fmaf(a1, b0, acc[1][0]); acc[1][1] = fmaf(a1, b1, acc[1][1]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int col = n0 + tx * 2 + j;
+            if (col < N) epi(m0 + ty * 2 + i, col, acc[i][j]);
+        }
+}
+
+// ---------------------------------------------------------------------------------------------
 // SGEMM: C[M,N] = A[M,K] * W[N,K]^T, fp32, 128x128x16 tiles, 8x8 per thread.
 // Requires M % 128 == 0, K % 16 == 0, lda/ldw % 4 == 0; N arbitrary (guarded).
 // ---------------------------------------------------------------------------------------------

@@ -286,6 +286,13 @@ static int s1_expected(const egoego_seqnet_ctx* c, std::map<std::string, int64_t
     return 0;
 }
 
+// C = A W^T + epilogue: 32 x 32 tiles while the problem is a handful of windows (latency-bound), 128 x 128 tiles otherwise
+template <class Epi>
+static void s1_gemm(const float* A, int lda, const float* W, int ldw, int M, int N, int K, const Epi& e, cudaStream_t s) {
+    if (M <= 1024 && K % 32 == 0) sgemm_tn_small_kernel<<<dim3((N + 31) / 32, M / 32), 256, 0, s>>>(A, lda, W, ldw, N, K, e);
+    else                          sgemm_tn_kernel<<<dim3((N + 127) / 128, M / 128), 256, 0, s>>>(A, lda, W, ldw, N, K, e);
+}
+
 extern "C" {
 
 int egoego_seqnet_create(const egoego_seqnet_cfg* cfg, egoego_seqnet* out) {
@@ -405,21 +412,21 @@ int egoego_seqnet_forward(egoego_seqnet c, const float* feats, int B, int T, flo
         const long long tot = (long long)B * T * g.d_feats;
         s1_stage_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(c->Ain.p, c->kpad, feats, g.d_feats, B, T);
         S1EpiStart e{c->H.p, d, c->start_b.p, c->pos.p, g.window};
-        sgemm_tn_kernel<<<dim3(d / 128, M / 128), 256, 0, s>>>(c->Ain.p, c->kpad, c->start_w.p, c->kpad, d, c->kpad, e);
+        s1_gemm(c->Ain.p, c->kpad, c->start_w.p, c->kpad, M, d, c->kpad, e, s);
         c->launches += 2;
     }
     for (auto& Lp : c->layers) {
         S1Layer& w = *Lp;
         EpiBiasScale eq{c->QKV.p, nqkv, w.bqkv.p, H * dk, 1.0f / sqrtf((float)dk)};
-        sgemm_tn_kernel<<<dim3(nqkv / 128, M / 128), 256, 0, s>>>(c->H.p, d, w.wqkv.p, d, nqkv, d, eq);
+        s1_gemm(c->H.p, d, w.wqkv.p, d, M, nqkv, d, eq, s);
         attention_simt_kernel<false><<<B * H, 256, ATT_SIMT_SMEM, s>>>(c->QKV.p, nqkv, c->O.p, nullptr, nullptr, H * dk, H, g.window);
         EpiBiasResid ef{c->Y.p, d, w.fc_b.p, c->H.p};
-        sgemm_tn_kernel<<<dim3(d / 128, M / 128), 256, 0, s>>>(c->O.p, H * dk, w.fc_w.p, H * dk, d, H * dk, ef);
+        s1_gemm(c->O.p, H * dk, w.fc_w.p, H * dk, M, d, H * dk, ef, s);
         s1_layernorm_kernel<256><<<M / 8, 256, 0, s>>>(c->Y.p, c->H.p, w.ln1_g.p, w.ln1_b.p, c->n_valid, M);
         EpiBiasRelu e1{c->F.p, d, w.b1.p};
-        sgemm_tn_kernel<<<dim3(d / 128, M / 128), 256, 0, s>>>(c->H.p, d, w.w1.p, d, d, d, e1);
+        s1_gemm(c->H.p, d, w.w1.p, d, M, d, d, e1, s);
         EpiBiasResid e2{c->Y.p, d, w.b2.p, c->H.p};
-        sgemm_tn_kernel<<<dim3(d / 128, M / 128), 256, 0, s>>>(c->F.p, d, w.w2.p, d, d, d, e2);
+        s1_gemm(c->F.p, d, w.w2.p, d, M, d, d, e2, s);
         s1_layernorm_kernel<256><<<M / 8, 256, 0, s>>>(c->Y.p, c->H.p, w.ln2_g.p, w.ln2_b.p, c->n_valid, M);
         c->launches += 7;
     }
@@ -434,12 +441,12 @@ int egoego_seqnet_forward(egoego_seqnet c, const float* feats, int B, int T, flo
         float* buf[2] = {c->T1.p, c->T2.p};
         for (size_t j = 0; j < hd.dims.size(); ++j) {
             EpiBiasRelu e{buf[j & 1], hd.dims[j], hd.b[j].p};
-            sgemm_tn_kernel<<<dim3((hd.dims[j] + 127) / 128, M / 128), 256, 0, s>>>(x, last, hd.w[j].p, last, hd.dims[j], last, e);
+            s1_gemm(x, last, hd.w[j].p, last, M, hd.dims[j], last, e, s);
             x = buf[j & 1]; last = hd.dims[j];
             c->launches++;
         }
         S1EpiHeadOut eo{outs[h], hd.out, hd.fc_b.p, token0_only ? 1 : T};
-        sgemm_tn_kernel<<<dim3((hd.out + 127) / 128, M / 128), 256, 0, s>>>(x, last, hd.fc_w.p, last, hd.out, last, eo);
+        s1_gemm(x, last, hd.fc_w.p, last, M, hd.out, last, eo, s);
         c->launches++;
     }
     EG_CUDA(cudaGetLastError());
