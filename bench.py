@@ -569,7 +569,7 @@ def main():
                   if K_prec < N else "fp16 hi/lo 3-term split (fp32 accumulate)") if eng == "tcgen05" else "f32",
         "data": "synthetic", "config": dict(cfg, engine=eng, precise_last_steps=K_prec, weight_sets=W_sets),
         "e2e": {"value": e2e, "unit": "windows/s", "h2d_bytes_per_step": 2 * B * T * D * 4 * world, "d2h_bytes_per_step": B * T * D * 4 * world},
-        "gpu_launches": int(launches), "clocks": clocks, "shard_check": shard_check,
+        "gpu_launches": int(launches), "clocks": clocks, "shard_check": shard_check, "engine_info": m.engine_info(),
         "path_roofline": {"bound": "tensor", "achieved": path_tflops, "peak": peak, "unit": "TFLOP/s", "frac": path_tflops / peak,
                           "scope": "whole sampling path: algorithmic 2.8507 TFLOP per 1000-step window / wall time, per GPU"},
     }
@@ -652,7 +652,8 @@ def main():
         line["parity_vs_reference"] = parity_vs_reference(m, dev, N)
     else:
         line["roofline"] = dict(line["path_roofline"], traffic=None, peak_source=pk_src)
-    if world == 1 and eng == "tcgen05":
+    light = bool(os.environ.get("EGOEGO_BENCH_LIGHT"))      # profiler runs: headline + kernel table only
+    if world == 1 and eng == "tcgen05" and not light:
         # the same workload with EVERY step in the fp32-grade 3-term split format (precise_last_steps = N): what the path costs
         # without the step-adaptive precision policy
         try:
@@ -663,6 +664,7 @@ def main():
             line["all_split_windows_per_s"] = {"error": repr(ex)[:200]}
     if world == 1:                                       # reported baseline: rank 0 at N = 1 only
         line["cpu_baseline"] = cpu_baseline(32, T, N, a.cpu_seconds)
+    if world == 1 and not light:
         try:
             line["next_rows"] = next_rows(dev, B, T, pk)
             line["single_window_latency"] = config1_latency(dev, T)
