@@ -97,15 +97,27 @@ def q_sample(sched, x_start, t, noise):
 
 
 def p_losses(p: Dict[str, torch.Tensor], sched, x_start, cond_mask, t, noise, cond_noise,
-             padding_mask: Optional[torch.Tensor] = None, objective: str = "pred_x0", loss_type: str = "l1", dropout=None) -> torch.Tensor:
+             padding_mask: Optional[torch.Tensor] = None, objective: str = "pred_x0", loss_type: str = "l1", dropout=None,
+             l1_sign: Optional[torch.Tensor] = None, resid_out: Optional[list] = None) -> torch.Tensor:
     """:574-605.  t int64 [B]; noise / cond_noise [B,T,D]; padding_mask bool [B,1,T+1] or None; dropout: None (eval mode) or a
-    DropoutMasks (train mode)."""
+    DropoutMasks (train mode).
+
+    Test hooks (not part of the reference): `resid_out` receives the detached residual out - target; `l1_sign` [B,T,D] replaces
+    |d| by l1_sign * d wherever it is not NaN.  The L1 gradient is sign(d) / N per output element -- discontinuous at d = 0 -- so two
+    fp32-grade implementations whose outputs differ by 1e-5 legitimately disagree on the WHOLE contribution of an element whose
+    residual is smaller than that; the GPU gradient test enumerates the signs of those few elements."""
     x = q_sample(sched, x_start, t, noise)
     x_cond = x_start * (1.0 - cond_mask) + cond_mask * cond_noise
     out = O.denoiser_forward(p, torch.cat((x, x_cond), dim=-1), t, padding_mask, dropout=dropout)
     target = noise if objective == "pred_noise" else x_start
     fn = F.l1_loss if loss_type == "l1" else F.mse_loss
     loss = fn(out, target, reduction="none")
+    if resid_out is not None:
+        resid_out.append((out - target).detach())
+    if l1_sign is not None:
+        assert loss_type == "l1"
+        given = ~torch.isnan(l1_sign)
+        loss = torch.where(given, torch.nan_to_num(l1_sign) * (out - target), loss)
     if padding_mask is not None:
         loss = loss * padding_mask[:, 0, 1:][:, :, None]
     loss = loss.reshape(loss.shape[0], -1).mean(dim=1)
@@ -113,10 +125,12 @@ def p_losses(p: Dict[str, torch.Tensor], sched, x_start, cond_mask, t, noise, co
     return loss.mean()
 
 
-def loss_and_grads(p, sched, x_start, cond_mask, t, noise, cond_noise, padding_mask=None, objective="pred_x0", dropout=None):
+def loss_and_grads(p, sched, x_start, cond_mask, t, noise, cond_noise, padding_mask=None, objective="pred_x0", dropout=None,
+                   loss_type="l1", l1_sign=None, resid_out=None):
     """Loss and d loss / d parameter for every trainable tensor of the denoiser (the positional table is frozen)."""
     q = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "position_vec" not in k else v) for k, v in p.items()}
-    loss = p_losses(q, sched, x_start, cond_mask, t, noise, cond_noise, padding_mask, objective, dropout=dropout)
+    loss = p_losses(q, sched, x_start, cond_mask, t, noise, cond_noise, padding_mask, objective, loss_type=loss_type, dropout=dropout,
+                    l1_sign=l1_sign, resid_out=resid_out)
     loss.backward()
     return loss.detach(), {k: v.grad for k, v in q.items() if v.requires_grad and v.grad is not None}
 

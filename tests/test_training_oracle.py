@@ -89,17 +89,38 @@ def test_gpu_training_step_vs_reference_golden(tag, B, T, seed, with_pm, dseed, 
         assert err < 0.25, (k, err, v.numpy()[:4], ref[:4])
         assert abs(v.numpy()[0] - ref[0]) < 3e-3 * scale and np.abs(v.numpy()[2:] - ref[2:]).max() < 3e-3 * scale, (k, v.numpy()[:4], ref[:4])
     print(f"[{tag}] loss {float(loss.detach()):.6f} vs {float(g[f'{tag}_loss']):.6f}; worst gradient fingerprint error {worst[0]:.2e} of its norm ({worst[1]})")
-    # full tensors: every element of every gradient against the oracle's autograd result (same inputs, same dropout masks)
+    # full tensors: every element of every gradient against the oracle's autograd result (same inputs, same dropout masks).
+    # The L1 gradient of an output element is sign(out - target) / N: an element whose residual is smaller than the difference between
+    # two fp32-grade forwards (the CUDA products are 3-term bf16 splits, 1e-5) carries an undetermined sign, and its whole
+    # contribution (2 / N times the activation row, 3.5e-2 of linear_out.weight's largest entry in the 2 x 30-frame dropout case,
+    # whose smallest residual is 5.7e-6) flips.  The oracle therefore enumerates the signs of the elements with |residual| < 3e-5
+    # (at most a handful) and the CUDA gradients must match ONE assignment, every element of every tensor.
     drop = None if dseed is None else TR.DropoutMasks(dseed, 0.1)
-    _, og = TR.loss_and_grads(params0, O.make_schedule(1000), x_start, cm, t, noise, cond_noise, pm, dropout=drop)
-    worst_full = (0.0, "")
-    for k, gv in grads.items():
-        ref = og[k]
-        rel = float((gv - ref).abs().max() / max(float(ref.abs().max()), 1e-7))
-        worst_full = max(worst_full, (rel, k))
-        assert rel < 2e-2, (k, rel)                 # max element error relative to the tensor's largest gradient entry (measured worst: 1.03e-2 on
-                                                    # w_k.weight of the 2 x 30-frame dropout case, whose key gradients nearly cancel; 2e-3 .. 4e-3 elsewhere)
-    print(f"[{tag}] full-tensor gradients vs oracle autograd: worst max-abs error {worst_full[0]:.2e} of the tensor's max ({worst_full[1]})")
+    resid = []
+    _, og0 = TR.loss_and_grads(params0, O.make_schedule(1000), x_start, cm, t, noise, cond_noise, pm, dropout=drop, resid_out=resid)
+    amb = (resid[0].abs() < 3e-5).nonzero()
+    assert len(amb) <= 4, f"{len(amb)} sign-ambiguous residuals: pick another test case"
+    candidates = []
+    for bits in range(1 << len(amb)):
+        if len(amb) == 0:
+            og = og0
+        else:
+            sgn = torch.full_like(resid[0], float("nan"))
+            for j, idx in enumerate(amb):
+                sgn[tuple(idx.tolist())] = 1.0 if (bits >> j) & 1 else -1.0
+            _, og = TR.loss_and_grads(params0, O.make_schedule(1000), x_start, cm, t, noise, cond_noise, pm, dropout=drop, l1_sign=sgn)
+        worst_full = (0.0, "")
+        for k, gv in grads.items():
+            ref = og[k]
+            rel = float((gv - ref).abs().max() / max(float(ref.abs().max()), 1e-7))
+            worst_full = max(worst_full, (rel, k))
+        candidates.append(worst_full)
+    worst_full = min(candidates)
+    # max element error relative to the tensor's largest gradient entry (measured worst: 1.03e-2 on w_k.weight of the 2 x 30-frame
+    # dropout case, whose key gradients nearly cancel; 2e-3 .. 4e-3 elsewhere)
+    assert worst_full[0] < 2e-2, (worst_full, candidates)
+    print(f"[{tag}] full-tensor gradients vs oracle autograd ({len(amb)} sign-ambiguous residual(s), {len(candidates)} assignment(s)): "
+          f"worst max-abs error {worst_full[0]:.2e} of the tensor's max ({worst_full[1]})")
     # a small gradient-descent step through a stock torch optimizer lowers the loss on the same batch: the gradients point downhill
     # and the engine picks up the updated parameters
     opt = torch.optim.SGD(m.parameters(), lr=1e-3)
@@ -108,3 +129,32 @@ def test_gpu_training_step_vs_reference_golden(tag, B, T, seed, with_pm, dseed, 
                        cond_noise=cond_noise.cuda(), dropout_seed=dseed)
     print(f"[{tag}] loss after one SGD step: {float(loss2.detach()):.6f} (before {float(loss.detach()):.6f})")
     assert float(loss2.detach()) < float(loss.detach())
+
+
+@pytest.mark.gpu
+def test_gpu_training_step_l2_loss_full_gradients(params0):
+    """The same step with loss_type='l2' (transformer_cond_diffusion_model.py:607-613: F.mse_loss): a SMOOTH objective, so every
+    element of every gradient is compared with the oracle's autograd result without the sign caveat of the L1 cases."""
+    import torch
+    import egoego_release_b200 as E
+    tag, B, T, seed, with_pm, dseed = DROP_CASES[-1]
+    m = E.CondGaussianDiffusion(d_feats=198, d_model=512, n_dec_layers=4, n_head=4, d_k=256, d_v=256, max_timesteps=121,
+                                out_dim=198, timesteps=1000, objective="pred_x0", loss_type="l2", max_batch=4)
+    m.load_state_dict(params0, strict=False)
+    m = m.cuda()
+    m.train(True)
+    x_start, cm, t, noise, cond_noise, pm = case_inputs(seed, B, T, with_pm)
+    loss = m.p_losses(x_start.cuda(), cm.cuda(), t.cuda(), noise=noise.cuda(), padding_mask=None if pm is None else pm.cuda(),
+                      cond_noise=cond_noise.cuda(), dropout_seed=dseed)
+    loss.backward()
+    grads = {k: v.grad.detach().cpu() for k, v in m.named_parameters() if v.grad is not None}
+    ol, og = TR.loss_and_grads(params0, O.make_schedule(1000), x_start, cm, t, noise, cond_noise, pm, dropout=TR.DropoutMasks(dseed, 0.1),
+                               loss_type="l2")
+    assert abs(float(loss.detach()) - float(ol)) < 2e-5 * max(1.0, float(ol)), (float(loss.detach()), float(ol))
+    worst = (0.0, "")
+    for k, gv in grads.items():
+        ref = og[k]
+        rel = float((gv - ref).abs().max() / max(float(ref.abs().max()), 1e-7))
+        worst = max(worst, (rel, k))
+    print(f"[l2 {tag}] loss {float(loss.detach()):.6f} vs {float(ol):.6f}; full-tensor gradients: worst max-abs error {worst[0]:.2e} of the tensor's max ({worst[1]})")
+    assert len(grads) == 72 and worst[0] < 1e-2, worst
