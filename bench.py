@@ -12,6 +12,7 @@ denoiser, synthetic head-pose cond, 1xB200").  `value` is device-resident throug
 import argparse
 import json
 import os
+import re
 import statistics
 import subprocess
 import sys
@@ -558,16 +559,21 @@ def main():
     path_tflops = value / world * N * FLOP_PER_WINDOW_CALL / 1e12          # per GPU
     peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
     W_sets = 1
+    S_split = None
     if eng == "tcgen05":
         K_prec = m.precise_last_steps()
         W_sets = m.weight_sets()
+        mm = re.search(r"split_steps=(\d+)", m.engine_info())
+        S_split = int(mm.group(1)) if mm else K_prec
     line = {
         "metric": "motion-windows/sec (T=120, 1000-step)", "value": value, "unit": "windows/s", "n_gpus": world,
         "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None,
-        "dtype": (f"fp16 single-pass (dithered weight sets x{W_sets}) for t>={K_prec}, fp16 hi/lo 3-term split for t<{K_prec} (fp32 accumulate)"
+        "dtype": (f"fp16 single-pass (dithered weight sets x{W_sets}) for t>={K_prec}, "
+                  + (f"fp16 activations x fp16 hi/lo weight pair for {S_split}<=t<{K_prec}, " if S_split < K_prec else "")
+                  + f"fp16 hi/lo 3-term split for t<{S_split} (fp32 accumulate)"
                   if K_prec < N else "fp16 hi/lo 3-term split (fp32 accumulate)") if eng == "tcgen05" else "f32",
-        "data": "synthetic", "config": dict(cfg, engine=eng, precise_last_steps=K_prec, weight_sets=W_sets),
+        "data": "synthetic", "config": dict(cfg, engine=eng, precise_last_steps=K_prec, split_steps=S_split, weight_sets=W_sets),
         "e2e": {"value": e2e, "unit": "windows/s", "h2d_bytes_per_step": 2 * B * T * D * 4 * world, "d2h_bytes_per_step": B * T * D * 4 * world},
         "gpu_launches": int(launches), "clocks": clocks, "shard_check": shard_check, "engine_info": m.engine_info(),
         "path_roofline": {"bound": "tensor", "achieved": path_tflops, "peak": peak, "unit": "TFLOP/s", "frac": path_tflops / peak,

@@ -61,9 +61,12 @@ struct egoego_ctx {
     cudaStream_t own_stream = nullptr;
     cudaEvent_t ev_in = nullptr, ev_out = nullptr;
     // one captured step per format: [0] = FMT_SPLIT with dual accumulators (the last `dual_last` steps), [1 + r] = FMT_HALF reading
-    // dithered weight set r (engine_tc.cu, upload_weight), [1 + MAX_WEIGHT_SETS] = FMT_SPLIT with a single accumulator
+    // dithered weight set r (engine_tc.cu, upload_weight), [1 + MAX_WEIGHT_SETS] = FMT_SPLIT with a single accumulator,
+    // [2 + MAX_WEIGHT_SETS] = FMT_HALF kernels reading the weights as an fp16 pair in two passes ("pair" steps)
     static constexpr int MAX_WEIGHT_SETS = 16;
-    cudaGraphExec_t step_graph[2 + MAX_WEIGHT_SETS] = {};
+    cudaGraphExec_t step_graph[3 + MAX_WEIGHT_SETS] = {};
+    int split_last = 16;                   // of the last `precise_last` steps, those with t < split_last run the 3-term split; the others
+                                           // (split_last <= t < precise_last) fp16 activations x fp16-pair weights (EGOEGO_SPLIT_STEPS; >= N: all split)
     int dual_last = 16;                    // steps t < dual_last run the dual-accumulator split GEMMs (EGOEGO_DUAL_STEPS; >= N: every split step)
     int graph_B = -1, graph_T = -1; const void* graph_key[4] = {nullptr};
     int precise_last = 0;                  // steps t < precise_last use the 3-term split; earlier steps single-pass fp16
@@ -267,6 +270,9 @@ int egoego_create(const egoego_cfg* cfg, egoego_handle* out) {
         c->precise_last = (cfg->engine == EGOEGO_ENGINE_TCGEN05) ? pl : cfg->timesteps;
     }
     { const char* e = getenv("EGOEGO_DUAL_STEPS"); if (e && e[0]) c->dual_last = atoi(e); if (c->dual_last < 0) c->dual_last = 0; }
+    // precise_last_steps >= timesteps is the "3-term split at every step" engine (the in-library fp32-grade reference of tests and tools)
+    if (c->precise_last >= cfg->timesteps) c->split_last = cfg->timesteps;
+    { const char* e = getenv("EGOEGO_SPLIT_STEPS"); if (e && e[0]) c->split_last = atoi(e); if (c->split_last < 0) c->split_last = 0; }
     if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming) != cudaSuccess) {
@@ -561,11 +567,16 @@ static int sample_chunk(egoego_ctx* c, const float* x_start, const float* cond_m
         EG_CUDA(cudaGetLastError());
         return 0;
     };
-    auto fmt_of_step = [&](int i) -> int { return (N - 1 - i) >= c->precise_last ? 1 : 0; };   // i-th executed step has t = N-1-i
+    const bool tc_engine = c->cfg.engine == EGOEGO_ENGINE_TCGEN05 && c->tc;
+    // The last `precise_last` steps come in two precisions: t < split_last in the 3-term split (fp32-grade products), the others with
+    // fp16 activations against the fp16 hi/lo PAIR of every weight (FMT_HALF kernels, two passes over K).  What the sampler
+    // integrates coherently over steps is the WEIGHT rounding; the activation rounding is fresh at every step and its
+    // effect on the final sample is scaled by ~1/(t (t+1)).
+    auto pair_of_step = [&](int i) -> bool { const int t = N - 1 - i; return tc_engine && t < c->precise_last && t >= c->split_last; };
+    auto fmt_of_step = [&](int i) -> int { return ((N - 1 - i) >= c->precise_last || pair_of_step(i)) ? 1 : 0; };   // i-th executed step has t = N-1-i
     // The 3-term split steps come in two kinds: the last `dual_last` steps (t < dual_last) keep hi*hi and the cross terms in separate
     // TMEM accumulators (the tensor core's truncating fp32 accumulation is a bias that is the same at every step; an error made at
     // step t reaches the final sample scaled by ~1/(t (t+1)), so only the last steps need the tighter, 18 % slower kernels).
-    const bool tc_engine = c->cfg.engine == EGOEGO_ENGINE_TCGEN05 && c->tc;
     auto dual_of_step = [&](int i) -> bool { return tc_engine && (N - 1 - i) < c->dual_last; };
     // single-pass fp16 steps cycle through the dithered fp16 weight sets so that the weight rounding averages out over steps
     // (slot 0 = dual split step, slot 1 + r = fp16 step reading copy r, last slot = single-accumulator split step).  Averaging needs
@@ -573,22 +584,26 @@ static int sample_chunk(egoego_ctx* c, const float* x_start, const float* cond_m
     // is up to one ulp off, plain RN half).
     int n_sets = tc_engine ? std::min(c->tc->n_weight_sets(), (int)egoego_ctx::MAX_WEIGHT_SETS) : 1;
     int n_half = 0;
-    for (int i = 0; i < N; ++i) n_half += fmt_of_step(i);
+    for (int i = 0; i < N; ++i) n_half += (fmt_of_step(i) && !pair_of_step(i)) ? 1 : 0;
     const bool dither = n_sets > 1 && n_half >= 4 * n_sets;
     if (!dither) n_sets = 1;
-    constexpr int SLOT_SINGLE = 1 + egoego_ctx::MAX_WEIGHT_SETS;
-    auto slot_of_step = [&](int i) -> int { return fmt_of_step(i) ? 1 + (i % n_sets) : ((tc_engine && !dual_of_step(i)) ? SLOT_SINGLE : 0); };
+    constexpr int SLOT_SINGLE = 1 + egoego_ctx::MAX_WEIGHT_SETS, SLOT_PAIR = 2 + egoego_ctx::MAX_WEIGHT_SETS;
+    auto slot_of_step = [&](int i) -> int {
+        if (pair_of_step(i)) return SLOT_PAIR;
+        return fmt_of_step(i) ? 1 + (i % n_sets) : ((tc_engine && !dual_of_step(i)) ? SLOT_SINGLE : 0);
+    };
     auto select_set = [&](int slot) {
         if (!c->tc) return;
         c->tc->use_weight_set((dither && slot > 0 && slot < SLOT_SINGLE) ? slot - 1 : -1);
         c->tc->set_dual_acc(slot != SLOT_SINGLE);
+        c->tc->set_weight_pair(slot == SLOT_PAIR);
     };
     const void* key[4] = {ns.tape, inpaint, (const void*)(uintptr_t)(ns.seed ^ (ns.window_offset * 0x9E3779B97F4A7C15ull)),
                           (const void*)(uintptr_t)(((uint64_t)inpaint_len << 32) ^ (uint64_t)ns.draw_stride)};
     if (c->use_graph) {
         bool reuse = c->graph_B == Bc && c->graph_T == T && !memcmp(key, c->graph_key, sizeof(key));
         if (!reuse) for (auto& g : c->step_graph) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
-        for (int slot = 0; slot <= SLOT_SINGLE; ++slot) {
+        for (int slot = 0; slot <= SLOT_PAIR; ++slot) {
             bool needed = false;
             for (int i = 0; i < N && !needed; ++i) needed = slot_of_step(i) == slot;
             if (!needed || c->step_graph[slot]) continue;
@@ -596,7 +611,7 @@ static int sample_chunk(egoego_ctx* c, const float* x_start, const float* cond_m
             int64_t before = c->launches;
             select_set(slot);                           // tensor maps and the accumulator mode are launch-time choices: captured by value
             EG_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-            int rc = one_step(s, (slot >= 1 && slot < SLOT_SINGLE) ? 1 : 0);
+            int rc = one_step(s, ((slot >= 1 && slot < SLOT_SINGLE) || slot == SLOT_PAIR) ? 1 : 0);
             cudaError_t ce = cudaStreamEndCapture(s, &g);
             c->launches = before;                       // captured, not launched
             select_set(0);
@@ -853,7 +868,8 @@ int egoego_precise_last_steps(egoego_handle c) { return c ? c->precise_last : -1
 int egoego_engine_info(egoego_handle c, char* buf, int n) {
     EG_CHECK(c && buf && n > 0, "null argument");
     std::string s = (c->cfg.engine == EGOEGO_ENGINE_TCGEN05 && c->tc) ? c->tc->info() : std::string(c->cfg.engine == EGOEGO_ENGINE_SIMT ? "engine=simt" : "engine=tcgen05 (weights not committed)");
-    s += " precise_last_steps=" + std::to_string(c->precise_last) + " dual_accumulator_steps=" + std::to_string(std::min(c->dual_last, c->precise_last));
+    s += " precise_last_steps=" + std::to_string(c->precise_last) + " split_steps=" + std::to_string(std::min(c->split_last, c->precise_last)) +
+         " dual_accumulator_steps=" + std::to_string(std::min(c->dual_last, std::min(c->split_last, c->precise_last)));
     snprintf(buf, (size_t)n, "%s", s.c_str());
     return 0;
 }

@@ -182,6 +182,9 @@ struct TcImpl {
     bool dual_acc = true;                       // sampler engines: dual-accumulator split GEMMs (the selftest / training instances set it per call)
     int c8_clusters = 0;                        // co-resident clusters of 8 for the multicast GEMM (EGOEGO_GEMM_C8=1; 0 = off)
     bool zigzag = true;
+    // FMT_HALF launches read the weights as an fp16 PAIR in two passes over K (A W_lo^T first, then A W_hi^T): the format of the steps
+    // between the single-pass and the 3-term ones (set per captured step by the sampler, like dual_acc)
+    bool w_pair = false;
     int dir = 0;                                // direction of the next kernel launched (0 = ascending windows)
     int next_dir() { const int d = zigzag ? dir : 0; dir ^= 1; return d; }
     float *base = nullptr, *H = nullptr, *Y = nullptr, *QKV = nullptr;
@@ -248,7 +251,7 @@ static int launch_gemm_2cta_dual(TcImpl* I, const Plane& A, const Plane& W, int 
     int pairs = I->sms / 2;
     if (tiles < pairs) pairs = tiles;
     LaunchCfg lc(2 * pairs, GEMM_THREADS, GEMM2_SMEM_BYTES, s, 2);
-    EG_CUDA(cudaLaunchKernelEx(&lc.cfg, kern, A.mhi, A.mlo, W.mhi128, W.mlo128, M, N, K, epi, I->next_dir()));
+    EG_CUDA(cudaLaunchKernelEx(&lc.cfg, kern, A.mhi, A.mlo, W.mhi128, W.mlo128, M, N, K, epi, I->next_dir(), 1));
     return 0;
 }
 
@@ -271,8 +274,9 @@ static int launch_gemm_2cta(TcImpl* I, const Plane& A, const Plane& W, int M, in
     if (tiles < pairs) pairs = tiles;
     LaunchCfg lc(2 * pairs, GEMM_THREADS, GEMM2_SMEM_BYTES, s, 2);
     const int rev = I->next_dir();
-    if (fmt_is_split(FMT)) { EG_CUDA(cudaLaunchKernelEx(&lc.cfg, kern, A.mhi, A.mlo, W.mhi128, W.mlo128, M, N, K, epi, rev)); }
-    else                  { EG_CUDA(cudaLaunchKernelEx(&lc.cfg, kern, A.m16, A.m16, W.m16_128, W.m16_128, M, N, K, epi, rev)); }
+    if (fmt_is_split(FMT)) { EG_CUDA(cudaLaunchKernelEx(&lc.cfg, kern, A.mhi, A.mlo, W.mhi128, W.mlo128, M, N, K, epi, rev, 1)); }
+    else if (I->w_pair)   { EG_CUDA(cudaLaunchKernelEx(&lc.cfg, kern, A.m16, A.m16, W.mlo128, W.mhi128, M, N, K, epi, rev, 2)); }
+    else                  { EG_CUDA(cudaLaunchKernelEx(&lc.cfg, kern, A.m16, A.m16, W.m16_128, W.m16_128, M, N, K, epi, rev, 1)); }
     return 0;
 }
 
@@ -305,13 +309,13 @@ static int launch_gemm_tma_c8(TcImpl* I, const Plane& A, const Plane& W, int M, 
     const int super_tiles = (M / 512) * (N / 512);
     const int clusters = super_tiles < I->c8_clusters ? super_tiles : I->c8_clusters;
     LaunchCfg lc(8 * clusters, GEMM_TMAEPI_THREADS, GemmTmaEpiCfg::SMEM_BYTES, s, 8);
-    EG_CUDA(cudaLaunchKernelEx(&lc.cfg, kern, A.m16_64, W.m16_64, M, N, K, bias, epi, I->next_dir()));
+    EG_CUDA(cudaLaunchKernelEx(&lc.cfg, kern, A.m16_64, W.m16_64, M, N, K, bias, epi, I->next_dir(), W.m16_64, 1));
     return 0;
 }
 
 template <class Epi>
 static int launch_gemm_tma_epi(TcImpl* I, const Plane& A, const Plane& W, int M, int N, int K, const float* bias, const Epi& epi, cudaStream_t s) {
-    if (I->c8_clusters > 0 && M % 512 == 0 && N % 512 == 0) return launch_gemm_tma_c8(I, A, W, M, N, K, bias, epi, s);
+    if (I->c8_clusters > 0 && M % 512 == 0 && N % 512 == 0 && !I->w_pair) return launch_gemm_tma_c8(I, A, W, M, N, K, bias, epi, s);
     static PerDeviceOnce attr_once;          // opt-in shared-memory size is a per-device function attribute
     auto kern = gemm_half_tma_2cta_kernel<Epi>;
     if (attr_once.need()) {
@@ -322,7 +326,8 @@ static int launch_gemm_tma_epi(TcImpl* I, const Plane& A, const Plane& W, int M,
     int pairs = I->sms / 2;
     if (tiles < pairs) pairs = tiles;
     LaunchCfg lc(2 * pairs, GEMM_TMAEPI_THREADS, GemmTmaEpiCfg::SMEM_BYTES, s, 2);
-    EG_CUDA(cudaLaunchKernelEx(&lc.cfg, kern, A.m16, W.m16_128, M, N, K, bias, epi, I->next_dir()));
+    if (I->w_pair) { EG_CUDA(cudaLaunchKernelEx(&lc.cfg, kern, A.m16, W.mlo128, M, N, K, bias, epi, I->next_dir(), W.mhi128, 2)); }
+    else           { EG_CUDA(cudaLaunchKernelEx(&lc.cfg, kern, A.m16, W.m16_128, M, N, K, bias, epi, I->next_dir(), W.m16_128, 1)); }
     return 0;
 }
 
@@ -457,6 +462,7 @@ std::string TcEngine::info() const {
 
 int TcEngine::n_weight_sets() const { return impl_ && !impl_->Wx.set16.empty() ? (int)impl_->Wx.set16.size() : 1; }
 void TcEngine::set_dual_acc(bool on) { if (impl_) impl_->dual_acc = on; }
+void TcEngine::set_weight_pair(bool on) { if (impl_) impl_->w_pair = on; }
 void TcEngine::use_weight_set(int r) {
     TcImpl* I = impl_;
     if (!I) return;
@@ -480,7 +486,8 @@ static int launch_gemm_ln(TcImpl* I, const Plane& A, const Plane& W, int M, int 
     const int tiles = M / 256;
     const int clusters = tiles < I->ln4_clusters ? tiles : I->ln4_clusters;
     LaunchCfg lc(4 * clusters, GEMM_LN4_THREADS, GemmLn4Cfg::SMEM_BYTES, s, 4);
-    EG_CUDA(cudaLaunchKernelEx(&lc.cfg, gemm_ln_half_c4_kernel, A.m16_128, W.m16_128, I->Hs.m16_128, M, K, bias, g, b, I->next_dir()));
+    if (I->w_pair) { EG_CUDA(cudaLaunchKernelEx(&lc.cfg, gemm_ln_half_c4_kernel, A.m16_128, W.mlo128, I->Hs.m16_128, M, K, bias, g, b, I->next_dir(), W.mhi128, 2)); }
+    else           { EG_CUDA(cudaLaunchKernelEx(&lc.cfg, gemm_ln_half_c4_kernel, A.m16_128, W.m16_128, I->Hs.m16_128, M, K, bias, g, b, I->next_dir(), W.m16_128, 1)); }
     return 0;
 }
 

@@ -50,6 +50,8 @@ public:
     void use_weight_set(int r);
     // 3-term split launches: hi*hi and the cross terms in separate TMEM accumulators (true, the default) or in one (false)
     void set_dual_acc(bool on);
+    // FMT_HALF launches: weights as an fp16 hi/lo pair in two passes over K (fp16 activations, exact weights) instead of one fp16 copy
+    void set_weight_pair(bool on);
     int time_stage(int B, int T, int stage, int fmt, int iters, float* model_out, cudaStream_t s, float* ms, const DdpmArgs* fuse = nullptr);
     // "key=value ..." description of the resolved kernel choices (cluster counts, zig-zag, fused LN)
     std::string info() const;

@@ -434,7 +434,9 @@ template <int FMT, class Epi, bool DUAL = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_split3_2cta_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl,
                         const __grid_constant__ CUtensorMap mWh, const __grid_constant__ CUtensorMap mWl,   // W maps: 128-row boxes
-                        int M, int N, int K, Epi epi, int rev = 0 /* 1: walk the tiles from the last row block to the first (L2 zig-zag) */) {
+                        int M, int N, int K, Epi epi, int rev = 0 /* 1: walk the tiles from the last row block to the first (L2 zig-zag) */,
+                        int wpasses = 1 /* FMT_HALF only: 2 = weights as an fp16 pair, pass 0 multiplies A by mWh (the LO plane goes
+                                           first), pass 1 by mWl -- see gemm_half_tma_2cta_kernel */) {
     constexpr int BN = 256;
     constexpr int NP = Gemm2Cfg<FMT>::NP;
     static_assert(!DUAL || NP == 2, "the dual-accumulator variant is for the 3-term split formats");
@@ -462,7 +464,8 @@ gemm_split3_2cta_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_co
     const uint32_t rank = ptx::cluster_ctarank();
     const bool leader = rank == 0;
     const int pair = blockIdx.x / 2, n_pairs = gridDim.x / 2;
-    const int m_tiles = M / 256, n_tiles = N / BN, k_blocks = K / GEMM_BK;
+    const int m_tiles = M / 256, n_tiles = N / BN, k_real = K / GEMM_BK;
+    const int k_blocks = (NP == 1 ? wpasses : 1) * k_real;          // k-blocks streamed per tile
     const int total_tiles = m_tiles * n_tiles;
 
     if (warp == 0 && lane == 0) {
@@ -492,10 +495,11 @@ gemm_split3_2cta_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_co
                     uint8_t* st = smem + s * GEMM2_STAGE_BYTES;
                     if (leader) ptx::mbar_arrive_expect_tx(&full_bar[s], 2 * GEMM2_STAGE_BYTES);
                     else        ptx::mbar_arrive_cluster(&full_bar[s], 0);
-                    ptx::tma_load_2d_2cta(st, &mAh, &full_bar[s], kb * GEMM_BK, m0);
-                    if (NP == 2) ptx::tma_load_2d_2cta(st + T_BYTES, &mAl, &full_bar[s], kb * GEMM_BK, m0);
-                    ptx::tma_load_2d_2cta(st + NP * T_BYTES, &mWh, &full_bar[s], kb * GEMM_BK, n0);
-                    if (NP == 2) ptx::tma_load_2d_2cta(st + 3 * T_BYTES, &mWl, &full_bar[s], kb * GEMM_BK, n0);
+                    const int kx = (NP == 1 && kb >= k_real) ? kb - k_real : kb;
+                    ptx::tma_load_2d_2cta(st, &mAh, &full_bar[s], kx * GEMM_BK, m0);
+                    if (NP == 2) ptx::tma_load_2d_2cta(st + T_BYTES, &mAl, &full_bar[s], kx * GEMM_BK, m0);
+                    ptx::tma_load_2d_2cta(st + NP * T_BYTES, (NP == 1 && kb >= k_real) ? &mWl : &mWh, &full_bar[s], kx * GEMM_BK, n0);
+                    if (NP == 2) ptx::tma_load_2d_2cta(st + 3 * T_BYTES, &mWl, &full_bar[s], kx * GEMM_BK, n0);
                     if (++s == GEMM2_STAGES) { s = 0; ph ^= 1; }
                 }
             }
@@ -588,7 +592,13 @@ struct GemmTmaEpiCfg {
 template <class Epi, bool CL8 = false>
 __global__ void __launch_bounds__(GEMM_TMAEPI_THREADS, 1)
 gemm_half_tma_2cta_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mW /*128-row boxes; CL8: 64-row boxes*/,
-                          int M, int N, int K, const float* __restrict__ bias, const __grid_constant__ Epi epi, int rev) {
+                          int M, int N, int K, const float* __restrict__ bias, const __grid_constant__ Epi epi, int rev,
+                          const __grid_constant__ CUtensorMap mW2, int wpasses) {
+    // wpasses = 2 ("fp16 activations x fp16-pair weights", the steps between the single-pass and the 3-term format):
+    // the k loop runs twice over the same A k-blocks, first against mW (the caller passes the LO weight plane so the small
+    // terms meet an empty accumulator), then against mW2 (the hi plane): D = A W_lo^T + A W_hi^T with A rounded to fp16 once.
+    // The weight rounding -- the error the sampler integrates coherently over steps -- is gone; the activation rounding, which is
+    // fresh at every step, stays.  Not combined with CL8.
     using Cfg = GemmTmaEpiCfg;
     constexpr int STAGES = Cfg::STAGES, T_BYTES = Cfg::T_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES, BN = 256;
     constexpr uint32_t IDESC = ptx::make_idesc_f16(256, BN);
@@ -615,7 +625,8 @@ gemm_half_tma_2cta_kernel(const __grid_constant__ CUtensorMap mA, const __grid_c
     const int cmi = CL8 ? (int)(crank >> 2) : 0, cni = CL8 ? (int)((crank >> 1) & 1u) : 0;     // pair position in the 2 x 2 super-tile
     // CL8: `pair` / `n_pairs` count CLUSTERS and `total_tiles` super-tiles; tile_of() maps to this pair's 256 x 256 tile
     const int pair = CL8 ? blockIdx.x / 8 : blockIdx.x / 2, n_pairs = CL8 ? gridDim.x / 8 : gridDim.x / 2;
-    const int m_tiles = M / 256, n_tiles = N / BN, k_blocks = K / GEMM_BK;
+    const int m_tiles = M / 256, n_tiles = N / BN, k_real = K / GEMM_BK;
+    const int k_blocks = (CL8 ? 1 : wpasses) * k_real;                // k-blocks streamed per tile
     const int total_tiles = CL8 ? (m_tiles / 2) * (n_tiles / 2) : m_tiles * n_tiles;
     auto tile_of = [&](int tl, int& tm, int& tn) {
         const int t = rev ? total_tiles - 1 - tl : tl;
@@ -631,7 +642,7 @@ gemm_half_tma_2cta_kernel(const __grid_constant__ CUtensorMap mA, const __grid_c
 
     for (int i = threadIdx.x; i < N; i += blockDim.x) vec[i] = bias[i];
     if (warp == 0 && lane == 0) {
-        ptx::prefetch_tmap(&mA); ptx::prefetch_tmap(&mW);
+        ptx::prefetch_tmap(&mA); ptx::prefetch_tmap(&mW); ptx::prefetch_tmap(&mW2);
         for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 2); ptx::mbar_init(&empty_bar[s], CL8 ? 3 : 1); }
         for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], 2 * GEMM_EPI_WARPS); }
         for (int b = 0; b < 4; ++b) { ptx::mbar_init(&out_ready[b], 4); ptx::mbar_init(&box_free[b], 1); }
@@ -663,8 +674,10 @@ gemm_half_tma_2cta_kernel(const __grid_constant__ CUtensorMap mA, const __grid_c
                         ptx::tma_load_2d_2cta_mc(st + cni * (T_BYTES / 2), &mA, &full_bar[s], kb * GEMM_BK, m0 + cni * 64, mcast_a);
                         ptx::tma_load_2d_2cta_mc(st + T_BYTES + cmi * (T_BYTES / 2), &mW, &full_bar[s], kb * GEMM_BK, n0 + cmi * 64, mcast_w);
                     } else {
-                        ptx::tma_load_2d_2cta(st, &mA, &full_bar[s], kb * GEMM_BK, m0);
-                        ptx::tma_load_2d_2cta(st + T_BYTES, &mW, &full_bar[s], kb * GEMM_BK, n0);
+                        const bool second = kb >= k_real;
+                        const int kx = second ? kb - k_real : kb;
+                        ptx::tma_load_2d_2cta(st, &mA, &full_bar[s], kx * GEMM_BK, m0);
+                        ptx::tma_load_2d_2cta(st + T_BYTES, second ? &mW2 : &mW, &full_bar[s], kx * GEMM_BK, n0);
                     }
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
@@ -829,7 +842,8 @@ static __global__ void __launch_bounds__(GEMM_LN4_THREADS, 1)
 gemm_ln_half_c4_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mW /*128-row boxes*/,
                        const __grid_constant__ CUtensorMap mH /* residual in / output out: [M,512] fp16, 128-row x 64-col boxes */,
                        int M, int K, const float* __restrict__ bias, const float* __restrict__ gamma,
-                       const float* __restrict__ beta, int rev) {
+                       const float* __restrict__ beta, int rev,
+                       const __grid_constant__ CUtensorMap mW2, int wpasses /* 2: second pass over K against mW2, see gemm_half_tma_2cta_kernel */) {
     using Cfg = GemmLn4Cfg;
     constexpr int STAGES = Cfg::STAGES, T_BYTES = Cfg::T_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES;
     constexpr uint32_t IDESC = ptx::make_idesc_f16(256, 256);
@@ -858,13 +872,13 @@ gemm_ln_half_c4_kernel(const __grid_constant__ CUtensorMap mA, const __grid_cons
     const bool leader = prank == 0;
     const uint16_t pair_mask = (uint16_t)(3u << leader_rank);
     const int cl = blockIdx.x / 4, n_cl = gridDim.x / 4;
-    const int m_tiles = M / 256, kb_total = K / GEMM_BK;
+    const int m_tiles = M / 256, k_real = K / GEMM_BK, kb_total = wpasses * k_real;
 
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
         vec[i] = bias[chalf * 256 + i]; vec[256 + i] = gamma[chalf * 256 + i]; vec[512 + i] = beta[chalf * 256 + i];
     }
     if (warp == 0 && lane == 0) {
-        ptx::prefetch_tmap(&mA); ptx::prefetch_tmap(&mW); ptx::prefetch_tmap(&mH);
+        ptx::prefetch_tmap(&mA); ptx::prefetch_tmap(&mW); ptx::prefetch_tmap(&mH); ptx::prefetch_tmap(&mW2);
         for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 2); ptx::mbar_init(&empty_bar[s], 1); }
         for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], 2 * GEMM_EPI_WARPS); }
         for (int b = 0; b < 8; ++b) ptx::mbar_init(&stat_bar[b], 64);
@@ -892,8 +906,10 @@ gemm_ln_half_c4_kernel(const __grid_constant__ CUtensorMap mA, const __grid_cons
                     uint8_t* st = smem + s * STAGE_BYTES;
                     if (leader) ptx::mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
                     else        ptx::mbar_arrive_cluster(&full_bar[s], leader_rank);
-                    ptx::tma_load_2d_2cta(st, &mA, &full_bar[s], kb * GEMM_BK, m0);
-                    ptx::tma_load_2d_2cta(st + T_BYTES, &mW, &full_bar[s], kb * GEMM_BK, n0);
+                    const bool second = kb >= k_real;
+                    const int kx = second ? kb - k_real : kb;
+                    ptx::tma_load_2d_2cta(st, &mA, &full_bar[s], kx * GEMM_BK, m0);
+                    ptx::tma_load_2d_2cta(st + T_BYTES, second ? &mW2 : &mW, &full_bar[s], kx * GEMM_BK, n0);
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
             }

@@ -183,7 +183,8 @@ class CondGaussianDiffusion(nn.Module):
         self._cfg = dict(d_feats=d_feats, d_model=d_model, n_head=n_head, n_dec_layers=n_dec_layers, d_k=d_k, d_v=d_v,
                          max_timesteps=max_timesteps)
         self._max_batch = int(max_batch)
-        # 0 / -1: default policy max(ceil(N/16), 48) split steps; K > 0: K split steps (>= N: all); PRECISE_ALL_FP16: none
+        # 0 / -1: default policy, the last max(ceil(N/16), 48) steps with exact hi/lo weights (the last 16 of them in the 3-term split);
+        # K > 0: K such steps (>= N: the 3-term split everywhere); PRECISE_ALL_FP16: none
         self._precise_last_steps = int(precise_last_steps)
         eng = engine or os.environ.get("EGOEGO_ENGINE", DEFAULT_ENGINE)
         if eng not in ("tcgen05", "simt"):

@@ -54,12 +54,15 @@ typedef struct egoego_cfg {
     int32_t max_batch;     /* workspace is sized for this many windows per call        */
     int32_t device;        /* CUDA ordinal                                             */
     int32_t engine;        /* EGOEGO_ENGINE_*                                          */
-    int32_t precise_last_steps; /* tensor engine precision policy: the last K diffusion steps (t < K) use the
-                              3-term fp16 hi/lo split (fp32-grade); earlier steps one fp16 pass over dithered weight
-                              copies (egoego_weight_sets), whose error is damped by posterior_mean_coef1[t].
-                              0 (a zero-initialised cfg) or -1 = default max(ceil(timesteps/16), 48); K >= timesteps = all
-                              steps split; EGOEGO_PRECISE_ALL_FP16 = every step single-pass (30 mm worst-window error:
-                              measurements only).  The per-call entry points (denoiser_forward, p_sample_step) always split. */
+    int32_t precise_last_steps; /* tensor engine precision policy: the last K diffusion steps (t < K) read every weight as an
+                              exact fp16 hi/lo pair -- the last 16 of them (env EGOEGO_SPLIT_STEPS) in the 3-term split with
+                              hi/lo activations too (fp32-grade products), the others with fp16 activations (two passes over
+                              K); earlier steps one fp16 pass over dithered weight copies (egoego_weight_sets), whose error
+                              is damped by posterior_mean_coef1[t].
+                              0 (a zero-initialised cfg) or -1 = default max(ceil(timesteps/16), 48); K >= timesteps = the
+                              3-term split at EVERY step; EGOEGO_PRECISE_ALL_FP16 = every step single-pass (30 mm
+                              worst-window error: measurements only).  The per-call entry points (denoiser_forward,
+                              p_sample_step) always use the 3-term split. */
 } egoego_cfg;
 
 /* explicit opt-out of the precision policy (egoego_cfg.precise_last_steps): no split steps at all */
@@ -308,7 +311,8 @@ int  egoego_time_dominant_kernel(egoego_handle h, int B, int half_fmt, int iters
  * tensor engine runs the DDPM update in the epilogue of linear_out -- opt-in, EGOEGO_FUSE_DDPM=1 -- and
  * EGOEGO_KERNEL_OUT then times that fused kernel). */
 int  egoego_launches_per_step(egoego_handle h, int which);
-/* Resolved precision policy: steps t < K run the 3-term split (see egoego_cfg.precise_last_steps). */
+/* Resolved precision policy: steps t < K read exact (hi/lo) weights (see egoego_cfg.precise_last_steps; how many of them run the
+ * full 3-term split is the `split_steps=` field of egoego_engine_info). */
 int  egoego_precise_last_steps(egoego_handle h);
 /* Human-readable "key=value ..." line of the engine's resolved kernel choices (co-resident cluster counts of the cluster-of-4
  * GEMM+LayerNorm and the cluster-of-8 multicast GEMM, zig-zag tile order, weight sets, precise_last_steps), for logs and bench lines. */

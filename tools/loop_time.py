@@ -18,7 +18,13 @@ xs = synth_x_start(1, B, 120).cuda()
 cm = O.prep_head_condition_mask(xs.shape).cuda()
 params = O.init_params(0)
 res = {}
-for tag, K, n in (("fp16", E.PRECISE_ALL_FP16, N), ("split", 10 ** 6, max(N // 4, 50)), ("default", 0, N)):
+os.environ.setdefault("EGOEGO_SPLIT_STEPS", "")
+SPLIT_ENV = os.environ["EGOEGO_SPLIT_STEPS"]
+for tag, K, n in (("fp16", E.PRECISE_ALL_FP16, N), ("split", 10 ** 6, max(N // 4, 50)), ("pair", 10 ** 6, max(N // 4, 50)), ("default", 0, N)):
+    # "split": every step in the 3-term format; "pair": every step with fp16 activations x fp16-pair weights
+    os.environ["EGOEGO_SPLIT_STEPS"] = {"split": "1000000", "pair": "0"}.get(tag, SPLIT_ENV)
+    if not os.environ["EGOEGO_SPLIT_STEPS"]:
+        del os.environ["EGOEGO_SPLIT_STEPS"]
     m = E.CondGaussianDiffusion(d_feats=198, d_model=512, n_dec_layers=4, n_head=4, d_k=256, d_v=256, max_timesteps=121,
                                 out_dim=198, timesteps=n, objective="pred_x0", max_batch=B, precise_last_steps=K)
     m.load_state_dict(params, strict=False)

@@ -7,7 +7,9 @@ Runs: (1) the reference op sequence (oracle port) as stock PyTorch eager fp32 on
 (3) the same in fp64 (the exact arithmetic, when the port runs in double); (4) the fp32 CUDA-core engine (`simt`);
 (5) the tensor-core engine for several policies K.  Every run is compared with (1) and with (3): raw max-abs of the
 normalised sample, joint positions (oracle FK, metres -> mm): max, mean, per-window-max percentiles, windows over 1 mm.
-usage: python tools/parity_floor.py [B] [K[:R] ...]      (R = number of dithered fp16 weight sets, EGOEGO_WEIGHT_SETS)
+usage: python tools/parity_floor.py [B] [K[:R[:S]] ...]  (R = number of dithered fp16 weight sets, EGOEGO_WEIGHT_SETS, empty = default;
+                                                          S = how many of the last K steps run the 3-term split, EGOEGO_SPLIT_STEPS: the
+                                                          others run fp16 activations x fp16-pair weights)
 env PARITY_FLOOR_QUICK=1 skips the fp64 and chunked torch runs; PARITY_FLOOR_WEIGHTS=seed1|seed2|trained_like selects one of the
 weight sets of oracle/gen_golden_weightsets.py instead of oracle.init_params(0)."""
 import math
@@ -29,7 +31,12 @@ import egoego_release_b200 as E  # noqa: E402
 torch.backends.cuda.matmul.allow_tf32 = False
 torch.backends.cudnn.allow_tf32 = False
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
-KS = [(int(v.split(":")[0]), int(v.split(":")[1]) if ":" in v else None) for v in sys.argv[2:]] or [(k, None) for k in (1000, 500, 250, 125, 63, 32)]
+def _spec(v):
+    f = v.split(":") + ["", ""]
+    return int(f[0]), int(f[1]) if f[1] else None, int(f[2]) if f[2] else None
+
+
+KS = [_spec(v) for v in sys.argv[2:]] or [(k, None, None) for k in (1000, 500, 250, 125, 63, 32)]
 QUICK = bool(os.environ.get("PARITY_FLOOR_QUICK"))
 N, T = 1000, 120
 dev = torch.device("cuda:0")
@@ -76,11 +83,12 @@ def torch_run(dtype, chunks=1):
     return torch.cat(outs).float()
 
 
-def engine_run(engine, K, R=None):
-    if R is None:
-        os.environ.pop("EGOEGO_WEIGHT_SETS", None)
-    else:
-        os.environ["EGOEGO_WEIGHT_SETS"] = str(R)
+def engine_run(engine, K, R=None, S=None):
+    for name, v in (("EGOEGO_WEIGHT_SETS", R), ("EGOEGO_SPLIT_STEPS", S)):
+        if v is None:
+            os.environ.pop(name, None)
+        else:
+            os.environ[name] = str(v)
     m = E.CondGaussianDiffusion(d_feats=198, d_model=512, n_dec_layers=4, n_head=4, d_k=256, d_v=256, max_timesteps=121,
                                 out_dim=198, timesteps=N, objective="pred_x0", max_batch=B, engine=engine,
                                 precise_last_steps=K)
@@ -119,5 +127,5 @@ if not QUICK:
     report("torch fp32 (whole batch)", t32, {"torch64": refs["torch64"]})
     report("torch fp32 (2 chunks)", torch_run(torch.float32, 2), refs)
     report("simt fp32 engine", engine_run("simt", N), refs)
-for K, R in KS:
-    report(f"tcgen05 K={K} sets={R if R is not None else 'default'}", engine_run("tcgen05", K, R), refs)
+for K, R, S in KS:
+    report(f"tcgen05 K={K} sets={R if R is not None else 'default'} split={S if S is not None else 'default'}", engine_run("tcgen05", K, R, S), refs)
