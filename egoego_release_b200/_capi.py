@@ -17,6 +17,7 @@ EXPORTS = [
     "egoego_rigid_apply", "egoego_resnet18_create", "egoego_resnet18_destroy", "egoego_resnet18_set_tensor", "egoego_resnet18_commit",
     "egoego_resnet18_forward", "egoego_resnet18_launch_count", "egoego_train_step", "egoego_train_get_grad", "egoego_update_tensor_device", "egoego_train_get_grads", "egoego_update_tensors_device",
     "egoego_tensors_checksum", "egoego_floor_contacts", "egoego_train_set_dropout", "egoego_engine_info",
+    "egoego_debug_timeline",
 ]
 
 ENGINE_TCGEN05, ENGINE_SIMT = 0, 1
@@ -77,6 +78,7 @@ def lib():
     L.egoego_time_kernel.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp]
     L.egoego_precise_last_steps.argtypes = [vp]
     L.egoego_engine_info.argtypes = [vp, C.c_char_p, i32]
+    L.egoego_debug_timeline.argtypes = [i32, i32, vp, i32]
     L.egoego_weight_sets.argtypes = [vp]
     L.egoego_dither_weights_f16.argtypes = [vp, C.c_int64, i32, i32, vp]
     L.egoego_launches_per_step.argtypes = [vp, i32]

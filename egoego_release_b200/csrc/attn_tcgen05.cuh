@@ -291,7 +291,15 @@ __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.
 __global__ void __launch_bounds__(ATT2_THREADS, 1)
 attention_half_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUtensorMap mK,
                       const __grid_constant__ CUtensorMap mV /* 64-row boxes */, const __grid_constant__ CUtensorMap mO /* [M, H*256] fp16, 128-row x 64-col boxes */,
-                      int n_items, int n_head, int L, int rev /* 1: walk the items from the last window to the first (L2 zig-zag) */) {
+                      int n_items, int n_head, int L, int rev /* 1: walk the items from the last window to the first (L2 zig-zag) */,
+                      const int* __restrict__ win_cnt /* nullptr, or: streamed mode -- this grid runs CONCURRENTLY with the QKV projection that
+                                                         feeds it (gemm_half_tma_2cta_kernel with row_cnt = win_cnt) and loads window w once
+                                                         win_cnt[w] >= tiles_per_window * (*d_step + 1) */,
+                      const int* __restrict__ d_step, int tiles_per_window,
+                      int early_ctas, int early_items /* streamed mode, two phases: CTAs [0, early_ctas) -- resident next to the producer grid --
+                                                         share items [0, early_items) and follow the counters; the other CTAs become resident
+                                                         as the producer's CTAs exit and share the remaining items (already produced, still in
+                                                         the L2).  early_ctas = 0: every CTA strides over all items */) {
     constexpr uint32_t IDESC_S = ptx::make_idesc_f16(128, 128);
     constexpr uint32_t IDESC_O = ptx::make_idesc_f16(128, 256) | ptx::IDESC_B_MN_MAJOR;
     constexpr int STAGE = 32768, STAGES = ATT_RING_BYTES / STAGE;           // 4
@@ -333,14 +341,28 @@ attention_half_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_const
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     ptx::grid_dep_launch();
-    ptx::grid_dep_wait();                                // prologue above overlaps the previous kernel's tail (PDL)
-    const int n_mine = blockIdx.x < n_items ? (n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;   // items of this CTA
-    auto item_of = [&](int j) { const int i = (int)blockIdx.x + j * (int)gridDim.x; return rev ? n_items - 1 - i : i; };
+    // Streamed mode: no wait for the producer grid.  Its CTAs release this grid only after their own griddepcontrol.wait, so all
+    // earlier kernels have completed (their reads of O, their write of *d_step) when the first thread gets here.
+    if (!win_cnt) ptx::grid_dep_wait();                  // prologue above overlaps the previous kernel's tail (PDL)
+    if (threadIdx.x == 0) timeline_mark(1, 0);
+    // items of this CTA: first + j * stride < last
+    int first = (int)blockIdx.x, stride = (int)gridDim.x, last = n_items;
+    if (early_ctas > 0) {
+        if ((int)blockIdx.x < early_ctas) { stride = early_ctas; last = early_items; }
+        else { first = early_items + (int)blockIdx.x - early_ctas; stride = (int)gridDim.x - early_ctas; }
+    }
+    const int n_mine = first < last ? (last - 1 - first) / stride + 1 : 0;
+    auto item_of = [&](int j) { const int i = first + j * stride; return rev ? n_items - 1 - i : i; };
 
     if (warp == 0) {
         if (lane == 0) {                                   // ===== TMA producer: QK(0) QK(1) | V(0) QK(2) | V(1) QK(3) ... =====
             int s = 0; uint32_t ph = 0;
+            const int cnt_target = win_cnt ? tiles_per_window * ((d_step ? *d_step : 0) + 1) : 0;
             auto load_qk = [&](int item) {
+                if (win_cnt) {                             // Q, K and V of this window are performed in global memory?
+                    const int* c = win_cnt + item / n_head;
+                    while (ptx::ld_acquire_gpu(c) < cnt_target) __nanosleep(64);
+                }
                 for (int kb = 0; kb < 4; ++kb) {
                     ptx::mbar_wait(&empty_bar[s], ph ^ 1);
                     uint8_t* st = smem + s * STAGE;
@@ -426,6 +448,7 @@ attention_half_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_const
                 }
             }
             ptx::tma_store_wait_all();
+            timeline_mark(1, 1);
         }
     } else {                                               // ===== softmax + epilogue warps 2..9 =====
         const int quarter = (warp - 2) & 3, hf = (warp - 2) >> 2;  // TMEM lane quarter, key / output-column half

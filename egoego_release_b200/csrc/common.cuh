@@ -62,6 +62,20 @@ struct LaunchCfg {
     LaunchCfg(const LaunchCfg&) = delete;
 };
 
+// Debug timeline (tools/stream_timeline.py): when switched on, every CTA of the streamed QKV projection (kernel 0) and of the
+// attention kernel (kernel 1) records %globaltimer after its start-up waits and before it exits; the last launch wins.  Per
+// translation unit; the kernels and the accessor (tc_debug_timeline) live in engine_tc.cu.
+constexpr int TIMELINE_CTAS = 160;
+static __device__ unsigned long long g_timeline[2][TIMELINE_CTAS][2];
+static __device__ int g_timeline_on = 0;
+__device__ __forceinline__ void timeline_mark(int kernel, int which) {
+    if (g_timeline_on && blockIdx.x < TIMELINE_CTAS) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_timeline[kernel][blockIdx.x][which] = t;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Which diffusion step a window is at.  Loop mode: t = t_start - *d_step (device counter advanced
 // once per step so one captured CUDA graph serves every step).  Step-API mode: explicit int64 array.
@@ -105,6 +119,7 @@ struct DdpmArgs {
     int stage_mode;          // tensor engine planes to write: 0 = fp16 hi/lo pair only, 1 = single fp16 plane only, 2 = all (next step's format unknown)
     TSrc ts; NoiseSrc ns;
     int B, T, D;
+    int* advance; unsigned* done;   // ddpm_update_kernel in the sampling loop: step counter to advance once all blocks are done + its block counter (nullable)
 };
 
 __device__ __forceinline__ uint32_t mulhilo32(uint32_t a, uint32_t b, uint32_t* hi) {

@@ -187,6 +187,7 @@ static void fill_ddpm(egoego_ctx* c, DdpmArgs& a, const float* x, float* x_out, 
         else c->tc->stage_targets(&a.stage_hi, &a.stage_lo, &a.stage_h16, &a.stage_ld16);
     }
     a.ts = ts; a.ns = ns; a.B = B; a.T = T; a.D = c->D;
+    a.advance = nullptr; a.done = nullptr;
 }
 
 
@@ -546,7 +547,8 @@ static int sample_chunk(egoego_ctx* c, const float* x_start, const float* cond_m
     if (stage_input(c, xcond, D, 0, true, Bc, T, s)) return 1;
     if (prepare_cond(c, Bc, T, s)) return 1;
     if (stage_input(c, xc, D, 0, false, Bc, T, s)) return 1;
-    EG_CUDA(cudaMemsetAsync(d_step, 0, sizeof(int), s));
+    EG_CUDA(cudaMemsetAsync(d_step, 0, 64, s));                 // step counter + the block counter of ddpm_update_kernel (word 8)
+    if (c->tc && c->tc->reset_stream_counters(s)) return 1;
     TSrc ts{nullptr, d_step, N - 1, N - 1};
     NoiseSrc ns = ns_base;
     ns.d_step = d_step; ns.draw_static = 2;
@@ -561,8 +563,12 @@ static int sample_chunk(egoego_ctx* c, const float* x_start, const float* cond_m
         if (run_denoiser(c, Bc, T, ts, nullptr, st, fmt, fused ? &a : nullptr)) return 1;
         LaunchCfg ld(1, 256, 0, st), la(1, 32, 0, st);
         ld.cfg.gridDim = ddpm_grid(T, D, Bc);
-        if (!fused) { EG_CUDA(cudaLaunchKernelEx(&ld.cfg, ddpm_update_kernel, a)); c->launches++; }
-        EG_CUDA(cudaLaunchKernelEx(&la.cfg, advance_step_kernel, d_step));
+        if (!fused) {           // the update's last block advances the step counter
+            a.advance = d_step; a.done = reinterpret_cast<unsigned*>(d_step + 8);
+            EG_CUDA(cudaLaunchKernelEx(&ld.cfg, ddpm_update_kernel, a));
+        } else {
+            EG_CUDA(cudaLaunchKernelEx(&la.cfg, advance_step_kernel, d_step));
+        }
         c->launches += 1;
         EG_CUDA(cudaGetLastError());
         return 0;
@@ -625,7 +631,7 @@ static int sample_chunk(egoego_ctx* c, const float* x_start, const float* cond_m
             const int fmt = fmt_of_step(i);
             if (i > 0 && fmt != fmt_of_step(i - 1) && stage_input(c, xc, D, 0, false, Bc, T, s)) return 1;
             EG_CUDA(cudaGraphLaunch(c->step_graph[slot_of_step(i)], s));
-            c->launches += (c->cfg.engine == EGOEGO_ENGINE_SIMT ? (2 + 7 * c->NL) : c->tc->launches_per_denoiser(fmt)) + (fused ? 1 : 2);
+            c->launches += (c->cfg.engine == EGOEGO_ENGINE_SIMT ? (2 + 7 * c->NL) : c->tc->launches_per_denoiser(fmt)) + 1;
         }
     } else {
         for (int i = 0; i < N; ++i) {
@@ -872,6 +878,10 @@ int egoego_engine_info(egoego_handle c, char* buf, int n) {
          " dual_accumulator_steps=" + std::to_string(std::min(c->dual_last, std::min(c->split_last, c->precise_last)));
     snprintf(buf, (size_t)n, "%s", s.c_str());
     return 0;
+}
+int egoego_debug_timeline(int device, int enable, uint64_t* out, int n) {
+    EG_CUDA(cudaSetDevice(device));
+    return tc_debug_timeline(enable, reinterpret_cast<unsigned long long*>(out), n);
 }
 int egoego_dither_weights_f16(const float* w, int64_t n, int set, int n_sets, uint16_t* out) {
     EG_CHECK(w && out && n >= 0 && n_sets >= 1 && n_sets <= 16 && set >= 0 && set < n_sets, "egoego_dither_weights_f16: bad arguments");

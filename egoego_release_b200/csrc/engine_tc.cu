@@ -185,6 +185,15 @@ struct TcImpl {
     // FMT_HALF launches read the weights as an fp16 PAIR in two passes over K (A W_lo^T first, then A W_hi^T): the format of the steps
     // between the single-pass and the 3-term ones (set per captured step by the sampler, like dual_acc)
     bool w_pair = false;
+    // Streamed attention (EGOEGO_STREAM_ATT=1; off by default, see DESIGN.md 5.2: measured no faster): in the sampling loop the fp16-format QKV projection runs on `stream_pairs`
+    // CTA pairs and attention_half_kernel CONCURRENTLY on the remaining SMs, following the projection window by window through
+    // per-window completion counters (one row of `att_cnt` per layer; a window is complete at 12 tiles x (steps since reset)).
+    // Q / K / V (201 MB per layer at 256 windows, more than the L2 holds) are then read back while they are still in the L2.
+    bool stream_att = false;
+    int stream_pairs = 62;
+    double stream_ratio = 0.96;                 // attention item time / projection tile time (EGOEGO_STREAM_ATT_RATIO; measured 4.1 / 4.28 us)
+    int* att_cnt = nullptr;                     // [NL][cnt_ld]
+    int cnt_ld = 0;
     int dir = 0;                                // direction of the next kernel launched (0 = ascending windows)
     int next_dir() { const int d = zigzag ? dir : 0; dir ^= 1; return d; }
     float *base = nullptr, *H = nullptr, *Y = nullptr, *QKV = nullptr;
@@ -192,6 +201,7 @@ struct TcImpl {
         for (Plane* p : {&Wx, &Wc, &Wout, &X, &C, &Hs, &O, &F, &Qp, &Kp, &VT}) p->release();
         for (auto& l : layers) for (Plane* p : {&l.wqkv, &l.fc, &l.w1, &l.w2}) p->release();
         for (float* p : {base, H, Y, QKV}) if (p) cudaFree(p);
+        if (att_cnt) cudaFree(att_cnt);
     }
 };
 
@@ -309,13 +319,16 @@ static int launch_gemm_tma_c8(TcImpl* I, const Plane& A, const Plane& W, int M, 
     const int super_tiles = (M / 512) * (N / 512);
     const int clusters = super_tiles < I->c8_clusters ? super_tiles : I->c8_clusters;
     LaunchCfg lc(8 * clusters, GEMM_TMAEPI_THREADS, GemmTmaEpiCfg::SMEM_BYTES, s, 8);
-    EG_CUDA(cudaLaunchKernelEx(&lc.cfg, kern, A.m16_64, W.m16_64, M, N, K, bias, epi, I->next_dir(), W.m16_64, 1));
+    EG_CUDA(cudaLaunchKernelEx(&lc.cfg, kern, A.m16_64, W.m16_64, M, N, K, bias, epi, I->next_dir(), W.m16_64, 1, (int*)nullptr));
     return 0;
 }
 
+// `row_cnt` != nullptr: streamed consumer (see TcImpl::stream_att): at most `max_pairs` CTA pairs, per-window completion counters
+// published by the store warp; *pairs_used / *rev_used report the grid and the tile direction to the caller (the consumer follows both).
 template <class Epi>
-static int launch_gemm_tma_epi(TcImpl* I, const Plane& A, const Plane& W, int M, int N, int K, const float* bias, const Epi& epi, cudaStream_t s) {
-    if (I->c8_clusters > 0 && M % 512 == 0 && N % 512 == 0 && !I->w_pair) return launch_gemm_tma_c8(I, A, W, M, N, K, bias, epi, s);
+static int launch_gemm_tma_epi(TcImpl* I, const Plane& A, const Plane& W, int M, int N, int K, const float* bias, const Epi& epi, cudaStream_t s,
+                               int* row_cnt = nullptr, int max_pairs = 0, int* pairs_used = nullptr, int* rev_used = nullptr) {
+    if (I->c8_clusters > 0 && M % 512 == 0 && N % 512 == 0 && !I->w_pair && !row_cnt) return launch_gemm_tma_c8(I, A, W, M, N, K, bias, epi, s);
     static PerDeviceOnce attr_once;          // opt-in shared-memory size is a per-device function attribute
     auto kern = gemm_half_tma_2cta_kernel<Epi>;
     if (attr_once.need()) {
@@ -324,10 +337,14 @@ static int launch_gemm_tma_epi(TcImpl* I, const Plane& A, const Plane& W, int M,
     EG_CHECK(M % 256 == 0 && N % 256 == 0 && K % GEMM_BK == 0 && N <= GemmTmaEpiCfg::MAX_N, "TMA-epilogue gemm shape not supported");
     const int tiles = (M / 256) * (N / 256);
     int pairs = I->sms / 2;
+    if (row_cnt && max_pairs > 0 && max_pairs < pairs) pairs = max_pairs;
     if (tiles < pairs) pairs = tiles;
     LaunchCfg lc(2 * pairs, GEMM_TMAEPI_THREADS, GemmTmaEpiCfg::SMEM_BYTES, s, 2);
-    if (I->w_pair) { EG_CUDA(cudaLaunchKernelEx(&lc.cfg, kern, A.m16, W.mlo128, M, N, K, bias, epi, I->next_dir(), W.mhi128, 2)); }
-    else           { EG_CUDA(cudaLaunchKernelEx(&lc.cfg, kern, A.m16, W.m16_128, M, N, K, bias, epi, I->next_dir(), W.m16_128, 1)); }
+    const int rev = I->next_dir();
+    if (pairs_used) *pairs_used = pairs;
+    if (rev_used) *rev_used = rev;
+    if (I->w_pair) { EG_CUDA(cudaLaunchKernelEx(&lc.cfg, kern, A.m16, W.mlo128, M, N, K, bias, epi, rev, W.mhi128, 2, row_cnt)); }
+    else           { EG_CUDA(cudaLaunchKernelEx(&lc.cfg, kern, A.m16, W.m16_128, M, N, K, bias, epi, rev, W.m16_128, 1, row_cnt)); }
     return 0;
 }
 
@@ -401,6 +418,20 @@ int TcEngine::init(const TcWeights& w, cudaStream_t) {
         if (I->ln4_clusters == 0) I->fuse_ln = false;
     }
     { const char* zz = getenv("EGOEGO_ZIGZAG"); I->zigzag = !(zz && zz[0] == '0'); }
+    {
+        const char* sa = getenv("EGOEGO_STREAM_ATT");
+        I->stream_att = sa && sa[0] == '1';
+        const char* sp = getenv("EGOEGO_STREAM_ATT_PAIRS");
+        if (sp && sp[0]) I->stream_pairs = atoi(sp);
+        if (I->stream_pairs < 1) I->stream_pairs = 1;
+        if (I->stream_pairs > I->sms / 2 - 2) I->stream_pairs = I->sms / 2 - 2;       // the consumer keeps at least four SMs
+        const char* sr = getenv("EGOEGO_STREAM_ATT_RATIO");
+        if (sr && sr[0]) I->stream_ratio = atof(sr);
+        if (!(I->stream_ratio > 0.05 && I->stream_ratio < 20.0)) I->stream_ratio = 0.96;
+        I->cnt_ld = ((w.max_batch + 1) / 2) * 2;
+        EG_CUDA(cudaMalloc(&I->att_cnt, (size_t)w.NL * I->cnt_ld * sizeof(int)));
+        EG_CUDA(cudaMemset(I->att_cnt, 0, (size_t)w.NL * I->cnt_ld * sizeof(int)));
+    }
     {   // cluster-of-8 multicast GEMM for the QKV projection and w_1 (opt-in until measured: EGOEGO_GEMM_C8=1)
         const char* c8 = getenv("EGOEGO_GEMM_C8");
         I->c8_clusters = 0;
@@ -457,12 +488,18 @@ std::string TcEngine::info() const {
     const TcImpl* I = impl_;
     if (!I) return "engine=tcgen05 (not initialised)";
     return "engine=tcgen05 sms=" + std::to_string(I->sms) + " ln4_clusters=" + std::to_string(I->ln4_clusters) + " c8_clusters=" + std::to_string(I->c8_clusters) +
-           " zigzag=" + std::to_string(I->zigzag ? 1 : 0) + " fuse_ln=" + std::to_string(I->fuse_ln ? 1 : 0) + " weight_sets=" + std::to_string(n_weight_sets());
+           " zigzag=" + std::to_string(I->zigzag ? 1 : 0) + " fuse_ln=" + std::to_string(I->fuse_ln ? 1 : 0) + " stream_att=" + std::to_string(I->stream_att ? I->stream_pairs : 0) + " weight_sets=" + std::to_string(n_weight_sets());
 }
 
 int TcEngine::n_weight_sets() const { return impl_ && !impl_->Wx.set16.empty() ? (int)impl_->Wx.set16.size() : 1; }
 void TcEngine::set_dual_acc(bool on) { if (impl_) impl_->dual_acc = on; }
 void TcEngine::set_weight_pair(bool on) { if (impl_) impl_->w_pair = on; }
+int TcEngine::reset_stream_counters(cudaStream_t s) {
+    TcImpl* I = impl_;
+    if (!I || !I->att_cnt) return 0;
+    EG_CUDA(cudaMemsetAsync(I->att_cnt, 0, (size_t)I->w.NL * I->cnt_ld * sizeof(int), s));
+    return 0;
+}
 void TcEngine::use_weight_set(int r) {
     TcImpl* I = impl_;
     if (!I) return;
@@ -582,12 +619,17 @@ static int denoiser_impl(TcImpl* I, int B, int T, TSrc ts, const float* pmask, f
     }
     for (int l = 0; l < I->w.NL; ++l) {
         TcLayer& W = I->layers[l];
+        // streamed attention: loop mode only (the counters count steps since the last reset_stream_counters(), read through *d_step)
+        const bool streamed = FMT == FMT_HALF && I->stream_att && I->attn_tc && I->attn_v2 && use_tma_epi() && Mg % 256 == 0 && only < 0 &&
+                              ts.d_step != nullptr && ts.t_arr == nullptr && I->c8_clusters == 0 && I->att_cnt != nullptr;
+        int* cnt_l = streamed ? I->att_cnt + (size_t)l * I->cnt_ld : nullptr;
+        int q_pairs = 0, q_rev = 0;
         if (I->attn_tc) {
             if (on(1, l)) {
                 TcEpiQKVPlanes<FMT> eq{{}, {}, I->Qp.hi, I->Qp.lo, I->Kp.hi, I->Kp.lo, I->VT.hi, I->VT.lo, W.bqkv, H, 1.0f / sqrtf((float)dk)};
                 if (FMT == FMT_HALF && use_tma_epi() && Mg % 256 == 0) {
                     TmaEpiQKV te{I->Qp.m16_128, I->Kp.m16_128, I->VT.m16_128, H, 1.0f / sqrtf((float)dk)};
-                    if (launch_gemm_tma_epi(I, I->Hs, W.wqkv, Mg, nqkv, d, W.bqkv, te, s)) return 1;
+                    if (launch_gemm_tma_epi(I, I->Hs, W.wqkv, Mg, nqkv, d, W.bqkv, te, s, cnt_l, I->stream_pairs, &q_pairs, &q_rev)) return 1;
                 } else {
                     if (gemm<FMT>(I, I->Hs, W.wqkv, Mg, nqkv, d, eq, s)) return 1;
                 }
@@ -595,8 +637,33 @@ static int denoiser_impl(TcImpl* I, int B, int T, TSrc ts, const float* pmask, f
             if (on(2, l)) {
                 const int items = B * H;
                 if (FMT == FMT_HALF && I->attn_v2) {
-                    LaunchCfg lc(items < I->sms ? items : I->sms, ATT2_THREADS, ATT2_SMEM_BYTES, s);
-                    EG_CUDA(cudaLaunchKernelEx(&lc.cfg, attention_half_kernel, I->Qp.m16, I->Kp.m16, I->VT.m16, I->O.m16_128, items, H, L, I->next_dir()));
+                    if (streamed) {
+                        // Concurrently with the projection, in the SAME window order.  Two phases: G = sms - 2 q_pairs CTAs are resident next to
+                        // the projection and take the first X items; the other 2 q_pairs CTAs become resident as the projection's CTAs exit and
+                        // take the rest.  X balances the two finishing times for a per-item attention time of `stream_ratio` projection-tile times:
+                        //   X r / G = tiles / q_pairs + (items - X) r / (2 q_pairs),   then (items - X) rounded to whole waves of the late CTAs
+                        const int G = I->sms - 2 * q_pairs, late = 2 * q_pairs;
+                        const int tiles = (Mg / 256) * (nqkv / 256);
+                        int X = items, early = G < items ? G : items, total = early;
+                        if (G < items) {
+                            const double r = I->stream_ratio;
+                            const double x = ((double)tiles / q_pairs + (double)items * r / late) / (r / G + r / late);
+                            double restf = (double)items - x;
+                            int rest = restf >= late ? (int)(restf / late + 0.5) * late : (int)(restf + 0.999);   // whole waves once there is one
+                            if (rest < 0) rest = 0;
+                            if (rest > items - 1) rest = items - 1;
+                            X = items - rest;
+                            if (early > X) early = X;
+                            total = early + (rest < late ? rest : late);
+                        }
+                        LaunchCfg lc(total, ATT2_THREADS, ATT2_SMEM_BYTES, s);
+                        EG_CUDA(cudaLaunchKernelEx(&lc.cfg, attention_half_kernel, I->Qp.m16, I->Kp.m16, I->VT.m16, I->O.m16_128, items, H, L, q_rev,
+                                                   (const int*)cnt_l, ts.d_step, nqkv / 256, total > early ? early : 0, X));
+                    } else {
+                        LaunchCfg lc(items < I->sms ? items : I->sms, ATT2_THREADS, ATT2_SMEM_BYTES, s);
+                        EG_CUDA(cudaLaunchKernelEx(&lc.cfg, attention_half_kernel, I->Qp.m16, I->Kp.m16, I->VT.m16, I->O.m16_128, items, H, L, I->next_dir(),
+                                                   (const int*)nullptr, (const int*)nullptr, 0, 0, 0));
+                    }
                 } else {
                     LaunchCfg lc(items < I->sms ? items : I->sms, ATT_THREADS, ATT_SMEM_BYTES, s);
                     EG_CUDA(cudaLaunchKernelEx(&lc.cfg, attention_tc_kernel<FMT>, I->Qp.mhi, I->Qp.mlo, I->Kp.mhi, I->Kp.mlo, I->VT.mhi, I->VT.mlo,
@@ -688,6 +755,23 @@ int TcEngine::time_stage(int B, int T, int stage, int fmt, int iters, float* mod
     EG_CUDA(cudaEventElapsedTime(&t, e0, e1));
     *ms = t / iters;
     cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return 0;
+}
+
+// Debug timeline of the streamed QKV projection / attention pair (common.cuh: g_timeline): switch recording on / off, or copy the
+// timestamps of the last launch ([kernel][cta][start, end], nanoseconds of %globaltimer) to the host.
+int tc_debug_timeline(int enable, unsigned long long* out, int n) {
+    if (out) {
+        EG_CHECK(n <= 2 * TIMELINE_CTAS * 2, "timeline buffer too large");
+        EG_CUDA(cudaDeviceSynchronize());
+        EG_CUDA(cudaMemcpyFromSymbol(out, g_timeline, (size_t)n * sizeof(unsigned long long)));
+    }
+    if (enable >= 0) {
+        const int v = enable ? 1 : 0;
+        unsigned long long z[2 * TIMELINE_CTAS * 2] = {};
+        EG_CUDA(cudaMemcpyToSymbol(g_timeline, z, sizeof(z)));
+        EG_CUDA(cudaMemcpyToSymbol(g_timeline_on, &v, sizeof(int)));
+    }
     return 0;
 }
 

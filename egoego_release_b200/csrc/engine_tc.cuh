@@ -52,12 +52,17 @@ public:
     void set_dual_acc(bool on);
     // FMT_HALF launches: weights as an fp16 hi/lo pair in two passes over K (fp16 activations, exact weights) instead of one fp16 copy
     void set_weight_pair(bool on);
+    // zero the per-window completion counters of the streamed attention; call wherever the loop's device step counter is reset
+    int reset_stream_counters(cudaStream_t s);
     int time_stage(int B, int T, int stage, int fmt, int iters, float* model_out, cudaStream_t s, float* ms, const DdpmArgs* fuse = nullptr);
     // "key=value ..." description of the resolved kernel choices (cluster counts, zig-zag, fused LN)
     std::string info() const;
 private:
     TcImpl* impl_;
 };
+
+// debug: per-CTA start / end timestamps of the streamed QKV projection and attention kernels (enable: 1 / 0, -1 = leave; out: nullable)
+int tc_debug_timeline(int enable, unsigned long long* out, int n);
 
 // C[M, N] (= or +=) A[M, K] W[N, K]^T, fp32 row-major device operands, on the tensor cores (3-term bf16 split, fp32 accumulate).
 // C must have ceil(M / 256) * 256 rows of ldc floats; columns [0, n_valid) are written (n_valid % 4 == 0 <= ldc).

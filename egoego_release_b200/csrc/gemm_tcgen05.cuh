@@ -593,7 +593,10 @@ template <class Epi, bool CL8 = false>
 __global__ void __launch_bounds__(GEMM_TMAEPI_THREADS, 1)
 gemm_half_tma_2cta_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mW /*128-row boxes; CL8: 64-row boxes*/,
                           int M, int N, int K, const float* __restrict__ bias, const __grid_constant__ Epi epi, int rev,
-                          const __grid_constant__ CUtensorMap mW2, int wpasses) {
+                          const __grid_constant__ CUtensorMap mW2, int wpasses,
+                          int* __restrict__ row_cnt /* nullptr, or one counter per 128-row block (window): +1 for every tile of the block
+                                                       whose output is PERFORMED in global memory -- a consumer kernel running
+                                                       concurrently (attention_half_kernel) polls it instead of waiting for this grid */) {
     // wpasses = 2 ("fp16 activations x fp16-pair weights", the steps between the single-pass and the 3-term format):
     // the k loop runs twice over the same A k-blocks, first against mW (the caller passes the LO weight plane so the small
     // terms meet an empty accumulator), then against mW2 (the hi plane): D = A W_lo^T + A W_hi^T with A rounded to fp16 once.
@@ -654,8 +657,16 @@ gemm_half_tma_2cta_kernel(const __grid_constant__ CUtensorMap mA, const __grid_c
     ptx::cluster_sync();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    ptx::grid_dep_launch();
-    ptx::grid_dep_wait();                                // prologue above overlaps the previous kernel's tail (PDL)
+    if (row_cnt) {
+        // streamed consumer: the dependent grid starts as soon as every CTA here has passed its own wait (so everything before
+        // this kernel has completed when the consumer runs) and then follows the counters, not this grid's completion
+        ptx::grid_dep_wait();
+        ptx::grid_dep_launch();
+        if (threadIdx.x == 0) timeline_mark(0, 0);
+    } else {
+        ptx::grid_dep_launch();
+        ptx::grid_dep_wait();                            // prologue above overlaps the previous kernel's tail (PDL)
+    }
 
     if (warp == 0) {
         if (lane == 0) {                                 // ===== TMA producer (both CTAs) =====
@@ -708,6 +719,11 @@ gemm_half_tma_2cta_kernel(const __grid_constant__ CUtensorMap mA, const __grid_c
     } else if (warp == 10) {
         if (lane == 0) {                                 // ===== store I/O (both CTAs) =====
             int it = 0;
+            int prev_blk = -1;                           // row block of the previous tile, published one tile late (no stall)
+            auto publish = [&](int blk) {           // the block's bulk stores are PERFORMED (wait_group, non-.read) before this release
+                __threadfence();
+                ptx::red_release_gpu_add(row_cnt + blk, 1);
+            };
             for (int tl = pair; tl < total_tiles; tl += n_pairs, ++it) {
                 int tm, tn;
                 tile_of(tl, tm, tn);
@@ -723,8 +739,14 @@ gemm_half_tma_2cta_kernel(const __grid_constant__ CUtensorMap mA, const __grid_c
                     ptx::tma_store_wait_read();
                     ptx::mbar_arrive(&box_free[b]);
                 }
+                if (row_cnt) {
+                    if (prev_blk >= 0) { ptx::tma_store_wait_pending<4>(); publish(prev_blk); }   // all but this tile's 4 boxes are performed
+                    prev_blk = row0 / GEMM_BM;
+                }
             }
             ptx::tma_store_wait_all();
+            if (row_cnt && prev_blk >= 0) publish(prev_blk);
+            if (row_cnt) timeline_mark(0, 1);
         }
     } else {                                             // ===== epilogue warps 2..9 (both CTAs) =====
         const int quarter = (warp - 2) & 3, hf = (warp - 2) >> 2;

@@ -482,9 +482,7 @@ static __global__ void stage_rows_split_kernel(__nv_bfloat16* __restrict__ Ahi, 
 // DDPM update (p_mean_variance tail + p_sample, transformer_cond_diffusion_model.py:235-256) fused with
 // the in-paint overwrite (:395-397) and the staging of the next step's GEMM A operand.
 
-static __global__ void ddpm_update_kernel(DdpmArgs a) {
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");          // PDL: everything below reads the previous kernel's output
+__device__ __forceinline__ void ddpm_update_body(const DdpmArgs& a) {
     // 32-bit index arithmetic throughout (the kernel is issue-bound: 64-bit divisions cost more than the Philox rounds);
     // grid = (quads of one window, windows)
     const int epw = a.T * a.D;
@@ -551,6 +549,21 @@ static __global__ void ddpm_update_kernel(DdpmArgs a) {
         }
     }
     if (vec) *reinterpret_cast<float4*>(a.x_out + i0) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+static __global__ void ddpm_update_kernel(DdpmArgs a) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");          // PDL: everything below reads the previous kernel's output
+    ddpm_update_body(a);
+    if (a.advance) {
+        // Sampling loop: the LAST block to finish advances the device step counter (every block has read it by then), which saves
+        // the separate one-thread advance_step_kernel node of every step.
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(a.done, 1u) == gridDim.x * gridDim.y - 1u) { *a.done = 0u; __threadfence(); (*a.advance)++; }
+        }
+    }
 }
 
 static __global__ void advance_step_kernel(int* d_step) {

@@ -317,6 +317,10 @@ int  egoego_precise_last_steps(egoego_handle h);
 /* Human-readable "key=value ..." line of the engine's resolved kernel choices (co-resident cluster counts of the cluster-of-4
  * GEMM+LayerNorm and the cluster-of-8 multicast GEMM, zig-zag tile order, weight sets, precise_last_steps), for logs and bench lines. */
 int  egoego_engine_info(egoego_handle h, char* buf, int buf_len);
+/* Debug hook for the streamed QKV-projection / attention pair of the fp16-format steps (tools/stream_timeline.py): enable = 1 / 0
+ * switches per-CTA recording of %globaltimer on / off (-1 = leave), out (nullable) receives [2 kernels][160 CTAs][start, end] in
+ * nanoseconds for the last launch of each kernel (n = number of uint64 to copy, <= 640).  Synchronises the device. */
+int  egoego_debug_timeline(int device, int enable, uint64_t* out, int n);
 /* Number R of dithered fp16 weight sets the single-pass steps cycle through (env EGOEGO_WEIGHT_SETS at weight commit,
  * default 8, 1 = plain round-to-nearest; always 1 for the fp32 engine).  Step i of the loop reads set i mod R, so the fp16
  * rounding of the weights -- the only rounding of those steps that survives to the final sample -- averages out over steps

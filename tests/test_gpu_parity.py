@@ -365,6 +365,38 @@ def test_fused_ln_kernels_agree(params0, monkeypatch):
     assert d2 < 2e-2
 
 
+@pytest.mark.parametrize("B,T,N,K", [(160, 120, 6, -2), (37, 120, 40, 0), (3, 30, 60, 0), (1, 120, 24, 8)])
+def test_streamed_attention_is_bit_identical(params0, monkeypatch, B, T, N, K):
+    """Streamed attention (opt-in EGOEGO_STREAM_ATT=1: attention_half_kernel runs CONCURRENTLY with the QKV projection and follows it
+    window by window through completion counters) against the same kernels run one after the other (the default): scheduling only, so the
+    samples must agree bit for bit -- a window read before its Q / K / V were performed would show here.  Covers many windows per
+    consumer CTA, odd window counts, short windows, loops with fp16, pair and 3-term steps, two SM partitions, and repeated calls
+    on one handle (the counters restart with the loop's step counter)."""
+    import egoego_release_b200 as E
+    xs = synth_x_start(19, B, T).cuda()
+    cm = O.prep_head_condition_mask(xs.shape).cuda()
+    outs = {}
+    for tag, env in (("serial", {}), ("streamed", {"EGOEGO_STREAM_ATT": "1"}), ("streamed_p40", {"EGOEGO_STREAM_ATT": "1", "EGOEGO_STREAM_ATT_PAIRS": "40"})):
+        for k in ("EGOEGO_STREAM_ATT", "EGOEGO_STREAM_ATT_PAIRS"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        m = E.CondGaussianDiffusion(d_feats=198, d_model=512, n_dec_layers=4, n_head=4, d_k=256, d_v=256, max_timesteps=121,
+                                    out_dim=198, timesteps=N, objective="pred_x0", max_batch=B, engine="tcgen05",
+                                    precise_last_steps=E.PRECISE_ALL_FP16 if K == -2 else K)
+        m.load_state_dict(params0, strict=False)
+        m = m.cuda()
+        assert ("stream_att=0" in m.engine_info()) == (tag == "serial"), m.engine_info()
+        res = []
+        for rep in range(2):
+            torch.manual_seed(3)
+            res.append(m.sample(xs, cm))
+        assert torch.isfinite(res[0]).all() and torch.equal(res[0], res[1])
+        outs[tag] = res[0]
+    assert torch.equal(outs["serial"], outs["streamed"])
+    assert torch.equal(outs["serial"], outs["streamed_p40"])
+
+
 @pytest.mark.parametrize("K", [12, -2])
 def test_fused_ddpm_epilogue_matches_ddpm_kernel(params0, monkeypatch, K):
     """linear_out with the DDPM update in its epilogue (EGOEGO_FUSE_DDPM=1) against linear_out + ddpm_update_kernel (default):

@@ -20,7 +20,10 @@ params = O.init_params(0)
 res = {}
 os.environ.setdefault("EGOEGO_SPLIT_STEPS", "")
 SPLIT_ENV = os.environ["EGOEGO_SPLIT_STEPS"]
+ONLY = os.environ.get("LOOP_ONLY", "")          # e.g. LOOP_ONLY=fp16: time just that mode
 for tag, K, n in (("fp16", E.PRECISE_ALL_FP16, N), ("split", 10 ** 6, max(N // 4, 50)), ("pair", 10 ** 6, max(N // 4, 50)), ("default", 0, N)):
+    if ONLY and tag not in ONLY.split(","):
+        continue
     # "split": every step in the 3-term format; "pair": every step with fp16 activations x fp16-pair weights
     os.environ["EGOEGO_SPLIT_STEPS"] = {"split": "1000000", "pair": "0"}.get(tag, SPLIT_ENV)
     if not os.environ["EGOEGO_SPLIT_STEPS"]:

@@ -122,13 +122,14 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--arms", default="ours,torch", help="comma-separated: ours, torch")
     a = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    res = run_arms(dev, a.batch, 120, a.steps, a.warmup, rank, world, local)
+    res = run_arms(dev, a.batch, 120, a.steps, a.warmup, rank, world, local, arms=tuple(a.arms.split(",")))
     if rank == 0:
         print(json.dumps(res), flush=True)
     if world > 1:
