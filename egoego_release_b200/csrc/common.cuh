@@ -184,10 +184,12 @@ struct DropCfg {
     uint32_t thresh;      // keep iff philox word < thresh
     float scale;          // 1 / (1 - p)
     int on;               // 0: identity (eval mode)
+    const unsigned long long* seed_dev;   // non-null: the seed lives in device memory (a captured training step is replayed with a new seed)
 };
 __device__ __forceinline__ uint4 drop_words(const DropCfg& d, uint32_t stream, unsigned long long quad) {
+    const unsigned long long sd = d.seed_dev ? *d.seed_dev : d.seed;
     return philox4x32_10(make_uint4((uint32_t)quad, (uint32_t)(quad >> 32), stream, 0x44524f50u),
-                         make_uint2((uint32_t)d.seed, (uint32_t)(d.seed >> 32)));
+                         make_uint2((uint32_t)sd, (uint32_t)(sd >> 32)));
 }
 __device__ __forceinline__ float drop_factor(const DropCfg& d, uint32_t stream, unsigned long long idx) {
     if (!d.on) return 1.0f;

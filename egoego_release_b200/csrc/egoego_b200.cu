@@ -922,6 +922,12 @@ struct TrainWs {
     std::vector<TrainLayerBufs> L;
     DevBuf OUT, dOUT, dH, dH1, dY, dZ, dF, dO, dQKV, Ta, Tb, WT, gp, bp, loss, Tmp, temb_b, iota;
     std::map<std::string, DevBuf> grads;         // fused / padded gradient buffers
+    // The step is captured into a CUDA graph per (B, T, loss, mask, dropout) and replayed: its inputs are first copied into these
+    // buffers (the caller's tensors move between steps), the dropout seed and the loss live in device memory.
+    DevBuf s_x, s_cm, s_noise, s_cn, s_pm, s_t, s_sa, s_sb, s_wt, s_seed, s_loss;
+    struct GraphKey { int B, T, l2, pm, drop; uint32_t thresh; bool operator<(const GraphKey& o) const {
+        return std::tie(B, T, l2, pm, drop, thresh) < std::tie(o.B, o.T, o.l2, o.pm, o.drop, o.thresh); } };
+    std::map<GraphKey, cudaGraphExec_t> graphs;  // nullptr value: the key has run once eagerly (allocations, attributes) and is captured next time
 };
 
 static std::map<egoego_ctx*, std::unique_ptr<TrainWs>> g_train;
@@ -934,6 +940,8 @@ void train_release(egoego_ctx* c) {
         for (auto& l : w->L) for (DevBuf* b : {&l.QKV, &l.O, &l.Y1, &l.st1, &l.H1, &l.F, &l.Y2, &l.st2}) b->release();
         for (DevBuf* b : {&w->OUT, &w->dOUT, &w->dH, &w->dH1, &w->dY, &w->dZ, &w->dF, &w->dO, &w->dQKV, &w->Ta, &w->Tb, &w->WT, &w->gp, &w->bp, &w->loss, &w->Tmp, &w->temb_b, &w->iota}) b->release();
         for (auto& kv : w->grads) kv.second.release();
+        for (DevBuf* b : {&w->s_x, &w->s_cm, &w->s_noise, &w->s_cn, &w->s_pm, &w->s_t, &w->s_sa, &w->s_sb, &w->s_wt, &w->s_seed, &w->s_loss}) b->release();
+        for (auto& kv : w->graphs) if (kv.second) cudaGraphExecDestroy(kv.second);
     }
     g_train.erase(it);
 }
@@ -987,6 +995,14 @@ static int tr_weight_grad(TrainWs* w, const float* dY, int ldy, int rowsW, const
 
 static int train_alloc(egoego_ctx* c, TrainWs* w, int B) {
     if (w->B >= B) return 0;
+    for (auto& kv : w->graphs) if (kv.second) cudaGraphExecDestroy(kv.second);      // captured pointers die with the old workspace
+    w->graphs.clear();
+    {
+        const size_t xe = (size_t)B * (c->cfg.max_timesteps - 1) * c->D * 4;
+        if (w->s_x.alloc(xe) || w->s_cm.alloc(xe) || w->s_noise.alloc(xe) || w->s_cn.alloc(xe) || w->s_pm.alloc((size_t)B * c->cfg.max_timesteps * 4) ||
+            w->s_t.alloc((size_t)B * 8) || w->s_sa.alloc((size_t)B * 4) || w->s_sb.alloc((size_t)B * 4) || w->s_wt.alloc((size_t)B * 4) ||
+            w->s_seed.alloc(8) || w->s_loss.alloc(4)) return 1;
+    }
     const size_t M = (size_t)((B + 1) / 2) * 2 * LP, d = c->d, nq = 3 * c->H * c->dk, hd = c->H * c->dk;   // rows rounded to the 256-row tile grid
     w->Hin.resize(c->NL + 1); w->L.resize(c->NL);
     for (auto& h : w->Hin) if (h.alloc(M * d * 4)) return 1;
@@ -1011,35 +1027,60 @@ static int train_alloc(egoego_ctx* c, TrainWs* w, int B) {
     return 0;
 }
 
-}  // namespace egoego
-
-extern "C" {
-
-int egoego_train_step(egoego_handle c, const float* x_start, const float* cond_mask, const float* pmask, const int64_t* t_dev,
-                      const float* noise, const float* cond_noise, const float* sqrt_ac, const float* sqrt_1mac, const float* weight,
-                      int loss_l2, int B, int T, float* loss_out, void* stream_v) {
-    if (check_ready(c, B, T)) return 1;
-    EG_CHECK(x_start && cond_mask && t_dev && noise && cond_noise && sqrt_ac && sqrt_1mac && weight && loss_out, "null argument");
-    EG_CHECK(c->cfg.engine == EGOEGO_ENGINE_SIMT, "the training step runs on the fp32 engine: create the handle with EGOEGO_ENGINE_SIMT");
-    EG_CHECK(c->d == 512 && c->dk == 256, "training step is specialised for d_model = 512, d_k = 256");
-    EG_CHECK(B <= c->cfg.max_batch, "training batch exceeds cfg.max_batch");
-    EG_CUDA(cudaSetDevice(c->cfg.device));
-    {
-        static bool attr = false;
-        if (!attr) { EG_CUDA(cudaFuncSetAttribute(attention_bwd_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_BWD_SMEM)); attr = true; }
+// Many small device-to-device copies in ONE launch (parameter refresh before a training step: 72 tensors; gradients after it: 72
+// tensors -- 144 copy nodes of 2-3 us each otherwise).  Entries are 2-D fp32 blocks (rows x cols with leading dimensions).
+constexpr int MCOPY_MAX = 96;
+struct MCopyEntry { float* dst; const float* src; int rows, cols, dld, sld; };
+struct MCopyTable { MCopyEntry e[MCOPY_MAX]; };
+static __global__ void multi_copy_kernel(const __grid_constant__ MCopyTable tab) {
+    const MCopyEntry& e = tab.e[blockIdx.y];
+    const long long n = (long long)e.rows * e.cols;
+    const bool v4 = (e.cols & 3) == 0 && (e.dld & 3) == 0 && (e.sld & 3) == 0 &&
+                    (((uintptr_t)e.dst | (uintptr_t)e.src) & 15) == 0;
+    if (v4) {
+        const int c4 = e.cols >> 2;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n / 4; i += (long long)gridDim.x * blockDim.x) {
+            const int r = (int)(i / c4), c = (int)(i % c4) * 4;
+            *reinterpret_cast<float4*>(e.dst + (long long)r * e.dld + c) = *reinterpret_cast<const float4*>(e.src + (long long)r * e.sld + c);
+        }
+    } else {
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+            const int r = (int)(i / e.cols), c = (int)(i % e.cols);
+            e.dst[(long long)r * e.dld + c] = e.src[(long long)r * e.sld + c];
+        }
     }
-    cudaStream_t s = (cudaStream_t)stream_v;
-    std::unique_ptr<TrainWs>& wp = g_train[c];
-    if (!wp) wp.reset(new TrainWs());
-    TrainWs* w = wp.get();
-    if (train_alloc(c, w, B)) return 1;
+}
+// While `g_copy_batch` is set (the batched entry points below), copy_block() collects instead of issuing a memcpy.
+static thread_local std::vector<MCopyEntry>* g_copy_batch = nullptr;
+static int copy_block(float* dst, int dld, const float* src, int sld, int rows, int cols, cudaStream_t s) {
+    if (g_copy_batch) { g_copy_batch->push_back(MCopyEntry{dst, src, rows, cols, dld, sld}); return 0; }
+    if (rows == 1 || (dld == cols && sld == cols)) { EG_CUDA(cudaMemcpyAsync(dst, src, (size_t)rows * cols * 4, cudaMemcpyDeviceToDevice, s)); }
+    else { EG_CUDA(cudaMemcpy2DAsync(dst, (size_t)dld * 4, src, (size_t)sld * 4, (size_t)cols * 4, (size_t)rows, cudaMemcpyDeviceToDevice, s)); }
+    return 0;
+}
+static int flush_copy_batch(std::vector<MCopyEntry>& v, cudaStream_t s) {
+    for (size_t i0 = 0; i0 < v.size(); i0 += MCOPY_MAX) {
+        MCopyTable tab;
+        const int n = (int)std::min(v.size() - i0, (size_t)MCOPY_MAX);
+        for (int i = 0; i < n; ++i) tab.e[i] = v[i0 + i];
+        multi_copy_kernel<<<dim3(32, n), 256, 0, s>>>(tab);
+        EG_CUDA(cudaGetLastError());
+    }
+    v.clear();
+    return 0;
+}
+
+static __global__ void tr_set_u64_kernel(unsigned long long* p, unsigned long long v) { *p = v; }
+
+// The launches of one training step on stream `s` (capturable: no allocation, no host synchronisation; every pointer is either the
+// handle's own or one of the workspace's staging buffers).
+static int train_step_body(egoego_ctx* c, TrainWs* w, const float* x_start, const float* cond_mask, const float* pmask, const int64_t* t_dev,
+                           const float* noise, const float* cond_noise, const float* sqrt_ac, const float* sqrt_1mac, const float* weight,
+                           int loss_l2, int B, int T, float* loss_out, DropCfg drop, cudaStream_t s) {
     const int M = B * LP, d = c->d, H = c->H, dk = c->dk, nq = 3 * H * dk, hd = H * dk, D = c->D, L = T + 1, KP = c->kin_pad;
     const long long nel = (long long)B * T * D;
     const float qs = 1.0f / sqrtf((float)dk);
     auto nblk = [](long long n) { return (unsigned)((n + 255) / 256); };
-    // dropout of the three sites per layer (common.cuh: DropCfg); p = 0 keeps the eval-mode semantics
-    DropCfg drop{c->drop_seed, 0u, 1.0f, 0};
-    if (c->drop_p > 0.0) { drop.on = 1; drop.thresh = (uint32_t)((1.0 - c->drop_p) * 4294967296.0); drop.scale = (float)(1.0 / (1.0 - c->drop_p)); }
 
     // the batch's own timestep embeddings from the CURRENT time_mlp weights; the start epilogue indexes them by window (the
     // sampler's full table stays stale until the next egoego_commit_weights -- training handles never sample)
@@ -1123,9 +1164,85 @@ int egoego_train_step(egoego_handle c, const float* x_start, const float* cond_m
     tr_frame_rows_kernel<<<nblk((long long)M * d), 256, 0, s>>>(dH, dY, T, M, d);
     tr_colsum(dY, M, d, d, G("start_b"), s);
     if (tr_weight_grad(w, dY, d, d, c->Ain.as<float>(), KP, KP, M, G("start_w"), KP, s)) return 1;
-    tr_loss_finish_kernel<<<1, 1, 0, s>>>(w->loss.as<double>(), loss_out);      // fp64 accumulator -> the caller's float, no host round trip
-    c->launches += 40 * c->NL + 20;
+    tr_loss_finish_kernel<<<1, 1, 0, s>>>(w->loss.as<double>(), loss_out);      // fp64 accumulator -> float, no host round trip
     EG_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace egoego
+
+extern "C" {
+
+int egoego_train_step(egoego_handle c, const float* x_start, const float* cond_mask, const float* pmask, const int64_t* t_dev,
+                      const float* noise, const float* cond_noise, const float* sqrt_ac, const float* sqrt_1mac, const float* weight,
+                      int loss_l2, int B, int T, float* loss_out, void* stream_v) {
+    if (check_ready(c, B, T)) return 1;
+    EG_CHECK(x_start && cond_mask && t_dev && noise && cond_noise && sqrt_ac && sqrt_1mac && weight && loss_out, "null argument");
+    EG_CHECK(c->cfg.engine == EGOEGO_ENGINE_SIMT, "the training step runs on the fp32 engine: create the handle with EGOEGO_ENGINE_SIMT");
+    EG_CHECK(c->d == 512 && c->dk == 256, "training step is specialised for d_model = 512, d_k = 256");
+    EG_CHECK(B <= c->cfg.max_batch, "training batch exceeds cfg.max_batch");
+    EG_CUDA(cudaSetDevice(c->cfg.device));
+    {
+        static bool attr = false;
+        if (!attr) { EG_CUDA(cudaFuncSetAttribute(attention_bwd_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_BWD_SMEM)); attr = true; }
+    }
+    cudaStream_t user = (cudaStream_t)stream_v;
+    std::unique_ptr<TrainWs>& wp = g_train[c];
+    if (!wp) wp.reset(new TrainWs());
+    TrainWs* w = wp.get();
+    if (train_alloc(c, w, B)) return 1;
+    // dropout of the three sites per layer (common.cuh: DropCfg); p = 0 keeps the eval-mode semantics
+    DropCfg drop{c->drop_seed, 0u, 1.0f, 0, nullptr};
+    if (c->drop_p > 0.0) { drop.on = 1; drop.thresh = (uint32_t)((1.0 - c->drop_p) * 4294967296.0); drop.scale = (float)(1.0 / (1.0 - c->drop_p)); }
+    c->launches += 40 * c->NL + 20;
+    static const bool use_graph = []() { const char* e = getenv("EGOEGO_TRAIN_GRAPH"); return !(e && e[0] == '0'); }();
+    if (!use_graph)
+        return train_step_body(c, w, x_start, cond_mask, pmask, t_dev, noise, cond_noise, sqrt_ac, sqrt_1mac, weight, loss_l2, B, T, loss_out, drop, user);
+
+    // ---- graph path: stage the inputs (caller's stream), then run / capture / replay the body on the handle's own stream ----
+    const size_t xe = (size_t)B * T * c->D * 4;
+    EG_CUDA(cudaMemcpyAsync(w->s_x.p, x_start, xe, cudaMemcpyDeviceToDevice, user));
+    EG_CUDA(cudaMemcpyAsync(w->s_cm.p, cond_mask, xe, cudaMemcpyDeviceToDevice, user));
+    EG_CUDA(cudaMemcpyAsync(w->s_noise.p, noise, xe, cudaMemcpyDeviceToDevice, user));
+    EG_CUDA(cudaMemcpyAsync(w->s_cn.p, cond_noise, xe, cudaMemcpyDeviceToDevice, user));
+    if (pmask) EG_CUDA(cudaMemcpyAsync(w->s_pm.p, pmask, (size_t)B * (T + 1) * 4, cudaMemcpyDeviceToDevice, user));
+    EG_CUDA(cudaMemcpyAsync(w->s_t.p, t_dev, (size_t)B * 8, cudaMemcpyDeviceToDevice, user));
+    EG_CUDA(cudaMemcpyAsync(w->s_sa.p, sqrt_ac, (size_t)B * 4, cudaMemcpyDeviceToDevice, user));
+    EG_CUDA(cudaMemcpyAsync(w->s_sb.p, sqrt_1mac, (size_t)B * 4, cudaMemcpyDeviceToDevice, user));
+    EG_CUDA(cudaMemcpyAsync(w->s_wt.p, weight, (size_t)B * 4, cudaMemcpyDeviceToDevice, user));
+    tr_set_u64_kernel<<<1, 1, 0, user>>>(w->s_seed.as<unsigned long long>(), c->drop_seed);
+    drop.seed_dev = w->s_seed.as<unsigned long long>();
+    cudaStream_t s = c->own_stream;
+    EG_CUDA(cudaEventRecord(c->ev_in, user));
+    EG_CUDA(cudaStreamWaitEvent(s, c->ev_in, 0));
+    auto body = [&](cudaStream_t st) -> int {
+        return train_step_body(c, w, w->s_x.as<float>(), w->s_cm.as<float>(), pmask ? w->s_pm.as<float>() : nullptr, w->s_t.as<int64_t>(),
+                               w->s_noise.as<float>(), w->s_cn.as<float>(), w->s_sa.as<float>(), w->s_sb.as<float>(), w->s_wt.as<float>(),
+                               loss_l2, B, T, w->s_loss.as<float>(), drop, st);
+    };
+    const TrainWs::GraphKey key{B, T, loss_l2, pmask ? 1 : 0, drop.on, drop.thresh};
+    auto it = w->graphs.find(key);
+    if (it == w->graphs.end()) {                   // first step of this shape: eager (plane caches, function attributes, scratch buffers)
+        if (body(s)) return 1;
+        w->graphs[key] = nullptr;
+    } else {
+        if (!it->second) {                         // second step: capture
+            cudaGraph_t g = nullptr;
+            EG_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+            const int rc = body(s);
+            const cudaError_t ce = cudaStreamEndCapture(s, &g);
+            EG_CHECK(rc == 0, std::string("training step capture failed: ") + g_err);
+            EG_CUDA(ce);
+            cudaGraphExec_t ex = nullptr;
+            EG_CUDA(cudaGraphInstantiate(&ex, g, 0));
+            cudaGraphDestroy(g);
+            it->second = ex;
+        }
+        EG_CUDA(cudaGraphLaunch(it->second, s));
+    }
+    EG_CUDA(cudaEventRecord(c->ev_out, s));
+    EG_CUDA(cudaStreamWaitEvent(user, c->ev_out, 0));
+    EG_CUDA(cudaMemcpyAsync(loss_out, w->s_loss.p, 4, cudaMemcpyDeviceToDevice, user));
     return 0;
 }
 
@@ -1154,8 +1271,7 @@ int egoego_update_tensor_device(egoego_handle c, const char* name_in, const floa
     const std::string pre = "denoise_fn.motion_transformer.";
     if (name == pre + "start_conv.weight") {
         EG_CHECK(numel == (int64_t)d * 2 * D, "tensor '" + name + "': wrong size");
-        EG_CUDA(cudaMemcpy2DAsync(c->start_w.p, (size_t)c->kin_pad * 4, src, (size_t)2 * D * 4, (size_t)2 * D * 4, d, cudaMemcpyDeviceToDevice, s));
-        return 0;
+        return copy_block(c->start_w.as<float>(), c->kin_pad, src, 2 * D, d, 2 * D, s);
     }
     if (name == pre + "start_conv.bias") { dst = c->start_b.as<float>(); expect = d; }
     else if (name == pre + "position_vec.weight") { dst = c->pos.as<float>(); expect = (int64_t)(c->cfg.max_timesteps + 1) * d; }
@@ -1191,8 +1307,8 @@ int egoego_update_tensor_device(egoego_handle c, const char* name_in, const floa
     }
     if (!dst) return 0;                                  // schedule buffers etc.: not used by the training step
     EG_CHECK(expect == numel, "tensor '" + name + "': expected " + std::to_string(expect) + " elements, got " + std::to_string(numel));
-    EG_CUDA(cudaMemcpyAsync(dst, src, (size_t)numel * 4, cudaMemcpyDeviceToDevice, s));
-    return 0;
+    EG_CHECK(numel < (1ll << 31), "tensor too large");
+    return copy_block(dst, (int)numel, src, (int)numel, 1, (int)numel, s);
 }
 
 // Gradient of the tensor `name` (reference state_dict key, e.g. "denoise_fn.motion_transformer.layer_stack.2.self_attn.w_k.weight")
@@ -1243,21 +1359,28 @@ int egoego_train_get_grad(egoego_handle c, const char* name_in, float* dst, int6
     }
     EG_CHECK(src != nullptr, "no gradient for tensor: " + name);
     EG_CHECK(rows * cols == numel, "tensor '" + name + "': expected " + std::to_string(rows * cols) + " elements, got " + std::to_string(numel));
-    if (rows == 1 || ld == cols) { EG_CUDA(cudaMemcpyAsync(dst, src, (size_t)numel * 4, cudaMemcpyDeviceToDevice, s)); }
-    else { EG_CUDA(cudaMemcpy2DAsync(dst, (size_t)cols * 4, src, (size_t)ld * 4, (size_t)cols * 4, (size_t)rows, cudaMemcpyDeviceToDevice, s)); }
-    return 0;
+    EG_CHECK(cols < (1ll << 31) && rows < (1ll << 31), "tensor too large");
+    return copy_block(dst, (int)cols, src, rows == 1 ? (int)cols : (int)ld, (int)rows, (int)cols, s);
 }
 
 // batched forms (one FFI call per step instead of one per tensor)
 int egoego_train_get_grads(egoego_handle c, int n, const char* const* names, float* const* dsts, const int64_t* numels, void* stream_v) {
     EG_CHECK(n >= 0 && (n == 0 || (names && dsts && numels)), "null argument");
-    for (int i = 0; i < n; ++i) if (egoego_train_get_grad(c, names[i], dsts[i], numels[i], stream_v)) return 1;
-    return 0;
+    std::vector<MCopyEntry> batch;
+    g_copy_batch = &batch;
+    int rc = 0;
+    for (int i = 0; i < n && !rc; ++i) rc = egoego_train_get_grad(c, names[i], dsts[i], numels[i], stream_v);
+    g_copy_batch = nullptr;
+    return rc ? 1 : flush_copy_batch(batch, (cudaStream_t)stream_v);
 }
 int egoego_update_tensors_device(egoego_handle c, int n, const char* const* names, const float* const* srcs, const int64_t* numels, void* stream_v) {
     EG_CHECK(n >= 0 && (n == 0 || (names && srcs && numels)), "null argument");
-    for (int i = 0; i < n; ++i) if (egoego_update_tensor_device(c, names[i], srcs[i], numels[i], stream_v)) return 1;
-    return 0;
+    std::vector<MCopyEntry> batch;
+    g_copy_batch = &batch;
+    int rc = 0;
+    for (int i = 0; i < n && !rc; ++i) rc = egoego_update_tensor_device(c, names[i], srcs[i], numels[i], stream_v);
+    g_copy_batch = nullptr;
+    return rc ? 1 : flush_copy_batch(batch, (cudaStream_t)stream_v);
 }
 
 }  // extern "C"

@@ -261,14 +261,15 @@ static int launch_gemm_2cta_dual(TcImpl* I, const Plane& A, const Plane& W, int 
     int pairs = I->sms / 2;
     if (tiles < pairs) pairs = tiles;
     LaunchCfg lc(2 * pairs, GEMM_THREADS, GEMM2_SMEM_BYTES, s, 2);
-    EG_CUDA(cudaLaunchKernelEx(&lc.cfg, kern, A.mhi, A.mlo, W.mhi128, W.mlo128, M, N, K, epi, I->next_dir(), 1));
+    EG_CUDA(cudaLaunchKernelEx(&lc.cfg, kern, A.mhi, A.mlo, W.mhi128, W.mlo128, M, N, K, epi, I->next_dir(), 1, 1));
     return 0;
 }
 
 // 2-CTA (cluster of 2, cta_group::2) launch: 256 x 256 tiles per CTA pair.
 template <int FMT, class Epi>
-static int launch_gemm_2cta(TcImpl* I, const Plane& A, const Plane& W, int M, int N, int K, const Epi& epi, cudaStream_t s) {
+static int launch_gemm_2cta(TcImpl* I, const Plane& A, const Plane& W, int M, int N, int K, const Epi& epi, cudaStream_t s, int ksplit = 1) {
     EG_CHECK(M % 256 == 0 && N % 256 == 0 && K % GEMM_BK == 0, "2-CTA gemm shape not tile-aligned");
+    EG_CHECK(ksplit >= 1 && (K / GEMM_BK) % ksplit == 0 && (ksplit == 1 || fmt_is_split(FMT)), "bad split-K factor");
     if constexpr (FMT == FMT_SPLIT) {
         if (I->dual_acc && use_dual_acc()) return launch_gemm_2cta_dual<FMT>(I, A, W, M, N, K, epi, s);
     }
@@ -279,14 +280,14 @@ static int launch_gemm_2cta(TcImpl* I, const Plane& A, const Plane& W, int M, in
         EG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_BYTES));
     }
     EG_CHECK(M % 256 == 0 && N % 256 == 0 && K % GEMM_BK == 0, "2-CTA gemm shape not tile-aligned");
-    const int tiles = (M / 256) * (N / 256);
+    const int tiles = (M / 256) * (N / 256) * ksplit;
     int pairs = I->sms / 2;
     if (tiles < pairs) pairs = tiles;
     LaunchCfg lc(2 * pairs, GEMM_THREADS, GEMM2_SMEM_BYTES, s, 2);
     const int rev = I->next_dir();
-    if (fmt_is_split(FMT)) { EG_CUDA(cudaLaunchKernelEx(&lc.cfg, kern, A.mhi, A.mlo, W.mhi128, W.mlo128, M, N, K, epi, rev, 1)); }
-    else if (I->w_pair)   { EG_CUDA(cudaLaunchKernelEx(&lc.cfg, kern, A.m16, A.m16, W.mlo128, W.mhi128, M, N, K, epi, rev, 2)); }
-    else                  { EG_CUDA(cudaLaunchKernelEx(&lc.cfg, kern, A.m16, A.m16, W.m16_128, W.m16_128, M, N, K, epi, rev, 1)); }
+    if (fmt_is_split(FMT)) { EG_CUDA(cudaLaunchKernelEx(&lc.cfg, kern, A.mhi, A.mlo, W.mhi128, W.mlo128, M, N, K, epi, rev, 1, ksplit)); }
+    else if (I->w_pair)   { EG_CUDA(cudaLaunchKernelEx(&lc.cfg, kern, A.m16, A.m16, W.mlo128, W.mhi128, M, N, K, epi, rev, 2, 1)); }
+    else                  { EG_CUDA(cudaLaunchKernelEx(&lc.cfg, kern, A.m16, A.m16, W.m16_128, W.m16_128, M, N, K, epi, rev, 1, 1)); }
     return 0;
 }
 
@@ -864,8 +865,16 @@ int tc_gemm_f32(const float* A, int lda, const float* W, int ldw, int M, int N, 
     EG_CHECK(PA && PW, "tc_gemm_f32: plane allocation failed");
     split_pad_kernel<<<(unsigned)(((long long)Mp * Kp / 4 + 255) / 256), 256, 0, s>>>(A, M, K, lda, PA->hi, PA->lo, Mp, Kp);
     split_pad_kernel<<<(unsigned)(((long long)Np * Kp / 4 + 255) / 256), 256, 0, s>>>(W, N, K, ldw, PW->hi, PW->lo, Np, Kp);
-    TcEpiPlainAcc e{{}, C, ldc, n_valid, accumulate};
-    return launch_gemm_2cta<FMT_SPLIT_BF16>(&g_tcg.I, *PA, *PW, Mp, Np, Kp, e, s);
+    // Split-K for products with few output tiles and a long K (the weight gradients: 512 x 512 x 4096 is 4 tiles, i.e. 8 of 148 SMs for
+    // 64 k-blocks): the largest power of two that keeps every CTA pair at one tile or less and a partial product at >= 8 k-blocks.
+    // Partials are added with float4 atomics into a zeroed (or, when accumulating, the existing) C -- fp32 sums in arrival order.
+    const int out_tiles = (Mp / 256) * (Np / 256), kb = Kp / 64, pairs = g_tcg.I.sms / 2;
+    int ksplit = 1;
+    static const bool allow_split = []() { const char* e = getenv("EGOEGO_TRAIN_SPLITK"); return !(e && e[0] == '0'); }();
+    while (allow_split && ksplit < 16 && out_tiles * ksplit * 2 <= pairs && kb % (ksplit * 2) == 0 && kb / (ksplit * 2) >= 8) ksplit *= 2;
+    if (ksplit > 1 && !accumulate) EG_CUDA(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)n_valid * 4, (size_t)Mp, s));
+    TcEpiPlainAcc e{{}, C, ldc, n_valid, ksplit > 1 ? 2 : accumulate};
+    return launch_gemm_2cta<FMT_SPLIT_BF16>(&g_tcg.I, *PA, *PW, Mp, Np, Kp, e, s, ksplit);
 }
 
 struct EpiStore { float* C; int ldc; __device__ void operator()(int r, int c, float a) const { C[(long long)r * ldc + c] = a; } };

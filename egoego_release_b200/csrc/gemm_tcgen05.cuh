@@ -201,15 +201,17 @@ struct TcEpiPlain : EpiNoDirect, EpiNoPre {   // C = acc (+ bias): self-test / g
     }
 };
 
-struct TcEpiPlainAcc : EpiNoDirect {         // C = acc (accumulate == 0) or C += acc: generic products of the training step
-    float* C; int ldc; int n_valid; int accumulate;
+struct TcEpiPlainAcc : EpiNoDirect {         // C = acc (accumulate == 0), C += acc (1), or atomic C += acc (2: the partial products of a
+    float* C; int ldc; int n_valid; int accumulate;      // split-K launch, whose tiles of one output block run on different CTA pairs)
     __device__ __forceinline__ float4 bias4(int) const { return make_float4(0.f, 0.f, 0.f, 0.f); }
     __device__ __forceinline__ float4 pre(int row, int col) const {
-        return (accumulate && col < n_valid) ? *reinterpret_cast<const float4*>(C + (long long)row * ldc + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+        return (accumulate == 1 && col < n_valid) ? *reinterpret_cast<const float4*>(C + (long long)row * ldc + col) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __device__ __forceinline__ void apply4(int row, int col, float4 a, float4, float4 old) const {
         if (col >= n_valid) return;
-        *reinterpret_cast<float4*>(C + (long long)row * ldc + col) = add4(a, old);
+        float4* dst = reinterpret_cast<float4*>(C + (long long)row * ldc + col);
+        if (accumulate == 2) atomicAdd(dst, a);
+        else *dst = add4(a, old);
     }
 };
 
@@ -436,7 +438,10 @@ gemm_split3_2cta_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_co
                         const __grid_constant__ CUtensorMap mWh, const __grid_constant__ CUtensorMap mWl,   // W maps: 128-row boxes
                         int M, int N, int K, Epi epi, int rev = 0 /* 1: walk the tiles from the last row block to the first (L2 zig-zag) */,
                         int wpasses = 1 /* FMT_HALF only: 2 = weights as an fp16 pair, pass 0 multiplies A by mWh (the LO plane goes
-                                           first), pass 1 by mWl -- see gemm_half_tma_2cta_kernel */) {
+                                           first), pass 1 by mWl -- see gemm_half_tma_2cta_kernel */,
+                        int ksplit = 1 /* split-K: every output tile is computed as `ksplit` partial products over K / ksplit each, on
+                                          different CTA pairs; the functor must accumulate atomically (TcEpiPlainAcc mode 2).  For the
+                                          weight gradients of the training step: 512 x 512 outputs with K = 4096 are 4 tiles */) {
     constexpr int BN = 256;
     constexpr int NP = Gemm2Cfg<FMT>::NP;
     static_assert(!DUAL || NP == 2, "the dual-accumulator variant is for the 3-term split formats");
@@ -464,9 +469,10 @@ gemm_split3_2cta_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_co
     const uint32_t rank = ptx::cluster_ctarank();
     const bool leader = rank == 0;
     const int pair = blockIdx.x / 2, n_pairs = gridDim.x / 2;
-    const int m_tiles = M / 256, n_tiles = N / BN, k_real = K / GEMM_BK;
+    const int m_tiles = M / 256, n_tiles = N / BN, k_real = K / GEMM_BK / ksplit;   // k-blocks of one (partial) product
     const int k_blocks = (NP == 1 ? wpasses : 1) * k_real;          // k-blocks streamed per tile
-    const int total_tiles = m_tiles * n_tiles;
+    const int out_tiles = m_tiles * n_tiles;
+    const int total_tiles = out_tiles * ksplit;                      // tile index = split * out_tiles + output tile
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&mAh); ptx::prefetch_tmap(&mAl); ptx::prefetch_tmap(&mWh); ptx::prefetch_tmap(&mWl);
@@ -487,7 +493,8 @@ gemm_split3_2cta_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_co
         if (lane == 0) {                                 // ===== TMA producer (both CTAs) =====
             int s = 0; uint32_t ph = 0;
             for (int tl = pair; tl < total_tiles; tl += n_pairs) {
-                const int tile = rev ? total_tiles - 1 - tl : tl;
+                const int tile_s = rev ? total_tiles - 1 - tl : tl;
+                const int tile = tile_s % out_tiles, k_first = (tile_s / out_tiles) * k_real;
                 const int m0 = (tile / n_tiles) * 256 + (int)rank * 128;
                 const int n0 = (tile % n_tiles) * BN + (int)rank * 128;
                 for (int kb = 0; kb < k_blocks; ++kb) {
@@ -495,7 +502,7 @@ gemm_split3_2cta_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_co
                     uint8_t* st = smem + s * GEMM2_STAGE_BYTES;
                     if (leader) ptx::mbar_arrive_expect_tx(&full_bar[s], 2 * GEMM2_STAGE_BYTES);
                     else        ptx::mbar_arrive_cluster(&full_bar[s], 0);
-                    const int kx = (NP == 1 && kb >= k_real) ? kb - k_real : kb;
+                    const int kx = k_first + ((NP == 1 && kb >= k_real) ? kb - k_real : kb);
                     ptx::tma_load_2d_2cta(st, &mAh, &full_bar[s], kx * GEMM_BK, m0);
                     if (NP == 2) ptx::tma_load_2d_2cta(st + T_BYTES, &mAl, &full_bar[s], kx * GEMM_BK, m0);
                     ptx::tma_load_2d_2cta(st + NP * T_BYTES, (NP == 1 && kb >= k_real) ? &mWl : &mWh, &full_bar[s], kx * GEMM_BK, n0);
@@ -539,7 +546,7 @@ gemm_split3_2cta_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_co
         const int quarter = (warp - 2) & 3;
         int it = 0;
         for (int tl = pair; tl < total_tiles; tl += n_pairs, ++it) {
-            const int tile = rev ? total_tiles - 1 - tl : tl;
+            const int tile = (rev ? total_tiles - 1 - tl : tl) % out_tiles;
             const int a = DUAL ? 0 : (it & 1);
             const uint32_t aph = DUAL ? (it & 1) : ((it >> 1) & 1);
             const int m0 = (tile / n_tiles) * 256 + (int)rank * 128, n0 = (tile % n_tiles) * BN;
