@@ -83,6 +83,7 @@ struct egoego_ctx {
 namespace egoego {
 
 void train_release(egoego_ctx* c);     // frees the training workspace of a handle (defined with the training step below)
+void train_drop_graphs(egoego_ctx* c); // captured training steps hold the handle's buffer addresses: dropped whenever those may move
 
 // largest opt-in dynamic shared-memory size requested so far per device (function attributes are per device)
 struct PerDeviceMax {
@@ -393,6 +394,7 @@ static int upload(DevBuf& b, const std::vector<float>& v) {
 int egoego_commit_weights(egoego_handle c, void* stream_v) {
     EG_CHECK(c, "null handle");
     EG_CUDA(cudaSetDevice(c->cfg.device));
+    train_drop_graphs(c);
     cudaStream_t s = (cudaStream_t)stream_v;
     auto need = [&](const std::string& k) -> const std::vector<float>* {
         auto it = c->staged.find(k);
@@ -931,6 +933,13 @@ struct TrainWs {
 };
 
 static std::map<egoego_ctx*, std::unique_ptr<TrainWs>> g_train;
+
+void train_drop_graphs(egoego_ctx* c) {
+    auto it = g_train.find(c);
+    if (it == g_train.end() || !it->second) return;
+    for (auto& kv : it->second->graphs) if (kv.second) cudaGraphExecDestroy(kv.second);
+    it->second->graphs.clear();
+}
 
 void train_release(egoego_ctx* c) {
     auto it = g_train.find(c);

@@ -28,7 +28,7 @@ from oracle import egoego_oracle as O
 from oracle import training as TR
 
 
-def run_arms(dev, B=32, T=120, steps=20, warmup=5, rank=0, world=1, local=0, arms=("ours", "torch")):
+def run_arms(dev, B=32, T=120, steps=20, warmup=5, rank=0, world=1, local=0, arms=("ours", "torch"), sync_mode="flat"):
     """Time the two arms on this rank's GPU; returns {arm: {ms_per_step, samples_per_s, ...}} (max over ranks when world > 1)."""
     g = torch.Generator(device=dev).manual_seed(100 + rank)
     x0 = torch.rand(B, T, 198, device=dev, generator=g) * 2 - 1                       # motion ~ U(-1, 1) (SURVEY.md 8d config 5)
@@ -65,13 +65,18 @@ def run_arms(dev, B=32, T=120, steps=20, warmup=5, rank=0, world=1, local=0, arm
 
     def run(arm):
         mod = (OursStep() if arm == "ours" else TorchStep()).to(dev).train()
-        net = DDP(mod, device_ids=[local]) if world > 1 else mod
+        flat = arm == "ours" and world > 1 and sync_mode == "flat"
+        if flat:                                   # the engine's own gradient averaging: one all-reduce of the flat buffer, no DDP wrapper
+            mod.model.set_grad_sync()
+            net = mod
+        else:
+            net = DDP(mod, device_ids=[local]) if world > 1 else mod
         opt = torch.optim.Adam([p for p in mod.parameters() if p.requires_grad], lr=1e-4)
         scaler = torch.amp.GradScaler("cuda", enabled=True)
 
         def step(sync=True):
             opt.zero_grad(set_to_none=True)
-            ctx = net.no_sync() if (world > 1 and not sync) else contextlib.nullcontext()
+            ctx = (mod.model.no_grad_sync() if flat else net.no_sync()) if (world > 1 and not sync) else contextlib.nullcontext()
             with ctx:
                 with torch.autocast("cuda", dtype=torch.float16, enabled=True):
                     loss = net(x0, cm, pm)
@@ -100,6 +105,8 @@ def run_arms(dev, B=32, T=120, steps=20, warmup=5, rank=0, world=1, local=0, arm
         ms, loss = timed(True)
         out = {"ms_per_step": ms, "samples_per_s": world * B / (ms * 1e-3), "last_loss": loss}
         if world > 1:
+            out["grad_sync"] = "set_grad_sync (one flat all-reduce)" if flat else "torch DDP"
+        if world > 1:
             ms_ns, _ = timed(False)
             out["ms_per_step_no_grad_sync"] = ms_ns
             out["exposed_allreduce_share"] = max(0.0, 1.0 - ms_ns / ms)
@@ -123,13 +130,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--arms", default="ours,torch", help="comma-separated: ours, torch")
+    ap.add_argument("--sync", default="flat", choices=("flat", "ddp"),
+                    help="N > 1, our arm: flat = CondGaussianDiffusion.set_grad_sync (one all-reduce), ddp = torch DDP wrapper; the torch arm always uses DDP")
     a = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    res = run_arms(dev, a.batch, 120, a.steps, a.warmup, rank, world, local, arms=tuple(a.arms.split(",")))
+    res = run_arms(dev, a.batch, 120, a.steps, a.warmup, rank, world, local, arms=tuple(a.arms.split(",")), sync_mode=a.sync)
     if rank == 0:
         print(json.dumps(res), flush=True)
     if world > 1:
