@@ -997,9 +997,21 @@ static void tr_colsum(const float* X, int M, int C, int ld, float* out, cudaStre
 }
 // g [rowsW, Kd] = dY^T [rowsW, M] X [M, Kd]  (dY [M, ldy] with rowsW valid columns, X [M, ldx] with Kd valid columns)
 static int tr_weight_grad(TrainWs* w, const float* dY, int ldy, int rowsW, const float* X, int ldx, int Kd, int M, float* g, int ldg, cudaStream_t s) {
+    // tensor cores: both operands are stored with the reduction index (the token row) as the ROW -- converted to K-major planes directly
+    if (train_use_tc()) return tc_gemm_f32_ex(dY, ldy, 1, X, ldx, 1, rowsW, Kd, M, g, ldg, Kd, 0, s);
     tr_transpose(dY, M, rowsW, ldy, w->Ta.as<float>(), M, s);          // [rowsW, M] (SIMT path: rows up to the next multiple of 128 may hold
     tr_transpose(X, M, Kd, ldx, w->Tb.as<float>(), M, s);              // stale data; their products land in the padded rows of g)
     return tr_gemm_plain(w->Ta.as<float>(), M, w->Tb.as<float>(), M, rowsW, Kd, M, g, ldg, false, s);
+}
+
+// C [rows, N] (= or +=) A [rows, K] Wsrc [K, N]: the input gradient of a linear layer whose weight is stored [out = K, in = N]
+static int tr_gemm_wt(TrainWs* w, const float* A, int lda, const float* Wsrc, int ldw, int rows, int N, int K, float* C, int ldc, bool acc, cudaStream_t s) {
+    if (train_use_tc()) return tc_gemm_f32_ex(A, lda, 0, Wsrc, ldw, 1, rows, N, K, C, ldc, N, acc ? 1 : 0, s);
+    const int Kp = ((K + 63) / 64) * 64;                 // fp32 CUDA-core path: explicit transpose into WT [N, Kp], zero padded
+    float* WT = w->WT.as<float>();
+    EG_CUDA(cudaMemsetAsync(WT, 0, (size_t)N * Kp * 4, s));
+    tr_transpose(Wsrc, K, N, ldw, WT, Kp, s);
+    return tr_gemm_plain(A, lda, WT, Kp, rows, N, Kp, C, ldc, acc, s);
 }
 
 static int train_alloc(egoego_ctx* c, TrainWs* w, int B) {
@@ -1121,13 +1133,11 @@ static int train_step_body(egoego_ctx* c, TrainWs* w, const float* x_start, cons
 
     // ---------------- backward ----------------
     auto G = [&](const std::string& k) { return w->grads[k].as<float>(); };
-    float *dH = w->dH.as<float>(), *dH1 = w->dH1.as<float>(), *dY = w->dY.as<float>(), *dF = w->dF.as<float>(), *WT = w->WT.as<float>();
+    float *dH = w->dH.as<float>(), *dH1 = w->dH1.as<float>(), *dY = w->dY.as<float>(), *dF = w->dF.as<float>();
     // linear_out (:102,139): out = H[:, 1:] Wout^T + b
     if (tr_weight_grad(w, w->dOUT.as<float>(), 256, D, w->Hin[c->NL].as<float>(), d, d, M, G("out_w"), d, s)) return 1;
     tr_colsum(w->dOUT.as<float>(), M, D, 256, G("out_b"), s);
-    EG_CUDA(cudaMemsetAsync(WT, 0, (size_t)d * 256 * 4, s));
-    tr_transpose(c->out_w.as<float>(), D, d, d, WT, 256, s);                              // Wout^T [512, 256]
-    if (tr_gemm_plain(w->dOUT.as<float>(), 256, WT, 256, M, d, 256, dH, d, false, s)) return 1;
+    if (tr_gemm_wt(w, w->dOUT.as<float>(), 256, c->out_w.as<float>(), d, M, d, D, dH, d, false, s)) return 1;
     for (int l = c->NL - 1; l >= 0; --l) {
         LayerW& W = c->layers[l];
         TrainLayerBufs& b = w->L[l];
@@ -1141,14 +1151,12 @@ static int train_step_body(egoego_ctx* c, TrainWs* w, const float* x_start, cons
         if (drop.on) { tr_dropout_bwd_kernel<<<nblk((long long)M * d / 4), 256, 0, s>>>(dY, w->dZ.as<float>(), (long long)M * d, drop, 4u * l + 2u); dZ2 = w->dZ.as<float>(); }
         tr_colsum(dZ2, M, d, d, G(p + "b2"), s);
         if (tr_weight_grad(w, dZ2, d, d, b.F.as<float>(), d, d, M, G(p + "w2"), d, s)) return 1;
-        tr_transpose(W.w2.as<float>(), d, d, d, WT, d, s);
-        if (tr_gemm_plain(dZ2, d, WT, d, M, d, d, dF, d, false, s)) return 1;
+        if (tr_gemm_wt(w, dZ2, d, W.w2.as<float>(), d, M, d, d, dF, d, false, s)) return 1;
         tr_relu_bwd_kernel<<<nblk((long long)M * d), 256, 0, s>>>(dF, b.F.as<float>(), (long long)M * d);
         tr_colsum(dF, M, d, d, G(p + "b1"), s);
         if (tr_weight_grad(w, dF, d, d, b.H1.as<float>(), d, d, M, G(p + "w1"), d, s)) return 1;
         EG_CUDA(cudaMemcpyAsync(dH1, dY, (size_t)M * d * 4, cudaMemcpyDeviceToDevice, s));      // residual branch
-        tr_transpose(W.w1.as<float>(), d, d, d, WT, d, s);
-        if (tr_gemm_plain(dF, d, WT, d, M, d, d, dH1, d, true, s)) return 1;
+        if (tr_gemm_wt(w, dF, d, W.w1.as<float>(), d, M, d, d, dH1, d, true, s)) return 1;
         // ---- attention block (:61-95): H1 = LN1(O Wfc^T + bfc + Hin) * pm
         tr_ln_bwd_kernel<<<M / 8, 256, 0, s>>>(dH1, b.Y1.as<float>(), b.st1.as<float>(), W.ln1_g.as<float>(), pmask, T, M, dY, w->gp.as<float>(), w->bp.as<float>());
         tr_colsum(w->gp.as<float>(), M, d, d, G(p + "ln1_g"), s);
@@ -1157,14 +1165,12 @@ static int train_step_body(egoego_ctx* c, TrainWs* w, const float* x_start, cons
         if (drop.on) { tr_dropout_bwd_kernel<<<nblk((long long)M * d / 4), 256, 0, s>>>(dY, w->dZ.as<float>(), (long long)M * d, drop, 4u * l + 1u); dZ1 = w->dZ.as<float>(); }
         tr_colsum(dZ1, M, d, d, G(p + "fc_b"), s);
         if (tr_weight_grad(w, dZ1, d, d, b.O.as<float>(), hd, hd, M, G(p + "fc_w"), hd, s)) return 1;
-        tr_transpose(W.fc_w.as<float>(), d, hd, hd, WT, d, s);                              // Wfc^T [1024, 512]
-        if (tr_gemm_plain(dZ1, d, WT, d, M, hd, d, w->dO.as<float>(), hd, false, s)) return 1;
+        if (tr_gemm_wt(w, dZ1, d, W.fc_w.as<float>(), hd, M, hd, d, w->dO.as<float>(), hd, false, s)) return 1;
         attention_bwd_simt_kernel<<<B * H, 256, ATT_BWD_SMEM, s>>>(b.QKV.as<float>(), nq, w->dO.as<float>(), hd, w->dQKV.as<float>(), H, L, qs, drop, 4u * l + 0u);
         tr_colsum(w->dQKV.as<float>(), M, nq, nq, G(p + "bqkv"), s);
         if (tr_weight_grad(w, w->dQKV.as<float>(), nq, nq, w->Hin[l].as<float>(), d, d, M, G(p + "wqkv"), d, s)) return 1;
         EG_CUDA(cudaMemcpyAsync(dH, dY, (size_t)M * d * 4, cudaMemcpyDeviceToDevice, s));       // residual branch
-        tr_transpose(W.wqkv.as<float>(), nq, d, d, WT, nq, s);                              // Wqkv^T [512, 3072]
-        if (tr_gemm_plain(w->dQKV.as<float>(), nq, WT, nq, M, d, nq, dH, d, true, s)) return 1;
+        if (tr_gemm_wt(w, w->dQKV.as<float>(), nq, W.wqkv.as<float>(), d, M, d, nq, dH, d, true, s)) return 1;
     }
     // ---- time token (:105-116,122-123) and start_conv (transformer_module.py:203)
     for (const char* k : {"t_w1", "t_b1", "t_w2", "t_b2"}) EG_CUDA(cudaMemsetAsync(w->grads[k].p, 0, w->grads[k].bytes, s));

@@ -832,6 +832,32 @@ __global__ void split_pad_kernel(const float* __restrict__ src, int rows, int co
     *reinterpret_cast<uint2*>(lo + o) = make_uint2(*reinterpret_cast<uint32_t*>(&l01), *reinterpret_cast<uint32_t*>(&l23));
 }
 
+// The same conversion for an operand given TRANSPOSED: src is [cols, rows] row-major (leading dimension ld), the planes are
+// [rows_pad, cols_pad] -- plane[r][k] = src[k][r].  32 x 32 tiles through shared memory, coalesced on both sides.  Lets the weight
+// gradients (dY^T X: both operands are stored with the reduction index as the ROW) and the input gradients (dY W: the weight is
+// stored [out, in]) feed the K-major GEMM without separate fp32 transposes.
+__global__ void split_pad_t_kernel(const float* __restrict__ src, int rows, int cols, int ld, __nv_bfloat16* __restrict__ hi,
+                                   __nv_bfloat16* __restrict__ lo, int rows_pad, int cols_pad) {
+    __shared__ float tile[32][33];
+    const int r0 = blockIdx.x * 32, k0 = blockIdx.y * 32;          // plane rows r0.., plane columns k0..
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int k = k0 + threadIdx.y + 8 * i, r = r0 + threadIdx.x;
+        tile[threadIdx.y + 8 * i][threadIdx.x] = (k < cols && r < rows) ? src[(long long)k * ld + r] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = r0 + threadIdx.y + 8 * i, k = k0 + threadIdx.x;
+        if (r < rows_pad && k < cols_pad) {
+            __nv_bfloat16 h, l;
+            split_bf16(tile[threadIdx.x][threadIdx.y + 8 * i], h, l);
+            hi[(long long)r * cols_pad + k] = h;
+            lo[(long long)r * cols_pad + k] = l;
+        }
+    }
+}
+
 struct TcGemmCache {
     std::map<std::pair<long long, int>, std::unique_ptr<Plane>> planes;     // (rows_pad << 20 | cols_pad, role) -> plane
     TcImpl I;
@@ -842,6 +868,11 @@ static TcGemmCache g_tcg;
 
 int tc_gemm_f32(const float* A, int lda, const float* W, int ldw, int M, int N, int K, float* C, int ldc, int n_valid, int accumulate,
                 cudaStream_t s) {
+    return tc_gemm_f32_ex(A, lda, 0, W, ldw, 0, M, N, K, C, ldc, n_valid, accumulate, s);
+}
+
+int tc_gemm_f32_ex(const float* A, int lda, int trans_a, const float* W, int ldw, int trans_w, int M, int N, int K, float* C, int ldc, int n_valid,
+                   int accumulate, cudaStream_t s) {
     EG_CHECK(M >= 1 && N >= 1 && K >= 1 && n_valid % 4 == 0 && ldc % 4 == 0, "tc_gemm_f32: bad shape");
     int dev = 0;
     EG_CUDA(cudaGetDevice(&dev));
@@ -863,8 +894,10 @@ int tc_gemm_f32(const float* A, int lda, const float* W, int ldw, int M, int N, 
     Plane* PA = plane(Mp, Kp, 0, 128);
     Plane* PW = plane(Np, Kp, 1, 256);
     EG_CHECK(PA && PW, "tc_gemm_f32: plane allocation failed");
-    split_pad_kernel<<<(unsigned)(((long long)Mp * Kp / 4 + 255) / 256), 256, 0, s>>>(A, M, K, lda, PA->hi, PA->lo, Mp, Kp);
-    split_pad_kernel<<<(unsigned)(((long long)Np * Kp / 4 + 255) / 256), 256, 0, s>>>(W, N, K, ldw, PW->hi, PW->lo, Np, Kp);
+    if (trans_a) split_pad_t_kernel<<<dim3(Mp / 32, Kp / 32), dim3(32, 8), 0, s>>>(A, M, K, lda, PA->hi, PA->lo, Mp, Kp);
+    else         split_pad_kernel<<<(unsigned)(((long long)Mp * Kp / 4 + 255) / 256), 256, 0, s>>>(A, M, K, lda, PA->hi, PA->lo, Mp, Kp);
+    if (trans_w) split_pad_t_kernel<<<dim3(Np / 32, Kp / 32), dim3(32, 8), 0, s>>>(W, N, K, ldw, PW->hi, PW->lo, Np, Kp);
+    else         split_pad_kernel<<<(unsigned)(((long long)Np * Kp / 4 + 255) / 256), 256, 0, s>>>(W, N, K, ldw, PW->hi, PW->lo, Np, Kp);
     // Split-K for products with few output tiles and a long K (the weight gradients: 512 x 512 x 4096 is 4 tiles, i.e. 8 of 148 SMs for
     // 64 k-blocks): the largest power of two that keeps every CTA pair at one tile or less and a partial product at >= 8 k-blocks.
     // Partials are added with float4 atomics into a zeroed (or, when accumulating, the existing) C -- fp32 sums in arrival order.

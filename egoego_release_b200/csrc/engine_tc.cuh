@@ -66,6 +66,10 @@ int tc_debug_timeline(int enable, unsigned long long* out, int n);
 
 // C[M, N] (= or +=) A[M, K] W[N, K]^T, fp32 row-major device operands, on the tensor cores (3-term bf16 split, fp32 accumulate).
 // C must have ceil(M / 256) * 256 rows of ldc floats; columns [0, n_valid) are written (n_valid % 4 == 0 <= ldc).
+// tc_gemm_f32_ex: trans_a / trans_w = 1 means that operand is stored with the reduction index as the ROW ([K, M] / [K, N], leading
+// dimension lda / ldw): C = A^T W for the weight gradients, C = A W' for a weight stored [out, in] -- no separate transposes.
+int tc_gemm_f32_ex(const float* A, int lda, int trans_a, const float* W, int ldw, int trans_w, int M, int N, int K, float* C, int ldc, int n_valid,
+                   int accumulate, cudaStream_t s);
 int tc_gemm_f32(const float* A, int lda, const float* W, int ldw, int M, int N, int K, float* C, int ldc, int n_valid, int accumulate,
                 cudaStream_t s);
 
