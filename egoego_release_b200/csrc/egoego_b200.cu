@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <type_traits>
 
 #include "common.cuh"
 #include "kernels_simt.cuh"
@@ -973,6 +974,13 @@ static __global__ void tr_epi_kernel(const float* __restrict__ C, int ldc, int r
 template <class Epi>
 static int tr_gemm(TrainWs* w, const float* A, int lda, const float* W, int ldw, int rows, int N, int K, const Epi& e, cudaStream_t s) {
     if (!train_use_tc()) { sgemm_tn_kernel<<<dim3((N + 127) / 128, rows / 128), 256, 0, s>>>(A, lda, W, ldw, N, K, e); return 0; }
+    // The functor runs in the GEMM's own epilogue -- except the dropout one while dropout is on: a Philox call per element on the 8
+    // epilogue warps of an SM costs more than the separate full-occupancy pass saves (measured 5.37 vs 5.28 ms per step with
+    // everything fused; the same lesson as the DDPM update in linear_out's epilogue).  EGOEGO_TRAIN_FUSE_EPI=0: never fuse.
+    static const bool fuse = []() { const char* v = getenv("EGOEGO_TRAIN_FUSE_EPI"); return !(v && v[0] == '0'); }();
+    bool heavy = false;
+    if constexpr (std::is_same<Epi, EpiBiasDropResid>::value) heavy = e.drop.on != 0;
+    if (fuse && !heavy) return tc_gemm_f32_epi(A, lda, W, ldw, rows, N, K, e, s);
     const int ldt = ((N + 3) / 4) * 4;
     if (tc_gemm_f32(A, lda, W, ldw, rows, N, K, w->Tmp.as<float>(), ldt, ldt, 0, s)) return 1;
     tr_epi_kernel<<<(unsigned)(((long long)rows * N + 255) / 256), 256, 0, s>>>(w->Tmp.as<float>(), ldt, rows, N, e);

@@ -871,16 +871,16 @@ int tc_gemm_f32(const float* A, int lda, const float* W, int ldw, int M, int N, 
     return tc_gemm_f32_ex(A, lda, 0, W, ldw, 0, M, N, K, C, ldc, n_valid, accumulate, s);
 }
 
-int tc_gemm_f32_ex(const float* A, int lda, int trans_a, const float* W, int ldw, int trans_w, int M, int N, int K, float* C, int ldc, int n_valid,
-                   int accumulate, cudaStream_t s) {
-    EG_CHECK(M >= 1 && N >= 1 && K >= 1 && n_valid % 4 == 0 && ldc % 4 == 0, "tc_gemm_f32: bad shape");
+// operand planes of one product (cached per padded shape, role and device), filled from the fp32 operands
+static int tc_prep_planes(const float* A, int lda, int trans_a, const float* W, int ldw, int trans_w, int M, int N, int K,
+                          Plane*& PA, Plane*& PW, int& Mp, int& Np, int& Kp, cudaStream_t s) {
     int dev = 0;
     EG_CUDA(cudaGetDevice(&dev));
     if (!g_tcg.init) {
         EG_CUDA(cudaDeviceGetAttribute(&g_tcg.I.sms, cudaDevAttrMultiProcessorCount, dev));
         g_tcg.init = true;
     }
-    const int Mp = ((M + 255) / 256) * 256, Np = ((N + 255) / 256) * 256, Kp = ((K + 63) / 64) * 64;
+    Mp = ((M + 255) / 256) * 256; Np = ((N + 255) / 256) * 256; Kp = ((K + 63) / 64) * 64;
     auto plane = [&](int rows, int cols, int role, uint32_t box) -> Plane* {
         auto key = std::make_pair(((long long)rows << 20) | cols, role + 2 * dev);      // planes live on the device that made them
         auto it = g_tcg.planes.find(key);
@@ -891,13 +891,22 @@ int tc_gemm_f32_ex(const float* A, int lda, int trans_a, const float* W, int ldw
         g_tcg.planes[key] = std::move(p);
         return raw;
     };
-    Plane* PA = plane(Mp, Kp, 0, 128);
-    Plane* PW = plane(Np, Kp, 1, 256);
+    PA = plane(Mp, Kp, 0, 128);
+    PW = plane(Np, Kp, 1, 256);
     EG_CHECK(PA && PW, "tc_gemm_f32: plane allocation failed");
     if (trans_a) split_pad_t_kernel<<<dim3(Mp / 32, Kp / 32), dim3(32, 8), 0, s>>>(A, M, K, lda, PA->hi, PA->lo, Mp, Kp);
     else         split_pad_kernel<<<(unsigned)(((long long)Mp * Kp / 4 + 255) / 256), 256, 0, s>>>(A, M, K, lda, PA->hi, PA->lo, Mp, Kp);
     if (trans_w) split_pad_t_kernel<<<dim3(Np / 32, Kp / 32), dim3(32, 8), 0, s>>>(W, N, K, ldw, PW->hi, PW->lo, Np, Kp);
     else         split_pad_kernel<<<(unsigned)(((long long)Np * Kp / 4 + 255) / 256), 256, 0, s>>>(W, N, K, ldw, PW->hi, PW->lo, Np, Kp);
+    return 0;
+}
+
+int tc_gemm_f32_ex(const float* A, int lda, int trans_a, const float* W, int ldw, int trans_w, int M, int N, int K, float* C, int ldc, int n_valid,
+                   int accumulate, cudaStream_t s) {
+    EG_CHECK(M >= 1 && N >= 1 && K >= 1 && n_valid % 4 == 0 && ldc % 4 == 0, "tc_gemm_f32: bad shape");
+    Plane *PA = nullptr, *PW = nullptr;
+    int Mp, Np, Kp;
+    if (tc_prep_planes(A, lda, trans_a, W, ldw, trans_w, M, N, K, PA, PW, Mp, Np, Kp, s)) return 1;
     // Split-K for products with few output tiles and a long K (the weight gradients: 512 x 512 x 4096 is 4 tiles, i.e. 8 of 148 SMs for
     // 64 k-blocks): the largest power of two that keeps every CTA pair at one tile or less and a partial product at >= 8 k-blocks.
     // Partials are added with float4 atomics into a zeroed (or, when accumulating, the existing) C -- fp32 sums in arrival order.
@@ -909,6 +918,36 @@ int tc_gemm_f32_ex(const float* A, int lda, int trans_a, const float* W, int ldw
     TcEpiPlainAcc e{{}, C, ldc, n_valid, ksplit > 1 ? 2 : accumulate};
     return launch_gemm_2cta<FMT_SPLIT_BF16>(&g_tcg.I, *PA, *PW, Mp, Np, Kp, e, s, ksplit);
 }
+
+// The forward products of the training step with their element-wise epilogue (bias, scale, ReLU, dropout, residual, time token) run
+// in the GEMM's own epilogue: any functor of the fp32 engine (kernels_simt.cuh: operator()(row, col, acc)) is adapted to the
+// coalesced 4-columns-per-lane layout of the tensor-core epilogue, instead of a separate pass over the raw product.
+template <class E>
+struct TcEpiScalar : EpiNoDirect, EpiNoPre {
+    E e; int rows, n_valid;
+    __device__ __forceinline__ float4 bias4(int) const { return make_float4(0.f, 0.f, 0.f, 0.f); }
+    __device__ __forceinline__ void apply4(int row, int col, float4 a, float4, float4) const {
+        if (row >= rows) return;
+        if (col < n_valid) e(row, col, a.x);
+        if (col + 1 < n_valid) e(row, col + 1, a.y);
+        if (col + 2 < n_valid) e(row, col + 2, a.z);
+        if (col + 3 < n_valid) e(row, col + 3, a.w);
+    }
+};
+template <class E>
+int tc_gemm_f32_epi(const float* A, int lda, const float* W, int ldw, int M, int N, int K, const E& e, cudaStream_t s) {
+    EG_CHECK(M >= 1 && N >= 1 && K >= 1, "tc_gemm_f32_epi: bad shape");
+    Plane *PA = nullptr, *PW = nullptr;
+    int Mp, Np, Kp;
+    if (tc_prep_planes(A, lda, 0, W, ldw, 0, M, N, K, PA, PW, Mp, Np, Kp, s)) return 1;
+    TcEpiScalar<E> te{{}, {}, e, M, N};
+    return launch_gemm_2cta<FMT_SPLIT_BF16>(&g_tcg.I, *PA, *PW, Mp, Np, Kp, te, s, 1);
+}
+template int tc_gemm_f32_epi<EpiStart>(const float*, int, const float*, int, int, int, int, const EpiStart&, cudaStream_t);
+template int tc_gemm_f32_epi<EpiBiasScale>(const float*, int, const float*, int, int, int, int, const EpiBiasScale&, cudaStream_t);
+template int tc_gemm_f32_epi<EpiBiasRelu>(const float*, int, const float*, int, int, int, int, const EpiBiasRelu&, cudaStream_t);
+template int tc_gemm_f32_epi<EpiBiasDropResid>(const float*, int, const float*, int, int, int, int, const EpiBiasDropResid&, cudaStream_t);
+template int tc_gemm_f32_epi<EpiPlainBias>(const float*, int, const float*, int, int, int, int, const EpiPlainBias&, cudaStream_t);
 
 struct EpiStore { float* C; int ldc; __device__ void operator()(int r, int c, float a) const { C[(long long)r * ldc + c] = a; } };
 

@@ -70,6 +70,10 @@ int tc_debug_timeline(int enable, unsigned long long* out, int n);
 // dimension lda / ldw): C = A^T W for the weight gradients, C = A W' for a weight stored [out, in] -- no separate transposes.
 int tc_gemm_f32_ex(const float* A, int lda, int trans_a, const float* W, int ldw, int trans_w, int M, int N, int K, float* C, int ldc, int n_valid,
                    int accumulate, cudaStream_t s);
+// C = A W^T with the element-wise functor `e` (kernels_simt.cuh / train.cuh: operator()(row, col, acc), rows < M, cols < N) applied in
+// the GEMM epilogue; instantiated in engine_tc.cu for the functors of the training step's forward pass.
+template <class E>
+int tc_gemm_f32_epi(const float* A, int lda, const float* W, int ldw, int M, int N, int K, const E& e, cudaStream_t s);
 int tc_gemm_f32(const float* A, int lda, const float* W, int ldw, int M, int N, int K, float* C, int ldc, int n_valid, int accumulate,
                 cudaStream_t s);
 

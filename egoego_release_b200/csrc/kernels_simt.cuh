@@ -60,6 +60,16 @@ struct EpiBiasDropResid {    // training: dropout(acc + bias) + residual (transf
     }
 };
 
+// training step (train.cuh); defined here because the tensor-core products instantiate their fused epilogues in engine_tc.cu
+struct EpiPlainBias {        // C = acc (+ bias): all rows, cols < N
+    float* C; int ldc; const float* bias;
+    __device__ __forceinline__ void operator()(int row, int col, float acc) const { C[(long long)row * ldc + col] = acc + (bias ? bias[col] : 0.f); }
+};
+struct EpiAccum {            // C += acc
+    float* C; int ldc;
+    __device__ __forceinline__ void operator()(int row, int col, float acc) const { C[(long long)row * ldc + col] += acc; }
+};
+
 struct EpiOut {              // linear_out on tokens 1..T -> compact [B,T,d_feats]
     float* out; int d_feats; const float* bias; int T;
     __device__ __forceinline__ void operator()(int row, int col, float acc) const {

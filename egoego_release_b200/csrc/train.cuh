@@ -14,15 +14,6 @@
 
 namespace egoego {
 
-struct EpiPlainBias {        // C = acc (+ bias): all rows, cols < N
-    float* C; int ldc; const float* bias;
-    __device__ __forceinline__ void operator()(int row, int col, float acc) const { C[(long long)row * ldc + col] = acc + (bias ? bias[col] : 0.f); }
-};
-struct EpiAccum {            // C += acc
-    float* C; int ldc;
-    __device__ __forceinline__ void operator()(int row, int col, float acc) const { C[(long long)row * ldc + col] += acc; }
-};
-
 // [R, C] (ld) -> [C, R] (ldo), 32 x 32 tiles
 static __global__ void tr_transpose_kernel(const float* __restrict__ src, int R, int C, int ld, float* __restrict__ dst, int ldo) {
     __shared__ float t[32][33];
