@@ -306,6 +306,42 @@ def test_precision_policy_knob(golden_dir, params0):
     assert errs[E.PRECISE_ALL_FP16] > errs[50]            # the fp16 format alone is NOT fp32-grade: the policy matters
 
 
+@pytest.mark.parametrize("B,T,inp", [(5, 120, 0), (3, 30, 10), (1, 120, 10)])
+def test_pair_steps_vs_all_split_engine(params0, monkeypatch, B, T, inp):
+    """Pair steps (fp16 activations x exact fp16 hi/lo weights: the fp16-format kernels with two passes over K) against the 3-term
+    split at every step, on one noise tape: N = 64 with precise_last_steps = 63 runs ONE single-pass step, 47 pair steps and 16 split
+    steps; EGOEGO_SPLIT_STEPS = 63 turns the 47 pair steps back into split steps.  Odd window counts (the rounding-up window of the
+    CTA-pair tiles), a short window and in-painting.  The two runs may differ by the fp16 rounding of the activations of 47
+    steps, each damped by ~1 / (t (t + 1)): well under 0.1 mm of joint position."""
+    import egoego_release_b200 as E
+    N = 64
+    xs = synth_x_start(29, B, T).cuda()
+    cm = O.prep_head_condition_mask(xs.shape).cuda()
+    tape = torch.stack([Tape(5).draw(xs.shape) for _ in range(N + 2)]).cuda()
+    outs = {}
+    for tag, env in (("pair", {}), ("split", {"EGOEGO_SPLIT_STEPS": "63"})):
+        monkeypatch.delenv("EGOEGO_SPLIT_STEPS", raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        m = E.CondGaussianDiffusion(d_feats=198, d_model=512, n_dec_layers=4, n_head=4, d_k=256, d_v=256, max_timesteps=121,
+                                    out_dim=198, timesteps=N, objective="pred_x0", max_batch=B, engine="tcgen05", precise_last_steps=63)
+        m.load_state_dict(params0, strict=False)
+        m = m.cuda()
+        assert f"split_steps={16 if tag == 'pair' else 63}" in m.engine_info(), m.engine_info()
+        m.set_noise_tape(tape)
+        if inp:
+            # the sliding-window sampler's in-painting of the first frames (p_sample_loop_sliding_window_w_canonical)
+            m.denoise_fn.eval()
+            outs[tag] = m.p_sample_loop(xs.shape, xs, cm, inpaint=xs[:, :inp].contiguous())
+        else:
+            outs[tag] = m.sample(xs, cm)
+        assert torch.isfinite(outs[tag]).all()
+    raw = maxabs(outs["pair"], outs["split"])
+    jerr = maxabs(joints(outs["pair"].cpu()), joints(outs["split"].cpu()))
+    print(f"pair steps vs split steps (B={B}, T={T}, inpaint={inp}): raw {raw:.2e}, joints {jerr * 1e3:.4f} mm")
+    assert jerr < 1e-4
+
+
 def test_full_size_policy_vs_fp32_engines(params0):
     """BASELINE configs[1] at FULL size and length (B = 256, T = 120, N = 1000, Philox noise): the default precision policy
     against (a) the same engine with every step in the 3-term split format, all 256 windows, and (b) the independent fp32
