@@ -231,12 +231,18 @@ struct TcEpiStart : EpiNoDirect {         // H = x-half GEMM + base ; row 0 = ti
     float* H; __nv_bfloat16* Hhi; __nv_bfloat16* Hlo; int ld;
     const float* base; const float* pos; const float* temb; TSrc ts; int T; int n_windows;
     __device__ __forceinline__ float4 bias4(int) const { return make_float4(0.f, 0.f, 0.f, 0.f); }
-    __device__ __forceinline__ float4 pre(int row, int col) const { return ld4(base + (long long)row * ld + col); }
+    // the per-element operand, fetched one chunk ahead: `base` for frame rows, the time token (timestep embedding + positional row 1)
+    // for row 0 of a window -- its dependent loads (step counter -> table row) then sit in the prefetch, not in the drain
+    __device__ __forceinline__ float4 pre(int row, int col) const {
+        const int w = row / LP;
+        if (row % LP == 0 && w < n_windows) return add4(ld4(temb + (long long)ts.get(w) * ld + col), ld4(pos + ld + col));
+        return ld4(base + (long long)row * ld + col);
+    }
     __device__ __forceinline__ void apply4(int row, int col, float4 a, float4, float4 bv) const {
         const int w = row / LP;
         const int l = (w < n_windows) ? row % LP : LP;      // rows of the rounding-up window are padding
         float4 r;
-        if (l == 0)      r = add4(ld4(temb + (long long)ts.get(w) * ld + col), ld4(pos + ld + col));
+        if (l == 0)      r = bv;
         else if (l <= T) r = add4(a, bv);
         else             r = make_float4(0.f, 0.f, 0.f, 0.f);
         const long long o = (long long)row * ld + col;
