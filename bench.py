@@ -573,7 +573,8 @@ def main():
                   + (f"fp16 activations x fp16 hi/lo weight pair for {S_split}<=t<{K_prec}, " if S_split < K_prec else "")
                   + f"fp16 hi/lo 3-term split for t<{S_split} (fp32 accumulate)"
                   if K_prec < N else "fp16 hi/lo 3-term split (fp32 accumulate)") if eng == "tcgen05" else "f32",
-        "data": "synthetic", "config": dict(cfg, engine=eng, precise_last_steps=K_prec, split_steps=S_split, weight_sets=W_sets),
+        "data": "synthetic", "config": cfg,      # identical in both arms; the engine's own settings are a separate key
+        "engine_config": {"engine": eng, "precise_last_steps": K_prec, "split_steps": S_split, "weight_sets": W_sets},
         "e2e": {"value": e2e, "unit": "windows/s", "h2d_bytes_per_step": 2 * B * T * D * 4 * world, "d2h_bytes_per_step": B * T * D * 4 * world},
         "gpu_launches": int(launches), "clocks": clocks, "shard_check": shard_check, "engine_info": m.engine_info(),
         "path_roofline": {"bound": "tensor", "achieved": path_tflops, "peak": peak, "unit": "TFLOP/s", "frac": path_tflops / peak,
