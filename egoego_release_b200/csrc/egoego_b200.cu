@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <set>
 #include <type_traits>
 
 #include "common.cuh"
@@ -931,6 +932,7 @@ struct TrainWs {
     struct GraphKey { int B, T, l2, pm, drop; uint32_t thresh; bool operator<(const GraphKey& o) const {
         return std::tie(B, T, l2, pm, drop, thresh) < std::tie(o.B, o.T, o.l2, o.pm, o.drop, o.thresh); } };
     std::map<GraphKey, cudaGraphExec_t> graphs;  // nullptr value: the key has run once eagerly (allocations, attributes) and is captured next time
+    std::set<GraphKey> no_graph;                 // shapes whose capture failed: eager from then on
 };
 
 static std::map<egoego_ctx*, std::unique_ptr<TrainWs>> g_train;
@@ -1026,6 +1028,7 @@ static int train_alloc(egoego_ctx* c, TrainWs* w, int B) {
     if (w->B >= B) return 0;
     for (auto& kv : w->graphs) if (kv.second) cudaGraphExecDestroy(kv.second);      // captured pointers die with the old workspace
     w->graphs.clear();
+    w->no_graph.clear();
     {
         const size_t xe = (size_t)B * (c->cfg.max_timesteps - 1) * c->D * 4;
         if (w->s_x.alloc(xe) || w->s_cm.alloc(xe) || w->s_noise.alloc(xe) || w->s_cn.alloc(xe) || w->s_pm.alloc((size_t)B * c->cfg.max_timesteps * 4) ||
@@ -1245,23 +1248,22 @@ int egoego_train_step(egoego_handle c, const float* x_start, const float* cond_m
     };
     const TrainWs::GraphKey key{B, T, loss_l2, pmask ? 1 : 0, drop.on, drop.thresh};
     auto it = w->graphs.find(key);
-    if (it == w->graphs.end()) {                   // first step of this shape: eager (plane caches, function attributes, scratch buffers)
-        if (body(s)) return 1;
-        w->graphs[key] = nullptr;
+    if (it == w->graphs.end() || w->no_graph.count(key)) {   // first step of this shape (plane caches, function attributes, scratch
+        if (body(s)) return 1;                               // buffers), or a shape whose capture failed once: eager launches
+        if (it == w->graphs.end()) w->graphs[key] = nullptr;
     } else {
-        if (!it->second) {                         // second step: capture
+        if (!it->second) {                         // second step: capture; if anything in it cannot be captured, stay eager for this shape
             cudaGraph_t g = nullptr;
-            EG_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-            const int rc = body(s);
-            const cudaError_t ce = cudaStreamEndCapture(s, &g);
-            EG_CHECK(rc == 0, std::string("training step capture failed: ") + g_err);
-            EG_CUDA(ce);
             cudaGraphExec_t ex = nullptr;
-            EG_CUDA(cudaGraphInstantiate(&ex, g, 0));
-            cudaGraphDestroy(g);
-            it->second = ex;
+            const cudaError_t cb = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+            const int rc = cb == cudaSuccess ? body(s) : 1;
+            const cudaError_t ce = cb == cudaSuccess ? cudaStreamEndCapture(s, &g) : cb;
+            if (rc == 0 && ce == cudaSuccess && g && cudaGraphInstantiate(&ex, g, 0) == cudaSuccess) it->second = ex;
+            else { cudaGetLastError(); w->no_graph.insert(key); }
+            if (g) cudaGraphDestroy(g);
         }
-        EG_CUDA(cudaGraphLaunch(it->second, s));
+        if (it->second) { EG_CUDA(cudaGraphLaunch(it->second, s)); }
+        else if (body(s)) return 1;
     }
     EG_CUDA(cudaEventRecord(c->ev_out, s));
     EG_CUDA(cudaStreamWaitEvent(user, c->ev_out, 0));
