@@ -507,6 +507,15 @@ __device__ __forceinline__ void ddpm_update_body(const DdpmArgs& a) {
     // float4 path: no tail quad and every window base 16-byte aligned (warp-uniform)
     const bool vec = (epw & 3) == 0 && (((uintptr_t)a.x | (uintptr_t)a.x_out | (uintptr_t)a.model_out) & 15) == 0;
     float nz[4], xv[4], mo[4];
+    // the two HBM reads first: the Philox rounds and the Box-Muller below (a ~400-cycle dependent chain) then run under their latency
+    // (SASS of the previous order: both LDG.128 were issued after the last MUFU)
+    if (vec) {
+        const float4 xq = *reinterpret_cast<const float4*>(a.x + i0), mq = *reinterpret_cast<const float4*>(a.model_out + i0);
+        xv[0] = xq.x; xv[1] = xq.y; xv[2] = xq.z; xv[3] = xq.w; mo[0] = mq.x; mo[1] = mq.y; mo[2] = mq.z; mo[3] = mq.w;
+    } else {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { const bool ok = e0 + r < epw; xv[r] = ok ? a.x[i0 + r] : 0.f; mo[r] = ok ? a.model_out[i0 + r] : 0.f; }
+    }
     const int draw = a.ns.draw();
     if (a.ns.tape) {
         const float* tp = a.ns.tape + (long long)draw * a.ns.draw_stride + i0;
@@ -518,13 +527,6 @@ __device__ __forceinline__ void ddpm_update_body(const DdpmArgs& a) {
     } else {
         float4 n = philox_normal4(a.ns.seed, a.ns.window_offset + w, (uint32_t)draw, (uint32_t)(e0 >> 2));
         nz[0] = n.x; nz[1] = n.y; nz[2] = n.z; nz[3] = n.w;
-    }
-    if (vec) {
-        const float4 xq = *reinterpret_cast<const float4*>(a.x + i0), mq = *reinterpret_cast<const float4*>(a.model_out + i0);
-        xv[0] = xq.x; xv[1] = xq.y; xv[2] = xq.z; xv[3] = xq.w; mo[0] = mq.x; mo[1] = mq.y; mo[2] = mq.z; mo[3] = mq.w;
-    } else {
-#pragma unroll
-        for (int r = 0; r < 4; ++r) { const bool ok = e0 + r < epw; xv[r] = ok ? a.x[i0 + r] : 0.f; mo[r] = ok ? a.model_out[i0 + r] : 0.f; }
     }
     float v[4];
 #pragma unroll
