@@ -731,9 +731,7 @@ class _TrainStepFn(torch.autograd.Function):
         flat.mul_(gout)
         sync = getattr(model, "_grad_sync", None)
         if sync is not None:                      # set_grad_sync(): one all-reduce of the whole gradient set, averaged like DDP
-            import torch.distributed as dist
-            if dist.is_available() and dist.is_initialized() and dist.get_world_size(sync[0]) > 1:
-                dist.all_reduce(flat, group=sync[0])
-                flat.div_(dist.get_world_size(sync[0]))
+            from .parallel import average_flat_gradients
+            average_flat_gradients(flat, sync[0])
         grads = [flat[offs[i]:offs[i + 1]].view(ctx.shapes[i]) for i in range(n)]
         return (None,) * 8 + tuple(grads)

@@ -80,3 +80,17 @@ def smpl_post_fn(model, ds, recover_rot_quat=None) -> Callable[[torch.Tensor, in
 def unpack_smpl(packed: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     """[B, T, 69] from ``smpl_post_fn`` -> (local_aa [B, T, 22, 3], root_trans [B, T, 3])."""
     return packed[..., :66].reshape(packed.shape[0], packed.shape[1], 22, 3), packed[..., 66:]
+
+
+def average_flat_gradients(flat: torch.Tensor, group=None) -> torch.Tensor:
+    """Data-parallel training without a DDP wrapper (CondGaussianDiffusion.set_grad_sync): ONE all-reduce of the flat buffer that
+    holds every gradient of the step, divided by the group size (DDP's mean).  No-op outside an initialised process group or in a
+    group of one.  In place; returns ``flat``."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return flat
+    world = dist.get_world_size(group)
+    if world > 1:
+        dist.all_reduce(flat, group=group)
+        flat.div_(world)
+    return flat
+

@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from egoego_release_b200.parallel import sample_sharded, shard_range
+from egoego_release_b200.parallel import average_flat_gradients, sample_sharded, shard_range
 
 
 def _fake_sample(xs, cm, offset):
@@ -69,3 +69,48 @@ def test_shard_range_partitions():
             assert spans[0][0] == 0 and sum(c for _, c in spans) == B
             for (s0, c0), (s1, _) in zip(spans, spans[1:]):
                 assert s0 + c0 == s1
+
+
+def _grad_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    flat = torch.arange(10, dtype=torch.float32) * (rank + 1)          # what the CUDA backward would leave in the flat buffer
+    out = average_flat_gradients(flat)
+    assert out is flat
+    if rank == 0:
+        q.put(flat.clone())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_average_over_ranks():
+    """set_grad_sync's reduction (one all-reduce of the flat gradient buffer, mean over ranks) with two gloo processes; outside a
+    process group it leaves the buffer untouched."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=180)
+        assert p.exitcode == 0
+    assert torch.equal(got, torch.arange(10, dtype=torch.float32) * 1.5)
+    alone = torch.ones(4)
+    assert torch.equal(average_flat_gradients(alone), torch.ones(4))
+
+
+def test_grad_sync_switches():
+    """set_grad_sync / no_grad_sync on the mirror (pure host state; the reduction itself is average_flat_gradients)."""
+    import egoego_release_b200 as E
+    m = E.CondGaussianDiffusion(d_feats=198, d_model=512, n_dec_layers=4, n_head=4, d_k=256, d_v=256, max_timesteps=121,
+                                out_dim=198, timesteps=10, objective="pred_x0")
+    assert getattr(m, "_grad_sync", None) is None
+    m.set_grad_sync()
+    assert m._grad_sync == (None, True)
+    with m.no_grad_sync():
+        assert m._grad_sync is None
+    assert m._grad_sync == (None, True)
+    m.set_grad_sync(enabled=False)
+    assert m._grad_sync is None
