@@ -172,6 +172,25 @@ def test_postprocess_vs_golden(golden_dir, params0):
     assert (R.quaternion_to_matrix(q_ref) - R.quaternion_to_matrix(q_got)).abs().max() < 2e-5
 
 
+def test_fk_smpl_kernel_vs_reference_function_body(golden_dir, params0):
+    """fk_smpl_kernel (egoego_fk_smpl through the mirror / MotionDataStub.fk_smpl) against the output of the reference's OWN
+    AMASSDataset.fk_smpl body (tests/golden/fk_ref.npz, oracle/gen_golden_fk.py): joint positions in metres and global rotations,
+    incl. an identity rotation, an angle 1e-3 below pi and a single frame."""
+    import egoego_release_b200 as E
+    from oracle.gen_golden_fk import CASES, fk_inputs
+    g = _g(golden_dir, "fk_ref.npz")
+    m = make_model(50, "simt", params0)
+    ds = E.MotionDataStub().bind(m)
+    for seed, n in CASES:
+        aa, root, _, _ = fk_inputs(seed, n)
+        gq, gj = ds.fk_smpl(root.cuda(), aa.cuda())
+        k = f"s{seed}_n{n}"
+        ej = float(np.abs(gj.cpu().numpy() - g[k + "_fk_jpos"]).max())
+        er = float((R.quaternion_to_matrix(gq.cpu()) - R.quaternion_to_matrix(torch.from_numpy(g[k + "_fk_quat"]))).abs().max())
+        print(f"fk_smpl kernel vs reference body (seed {seed}, {n} frames): joints {ej * 1e3:.5f} mm, rotation matrices {er:.2e}")
+        assert ej < 2e-5 and er < 2e-5
+
+
 @pytest.mark.parametrize("engine", ENGINES)
 def test_sliding_window_vs_golden(engine, golden_dir, params0):
     import egoego_release_b200 as E
