@@ -258,7 +258,13 @@ int64_t egoego_resnet18_launch_count(egoego_resnet h);
  * x_start / cond_mask / noise / cond_noise [B,T,d_feats], padding_mask float [B,T+1] or NULL, t int64 [B],
  * sqrt_ac = sqrt_alphas_cumprod[t], sqrt_1mac = sqrt_one_minus_alphas_cumprod[t], weight = p2_loss_weight[t] (each float [B]).
  * loss_out_dev[1] receives the scalar loss; gradients stay in the handle until the next call and are read with
- * egoego_train_get_grad(name = reference state_dict key, dst_dev[numel] in the reference's layout). */
+ * egoego_train_get_grad(name = reference state_dict key, dst_dev[numel] in the reference's layout).
+ * Execution: the inputs are copied into the handle's staging buffers on `stream`; the ~340 launches of the step run on the handle's
+ * own stream (ordered after / before `stream` by events) -- eagerly for the first step of a (B, T, loss, mask, dropout) shape, as ONE
+ * captured CUDA graph from the second step on (a shape whose capture fails stays eager).  The input tensors may therefore be freed or
+ * overwritten as soon as the call returns.  Environment: EGOEGO_TRAIN_GRAPH=0 (always eager), EGOEGO_TRAIN_SPLITK=0 (weight gradients
+ * as deterministic single-pass products instead of split-K partial products added with atomics), EGOEGO_TRAIN_FUSE_EPI=0 (element-wise
+ * epilogues as separate passes), EGOEGO_TRAIN_GEMM=simt (fp32 CUDA-core products). */
 int  egoego_train_step(egoego_handle h, const float* x_start_dev, const float* cond_mask_dev, const float* padding_mask_dev,
                        const int64_t* t_dev, const float* noise_dev, const float* cond_noise_dev, const float* sqrt_ac_dev,
                        const float* sqrt_1mac_dev, const float* weight_dev, int loss_l2, int B, int T, float* loss_out_dev, void* stream);
