@@ -263,7 +263,8 @@ int64_t egoego_resnet18_launch_count(egoego_resnet h);
  * own stream (ordered after / before `stream` by events) -- eagerly for the first step of a (B, T, loss, mask, dropout) shape, as ONE
  * captured CUDA graph from the second step on (a shape whose capture fails stays eager).  The input tensors may therefore be freed or
  * overwritten as soon as the call returns.  Environment: EGOEGO_TRAIN_GRAPH=0 (always eager), EGOEGO_TRAIN_SPLITK=0 (weight gradients
- * as deterministic single-pass products instead of split-K partial products added with atomics), EGOEGO_TRAIN_FUSE_EPI=0 (element-wise
+ * as single-pass products instead of split-K partial products added with atomics; the time-MLP gradients and the loss use atomics
+ * either way: results vary by ~1e-7 relative run to run), EGOEGO_TRAIN_FUSE_EPI=0 (element-wise
  * epilogues as separate passes), EGOEGO_TRAIN_GEMM=simt (fp32 CUDA-core products). */
 int  egoego_train_step(egoego_handle h, const float* x_start_dev, const float* cond_mask_dev, const float* padding_mask_dev,
                        const int64_t* t_dev, const float* noise_dev, const float* cond_noise_dev, const float* sqrt_ac_dev,
